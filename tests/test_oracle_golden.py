@@ -173,7 +173,7 @@ def test_train_step_matches_reference(golden_dir, tag, netG):
                 # post-Adam weights (strided subsample).  First step with beta1=0 moves every weight
                 # by ~lr*sign(g); skip the pure-noise-gradient biases and near-zero-gradient elements.
                 g = z[gk].reshape(-1)[::7]
-                ok = np.abs(g) > 1e-6
+                ok = np.abs(g) > max(1e-6, 0.05 * float(np.sqrt(np.mean(z[gk] ** 2))))
                 wk = "%s_grad.%s" % (net, k.replace(".bias", ".weight"))
                 if k.endswith(".bias") and wk in z and np.linalg.norm(z[gk]) < 1e-3 * np.linalg.norm(z[wk]):
                     continue
