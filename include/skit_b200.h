@@ -1,0 +1,216 @@
+/* skit_b200 — C-ABI of the B200-native skitG/sinskitG hot path.
+ *
+ * The reference (RuihanGao/visual-tactile-synthesis) is pure PyTorch: its "FFI" for this path
+ * is ATen (F.conv2d, F.instance_norm, F.batch_norm, advanced indexing, Adam ...).  Every entry
+ * point below names the reference call site (file:line under /root/reference) it replaces.
+ * All pointers are DEVICE pointers unless stated otherwise; `stream` is a cudaStream_t passed as
+ * void*.  Every function returns SKIT_OK (0) or a negative error code; skit_last_error() returns
+ * the message of the last failure on the calling thread.  No function synchronises the device.
+ *
+ * Device data layout:
+ *   feature maps ......... NHWC fp32 ("raw" conv outputs, residual stream, gradients)
+ *   conv operands ........ NHWC with an explicit halo, either fp32 (SKIT_FMT_F32) or two bf16
+ *                          planes hi/lo with hi+lo ~= x (SKIT_FMT_BF16X2) for the tcgen05 path
+ *   images / patches ..... NCHW fp32 planar, exactly the reference's tensors
+ *   parameters ........... reference layout ([Co][Ci][kh][kw] fp32), repacked per step
+ */
+#ifndef SKIT_B200_H
+#define SKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKIT_OK 0
+#define SKIT_ERR_INVALID (-1)
+#define SKIT_ERR_CUDA (-2)
+#define SKIT_ERR_UNSUPPORTED (-3)
+
+#define SKIT_FMT_F32 0
+#define SKIT_FMT_BF16X2 1
+
+#define SKIT_PAD_ZERO 0
+#define SKIT_PAD_REFLECT 1
+#define SKIT_PAD_REPLICATE 2
+
+#define SKIT_ACT_NONE 0
+#define SKIT_ACT_RELU 1
+#define SKIT_ACT_LRELU 2 /* negative slope 0.2 (networks.py:1712, unet_parts_custom.py:23) */
+
+#define SKIT_NORM_NONE 0
+#define SKIT_NORM_INSTANCE 1 /* statistics per (n, c) */
+#define SKIT_NORM_BATCH 2    /* statistics per c over (n, h, w) */
+
+#define SKIT_IMPL_AUTO 0
+#define SKIT_IMPL_SIMT 1
+#define SKIT_IMPL_TC 2 /* tcgen05 + TMA; fails with SKIT_ERR_UNSUPPORTED if the shape is not eligible */
+
+/* A conv operand: NHWC tensor [n][hp][wp][c] that already contains its halo. */
+typedef struct skit_operand {
+    void* p0;  /* F32: float*;  BF16X2: bf16 hi plane */
+    void* p1;  /* BF16X2: bf16 lo plane; otherwise NULL */
+    int fmt;   /* SKIT_FMT_* */
+    int n, hp, wp, c;
+} skit_operand;
+
+/* Packed conv weights produced by skit_pack_conv_weights. */
+typedef struct skit_weights {
+    const float* f32; /* [k*k*ci][co]  (SIMT path)           */
+    const void* hi;   /* bf16 [k*k][co][ci] (tcgen05 path)   */
+    const void* lo;   /* bf16 [k*k][co][ci]                  */
+    int k, ci, co;
+} skit_weights;
+
+const char* skit_last_error(void);
+/* Library/ABI version and the compute capability the kernels were built for (100 = sm_100a). */
+int skit_version(void);
+int skit_built_arch(void);
+
+/* ---------------------------------------------------------------- weights
+ * Repack a reference-layout conv weight [co][ci][k][k] (nn.Conv2d.weight, networks.py:1078 etc.).
+ * mode 0: forward pack        Wf[(ky*k+kx)*ci + c][o]      = w[o][c][ky][kx]
+ * mode 1: stride-1 dgrad pack Wd[((k-1-ky)*k+(k-1-kx))*co + o][c] = w[o][c][ky][kx]
+ *         (conv of the zero-padded output gradient with the flipped, transposed filter)
+ * mode 2: gather dgrad pack   Wg[(ky*k+kx)*co + o][c]      = w[o][c][ky][kx]
+ * f32 / hi / lo may each be NULL to skip that product.  hi/lo are [tap][N][K] K-major bf16.  */
+int skit_pack_conv_weights(const float* w, int co, int ci, int k, int mode,
+                           float* f32, void* hi, void* lo, void* stream);
+/* Inverse of the forward pack for gradients: dWf [(tap*ci+c)][o] fp32 -> dw[o][c][ky][kx] (+= if accumulate). */
+int skit_unpack_conv_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- convolution
+ * Replaces F.conv2d / nn.Conv2d.forward (networks.py:1078,1090,1281-1310,1124,1706-1727) as a
+ * VALID convolution over an operand that already carries its halo:
+ *   y[n][oy][ox][o] = bias[o] + sum_{ky,kx,c} x[n][org+oy*stride+ky][org+ox*stride+kx][c] * W[ky][kx][c][o]
+ * y is NHWC fp32 [n][ho][wo][co].  If stats != NULL, accumulates sum and sum-of-squares of y
+ * (double, [groups][co][2]; groups = n for SKIT_NORM_INSTANCE, 1 for SKIT_NORM_BATCH) — the
+ * InstanceNorm/BatchNorm statistics, fused into the conv epilogue.  stats must be zeroed by the caller. */
+int skit_conv2d_fwd(const skit_operand* x, const skit_weights* w, int stride, int org,
+                    int ho, int wo, const float* bias, float* y,
+                    double* stats, int stats_mode, int impl, void* stream);
+
+/* Input gradient of the conv above for any stride (autograd of F.conv2d), gather form:
+ *   dx[n][iy][ix][c] = sum_{ky,kx,o : (iy-ky)%s==0, (ix-kx)%s==0} dy[n][(iy-ky)/s][(ix-kx)/s][o] * w[o][c][ky][kx]
+ * dy: NHWC fp32 [n][ho][wo][co] (no halo); wg: mode-2 pack (f32); dx: NHWC fp32 [n][hp][wp][ci]
+ * (gradient w.r.t. the padded operand).  SIMT kernel; stride-1 layers use skit_conv2d_fwd with a
+ * mode-1 pack on the tensor-core path instead. */
+int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, int co,
+                             const skit_weights* wg, int stride, int hp, int wp, float* dx, void* stream);
+
+/* Weight gradient: dWf[(tap*ci+c)][o] += sum_{n,oy,ox} dy[n][oy][ox][o] * x[n][org+oy*s+ky][org+ox*s+kx][c]
+ * dy is an operand (fp32 or bf16x2) read with halo offset dy_org; dWf fp32 (forward-pack layout),
+ * must be zeroed by the caller (split-K accumulation with atomics).  dbias (may be NULL): [co] += sum dy. */
+int skit_conv2d_wgrad(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
+                      int k, int stride, int ho, int wo, float* dwf, float* dbias, int impl, void* stream);
+
+/* ---------------------------------------------------------------- normalisation + activation + halo
+ * Turn double (sum, sumsq) into float (mean, rstd), eps 1e-5, biased variance
+ * (nn.InstanceNorm2d networks.py:138-139; nn.BatchNorm2d training mode networks.py:1714-1723).
+ * For BatchNorm also updates running_mean / running_var (momentum, unbiased var) when non-NULL. */
+int skit_stats_finalize(const double* stats, int groups, int c, double count, float eps,
+                        float* mean_rstd, float* running_mean, float* running_var, float momentum, void* stream);
+
+/* y = act(norm(raw) * gamma + beta) [+ residual]  →  optional dense copy `out` (NHWC fp32) and/or a
+ * haloed operand `op` (pad, pad_mode, fmt).  Fuses InstanceNorm/BatchNorm-apply, ReLU/LeakyReLU,
+ * the ResnetBlock skip add (networks.py:1322), ReflectionPad2d / zero padding and the bf16 hi/lo
+ * split for the tensor-core conv that follows.  mean_rstd: [groups][c][2] or NULL (norm none). */
+int skit_norm_act_pad(const float* raw, int n, int h, int w, int c,
+                      const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                      int act, const float* residual, float* out,
+                      const skit_operand* op, int pad, int pad_mode, void* stream);
+
+/* Backward, phase A: fold the halo gradient back (adjoint of the padding), add an optional dense
+ * gradient, apply act', and reduce the two norm-backward sums.
+ *   g = act'(pre) * ( fold(dpad) + dadd ),  pre = norm(raw)*gamma+beta
+ *   sums[group][c][0] += sum g ; sums[group][c][1] += sum g * xhat        (double)
+ * dpad: NHWC fp32 [n][h+2pad][w+2pad][c] or NULL; dadd: NHWC fp32 [n][h][w][c] or NULL. */
+int skit_act_norm_bwd_reduce(const float* dpad, int pad, int pad_mode, const float* dadd,
+                             const float* raw, int n, int h, int w, int c,
+                             const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                             int act, float* g, double* sums, void* stream);
+
+/* Backward, phase B: d_raw = gamma*rstd*( g - S0/count - xhat*S1/count )  (norm none: d_raw = g),
+ * written as a zero-haloed operand (pad q) in fmt, ready for dgrad/wgrad.
+ * For BatchNorm, dgamma[c] += S1, dbeta[c] += S0 when non-NULL. */
+int skit_norm_bwd_apply(const float* g, const float* raw, int n, int h, int w, int c,
+                        const float* mean_rstd, int norm_mode, const float* gamma,
+                        const double* sums, double count, float* dgamma, float* dbeta,
+                        const skit_operand* op, int pad, void* stream);
+
+/* Antialiased resamplers (networks.py:51-74 Downsample, :87-107 Upsample), NHWC fp32 dense.
+ * down: reflect pad 1, depthwise [1,2,1]^2/16, stride 2  ([h][w] -> [h/2][w/2], even h,w)
+ * up:   replicate pad 1, depthwise conv_transpose [1,3,3,1]^2*4/64 stride 2, cropped -> [2h][2w] */
+int skit_blur_down_fwd(const float* x, int n, int h, int w, int c, float* y, void* stream);
+int skit_blur_down_bwd(const float* dy, int n, int h, int w, int c, float* dx, void* stream);
+int skit_blur_up_fwd(const float* x, int n, int h, int w, int c, float* y, void* stream);
+int skit_blur_up_bwd(const float* dy, int n, int h, int w, int c, float* dx, void* stream);
+
+/* ---------------------------------------------------------------- image-level ops (NCHW fp32 planar)
+ * Concatenate up to 4 NCHW sources along channels into a haloed NHWC fp32 operand
+ * (torch.cat + ReflectionPad2d(3) at networks.py:1077 / zero padding 2 of the PatchGAN convs :1703). */
+int skit_nchw_cat_to_operand(const float* const* srcs, const int* chans, int nsrc,
+                             int n, int h, int w, const skit_operand* op, int pad, int pad_mode, void* stream);
+/* Adjoint for one channel slice: dst[n][cs][h][w] (+)= fold(dpad)[.., c0:c0+cs]. */
+int skit_operand_grad_to_nchw(const float* dpad, int n, int h, int w, int c, int pad, int pad_mode,
+                              int c0, int cs, float* dst, int accumulate, void* stream);
+
+/* Generator head: raw [n][h][w][5] (conv + bias) -> tanh -> *M -> fake_I [n][3][h][w], fake_T [n][2][h][w],
+ * fake_N = normalize([gx, gy, scale_nz]) (networks.py:1127; sinskitG_model.py:1309-1319; model_utils.py:418-425). */
+int skit_g_head_fwd(const float* raw, const float* mask, int n, int h, int w, float scale_nz,
+                    float* fake_I, float* fake_T, float* fake_N, void* stream);
+/* d_raw[n][h][w][5] = [dI, dT] * M * (1 - tanh(raw)^2), written as a zero-haloed fp32 operand (pad q). */
+int skit_g_head_bwd(const float* raw, const float* mask, const float* dI, const float* dT,
+                    int n, int h, int w, const skit_operand* op, int pad, void* stream);
+
+/* DiffAugment policy 'bs' followed by *M (thirdparty/DiffAugment.py:25-33; sinskitG_model.py:1330-1340).
+ * u_b, u_s: [n] device floats (the host's torch.rand draws). x: [n][3][h][w]. */
+int skit_diffaug_bs_mask(const float* x, const float* mask, const float* u_b, const float* u_s,
+                         int n, int h, int w, float* y, void* stream);
+
+/* AvgPool2d(3, stride 2, padding 1, count_include_pad=False) (networks.py:1670), NCHW planes. */
+int skit_avgpool3s2_fwd(const float* x, int planes, int h, int w, float* y, void* stream);
+int skit_avgpool3s2_bwd(const float* dy, int planes, int h, int w, float* dx, int accumulate, void* stream);
+
+/* Patch gather (get_patch_in_input, model_utils.py:254-335): for each of np patches and each source
+ * s, dst[p][coff_s + c][y][x] = src_s[0][c][clamp(oy[p]+y)][clamp(ox[p]+x)]; dst is NCHW
+ * [np][ctot][ps][ps].  ox/oy: int32 device arrays.  One launch covers all sources. */
+int skit_patch_gather(const float* const* srcs, const int* chans, const int* coffs, int nsrc,
+                      int h, int w, const int* ox, const int* oy, int np, int ps,
+                      float* dst, int ctot, void* stream);
+/* Adjoint: dsrc[0][c][clamp(..)][clamp(..)] += dpatch[p][coff + c][y][x]  (atomic scatter-add). */
+int skit_patch_scatter_add(const float* dpatch, int ctot, int coff, int cs, int h, int w,
+                           const int* ox, const int* oy, int np, int ps, float* dsrc, void* stream);
+
+/* GANLoss 'nonsaturating' on one scale (networks.py:500-522): loss[b] += mean_hw softplus(sign * pred[b]).
+ * sign = -1 for target_is_real, +1 for fake.  If dpred != NULL: dpred = gscale * sign * sigmoid(sign*pred)/(h*w). */
+int skit_gan_softplus(const float* pred, int n, int hw, float sign, float* loss, float* dpred, float gscale, void* stream);
+
+/* L1: loss[0] += scale * sum |a-b| ; if grad != NULL: grad (+)= gscale * sign(a-b)  (sinskitG_model.py:1702,1812). */
+int skit_l1_loss(const float* a, const float* b, long long numel, float scale, float* loss,
+                 float* grad, float gscale, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- optimiser
+ * torch.optim.Adam step on a flat fp32 bucket (sinskitG_model.py:590-599), optional grad scaling
+ * (1/world_size after the all-reduce). step >= 1. */
+int skit_adam_step(float* p, const float* g, float* m, float* v, long long numel, int step,
+                   float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------- PatchNCE
+ * PatchSampleF gather + Normalize (networks.py:689-719, 585-594): feat NHWC fp32 [b][hw][c];
+ * out[b*np + i][c] = f[b][ids[i]][c] / (||f||_2 + 1e-7).  `pre` (optional) keeps the un-normalised rows. */
+int skit_patch_sample_l2norm(const float* feat, int b, int hw, int c, const int* ids, int np,
+                             float* out, float* pre, void* stream);
+/* Backward of the normalisation + gather: dfeat[b][ids[i]][c] += d(pre) */
+int skit_patch_sample_l2norm_bwd(const float* dout, const float* pre, int b, int hw, int c,
+                                 const int* ids, int np, float* dfeat, void* stream);
+/* PatchNCELoss.forward (patchnce.py:13-55): q,k [b*np][dim]; loss[b*np]; optional dq (gradient of
+ * sum_i loss[i]*gscale w.r.t. q; k is detached in the reference). */
+int skit_patchnce(const float* q, const float* k, int b, int np, int dim, float inv_T,
+                  float* loss, float* dq, float gscale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKIT_B200_H */

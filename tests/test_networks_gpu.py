@@ -1,0 +1,166 @@
+"""GPU parity of the networks (define_G / define_D API and the explicit fwd/bwd) against
+(1) the golden fixtures generated from the real reference (tests/golden/networks.npz) and
+(2) the CPU oracle on the same seeded inputs.  Gate: 1e-3 relative L2 per output tensor
+(BASELINE.json north_star); observed values are ~1e-5, asserted at 2e-4."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GATE = 1e-3
+TIGHT = 2e-4
+
+
+@pytest.fixture(scope="module")
+def V():
+    import vts_b200
+    vts_b200._lib.load()
+    return vts_b200
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), torch.as_tensor(np.asarray(b)).double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def rand_input(seed, *shape):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(*shape, generator=g) * 2 - 1
+
+
+def load_sd(z, prefix):
+    return {k[len(prefix):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(prefix)}
+
+
+def opt_ns(**kw):
+    return argparse.Namespace(gan_mode="nonsaturating", **kw)
+
+
+def test_resnet_generator_matches_reference_golden(V, golden_dir):
+    """Weights, input and output all come from the real reference run (oracle/make_golden.py)."""
+    z = np.load(os.path.join(golden_dir, "networks.npz"))
+    sd = load_sd(z, "Gres.")
+    ngf = sd["model.1.weight"].shape[0]
+    G = V.define_G(9, 5, ngf, "resnet_9blocks", "instance", False, "xavier", 0.02, False, False, [], opt_ns()).cuda()
+    G.load_state_dict(sd)
+    x = rand_input(11, 1, 9, 48, 40).cuda()
+    y = G(x)
+    assert y.shape == (1, 5, 48, 40)
+    assert rel(y, z["Gres_out"]) < TIGHT
+    y2, feats = G(x, layers=[0, 4, 8, 12, 16])
+    assert rel(y2, z["Gres_out"]) < TIGHT
+    for i, f in enumerate(feats):
+        assert rel(f[..., ::2, ::2], z["Gres_feat%d" % i]) < TIGHT
+    enc = G(x, layers=[0, 4, 8], encode_only=True)
+    assert len(enc) == 3
+    with pytest.raises(NotImplementedError):
+        G(x, layers=[2])
+
+
+@pytest.mark.parametrize("hw,n,nb", [((32, 32), 1, 9), ((64, 48), 2, 4)])
+def test_resnet_generator_ngf64_tcgen05_fwd_bwd(V, hw, n, nb):
+    """The tensor-core configuration (ngf 64: every trunk conv on tcgen05) vs the CPU oracle:
+    forward outputs and every parameter gradient of sum(out * R)."""
+    from oracle import skit_oracle as O
+    torch.manual_seed(3)
+    G = V.define_G(9, 5, 64, "resnet_%dblocks" % nb, "instance", False, "xavier", 1.0, False, False, [], opt_ns())
+    sd = {k: v.clone() for k, v in G.state_dict().items()}
+    G = G.cuda()
+    G.ensure_flat()
+    G.refresh_packs()
+    x = rand_input(5, n, 9, *hw)
+    M = (rand_input(6, n, 1, *hw) > -0.8).float()
+    RI, RT = rand_input(7, n, 3, *hw), rand_input(8, n, 2, *hw)
+    # oracle
+    ps = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "filt" not in k}
+    run = dict(sd)
+    run.update(ps)
+    out = O.resnet_g_forward(run, x, n_blocks=nb)
+    fI, fT = out[:, :3] * M, out[:, 3:] * M
+    ((fI * RI).sum() + (fT * RT).sum()).backward()
+    # CUDA path
+    (kI, kT, kN), ctx, _ = G.fwd([x.cuda()], mask=M.cuda())
+    G.zero_grad()
+    G.bwd(ctx, RI.cuda(), RT.cuda())
+    torch.cuda.synchronize()
+    assert rel(kI, fI) < TIGHT and rel(kT, fT) < TIGHT
+    assert rel(kN, O.compute_normal(fT.detach(), 0.25)) < TIGHT
+    worst = 0.0
+    for k, p in G.named_parameters():
+        if k.endswith("bias") and not k.startswith("model.%d." % (12 + nb + 9)):
+            continue  # bias before InstanceNorm: gradient is exactly zero in exact arithmetic
+        r = rel(p.grad, ps[k].grad)
+        worst = max(worst, r)
+        assert r < GATE, (k, r)
+    print("worst grad rel err", worst)
+
+
+def test_multiscale_discriminator_matches_reference_golden(V, golden_dir):
+    z = np.load(os.path.join(golden_dir, "networks.npz"))
+    sd = load_sd(z, "D_before.")
+    ndf = sd["layer0.0.weight"].shape[0]
+    cin = sd["layer0.0.weight"].shape[1]
+    D = V.define_D(cin, ndf, "multiscale", 3, "batch", "xavier", 0.02, False, 3, [], opt_ns()).cuda()
+    D.load_state_dict(sd)
+    D.train()
+    x = rand_input(14, 6, 7, 32, 32).cuda()
+    pred = D(x)
+    for i, p in enumerate(pred):
+        assert rel(p[-1], z["D_pred%d" % i]) < TIGHT
+    crit = V.GANLoss("nonsaturating").cuda()
+    assert rel(crit(pred, False), z["D_loss_fake"]) < TIGHT
+    assert rel(crit(pred, True), z["D_loss_real"]) < TIGHT
+    assert rel(crit(pred[0][-1], True), z["D_loss_tensor_real"]) < TIGHT
+    after = load_sd(z, "D_after.")  # BN running stats after one training-mode forward
+    for k, v in D.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert rel(v, after[k]) < TIGHT, k
+        else:
+            assert int(v) == int(after[k]), k
+    sdb = load_sd(z, "Dbasic.")
+    Db = V.define_D(4, sdb["model.0.weight"].shape[0], "basic", 3, "batch", "xavier", 0.02, False, 3, [], None).cuda()
+    Db.load_state_dict(sdb)
+    assert rel(Db(rand_input(15, 1, 4, 70, 58).cuda()), z["Dbasic_pred"]) < TIGHT
+
+
+@pytest.mark.parametrize("ndf,hw,n", [(8, (40, 36), 2), (64, (32, 32), 4)])
+def test_multiscale_discriminator_backward(V, ndf, hw, n):
+    """Explicit backward of the 3-scale PatchGAN (BN batch stats, avg-pool pyramid, softplus GAN loss):
+    parameter gradients and the gradient w.r.t. a channel slice of the input vs autograd on the oracle."""
+    from oracle import skit_oracle as O
+    torch.manual_seed(4)
+    D = V.define_D(4, ndf, "multiscale", 3, "batch", "xavier", 1.0, False, 3, [], opt_ns())
+    sd = {k: v.clone() for k, v in D.state_dict().items()}
+    D = D.cuda()
+    D.ensure_flat()
+    D.refresh_packs()
+    S = rand_input(1, n, 1, *hw)
+    I = rand_input(2, n, 3, *hw).requires_grad_(True)
+    ps = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
+    run = dict(sd)
+    run.update(ps)
+    pred = O.multiscale_d_forward(run, torch.cat([S, I], 1))
+    loss = O.gan_loss(pred, True).mean() * 0.5
+    loss.backward()
+    # CUDA
+    preds, ctx = D.fwd([S.cuda(), I.detach().cuda()])
+    lossk = torch.zeros(n, device="cuda")
+    dps = []
+    for p in preds:
+        dp = torch.empty_like(p)
+        V.ops.gan_softplus(p, -1.0, lossk, dp, 0.5 / n)
+        dps.append(dp)
+    D.zero_grad()
+    dI = D.bwd(ctx, dps, need_wgrad=True, input_slice=(1, 3))
+    torch.cuda.synchronize()
+    assert abs(lossk.mean().item() * 0.5 - loss.item()) < 1e-5 * max(1, abs(loss.item()))
+    assert rel(dI, I.grad) < GATE
+    for k, p in D.named_parameters():
+        is_bias_before_bn = k.endswith("bias") and k.split(".")[1] in ("2", "5", "8")
+        if is_bias_before_bn:
+            continue
+        assert rel(p.grad, ps[k].grad) < GATE, k

@@ -1,0 +1,18 @@
+"""visual-tactile-synthesis_b200 — B200-native (sm_100a) skitG / sinskitG hot path.
+
+Import as `vts_b200` (the directory name is not a valid Python identifier; `vts_b200.py` at the
+repo root registers this package under that name).  Layout:
+
+  csrc/         CUDA kernels + the C ABI (include/skit_b200.h) -> csrc/libskit_b200.so
+  _lib.py       ctypes binding (fails loudly when the library is missing)
+  ops.py        tensor-level wrappers, one per C entry point
+  networks.py   define_G / define_D / define_F / GANLoss / PatchSampleF  (reference: models/networks.py)
+  patchnce.py   PatchNCELoss                                             (reference: models/patchnce.py)
+  model_utils.py get_patch_in_input / find_coords_for_patch / compute_normal (reference: models/model_utils.py)
+  skit_model.py SinSKITGModel / SKITGModel train step + forward           (reference: models/{sinskitG,skitG}_model.py)
+  dist.py       one-process-per-GPU data parallel: flat gradient buckets + NCCL all-reduce
+"""
+from . import _lib, ops, networks  # noqa: F401
+from .networks import define_D, define_F, define_G, GANLoss, PatchSampleF  # noqa: F401
+
+__all__ = ["define_G", "define_D", "define_F", "GANLoss", "PatchSampleF", "ops", "networks"]

@@ -1,0 +1,529 @@
+// NHWC feature-map kernels between convolutions: statistics finalise, normalise + activation +
+// residual + halo + bf16 split (forward), the two-phase norm/activation backward, and the
+// antialiased blur resamplers with their adjoints.  All are HBM/L2-bandwidth bound: float4
+// accesses along the channel axis, grid-stride loops sized in multiples of the SM count.
+#include "skit_common.cuh"
+
+namespace skit {
+
+constexpr int kSMs = 148;
+
+static inline int grid_for(long long work, int threads, int max_per_sm = 8) {
+    long long b = cdivll(work, threads);
+    long long cap = (long long)kSMs * max_per_sm;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ------------------------------------------------------------------------------ stats finalise
+__global__ void stats_finalize_kernel(const double* stats, int groups, int c, double count, float eps,
+                                      float* mean_rstd, float* rmean, float* rvar, float momentum) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= groups * c) return;
+    double mean = stats[2 * i] / count;
+    double var = stats[2 * i + 1] / count - mean * mean;
+    if (var < 0) var = 0;
+    mean_rstd[2 * i] = (float)mean;
+    mean_rstd[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean && i < c) {
+        double unb = count > 1 ? var * count / (count - 1) : var;
+        rmean[i] = (1.f - momentum) * rmean[i] + momentum * (float)mean;
+        rvar[i] = (1.f - momentum) * rvar[i] + momentum * (float)unb;
+    }
+}
+
+// ------------------------------------------------------------------------------ forward prep
+struct PrepP {
+    const float* raw; int n, h, w, c;
+    const float* mr; int per_n;      // mean/rstd, indexed by n (instance) or 0 (batch); NULL = no norm
+    const float* gamma; const float* beta;
+    int act;
+    const float* residual;
+    float* out;                      // dense [n][h][w][c] or NULL
+    float* o0; __nv_bfloat16* oh; __nv_bfloat16* ol; int fmt;  // operand planes or NULL
+    int pad, pad_mode;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) norm_act_pad_kernel(PrepP p) {
+    const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
+    const int cv = p.c / VEC;
+    const long long total = (long long)p.n * hp * wp * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % cv) * VEC;
+        long long t = i / cv;
+        const int px = (int)(t % wp); t /= wp;
+        const int py = (int)(t % hp);
+        const int n = (int)(t / hp);
+        const int sy = pad_src(py, p.pad, p.h, p.pad_mode), sx = pad_src(px, p.pad, p.w, p.pad_mode);
+        float v[VEC];
+        if (sy < 0 || sx < 0) {
+#pragma unroll
+            for (int j = 0; j < VEC; j++) v[j] = 0.f;
+        } else {
+            const long long src = (((long long)n * p.h + sy) * p.w + sx) * p.c + ch;
+            if (VEC == 4) {
+                float4 r = *reinterpret_cast<const float4*>(p.raw + src);
+                v[0] = r.x; v[1 % VEC] = r.y; v[2 % VEC] = r.z; v[3 % VEC] = r.w;
+            } else {
+                v[0] = p.raw[src];
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; j++) {
+                float x = v[j];
+                if (p.mr) {
+                    const float* mr = p.mr + ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
+                    x = (x - mr[0]) * mr[1];
+                }
+                if (p.gamma) x = x * p.gamma[ch + j] + p.beta[ch + j];
+                x = act_fwd(x, p.act);
+                if (p.residual) x += p.residual[src + j];
+                v[j] = x;
+            }
+            if (p.out && py - p.pad == sy && px - p.pad == sx) {
+                if (VEC == 4) *reinterpret_cast<float4*>(p.out + src) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+                else p.out[src] = v[0];
+            }
+        }
+        const long long dst = (((long long)n * hp + py) * wp + px) * p.c + ch;
+        if (p.o0 && p.fmt == SKIT_FMT_F32) {
+            if (VEC == 4) *reinterpret_cast<float4*>(p.o0 + dst) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+            else p.o0[dst] = v[0];
+        } else if (p.oh) {
+            __nv_bfloat16 hi[VEC], lo[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; j++) split_bf16(v[j], hi[j], lo[j]);
+            if (VEC == 4) {
+                *reinterpret_cast<uint2*>(p.oh + dst) = *reinterpret_cast<uint2*>(hi);
+                *reinterpret_cast<uint2*>(p.ol + dst) = *reinterpret_cast<uint2*>(lo);
+            } else {
+                p.oh[dst] = hi[0]; p.ol[dst] = lo[0];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ backward phase A
+struct BwdAP {
+    const float* dpad; int pad, pad_mode;
+    const float* dadd;
+    const float* raw; int n, h, w, c;
+    const float* mr; int per_n;
+    const float* gamma; const float* beta;
+    int act;
+    float* g;
+    double* sums;
+    int chunk;  // pixels per block
+};
+
+// number of halo positions that alias source coordinate y on an axis of length len (reflect): returns
+// their padded coordinates in out[], count as return value (always includes the interior one).
+__device__ inline int fold_coords(int y, int pad, int len, int mode, int out[3]) {
+    int cnt = 0;
+    out[cnt++] = y + pad;
+    if (mode == SKIT_PAD_REFLECT) {
+        if (y >= 1 && y <= pad) out[cnt++] = pad - y;
+        if (y <= len - 2 && y >= len - 1 - pad) out[cnt++] = pad + 2 * (len - 1) - y;
+    }
+    return cnt;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) act_norm_bwd_reduce_kernel(BwdAP p) {
+    __shared__ float red[256 * 2 * VEC];
+    const int n = blockIdx.y;
+    const int cv = p.c / VEC;
+    const int lanes_c = cv < 256 ? cv : 256;
+    const int PL = 256 / lanes_c;
+    const int cl = threadIdx.x % lanes_c, pl = threadIdx.x / lanes_c;
+    const int P = p.h * p.w;
+    const int pbeg = blockIdx.x * p.chunk, pend = min(P, pbeg + p.chunk);
+    const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
+    for (int t = threadIdx.x; t < 256 * 2 * VEC; t += 256) red[t] = 0.f;
+    __syncthreads();
+    if (pl < PL) {
+        for (int cvv = cl; cvv < cv; cvv += lanes_c) {
+            const int ch = cvv * VEC;
+            float mean[VEC], rstd[VEC], gam[VEC], bet[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; j++) {
+                mean[j] = 0.f; rstd[j] = 1.f; gam[j] = 1.f; bet[j] = 0.f;
+                if (p.mr) {
+                    const float* mr = p.mr + ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
+                    mean[j] = mr[0]; rstd[j] = mr[1];
+                }
+                if (p.gamma) { gam[j] = p.gamma[ch + j]; bet[j] = p.beta[ch + j]; }
+            }
+            float s0[VEC], s1[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; j++) { s0[j] = 0.f; s1[j] = 0.f; }
+            for (int pix = pbeg + pl; pix < pend; pix += PL) {
+                const int y = pix / p.w, x = pix - y * p.w;
+                const long long src = (((long long)n * p.h + y) * p.w + x) * p.c + ch;
+                float d[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; j++) d[j] = p.dadd ? p.dadd[src + j] : 0.f;
+                if (p.dpad) {
+                    int ys[3], xs[3];
+                    const int ny = fold_coords(y, p.pad, p.h, p.pad_mode, ys);
+                    const int nx = fold_coords(x, p.pad, p.w, p.pad_mode, xs);
+                    for (int a = 0; a < ny; a++)
+                        for (int b = 0; b < nx; b++) {
+                            const long long q = (((long long)n * hp + ys[a]) * wp + xs[b]) * p.c + ch;
+#pragma unroll
+                            for (int j = 0; j < VEC; j++) d[j] += p.dpad[q + j];
+                        }
+                }
+                float gout[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; j++) {
+                    const float xhat = ((p.raw ? p.raw[src + j] : 0.f) - mean[j]) * rstd[j];
+                    const float pre = xhat * gam[j] + bet[j];
+                    const float gg = act_grad(pre, p.act) * d[j];
+                    gout[j] = gg;
+                    s0[j] += gg; s1[j] += gg * xhat;
+                }
+                if (VEC == 4) *reinterpret_cast<float4*>(p.g + src) = make_float4(gout[0], gout[1 % VEC], gout[2 % VEC], gout[3 % VEC]);
+                else p.g[src] = gout[0];
+            }
+            if (p.sums) {
+#pragma unroll
+                for (int j = 0; j < VEC; j++) {
+                    atomicAdd(&red[(cl * VEC + j) * 2], s0[j]);
+                    atomicAdd(&red[(cl * VEC + j) * 2 + 1], s1[j]);
+                }
+                // cv > lanes_c never happens for the supported channel counts (c <= 1024)
+            }
+        }
+    }
+    __syncthreads();
+    if (p.sums) {
+        for (int t = threadIdx.x; t < lanes_c * VEC; t += 256) {
+            double* dst = p.sums + ((long long)(p.per_n ? n : 0) * p.c + t) * 2;
+            atomicAdd(dst, (double)red[t * 2]);
+            atomicAdd(dst + 1, (double)red[t * 2 + 1]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ backward phase B
+struct BwdBP {
+    const float* g; const float* raw; int n, h, w, c;
+    const float* mr; int per_n;
+    const float* gamma;
+    const double* sums; double inv_count;
+    float* o0; __nv_bfloat16* oh; __nv_bfloat16* ol; int fmt;
+    int pad;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(BwdBP p) {
+    const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
+    const int cv = p.c / VEC;
+    const long long total = (long long)p.n * hp * wp * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % cv) * VEC;
+        long long t = i / cv;
+        const int px = (int)(t % wp); t /= wp;
+        const int py = (int)(t % hp);
+        const int n = (int)(t / hp);
+        const int y = py - p.pad, x = px - p.pad;
+        float v[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; j++) v[j] = 0.f;
+        if (y >= 0 && y < p.h && x >= 0 && x < p.w) {
+            const long long src = (((long long)n * p.h + y) * p.w + x) * p.c + ch;
+#pragma unroll
+            for (int j = 0; j < VEC; j++) {
+                float gg = p.g[src + j];
+                if (p.mr) {
+                    const long long gi = ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
+                    const float mean = p.mr[gi], rstd = p.mr[gi + 1];
+                    const float xhat = (p.raw[src + j] - mean) * rstd;
+                    const float m0 = (float)(p.sums[gi] * p.inv_count), m1 = (float)(p.sums[gi + 1] * p.inv_count);
+                    const float gam = p.gamma ? p.gamma[ch + j] : 1.f;
+                    gg = gam * rstd * (gg - m0 - xhat * m1);
+                }
+                v[j] = gg;
+            }
+        }
+        const long long dst = (((long long)n * hp + py) * wp + px) * p.c + ch;
+        if (p.fmt == SKIT_FMT_F32) {
+            if (VEC == 4) *reinterpret_cast<float4*>(p.o0 + dst) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+            else p.o0[dst] = v[0];
+        } else {
+            __nv_bfloat16 hi[VEC], lo[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; j++) split_bf16(v[j], hi[j], lo[j]);
+            if (VEC == 4) {
+                *reinterpret_cast<uint2*>(p.oh + dst) = *reinterpret_cast<uint2*>(hi);
+                *reinterpret_cast<uint2*>(p.ol + dst) = *reinterpret_cast<uint2*>(lo);
+            } else {
+                p.oh[dst] = hi[0]; p.ol[dst] = lo[0];
+            }
+        }
+    }
+}
+
+__global__ void bn_param_grad_kernel(const double* sums, int c, float* dgamma, float* dbeta) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    if (dbeta) dbeta[i] += (float)sums[2 * i];
+    if (dgamma) dgamma[i] += (float)sums[2 * i + 1];
+}
+
+// ------------------------------------------------------------------------------ blur resamplers
+// 1-D reflect(1) [1,2,1]/4 stride 2 down; bilinear-like [1,3,3,1]/4 stride 2 up with replicate edge.
+__global__ void __launch_bounds__(256) blur_down_fwd_kernel(const float* __restrict__ x, int n, int h, int w, int c, float* __restrict__ y) {
+    const int ho = h / 2, wo = w / 2, cv = c / 4;
+    const long long total = (long long)n * ho * wo * cv;
+    const float f[3] = {0.25f, 0.5f, 0.25f};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % cv) * 4;
+        long long t = i / cv;
+        const int ox = (int)(t % wo); t /= wo;
+        const int oy = (int)(t % ho);
+        const int b = (int)(t / ho);
+        float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int sy = pad_src(2 * oy + a, 1, h, SKIT_PAD_REFLECT);
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const int sx = pad_src(2 * ox + d, 1, w, SKIT_PAD_REFLECT);
+                const float wgt = f[a] * f[d];
+                const float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * h + sy) * w + sx) * c + ch);
+                acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+            }
+        }
+        *reinterpret_cast<float4*>(y + (((long long)b * ho + oy) * wo + ox) * c + ch) = acc;
+    }
+}
+
+// taps of the adjoint on one axis: for source index s, list (output index, weight)
+__device__ inline int blur_down_adj(int s, int len, int outs[4], float ws[4]) {
+    const float f[3] = {0.25f, 0.5f, 0.25f};
+    const int lo = len / 2;
+    int cnt = 0;
+    int cands[3]; int nc = 0;
+    cands[nc++] = s;
+    if (s == 1) cands[nc++] = -1;
+    if (s == len - 2) cands[nc++] = len;
+    for (int q = 0; q < nc; q++) {
+        const int pp = cands[q] + 1;  // padded coordinate
+        for (int a = 0; a < 3; a++) {
+            const int t = pp - a;
+            if (t >= 0 && (t & 1) == 0 && t / 2 < lo) { outs[cnt] = t / 2; ws[cnt] = f[a]; cnt++; }
+        }
+    }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(256) blur_down_bwd_kernel(const float* __restrict__ dy, int n, int h, int w, int c, float* __restrict__ dx) {
+    const int ho = h / 2, wo = w / 2, cv = c / 4;
+    const long long total = (long long)n * h * w * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % cv) * 4;
+        long long t = i / cv;
+        const int x = (int)(t % w); t /= w;
+        const int y = (int)(t % h);
+        const int b = (int)(t / h);
+        int oys[4], oxs[4]; float wy[4], wx[4];
+        const int ny = blur_down_adj(y, h, oys, wy), nx = blur_down_adj(x, w, oxs, wx);
+        float4 acc = make_float4(0, 0, 0, 0);
+        for (int a = 0; a < ny; a++)
+            for (int d = 0; d < nx; d++) {
+                const float wgt = wy[a] * wx[d];
+                const float4 v = *reinterpret_cast<const float4*>(dy + (((long long)b * ho + oys[a]) * wo + oxs[d]) * c + ch);
+                acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+            }
+        *reinterpret_cast<float4*>(dx + (((long long)b * h + y) * w + x) * c + ch) = acc;
+    }
+}
+
+__device__ inline void blur_up_taps(int u, int len, int src[2], float ws[2]) {
+    const int m = u >> 1;
+    if ((u & 1) == 0) { src[0] = max(m - 1, 0); ws[0] = 0.25f; src[1] = m; ws[1] = 0.75f; }
+    else { src[0] = m; ws[0] = 0.75f; src[1] = min(m + 1, len - 1); ws[1] = 0.25f; }
+}
+
+__global__ void __launch_bounds__(256) blur_up_fwd_kernel(const float* __restrict__ x, int n, int h, int w, int c, float* __restrict__ y) {
+    const int ho = 2 * h, wo = 2 * w, cv = c / 4;
+    const long long total = (long long)n * ho * wo * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % cv) * 4;
+        long long t = i / cv;
+        const int ox = (int)(t % wo); t /= wo;
+        const int oy = (int)(t % ho);
+        const int b = (int)(t / ho);
+        int sy[2], sx[2]; float wy[2], wx[2];
+        blur_up_taps(oy, h, sy, wy); blur_up_taps(ox, w, sx, wx);
+        float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int d = 0; d < 2; d++) {
+                const float wgt = wy[a] * wx[d];
+                const float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * h + sy[a]) * w + sx[d]) * c + ch);
+                acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+            }
+        *reinterpret_cast<float4*>(y + (((long long)b * ho + oy) * wo + ox) * c + ch) = acc;
+    }
+}
+
+// adjoint taps on one axis for source index m (input length len, output length 2*len)
+__device__ inline int blur_up_adj(int m, int len, int outs[6], float ws[6]) {
+    int cnt = 0;
+    outs[cnt] = 2 * m; ws[cnt++] = 0.75f;
+    outs[cnt] = 2 * m + 1; ws[cnt++] = 0.75f;
+    if (m + 1 <= len - 1) { outs[cnt] = 2 * (m + 1); ws[cnt++] = 0.25f; }   // y[2m'] uses x[m'-1]
+    if (m - 1 >= 0) { outs[cnt] = 2 * (m - 1) + 1; ws[cnt++] = 0.25f; }     // y[2m'+1] uses x[m'+1]
+    if (m == 0) { outs[cnt] = 0; ws[cnt++] = 0.25f; }                       // clamp at the low edge
+    if (m == len - 1) { outs[cnt] = 2 * len - 1; ws[cnt++] = 0.25f; }       // clamp at the high edge
+    return cnt;
+}
+
+__global__ void __launch_bounds__(256) blur_up_bwd_kernel(const float* __restrict__ dy, int n, int h, int w, int c, float* __restrict__ dx) {
+    const int ho = 2 * h, wo = 2 * w, cv = c / 4;
+    const long long total = (long long)n * h * w * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % cv) * 4;
+        long long t = i / cv;
+        const int x = (int)(t % w); t /= w;
+        const int y = (int)(t % h);
+        const int b = (int)(t / h);
+        int oys[6], oxs[6]; float wy[6], wx[6];
+        const int ny = blur_up_adj(y, h, oys, wy), nx = blur_up_adj(x, w, oxs, wx);
+        float4 acc = make_float4(0, 0, 0, 0);
+        for (int a = 0; a < ny; a++)
+            for (int d = 0; d < nx; d++) {
+                const float wgt = wy[a] * wx[d];
+                const float4 v = *reinterpret_cast<const float4*>(dy + (((long long)b * ho + oys[a]) * wo + oxs[d]) * c + ch);
+                acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+            }
+        *reinterpret_cast<float4*>(dx + (((long long)b * h + y) * w + x) * c + ch) = acc;
+    }
+}
+
+static int check_operand(const skit_operand* op, int n, int h, int w, int c, int pad, const char* who) {
+    if (!op) return SKIT_OK;
+    if (!op->p0 || (op->fmt == SKIT_FMT_BF16X2 && !op->p1) || (op->fmt != SKIT_FMT_F32 && op->fmt != SKIT_FMT_BF16X2)) {
+        set_error("%s: bad operand pointers/format", who);
+        return SKIT_ERR_INVALID;
+    }
+    if (op->n != n || op->hp != h + 2 * pad || op->wp != w + 2 * pad || op->c != c) {
+        set_error("%s: operand dims [%d,%d,%d,%d] do not match [%d,%d+2*%d,%d+2*%d,%d]", who, op->n, op->hp, op->wp, op->c, n, h, pad, w, pad, c);
+        return SKIT_ERR_INVALID;
+    }
+    return SKIT_OK;
+}
+
+}  // namespace skit
+
+using namespace skit;
+
+extern "C" int skit_stats_finalize(const double* stats, int groups, int c, double count, float eps,
+                                   float* mean_rstd, float* running_mean, float* running_var, float momentum, void* stream) {
+    SKIT_REQUIRE(stats && mean_rstd && groups > 0 && c > 0 && count > 0, "stats_finalize: bad arguments");
+    SKIT_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "stats_finalize: running stats must come in pairs");
+    SKIT_REQUIRE(!running_mean || groups == 1, "stats_finalize: running stats only for batch statistics (groups == 1)");
+    stats_finalize_kernel<<<cdiv(groups * c, 128), 128, 0, as_stream(stream)>>>(stats, groups, c, count, eps, mean_rstd, running_mean, running_var, momentum);
+    return check_launch("stats_finalize_kernel");
+}
+
+extern "C" int skit_norm_act_pad(const float* raw, int n, int h, int w, int c,
+                                 const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                 int act, const float* residual, float* out,
+                                 const skit_operand* op, int pad, int pad_mode, void* stream) {
+    SKIT_REQUIRE(raw && n > 0 && h > 0 && w > 0 && c > 0, "norm_act_pad: bad arguments");
+    SKIT_REQUIRE(out || op, "norm_act_pad: nothing to write");
+    SKIT_REQUIRE((norm_mode == SKIT_NORM_NONE) == (mean_rstd == nullptr), "norm_act_pad: mean_rstd must be given iff norm_mode != none");
+    SKIT_REQUIRE((gamma == nullptr) == (beta == nullptr), "norm_act_pad: gamma/beta must come in pairs");
+    SKIT_REQUIRE(pad >= 0 && (pad_mode != SKIT_PAD_REFLECT || (pad < h && pad < w)), "norm_act_pad: reflect pad %d too large for %dx%d", pad, h, w);
+    if (!op) pad = 0;
+    int rc = check_operand(op, n, h, w, c, pad, "norm_act_pad");
+    if (rc) return rc;
+    PrepP p{};
+    p.raw = raw; p.n = n; p.h = h; p.w = w; p.c = c;
+    p.mr = mean_rstd; p.per_n = norm_mode == SKIT_NORM_INSTANCE; p.gamma = gamma; p.beta = beta;
+    p.act = act; p.residual = residual; p.out = out;
+    if (op) {
+        p.fmt = op->fmt;
+        if (op->fmt == SKIT_FMT_F32) p.o0 = (float*)op->p0;
+        else { p.oh = (__nv_bfloat16*)op->p0; p.ol = (__nv_bfloat16*)op->p1; }
+    }
+    p.pad = pad; p.pad_mode = pad_mode;
+    const long long pix = (long long)n * (h + 2 * pad) * (w + 2 * pad);
+    if (c % 4 == 0) norm_act_pad_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
+    else norm_act_pad_kernel<1><<<grid_for(pix * c, 256), 256, 0, as_stream(stream)>>>(p);
+    return check_launch("norm_act_pad_kernel");
+}
+
+extern "C" int skit_act_norm_bwd_reduce(const float* dpad, int pad, int pad_mode, const float* dadd,
+                                        const float* raw, int n, int h, int w, int c,
+                                        const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                        int act, float* g, double* sums, void* stream) {
+    SKIT_REQUIRE(g && (dpad || dadd) && n > 0 && h > 0 && w > 0 && c > 0, "act_norm_bwd_reduce: bad arguments");
+    SKIT_REQUIRE(raw || (norm_mode == SKIT_NORM_NONE && act == SKIT_ACT_NONE), "act_norm_bwd_reduce: raw required unless norm and act are both none");
+    SKIT_REQUIRE((norm_mode == SKIT_NORM_NONE) == (mean_rstd == nullptr), "act_norm_bwd_reduce: mean_rstd must be given iff norm_mode != none");
+    SKIT_REQUIRE(norm_mode == SKIT_NORM_NONE || sums, "act_norm_bwd_reduce: sums required with a norm");
+    SKIT_REQUIRE(pad_mode == SKIT_PAD_ZERO || pad_mode == SKIT_PAD_REFLECT, "act_norm_bwd_reduce: unsupported pad mode");
+    SKIT_REQUIRE((gamma == nullptr) == (beta == nullptr), "act_norm_bwd_reduce: gamma/beta must come in pairs");
+    const int vec = (c % 4 == 0) ? 4 : 1;
+    SKIT_REQUIRE(c / vec <= 256, "act_norm_bwd_reduce: channel count %d too large", c);
+    BwdAP p{};
+    p.dpad = dpad; p.pad = dpad ? pad : 0; p.pad_mode = pad_mode; p.dadd = dadd;
+    p.raw = raw; p.n = n; p.h = h; p.w = w; p.c = c;
+    p.mr = mean_rstd; p.per_n = norm_mode == SKIT_NORM_INSTANCE; p.gamma = gamma; p.beta = beta;
+    p.act = act; p.g = g; p.sums = sums;
+    const int P = h * w;
+    const int lanes_c = min(c / vec, 256), PL = 256 / lanes_c;
+    int blocks_per_n = max(1, min(cdiv(P, PL * 4), cdiv(kSMs * 8, n)));
+    p.chunk = cdiv(P, blocks_per_n);
+    dim3 grid(cdiv(P, p.chunk), n);
+    if (vec == 4) act_norm_bwd_reduce_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(p);
+    else act_norm_bwd_reduce_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(p);
+    return check_launch("act_norm_bwd_reduce_kernel");
+}
+
+extern "C" int skit_norm_bwd_apply(const float* g, const float* raw, int n, int h, int w, int c,
+                                   const float* mean_rstd, int norm_mode, const float* gamma,
+                                   const double* sums, double count, float* dgamma, float* dbeta,
+                                   const skit_operand* op, int pad, void* stream) {
+    SKIT_REQUIRE(g && op && n > 0 && h > 0 && w > 0 && c > 0 && pad >= 0, "norm_bwd_apply: bad arguments");
+    SKIT_REQUIRE((norm_mode == SKIT_NORM_NONE) == (mean_rstd == nullptr), "norm_bwd_apply: mean_rstd must be given iff norm_mode != none");
+    SKIT_REQUIRE(norm_mode == SKIT_NORM_NONE || (sums && raw && count > 0), "norm_bwd_apply: sums/raw/count required with a norm");
+    int rc = check_operand(op, n, h, w, c, pad, "norm_bwd_apply");
+    if (rc) return rc;
+    BwdBP p{};
+    p.g = g; p.raw = raw; p.n = n; p.h = h; p.w = w; p.c = c;
+    p.mr = mean_rstd; p.per_n = norm_mode == SKIT_NORM_INSTANCE; p.gamma = gamma;
+    p.sums = sums; p.inv_count = count > 0 ? 1.0 / count : 0.0;
+    p.fmt = op->fmt;
+    if (op->fmt == SKIT_FMT_F32) p.o0 = (float*)op->p0;
+    else { p.oh = (__nv_bfloat16*)op->p0; p.ol = (__nv_bfloat16*)op->p1; }
+    p.pad = pad;
+    const long long pix = (long long)n * (h + 2 * pad) * (w + 2 * pad);
+    if (c % 4 == 0) norm_bwd_apply_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
+    else norm_bwd_apply_kernel<1><<<grid_for(pix * c, 256), 256, 0, as_stream(stream)>>>(p);
+    rc = check_launch("norm_bwd_apply_kernel");
+    if (rc) return rc;
+    if (norm_mode == SKIT_NORM_BATCH && (dgamma || dbeta)) {
+        bn_param_grad_kernel<<<cdiv(c, 128), 128, 0, as_stream(stream)>>>(sums, c, dgamma, dbeta);
+        return check_launch("bn_param_grad_kernel");
+    }
+    return SKIT_OK;
+}
+
+#define SKIT_BLUR_ENTRY(name, kernel, work_h, work_w, cond)                                              \
+    extern "C" int name(const float* a, int n, int h, int w, int c, float* b, void* stream) {           \
+        SKIT_REQUIRE(a && b && n > 0 && h > 1 && w > 1 && c > 0 && c % 4 == 0 && (cond),                 \
+                     #name ": bad arguments (n=%d h=%d w=%d c=%d)", n, h, w, c);                         \
+        const long long work = (long long)n * (work_h) * (work_w) * (c / 4);                             \
+        kernel<<<grid_for(work, 256), 256, 0, as_stream(stream)>>>(a, n, h, w, c, b);                    \
+        return check_launch(#kernel);                                                                    \
+    }
+
+SKIT_BLUR_ENTRY(skit_blur_down_fwd, blur_down_fwd_kernel, h / 2, w / 2, (h % 2 == 0 && w % 2 == 0))
+SKIT_BLUR_ENTRY(skit_blur_down_bwd, blur_down_bwd_kernel, h, w, (h % 2 == 0 && w % 2 == 0))
+SKIT_BLUR_ENTRY(skit_blur_up_fwd, blur_up_fwd_kernel, 2 * h, 2 * w, true)
+SKIT_BLUR_ENTRY(skit_blur_up_bwd, blur_up_bwd_kernel, h, w, true)

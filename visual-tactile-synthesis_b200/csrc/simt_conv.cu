@@ -1,0 +1,410 @@
+// Generic fp32 CUDA-core implicit-GEMM convolution kernels (forward, gather dgrad, wgrad) and the
+// weight (un)packers.  These cover every layer shape of the path (tiny channel counts, strides,
+// first/last 7x7 convs); the tcgen05 kernel in tc_conv.cu takes the tensor-core-eligible layers.
+#include "skit_common.cuh"
+
+namespace skit {
+
+struct ConvP {
+    const float* x0;
+    const __nv_bfloat16* xh;
+    const __nv_bfloat16* xl;
+    int hp, wp, ci;       // operand (A side) geometry
+    const float* w;       // [K][ncol]
+    const float* bias;
+    float* y;
+    double* stats;
+    int stats_per_n;      // 1: stats index = n (instance), 0: index 0 (batch)
+    int k, stride, org;
+    int ho, wo;           // fwd: output size; dgrad: dy size
+    int ncol;             // fwd: co; dgrad: ci
+    int K;                // reduction length
+    int M;                // rows per image (fwd: ho*wo; dgrad: hp*wp)
+    int arows;            // dgrad: channels of dy (co)
+};
+
+constexpr int BM = 128, BN = 64, BK = 16;
+
+// MODE 0: forward valid conv.  MODE 1: gather dgrad.
+template <int MODE, int FMT>
+__global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z;
+    const int m0 = blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int kk = tid & 15, rg = tid >> 4;
+    const int ty = tid >> 4, tx = tid & 15;
+
+    long long base[8];
+    int ry[8], rx[8];
+    bool rvalid[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int m = m0 + rg + 16 * i;
+        rvalid[i] = m < p.M;
+        if (MODE == 0) {
+            int oy = m / p.wo, ox = m - oy * p.wo;
+            base[i] = (((long long)n * p.hp + p.org + oy * p.stride) * p.wp + p.org + ox * p.stride) * p.ci;
+            ry[i] = 0; rx[i] = 0;
+        } else {
+            int iy = m / p.wp, ix = m - iy * p.wp;
+            ry[i] = iy; rx[i] = ix;
+            base[i] = 0;
+        }
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+    const int brow = tid >> 4, bcol = (tid & 15) * 4;
+
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+        const int kg = k0 + kk;
+        const bool kvalid = kg < p.K;
+        if (MODE == 0) {
+            int tap = kg / p.ci, c = kg - tap * p.ci;
+            int ky = tap / p.k, kx = tap - ky * p.k;
+            long long off = ((long long)ky * p.wp + kx) * p.ci + c;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float v = 0.f;
+                if (kvalid && rvalid[i]) {
+                    if (FMT == SKIT_FMT_F32) v = __ldg(p.x0 + base[i] + off);
+                    else v = __bfloat162float(p.xh[base[i] + off]) + __bfloat162float(p.xl[base[i] + off]);
+                }
+                As[kk][rg + 16 * i] = v;
+            }
+        } else {
+            int tap = kg / p.arows, o = kg - tap * p.arows;
+            int ky = tap / p.k, kx = tap - ky * p.k;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float v = 0.f;
+                if (kvalid && rvalid[i]) {
+                    int ty_ = ry[i] - ky, tx_ = rx[i] - kx;
+                    if (ty_ >= 0 && tx_ >= 0) {
+                        int oy = ty_ / p.stride, ox = tx_ / p.stride;
+                        if (oy * p.stride == ty_ && ox * p.stride == tx_ && oy < p.ho && ox < p.wo)
+                            v = __ldg(p.x0 + (((long long)n * p.ho + oy) * p.wo + ox) * p.arows + o);
+                    }
+                }
+                As[kk][rg + 16 * i] = v;
+            }
+        }
+        {
+            const int kgb = k0 + brow;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int col = n0 + bcol + j;
+                Bs[brow][bcol + j] = (kgb < p.K && col < p.ncol) ? __ldg(p.w + (long long)kgb * p.ncol + col) : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k2 = 0; k2 < BK; k2++) {
+            float a[8], b[4];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k2][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k2][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k2][tx * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int m = m0 + ty * 8 + i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int col = n0 + tx * 4 + j;
+            if (col >= p.ncol) continue;
+            float v = acc[i][j] + (p.bias ? p.bias[col] : 0.f);
+            p.y[((long long)n * p.M + m) * p.ncol + col] = v;
+            s[j] += v; q[j] += v * v;
+        }
+    }
+    if (p.stats) {
+        float* red = &As[0][0];  // 2*BN floats
+        if (tid < 2 * BN) red[tid] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            atomicAdd(&red[tx * 4 + j], s[j]);
+            atomicAdd(&red[BN + tx * 4 + j], q[j]);
+        }
+        __syncthreads();
+        if (tid < BN && n0 + tid < p.ncol) {
+            double* dst = p.stats + ((long long)(p.stats_per_n ? n : 0) * p.ncol + n0 + tid) * 2;
+            atomicAdd(dst, (double)red[tid]);
+            atomicAdd(dst + 1, (double)red[BN + tid]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- wgrad
+struct WgradP {
+    const float* x0; const __nv_bfloat16* xh; const __nv_bfloat16* xl;
+    int hp, wp, ci, org;
+    const float* d0; const __nv_bfloat16* dh; const __nv_bfloat16* dl;
+    int dhp, dwp, co, dorg;
+    int k, stride, ho, wo;
+    int Kf;        // k*k*ci
+    int chunk;     // pixels per split
+    int splits;    // per image
+    float* dwf;
+};
+
+constexpr int WM = 64, WN = 64, WK = 16;
+
+template <int XFMT, int DFMT>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
+    __shared__ float As[WK][WM + 4];  // [pix][o]
+    __shared__ float Bs[WK][WN + 4];  // [pix][col]
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z / p.splits, sp = blockIdx.z - n * p.splits;
+    const int o0 = blockIdx.x * WM, c0 = blockIdx.y * WN;
+    const int P = p.ho * p.wo;
+    const int pbeg = sp * p.chunk, pend = min(P, pbeg + p.chunk);
+    const int pk = tid >> 4, q4 = (tid & 15) * 4;
+    const int ty = tid >> 4, tx = tid & 15;
+
+    long long coloff[4];
+    bool colvalid[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int col = c0 + q4 + j;
+        colvalid[j] = col < p.Kf;
+        int tap = col / p.ci, c = col - tap * p.ci;
+        int ky = tap / p.k, kx = tap - ky * p.k;
+        coloff[j] = ((long long)ky * p.wp + kx) * p.ci + c;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+    for (int p0 = pbeg; p0 < pend; p0 += WK) {
+        const int pix = p0 + pk;
+        const bool pvalid = pix < pend;
+        int oy = 0, ox = 0;
+        if (pvalid) { oy = pix / p.wo; ox = pix - oy * p.wo; }
+        const long long dbase = (((long long)n * p.dhp + p.dorg + oy) * p.dwp + p.dorg + ox) * p.co;
+        const long long xbase = (((long long)n * p.hp + p.org + oy * p.stride) * p.wp + p.org + ox * p.stride) * p.ci;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int o = o0 + q4 + j;
+            float v = 0.f;
+            if (pvalid && o < p.co) {
+                if (DFMT == SKIT_FMT_F32) v = __ldg(p.d0 + dbase + o);
+                else v = __bfloat162float(p.dh[dbase + o]) + __bfloat162float(p.dl[dbase + o]);
+            }
+            As[pk][q4 + j] = v;
+            float u = 0.f;
+            if (pvalid && colvalid[j]) {
+                if (XFMT == SKIT_FMT_F32) u = __ldg(p.x0 + xbase + coloff[j]);
+                else u = __bfloat162float(p.xh[xbase + coloff[j]]) + __bfloat162float(p.xl[xbase + coloff[j]]);
+            }
+            Bs[pk][q4 + j] = u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k2 = 0; k2 < WK; k2++) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k2][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k2][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int o = o0 + ty * 4 + i;
+        if (o >= p.co) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int col = c0 + tx * 4 + j;
+            if (col >= p.Kf) continue;
+            atomicAdd(p.dwf + (long long)col * p.co + o, acc[i][j]);
+        }
+    }
+}
+
+// dbias[o] += sum over pixels of dy (operand with halo).  grid: (pixel chunks, n), block 256.
+template <int DFMT>
+__global__ void __launch_bounds__(256) dbias_kernel(const float* d0, const __nv_bfloat16* dh, const __nv_bfloat16* dl,
+                                                    int dhp, int dwp, int co, int dorg, int ho, int wo,
+                                                    int chunk, float* dbias) {
+    const int n = blockIdx.y;
+    const int P = ho * wo;
+    const int pbeg = blockIdx.x * chunk, pend = min(P, pbeg + chunk);
+    for (int o = threadIdx.x; o < co; o += blockDim.x) {
+        float s = 0.f;
+        for (int pix = pbeg; pix < pend; pix++) {
+            int oy = pix / wo, ox = pix - oy * wo;
+            long long a = (((long long)n * dhp + dorg + oy) * dwp + dorg + ox) * co + o;
+            s += (DFMT == SKIT_FMT_F32) ? d0[a] : (__bfloat162float(dh[a]) + __bfloat162float(dl[a]));
+        }
+        atomicAdd(dbias + o, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------- weight packs
+__global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci, int k, int mode,
+                                    float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const long long total = (long long)co * ci * k * k;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int kx = i % k; long long t = i / k;
+        int ky = t % k; t /= k;
+        int c = t % ci; int o = t / ci;
+        float v = w[i];
+        int tap; long long fidx, bidx;
+        if (mode == 0) {  // forward: GEMM K = (tap, c), N = o
+            tap = ky * k + kx;
+            fidx = ((long long)tap * ci + c) * co + o;
+            bidx = ((long long)tap * co + o) * ci + c;
+        } else if (mode == 1) {  // stride-1 dgrad: K = (flipped tap, o), N = c
+            tap = (k - 1 - ky) * k + (k - 1 - kx);
+            fidx = ((long long)tap * co + o) * ci + c;
+            bidx = ((long long)tap * ci + c) * co + o;
+        } else {  // gather dgrad: K = (tap, o), N = c
+            tap = ky * k + kx;
+            fidx = ((long long)tap * co + o) * ci + c;
+            bidx = ((long long)tap * ci + c) * co + o;
+        }
+        if (f32) f32[fidx] = v;
+        if (hi) {
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            hi[bidx] = h; lo[bidx] = l;
+        }
+    }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int co, int ci, int k, float* dw, int accumulate) {
+    const long long total = (long long)co * ci * k * k;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int kx = i % k; long long t = i / k;
+        int ky = t % k; t /= k;
+        int c = t % ci; int o = t / ci;
+        float v = dwf[((long long)(ky * k + kx) * ci + c) * co + o];
+        dw[i] = accumulate ? dw[i] + v : v;
+    }
+}
+
+int conv_fwd_simt(const skit_operand* x, const skit_weights* w, int stride, int org, int ho, int wo,
+                  const float* bias, float* y, double* stats, int stats_mode, cudaStream_t st) {
+    ConvP p{};
+    p.x0 = (const float*)x->p0; p.xh = (const __nv_bfloat16*)x->p0; p.xl = (const __nv_bfloat16*)x->p1;
+    p.hp = x->hp; p.wp = x->wp; p.ci = x->c;
+    p.w = w->f32; p.bias = bias; p.y = y; p.stats = stats; p.stats_per_n = stats_mode == SKIT_NORM_INSTANCE;
+    p.k = w->k; p.stride = stride; p.org = org; p.ho = ho; p.wo = wo;
+    p.ncol = w->co; p.K = w->k * w->k * w->ci; p.M = ho * wo; p.arows = 0;
+    dim3 grid(cdiv(p.M, BM), cdiv(p.ncol, BN), x->n);
+    if (x->fmt == SKIT_FMT_F32) conv_simt_kernel<0, SKIT_FMT_F32><<<grid, 256, 0, st>>>(p);
+    else conv_simt_kernel<0, SKIT_FMT_BF16X2><<<grid, 256, 0, st>>>(p);
+    return check_launch("conv_simt_kernel<fwd>");
+}
+
+}  // namespace skit
+
+using namespace skit;
+
+extern "C" int skit_pack_conv_weights(const float* w, int co, int ci, int k, int mode,
+                                      float* f32, void* hi, void* lo, void* stream) {
+    SKIT_REQUIRE(w && co > 0 && ci > 0 && k > 0 && mode >= 0 && mode <= 2, "pack_conv_weights: bad arguments");
+    SKIT_REQUIRE((hi == nullptr) == (lo == nullptr), "pack_conv_weights: hi and lo must be given together");
+    long long total = (long long)co * ci * k * k;
+    int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
+    pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, co, ci, k, mode, f32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    return check_launch("pack_weights_kernel");
+}
+
+extern "C" int skit_unpack_conv_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, void* stream) {
+    SKIT_REQUIRE(dwf && dw && co > 0 && ci > 0 && k > 0, "unpack_conv_wgrad: bad arguments");
+    long long total = (long long)co * ci * k * k;
+    int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
+    unpack_wgrad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dwf, co, ci, k, dw, accumulate);
+    return check_launch("unpack_wgrad_kernel");
+}
+
+extern "C" int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, int co,
+                                        const skit_weights* wg, int stride, int hp, int wp, float* dx, void* stream) {
+    SKIT_REQUIRE(dy && wg && wg->f32 && dx, "conv2d_dgrad_gather: null pointer");
+    SKIT_REQUIRE(wg->co == co, "conv2d_dgrad_gather: weight pack co=%d != dy channels %d", wg->co, co);
+    ConvP p{};
+    p.x0 = dy; p.hp = hp; p.wp = wp; p.ci = wg->ci;
+    p.w = wg->f32; p.bias = nullptr; p.y = dx; p.stats = nullptr;
+    p.k = wg->k; p.stride = stride; p.org = 0; p.ho = ho; p.wo = wo;
+    p.ncol = wg->ci; p.K = wg->k * wg->k * co; p.M = hp * wp; p.arows = co;
+    dim3 grid(cdiv(p.M, BM), cdiv(p.ncol, BN), n);
+    conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
+    return check_launch("conv_simt_kernel<dgrad>");
+}
+
+namespace skit {
+int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org, int k, int stride,
+             int ho, int wo, float* dwf, cudaStream_t st);  // tc_wgrad.cu
+bool wgrad_tc_eligible(const skit_operand* x, const skit_operand* dy, int k, int stride, int ho, int wo);
+}
+
+extern "C" int skit_conv2d_wgrad(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
+                                 int k, int stride, int ho, int wo, float* dwf, float* dbias, int impl, void* stream) {
+    SKIT_REQUIRE(x && dy && dwf && x->p0 && dy->p0, "conv2d_wgrad: null pointer");
+    SKIT_REQUIRE(x->n == dy->n, "conv2d_wgrad: batch mismatch");
+    cudaStream_t st = as_stream(stream);
+    const int n = x->n, co = dy->c, ci = x->c, P = ho * wo;
+    bool tc = impl != SKIT_IMPL_SIMT && wgrad_tc_eligible(x, dy, k, stride, ho, wo);
+    if (impl == SKIT_IMPL_TC && !tc) {
+        set_error("conv2d_wgrad: shape not eligible for the tcgen05 path");
+        return SKIT_ERR_UNSUPPORTED;
+    }
+    if (tc) {
+        int rc = wgrad_tc(x, org, dy, dy_org, k, stride, ho, wo, dwf, st);
+        if (rc) return rc;
+    } else {
+        WgradP p{};
+        p.x0 = (const float*)x->p0; p.xh = (const __nv_bfloat16*)x->p0; p.xl = (const __nv_bfloat16*)x->p1;
+        p.hp = x->hp; p.wp = x->wp; p.ci = ci; p.org = org;
+        p.d0 = (const float*)dy->p0; p.dh = (const __nv_bfloat16*)dy->p0; p.dl = (const __nv_bfloat16*)dy->p1;
+        p.dhp = dy->hp; p.dwp = dy->wp; p.co = co; p.dorg = dy_org;
+        p.k = k; p.stride = stride; p.ho = ho; p.wo = wo; p.Kf = k * k * ci; p.dwf = dwf;
+        int tiles = cdiv(co, WM) * cdiv(p.Kf, WN);
+        int want = cdiv(148 * 4, tiles);
+        int splits = max(1, min(cdiv(want, n), cdiv(P, 64)));
+        p.chunk = cdiv(cdiv(P, splits), WK) * WK;
+        p.splits = cdiv(P, p.chunk);
+        dim3 grid(cdiv(co, WM), cdiv(p.Kf, WN), n * p.splits);
+        if (x->fmt == SKIT_FMT_F32 && dy->fmt == SKIT_FMT_F32) wgrad_simt_kernel<0, 0><<<grid, 256, 0, st>>>(p);
+        else if (x->fmt == SKIT_FMT_F32) wgrad_simt_kernel<0, 1><<<grid, 256, 0, st>>>(p);
+        else if (dy->fmt == SKIT_FMT_F32) wgrad_simt_kernel<1, 0><<<grid, 256, 0, st>>>(p);
+        else wgrad_simt_kernel<1, 1><<<grid, 256, 0, st>>>(p);
+        int rc = check_launch("wgrad_simt_kernel");
+        if (rc) return rc;
+    }
+    if (dbias) {
+        int chunk = max(64, cdiv(P, 64));
+        dim3 grid(cdiv(P, chunk), n);
+        if (dy->fmt == SKIT_FMT_F32)
+            dbias_kernel<0><<<grid, 256, 0, st>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, co, dy_org, ho, wo, chunk, dbias);
+        else
+            dbias_kernel<1><<<grid, 256, 0, st>>>(nullptr, (const __nv_bfloat16*)dy->p0, (const __nv_bfloat16*)dy->p1, dy->hp, dy->wp, co, dy_org, ho, wo, chunk, dbias);
+        return check_launch("dbias_kernel");
+    }
+    return SKIT_OK;
+}

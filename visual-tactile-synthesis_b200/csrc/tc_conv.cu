@@ -1,0 +1,297 @@
+// tcgen05 + TMA implicit-GEMM convolution (stride 1, valid, NHWC haloed bf16x2 operand).
+//
+//   D[pixel][co] = sum_{tap, ci} A[pixel + tap][ci] * W[tap][co][ci]
+//
+// GEMM view per CTA: M = 128 output pixels (a TH x TW patch of one image), N = BN output channels,
+// K = taps * Ci walked in 64-channel steps.  Each K step is one TMA box of the haloed activation
+// tensor (shifted by the tap: implicit im2col, nothing is materialised) and one box of the packed
+// filter, both landing in 128B-swizzled shared memory.  fp32 fidelity comes from a 3-term bf16
+// split: x = hi + lo for both operands and D += A_lo*W_hi + A_hi*W_lo + A_hi*W_hi, accumulated in
+// fp32 in TMEM (a single bf16 pass misses the 1e-3 parity gate by 17x).
+// Epilogue: TMEM -> registers -> (+bias) -> NHWC fp32 store, plus the per-channel sum / sum of
+// squares of the tile (the InstanceNorm / BatchNorm statistics) reduced by warp shuffles and added
+// to the global double accumulators.
+//
+// Warp roles (128 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer,
+// warp 1 = TMEM allocator, all four warps = epilogue (warp w owns TMEM lanes 32w..32w+31).
+#include "tc_common.cuh"
+
+namespace skit {
+namespace tc {
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* estrides) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return SKIT_ERR_CUDA;
+    }
+    cuuint64_t gd[5];
+    cuuint64_t gs[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estrides ? estrides[i] : 1; }
+    for (int i = 0; i + 1 < rank; i++) gs[i] = strides_bytes[i];
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]", (int)r,
+                  rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                  (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+        return SKIT_ERR_CUDA;
+    }
+    return SKIT_OK;
+}
+
+struct TcConvP {
+    int k, kc;        // filter size, Ci/64
+    int org;          // halo origin offset
+    int ho, wo, co;
+    int tw, th;       // pixel patch (tw*th == 128)
+    int tiles_x;
+    const float* bias;
+    float* y;
+    double* stats;
+    int stats_per_n;
+};
+
+constexpr int A_BYTES = 128 * 128;  // 128 pixels x 64 bf16
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, TcConvP p) {
+    constexpr int W_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+    const uint32_t bar0 = smem0 + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full, slot
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar0 + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 1);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.z;
+    const int n0 = blockIdx.y * BN;
+    const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
+    const int y0 = tile_y * p.th, x0 = tile_x * p.tw;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
+        tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int num_k = p.k * p.k * p.kc;
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer
+        for (int it = 0; it < num_k; it++) {
+            const int s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(full_bar(s), STAGE_BYTES);
+            const int tap = it / p.kc, c0 = (it - tap * p.kc) * 64;
+            const int ky = tap / p.k, kx = tap - ky * p.k;
+            const uint32_t sa = smem0 + s * STAGE_BYTES;
+            tma_load_4d(sa, &tmA_hi, full_bar(s), c0, p.org + x0 + kx, p.org + y0 + ky, n);
+            tma_load_4d(sa + A_BYTES, &tmA_lo, full_bar(s), c0, p.org + x0 + kx, p.org + y0 + ky, n);
+            tma_load_3d(sa + 2 * A_BYTES, &tmW_hi, full_bar(s), c0, n0, tap);
+            tma_load_3d(sa + 2 * A_BYTES + W_BYTES, &tmW_lo, full_bar(s), c0, n0, tap);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+        for (int it = 0; it < num_k; it++) {
+            const int s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t sa = smem0 + s * STAGE_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const uint64_t a_hi = make_desc(sa + kk * 32, 16, 1024);
+                const uint64_t a_lo = make_desc(sa + A_BYTES + kk * 32, 16, 1024);
+                const uint64_t w_hi = make_desc(sa + 2 * A_BYTES + kk * 32, 16, 1024);
+                const uint64_t w_lo = make_desc(sa + 2 * A_BYTES + W_BYTES + kk * 32, 16, 1024);
+                mma_bf16(tmem_base, a_lo, w_hi, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                mma_bf16(tmem_base, a_hi, w_lo, idesc, 1u);
+                mma_bf16(tmem_base, a_hi, w_hi, idesc, 1u);
+            }
+            mma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+        }
+        mma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+
+    // ---------------- epilogue (all 4 warps)
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    __syncwarp();
+    float* red = reinterpret_cast<float*>(smem_gen);  // [4 warps][BN][2], stage memory is free now
+    {
+        const int r = warp * 32 + lane;
+        const int ty = r / p.tw, tx = r - ty * p.tw;
+        const int oy = y0 + ty, ox = x0 + tx;
+        const bool valid = oy < p.ho && ox < p.wo;
+        float* yrow = p.y + (((long long)n * p.ho + oy) * p.wo + ox) * p.co + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] += __ldg(p.bias + n0 + c + j);
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(yrow + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.stats) {
+                float sq[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    v[j] = valid ? v[j] : 0.f;
+                    sq[j] = v[j] * v[j];
+                }
+                const float s1 = col_reduce32(v, lane);
+                const float s2 = col_reduce32(sq, lane);
+                red[(warp * BN + c + lane) * 2 + 0] = s1;
+                red[(warp * BN + c + lane) * 2 + 1] = s2;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (p.stats) {
+        for (int col = threadIdx.x; col < BN; col += 128) {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; w++) { s1 += red[(w * BN + col) * 2]; s2 += red[(w * BN + col) * 2 + 1]; }
+            double* dst = p.stats + ((long long)(p.stats_per_n ? n : 0) * p.co + n0 + col) * 2;
+            atomicAdd(dst, (double)s1);
+            atomicAdd(dst + 1, (double)s2);
+        }
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_conv_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                          const CUtensorMap& w_lo, const TcConvP& p, dim3 grid, cudaStream_t st) {
+    constexpr int SMEM = STAGES * (2 * A_BYTES + 2 * BN * 128) + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_tc_kernel<%d>) failed: %s", BN, cudaGetErrorString(e));
+            return SKIT_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    conv_tc_kernel<BN, STAGES><<<grid, 128, SMEM, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+    return check_launch("conv_tc_kernel");
+}
+
+}  // namespace tc
+
+bool conv_tc_eligible(const skit_operand* x, const skit_weights* w, int stride) {
+    return x->fmt == SKIT_FMT_BF16X2 && w->hi && w->lo && stride == 1 && x->c % 64 == 0 && w->co % 64 == 0 && w->ci == x->c;
+}
+
+int conv_fwd_tc(const skit_operand* x, const skit_weights* w, int org, int ho, int wo,
+                const float* bias, float* y, double* stats, int stats_mode, cudaStream_t st) {
+    using namespace tc;
+    const int ci = x->c, co = w->co, k = w->k;
+    const int BN = (co % 256 == 0) ? 256 : (co % 128 == 0) ? 128 : 64;
+    TcConvP p{};
+    p.k = k; p.kc = ci / 64; p.org = org; p.ho = ho; p.wo = wo; p.co = co;
+    p.tw = (wo <= 8) ? 8 : 16; p.th = 128 / p.tw;
+    p.tiles_x = cdiv(wo, p.tw);
+    p.bias = bias; p.y = y; p.stats = stats; p.stats_per_n = stats_mode == SKIT_NORM_INSTANCE;
+    const int tiles_y = cdiv(ho, p.th);
+
+    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+    {
+        uint64_t dims[4] = {(uint64_t)ci, (uint64_t)x->wp, (uint64_t)x->hp, (uint64_t)x->n};
+        uint64_t strides[3] = {(uint64_t)ci * 2, (uint64_t)ci * 2 * x->wp, (uint64_t)ci * 2 * x->wp * x->hp};
+        uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
+        int rc = encode_bf16_map(&a_hi, x->p0, 4, dims, strides, box, nullptr);
+        if (rc) return rc;
+        rc = encode_bf16_map(&a_lo, x->p1, 4, dims, strides, box, nullptr);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)ci, (uint64_t)co, (uint64_t)(k * k)};
+        uint64_t strides[2] = {(uint64_t)ci * 2, (uint64_t)ci * 2 * co};
+        uint32_t box[3] = {64, (uint32_t)BN, 1};
+        int rc = encode_bf16_map(&w_hi, w->hi, 3, dims, strides, box, nullptr);
+        if (rc) return rc;
+        rc = encode_bf16_map(&w_lo, w->lo, 3, dims, strides, box, nullptr);
+        if (rc) return rc;
+    }
+    dim3 grid(p.tiles_x * tiles_y, co / BN, x->n);
+    if (BN == 256) return launch_conv_tc<256, 2>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
+    if (BN == 128) return launch_conv_tc<128, 3>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
+    return launch_conv_tc<64, 4>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
+}
+
+int conv_fwd_simt(const skit_operand* x, const skit_weights* w, int stride, int org, int ho, int wo,
+                  const float* bias, float* y, double* stats, int stats_mode, cudaStream_t st);
+
+// tensor-core wgrad: not built yet — the CUDA-core kernel in simt_conv.cu takes every shape.
+bool wgrad_tc_eligible(const skit_operand*, const skit_operand*, int, int, int, int) { return false; }
+int wgrad_tc(const skit_operand*, int, const skit_operand*, int, int, int, int, int, float*, cudaStream_t) {
+    set_error("wgrad_tc: not implemented");
+    return SKIT_ERR_UNSUPPORTED;
+}
+
+}  // namespace skit
+
+using namespace skit;
+
+extern "C" int skit_conv2d_fwd(const skit_operand* x, const skit_weights* w, int stride, int org,
+                               int ho, int wo, const float* bias, float* y,
+                               double* stats, int stats_mode, int impl, void* stream) {
+    SKIT_REQUIRE(x && w && y && x->p0, "conv2d_fwd: null pointer");
+    SKIT_REQUIRE(x->fmt == SKIT_FMT_F32 || (x->fmt == SKIT_FMT_BF16X2 && x->p1), "conv2d_fwd: bad operand format");
+    SKIT_REQUIRE(w->ci == x->c, "conv2d_fwd: weight ci=%d != operand channels %d", w->ci, x->c);
+    SKIT_REQUIRE(stride >= 1 && ho > 0 && wo > 0 && org >= 0, "conv2d_fwd: bad geometry");
+    SKIT_REQUIRE(org + (ho - 1) * stride + w->k <= x->hp && org + (wo - 1) * stride + w->k <= x->wp,
+                 "conv2d_fwd: window exceeds the haloed operand (hp=%d wp=%d k=%d stride=%d ho=%d wo=%d org=%d)",
+                 x->hp, x->wp, w->k, stride, ho, wo, org);
+    SKIT_REQUIRE(stats == nullptr || stats_mode == SKIT_NORM_INSTANCE || stats_mode == SKIT_NORM_BATCH,
+                 "conv2d_fwd: stats given without a stats mode");
+    const bool tc_ok = conv_tc_eligible(x, w, stride);
+    if (impl == SKIT_IMPL_TC && !tc_ok) {
+        set_error("conv2d_fwd: shape not eligible for the tcgen05 path (fmt=%d ci=%d co=%d stride=%d)", x->fmt, x->c, w->co, stride);
+        return SKIT_ERR_UNSUPPORTED;
+    }
+    if (tc_ok && impl != SKIT_IMPL_SIMT) return conv_fwd_tc(x, w, org, ho, wo, bias, y, stats, stats_mode, as_stream(stream));
+    SKIT_REQUIRE(w->f32, "conv2d_fwd: CUDA-core path needs the fp32 weight pack");
+    return conv_fwd_simt(x, w, stride, org, ho, wo, bias, y, stats, stats_mode, as_stream(stream));
+}

@@ -1,0 +1,703 @@
+"""Drop-in mirror of the reference's `models/networks.py` API for the skitG/sinskitG hot path:
+define_G / define_D / define_F / GANLoss / PatchSampleF / init_net / get_scheduler, with
+identical signatures, error behaviour and state_dict key names — but
+every forward and backward runs as explicit launches of the sm_100a kernels behind
+include/skit_b200.h (no autograd, no ATen convolution on the hot path).
+
+Reference: models/networks.py:148-174 (schedulers), :191-252 (init), :255-325 (define_G),
+:328-341 (define_F), :392-442 (define_D), :448-542 (GANLoss), :585-594 (Normalize),
+:667-719 (PatchSampleF), :1051-1154 (ResnetGenerator), :1267-1324 (ResnetBlock),
+:1649-1750 (Multiscale / NLayer discriminators).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn import init
+from torch.optim import lr_scheduler
+
+from . import ops
+from .ops import (ACT_LRELU, ACT_NONE, ACT_RELU, FMT_BF16X2, FMT_F32, NORM_BATCH, NORM_INSTANCE, NORM_NONE,
+                  PAD_REFLECT, PAD_ZERO)
+
+TC_ENABLED = True  # tcgen05 path for eligible layers (64-multiple channels, stride 1)
+
+
+def _require_cuda(t, who):
+    if not t.is_cuda:
+        raise RuntimeError("%s runs only on a CUDA device through libskit_b200.so; there is no CPU fallback "
+                           "(use the reference or oracle/ for CPU checks)" % who)
+
+
+# ----------------------------------------------------------------------------- parameter holders
+class Conv2d(nn.Module):
+    """Parameter holder with nn.Conv2d's state_dict keys (weight [co,ci,k,k], bias [co]).
+    Class name contains 'Conv' so init_weights treats it like the reference's conv layers."""
+
+    def __init__(self, ci, co, k, stride=1, bias=True):
+        super().__init__()
+        self.ci, self.co, self.k, self.stride = ci, co, k, stride
+        self.weight = nn.Parameter(torch.empty(co, ci, k, k))
+        self.bias = nn.Parameter(torch.zeros(co)) if bias else None
+        self.reset_parameters()
+        self._packs = {}
+
+    def reset_parameters(self):
+        init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1 / math.sqrt(self.ci * self.k * self.k)
+            init.uniform_(self.bias, -bound, bound)
+
+    @property
+    def use_tc(self):
+        return TC_ENABLED and self.stride == 1 and self.ci % 64 == 0 and self.co % 64 == 0
+
+    def pack(self, mode):
+        """mode 0 forward, 1 stride-1 dgrad (tensor-core), 2 gather dgrad (CUDA-core)."""
+        pk = self._packs.get(mode)
+        if pk is None:
+            bf16 = self.use_tc and mode in (0, 1)
+            pk = ops.PackedWeights(self.weight, mode, want_f32=not bf16, want_bf16=bf16)
+            self._packs[mode] = pk
+        return pk
+
+    def refresh_packs(self):
+        for pk in self._packs.values():
+            pk.refresh(self.weight)
+
+    def drop_packs(self):
+        self._packs = {}
+
+
+class BatchNorm2d(nn.Module):
+    """Parameter/buffer holder with nn.BatchNorm2d's keys (networks.py:127-145 norm_layer)."""
+
+    def __init__(self, c, momentum=0.1, eps=1e-5):
+        super().__init__()
+        self.c, self.momentum, self.eps = c, momentum, eps
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class _Placeholder(nn.Module):
+    """Keeps nn.Sequential indices aligned with the reference (ReLU, pads, norms without state)."""
+
+    def __init__(self, what):
+        super().__init__()
+        self.what = what
+
+    def extra_repr(self):
+        return self.what
+
+
+class _Blur(nn.Module):
+    """Downsample / Upsample filter buffer `filt` (networks.py:51-107); the kernels hard-code the
+    same [1,2,1] / [1,3,3,1] taps, the buffer exists for checkpoint compatibility."""
+
+    def __init__(self, channels, filt_size, up):
+        super().__init__()
+        a = np.array([1.0, 2.0, 1.0] if filt_size == 3 else [1.0, 3.0, 3.0, 1.0])
+        f = torch.tensor(a[:, None] * a[None, :], dtype=torch.float32)
+        f = f / f.sum() * (4.0 if up else 1.0)
+        self.register_buffer("filt", f[None, None].repeat(channels, 1, 1, 1))
+
+
+class _FlatParamsMixin:
+    """All parameters of a net live in one flat fp32 bucket (and one flat gradient bucket): the Adam
+    kernel and the data-parallel all-reduce each touch exactly one tensor."""
+
+    def flatten_parameters(self):
+        params = [p for p in self.parameters()]
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            n = p.numel()
+            flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + n].view(p.shape)
+            p.grad = grad[off:off + n].view(p.shape)
+            off += n
+        self.flat_param, self.flat_grad = flat, grad
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        for m in self.modules():
+            if isinstance(m, Conv2d):
+                m.drop_packs()
+        return self
+
+    def ensure_flat(self):
+        p = next(self.parameters())
+        if getattr(self, "flat_param", None) is None or self.flat_param.device != p.device or \
+                p.data.untyped_storage().data_ptr() != self.flat_param.untyped_storage().data_ptr():
+            self.flatten_parameters()
+
+    def zero_grad(self, set_to_none=False):  # grads are views of the flat bucket; never set to None
+        if getattr(self, "flat_grad", None) is not None:
+            self.flat_grad.zero_()
+        else:
+            super().zero_grad(set_to_none=False)
+
+    def refresh_packs(self):
+        for m in self.modules():
+            if isinstance(m, Conv2d):
+                m.refresh_packs()
+
+
+# ----------------------------------------------------------------------------- shared conv stage helpers
+def _conv_fwd(layer, x_op, org, ho, wo, stats_mode, with_bias=True):
+    pk = layer.pack(0)
+    return ops.conv2d_fwd(x_op, pk, layer.stride, org, ho, wo, bias=layer.bias if with_bias else None, stats_mode=stats_mode)
+
+
+def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None,
+               gamma=None, beta=None, dgamma=None, dbeta=None, need_dgrad=True, need_wgrad=True):
+    """Backward of [conv -> norm -> act] given the gradient w.r.t. the activated output, either as
+    a halo'd tensor `dpad` (gradient of the next conv's operand) and/or a dense `dadd`.
+    Returns the gradient w.r.t. the conv's own haloed operand (NHWC fp32 [n, hp, wp, ci]) or None."""
+    n, ho, wo, co = raw.shape
+    g, sums = ops.act_norm_bwd_reduce(raw.shape, dpad, pad, pad_mode, dadd, raw, mr, norm_mode, gamma, beta, act)
+    tc = layer.use_tc
+    q = layer.k - 1 if tc else 0
+    d_op = ops.norm_bwd_apply(g, raw, mr, norm_mode, gamma, sums, count, dgamma, dbeta, pad=q,
+                              fmt=FMT_BF16X2 if tc else FMT_F32)
+    if need_wgrad:
+        ops.conv2d_wgrad(x_op, 0, d_op, q, layer.k, layer.stride, ho, wo, layer.weight.grad,
+                         layer.bias.grad if layer.bias is not None else None)
+    if not need_dgrad:
+        return None
+    if tc:
+        dx, _ = ops.conv2d_fwd(d_op, layer.pack(1), 1, 0, x_op.hp, x_op.wp)
+        return dx
+    return ops.conv2d_dgrad_gather(d_op.data, layer.pack(2), layer.stride, x_op.hp, x_op.wp)
+
+
+# ----------------------------------------------------------------------------- generator
+class ResnetBlock(nn.Module):
+    """conv_block = [ReflectionPad2d(1), Conv2d, IN, ReLU, ReflectionPad2d(1), Conv2d, IN]
+    (networks.py:1281-1320); out = x + conv_block(x) (:1322)."""
+
+    def __init__(self, dim, use_bias=True):
+        super().__init__()
+        self.conv_block = nn.Sequential(
+            _Placeholder("ReflectionPad2d(1)"), Conv2d(dim, dim, 3, bias=use_bias), _Placeholder("InstanceNorm2d"),
+            _Placeholder("ReLU"), _Placeholder("ReflectionPad2d(1)"), Conv2d(dim, dim, 3, bias=use_bias),
+            _Placeholder("InstanceNorm2d"))
+
+
+class ResnetGenerator(_FlatParamsMixin, nn.Module):
+    """Resnet generator with antialiased down/up-sampling (networks.py:1051-1154), InstanceNorm
+    (affine=False), reflect padding, 5 output channels.  `model` index map: SURVEY.md A.2."""
+
+    def __init__(self, input_nc, output_nc, ngf=64, n_blocks=9, opt=None, **unused):
+        super().__init__()
+        assert n_blocks >= 0
+        self.input_nc, self.output_nc, self.ngf, self.n_blocks, self.opt = input_nc, output_nc, ngf, n_blocks, opt
+        P = _Placeholder
+        seq = [P("ReflectionPad2d(3)"), Conv2d(input_nc, ngf, 7), P("InstanceNorm2d"), P("ReLU")]
+        for i in range(2):
+            m = 2 ** i
+            seq += [Conv2d(ngf * m, ngf * m * 2, 3), P("InstanceNorm2d"), P("ReLU"), _Blur(ngf * m * 2, 3, up=False)]
+        seq += [ResnetBlock(ngf * 4) for _ in range(n_blocks)]
+        for i in range(2):
+            m = 2 ** (2 - i)
+            seq += [_Blur(ngf * m, 4, up=True), Conv2d(ngf * m, ngf * m // 2, 3), P("InstanceNorm2d"), P("ReLU")]
+        seq += [P("ReflectionPad2d(3)"), Conv2d(ngf, output_nc, 7), P("Tanh")]
+        self.model = nn.Sequential(*seq)
+        nb = n_blocks
+        # unregistered aliases (object.__setattr__ keeps them out of state_dict)
+        for name, idx in (("_c1", 1), ("_c4", 4), ("_c8", 8), ("_u1", 12 + nb + 1), ("_u2", 12 + nb + 5), ("_out", 12 + nb + 9)):
+            object.__setattr__(self, name, self.model[idx])
+        object.__setattr__(self, "_blocks", [self.model[12 + b] for b in range(nb)])
+
+    # -- explicit forward.  srcs: list of NCHW fp32 tensors whose channel concat is the input.
+    def fwd(self, srcs, mask=None, scale_nz=0.25, save=True, want_normal=True, taps=None):
+        _require_cuda(srcs[0], "ResnetGenerator")
+        IN = NORM_INSTANCE
+        n, _, S_h, S_w = srcs[0].shape
+        ctx = {}
+        feats = {}
+
+        def tap(i, fn):
+            if taps is not None and i in taps:
+                feats[i] = fn()
+
+        op0 = ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT)
+        tap(0, lambda: op0.data)
+        raw1, st = _conv_fwd(self._c1, op0, 0, S_h, S_w, IN)
+        mr1 = ops.stats_finalize(st, S_h * S_w)
+        tap(1, lambda: raw1)
+        _, op1 = ops.norm_act_pad(raw1, mr1, IN, act=ACT_RELU, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c4))
+        raw4, st = _conv_fwd(self._c4, op1, 0, S_h, S_w, IN)
+        mr4 = ops.stats_finalize(st, S_h * S_w)
+        tap(4, lambda: raw4)
+        a4, _ = ops.norm_act_pad(raw4, mr4, IN, act=ACT_RELU, want_dense=True)
+        d4 = ops.blur_down_fwd(a4)
+        del a4
+        _, op4 = ops.norm_act_pad(d4, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c8))
+        h2, w2 = S_h // 2, S_w // 2
+        raw8, st = _conv_fwd(self._c8, op4, 0, h2, w2, IN)
+        mr8 = ops.stats_finalize(st, h2 * w2)
+        tap(8, lambda: raw8)
+        a8, _ = ops.norm_act_pad(raw8, mr8, IN, act=ACT_RELU, want_dense=True)
+        t = ops.blur_down_fwd(a8)
+        del a8
+        h4, w4 = h2 // 2, w2 // 2
+        blocks = []
+        nb = self.n_blocks
+        fmt_b = self._fmt(self._blocks[0].conv_block[1]) if nb else FMT_F32
+        _, op_t = ops.norm_act_pad(t, pad=1, pad_mode=PAD_REFLECT, fmt=fmt_b) if nb else (None, None)
+        for b, blk in enumerate(self._blocks):
+            ca, cb = blk.conv_block[1], blk.conv_block[5]
+            rawA, st = _conv_fwd(ca, op_t, 0, h4, w4, IN)
+            mrA = ops.stats_finalize(st, h4 * w4)
+            _, opA = ops.norm_act_pad(rawA, mrA, IN, act=ACT_RELU, pad=1, pad_mode=PAD_REFLECT, fmt=self._fmt(cb))
+            rawB, st = _conv_fwd(cb, opA, 0, h4, w4, IN)
+            mrB = ops.stats_finalize(st, h4 * w4)
+            last = b == nb - 1
+            t_new, op_next = ops.norm_act_pad(rawB, mrB, IN, residual=t, want_dense=True, pad=1, pad_mode=PAD_REFLECT,
+                                              fmt=None if last else fmt_b)
+            blocks.append((op_t, rawA, mrA, opA, rawB, mrB))
+            t, op_t = t_new, op_next
+            tap(12 + b, lambda: t)
+        u1 = ops.blur_up_fwd(t)
+        _, op_u1 = ops.norm_act_pad(u1, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._u1))
+        del u1
+        raw22, st = _conv_fwd(self._u1, op_u1, 0, h2, w2, IN)
+        mr22 = ops.stats_finalize(st, h2 * w2)
+        a22, _ = ops.norm_act_pad(raw22, mr22, IN, act=ACT_RELU, want_dense=True)
+        u2 = ops.blur_up_fwd(a22)
+        del a22
+        _, op_u2 = ops.norm_act_pad(u2, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._u2))
+        del u2
+        raw26, st = _conv_fwd(self._u2, op_u2, 0, S_h, S_w, IN)
+        mr26 = ops.stats_finalize(st, S_h * S_w)
+        _, op26 = ops.norm_act_pad(raw26, mr26, IN, act=ACT_RELU, pad=3, pad_mode=PAD_REFLECT, fmt=self._fmt(self._out))
+        raw30, _ = _conv_fwd(self._out, op26, 0, S_h, S_w, NORM_NONE)
+        fI, fT, fN = ops.g_head_fwd(raw30, mask, scale_nz, want_normal)
+        if save:
+            ctx.update(op0=op0, raw1=raw1, mr1=mr1, op1=op1, raw4=raw4, mr4=mr4, op4=op4, raw8=raw8, mr8=mr8,
+                       blocks=blocks, op_u1=op_u1, raw22=raw22, mr22=mr22, op_u2=op_u2, raw26=raw26, mr26=mr26,
+                       op26=op26, raw30=raw30, mask=mask, dims=(n, S_h, S_w))
+        return (fI, fT, fN), ctx, feats
+
+    @staticmethod
+    def _fmt(layer):
+        return FMT_BF16X2 if layer.use_tc else FMT_F32
+
+    def tappable_layers(self):
+        """nn.Sequential indices whose output the fused path materialises: padded input, the three
+        stem convs (pre-norm) and every ResnetBlock output (CUT's nce_layers 0,4,8,12,16 are included)."""
+        return {0, 1, 4, 8} | {12 + b for b in range(self.n_blocks)}
+
+    # -- explicit backward: dI [n,3,h,w], dT [n,2,h,w] are gradients w.r.t. fake_I / fake_T (after *M).
+    def bwd(self, ctx, dI, dT):
+        IN = NORM_INSTANCE
+        n, S_h, S_w = ctx["dims"]
+        h2, w2, h4, w4 = S_h // 2, S_w // 2, S_h // 4, S_w // 4
+        d30 = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, 0)
+        lo = self._out
+        ops.conv2d_wgrad(ctx["op26"], 0, d30, 0, lo.k, 1, S_h, S_w, lo.weight.grad, lo.bias.grad)
+        dpad26 = ops.conv2d_dgrad_gather(d30.data, lo.pack(2), 1, S_h + 6, S_w + 6)
+        dpad_u2 = _stage_bwd(self._u2, ctx["op_u2"], ctx["raw26"], ctx["mr26"], IN, ACT_RELU, S_h * S_w,
+                             dpad=dpad26, pad=3, pad_mode=PAD_REFLECT)
+        du2, _ = ops.act_norm_bwd_reduce((n, S_h, S_w, dpad_u2.shape[3]), dpad=dpad_u2, pad=1, pad_mode=PAD_ZERO)
+        da22 = ops.blur_up_bwd(du2)
+        dpad_u1 = _stage_bwd(self._u1, ctx["op_u1"], ctx["raw22"], ctx["mr22"], IN, ACT_RELU, h2 * w2, dadd=da22)
+        du1, _ = ops.act_norm_bwd_reduce((n, h2, w2, dpad_u1.shape[3]), dpad=dpad_u1, pad=1, pad_mode=PAD_ZERO)
+        dt = ops.blur_up_bwd(du1)
+        for blk, (op_t, rawA, mrA, opA, rawB, mrB) in zip(reversed(self._blocks), reversed(ctx["blocks"])):
+            ca, cb = blk.conv_block[1], blk.conv_block[5]
+            dpadA = _stage_bwd(cb, opA, rawB, mrB, IN, ACT_NONE, h4 * w4, dadd=dt)
+            dpad_t = _stage_bwd(ca, op_t, rawA, mrA, IN, ACT_RELU, h4 * w4, dpad=dpadA, pad=1, pad_mode=PAD_REFLECT)
+            dt, _ = ops.act_norm_bwd_reduce(dt.shape, dpad=dpad_t, pad=1, pad_mode=PAD_REFLECT, dadd=dt)
+        da8 = ops.blur_down_bwd(dt, h2, w2)
+        dpad4 = _stage_bwd(self._c8, ctx["op4"], ctx["raw8"], ctx["mr8"], IN, ACT_RELU, h2 * w2, dadd=da8)
+        dd4, _ = ops.act_norm_bwd_reduce((n, h2, w2, dpad4.shape[3]), dpad=dpad4, pad=1, pad_mode=PAD_ZERO)
+        da4 = ops.blur_down_bwd(dd4, S_h, S_w)
+        dpad1 = _stage_bwd(self._c4, ctx["op1"], ctx["raw4"], ctx["mr4"], IN, ACT_RELU, S_h * S_w, dadd=da4)
+        _stage_bwd(self._c1, ctx["op0"], ctx["raw1"], ctx["mr1"], IN, ACT_RELU, S_h * S_w, dpad=dpad1, pad=1,
+                   pad_mode=PAD_ZERO, need_dgrad=False)
+
+    # -- reference module API (networks.py:1131-1154): returns tanh output [n, 5, h, w]
+    def forward(self, input, layers=[], encode_only=False, style_code=None):
+        _require_cuda(input, "ResnetGenerator")
+        self.ensure_flat()
+        self.refresh_packs()
+        bad = [i for i in layers if i not in self.tappable_layers()]
+        if bad:
+            raise NotImplementedError("feature taps %s are not exposed by the fused path (available: %s)" % (bad, sorted(self.tappable_layers())))
+        x = input.contiguous().float()
+        (fI, fT, _), _, feats = self.fwd([x], mask=None, save=False, want_normal=False, taps=set(layers) if len(layers) else None)
+        out = torch.cat([fI, fT], dim=1)
+        if len(layers) > 0:
+            fl = [feats[i].permute(0, 3, 1, 2) for i in layers if i in feats]  # NHWC storage, NCHW view
+            return fl if encode_only else (out, fl)
+        return out
+
+
+# ----------------------------------------------------------------------------- discriminators
+class NLayerDiscriminator(_FlatParamsMixin, nn.Module):
+    """PatchGAN (networks.py:1696-1750): k4, pad 2, strides 2,2,2,1,1; norm after convs 1..n_layers."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm="batch", **unused):
+        super().__init__()
+        self.n_layers, self.norm = n_layers, norm
+        self.model = nn.Sequential(*self._build(input_nc, ndf, n_layers, norm))
+        self._index_layers(self.model)
+
+    @staticmethod
+    def _build(input_nc, ndf, n_layers, norm):
+        def nl(c):
+            return BatchNorm2d(c) if norm == "batch" else _Placeholder("InstanceNorm2d" if norm == "instance" else "Identity")
+        seq = [Conv2d(input_nc, ndf, 4, stride=2), _Placeholder("LeakyReLU(0.2)")]
+        nf = ndf
+        for _ in range(1, n_layers):
+            nf_prev, nf = nf, min(nf * 2, 512)
+            seq += [Conv2d(nf_prev, nf, 4, stride=2), nl(nf), _Placeholder("LeakyReLU(0.2)")]
+        nf_prev, nf = nf, min(nf * 2, 512)
+        seq += [Conv2d(nf_prev, nf, 4, stride=1), nl(nf), _Placeholder("LeakyReLU(0.2)")]
+        seq += [Conv2d(nf, 1, 4, stride=1)]
+        return seq
+
+    def _index_layers(self, seq):
+        """[(conv, norm_module_or_None, act)] in execution order."""
+        self._stages = _d_stages(seq, self.norm)
+
+    def fwd(self, srcs, save=True, update_running=True):
+        return _d_fwd(self._stages, self.norm, srcs, save, update_running)
+
+    def bwd(self, ctx, dpred, need_wgrad=True, need_input_grad=False):
+        return _d_bwd(self._stages, self.norm, ctx, dpred, need_wgrad, need_input_grad)
+
+    def forward(self, input):
+        _require_cuda(input, "NLayerDiscriminator")
+        self.ensure_flat()
+        self.refresh_packs()
+        pred, _ = self.fwd([input.contiguous().float()], save=False, update_running=self.training)
+        return pred.permute(0, 3, 1, 2)
+
+
+def _d_stages(seq, norm):
+    stages, mods, i = [], list(seq), 0
+    while i < len(mods):
+        conv = mods[i]
+        assert isinstance(conv, Conv2d)
+        nm, act = None, ACT_NONE
+        j = i + 1
+        has_norm = False
+        while j < len(mods) and not isinstance(mods[j], Conv2d):
+            if isinstance(mods[j], BatchNorm2d):
+                nm, has_norm = mods[j], True
+            elif isinstance(mods[j], _Placeholder) and mods[j].what == "InstanceNorm2d":
+                has_norm = True
+            elif isinstance(mods[j], _Placeholder) and mods[j].what.startswith("LeakyReLU"):
+                act = ACT_LRELU
+            j += 1
+        mode = NORM_NONE if not has_norm else (NORM_BATCH if norm == "batch" else NORM_INSTANCE)
+        stages.append((conv, nm, mode, act))
+        i = j
+    return stages
+
+
+def _d_fwd(stages, norm, srcs, save, update_running=True):
+    """srcs: NCHW tensors (channel concat = D input).  Returns (pred NHWC [n,h,w,1], ctx)."""
+    _require_cuda(srcs[0], "discriminator")
+    n, _, h, w = srcs[0].shape
+    x_op = ops.nchw_cat_to_operand(srcs, 2, PAD_ZERO)
+    saved = []
+    for si, (conv, bn, mode, act) in enumerate(stages):
+        ho, wo = h // conv.stride + 1, w // conv.stride + 1   # floor((h + 4 - 4) / s) + 1
+        raw, st = _conv_fwd(conv, x_op, 0, ho, wo, mode)
+        mr = None
+        if mode != NORM_NONE:
+            cnt = n * ho * wo if mode == NORM_BATCH else ho * wo
+            upd = bn is not None and update_running
+            mr = ops.stats_finalize(st, cnt, bn.eps if bn is not None else 1e-5,
+                                    bn.running_mean if upd else None, bn.running_var if upd else None,
+                                    bn.momentum if bn is not None else 0.1)
+            if upd:
+                bn.num_batches_tracked += 1
+        if save:
+            saved.append((x_op, raw, mr, (h, w)))
+        if si == len(stages) - 1:
+            pred = raw
+            break
+        nxt = stages[si + 1][0]
+        _, x_op = ops.norm_act_pad(raw, mr, mode, bn.weight if bn is not None else None, bn.bias if bn is not None else None,
+                                   act, pad=2, pad_mode=PAD_ZERO, fmt=FMT_BF16X2 if nxt.use_tc else FMT_F32)
+        h, w = ho, wo
+    return pred, dict(saved=saved, n=n)
+
+
+def _d_bwd(stages, norm, ctx, dpred, need_wgrad=True, need_input_grad=False):
+    """dpred: NHWC [n,h,w,1] gradient w.r.t. the prediction map.  Returns the gradient w.r.t. the
+    haloed input operand (NHWC fp32 [n, H+4, W+4, cin]) if need_input_grad."""
+    n = ctx["n"]
+    dpad, dadd = None, dpred
+    for si in range(len(stages) - 1, -1, -1):
+        conv, bn, mode, act = stages[si]
+        x_op, raw, mr, _ = ctx["saved"][si]
+        _, ho, wo, _ = raw.shape
+        cnt = n * ho * wo if mode == NORM_BATCH else ho * wo
+        last_stage = si == len(stages) - 1
+        dgrad = si > 0 or need_input_grad
+        dx = _stage_bwd(conv, x_op, raw, mr, mode if not last_stage else NORM_NONE, act if not last_stage else ACT_NONE, cnt,
+                        dpad=dpad, pad=2, pad_mode=PAD_ZERO, dadd=dadd,
+                        gamma=bn.weight if bn is not None else None, beta=bn.bias if bn is not None else None,
+                        dgamma=bn.weight.grad if (bn is not None and need_wgrad) else None,
+                        dbeta=bn.bias.grad if (bn is not None and need_wgrad) else None,
+                        need_dgrad=dgrad, need_wgrad=need_wgrad)
+        dpad, dadd = dx, None
+    return dpad
+
+
+class MultiscaleDiscriminator(_FlatParamsMixin, nn.Module):
+    """num_D PatchGANs over an AvgPool2d(3,2,1,count_include_pad=False) pyramid
+    (networks.py:1649-1693): result[i] = [layer{num_D-1-i}(input downsampled i times)]."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm="batch", num_D=3, opt=None):
+        super().__init__()
+        self.n_layers, self.num_D, self.norm = n_layers, num_D, norm
+        self.getIntermFeat = bool(getattr(opt, "getIntermFeat_D", False)) if opt is not None else False
+        if self.getIntermFeat:
+            raise NotImplementedError("getIntermFeat_D is not supported on the B200 path")
+        for i in range(num_D):
+            setattr(self, "layer%d" % i, nn.Sequential(*NLayerDiscriminator._build(input_nc, ndf, n_layers, norm)))
+        self._scales = [_d_stages(getattr(self, "layer%d" % i), norm) for i in range(num_D)]
+
+    def fwd(self, srcs, save=True, update_running=True):
+        """-> (list of pred NHWC per scale i (full res first), ctx)"""
+        preds, ctxs = [], []
+        cur = srcs
+        for i in range(self.num_D):
+            pred, c = _d_fwd(self._scales[self.num_D - 1 - i], self.norm, cur, save, update_running)
+            preds.append(pred)
+            ctxs.append(c)
+            if i != self.num_D - 1:
+                cur = [ops.avgpool3s2_fwd(s) for s in cur]
+        hw = [tuple(s.shape[-2:]) for s in srcs[:1]]
+        return preds, dict(scales=ctxs, in_hw=hw[0], chans=[int(s.shape[1]) for s in srcs])
+
+    def bwd(self, ctx, dpreds, need_wgrad=True, input_slice=None):
+        """dpreds: per-scale NHWC gradients.  input_slice=(c0, cs): also return the NCHW gradient
+        w.r.t. that channel slice of the (concatenated) input, summed over the pyramid."""
+        H, W = ctx["in_hw"]
+        sizes = [(H, W)]
+        for _ in range(1, self.num_D):
+            sizes.append(((sizes[-1][0] - 1) // 2 + 1, (sizes[-1][1] - 1) // 2 + 1))
+        dins = []
+        for i in range(self.num_D):
+            d = _d_bwd(self._scales[self.num_D - 1 - i], self.norm, ctx["scales"][i], dpreds[i], need_wgrad,
+                       need_input_grad=input_slice is not None)
+            dins.append(d)
+        if input_slice is None:
+            return None
+        c0, cs = input_slice
+        acc = None
+        for i in range(self.num_D - 1, -1, -1):
+            h, w = sizes[i]
+            gi = ops.operand_grad_to_nchw(dins[i], h, w, 2, PAD_ZERO, c0, cs)
+            if acc is not None:
+                ops.avgpool3s2_bwd(acc, h, w, dx=gi, accumulate=True)
+            acc = gi
+        return acc
+
+    def forward(self, input):
+        _require_cuda(input, "MultiscaleDiscriminator")
+        self.ensure_flat()
+        self.refresh_packs()
+        preds, _ = self.fwd([input.contiguous().float()], save=False, update_running=self.training)
+        return [[p.permute(0, 3, 1, 2)] for p in preds]
+
+
+# ----------------------------------------------------------------------------- GAN loss
+class GANLoss(nn.Module):
+    """GANLoss (networks.py:448-542).  'nonsaturating' (the skitG default) runs on the fused
+    softplus-mean kernel; multiscale predictions sum the per-sample losses over scales; a bare
+    tensor uses `input[-1]`, i.e. the LAST batch element only (reference quirk, :541-542)."""
+
+    def __init__(self, gan_mode, target_real_label=1.0, target_fake_label=0.0):
+        super().__init__()
+        self.register_buffer("real_label", torch.tensor(target_real_label))
+        self.register_buffer("fake_label", torch.tensor(target_fake_label))
+        self.gan_mode = gan_mode
+        if gan_mode not in ("lsgan", "vanilla", "wgan", "wgangp", "nonsaturating", "hinge"):
+            raise NotImplementedError("gan mode %s not implemented" % gan_mode)
+        if gan_mode != "nonsaturating":
+            raise NotImplementedError("gan mode %s is outside the B200 hot path (only 'nonsaturating', the skitG/sinskitG default)" % gan_mode)
+
+    def get_loss_for_single_scale_discriminator(self, prediction, target_is_real):
+        _require_cuda(prediction, "GANLoss")
+        bs = prediction.shape[0]
+        loss = torch.zeros(bs, dtype=torch.float32, device=prediction.device)
+        ops.gan_softplus(prediction.contiguous().float(), -1.0 if target_is_real else 1.0, loss)
+        return loss
+
+    def __call__(self, input, target_is_real):
+        if isinstance(input[0], list):
+            loss = 0
+            for input_i in input:
+                loss = loss + self.get_loss_for_single_scale_discriminator(input_i[-1], target_is_real)
+            return loss
+        return self.get_loss_for_single_scale_discriminator(input[-1], target_is_real)
+
+
+# ----------------------------------------------------------------------------- PatchNCE feature sampler
+class Normalize(nn.Module):
+    """x / (||x||_p + 1e-7) (networks.py:585-594); p = 2 runs inside the sampling kernel."""
+
+    def __init__(self, power=2):
+        super().__init__()
+        self.power = power
+
+    def forward(self, x):
+        norm = x.pow(self.power).sum(1, keepdim=True).pow(1.0 / self.power)
+        return x.div(norm + 1e-7)
+
+
+class PatchSampleF(nn.Module):
+    """PatchSampleF (networks.py:667-719), netF='sample': gather `num_patches` spatial positions
+    (shared across the batch) from each feature map and L2-normalise — one warp per sampled row."""
+
+    def __init__(self, use_mlp=False, init_type="normal", init_gain=0.02, nc=256, gpu_ids=[]):
+        super().__init__()
+        self.l2norm = Normalize(2)
+        self.use_mlp, self.nc, self.mlp_init = use_mlp, nc, False
+        self.init_type, self.init_gain, self.gpu_ids = init_type, init_gain, gpu_ids
+        if use_mlp:
+            raise NotImplementedError("netF='mlp_sample' is not built on the B200 path yet (netF='sample' is)")
+
+    def forward(self, feats, num_patches=64, patch_ids=None):
+        return_ids, return_feats = [], []
+        for feat_id, feat in enumerate(feats):
+            _require_cuda(feat, "PatchSampleF")
+            B, C_, H, W = feat.shape
+            if num_patches <= 0:
+                raise NotImplementedError("num_patches == 0 (dense) is outside the B200 hot path")
+            if patch_ids is not None:
+                patch_id = patch_ids[feat_id]
+            else:
+                patch_id = np.random.permutation(H * W)
+                patch_id = patch_id[:int(min(num_patches, patch_id.shape[0]))]
+            ids = torch.as_tensor(np.asarray(patch_id.cpu() if torch.is_tensor(patch_id) else patch_id), dtype=torch.int32).to(feat.device)
+            # features produced by our generators are NHWC in memory (NCHW views): no copy then
+            nhwc = feat.permute(0, 2, 3, 1).contiguous().float()
+            out, _ = ops.patch_sample_l2norm(nhwc, ids)
+            return_ids.append(torch.as_tensor(np.asarray(patch_id.cpu() if torch.is_tensor(patch_id) else patch_id), dtype=torch.long, device=feat.device))
+            return_feats.append(out)
+        return return_feats, return_ids
+
+
+# ----------------------------------------------------------------------------- factories / init / schedulers
+def get_scheduler(optimizer, opt):
+    """networks.py:148-174."""
+    if opt.lr_policy == "linear":
+        def lambda_rule(epoch):
+            return 1.0 - max(0, epoch + opt.epoch_count - opt.n_epochs) / float(opt.n_epochs_decay + 1)
+        return lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda_rule)
+    if opt.lr_policy == "step":
+        return lr_scheduler.StepLR(optimizer, step_size=opt.lr_decay_iters, gamma=0.1)
+    if opt.lr_policy == "plateau":
+        return lr_scheduler.ReduceLROnPlateau(optimizer, mode="min", factor=0.2, threshold=0.01, patience=5)
+    if opt.lr_policy == "cosine":
+        return lr_scheduler.CosineAnnealingLR(optimizer, T_max=opt.n_epochs, eta_min=0)
+    raise NotImplementedError("learning rate policy [%s] is not implemented" % opt.lr_policy)
+
+
+def init_weights(net, init_type="normal", init_gain=0.02, debug=False):
+    """networks.py:191-231 (same class-name dispatch: 'Conv'/'Linear' weights, BatchNorm2d N(1, gain))."""
+    def init_func(m):
+        classname = m.__class__.__name__
+        if hasattr(m, "weight") and (classname.find("Conv") != -1 or classname.find("Linear") != -1):
+            if init_type == "normal":
+                init.normal_(m.weight.data, 0.0, init_gain)
+            elif init_type == "xavier":
+                init.xavier_normal_(m.weight.data, gain=init_gain)
+            elif init_type == "xavier_uniform":
+                init.xavier_uniform_(m.weight.data, gain=1.0)
+            elif init_type == "kaiming":
+                init.kaiming_normal_(m.weight.data, a=0, mode="fan_in")
+            elif init_type == "orthogonal":
+                init.orthogonal_(m.weight.data, gain=init_gain)
+            elif init_type == "none":
+                m.reset_parameters()
+            else:
+                raise NotImplementedError("initialization method [%s] is not implemented" % init_type)
+            if hasattr(m, "bias") and m.bias is not None:
+                init.constant_(m.bias.data, 0.0)
+        elif classname.find("BatchNorm2d") != -1:
+            init.normal_(m.weight.data, 1.0, init_gain)
+            init.constant_(m.bias.data, 0.0)
+    net.apply(init_func)
+
+
+def init_net(net, init_type="normal", init_gain=0.02, gpu_ids=[], debug=False, initialize_weights=True, gpu_idx=0):
+    """networks.py:234-252."""
+    if len(gpu_ids) > 0:
+        assert torch.cuda.is_available()
+        net.to(gpu_ids[gpu_idx])
+        net.gpu_idx = gpu_idx
+    if initialize_weights:
+        init_weights(net, init_type, init_gain=init_gain, debug=debug)
+    return net
+
+
+_NORM_NAMES = ("batch", "instance", "none")
+
+
+def define_G(input_nc, output_nc, ngf, netG, norm="batch", use_dropout=False, init_type="normal",
+             init_gain=0.02, no_antialias=False, no_antialias_up=False, gpu_ids=[], opt=None, generate_T_imgs=False,
+             num_layer_separate=0):
+    """networks.py:255-325.  The B200 path builds the Resnet family with InstanceNorm and the
+    antialiased resamplers (the reference's configuration for this path); other names raise the
+    reference's NotImplementedError text, unsupported-but-known ones a specific one."""
+    blocks = {"resnet_9blocks": 9, "resnet_6blocks": 6, "resnet_4blocks": 4}
+    if netG in blocks:
+        if norm != "instance":
+            raise NotImplementedError("B200 path: resnet generators are built with norm='instance' (got %r)" % norm)
+        if use_dropout or no_antialias or no_antialias_up:
+            raise NotImplementedError("B200 path: dropout / no_antialias variants of the resnet generator are not built")
+        net = ResnetGenerator(input_nc, output_nc, ngf, n_blocks=blocks[netG], opt=opt)
+    elif netG in ("unet_128", "unet_256", "unet256_custom", "stylegan2", "smallstylegan2"):
+        raise NotImplementedError("Generator model name [%s] is on the roadmap of the B200 path but not built yet" % netG)
+    else:
+        raise NotImplementedError("Generator model name [%s] is not recognized" % netG)
+    return init_net(net, init_type, init_gain, gpu_ids, initialize_weights=("stylegan2" not in netG))
+
+
+def define_D(input_nc, ndf, netD, n_layers_D=3, norm="batch", init_type="normal", init_gain=0.02, no_antialias=False,
+             num_D=3, gpu_ids=[], opt=None, gpu_idx=0):
+    """networks.py:392-442."""
+    if norm not in _NORM_NAMES:
+        raise NotImplementedError("normalization layer [%s] is not found" % norm)
+    if netD == "basic":
+        net = NLayerDiscriminator(input_nc, ndf, n_layers=3, norm=norm)
+    elif netD == "n_layers":
+        net = NLayerDiscriminator(input_nc, ndf, n_layers_D, norm=norm)
+    elif netD == "multiscale":
+        net = MultiscaleDiscriminator(input_nc, ndf, n_layers=n_layers_D, norm=norm, num_D=num_D, opt=opt)
+    elif netD == "pixel" or "stylegan2" in netD:
+        raise NotImplementedError("Discriminator model name [%s] is not built on the B200 path" % netD)
+    else:
+        raise NotImplementedError("Discriminator model name [%s] is not recognized" % netD)
+    return init_net(net, init_type, init_gain, gpu_ids, initialize_weights=("stylegan2" not in netD), gpu_idx=gpu_idx)
+
+
+def define_F(input_nc, netF, norm="batch", use_dropout=False, init_type="normal", init_gain=0.02, no_antialias=False,
+             gpu_ids=[], opt=None):
+    """networks.py:328-341."""
+    if netF == "sample":
+        net = PatchSampleF(use_mlp=False, init_type=init_type, init_gain=init_gain, gpu_ids=gpu_ids, nc=opt.netF_nc)
+    elif netF == "mlp_sample":
+        net = PatchSampleF(use_mlp=True, init_type=init_type, init_gain=init_gain, gpu_ids=gpu_ids, nc=opt.netF_nc)
+    elif netF in ("global_pool", "reshape", "strided_conv"):
+        raise NotImplementedError("projection model name [%s] is not built on the B200 path" % netF)
+    else:
+        raise NotImplementedError("projection model name [%s] is not recognized" % netF)
+    return init_net(net, init_type, init_gain, gpu_ids)

@@ -1,0 +1,296 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/skit_b200.h).
+
+Device layouts: feature maps NHWC fp32; conv operands NHWC with halo, fp32 or
+bf16 hi/lo planes; images/patches NCHW fp32.  PyTorch only provides memory and streams here.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, FMT_BF16X2, FMT_F32, IMPL_AUTO, IMPL_SIMT, IMPL_TC,
+                   NORM_BATCH, NORM_INSTANCE, NORM_NONE, PAD_REFLECT, PAD_REPLICATE, PAD_ZERO)
+
+_p = L.ptr
+
+
+class Operand:
+    """A haloed NHWC conv operand on the device (fp32, or bf16 hi/lo planes for tcgen05)."""
+
+    def __init__(self, n, h, w, c, pad, fmt, device):
+        self.n, self.h, self.w, self.c, self.pad, self.fmt = n, h, w, c, pad, fmt
+        self.hp, self.wp = h + 2 * pad, w + 2 * pad
+        if fmt == FMT_F32:
+            self.data = torch.empty((n, self.hp, self.wp, c), dtype=torch.float32, device=device)
+            p0, p1 = self.data.data_ptr(), None
+        else:
+            self.data = torch.empty((2, n, self.hp, self.wp, c), dtype=torch.bfloat16, device=device)
+            p0, p1 = self.data[0].data_ptr(), self.data[1].data_ptr()
+        self.struct = L.SkitOperand(p0, p1, fmt, n, self.hp, self.wp, c)
+
+    def ref(self):
+        return C.byref(self.struct)
+
+    def to_float(self):
+        """fp32 view of the contents (tests only)."""
+        return self.data if self.fmt == FMT_F32 else self.data[0].float() + self.data[1].float()
+
+
+class PackedWeights:
+    """Per-step repack of one conv's reference-layout weight (skit_pack_conv_weights)."""
+
+    def __init__(self, w, mode, want_f32=True, want_bf16=False):
+        co, ci, k, _ = w.shape
+        self.k, self.mode = k, mode
+        # the GEMM reduces over `rci` channels per tap and produces `rco` columns
+        self.rci, self.rco = (ci, co) if mode == 0 else (co, ci)
+        dev = w.device
+        self.f32 = torch.empty((k * k * self.rci, self.rco), dtype=torch.float32, device=dev) if want_f32 else None
+        self.hi = torch.empty((k * k, self.rco, self.rci), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+        self.lo = torch.empty_like(self.hi) if want_bf16 else None
+        self.co, self.ci = co, ci
+        self.struct = L.SkitWeights(self.f32.data_ptr() if want_f32 else None,
+                                    self.hi.data_ptr() if want_bf16 else None,
+                                    self.lo.data_ptr() if want_bf16 else None, k, self.rci, self.rco)
+        self.refresh(w)
+
+    def refresh(self, w):
+        L.call("skit_pack_conv_weights", _p(w.detach()), self.co, self.ci, self.k, self.mode,
+               _p(self.f32), _p(self.hi), _p(self.lo), L.stream())
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def conv2d_fwd(x, w, stride, org, ho, wo, bias=None, stats_mode=NORM_NONE, impl=IMPL_AUTO, out=None):
+    """Valid conv over a haloed operand -> (y NHWC fp32, stats double [groups, co, 2] or None)."""
+    co = w.rco
+    dev = x.data.device
+    y = out if out is not None else torch.empty((x.n, ho, wo, co), dtype=torch.float32, device=dev)
+    stats = None
+    if stats_mode != NORM_NONE:
+        groups = x.n if stats_mode == NORM_INSTANCE else 1
+        stats = torch.zeros((groups, co, 2), dtype=torch.float64, device=dev)
+    L.call("skit_conv2d_fwd", x.ref(), w.ref(), stride, org, ho, wo, _p(bias), _p(y), _p(stats), stats_mode, impl, L.stream())
+    return y, stats
+
+
+def conv2d_dgrad_gather(dy, wg, stride, hp, wp):
+    n, ho, wo, co = dy.shape
+    dx = torch.empty((n, hp, wp, wg.rco), dtype=torch.float32, device=dy.device)
+    L.call("skit_conv2d_dgrad_gather", _p(dy), n, ho, wo, co, wg.ref(), stride, hp, wp, _p(dx), L.stream())
+    return dx
+
+
+def conv2d_wgrad(x, org, dy, dy_org, k, stride, ho, wo, dw, dbias=None, impl=IMPL_AUTO):
+    """Accumulates into dw ([co][ci][k][k] view of the flat grad bucket) and dbias."""
+    co, ci = dy.c, x.c
+    dwf = torch.zeros((k * k * ci, co), dtype=torch.float32, device=x.data.device)
+    L.call("skit_conv2d_wgrad", x.ref(), org, dy.ref(), dy_org, k, stride, ho, wo, _p(dwf), _p(dbias), impl, L.stream())
+    L.call("skit_unpack_conv_wgrad", _p(dwf), co, ci, k, _p(dw), 1, L.stream())
+
+
+def stats_finalize(stats, count, eps=1e-5, running_mean=None, running_var=None, momentum=0.1):
+    groups, c, _ = stats.shape
+    mr = torch.empty((groups, c, 2), dtype=torch.float32, device=stats.device)
+    L.call("skit_stats_finalize", _p(stats), groups, c, float(count), eps, _p(mr), _p(running_mean), _p(running_var), momentum, L.stream())
+    return mr
+
+
+def norm_act_pad(raw, mr=None, norm_mode=NORM_NONE, gamma=None, beta=None, act=ACT_NONE, residual=None,
+                 want_dense=False, pad=0, pad_mode=PAD_ZERO, fmt=None):
+    """-> (dense NHWC fp32 or None, Operand or None)."""
+    n, h, w, c = raw.shape
+    dense = torch.empty_like(raw) if want_dense else None
+    op = Operand(n, h, w, c, pad, fmt, raw.device) if fmt is not None else None
+    L.call("skit_norm_act_pad", _p(raw), n, h, w, c, _p(mr), norm_mode, _p(gamma), _p(beta), act, _p(residual), _p(dense),
+           op.ref() if op is not None else None, pad, pad_mode, L.stream())
+    return dense, op
+
+
+def act_norm_bwd_reduce(shape, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None, raw=None, mr=None, norm_mode=NORM_NONE,
+                        gamma=None, beta=None, act=ACT_NONE):
+    """-> (g NHWC fp32, sums double [groups, c, 2] or None)."""
+    n, h, w, c = shape
+    dev = (dpad if dpad is not None else dadd).device
+    g = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
+    sums = None
+    if norm_mode != NORM_NONE:
+        sums = torch.zeros((n if norm_mode == NORM_INSTANCE else 1, c, 2), dtype=torch.float64, device=dev)
+    L.call("skit_act_norm_bwd_reduce", _p(dpad), pad, pad_mode, _p(dadd), _p(raw), n, h, w, c, _p(mr), norm_mode,
+           _p(gamma), _p(beta), act, _p(g), _p(sums), L.stream())
+    return g, sums
+
+
+def norm_bwd_apply(g, raw=None, mr=None, norm_mode=NORM_NONE, gamma=None, sums=None, count=0.0, dgamma=None, dbeta=None,
+                   pad=0, fmt=FMT_F32):
+    n, h, w, c = g.shape
+    op = Operand(n, h, w, c, pad, fmt, g.device)
+    L.call("skit_norm_bwd_apply", _p(g), _p(raw), n, h, w, c, _p(mr), norm_mode, _p(gamma), _p(sums), float(count),
+           _p(dgamma), _p(dbeta), op.ref(), pad, L.stream())
+    return op
+
+
+def _resample(name, x, out_hw):
+    n, h, w, c = x.shape
+    y = torch.empty((n, out_hw[0], out_hw[1], c), dtype=torch.float32, device=x.device)
+    return n, h, w, c, y
+
+
+def blur_down_fwd(x):
+    n, h, w, c = x.shape
+    y = torch.empty((n, h // 2, w // 2, c), dtype=torch.float32, device=x.device)
+    L.call("skit_blur_down_fwd", _p(x), n, h, w, c, _p(y), L.stream())
+    return y
+
+
+def blur_down_bwd(dy, h, w):
+    n, _, _, c = dy.shape
+    dx = torch.empty((n, h, w, c), dtype=torch.float32, device=dy.device)
+    L.call("skit_blur_down_bwd", _p(dy), n, h, w, c, _p(dx), L.stream())
+    return dx
+
+
+def blur_up_fwd(x):
+    n, h, w, c = x.shape
+    y = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float32, device=x.device)
+    L.call("skit_blur_up_fwd", _p(x), n, h, w, c, _p(y), L.stream())
+    return y
+
+
+def blur_up_bwd(dy):
+    n, h2, w2, c = dy.shape
+    dx = torch.empty((n, h2 // 2, w2 // 2, c), dtype=torch.float32, device=dy.device)
+    L.call("skit_blur_up_bwd", _p(dy), n, h2 // 2, w2 // 2, c, _p(dx), L.stream())
+    return dx
+
+
+def _src_arrays(srcs):
+    k = len(srcs)
+    ptrs = (C.c_void_p * k)(*[s.data_ptr() for s in srcs])
+    chans = (C.c_int * k)(*[int(s.shape[1]) for s in srcs])
+    return ptrs, chans
+
+
+def nchw_cat_to_operand(srcs, pad, pad_mode):
+    """srcs: list of contiguous NCHW fp32 tensors with equal N,H,W -> fp32 Operand of the channel concat."""
+    for s in srcs:
+        assert s.is_cuda and s.is_contiguous() and s.dtype == torch.float32
+    n, _, h, w = srcs[0].shape
+    ctot = sum(int(s.shape[1]) for s in srcs)
+    op = Operand(n, h, w, ctot, pad, FMT_F32, srcs[0].device)
+    ptrs, chans = _src_arrays(srcs)
+    L.call("skit_nchw_cat_to_operand", ptrs, chans, len(srcs), n, h, w, op.ref(), pad, pad_mode, L.stream())
+    return op
+
+
+def operand_grad_to_nchw(dpad, h, w, pad, pad_mode, c0, cs, dst=None, accumulate=False):
+    n, _, _, c = dpad.shape
+    if dst is None:
+        dst = torch.empty((n, cs, h, w), dtype=torch.float32, device=dpad.device)
+        accumulate = False
+    L.call("skit_operand_grad_to_nchw", _p(dpad), n, h, w, c, pad, pad_mode, c0, cs, _p(dst), int(accumulate), L.stream())
+    return dst
+
+
+def g_head_fwd(raw, mask, scale_nz=0.25, want_normal=True):
+    n, h, w, _ = raw.shape
+    dev = raw.device
+    fI = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+    fT = torch.empty((n, 2, h, w), dtype=torch.float32, device=dev)
+    fN = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev) if want_normal else None
+    L.call("skit_g_head_fwd", _p(raw), _p(mask), n, h, w, scale_nz, _p(fI), _p(fT), _p(fN), L.stream())
+    return fI, fT, fN
+
+
+def g_head_bwd(raw, mask, dI, dT, pad):
+    n, h, w, _ = raw.shape
+    op = Operand(n, h, w, 5, pad, FMT_F32, raw.device)
+    L.call("skit_g_head_bwd", _p(raw), _p(mask), _p(dI), _p(dT), n, h, w, op.ref(), pad, L.stream())
+    return op
+
+
+def diffaug_bs_mask(x, mask, u_b, u_s):
+    n, _, h, w = x.shape
+    y = torch.empty_like(x)
+    L.call("skit_diffaug_bs_mask", _p(x), _p(mask), _p(u_b), _p(u_s), n, h, w, _p(y), L.stream())
+    return y
+
+
+def avgpool3s2_fwd(x):
+    n, c, h, w = x.shape
+    y = torch.empty((n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1), dtype=torch.float32, device=x.device)
+    L.call("skit_avgpool3s2_fwd", _p(x), n * c, h, w, _p(y), L.stream())
+    return y
+
+
+def avgpool3s2_bwd(dy, h, w, dx=None, accumulate=False):
+    n, c = dy.shape[:2]
+    if dx is None:
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dy.device)
+        accumulate = False
+    L.call("skit_avgpool3s2_bwd", _p(dy), n * c, h, w, _p(dx), int(accumulate), L.stream())
+    return dx
+
+
+def patch_gather(srcs, ox, oy, ps, ctot=None, coffs=None, dst=None):
+    """srcs: [1,C,H,W] NCHW tensors; ox/oy int32 device tensors [P] -> [P, ctot, ps, ps]."""
+    for s in srcs:
+        assert s.shape[0] == 1, "coords should have batch size of 1"  # reference: model_utils.py:235
+    h, w = srcs[0].shape[-2:]
+    npatch = int(ox.numel())
+    total = sum(int(s.shape[1]) for s in srcs)
+    ctot = total if ctot is None else ctot
+    if dst is None:
+        dst = torch.empty((npatch, ctot, ps, ps), dtype=torch.float32, device=srcs[0].device)
+    ptrs, chans = _src_arrays(srcs)
+    co = None if coffs is None else (C.c_int * len(srcs))(*coffs)
+    L.call("skit_patch_gather", ptrs, chans, co, len(srcs), h, w, _p(ox), _p(oy), npatch, ps, _p(dst), ctot, L.stream())
+    return dst
+
+
+def patch_scatter_add(dpatch, coff, cs, ox, oy, dsrc):
+    npatch, ctot, ps, _ = dpatch.shape
+    h, w = dsrc.shape[-2:]
+    L.call("skit_patch_scatter_add", _p(dpatch), ctot, coff, cs, h, w, _p(ox), _p(oy), npatch, ps, _p(dsrc), L.stream())
+
+
+def gan_softplus(pred, sign, loss, dpred=None, gscale=0.0):
+    """pred: [N, h, w, 1] (or any [N, ...]); loss: [N] accumulator."""
+    n = pred.shape[0]
+    hw = pred.numel() // n
+    L.call("skit_gan_softplus", _p(pred), n, hw, float(sign), _p(loss), _p(dpred), float(gscale), L.stream())
+
+
+def l1_loss(a, b, scale, loss, grad=None, gscale=0.0, accumulate=False):
+    L.call("skit_l1_loss", _p(a), _p(b), a.numel(), float(scale), _p(loss), _p(grad), float(gscale), int(accumulate), L.stream())
+
+
+def adam_step(p, g, m, v, step, lr, beta1, beta2, eps=1e-8, grad_scale=1.0):
+    L.call("skit_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), int(step), float(lr), float(beta1), float(beta2),
+           float(eps), float(grad_scale), L.stream())
+
+
+def patch_sample_l2norm(feat_nhwc, ids, keep_pre=False):
+    b, h, w, c = feat_nhwc.shape
+    npatch = int(ids.numel())
+    out = torch.empty((b * npatch, c), dtype=torch.float32, device=feat_nhwc.device)
+    pre = torch.empty_like(out) if keep_pre else None
+    L.call("skit_patch_sample_l2norm", _p(feat_nhwc), b, h * w, c, _p(ids), npatch, _p(out), _p(pre), L.stream())
+    return out, pre
+
+
+def patch_sample_l2norm_bwd(dout, pre, ids, feat_shape):
+    b, h, w, c = feat_shape
+    dfeat = torch.zeros(feat_shape, dtype=torch.float32, device=dout.device)
+    L.call("skit_patch_sample_l2norm_bwd", _p(dout), _p(pre), b, h * w, c, _p(ids), int(ids.numel()), _p(dfeat), L.stream())
+    return dfeat
+
+
+def patchnce(q, k, b, nce_T, want_grad=False, gscale=1.0):
+    rows, dim = q.shape
+    npatch = rows // b
+    loss = torch.empty((rows,), dtype=torch.float32, device=q.device)
+    dq = torch.empty_like(q) if want_grad else None
+    L.call("skit_patchnce", _p(q), _p(k), b, npatch, dim, 1.0 / nce_T, _p(loss), _p(dq), float(gscale), L.stream())
+    return loss, dq
