@@ -60,7 +60,9 @@ typedef struct skit_weights {
     const float* f32; /* [k*k*ci][co]  (SIMT path)           */
     const void* hi;   /* bf16 [k*k][co][ci] (tcgen05 path)   */
     const void* lo;   /* bf16 [k*k][co][ci]                  */
-    int k, ci, co;
+    int k;
+    int ci; /* channels the GEMM reduces over per tap (forward pack: conv ci; dgrad packs: conv co) */
+    int co; /* GEMM output columns               (forward pack: conv co; dgrad packs: conv ci) */
 } skit_weights;
 
 const char* skit_last_error(void);

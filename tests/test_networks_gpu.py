@@ -13,6 +13,21 @@ pytestmark = pytest.mark.gpu
 
 GATE = 1e-3
 TIGHT = 2e-4
+# Whole-network GRADIENT parity cannot be gated at 1e-3: ReLU/LeakyReLU masks are discontinuous, so a
+# forward that agrees with the oracle to eps flips ~0.8*eps*N mask bits per layer (N = elements), and
+# each flip moves the upstream gradient by ~1/sqrt(N) relative.  With eps = 3e-5 (bf16x3 tensor-core
+# forward) and N = 65k..260k that is a few flips per layer -> 3e-3..1e-2 relative L2, varying run to run
+# with the order of the statistics atomics (tools/diag_gbwd.py shows the fp64 oracle agrees with the
+# fp32 one only because eps = 2e-6 there).  Per-stage backward parity IS gated tightly (2e-4) in
+# test_kernels_gpu.py::test_conv_stage_fwd_bwd, where both sides see bit-identical inputs.
+GRAD_REL = 3e-2
+GRAD_COS = 0.9995
+
+
+def cos(a, b):
+    b = b.detach().cpu() if torch.is_tensor(b) else torch.as_tensor(np.asarray(b))
+    a, b = a.detach().double().cpu().flatten(), b.double().flatten()
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-300)).item()
 
 
 @pytest.fixture(scope="module")
@@ -23,7 +38,8 @@ def V():
 
 
 def rel(a, b):
-    a, b = a.detach().double().cpu(), torch.as_tensor(np.asarray(b)).double()
+    b = b.detach().cpu() if torch.is_tensor(b) else torch.as_tensor(np.asarray(b))
+    a, b = a.detach().double().cpu(), b.double()
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
@@ -95,7 +111,7 @@ def test_resnet_generator_ngf64_tcgen05_fwd_bwd(V, hw, n, nb):
             continue  # bias before InstanceNorm: gradient is exactly zero in exact arithmetic
         r = rel(p.grad, ps[k].grad)
         worst = max(worst, r)
-        assert r < GATE, (k, r)
+        assert r < GRAD_REL and cos(p.grad, ps[k].grad) > GRAD_COS, (k, r)
     print("worst grad rel err", worst)
 
 
@@ -116,11 +132,13 @@ def test_multiscale_discriminator_matches_reference_golden(V, golden_dir):
     assert rel(crit(pred, True), z["D_loss_real"]) < TIGHT
     assert rel(crit(pred[0][-1], True), z["D_loss_tensor_real"]) < TIGHT
     after = load_sd(z, "D_after.")  # BN running stats after one training-mode forward
-    for k, v in D.state_dict().items():
+    assert len(after) > 0
+    for k, ref in after.items():
+        v = D.state_dict()[k]
         if v.dtype.is_floating_point:
-            assert rel(v, after[k]) < TIGHT, k
+            assert rel(v, ref) < TIGHT, k
         else:
-            assert int(v) == int(after[k]), k
+            assert int(v) == int(ref), k
     sdb = load_sd(z, "Dbasic.")
     Db = V.define_D(4, sdb["model.0.weight"].shape[0], "basic", 3, "batch", "xavier", 0.02, False, 3, [], None).cuda()
     Db.load_state_dict(sdb)
@@ -158,9 +176,9 @@ def test_multiscale_discriminator_backward(V, ndf, hw, n):
     dI = D.bwd(ctx, dps, need_wgrad=True, input_slice=(1, 3))
     torch.cuda.synchronize()
     assert abs(lossk.mean().item() * 0.5 - loss.item()) < 1e-5 * max(1, abs(loss.item()))
-    assert rel(dI, I.grad) < GATE
+    assert rel(dI, I.grad) < GRAD_REL and cos(dI, I.grad) > GRAD_COS
     for k, p in D.named_parameters():
         is_bias_before_bn = k.endswith("bias") and k.split(".")[1] in ("2", "5", "8")
         if is_bias_before_bn:
             continue
-        assert rel(p.grad, ps[k].grad) < GATE, k
+        assert rel(p.grad, ps[k].grad) < GRAD_REL and cos(p.grad, ps[k].grad) > GRAD_COS, k

@@ -346,12 +346,13 @@ extern "C" int skit_unpack_conv_wgrad(const float* dwf, int co, int ci, int k, f
 extern "C" int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, int co,
                                         const skit_weights* wg, int stride, int hp, int wp, float* dx, void* stream) {
     SKIT_REQUIRE(dy && wg && wg->f32 && dx, "conv2d_dgrad_gather: null pointer");
-    SKIT_REQUIRE(wg->co == co, "conv2d_dgrad_gather: weight pack co=%d != dy channels %d", wg->co, co);
+    // mode-2 pack: the GEMM reduces over (tap, dy channel) and produces the conv's input channels
+    SKIT_REQUIRE(wg->ci == co, "conv2d_dgrad_gather: weight pack reduces over %d channels but dy has %d", wg->ci, co);
     ConvP p{};
-    p.x0 = dy; p.hp = hp; p.wp = wp; p.ci = wg->ci;
+    p.x0 = dy; p.hp = hp; p.wp = wp; p.ci = wg->co;
     p.w = wg->f32; p.bias = nullptr; p.y = dx; p.stats = nullptr;
     p.k = wg->k; p.stride = stride; p.org = 0; p.ho = ho; p.wo = wo;
-    p.ncol = wg->ci; p.K = wg->k * wg->k * co; p.M = hp * wp; p.arows = co;
+    p.ncol = wg->co; p.K = wg->k * wg->k * co; p.M = hp * wp; p.arows = co;
     dim3 grid(cdiv(p.M, BM), cdiv(p.ncol, BN), n);
     conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
     return check_launch("conv_simt_kernel<dgrad>");
