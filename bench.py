@@ -1,0 +1,265 @@
+"""bench.py — skitG/sinskitG train-step throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl reference]
+
+Workload (config.workload): configs[1] of BASELINE.json — one single-material train step
+(G forward, D1 step, D2 step, G step with GAN + L1 + patch-L1, three Adam updates) at SxS = 512x512,
+NT = 64 touch patches + NF = 32 random fake patches, PatchNCE off, LPIPS / vision-aided off, on the
+tensor-core architecture (resnet_9blocks ngf 64, multiscale PatchGAN ndf 64), batch 1 per rank
+(the reference forces batch_size = 1).  Synthetic seeded inputs, random-init weights.
+
+One JSON line on stdout (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same
+step through the public model API with host inputs: set_input (pinned H2D) + optimize_parameters +
+get_current_losses (D2H) inside the timed region.  N > 1: one process per GPU (torchrun), one sample
+per rank per step, flat-bucket gradient all-reduce over NCCL — weak scaling.
+`--impl reference` times the CPU oracle (a restatement of the reference's own PyTorch code path,
+pinned to the real reference by tests/golden) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "skitG train-step images/sec"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample-size", type=int, default=256, help="image side of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a):
+    return {"workload": "skitG/sinskitG train step, single material, %dx%d, resnet_9blocks ngf64 + multiscale PatchGAN ndf64, "
+                        "NT=64 NF=32, GAN+L1+patch-L1, PatchNCE off, LPIPS/VAL off (BASELINE.json configs[1])" % (a.size, a.size),
+            "size": a.size, "images_per_rank_per_step": 1, "NT": 64, "NF": 32, "netG": "resnet_9blocks", "ngf": 64,
+            "netD": "multiscale", "ndf": 64, "parallelism": "dp%d (flat grad bucket all-reduce, NCCL)" % a.gpus,
+            "l2": "per-step working set (saved activations + operands) is several GB >> 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------- CPU oracle legs
+def oracle_step_time(size, steps, warmup, nt, nf, threads):
+    """Times the CPU oracle's train step (oracle/skit_oracle.py, pinned to the real reference) — the checker
+    run as a baseline, never as the product."""
+    from oracle import skit_oracle as O
+    import vts_b200
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    opt = argparse.Namespace(gan_mode="nonsaturating")
+    G = vts_b200.networks.define_G(9, 5, 64, "resnet_9blocks", "instance", False, "xavier", 0.02, False, False, [], opt)
+    D = vts_b200.networks.define_D(4, 64, "multiscale", 3, "batch", "xavier", 0.02, False, 3, [], opt)
+    D2 = vts_b200.networks.define_D(7, 64, "multiscale", 3, "batch", "xavier", 0.02, False, 3, [], opt)
+    sds = [{k: v.detach().clone() for k, v in n.state_dict().items()} for n in (G, D, D2)]
+    cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=nt, add_fake_T_sample_size=nf)
+    batch = O.step_inputs_from_batch(O.synthetic_batch(size, NT=nt, seed=0))
+    rs = np.random.RandomState(0)
+    times = []
+    state = {}
+    for i in range(warmup + steps):
+        rand = dict(real_b=[0.3], real_s=[0.8], fake_b=[0.6], fake_s=[0.2],
+                    fake_ox=rs.randint(0, size - 32, nf).astype(np.int32), fake_oy=rs.randint(0, size - 32, nf).astype(np.int32))
+        t0 = time.perf_counter()
+        O.train_step(cfg, sds[0], sds[1], sds[2], state, batch, rand, step=i + 1)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times))
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    s = a.cpu_sample_size
+    nt, nf = 16, 8
+    t = oracle_step_time(s, max(1, min(a.steps, 3)), min(a.warmup, 1), nt, nf, cores)
+    # bounded sample: a step at s x s; conv work scales with pixels, so images/s at the full size is scaled by (s/size)^2
+    value = (1.0 / t) * (s * s) / float(a.size * a.size)
+    sample = "CPU oracle train step at %dx%d (NT=%d NF=%d), %.2f s/step, scaled by (%d/%d)^2 to the %dx%d workload" % (s, s, nt, nf, t, s, a.size, a.size, a.size)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(a),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- the B200 arm
+def measure_dominant_kernel(size, peaks):
+    """The dominant kernel of the step is the tcgen05 ResnetBlock conv (256->256, 3x3, (S/4)^2 pixels; also used
+    for its dgrad).  Time it alone with CUDA events on the launching stream; report algorithmic FLOP/s."""
+    import math
+    from vts_b200 import ops
+    s = size // 4
+    x = torch.randn(1, s, s, 256, device="cuda")
+    w = torch.randn(256, 256, 3, 3, device="cuda") / math.sqrt(2304)
+    _, op = ops.norm_act_pad(x, pad=1, pad_mode=ops.PAD_REFLECT, fmt=ops.FMT_BF16X2)
+    pk = ops.PackedWeights(w, 0, want_f32=False, want_bf16=True)
+    y = torch.empty(1, s, s, 256, device="cuda")
+    for _ in range(5):
+        ops.conv2d_fwd(op, pk, 1, 0, s, s, stats_mode=ops.NORM_INSTANCE, impl=ops.IMPL_TC, out=y)
+    iters = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        ops.conv2d_fwd(op, pk, 1, 0, s, s, stats_mode=ops.NORM_INSTANCE, impl=ops.IMPL_TC, out=y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters  # includes the 1-element stats memset launched by the wrapper (negligible)
+    flops = 2.0 * 9 * 256 * 256 * s * s
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    return {"bound": "tensor", "kernel": "conv_tc_kernel<256,2> (ResnetBlock conv3x3 256->256 @%dx%d)" % (s, s),
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if "bf16_tflops" in peaks else "fallback 1.59 PFLOP/s",
+            "traffic": None, "ms_per_launch": ms,
+            "note": "achieved counts ALGORITHMIC flops; the kernel executes 3 bf16 MMAs per product (hi/lo split for fp32 parity), "
+                    "so tensor-pipe work is 3x: executed %.0f TFLOP/s = %.2f of peak" % (3 * achieved, 3 * achieved / peak)}
+
+
+def run_b200(a):
+    import vts_b200
+    from vts_b200 import _lib
+    from vts_b200.dist import DistContext
+    from oracle import skit_oracle as O  # synthetic batch factory only (seeded inputs of SURVEY.md §8d)
+    ctx = DistContext()
+    torch.cuda.set_device(ctx.local_rank)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    opt = vts_b200.default_options(gpu_ids=[ctx.local_rank])
+    torch.manual_seed(0)
+    model = vts_b200.SinSKITGModel(opt, dist_ctx=ctx if ctx.world_size > 1 else None)
+    ctx.broadcast_params([model.netG, model.netD, model.netD2])
+    batch = O.synthetic_batch(a.size, NT=64, seed=ctx.rank)   # a different (material, augmentation) sample per rank
+    for k in ("S", "I", "M", "T_images", "I_masks"):
+        batch[k] = batch[k].pin_memory()
+
+    def step_resident():
+        model.optimize_parameters(1)
+
+    def step_e2e():
+        model.set_input(batch)
+        model.optimize_parameters(1)
+        return model.get_current_losses()
+
+    model.set_input(batch)
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    # ---- timed region 1: inputs resident in HBM
+    ctx.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(ctx.local_rank) as clk:
+        e0.record()
+        for _ in range(a.steps):
+            step_resident()
+        e1.record()
+        torch.cuda.synchronize()
+    ctx.barrier()
+    launches = _lib.launches - l0
+    t_res = ctx.max_over_ranks(e0.elapsed_time(e1) / 1e3)
+    # ---- timed region 2: end to end through the public API, host inputs
+    step_e2e()
+    ctx.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        losses = step_e2e()
+    e1.record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t0
+    ctx.barrier()
+    t_e2e = ctx.max_over_ranks(max(e0.elapsed_time(e1) / 1e3, t_wall))
+    d2h = 4 * (8 + 3 * 64 + 32)
+    n = ctx.world_size
+    value = n * a.steps / t_res
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": 1e3 * t_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 split operands, fp32 accumulate (fp32-parity tensor-core path); fp32 elsewhere",
+            "data": "synthetic", "config": workload_config(a),
+            "e2e": {"value": n * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(model.h2d_bytes), "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clk.summary(),
+            "losses_last_step": {k: round(v, 5) for k, v in losses.items()}}
+    if ctx.rank == 0:
+        line["roofline"] = measure_dominant_kernel(a.size, peaks)
+        if n == 1 and not a.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            s, nt, nf = a.cpu_sample_size, 16, 8
+            t = oracle_step_time(s, 1, 1, nt, nf, cores)
+            v = (1.0 / t) * (s * s) / float(a.size * a.size)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "CPU oracle train step at %dx%d (NT=%d NF=%d), %.2f s/step, scaled by (%d/%d)^2" % (s, s, nt, nf, t, s, a.size)}
+        print(json.dumps(line), flush=True)
+    ctx.shutdown()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,106 @@
+"""Patch / normal / positional-encoding utilities of the hot path, mirroring
+models/model_utils.py (find_coords_for_patch :23-69, get_patch_in_input :72-405, compute_normal
+:408-428) and thirdparty/mmgeneration/positional_encoding.py (make_grid2d :113-159).
+Coordinate arithmetic stays on the host in float64 NumPy exactly like the reference; the gather
+itself is one coalesced CUDA kernel over all patches (no `input.repeat(NT,1,1,1)`)."""
+import math
+import random as _pyrandom
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def find_coords_for_patch(coords, scale_multiplier=1):
+    """model_utils.py:37-57: rows [ROI_x, ROI_y, ROI_h, ROI_w, patch_crop_size, resize_ratio, crop_x, crop_y];
+    offset = round((ROI + crop / ratio) * mult), cutout = round(patch_crop_size / ratio * mult);
+    np.round (half to even) in float64, then float32 -> int32."""
+    c = np.squeeze(np.asarray(coords, dtype=np.float64))
+    if c.ndim == 1:
+        c = c[None]
+    ox = np.round((c[..., 0] + c[..., -2] / c[..., -3]) * scale_multiplier)
+    oy = np.round((c[..., 1] + c[..., -1] / c[..., -3]) * scale_multiplier)
+    cs = np.round(c[..., -4] / c[..., -3] * scale_multiplier)
+    f = lambda a: np.asarray(a, dtype=np.float32).astype(np.int32)
+    return f(ox), f(oy), f(cs)
+
+
+class _OffsetTable:
+    """Candidate (row, col) offsets of the random-patch mode (model_utils.py:212-222)."""
+
+    def __init__(self, rows, cols):
+        self.rows, self.cols = rows, cols
+
+    def __len__(self):
+        return int(self.rows.shape[0])
+
+    def sample(self, k, rng=_pyrandom):
+        pick = rng.sample(range(len(self)), k)
+        return self.cols[pick].astype(np.int32), self.rows[pick].astype(np.int32)  # (offset_x, offset_y)
+
+
+def random_patch_offset_table(M):
+    """`clamp(conv2d(M, ones(1,1,17,17), padding=1), 0, 1)` then torch.nonzero in row-major order
+    (model_utils.py:212-218); the map is (H-14)x(W-14) and its (row, col) are used directly as
+    (offset_y, offset_x).  Computed on the host with an integral image (exact for 0/1 masks)."""
+    m = np.asarray(M[0, 0].cpu(), dtype=np.float64)
+    H, W = m.shape
+    p = np.zeros((H + 3, W + 3), dtype=np.float64)   # 1 zero halo + leading row/col for the integral image
+    p[2:H + 2, 2:W + 2] = m
+    ii = p.cumsum(0).cumsum(1)
+    oh, ow = H + 2 - 17 + 1, W + 2 - 17 + 1
+    box = ii[17:17 + oh, 17:17 + ow] - ii[0:oh, 17:17 + ow] - ii[17:17 + oh, 0:ow] + ii[0:oh, 0:ow]
+    rows, cols = np.nonzero(box > 0.5)
+    return _OffsetTable(rows, cols)
+
+
+def get_patch_in_input(input, coords=None, sample_size=None, scale_multiplier=1, patch_size=32,
+                       offset_x=None, offset_y=None, M=None, return_offset=False, **unused):
+    """get_patch_in_input (model_utils.py:72-405) for the usages on the hot path: known coords;
+    random offsets inside the mask; caller-supplied offsets.  input: [1, C, H, W] CUDA tensor."""
+    if not input.is_cuda:
+        raise RuntimeError("get_patch_in_input (B200 path) needs a CUDA tensor; there is no CPU fallback")
+    patch_size = patch_size * scale_multiplier
+    if coords is not None:
+        cnp = coords.cpu().numpy() if torch.is_tensor(coords) else np.asarray(coords)
+        assert cnp.shape[0] == 1, "coords should have batch size of 1"
+        ox, oy, cs = find_coords_for_patch(cnp, scale_multiplier)
+    else:
+        assert sample_size is not None
+        if offset_x is None:
+            ox, oy = random_patch_offset_table(M).sample(sample_size)
+        else:
+            ox = np.asarray(offset_x.cpu() if torch.is_tensor(offset_x) else offset_x).reshape(-1).astype(np.int32)
+            oy = np.asarray(offset_y.cpu() if torch.is_tensor(offset_y) else offset_y).reshape(-1).astype(np.int32)
+        cs = np.full((sample_size,), patch_size, dtype=np.int32)
+    if int(cs.max()) != patch_size:
+        raise NotImplementedError("cutout != patch size (bicubic patch resize) is outside the hot path (T_resolution_multiplier = 1, resize_ratio = 1)")
+    dev = input.device
+    out = ops.patch_gather([input.contiguous().float()], torch.from_numpy(ox).to(dev), torch.from_numpy(oy).to(dev), int(patch_size))
+    if return_offset:
+        return out, ox / scale_multiplier, oy / scale_multiplier, cs / scale_multiplier
+    return out
+
+
+def compute_normal(T, scale_nz=0.25):
+    """compute_normal (model_utils.py:418-425) — on the hot path this is fused into the generator head
+    kernel (skit_g_head_fwd); this standalone form serves callers that hold only T (logging)."""
+    n = torch.cat([T[:, 0:1], T[:, 1:2], torch.full_like(T[:, 0:1], scale_nz)], dim=1)
+    return n / n.norm(dim=1, keepdim=True).clamp_min(1e-12)
+
+
+def spe_grid(h, w, emb_dim=4, n=1):
+    """SinusoidalPositionalEmbedding(emb_dim, padding_idx=0).make_grid2d(h, w, n)
+    (positional_encoding.py:61-86,113-159): a constant of (h, w); built once on the host and cached on
+    the device by the model.  Channels: sin/cos of the x position (1..w), then of the y position."""
+    half = emb_dim // 2
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000.0) / (half - 1)))
+
+    def table(length):
+        pos = torch.arange(1, length + 1, dtype=torch.float32)[:, None] * freq[None, :]
+        return torch.cat([torch.sin(pos), torch.cos(pos)], dim=1)
+
+    ex = table(w).t()[None, :, None, :].expand(n, emb_dim, h, w)
+    ey = table(h).t()[None, :, :, None].expand(n, emb_dim, h, w)
+    return torch.cat([ex, ey], dim=1).contiguous()

@@ -1,0 +1,314 @@
+"""SinSKITGModel / SKITGModel on the B200 path: set_input / forward / optimize_parameters / test
+with the reference's method names and loss algebra, run as explicit kernel launches (no autograd).
+
+Reference: models/sinskitG_model.py — forward :1293-1344, optimize_parameters :601-700,
+compute_D1_loss :1346-1407, compute_D2_loss :1409-1617, compute_G1_loss :1660-1726,
+compute_G2_loss :1728-1842, set_input :702-793, optimizers :590-599;  models/skitG_model.py
+(:1284-1336 forward, style code / M_T) is the multi-material twin whose own optimize_parameters is
+broken as shipped — SKITGModel here reuses the sinskitG step.
+LPIPS / vision-aided (CLIP) terms are third-party networks outside the hot path:
+their lambdas must be 0 / False, anything else raises.
+"""
+import argparse
+import math
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import networks, ops
+from .model_utils import find_coords_for_patch, random_patch_offset_table, spe_grid
+
+
+def default_options(**kw):
+    """The options the step reads, with the reference's defaults
+    (models/sinskitG_model.py:50-357, options/base_options.py, options/train_options.py)."""
+    o = dict(
+        model="sinskitG", isTrain=True, gpu_ids=[0],
+        netG="resnet_9blocks", ngf=64, normG="instance", no_dropout=True, no_antialias=False, no_antialias_up=False,
+        netD="multiscale", netD2="multiscale", ndf=64, normD="batch", n_layers_D=3, num_D=3,
+        init_type="xavier", init_gain=0.02, input_nc=1, output_nc=5,
+        use_positional_encoding=True, use_bg_mask=True, use_diffaug=True, diffaugment="bs", use_more_fakeT=True,
+        gan_mode="nonsaturating",
+        lambda_G1_GAN=1.0, lambda_G1_L1=100.0, lambda_G1_lpips=0.0, lambda_G2_GAN=5.0, lambda_G2_L1=10.0,
+        lambda_G2_lpips=0.0, use_vision_aided_loss=False,
+        batch_size=1, batch_size_G2=64, add_fake_T_sample_size=32, scale_nz=0.25, T_resolution_multiplier=1,
+        lr=1e-3, lr_G2=5e-4, beta1=0.0, beta2=0.99, lr_policy="linear", n_epochs=5, n_epochs_decay=400, epoch_count=1,
+        run_full_res_D2=False,  # the reference's visualisation-only netD2(full image) pass (:1495); off on the hot path
+        checkpoints_dir="./checkpoints", name="experiment",
+    )
+    o.update(kw)
+    return argparse.Namespace(**o)
+
+
+class SinSKITGModel:
+    loss_names = ["D_fake_I", "D_real_I", "D_fake_T_concat", "D_more_fake_T", "D_real_T_concat",
+                  "G_GAN", "G_L1", "G2_GAN", "G2_L1"]
+    model_names = ["G", "D", "D2"]
+
+    def __init__(self, opt, dist_ctx=None):
+        self.opt = opt
+        self.isTrain = opt.isTrain
+        self.dist = dist_ctx
+        if not torch.cuda.is_available():
+            raise RuntimeError("SinSKITGModel (B200 path) needs a CUDA device; there is no CPU fallback")
+        dev_index = opt.gpu_ids[0] if len(opt.gpu_ids) else 0
+        self.device = torch.device("cuda", dev_index)
+        torch.cuda.set_device(self.device)
+        if opt.lambda_G1_lpips != 0 or opt.lambda_G2_lpips != 0 or opt.use_vision_aided_loss:
+            raise NotImplementedError("LPIPS / vision-aided losses are third-party networks outside the B200 hot path; "
+                                      "run with --lambda_G1_lpips 0 --lambda_G2_lpips 0 --use_vision_aided_loss False")
+        if opt.T_resolution_multiplier != 1:
+            raise NotImplementedError("T_resolution_multiplier != 1 (real bicubic resampling) is not built")
+        if opt.batch_size != 1:
+            raise NotImplementedError("batch_size is forced to 1 by the reference (sinskitG_model.py:342)")
+        g_in = opt.input_nc + (8 if opt.use_positional_encoding else 0)
+        gpu = [dev_index]
+        self.netG = networks.define_G(g_in, opt.output_nc, opt.ngf, opt.netG, opt.normG, not opt.no_dropout, opt.init_type,
+                                      opt.init_gain, opt.no_antialias, opt.no_antialias_up, gpu, opt)
+        self.netG.flatten_parameters()
+        if self.isTrain:
+            self.netD = networks.define_D(opt.input_nc + 3, opt.ndf, opt.netD, opt.n_layers_D, opt.normD, opt.init_type,
+                                          opt.init_gain, opt.no_antialias, opt.num_D, gpu, opt)
+            self.netD2 = networks.define_D(2 + opt.input_nc + 3 + 1, opt.ndf, opt.netD2, opt.n_layers_D, opt.normD,
+                                           opt.init_type, opt.init_gain, opt.no_antialias, opt.num_D, gpu, opt)
+            for net in (self.netD, self.netD2):
+                if not isinstance(net, networks.MultiscaleDiscriminator):
+                    raise NotImplementedError("the explicit train step is built for netD/netD2 = 'multiscale' (the model default)")
+                net.flatten_parameters()
+            self.step_count = 0
+            self.lr_factor = 1.0
+            self.loss_buf = torch.zeros(16, dtype=torch.float32, device=self.device)
+        self._spe_cache = {}
+        self._losses = {}
+
+    # ------------------------------------------------------------------ data staging
+    def _spe(self, n, h, w):
+        key = (n, h, w)
+        if key not in self._spe_cache:
+            self._spe_cache[key] = spe_grid(h, w, 4, n).to(self.device)
+        return self._spe_cache[key]
+
+    def set_input(self, input, phase="train"):
+        """Host tensors (the dataset dict, sinskitG_model.py:702-793) -> device.  Masking of S / I / T
+        (:724,734,789-790) is done on the host before the single pinned H2D copy of each tensor."""
+        dev = self.device
+        M = input["M"].float()
+        S = input["S"].float() * M if self.opt.use_bg_mask else input["S"].float()
+        n, _, h, w = S.shape
+        host = {"M": M, "real_S": S}
+        if "I" in input:
+            host["real_I"] = input["I"].float() * M if self.opt.use_bg_mask else input["I"].float()
+        pre = "" if phase == "train" else "val_"
+        if self.isTrain and (pre + "T_images") in input:
+            T = input[pre + "T_images"].float()
+            NT = T.shape[1]
+            Im = input[pre + "I_masks"].float().reshape(NT, 1, 32, 32)
+            host["I_masks"] = Im
+            host["real_T"] = T.reshape(NT, 2, 32, 32) * Im
+            ox, oy, _ = find_coords_for_patch(input[pre + "T_coords"].numpy() if torch.is_tensor(input[pre + "T_coords"]) else input[pre + "T_coords"])
+            host["ox"] = torch.from_numpy(ox.astype(np.int32))
+            host["oy"] = torch.from_numpy(oy.astype(np.int32))
+            self.NT = NT
+        self.h2d_bytes = 0
+        for k, v in host.items():
+            v = v.contiguous()
+            if not v.is_pinned():
+                v = v.pin_memory()
+            self.h2d_bytes += v.numel() * v.element_size()
+            setattr(self, k, v.to(dev, non_blocking=True))
+        self.S_pe = self._spe(n, h, w) if self.opt.use_positional_encoding else None
+        self.style_code = input.get("style_code")
+        if self.isTrain and hasattr(self, "real_T"):
+            NT, NF = self.NT, self.opt.add_fake_T_sample_size
+            self.fake_in = torch.zeros(NT, 7, 32, 32, device=dev)
+            self.real_in = torch.zeros(NT, 7, 32, 32, device=dev)
+            self.more_in = torch.ones(NF, 7, 32, 32, device=dev)
+            self.fake_in[:, 6:7] = self.I_masks
+            self.real_in[:, 6:7] = self.I_masks
+            self.real_in[:, 0:2] = self.real_T
+            self._offset_table = random_patch_offset_table(M) if self.opt.use_more_fakeT else None
+        self.image_paths = input.get("S_paths")
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, save=None, rand=None):
+        """sinskitG_model.py:1293-1344: G, channel split, *M, normal, DiffAugment('bs') real + fake, *M."""
+        opt = self.opt
+        save = self.isTrain if save is None else save
+        srcs = [self.real_S] + ([self.S_pe] if self.S_pe is not None else [])
+        (self.fake_I, self.fake_T, self.fake_N), self._g_ctx, _ = self.netG.fwd(
+            srcs, mask=self.M if opt.use_bg_mask else None, scale_nz=opt.scale_nz, save=save)
+        if hasattr(self, "real_I"):
+            if opt.use_diffaug:
+                n = self.real_S.shape[0]
+                if rand is None:  # the reference's torch.rand draws: real (b, s) then fake (b, s)
+                    rand = {k: torch.rand(n, 1, 1, 1).reshape(n) for k in ("real_b", "real_s", "fake_b", "fake_s")}
+                u = {k: torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(n).to(self.device, non_blocking=True) for k, v in rand.items() if k in ("real_b", "real_s", "fake_b", "fake_s")}
+                self.aug_real_I = ops.diffaug_bs_mask(self.real_I, self.M, u["real_b"], u["real_s"])
+                self.aug_fake_I = ops.diffaug_bs_mask(self.fake_I, self.M, u["fake_b"], u["fake_s"])
+            else:
+                self.aug_real_I, self.aug_fake_I = self.real_I, self.fake_I
+        return self.fake_I, self.fake_T, self.fake_N
+
+    def test(self):
+        """sinskitG_model.py:795-807: forward without saving anything for backward."""
+        self.netG.ensure_flat()
+        self.netG.refresh_packs()
+        return self.forward(save=False)
+
+    # ------------------------------------------------------------------ helpers of the step
+    def _allreduce(self, net):
+        if self.dist is not None:
+            self.dist.allreduce_grads(net.flat_grad)
+
+    def _adam(self, net, lr):
+        scale = 1.0 / self.dist.world_size if self.dist is not None else 1.0
+        ops.adam_step(net.flat_param, net.flat_grad, net.exp_avg, net.exp_avg_sq, self.step_count,
+                      lr * self.lr_factor, self.opt.beta1, self.opt.beta2, 1e-8, scale)
+        net.refresh_packs()
+
+    @staticmethod
+    def _gan(preds, sign, loss_slot, gscale=None):
+        """Sum over scales of the per-sample softplus loss; returns the per-scale dpred list if gscale."""
+        dps = []
+        for p in preds:
+            dp = torch.empty_like(p) if gscale is not None else None
+            ops.gan_softplus(p, sign, loss_slot, dp, gscale or 0.0)
+            dps.append(dp)
+        return dps
+
+    # ------------------------------------------------------------------ the train step
+    def optimize_parameters(self, epoch=None, rand=None):
+        """sinskitG_model.py:601-700.  rand (optional, for parity tests): dict with the DiffAugment draws
+        real_b/real_s/fake_b/fake_s and the NF random fake-patch offsets fake_ox/fake_oy; drawn from
+        torch / random like the reference when absent."""
+        opt = self.opt
+        G, D, D2 = self.netG, self.netD, self.netD2
+        NT, NF = self.NT, opt.add_fake_T_sample_size
+        n = self.real_S.shape[0]
+        self.step_count += 1
+        for net in (G, D, D2):
+            net.ensure_flat()
+        if self.step_count == 1:
+            for net in (G, D, D2):
+                net.refresh_packs()
+        self.forward(save=True, rand=rand)
+        fake_I, fake_T = self.fake_I, self.fake_T
+        ox, oy = self.ox, self.oy
+        # compute_additional_output (:1268-1291): patch gathers, written straight into the D2 input buffers
+        fake_T_p = ops.patch_gather([fake_T], ox, oy, 32)
+        ops.patch_gather([fake_T, self.real_S, self.aug_fake_I], ox, oy, 32, ctot=7, dst=self.fake_in)
+        ops.patch_gather([self.real_S, self.aug_real_I], ox, oy, 32, ctot=7, coffs=[2, 3], dst=self.real_in)
+        L = torch.zeros(8 + 3 * NT + NF, dtype=torch.float32, device=self.device)
+        sl = dict(D_fake=L[0:1], D_real=L[1:2], G_GAN=L[2:3], G_L1=L[3:4], G2_L1=L[4:5],
+                  D2_fake=L[8:8 + NT], D2_real=L[8 + NT:8 + 2 * NT], G2_GAN=L[8 + 2 * NT:8 + 3 * NT], D2_more=L[8 + 3 * NT:])
+
+        # ---- D1 step (:648-653, compute_D1_loss): un-augmented fake/real, conditioned on the sketch
+        D.zero_grad()
+        pf, cf = D.fwd([self.real_S, fake_I])
+        dpf = self._gan(pf, +1.0, sl["D_fake"], 0.5 * opt.lambda_G1_GAN / n)
+        D.bwd(cf, dpf)
+        del cf
+        pr, cr = D.fwd([self.real_S, self.real_I])
+        dpr = self._gan(pr, -1.0, sl["D_real"], 0.5 * opt.lambda_G1_GAN / n)
+        D.bwd(cr, dpr)
+        del cr
+        self._allreduce(D)
+        self._adam(D, opt.lr)
+
+        # ---- D2 step (:654-667, compute_D2_loss): touch patches conditioned on sketch + augmented image + mask
+        D2.zero_grad()
+        p2f, c2f = D2.fwd([self.fake_in])
+        D2.bwd(c2f, self._gan(p2f, +1.0, sl["D2_fake"], 0.5 * opt.lambda_G2_GAN / NT))
+        del c2f
+        if opt.run_full_res_D2:  # visualisation only in the reference (:1495-1500); updates BN running stats
+            self.pred_fake_T_full = D2.fwd([fake_T, self.real_S, self.aug_fake_I, self.M], save=False)[0][-1]
+        if opt.use_more_fakeT:
+            if rand is not None and "fake_ox" in rand:
+                fox, foy = np.asarray(rand["fake_ox"], dtype=np.int32), np.asarray(rand["fake_oy"], dtype=np.int32)
+            else:
+                fox, foy = self._offset_table.sample(NF)
+            fox_d = torch.from_numpy(fox).to(self.device, non_blocking=True)
+            foy_d = torch.from_numpy(foy).to(self.device, non_blocking=True)
+            ops.patch_gather([fake_T, self.real_S, fake_I], fox_d, foy_d, 32, ctot=7, dst=self.more_in)
+            p2m, c2m = D2.fwd([self.more_in])
+            D2.bwd(c2m, self._gan(p2m, +1.0, sl["D2_more"], 0.5 * opt.lambda_G2_GAN / NF))
+            del c2m
+        p2r, c2r = D2.fwd([self.real_in])
+        D2.bwd(c2r, self._gan(p2r, -1.0, sl["D2_real"], 0.5 * opt.lambda_G2_GAN / NT))
+        del c2r
+        self._allreduce(D2)
+        self._adam(D2, opt.lr_G2)
+
+        # ---- G step (:680-694): GAN through the updated (frozen) D, L1, patch L1; G2 GAN is value-only
+        G.zero_grad()
+        pg, cg = D.fwd([self.real_S, fake_I])
+        dpg = self._gan(pg, -1.0, sl["G_GAN"], opt.lambda_G1_GAN / n)
+        dI = D.bwd(cg, dpg, need_wgrad=False, input_slice=(opt.input_nc, 3))
+        del cg
+        ops.l1_loss(fake_I, self.real_I, opt.lambda_G1_L1 / fake_I.numel(), sl["G_L1"], dI, opt.lambda_G1_L1 / fake_I.numel(), accumulate=True)
+        pg2, _ = D2.fwd([self.fake_in], save=False)           # detached clone in the reference (:1751,1781)
+        self._gan(pg2, -1.0, sl["G2_GAN"])
+        per_patch = fake_T_p.numel() // NT
+        dTp = torch.empty_like(fake_T_p)
+        ops.l1_loss(fake_T_p, self.real_T, opt.lambda_G2_L1 / per_patch / n, sl["G2_L1"], dTp, opt.lambda_G2_L1 / per_patch / n)
+        dT = torch.zeros_like(fake_T)
+        ops.patch_scatter_add(dTp, 0, 2, ox, oy, dT)
+        G.bwd(self._g_ctx, dI, dT)
+        self._g_ctx = None
+        self._allreduce(G)
+        self._adam(G, opt.lr)
+        self._loss_raw = (L, NT, NF)
+        return L
+
+    def get_current_losses(self):
+        """Device -> host read of the step's loss scalars (the reference does ~12 .item() syncs per step,
+        sinskitG_model.py:1389-1838; here it is one D2H copy, only when somebody asks)."""
+        L, NT, NF = self._loss_raw
+        v = L.detach().cpu().numpy()
+        o = self.opt
+        return dict(
+            D_fake_I=float(v[0]) * o.lambda_G1_GAN, D_real_I=float(v[1]) * o.lambda_G1_GAN,
+            G_GAN=float(v[2]) * o.lambda_G1_GAN, G_L1=float(v[3]), G2_L1=float(v[4]),
+            D_fake_T_concat=float(v[8:8 + NT].mean()) * o.lambda_G2_GAN,
+            D_real_T_concat=float(v[8 + NT:8 + 2 * NT].mean()) * o.lambda_G2_GAN,
+            G2_GAN=float(v[8 + 2 * NT:8 + 3 * NT].sum()) * o.lambda_G2_GAN,
+            D_more_fake_T=float(v[8 + 3 * NT:].mean()) * o.lambda_G2_GAN if NF else 0.0,
+        )
+
+    def update_learning_rate(self, epoch):
+        """get_scheduler('linear') (networks.py:161-165), stepped once per epoch (train.py:204-205)."""
+        o = self.opt
+        self.lr_factor = 1.0 - max(0, epoch + o.epoch_count - o.n_epochs) / float(o.n_epochs_decay + 1)
+
+    # ------------------------------------------------------------------ checkpoints (base_model.py:205-304)
+    def save_networks(self, tag):
+        d = os.path.join(self.opt.checkpoints_dir, self.opt.name)
+        os.makedirs(d, exist_ok=True)
+        for name in self.model_names:
+            net = getattr(self, "net" + name, None)
+            if net is not None:
+                torch.save({k: v.detach().cpu().clone() for k, v in net.state_dict().items()},
+                           os.path.join(d, "%s_net_%s.pth" % (tag, name)))
+
+    def load_networks(self, tag):
+        d = os.path.join(self.opt.checkpoints_dir, self.opt.name)
+        for name in self.model_names:
+            net = getattr(self, "net" + name, None)
+            path = os.path.join(d, "%s_net_%s.pth" % (tag, name))
+            if net is None:
+                continue
+            if not os.path.exists(path):
+                raise FileNotFoundError(path)  # the reference silently continues (base_model.py:264-267); we fail loudly
+            sd = torch.load(path, map_location="cpu")
+            sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+            net.load_state_dict(sd)
+            net.refresh_packs()
+
+
+class SKITGModel(SinSKITGModel):
+    """skitG: multi-material twin (models/skitG_model.py).  Adds a CLIP style code that only the U-Net
+    generators consume (networks.py:1600-1633); the resnet generators accept and ignore it.  M_T equals M
+    at T_resolution_multiplier = 1 (skitG_model.py:687,1313)."""
+    pass
