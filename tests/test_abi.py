@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/skit_b200.h declares;
+the ctypes table binds exactly that set.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "skit_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(skit_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    import __graft_entry__ as ge
+    return ge.build()
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_symbols()
+    assert len(names) >= 30
+    for must in ("skit_conv2d_fwd", "skit_conv2d_wgrad", "skit_norm_act_pad", "skit_patch_gather", "skit_patchnce", "skit_adam_step"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for name in declared_symbols():
+        assert hasattr(lib, name), "libskit_b200.so does not export %s" % name
+    lib.skit_built_arch.restype = ctypes.c_int
+    assert lib.skit_built_arch() == 100
+    lib.skit_last_error.restype = ctypes.c_char_p
+    assert lib.skit_last_error() == b""
+
+
+def test_ctypes_table_matches_header(lib_path):
+    import vts_b200
+    bound = set(vts_b200._lib.SIGNATURES) | set(vts_b200._lib._NO_RC)
+    assert bound == set(declared_symbols())
+    vts_b200._lib.load()
+
+
+def test_sass_is_blackwell_native(lib_path):
+    """The tensor-core kernel must contain tcgen05 MMA / TMA / TMEM instructions (UTC*MMA, UTMALDG, LDTM)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", lib_path], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+    assert "sm_100a" in sass
