@@ -76,6 +76,8 @@ int skit_built_arch(void);
  * mode 1: stride-1 dgrad pack Wd[((k-1-ky)*k+(k-1-kx))*co + o][c] = w[o][c][ky][kx]
  *         (conv of the zero-padded output gradient with the flipped, transposed filter)
  * mode 2: gather dgrad pack   Wg[(ky*k+kx)*co + o][c]      = w[o][c][ky][kx]
+ * mode 3: stride-2 phase dgrad pack (k even): tap = phase*(k/2)^2 + (k/2-1-ky/2)*(k/2) + (k/2-1-kx/2),
+ *         phase = (ky%2)*2 + kx%2;  Wp[tap*co + o][c] = w[o][c][ky][kx]   (see skit_conv2d_dgrad_s2)
  * f32 / hi / lo may each be NULL to skip that product.  hi/lo are [tap][N][K] K-major bf16.  */
 int skit_pack_conv_weights(const float* w, int co, int ci, int k, int mode,
                            float* f32, void* hi, void* lo, void* stream);
@@ -101,11 +103,21 @@ int skit_conv2d_fwd(const skit_operand* x, const skit_weights* w, int stride, in
 int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, int co,
                              const skit_weights* wg, int stride, int hp, int wp, float* dx, void* stream);
 
-/* Weight gradient: dWf[(tap*ci+c)][o] += sum_{n,oy,ox} dy[n][oy][ox][o] * x[n][org+oy*s+ky][org+ox*s+kx][c]
- * dy is an operand (fp32 or bf16x2) read with halo offset dy_org; dWf fp32 (forward-pack layout),
- * must be zeroed by the caller (split-K accumulation with atomics).  dbias (may be NULL): [co] += sum dy. */
+/* Input gradient of a stride-2, even-k conv on the tensor cores (PatchGAN k4 s2 layers, networks.py:1706-1716):
+ * the four parities (iy%2, ix%2) of dx are four stride-1 (k/2 x k/2) convolutions of dy — which must be a
+ * bf16x2 operand zero-haloed by dy_pad = k/2-1 — with the mode-3 sub-filters; each writes its interleaved
+ * quarter of dx (NHWC fp32 [n][hp][wp][ci], every element written exactly once). */
+int skit_conv2d_dgrad_s2(const skit_operand* dy, int dy_pad, const skit_weights* wp, int k,
+                         int ho, int wo, int hp, int wp_, float* dx, void* stream);
+
+/* Weight gradient (autograd of F.conv2d w.r.t. weight and bias):
+ *   dw[o][c][ky][kx] += sum_{n,oy,ox} dy[n][oy][ox][o] * x[n][org+oy*s+ky][org+ox*s+kx][c]
+ * dy is an operand (fp32 or bf16x2) read with halo offset dy_org.  `scratch` is k*k*ci*co floats, ZEROED by
+ * the caller: the split-K partial sums land there (atomics) before being folded into dw (reference layout,
+ * accumulated).  dbias (may be NULL): [co] += sum dy.  tcgen05 path when both operands are bf16x2, channel
+ * counts are multiples of 64 and one of them of 128 (both GEMM operands MN-major straight from NHWC). */
 int skit_conv2d_wgrad(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
-                      int k, int stride, int ho, int wo, float* dwf, float* dbias, int impl, void* stream);
+                      int k, int stride, int ho, int wo, float* scratch, float* dw, float* dbias, int impl, void* stream);
 
 /* ---------------------------------------------------------------- normalisation + activation + halo
  * Turn double (sum, sumsq) into float (mean, rstd), eps 1e-5, biased variance

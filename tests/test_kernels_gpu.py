@@ -112,6 +112,12 @@ def test_conv_fwd_tcgen05(V, ci, co, k, pad, mode, hw, n):
     (128, 64, 3, 1, 1, 0, "instance", 1, (64, 64), 1, True, 3),
     (256, 256, 3, 1, 1, 1, "instance", 1, (16, 16), 1, True, 1),
     (256, 128, 3, 1, 1, 0, "instance", 1, (32, 32), 1, True, 1),
+    (64, 128, 4, 2, 2, 0, "batch", 2, (32, 32), 3, True, 1),      # PatchGAN k4 s2 on tcgen05 (TMA element strides)
+    (128, 256, 4, 2, 2, 0, "batch", 2, (33, 29), 2, True, 1),     # odd sizes: parity sub-convs read past dy's halo
+    (64, 64, 4, 2, 2, 0, "none", 2, (18, 40), 1, True, 2),
+    (512, 1, 4, 1, 2, 0, "none", 0, (10, 11), 2, False, 1),       # thin-N head (PatchGAN 512 -> 1)
+    (64, 5, 7, 1, 3, 1, "none", 0, (24, 21), 1, False, 1),        # thin-N head (generator 64 -> 5)
+    (4, 64, 4, 2, 2, 0, "none", 2, (21, 20), 2, False, 1),        # thin-N gather dgrad path (input gradient of a 4-ch stem)
 ])
 def test_conv_stage_fwd_bwd(V, ci, co, k, stride, pad, mode, norm, act, hw, n, tc, out_pad):
     """[pad -> conv -> norm -> act -> next pad] forward and the explicit backward
@@ -130,7 +136,7 @@ def test_conv_stage_fwd_bwd(V, ci, co, k, stride, pad, mode, norm, act, hw, n, t
         y = F.batch_norm(raw, None, None, gamma, beta, training=True, eps=1e-5)
     else:
         y = raw
-    y = F.relu(y) if act == 1 else F.leaky_relu(y, 0.2)
+    y = F.relu(y) if act == 1 else (F.leaky_relu(y, 0.2) if act == 2 else y)
     out_mode = 1  # the next layer's reflect halo
     yp = torch_pad(y, out_pad, out_mode)
     R = torch.randn(yp.shape, generator=g)

@@ -37,7 +37,8 @@ SIGNATURES = {
     "skit_unpack_conv_wgrad": [_P, _I, _I, _I, _P, _I, _P],
     "skit_conv2d_fwd": [_OP, _WT, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "skit_conv2d_dgrad_gather": [_P, _I, _I, _I, _I, _WT, _I, _I, _I, _P, _P],
-    "skit_conv2d_wgrad": [_OP, _I, _OP, _I, _I, _I, _I, _I, _P, _P, _I, _P],
+    "skit_conv2d_dgrad_s2": [_OP, _I, _WT, _I, _I, _I, _I, _I, _P, _P],
+    "skit_conv2d_wgrad": [_OP, _I, _OP, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "skit_stats_finalize": [_P, _I, _I, _D, _F, _P, _P, _P, _F, _P],
     "skit_norm_act_pad": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _OP, _I, _I, _P],
     "skit_act_norm_bwd_reduce": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P],

@@ -21,6 +21,8 @@ struct ConvP {
     int K;                // reduction length
     int M;                // rows per image (fwd: ho*wo; dgrad: hp*wp)
     int arows;            // dgrad: channels of dy (co)
+    int flat;             // 1: rows run over the whole batch (n*M), grid.z == 1 (batch statistics only)
+    int n_img;
 };
 
 constexpr int BM = 128, BN = 64, BK = 16;
@@ -31,19 +33,23 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
-    const int n = blockIdx.z;
+    const int nz = blockIdx.z;
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int kk = tid & 15, rg = tid >> 4;
     const int ty = tid >> 4, tx = tid & 15;
+    const long long Mtot = p.flat ? (long long)p.n_img * p.M : p.M;
 
     long long base[8];
-    int ry[8], rx[8];
+    int ry[8], rx[8], rn[8];
     bool rvalid[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         int m = m0 + rg + 16 * i;
-        rvalid[i] = m < p.M;
+        rvalid[i] = m < Mtot;
+        int n = nz;
+        if (p.flat) { n = m / p.M; m -= n * p.M; }
+        rn[i] = n;
         if (MODE == 0) {
             int oy = m / p.wo, ox = m - oy * p.wo;
             base[i] = (((long long)n * p.hp + p.org + oy * p.stride) * p.wp + p.org + ox * p.stride) * p.ci;
@@ -89,7 +95,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
                     if (ty_ >= 0 && tx_ >= 0) {
                         int oy = ty_ / p.stride, ox = tx_ / p.stride;
                         if (oy * p.stride == ty_ && ox * p.stride == tx_ && oy < p.ho && ox < p.wo)
-                            v = __ldg(p.x0 + (((long long)n * p.ho + oy) * p.wo + ox) * p.arows + o);
+                            v = __ldg(p.x0 + (((long long)rn[i] * p.ho + oy) * p.wo + ox) * p.arows + o);
                     }
                 }
                 As[kk][rg + 16 * i] = v;
@@ -125,13 +131,13 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         int m = m0 + ty * 8 + i;
-        if (m >= p.M) continue;
+        if (m >= Mtot) continue;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int col = n0 + tx * 4 + j;
             if (col >= p.ncol) continue;
             float v = acc[i][j] + (p.bias ? p.bias[col] : 0.f);
-            p.y[((long long)n * p.M + m) * p.ncol + col] = v;
+            p.y[((long long)(p.flat ? 0 : nz) * p.M + m) * p.ncol + col] = v;
             s[j] += v; q[j] += v * v;
         }
     }
@@ -146,11 +152,103 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
         }
         __syncthreads();
         if (tid < BN && n0 + tid < p.ncol) {
-            double* dst = p.stats + ((long long)(p.stats_per_n ? n : 0) * p.ncol + n0 + tid) * 2;
+            double* dst = p.stats + ((long long)(p.stats_per_n ? nz : 0) * p.ncol + n0 + tid) * 2;
             atomicAdd(dst, (double)red[tid]);
             atomicAdd(dst + 1, (double)red[BN + tid]);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------- thin-N convolution
+// ncol <= 8 (generator head 64->5, PatchGAN head 512->1, input gradients of the 4/7-channel PatchGAN
+// stems): a 128x64 GEMM tile would waste >90% of its columns, so one warp owns PIX output rows,
+// its lanes stride over the reduction (coalesced 128 B channel runs), and the NOUT x PIX partial
+// sums are combined with warp shuffles.  Requires the per-tap channel count to be a multiple of 32.
+template <int MODE, int FMT, int NOUT, int PIX>
+__global__ void __launch_bounds__(256) conv_thin_kernel(ConvP p, int n_img, int groups_per_row) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int rows_y = (MODE == 0) ? p.ho : p.hp;
+    const long long total = (long long)n_img * rows_y * groups_per_row;
+    if (warp >= total) return;
+    const int gx = (int)(warp % groups_per_row);
+    long long t = warp / groups_per_row;
+    const int y = (int)(t % rows_y);
+    const int n = (int)(t / rows_y);
+    const int x0 = gx * PIX;
+    const int row_w = (MODE == 0) ? p.wo : p.wp;
+    const int ch = (MODE == 0) ? p.ci : p.arows;  // channels per tap on the reduction side
+
+    float acc[PIX][NOUT];
+#pragma unroll
+    for (int i = 0; i < PIX; i++)
+#pragma unroll
+        for (int j = 0; j < NOUT; j++) acc[i][j] = 0.f;
+
+    for (int ky = 0; ky < p.k; ky++) {
+        for (int kx = 0; kx < p.k; kx++) {
+            long long abase[PIX];
+            bool av[PIX];
+#pragma unroll
+            for (int i = 0; i < PIX; i++) {
+                const int x = x0 + i;
+                av[i] = x < row_w;
+                if (MODE == 0) {
+                    abase[i] = (((long long)n * p.hp + p.org + y * p.stride + ky) * p.wp + p.org + x * p.stride + kx) * p.ci;
+                } else {
+                    const int ty_ = y - ky, tx_ = x - kx;
+                    const int oy = ty_ / p.stride, ox = tx_ / p.stride;
+                    av[i] = av[i] && ty_ >= 0 && tx_ >= 0 && oy * p.stride == ty_ && ox * p.stride == tx_ && oy < p.ho && ox < p.wo;
+                    abase[i] = (((long long)n * p.ho + oy) * p.wo + ox) * p.arows;
+                }
+            }
+            const float* wtap = p.w + (long long)(ky * p.k + kx) * ch * p.ncol;
+            for (int c0 = 0; c0 < ch; c0 += 32) {
+                const int c = c0 + lane;
+                float wv[NOUT];
+#pragma unroll
+                for (int j = 0; j < NOUT; j++) wv[j] = (j < p.ncol) ? __ldg(wtap + (long long)c * p.ncol + j) : 0.f;
+#pragma unroll
+                for (int i = 0; i < PIX; i++) {
+                    float a = 0.f;
+                    if (av[i]) {
+                        if (FMT == SKIT_FMT_F32) a = __ldg(p.x0 + abase[i] + c);
+                        else a = __bfloat162float(p.xh[abase[i] + c]) + __bfloat162float(p.xl[abase[i] + c]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NOUT; j++) acc[i][j] = fmaf(a, wv[j], acc[i][j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PIX; i++)
+#pragma unroll
+        for (int j = 0; j < NOUT; j++) acc[i][j] = warp_sum(acc[i][j]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < PIX; i++) {
+            const int x = x0 + i;
+            if (x >= row_w) continue;
+            float* dst = p.y + (((long long)n * rows_y + y) * row_w + x) * p.ncol;
+#pragma unroll
+            for (int j = 0; j < NOUT; j++)
+                if (j < p.ncol) dst[j] = acc[i][j] + (p.bias ? p.bias[j] : 0.f);
+        }
+    }
+}
+
+template <int MODE, int FMT>
+static int launch_thin(const ConvP& p, int n_img, cudaStream_t st) {
+    constexpr int PIX = (MODE == 0) ? 4 : 1;
+    const int row_w = (MODE == 0) ? p.wo : p.wp, rows_y = (MODE == 0) ? p.ho : p.hp;
+    const int gpr = cdiv(row_w, PIX);
+    const long long warps = (long long)n_img * rows_y * gpr;
+    const int blocks = (int)cdivll(warps, 8);
+    if (p.ncol <= 1) conv_thin_kernel<MODE, FMT, 1, PIX><<<blocks, 256, 0, st>>>(p, n_img, gpr);
+    else if (p.ncol <= 4) conv_thin_kernel<MODE, FMT, 4, PIX><<<blocks, 256, 0, st>>>(p, n_img, gpr);
+    else conv_thin_kernel<MODE, FMT, 8, PIX><<<blocks, 256, 0, st>>>(p, n_img, gpr);
+    return check_launch("conv_thin_kernel");
 }
 
 // ---------------------------------------------------------------------------------- wgrad
@@ -282,8 +380,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci,
             tap = (k - 1 - ky) * k + (k - 1 - kx);
             fidx = ((long long)tap * co + o) * ci + c;
             bidx = ((long long)tap * ci + c) * co + o;
-        } else {  // gather dgrad: K = (tap, o), N = c
+        } else if (mode == 2) {  // gather dgrad: K = (tap, o), N = c
             tap = ky * k + kx;
+            fidx = ((long long)tap * co + o) * ci + c;
+            bidx = ((long long)tap * ci + c) * co + o;
+        } else {  // stride-2 phase dgrad: phase (ky%2, kx%2), flipped (k/2 x k/2) sub-filter; K = o, N = c
+            const int kh = k / 2;
+            const int phase = (ky & 1) * 2 + (kx & 1);
+            tap = phase * kh * kh + (kh - 1 - ky / 2) * kh + (kh - 1 - kx / 2);
             fidx = ((long long)tap * co + o) * ci + c;
             bidx = ((long long)tap * ci + c) * co + o;
         }
@@ -296,13 +400,15 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci,
     }
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int co, int ci, int k, float* dw, int accumulate) {
+// layout 0: dwf[(tap*ci + c)*co + o]   layout 1: dwf[(tap*co + o)*ci + c]
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int co, int ci, int k, float* dw, int accumulate, int layout) {
     const long long total = (long long)co * ci * k * k;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int kx = i % k; long long t = i / k;
         int ky = t % k; t /= k;
         int c = t % ci; int o = t / ci;
-        float v = dwf[((long long)(ky * k + kx) * ci + c) * co + o];
+        const long long tap = ky * k + kx;
+        float v = layout == 0 ? dwf[(tap * ci + c) * co + o] : dwf[(tap * co + o) * ci + c];
         dw[i] = accumulate ? dw[i] + v : v;
     }
 }
@@ -315,7 +421,13 @@ int conv_fwd_simt(const skit_operand* x, const skit_weights* w, int stride, int 
     p.w = w->f32; p.bias = bias; p.y = y; p.stats = stats; p.stats_per_n = stats_mode == SKIT_NORM_INSTANCE;
     p.k = w->k; p.stride = stride; p.org = org; p.ho = ho; p.wo = wo;
     p.ncol = w->co; p.K = w->k * w->k * w->ci; p.M = ho * wo; p.arows = 0;
-    dim3 grid(cdiv(p.M, BM), cdiv(p.ncol, BN), x->n);
+    if (p.ncol <= 8 && p.ci % 32 == 0 && !stats) {
+        if (x->fmt == SKIT_FMT_F32) return launch_thin<0, SKIT_FMT_F32>(p, x->n, st);
+        return launch_thin<0, SKIT_FMT_BF16X2>(p, x->n, st);
+    }
+    p.n_img = x->n;
+    p.flat = (x->n > 1 && p.M < 4 * BM && !p.stats_per_n) ? 1 : 0;  // many small images: tile over the whole batch
+    dim3 grid(p.flat ? cdiv(x->n * p.M, BM) : cdiv(p.M, BM), cdiv(p.ncol, BN), p.flat ? 1 : x->n);
     if (x->fmt == SKIT_FMT_F32) conv_simt_kernel<0, SKIT_FMT_F32><<<grid, 256, 0, st>>>(p);
     else conv_simt_kernel<0, SKIT_FMT_BF16X2><<<grid, 256, 0, st>>>(p);
     return check_launch("conv_simt_kernel<fwd>");
@@ -327,7 +439,7 @@ using namespace skit;
 
 extern "C" int skit_pack_conv_weights(const float* w, int co, int ci, int k, int mode,
                                       float* f32, void* hi, void* lo, void* stream) {
-    SKIT_REQUIRE(w && co > 0 && ci > 0 && k > 0 && mode >= 0 && mode <= 2, "pack_conv_weights: bad arguments");
+    SKIT_REQUIRE(w && co > 0 && ci > 0 && k > 0 && mode >= 0 && mode <= 3 && (mode != 3 || k % 2 == 0), "pack_conv_weights: bad arguments");
     SKIT_REQUIRE((hi == nullptr) == (lo == nullptr), "pack_conv_weights: hi and lo must be given together");
     long long total = (long long)co * ci * k * k;
     int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
@@ -335,12 +447,16 @@ extern "C" int skit_pack_conv_weights(const float* w, int co, int ci, int k, int
     return check_launch("pack_weights_kernel");
 }
 
-extern "C" int skit_unpack_conv_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, void* stream) {
-    SKIT_REQUIRE(dwf && dw && co > 0 && ci > 0 && k > 0, "unpack_conv_wgrad: bad arguments");
+static int unpack_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, int layout, cudaStream_t st) {
     long long total = (long long)co * ci * k * k;
     int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
-    unpack_wgrad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dwf, co, ci, k, dw, accumulate);
+    unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(dwf, co, ci, k, dw, accumulate, layout);
     return check_launch("unpack_wgrad_kernel");
+}
+
+extern "C" int skit_unpack_conv_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, void* stream) {
+    SKIT_REQUIRE(dwf && dw && co > 0 && ci > 0 && k > 0, "unpack_conv_wgrad: bad arguments");
+    return unpack_wgrad(dwf, co, ci, k, dw, accumulate, 0, as_stream(stream));
 }
 
 extern "C" int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, int co,
@@ -353,20 +469,25 @@ extern "C" int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, 
     p.w = wg->f32; p.bias = nullptr; p.y = dx; p.stats = nullptr;
     p.k = wg->k; p.stride = stride; p.org = 0; p.ho = ho; p.wo = wo;
     p.ncol = wg->co; p.K = wg->k * wg->k * co; p.M = hp * wp; p.arows = co;
-    dim3 grid(cdiv(p.M, BM), cdiv(p.ncol, BN), n);
+    if (p.ncol <= 8 && co % 32 == 0) return launch_thin<1, SKIT_FMT_F32>(p, n, as_stream(stream));
+    p.n_img = n;
+    p.flat = (n > 1 && p.M < 4 * BM) ? 1 : 0;
+    dim3 grid(p.flat ? cdiv(n * p.M, BM) : cdiv(p.M, BM), cdiv(p.ncol, BN), p.flat ? 1 : n);
     conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
     return check_launch("conv_simt_kernel<dgrad>");
 }
 
 namespace skit {
 int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org, int k, int stride,
-             int ho, int wo, float* dwf, cudaStream_t st);  // tc_wgrad.cu
+             int ho, int wo, float* partial, int* layout, cudaStream_t st);  // tc_wgrad.cu
 bool wgrad_tc_eligible(const skit_operand* x, const skit_operand* dy, int k, int stride, int ho, int wo);
 }
 
 extern "C" int skit_conv2d_wgrad(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
-                                 int k, int stride, int ho, int wo, float* dwf, float* dbias, int impl, void* stream) {
-    SKIT_REQUIRE(x && dy && dwf && x->p0 && dy->p0, "conv2d_wgrad: null pointer");
+                                 int k, int stride, int ho, int wo, float* scratch, float* dw, float* dbias, int impl, void* stream) {
+    SKIT_REQUIRE(x && dy && scratch && dw && x->p0 && dy->p0, "conv2d_wgrad: null pointer");
+    float* dwf = scratch;
+    int layout = 0;
     SKIT_REQUIRE(x->n == dy->n, "conv2d_wgrad: batch mismatch");
     cudaStream_t st = as_stream(stream);
     const int n = x->n, co = dy->c, ci = x->c, P = ho * wo;
@@ -376,7 +497,7 @@ extern "C" int skit_conv2d_wgrad(const skit_operand* x, int org, const skit_oper
         return SKIT_ERR_UNSUPPORTED;
     }
     if (tc) {
-        int rc = wgrad_tc(x, org, dy, dy_org, k, stride, ho, wo, dwf, st);
+        int rc = wgrad_tc(x, org, dy, dy_org, k, stride, ho, wo, dwf, &layout, st);
         if (rc) return rc;
     } else {
         WgradP p{};
@@ -396,6 +517,10 @@ extern "C" int skit_conv2d_wgrad(const skit_operand* x, int org, const skit_oper
         else if (dy->fmt == SKIT_FMT_F32) wgrad_simt_kernel<1, 0><<<grid, 256, 0, st>>>(p);
         else wgrad_simt_kernel<1, 1><<<grid, 256, 0, st>>>(p);
         int rc = check_launch("wgrad_simt_kernel");
+        if (rc) return rc;
+    }
+    {
+        int rc = unpack_wgrad(dwf, co, ci, k, dw, 1, layout, st);
         if (rc) return rc;
     }
     if (dbias) {

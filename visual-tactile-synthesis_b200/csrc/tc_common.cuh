@@ -50,8 +50,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// Bounded wait: a byte-count / descriptor mistake would otherwise hang the GPU; after ~2^24 failed
+// probes (each probe suspends in hardware for a while) the kernel traps and the launch reports an error.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins == (1u << 24)) __trap();
     }
 }
 

@@ -58,9 +58,13 @@ int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 struct TcConvP {
     int k, kc;        // filter size, Ci/64
     int org;          // halo origin offset
+    int stride;       // input stride (TMA elementStrides do the striding)
+    int tap_base;     // first tap of this launch inside the packed filter (phase packs)
     int ho, wo, co;
     int tw, th;       // pixel patch (tw*th == 128)
     int tiles_x;
+    // output placement: y[n][oy*osy + ooy][ox*osx + oox][co] inside an [OH][OW] map (phase-wise dgrad writes)
+    int OH, OW, osy, osx, ooy, oox;
     const float* bias;
     float* y;
     double* stats;
@@ -115,10 +119,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int tap = it / p.kc, c0 = (it - tap * p.kc) * 64;
             const int ky = tap / p.k, kx = tap - ky * p.k;
             const uint32_t sa = smem0 + s * STAGE_BYTES;
-            tma_load_4d(sa, &tmA_hi, full_bar(s), c0, p.org + x0 + kx, p.org + y0 + ky, n);
-            tma_load_4d(sa + A_BYTES, &tmA_lo, full_bar(s), c0, p.org + x0 + kx, p.org + y0 + ky, n);
-            tma_load_3d(sa + 2 * A_BYTES, &tmW_hi, full_bar(s), c0, n0, tap);
-            tma_load_3d(sa + 2 * A_BYTES + W_BYTES, &tmW_lo, full_bar(s), c0, n0, tap);
+            const int cx = p.org + x0 * p.stride + kx, cy = p.org + y0 * p.stride + ky;
+            tma_load_4d(sa, &tmA_hi, full_bar(s), c0, cx, cy, n);
+            tma_load_4d(sa + A_BYTES, &tmA_lo, full_bar(s), c0, cx, cy, n);
+            tma_load_3d(sa + 2 * A_BYTES, &tmW_hi, full_bar(s), c0, n0, p.tap_base + tap);
+            tma_load_3d(sa + 2 * A_BYTES + W_BYTES, &tmW_lo, full_bar(s), c0, n0, p.tap_base + tap);
         }
     } else if (warp == 1 && lane == 0) {
         // ---------------- MMA issuer
@@ -153,8 +158,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int r = warp * 32 + lane;
         const int ty = r / p.tw, tx = r - ty * p.tw;
         const int oy = y0 + ty, ox = x0 + tx;
-        const bool valid = oy < p.ho && ox < p.wo;
-        float* yrow = p.y + (((long long)n * p.ho + oy) * p.wo + ox) * p.co + n0;
+        const int py = oy * p.osy + p.ooy, px = ox * p.osx + p.oox;
+        const bool valid = oy < p.ho && ox < p.wo && py < p.OH && px < p.OW;
+        float* yrow = p.y + (((long long)n * p.OH + py) * p.OW + px) * p.co + n0;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             float v[32];
@@ -220,55 +226,63 @@ static int launch_conv_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
 }  // namespace tc
 
 bool conv_tc_eligible(const skit_operand* x, const skit_weights* w, int stride) {
-    return x->fmt == SKIT_FMT_BF16X2 && w->hi && w->lo && stride == 1 && x->c % 64 == 0 && w->co % 64 == 0 && w->ci == x->c;
+    return x->fmt == SKIT_FMT_BF16X2 && w->hi && w->lo && (stride == 1 || stride == 2) && x->c % 64 == 0 &&
+           w->co % 64 == 0 && w->ci == x->c;
 }
 
-int conv_fwd_tc(const skit_operand* x, const skit_weights* w, int org, int ho, int wo,
-                const float* bias, float* y, double* stats, int stats_mode, cudaStream_t st) {
+struct TcOut {  // where the tile results land (defaults: dense [n][ho][wo][co])
+    int OH, OW, osy, osx, ooy, oox;
+};
+
+// k: taps per side of THIS launch; ntaps_total: taps in the packed filter (weight map extent); tap_base: first tap.
+int conv_tc_launch(const skit_operand* x, const void* w_hi, const void* w_lo, int ci, int co, int k, int ntaps_total,
+                   int tap_base, int stride, int org, int ho, int wo, const float* bias, float* y, const TcOut* out,
+                   double* stats, int stats_mode, cudaStream_t st) {
     using namespace tc;
-    const int ci = x->c, co = w->co, k = w->k;
     const int BN = (co % 256 == 0) ? 256 : (co % 128 == 0) ? 128 : 64;
     TcConvP p{};
-    p.k = k; p.kc = ci / 64; p.org = org; p.ho = ho; p.wo = wo; p.co = co;
+    p.k = k; p.kc = ci / 64; p.org = org; p.stride = stride; p.tap_base = tap_base; p.ho = ho; p.wo = wo; p.co = co;
     p.tw = (wo <= 8) ? 8 : 16; p.th = 128 / p.tw;
     p.tiles_x = cdiv(wo, p.tw);
+    if (out) { p.OH = out->OH; p.OW = out->OW; p.osy = out->osy; p.osx = out->osx; p.ooy = out->ooy; p.oox = out->oox; }
+    else { p.OH = ho; p.OW = wo; p.osy = 1; p.osx = 1; p.ooy = 0; p.oox = 0; }
     p.bias = bias; p.y = y; p.stats = stats; p.stats_per_n = stats_mode == SKIT_NORM_INSTANCE;
     const int tiles_y = cdiv(ho, p.th);
 
-    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+    CUtensorMap a_hi, a_lo, m_hi, m_lo;
     {
         uint64_t dims[4] = {(uint64_t)ci, (uint64_t)x->wp, (uint64_t)x->hp, (uint64_t)x->n};
         uint64_t strides[3] = {(uint64_t)ci * 2, (uint64_t)ci * 2 * x->wp, (uint64_t)ci * 2 * x->wp * x->hp};
-        uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
-        int rc = encode_bf16_map(&a_hi, x->p0, 4, dims, strides, box, nullptr);
+        uint32_t box[4] = {64, (uint32_t)(p.tw * stride), (uint32_t)(p.th * stride), 1};
+        uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        int rc = encode_bf16_map(&a_hi, x->p0, 4, dims, strides, box, es);
         if (rc) return rc;
-        rc = encode_bf16_map(&a_lo, x->p1, 4, dims, strides, box, nullptr);
+        rc = encode_bf16_map(&a_lo, x->p1, 4, dims, strides, box, es);
         if (rc) return rc;
     }
     {
-        uint64_t dims[3] = {(uint64_t)ci, (uint64_t)co, (uint64_t)(k * k)};
+        uint64_t dims[3] = {(uint64_t)ci, (uint64_t)co, (uint64_t)ntaps_total};
         uint64_t strides[2] = {(uint64_t)ci * 2, (uint64_t)ci * 2 * co};
         uint32_t box[3] = {64, (uint32_t)BN, 1};
-        int rc = encode_bf16_map(&w_hi, w->hi, 3, dims, strides, box, nullptr);
+        int rc = encode_bf16_map(&m_hi, w_hi, 3, dims, strides, box, nullptr);
         if (rc) return rc;
-        rc = encode_bf16_map(&w_lo, w->lo, 3, dims, strides, box, nullptr);
+        rc = encode_bf16_map(&m_lo, w_lo, 3, dims, strides, box, nullptr);
         if (rc) return rc;
     }
     dim3 grid(p.tiles_x * tiles_y, co / BN, x->n);
-    if (BN == 256) return launch_conv_tc<256, 2>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
-    if (BN == 128) return launch_conv_tc<128, 3>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
-    return launch_conv_tc<64, 4>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
+    if (BN == 256) return launch_conv_tc<256, 2>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
+    if (BN == 128) return launch_conv_tc<128, 3>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
+    return launch_conv_tc<64, 4>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
+}
+
+int conv_fwd_tc(const skit_operand* x, const skit_weights* w, int stride, int org, int ho, int wo,
+                const float* bias, float* y, double* stats, int stats_mode, cudaStream_t st) {
+    return conv_tc_launch(x, w->hi, w->lo, x->c, w->co, w->k, w->k * w->k, 0, stride, org, ho, wo, bias, y, nullptr,
+                          stats, stats_mode, st);
 }
 
 int conv_fwd_simt(const skit_operand* x, const skit_weights* w, int stride, int org, int ho, int wo,
                   const float* bias, float* y, double* stats, int stats_mode, cudaStream_t st);
-
-// tensor-core wgrad: not built yet — the CUDA-core kernel in simt_conv.cu takes every shape.
-bool wgrad_tc_eligible(const skit_operand*, const skit_operand*, int, int, int, int) { return false; }
-int wgrad_tc(const skit_operand*, int, const skit_operand*, int, int, int, int, int, float*, cudaStream_t) {
-    set_error("wgrad_tc: not implemented");
-    return SKIT_ERR_UNSUPPORTED;
-}
 
 }  // namespace skit
 
@@ -291,7 +305,29 @@ extern "C" int skit_conv2d_fwd(const skit_operand* x, const skit_weights* w, int
         set_error("conv2d_fwd: shape not eligible for the tcgen05 path (fmt=%d ci=%d co=%d stride=%d)", x->fmt, x->c, w->co, stride);
         return SKIT_ERR_UNSUPPORTED;
     }
-    if (tc_ok && impl != SKIT_IMPL_SIMT) return conv_fwd_tc(x, w, org, ho, wo, bias, y, stats, stats_mode, as_stream(stream));
+    if (tc_ok && impl != SKIT_IMPL_SIMT) return conv_fwd_tc(x, w, stride, org, ho, wo, bias, y, stats, stats_mode, as_stream(stream));
     SKIT_REQUIRE(w->f32, "conv2d_fwd: CUDA-core path needs the fp32 weight pack");
     return conv_fwd_simt(x, w, stride, org, ho, wo, bias, y, stats, stats_mode, as_stream(stream));
+}
+
+// Stride-2 input gradient on the tensor cores: the four output parities (iy%2, ix%2) are four independent
+// stride-1 convolutions of the zero-haloed output gradient with (k/2 x k/2) sub-filters (mode-3 pack),
+// each writing its own interleaved quarter of dx.
+extern "C" int skit_conv2d_dgrad_s2(const skit_operand* dy, int dy_pad, const skit_weights* wp, int k,
+                                    int ho, int wo, int hp, int wp_, float* dx, void* stream) {
+    SKIT_REQUIRE(dy && wp && dx && dy->p0 && dy->p1 && wp->hi && wp->lo, "conv2d_dgrad_s2: null pointer");
+    SKIT_REQUIRE(dy->fmt == SKIT_FMT_BF16X2 && k % 2 == 0 && dy_pad == k / 2 - 1, "conv2d_dgrad_s2: needs a bf16x2 dy operand with halo k/2-1");
+    SKIT_REQUIRE(dy->c % 64 == 0 && wp->co % 64 == 0 && wp->ci == dy->c, "conv2d_dgrad_s2: channel counts must be multiples of 64");
+    SKIT_REQUIRE(dy->hp == ho + 2 * dy_pad && dy->wp == wo + 2 * dy_pad, "conv2d_dgrad_s2: dy operand dims mismatch");
+    const int kh = k / 2;
+    for (int py = 0; py < 2; py++)
+        for (int px = 0; px < 2; px++) {
+            const int A = (hp - py + 1) / 2, B = (wp_ - px + 1) / 2;  // outputs of this parity
+            if (A <= 0 || B <= 0) continue;
+            TcOut out{hp, wp_, 2, 2, py, px};
+            int rc = conv_tc_launch(dy, wp->hi, wp->lo, dy->c, wp->co, kh, 4 * kh * kh, (py * 2 + px) * kh * kh, 1, 0, A, B,
+                                    nullptr, dx, &out, nullptr, SKIT_NORM_NONE, as_stream(stream));
+            if (rc) return rc;
+        }
+    return SKIT_OK;
 }

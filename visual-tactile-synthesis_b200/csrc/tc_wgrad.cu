@@ -1,0 +1,216 @@
+// tcgen05 + TMA weight gradient:  dW[tap][m][n] = sum_{image, pixel} Mop[pixel (+tap)][m] * Nop[pixel (+tap)][n]
+//
+// Both GEMM operands are activations in NHWC (pixels are the reduction axis), i.e. MN-major in
+// tcgen05 terms: a TMA box of 64 pixels x 64 channels lands as 64 rows of 128 B (SWIZZLE_128B) and
+// is consumed directly — no transpose anywhere.  The M side is whichever of {output-gradient
+// channels, input channels} is a multiple of 128 (one 128-row tile per CTA); the other side is the N
+// tile (64/128/256).  The input-side box is shifted by the filter tap (and strided for stride-2
+// layers through the tensor map's element strides); pixels outside the image read the zero halo of
+// the gradient operand (or TMA zero fill), so ragged tiles need no masking.  fp32 fidelity: the same
+// 3-term bf16 hi/lo split as the forward kernel.  Split-K over pixel tiles across CTAs; each CTA
+// accumulates in TMEM and adds its partial to the fp32 result with coalesced red.global.add.
+#include "tc_common.cuh"
+
+namespace skit {
+namespace tc {
+
+struct TcWgradP {
+    int k;                 // taps per side
+    int tiles_x, tiles_y;  // 8x8-pixel tiles per image
+    int n_img;
+    int tiles_per_cta;     // split-K chunk (in pixel tiles, over all images)
+    int total_tiles;
+    int m_is_x;            // 1: M operand is the (tap-shifted, strided) input, N operand the gradient; 0: the reverse
+    int x_org, x_stride, d_org;
+    int Mdim, Ndim;        // channel counts of the M / N side
+    float* out;            // [tap][Ndim][Mdim] fp32 partial sums (zeroed by the caller)
+};
+
+constexpr int PIX = 64;               // pixels per K stage (8x8 box)
+constexpr int BOX_BYTES = PIX * 128;  // 64 pixels x 64 bf16
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
+                const __grid_constant__ CUtensorMap tmN_hi, const __grid_constant__ CUtensorMap tmN_lo, TcWgradP p) {
+    constexpr int M_BYTES = 2 * BOX_BYTES;          // 128 M-channels = 2 boxes
+    constexpr int N_BYTES = (BN / 64) * BOX_BYTES;
+    constexpr int STAGE_BYTES = 2 * M_BYTES + 2 * N_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+    const uint32_t bar0 = smem0 + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar0 + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 1);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap = blockIdx.x % (p.k * p.k);
+    const int mt = blockIdx.x / (p.k * p.k);          // 128-row M tile
+    const int n0 = blockIdx.y * BN;
+    const int t_beg = blockIdx.z * p.tiles_per_cta;
+    const int t_end = min(p.total_tiles, t_beg + p.tiles_per_cta);
+    const int ky = tap / p.k, kx = tap - ky * p.k;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmM_hi); tma_prefetch_desc(&tmM_lo);
+        tma_prefetch_desc(&tmN_hi); tma_prefetch_desc(&tmN_lo);
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+    const int num_it = t_end - t_beg;
+
+    if (num_it > 0) {
+        if (warp == 0 && lane == 0) {
+            // ---------------- TMA producer
+            const int tpi = p.tiles_x * p.tiles_y;
+            for (int it = 0; it < num_it; it++) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                const int t = t_beg + it;
+                const int img = t / tpi, r = t - img * tpi;
+                const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+                const int xx = p.x_org + tx * 8 * p.x_stride + kx, xy = p.x_org + ty * 8 * p.x_stride + ky;  // input side
+                const int dx = p.d_org + tx * 8, dy = p.d_org + ty * 8;                                       // gradient side
+                const int mx = p.m_is_x ? xx : dx, my = p.m_is_x ? xy : dy;
+                const int nx = p.m_is_x ? dx : xx, ny = p.m_is_x ? dy : xy;
+                const uint32_t sa = smem0 + s * STAGE_BYTES;
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    tma_load_4d(sa + g * BOX_BYTES, &tmM_hi, full_bar(s), mt * 128 + g * 64, mx, my, img);
+                    tma_load_4d(sa + M_BYTES + g * BOX_BYTES, &tmM_lo, full_bar(s), mt * 128 + g * 64, mx, my, img);
+                }
+#pragma unroll
+                for (int g = 0; g < BN / 64; g++) {
+                    tma_load_4d(sa + 2 * M_BYTES + g * BOX_BYTES, &tmN_hi, full_bar(s), n0 + g * 64, nx, ny, img);
+                    tma_load_4d(sa + 2 * M_BYTES + N_BYTES + g * BOX_BYTES, &tmN_lo, full_bar(s), n0 + g * 64, nx, ny, img);
+                }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ---------------- MMA issuer (both operands MN-major: LBO = one 64-channel box, SBO = 8 pixel rows)
+            constexpr uint32_t idesc = make_idesc_bf16(BN, 1, 1);
+            for (int it = 0; it < num_it; it++) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa = smem0 + s * STAGE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < PIX / 16; kk++) {
+                    const uint32_t ko = kk * 16 * 128;
+                    const uint64_t m_hi = make_desc(sa + ko, BOX_BYTES, 1024);
+                    const uint64_t m_lo = make_desc(sa + M_BYTES + ko, BOX_BYTES, 1024);
+                    const uint64_t n_hi = make_desc(sa + 2 * M_BYTES + ko, BOX_BYTES, 1024);
+                    const uint64_t n_lo = make_desc(sa + 2 * M_BYTES + N_BYTES + ko, BOX_BYTES, 1024);
+                    mma_bf16(tmem_base, m_lo, n_hi, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    mma_bf16(tmem_base, m_hi, n_lo, idesc, 1u);
+                    mma_bf16(tmem_base, m_hi, n_hi, idesc, 1u);
+                }
+                mma_commit(empty_bar(s));
+            }
+            mma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+        // ---------------- epilogue: out[(tap*Ndim + n)*Mdim + m] += acc   (lanes = consecutive m: coalesced reds)
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        __syncwarp();
+        const int m = mt * 128 + warp * 32 + lane;
+        float* obase = p.out + ((long long)tap * p.Ndim + n0) * p.Mdim + m;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) atomicAdd(obase + (long long)(c + j) * p.Mdim, v[j]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad_tc(const CUtensorMap& m_hi, const CUtensorMap& m_lo, const CUtensorMap& n_hi, const CUtensorMap& n_lo,
+                           const TcWgradP& p, dim3 grid, cudaStream_t st) {
+    constexpr int SMEM = STAGES * (4 * BOX_BYTES + 2 * (BN / 64) * BOX_BYTES) + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(wgrad_tc_kernel<%d>) failed: %s", BN, cudaGetErrorString(e));
+            return SKIT_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    wgrad_tc_kernel<BN, STAGES><<<grid, 128, SMEM, st>>>(m_hi, m_lo, n_hi, n_lo, p);
+    return check_launch("wgrad_tc_kernel");
+}
+
+static int encode_act_map(CUtensorMap* hi, CUtensorMap* lo, const skit_operand* t, int estride) {
+    uint64_t dims[4] = {(uint64_t)t->c, (uint64_t)t->wp, (uint64_t)t->hp, (uint64_t)t->n};
+    uint64_t strides[3] = {(uint64_t)t->c * 2, (uint64_t)t->c * 2 * t->wp, (uint64_t)t->c * 2 * t->wp * t->hp};
+    uint32_t box[4] = {64, (uint32_t)(8 * estride), (uint32_t)(8 * estride), 1};
+    uint32_t es[4] = {1, (uint32_t)estride, (uint32_t)estride, 1};
+    int rc = encode_bf16_map(hi, t->p0, 4, dims, strides, box, es);
+    if (rc) return rc;
+    return encode_bf16_map(lo, t->p1, 4, dims, strides, box, es);
+}
+
+}  // namespace tc
+
+// layout of the partial-sum buffer the kernel fills: 0 = [tap][ci][co] (M = co), 1 = [tap][co][ci] (M = ci)
+bool wgrad_tc_eligible(const skit_operand* x, const skit_operand* dy, int k, int stride, int ho, int wo) {
+    if (x->fmt != SKIT_FMT_BF16X2 || dy->fmt != SKIT_FMT_BF16X2 || (stride != 1 && stride != 2)) return false;
+    const int ci = x->c, co = dy->c;
+    if (ci % 64 || co % 64) return false;
+    return co % 128 == 0 || ci % 128 == 0;
+}
+
+int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org, int k, int stride,
+             int ho, int wo, float* partial, int* layout, cudaStream_t st) {
+    using namespace tc;
+    const int ci = x->c, co = dy->c;
+    TcWgradP p{};
+    p.k = k;
+    p.tiles_x = cdiv(wo, 8); p.tiles_y = cdiv(ho, 8);
+    p.n_img = x->n;
+    p.total_tiles = p.tiles_x * p.tiles_y * x->n;
+    p.m_is_x = (co % 128 == 0) ? 0 : 1;
+    p.x_org = org; p.x_stride = stride; p.d_org = dy_org;
+    p.Mdim = p.m_is_x ? ci : co;
+    p.Ndim = p.m_is_x ? co : ci;
+    p.out = partial;
+    *layout = p.m_is_x;
+    const int BN = (p.Ndim % 256 == 0) ? 256 : (p.Ndim % 128 == 0) ? 128 : 64;
+    const int items = k * k * (p.Mdim / 128) * (p.Ndim / BN);
+    int splits = max(1, min(cdiv(2 * 148, items), p.total_tiles));
+    p.tiles_per_cta = cdiv(p.total_tiles, splits);
+    splits = cdiv(p.total_tiles, p.tiles_per_cta);
+
+    CUtensorMap x_hi, x_lo, d_hi, d_lo;
+    int rc = encode_act_map(&x_hi, &x_lo, x, stride);
+    if (rc) return rc;
+    rc = encode_act_map(&d_hi, &d_lo, dy, 1);
+    if (rc) return rc;
+    dim3 grid(k * k * (p.Mdim / 128), p.Ndim / BN, splits);
+    const CUtensorMap &mh = p.m_is_x ? x_hi : d_hi, &ml = p.m_is_x ? x_lo : d_lo;
+    const CUtensorMap &nh = p.m_is_x ? d_hi : x_hi, &nl = p.m_is_x ? d_lo : x_lo;
+    if (BN == 256) return launch_wgrad_tc<256, 2>(mh, ml, nh, nl, p, grid, st);
+    if (BN == 128) return launch_wgrad_tc<128, 3>(mh, ml, nh, nl, p, grid, st);
+    return launch_wgrad_tc<64, 4>(mh, ml, nh, nl, p, grid, st);
+}
+
+}  // namespace skit

@@ -51,13 +51,13 @@ class Conv2d(nn.Module):
 
     @property
     def use_tc(self):
-        return TC_ENABLED and self.stride == 1 and self.ci % 64 == 0 and self.co % 64 == 0
+        return TC_ENABLED and self.stride in (1, 2) and self.ci % 64 == 0 and self.co % 64 == 0 and (self.stride == 1 or self.k % 2 == 0)
 
     def pack(self, mode):
-        """mode 0 forward, 1 stride-1 dgrad (tensor-core), 2 gather dgrad (CUDA-core)."""
+        """mode 0 forward, 1 stride-1 dgrad (tensor-core), 2 gather dgrad (CUDA-core), 3 stride-2 phase dgrad (tensor-core)."""
         pk = self._packs.get(mode)
         if pk is None:
-            bf16 = self.use_tc and mode in (0, 1)
+            bf16 = self.use_tc and mode in (0, 1, 3)
             pk = ops.PackedWeights(self.weight, mode, want_f32=not bf16, want_bf16=bf16)
             self._packs[mode] = pk
         return pk
@@ -163,7 +163,7 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
     n, ho, wo, co = raw.shape
     g, sums = ops.act_norm_bwd_reduce(raw.shape, dpad, pad, pad_mode, dadd, raw, mr, norm_mode, gamma, beta, act)
     tc = layer.use_tc
-    q = layer.k - 1 if tc else 0
+    q = 0 if not tc else (layer.k - 1 if layer.stride == 1 else layer.k // 2 - 1)
     d_op = ops.norm_bwd_apply(g, raw, mr, norm_mode, gamma, sums, count, dgamma, dbeta, pad=q,
                               fmt=FMT_BF16X2 if tc else FMT_F32)
     if need_wgrad:
@@ -171,6 +171,8 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
                          layer.bias.grad if layer.bias is not None else None)
     if not need_dgrad:
         return None
+    if tc and layer.stride == 2:
+        return ops.conv2d_dgrad_s2(d_op, q, layer.pack(3), layer.k, ho, wo, x_op.hp, x_op.wp)
     if tc:
         dx, _ = ops.conv2d_fwd(d_op, layer.pack(1), 1, 0, x_op.hp, x_op.wp)
         return dx

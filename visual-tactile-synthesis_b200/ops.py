@@ -82,12 +82,18 @@ def conv2d_dgrad_gather(dy, wg, stride, hp, wp):
     return dx
 
 
+def conv2d_dgrad_s2(dy_op, dy_pad, wp, k, ho, wo, hp, wp_):
+    """Stride-2 input gradient on tcgen05 (four parity sub-convolutions); dy_op: bf16x2, halo k/2-1."""
+    dx = torch.empty((dy_op.n, hp, wp_, wp.rco), dtype=torch.float32, device=dy_op.data.device)
+    L.call("skit_conv2d_dgrad_s2", dy_op.ref(), dy_pad, wp.ref(), k, ho, wo, hp, wp_, _p(dx), L.stream())
+    return dx
+
+
 def conv2d_wgrad(x, org, dy, dy_org, k, stride, ho, wo, dw, dbias=None, impl=IMPL_AUTO):
     """Accumulates into dw ([co][ci][k][k] view of the flat grad bucket) and dbias."""
     co, ci = dy.c, x.c
-    dwf = torch.zeros((k * k * ci, co), dtype=torch.float32, device=x.data.device)
-    L.call("skit_conv2d_wgrad", x.ref(), org, dy.ref(), dy_org, k, stride, ho, wo, _p(dwf), _p(dbias), impl, L.stream())
-    L.call("skit_unpack_conv_wgrad", _p(dwf), co, ci, k, _p(dw), 1, L.stream())
+    scratch = torch.zeros((k * k * ci * co,), dtype=torch.float32, device=x.data.device)
+    L.call("skit_conv2d_wgrad", x.ref(), org, dy.ref(), dy_org, k, stride, ho, wo, _p(scratch), _p(dw), _p(dbias), impl, L.stream())
 
 
 def stats_finalize(stats, count, eps=1e-5, running_mean=None, running_var=None, momentum=0.1):
