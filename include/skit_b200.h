@@ -211,6 +211,12 @@ int skit_l1_loss(const float* a, const float* b, long long numel, float scale, f
 int skit_adam_step(float* p, const float* g, float* m, float* v, long long numel, int step,
                    float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* Same update, with the two step-dependent scalars in DEVICE memory: hyper = [lr / (1 - beta1^step),
+ * 1 / sqrt(1 - beta2^step)] (fp32).  Lets one captured CUDA graph of the whole train step be replayed
+ * while the step count and the LambdaLR factor (networks.py:161-165) advance. */
+int skit_adam_step_dev(float* p, const float* g, float* m, float* v, long long numel, const float* hyper,
+                       float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 /* ---------------------------------------------------------------- PatchNCE
  * PatchSampleF gather + Normalize (networks.py:689-719, 585-594): feat NHWC fp32 [b][hw][c];
  * out[b*np + i][c] = f[b][ids[i]][c] / (||f||_2 + 1e-7).  `pre` (optional) keeps the un-normalised rows. */

@@ -59,6 +59,7 @@ SIGNATURES = {
     "skit_gan_softplus": [_P, _I, _I, _F, _P, _P, _F, _P],
     "skit_l1_loss": [_P, _P, _LL, _F, _P, _P, _F, _I, _P],
     "skit_adam_step": [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _P],
+    "skit_adam_step_dev": [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _P],
     "skit_patch_sample_l2norm": [_P, _I, _I, _I, _P, _I, _P, _P, _P],
     "skit_patch_sample_l2norm_bwd": [_P, _P, _I, _I, _I, _P, _I, _P, _P],
     "skit_patchnce": [_P, _P, _I, _I, _I, _F, _P, _P, _F, _P],

@@ -302,6 +302,20 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
+// Same update with the step-dependent scalars read from device memory ([lr/bc1, 1/sqrt(bc2)]), so that a
+// captured CUDA graph of the whole train step stays valid while the step count and learning rate advance.
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                       long long numel, const float* __restrict__ hyper, float beta1, float beta2, float eps, float gs) {
+    const float lr_over_bc1 = hyper[0], inv_sqrt_bc2 = hyper[1];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x) {
+        const float gg = g[i] * gs;
+        const float mm = beta1 * m[i] + (1.f - beta1) * gg;
+        const float vv = beta2 * v[i] + (1.f - beta2) * gg * gg;
+        m[i] = mm; v[i] = vv;
+        p[i] -= lr_over_bc1 * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+    }
+}
+
 // ------------------------------------------------------------------------------ PatchNCE
 // one warp per sampled row: coalesced gather of c floats, warp-shuffle L2 norm.
 __global__ void __launch_bounds__(256) patch_sample_l2norm_kernel(const float* __restrict__ feat, int b, int hw, int c, const int* ids, int np,
@@ -500,6 +514,13 @@ extern "C" int skit_adam_step(float* p, const float* g, float* m, float* v, long
     const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     adam_kernel<<<grid_for(numel, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, numel, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale);
     return check_launch("adam_kernel");
+}
+
+extern "C" int skit_adam_step_dev(float* p, const float* g, float* m, float* v, long long numel, const float* hyper,
+                                  float beta1, float beta2, float eps, float grad_scale, void* stream) {
+    SKIT_REQUIRE(p && g && m && v && hyper && numel > 0, "adam_step_dev: bad arguments");
+    adam_dev_kernel<<<grid_for(numel, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, numel, hyper, beta1, beta2, eps, grad_scale);
+    return check_launch("adam_dev_kernel");
 }
 
 extern "C" int skit_patch_sample_l2norm(const float* feat, int b, int hw, int c, const int* ids, int np,

@@ -167,8 +167,12 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
     d_op = ops.norm_bwd_apply(g, raw, mr, norm_mode, gamma, sums, count, dgamma, dbeta, pad=q,
                               fmt=FMT_BF16X2 if tc else FMT_F32)
     if need_wgrad:
+        # A conv bias that feeds a norm layer has an identically zero gradient (the norm removes any constant
+        # per-channel shift; d_raw sums to zero over the normalised axes) — the reference only accumulates
+        # rounding noise there — so its reduction is skipped and the zeroed flat-grad entry stands.
+        want_db = layer.bias is not None and norm_mode == NORM_NONE
         ops.conv2d_wgrad(x_op, 0, d_op, q, layer.k, layer.stride, ho, wo, layer.weight.grad,
-                         layer.bias.grad if layer.bias is not None else None)
+                         layer.bias.grad if want_db else None)
     if not need_dgrad:
         return None
     if tc and layer.stride == 2:

@@ -277,6 +277,12 @@ def adam_step(p, g, m, v, step, lr, beta1, beta2, eps=1e-8, grad_scale=1.0):
            float(eps), float(grad_scale), L.stream())
 
 
+def adam_step_dev(p, g, m, v, hyper, beta1, beta2, eps=1e-8, grad_scale=1.0):
+    """hyper: device fp32 [2] = [lr / bias_correction1, 1 / sqrt(bias_correction2)] (graph-replay safe)."""
+    L.call("skit_adam_step_dev", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper), float(beta1), float(beta2),
+           float(eps), float(grad_scale), L.stream())
+
+
 def patch_sample_l2norm(feat_nhwc, ids, keep_pre=False):
     b, h, w, c = feat_nhwc.shape
     npatch = int(ids.numel())

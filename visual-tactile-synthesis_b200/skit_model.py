@@ -17,6 +17,7 @@ import random
 import numpy as np
 import torch
 
+from . import _lib as L_
 from . import networks, ops
 from .model_utils import find_coords_for_patch, random_patch_offset_table, spe_grid
 
@@ -37,6 +38,8 @@ def default_options(**kw):
         lr=1e-3, lr_G2=5e-4, beta1=0.0, beta2=0.99, lr_policy="linear", n_epochs=5, n_epochs_decay=400, epoch_count=1,
         run_full_res_D2=False,  # the reference's visualisation-only netD2(full image) pass (:1495); off on the hot path
         checkpoints_dir="./checkpoints", name="experiment",
+        cuda_graph=True,         # replay the whole train step as one CUDA graph once shapes are stable
+        cuda_graph_warmup=2,     # eager steps before capture (lazy weight packs, kernel attributes, NCCL warm-up)
     )
     o.update(kw)
     return argparse.Namespace(**o)
@@ -82,6 +85,10 @@ class SinSKITGModel:
             self.loss_buf = torch.zeros(16, dtype=torch.float32, device=self.device)
         self._spe_cache = {}
         self._losses = {}
+        self._graph = None          # captured train step (torch.cuda.CUDAGraph) + the attributes it produced
+        self._graph_attrs = None
+        self._graph_key = None
+        self._input_gen = 0         # bumped whenever an input buffer is (re)allocated -> invalidates the graph
 
     # ------------------------------------------------------------------ data staging
     def _spe(self, n, h, w):
@@ -117,22 +124,87 @@ class SinSKITGModel:
             if not v.is_pinned():
                 v = v.pin_memory()
             self.h2d_bytes += v.numel() * v.element_size()
-            setattr(self, k, v.to(dev, non_blocking=True))
+            self._stage(k, v)
         self.S_pe = self._spe(n, h, w) if self.opt.use_positional_encoding else None
         self.style_code = input.get("style_code")
         if self.isTrain and hasattr(self, "real_T"):
             NT, NF = self.NT, self.opt.add_fake_T_sample_size
-            self.fake_in = torch.zeros(NT, 7, 32, 32, device=dev)
-            self.real_in = torch.zeros(NT, 7, 32, 32, device=dev)
-            self.more_in = torch.ones(NF, 7, 32, 32, device=dev)
+            if getattr(self, "fake_in", None) is None or self.fake_in.shape[0] != NT or self.more_in.shape[0] != NF:
+                self.fake_in = torch.zeros(NT, 7, 32, 32, device=dev)
+                self.real_in = torch.zeros(NT, 7, 32, 32, device=dev)
+                self.more_in = torch.ones(NF, 7, 32, 32, device=dev)
+                self._input_gen += 1
             self.fake_in[:, 6:7] = self.I_masks
             self.real_in[:, 6:7] = self.I_masks
             self.real_in[:, 0:2] = self.real_T
             self._offset_table = random_patch_offset_table(M) if self.opt.use_more_fakeT else None
         self.image_paths = input.get("S_paths")
 
+    def _stage(self, name, host_t):
+        """Host tensor -> a persistent device buffer of the same name (same address every step, so the
+        captured CUDA graph of the train step stays valid); reallocates only when the shape changes."""
+        cur = getattr(self, name, None)
+        if torch.is_tensor(cur) and cur.is_cuda and cur.shape == host_t.shape and cur.dtype == host_t.dtype:
+            cur.copy_(host_t, non_blocking=True)
+        else:
+            setattr(self, name, host_t.to(self.device, non_blocking=True))
+            self._input_gen += 1
+
+    _RING = 4
+
+    def _stage_rand(self, rand):
+        """The step's host-side random draws (DiffAugment torch.rand x4, NF random-patch offsets) and the
+        Adam scalars go into ONE pinned blob and one H2D copy into a persistent device blob, before the
+        (possibly replayed) step body.  A small ring of pinned blobs, each guarded by an event, keeps the
+        host from overwriting a blob whose copy the GPU has not executed yet (the host runs ahead of a
+        replayed graph)."""
+        opt = self.opt
+        n = self.real_S.shape[0]
+        NF = opt.add_fake_T_sample_size if self.isTrain else 0
+        words = 4 * n + 2 * max(NF, 1) + 6
+        if getattr(self, "_blob_dev", None) is None or self._blob_dev.numel() != words:
+            self._blob_host = [torch.zeros(words, dtype=torch.float32).pin_memory() for _ in range(self._RING)]
+            self._blob_evt = [None] * self._RING
+            self._blob_i = 0
+            self._blob_dev = torch.zeros(words, dtype=torch.float32, device=self.device)
+            self._u_dev = self._blob_dev[:4 * n].view(4, n)
+            self._fo_dev = self._blob_dev[4 * n:4 * n + 2 * max(NF, 1)].view(torch.int32).view(2, max(NF, 1))
+            self._hy_dev = self._blob_dev[4 * n + 2 * max(NF, 1):].view(3, 2)
+            self._input_gen += 1
+        i = self._blob_i
+        self._blob_i = (i + 1) % self._RING
+        if self._blob_evt[i] is not None:
+            self._blob_evt[i].synchronize()
+        h = self._blob_host[i]
+        hu = h[:4 * n].view(4, n)
+        hfo = h[4 * n:4 * n + 2 * max(NF, 1)].view(torch.int32).view(2, max(NF, 1))
+        hhy = h[4 * n + 2 * max(NF, 1):].view(3, 2)
+        if opt.use_diffaug:
+            for j, k in enumerate(("real_b", "real_s", "fake_b", "fake_s")):
+                # the reference's torch.rand draws, in its order: real (b, s) then fake (b, s)
+                hu[j].copy_(torch.rand(n, 1, 1, 1).reshape(n) if rand is None else
+                            torch.as_tensor(np.asarray(rand[k], dtype=np.float32)).reshape(n))
+        if self.isTrain and opt.use_more_fakeT and NF:
+            if rand is not None and "fake_ox" in rand:
+                fox, foy = np.asarray(rand["fake_ox"], dtype=np.int32), np.asarray(rand["fake_oy"], dtype=np.int32)
+            else:
+                fox, foy = self._offset_table.sample(NF)
+            hfo[0].copy_(torch.from_numpy(np.ascontiguousarray(fox)))
+            hfo[1].copy_(torch.from_numpy(np.ascontiguousarray(foy)))
+        if self.isTrain:
+            t = max(1, self.step_count)
+            bc1 = 1.0 - opt.beta1 ** t
+            bc2 = 1.0 - opt.beta2 ** t
+            for j, lr in enumerate((opt.lr, opt.lr_G2, opt.lr)):   # rows: D, D2, G
+                hhy[j, 0] = lr * self.lr_factor / bc1
+                hhy[j, 1] = 1.0 / math.sqrt(bc2)
+        self._blob_dev.copy_(h, non_blocking=True)
+        evt = torch.cuda.Event()
+        evt.record()
+        self._blob_evt[i] = evt
+
     # ------------------------------------------------------------------ forward
-    def forward(self, save=None, rand=None):
+    def forward(self, save=None, rand=None, staged=False):
         """sinskitG_model.py:1293-1344: G, channel split, *M, normal, DiffAugment('bs') real + fake, *M."""
         opt = self.opt
         save = self.isTrain if save is None else save
@@ -141,12 +213,11 @@ class SinSKITGModel:
             srcs, mask=self.M if opt.use_bg_mask else None, scale_nz=opt.scale_nz, save=save)
         if hasattr(self, "real_I"):
             if opt.use_diffaug:
-                n = self.real_S.shape[0]
-                if rand is None:  # the reference's torch.rand draws: real (b, s) then fake (b, s)
-                    rand = {k: torch.rand(n, 1, 1, 1).reshape(n) for k in ("real_b", "real_s", "fake_b", "fake_s")}
-                u = {k: torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(n).to(self.device, non_blocking=True) for k, v in rand.items() if k in ("real_b", "real_s", "fake_b", "fake_s")}
-                self.aug_real_I = ops.diffaug_bs_mask(self.real_I, self.M, u["real_b"], u["real_s"])
-                self.aug_fake_I = ops.diffaug_bs_mask(self.fake_I, self.M, u["fake_b"], u["fake_s"])
+                if not staged:
+                    self._stage_rand(rand)
+                u = self._u_dev
+                self.aug_real_I = ops.diffaug_bs_mask(self.real_I, self.M, u[0], u[1])
+                self.aug_fake_I = ops.diffaug_bs_mask(self.fake_I, self.M, u[2], u[3])
             else:
                 self.aug_real_I, self.aug_fake_I = self.real_I, self.fake_I
         return self.fake_I, self.fake_T, self.fake_N
@@ -162,10 +233,11 @@ class SinSKITGModel:
         if self.dist is not None:
             self.dist.allreduce_grads(net.flat_grad)
 
-    def _adam(self, net, lr):
+    def _adam(self, net, slot):
+        """slot: row of the device hyper buffer (0 = D, 1 = D2, 2 = G) written by _stage_rand."""
         scale = 1.0 / self.dist.world_size if self.dist is not None else 1.0
-        ops.adam_step(net.flat_param, net.flat_grad, net.exp_avg, net.exp_avg_sq, self.step_count,
-                      lr * self.lr_factor, self.opt.beta1, self.opt.beta2, 1e-8, scale)
+        ops.adam_step_dev(net.flat_param, net.flat_grad, net.exp_avg, net.exp_avg_sq, self._hy_dev[slot],
+                          self.opt.beta1, self.opt.beta2, 1e-8, scale)
         net.refresh_packs()
 
     @staticmethod
@@ -185,15 +257,44 @@ class SinSKITGModel:
         torch / random like the reference when absent."""
         opt = self.opt
         G, D, D2 = self.netG, self.netD, self.netD2
-        NT, NF = self.NT, opt.add_fake_T_sample_size
-        n = self.real_S.shape[0]
         self.step_count += 1
         for net in (G, D, D2):
             net.ensure_flat()
         if self.step_count == 1:
             for net in (G, D, D2):
                 net.refresh_packs()
-        self.forward(save=True, rand=rand)
+        self._stage_rand(rand)
+        key = (self._input_gen, tuple(self.real_S.shape), self.NT, opt.add_fake_T_sample_size,
+               tuple(net.flat_param.data_ptr() for net in (G, D, D2)))
+        if self._graph is not None and self._graph_key == key:
+            self._graph.replay()
+            L_.launches += self._graph_launches   # kernel-launching ABI calls the replayed graph stands for
+            self.__dict__.update(self._graph_attrs)
+            return self._loss_raw[0]
+        self._graph = None
+        if opt.cuda_graph and self.step_count > opt.cuda_graph_warmup:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            before = dict(self.__dict__)
+            l0 = L_.launches
+            with torch.cuda.graph(g):
+                self._step_body()
+            self._graph_launches = L_.launches - l0
+            self._graph, self._graph_key = g, key
+            self._graph_attrs = {k: v for k, v in self.__dict__.items() if k not in before or before[k] is not v}
+            for k in ("_graph", "_graph_key", "_graph_attrs", "_graph_launches"):
+                self._graph_attrs.pop(k, None)
+            g.replay()    # capture does not execute: run the step once
+            return self._loss_raw[0]
+        return self._step_body()
+
+    def _step_body(self):
+        """All device work of one train step; reads only persistent device buffers (graph-capturable)."""
+        opt = self.opt
+        G, D, D2 = self.netG, self.netD, self.netD2
+        NT, NF = self.NT, opt.add_fake_T_sample_size
+        n = self.real_S.shape[0]
+        self.forward(save=True, staged=True)
         fake_I, fake_T = self.fake_I, self.fake_T
         ox, oy = self.ox, self.oy
         # compute_additional_output (:1268-1291): patch gathers, written straight into the D2 input buffers
@@ -215,7 +316,7 @@ class SinSKITGModel:
         D.bwd(cr, dpr)
         del cr
         self._allreduce(D)
-        self._adam(D, opt.lr)
+        self._adam(D, 0)
 
         # ---- D2 step (:654-667, compute_D2_loss): touch patches conditioned on sketch + augmented image + mask
         D2.zero_grad()
@@ -224,13 +325,8 @@ class SinSKITGModel:
         del c2f
         if opt.run_full_res_D2:  # visualisation only in the reference (:1495-1500); updates BN running stats
             self.pred_fake_T_full = D2.fwd([fake_T, self.real_S, self.aug_fake_I, self.M], save=False)[0][-1]
-        if opt.use_more_fakeT:
-            if rand is not None and "fake_ox" in rand:
-                fox, foy = np.asarray(rand["fake_ox"], dtype=np.int32), np.asarray(rand["fake_oy"], dtype=np.int32)
-            else:
-                fox, foy = self._offset_table.sample(NF)
-            fox_d = torch.from_numpy(fox).to(self.device, non_blocking=True)
-            foy_d = torch.from_numpy(foy).to(self.device, non_blocking=True)
+        if opt.use_more_fakeT and NF:
+            fox_d, foy_d = self._fo_dev[0], self._fo_dev[1]
             ops.patch_gather([fake_T, self.real_S, fake_I], fox_d, foy_d, 32, ctot=7, dst=self.more_in)
             p2m, c2m = D2.fwd([self.more_in])
             D2.bwd(c2m, self._gan(p2m, +1.0, sl["D2_more"], 0.5 * opt.lambda_G2_GAN / NF))
@@ -239,7 +335,7 @@ class SinSKITGModel:
         D2.bwd(c2r, self._gan(p2r, -1.0, sl["D2_real"], 0.5 * opt.lambda_G2_GAN / NT))
         del c2r
         self._allreduce(D2)
-        self._adam(D2, opt.lr_G2)
+        self._adam(D2, 1)
 
         # ---- G step (:680-694): GAN through the updated (frozen) D, L1, patch L1; G2 GAN is value-only
         G.zero_grad()
@@ -258,7 +354,7 @@ class SinSKITGModel:
         G.bwd(self._g_ctx, dI, dT)
         self._g_ctx = None
         self._allreduce(G)
-        self._adam(G, opt.lr)
+        self._adam(G, 2)
         self._loss_raw = (L, NT, NF)
         return L
 
