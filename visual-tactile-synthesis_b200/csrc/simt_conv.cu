@@ -343,59 +343,75 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
     }
 }
 
-// dbias[o] += sum over pixels of dy (operand with halo).  grid: (pixel chunks, n), block 256.
+// dbias[o] += sum over pixels of dy (operand with halo).  grid: (pixel chunks, n), block 256 = 8 pixel
+// lanes x 32 channel lanes: a warp reads 32 consecutive channels of one pixel (coalesced), the 8 pixel
+// lanes are combined through shared memory before one atomic per channel per CTA.
 template <int DFMT>
 __global__ void __launch_bounds__(256) dbias_kernel(const float* d0, const __nv_bfloat16* dh, const __nv_bfloat16* dl,
                                                     int dhp, int dwp, int co, int dorg, int ho, int wo,
                                                     int chunk, float* dbias) {
+    __shared__ float red[8][33];
     const int n = blockIdx.y;
     const int P = ho * wo;
     const int pbeg = blockIdx.x * chunk, pend = min(P, pbeg + chunk);
-    for (int o = threadIdx.x; o < co; o += blockDim.x) {
+    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    for (int o0 = 0; o0 < co; o0 += 32) {
+        const int o = o0 + cl;
         float s = 0.f;
-        for (int pix = pbeg; pix < pend; pix++) {
-            int oy = pix / wo, ox = pix - oy * wo;
-            long long a = (((long long)n * dhp + dorg + oy) * dwp + dorg + ox) * co + o;
-            s += (DFMT == SKIT_FMT_F32) ? d0[a] : (__bfloat162float(dh[a]) + __bfloat162float(dl[a]));
+        if (o < co) {
+            for (int pix = pbeg + pl; pix < pend; pix += 8) {
+                int oy = pix / wo, ox = pix - oy * wo;
+                long long a = (((long long)n * dhp + dorg + oy) * dwp + dorg + ox) * co + o;
+                s += (DFMT == SKIT_FMT_F32) ? d0[a] : (__bfloat162float(dh[a]) + __bfloat162float(dl[a]));
+            }
         }
-        atomicAdd(dbias + o, s);
+        red[pl][cl] = s;
+        __syncthreads();
+        if (pl == 0 && o < co) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) t += red[i][cl];
+            atomicAdd(dbias + o, t);
+        }
+        __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------------- weight packs
+// Iterates in OUTPUT order (coalesced bf16 / fp32 stores; the scattered side is the L2-resident source).
+// The bf16 packs are [tap][N][K] (K innermost), the fp32 packs [tap][K][N] (N innermost):
+//   mode 0: K = conv ci, N = conv co.   modes 1-3 (input-gradient packs): K = conv co, N = conv ci.
+__device__ __forceinline__ long long pack_src_index(int mode, int k, int co, int ci, int tap, int o, int c) {
+    int ky, kx;
+    if (mode == 0 || mode == 2) { ky = tap / k; kx = tap - ky * k; }
+    else if (mode == 1) { const int f = k * k - 1 - tap; ky = f / k; kx = f - ky * k; }
+    else {  // mode 3: tap = phase*(k/2)^2 + (k/2-1-ky/2)*(k/2) + (k/2-1-kx/2), phase = (ky%2)*2 + kx%2
+        const int kh = k / 2, phase = tap / (kh * kh), r = tap - phase * kh * kh;
+        const int a = r / kh, b2 = r - a * kh;
+        ky = 2 * (kh - 1 - a) + (phase >> 1); kx = 2 * (kh - 1 - b2) + (phase & 1);
+    }
+    return (((long long)o * ci + c) * k + ky) * k + kx;
+}
+
 __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci, int k, int mode,
                                     float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo) {
     const long long total = (long long)co * ci * k * k;
+    const int Kd = mode == 0 ? ci : co, Nd = mode == 0 ? co : ci;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int kx = i % k; long long t = i / k;
-        int ky = t % k; t /= k;
-        int c = t % ci; int o = t / ci;
-        float v = w[i];
-        int tap; long long fidx, bidx;
-        if (mode == 0) {  // forward: GEMM K = (tap, c), N = o
-            tap = ky * k + kx;
-            fidx = ((long long)tap * ci + c) * co + o;
-            bidx = ((long long)tap * co + o) * ci + c;
-        } else if (mode == 1) {  // stride-1 dgrad: K = (flipped tap, o), N = c
-            tap = (k - 1 - ky) * k + (k - 1 - kx);
-            fidx = ((long long)tap * co + o) * ci + c;
-            bidx = ((long long)tap * ci + c) * co + o;
-        } else if (mode == 2) {  // gather dgrad: K = (tap, o), N = c
-            tap = ky * k + kx;
-            fidx = ((long long)tap * co + o) * ci + c;
-            bidx = ((long long)tap * ci + c) * co + o;
-        } else {  // stride-2 phase dgrad: phase (ky%2, kx%2), flipped (k/2 x k/2) sub-filter; K = o, N = c
-            const int kh = k / 2;
-            const int phase = (ky & 1) * 2 + (kx & 1);
-            tap = phase * kh * kh + (kh - 1 - ky / 2) * kh + (kh - 1 - kx / 2);
-            fidx = ((long long)tap * co + o) * ci + c;
-            bidx = ((long long)tap * ci + c) * co + o;
-        }
-        if (f32) f32[fidx] = v;
-        if (hi) {
+        if (hi) {   // [tap][N][K]
+            const int kk = (int)(i % Kd); long long t = i / Kd;
+            const int nn = (int)(t % Nd); const int tap = (int)(t / Nd);
+            const int o = mode == 0 ? nn : kk, c = mode == 0 ? kk : nn;
+            const float v = __ldg(w + pack_src_index(mode, k, co, ci, tap, o, c));
             __nv_bfloat16 h, l;
             split_bf16(v, h, l);
-            hi[bidx] = h; lo[bidx] = l;
+            hi[i] = h; lo[i] = l;
+        }
+        if (f32) {  // [tap][K][N]
+            const int nn = (int)(i % Nd); long long t = i / Nd;
+            const int kk = (int)(t % Kd); const int tap = (int)(t / Kd);
+            const int o = mode == 0 ? nn : kk, c = mode == 0 ? kk : nn;
+            f32[i] = __ldg(w + pack_src_index(mode, k, co, ci, tap, o, c));
         }
     }
 }
@@ -524,7 +540,7 @@ extern "C" int skit_conv2d_wgrad(const skit_operand* x, int org, const skit_oper
         if (rc) return rc;
     }
     if (dbias) {
-        int chunk = max(64, cdiv(P, 64));
+        int chunk = max(64, cdiv(P, max(1, (148 * 4) / n)));
         dim3 grid(cdiv(P, chunk), n);
         if (dy->fmt == SKIT_FMT_F32)
             dbias_kernel<0><<<grid, 256, 0, st>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, co, dy_org, ho, wo, chunk, dbias);

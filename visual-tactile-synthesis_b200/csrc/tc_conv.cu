@@ -239,7 +239,6 @@ int conv_tc_launch(const skit_operand* x, const void* w_hi, const void* w_lo, in
                    int tap_base, int stride, int org, int ho, int wo, const float* bias, float* y, const TcOut* out,
                    double* stats, int stats_mode, cudaStream_t st) {
     using namespace tc;
-    const int BN = (co % 256 == 0) ? 256 : (co % 128 == 0) ? 128 : 64;
     TcConvP p{};
     p.k = k; p.kc = ci / 64; p.org = org; p.stride = stride; p.tap_base = tap_base; p.ho = ho; p.wo = wo; p.co = co;
     p.tw = (wo <= 8) ? 8 : 16; p.th = 128 / p.tw;
@@ -248,6 +247,24 @@ int conv_tc_launch(const skit_operand* x, const void* w_hi, const void* w_lo, in
     else { p.OH = ho; p.OW = wo; p.osy = 1; p.osx = 1; p.ooy = 0; p.oox = 0; }
     p.bias = bias; p.y = y; p.stats = stats; p.stats_per_n = stats_mode == SKIT_NORM_INSTANCE;
     const int tiles_y = cdiv(ho, p.th);
+    // N tile: the widest tile is the most L2-efficient (the activation box is re-read per N tile), but small maps
+    // leave most SMs idle and 148 < CTAs <= 296 wastes a wave.  Cost model per CTA and K step (cycles): the MMAs
+    // (3 x 4 x BN/2 at 128x(BN)x16 per ~BN/2 cycles) against the smem fill (A box, 4x for stride 2 because TMA
+    // element strides traverse the dense box, plus the weight box) at ~64 B/cycle/SM; total = waves x per-CTA cost.
+    int BN = 64;
+    {
+        const long long tiles = (long long)p.tiles_x * tiles_y * x->n;
+        double best = 1e30;
+        for (int cand = 256; cand >= 64; cand >>= 1) {
+            if (co % cand) continue;
+            const double mma = 12.0 * cand * 0.53;
+            const double fill = (32768.0 * stride * stride + cand * 256.0) / 64.0 + 300.0;
+            const double per = mma > fill ? mma : fill;
+            const long long ctas = tiles * (co / cand);
+            const double cost = (double)((ctas + 147) / 148) * per;
+            if (cost < best * 0.97) { best = cost; BN = cand; }
+        }
+    }
 
     CUtensorMap a_hi, a_lo, m_hi, m_lo;
     {
