@@ -110,6 +110,20 @@ int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, int co,
 int skit_conv2d_dgrad_s2(const skit_operand* dy, int dy_pad, const skit_weights* wp, int k,
                          int ho, int wo, int hp, int wp_, float* dx, void* stream);
 
+/* nn.ConvTranspose2d forward (thirdparty/unet/unet_parts_custom.py:63: k4, stride 2, padding 1), as the gather form
+ * of a strided conv's input gradient cropped by `pad`:
+ *   y[n][oy][ox][y_c0 + c] = bias[c] + sum_{ky,kx,o : (oy+pad-ky)%s==0, (ox+pad-kx)%s==0} x[n][(oy+pad-ky)/s][(ox+pad-kx)/s][o] * w[o][c][ky][kx]
+ * x: dense NHWC fp32 [n][h][w][ci]; wg: mode-2 pack of the ConvTranspose2d weight [ci][co][k][k] taken as a conv weight
+ * (co_conv = ci, ci_conv = co); y: NHWC fp32 with y_ctot channels, this call fills [y_c0, y_c0 + co).  stats as in
+ * skit_conv2d_fwd.  Its backward is skit_conv2d_fwd (dx: stride-s conv of the pad-haloed dy with the mode-0 pack) and
+ * skit_conv2d_wgrad with the operand roles swapped (x := haloed dy, dy := x). */
+int skit_conv_transpose2d_fwd(const float* x, int n, int h, int w, int ci, const skit_weights* wg, int stride, int pad,
+                              int ho, int wo, const float* bias, float* y, int y_ctot, int y_c0,
+                              double* stats, int stats_mode, void* stream);
+
+/* dbias[o] += sum over images and the [ho][wo] window at dy_org of an operand (bias gradient of a layer without norm). */
+int skit_dbias(const skit_operand* dy, int dy_org, int ho, int wo, float* dbias, void* stream);
+
 /* Weight gradient (autograd of F.conv2d w.r.t. weight and bias):
  *   dw[o][c][ky][kx] += sum_{n,oy,ox} dy[n][oy][ox][o] * x[n][org+oy*s+ky][org+ox*s+kx][c]
  * dy is an operand (fp32 or bf16x2) read with halo offset dy_org.  `scratch` is k*k*ci*co floats, ZEROED by
@@ -135,6 +149,13 @@ int skit_norm_act_pad(const float* raw, int n, int h, int w, int c,
                       int act, const float* residual, float* out,
                       const skit_operand* op, int pad, int pad_mode, void* stream);
 
+/* Same, writing channels [c_off, c_off + c) of a wider operand (op->c >= c_off + c): builds `ReLU(cat(x, skip))`
+ * of the U-Net decoder (thirdparty/unet/unet_parts_custom.py:46-79) slice by slice, never materialising the cat. */
+int skit_norm_act_pad_ex(const float* raw, int n, int h, int w, int c,
+                         const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                         int act, const float* residual, float* out,
+                         const skit_operand* op, int c_off, int pad, int pad_mode, void* stream);
+
 /* Backward, phase A: fold the halo gradient back (adjoint of the padding), add an optional dense
  * gradient, apply act', and reduce the two norm-backward sums.
  *   g = act'(pre) * ( fold(dpad) + dadd ),  pre = norm(raw)*gamma+beta
@@ -144,6 +165,16 @@ int skit_act_norm_bwd_reduce(const float* dpad, int pad, int pad_mode, const flo
                              const float* raw, int n, int h, int w, int c,
                              const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
                              int act, float* g, double* sums, void* stream);
+
+/* Same with the dense gradient(s) given as channel slices [dadd_c0, dadd_c0 + c) of NHWC tensors with dadd_ctot
+ * channels (the gradient of a concatenated decoder input), an optional second one (twin RGB / touch decoders,
+ * networks.py:1635-1644), and an optional ReLU mask [pre > 0] on them (the decoder's in-place ReLU acts on the
+ * concat, i.e. on the LeakyReLU'd skip tensor: SURVEY.md section 3.3). */
+int skit_act_norm_bwd_reduce_ex(const float* dpad, int pad, int pad_mode,
+                                const float* dadd, const float* dadd2, int dadd_c0, int dadd_ctot, int dadd_relu_mask,
+                                const float* raw, int n, int h, int w, int c,
+                                const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                int act, float* g, double* sums, void* stream);
 
 /* Backward, phase B: d_raw = gamma*rstd*( g - S0/count - xhat*S1/count )  (norm none: d_raw = g),
  * written as a zero-haloed operand (pad q) in fmt, ready for dgrad/wgrad.
@@ -177,6 +208,11 @@ int skit_g_head_fwd(const float* raw, const float* mask, int n, int h, int w, fl
 /* d_raw[n][h][w][5] = [dI, dT] * M * (1 - tanh(raw)^2), written as a zero-haloed fp32 operand (pad q). */
 int skit_g_head_bwd(const float* raw, const float* mask, const float* dI, const float* dT,
                     int n, int h, int w, const skit_operand* op, int pad, void* stream);
+
+/* Same gradient as two zero-haloed fp32 operands (3 RGB channels, 2 touch channels) for the twin decoders of the
+ * default U-Net generator, whose last layers are separate transposed convs (networks.py:1635-1644). raw: [n][h][w][5]. */
+int skit_g_head_bwd_split(const float* raw, const float* mask, const float* dI, const float* dT,
+                          int n, int h, int w, const skit_operand* opI, const skit_operand* opT, int pad, void* stream);
 
 /* DiffAugment policy 'bs' followed by *M (thirdparty/DiffAugment.py:25-33; sinskitG_model.py:1330-1340).
  * u_b, u_s: [n] device floats (the host's torch.rand draws). x: [n][3][h][w]. */

@@ -115,6 +115,73 @@ def test_resnet_generator_ngf64_tcgen05_fwd_bwd(V, hw, n, nb):
     print("worst grad rel err", worst)
 
 
+def test_unet_custom_generator_matches_reference_golden(V, golden_dir):
+    """Default generator `unet256_custom` (+ skitG's style-code variant): weights, input and output come from
+    the real reference run (oracle/make_golden.py)."""
+    z = np.load(os.path.join(golden_dir, "networks.npz"))
+    sd = load_sd(z, "Gunet.")
+    ngf = sd["down0.model.0.weight"].shape[0]
+    G = V.define_G(9, 5, ngf, "unet256_custom", "instance", False, "xavier", 0.02, False, False, [],
+                   opt_ns(batch_size=1), num_layer_separate=4)
+    assert set(G.state_dict().keys()) == set(sd.keys())
+    G = G.cuda()
+    G.load_state_dict(sd)
+    x = rand_input(12, 1, 9, 256, 256).cuda()
+    y = G(x)
+    assert y.shape == (1, 5, 256, 256)
+    assert rel(y[..., ::4, ::4], z["Gunet_out"]) < TIGHT
+    assert abs(y.double().norm().item() / float(z["Gunet_out_norm"]) - 1) < 1e-4
+    # skitG: style code tiled + concatenated at the innermost level (networks.py:1600-1623)
+    sds = load_sd(z, "Gunet_style.")
+    opt_s = opt_ns(batch_size=1, use_style_code=True, style_code_mode="concat", style_code_mapping_mode="tile",
+                   style_code_dim=16, num_layer_style_code=1)
+    Gs = V.networks.CustomUnetGenerator(9, 5, num_downs=8, ngf=sds["down0.model.0.weight"].shape[0], num_layer_separate=4,
+                                        opt=opt_s, input_size=256).cuda()
+    missing = Gs.load_state_dict(sds, strict=False)
+    assert all("style_code_mapping" in k for k in missing.missing_keys) and not missing.unexpected_keys
+    ys = Gs(x, style_code=torch.from_numpy(z["Gunet_style_code"]).half().cuda())
+    assert rel(ys[..., ::4, ::4], z["Gunet_style_out"]) < TIGHT
+    with pytest.raises(NotImplementedError):
+        V.define_G(9, 5, 8, "unet256_custom", "batch", False, "xavier", 0.02, False, False, [], opt_ns(batch_size=1))
+
+
+@pytest.mark.parametrize("ngf,nls,n", [(10, 4, 1), (4, 0, 2), (8, 8, 1)])
+def test_unet_custom_generator_fwd_bwd(V, ngf, nls, n):
+    """Explicit forward/backward of the U-Net (transposed convs, sliced concat operands, twin decoders, aliased
+    LeakyReLU skips) vs autograd on the CPU oracle."""
+    from oracle import skit_oracle as O
+    torch.manual_seed(5)
+    G = V.define_G(9, 5, ngf, "unet256_custom", "instance", False, "xavier", 1.0, False, False, [], opt_ns(batch_size=1),
+                   num_layer_separate=nls)
+    sd = {k: v.clone() for k, v in G.state_dict().items()}
+    G = G.cuda()
+    G.ensure_flat()
+    G.refresh_packs()
+    hw = (256, 256)
+    x = rand_input(5, n, 9, *hw)
+    M = (rand_input(6, n, 1, *hw) > -0.8).float()
+    RI, RT = rand_input(7, n, 3, *hw), rand_input(8, n, 2, *hw)
+    ps = {k: v.requires_grad_(True) for k, v in sd.items()}
+    out = O.unet_custom_forward(ps, x)
+    fI, fT = out[:, :3] * M, out[:, 3:] * M
+    ((fI * RI).sum() + (fT * RT).sum()).backward()
+    (kI, kT, kN), ctx, _ = G.fwd([x.cuda()], mask=M.cuda())
+    G.zero_grad()
+    G.bwd(ctx, RI.cuda(), RT.cuda())
+    torch.cuda.synchronize()
+    assert rel(kI, fI) < TIGHT and rel(kT, fT) < TIGHT
+    worst = 0.0
+    for k, p in G.named_parameters():
+        lvl = int(k.split(".")[0].replace("_T", "").replace("down", "").replace("up", ""))
+        normed = (k.startswith("down") and 0 < lvl < 7) or (k.startswith("up") and lvl > 0)
+        if k.endswith("bias") and normed:
+            continue  # bias before InstanceNorm: exactly zero gradient in exact arithmetic
+        r = rel(p.grad, ps[k].grad)
+        worst = max(worst, r)
+        assert r < GRAD_REL and cos(p.grad, ps[k].grad) > GRAD_COS, (k, r)
+    print("worst grad rel err", worst)
+
+
 def test_multiscale_discriminator_matches_reference_golden(V, golden_dir):
     z = np.load(os.path.join(golden_dir, "networks.npz"))
     sd = load_sd(z, "D_before.")

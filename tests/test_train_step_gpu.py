@@ -47,13 +47,14 @@ def check_grads(net, ref_grads, tag):
     return worst
 
 
-def test_train_step_matches_reference_golden(golden_dir):
+@pytest.mark.parametrize("tag,netG,wkey", [("resnet", "resnet_9blocks", "model.1.weight"), ("unet", "unet256_custom", "down0.model.0.weight")])
+def test_train_step_matches_reference_golden(golden_dir, tag, netG, wkey):
     import vts_b200
     from oracle import skit_oracle as O
-    z = np.load(os.path.join(golden_dir, "step_resnet.npz"))
+    z = np.load(os.path.join(golden_dir, "step_%s.npz" % tag))
     S, NT, NF = [int(v) for v in z["meta"]]
     sdG, sdD, sdD2 = sd_from(z, "G_before."), sd_from(z, "D_before."), sd_from(z, "D2_before.")
-    opt = vts_b200.default_options(ngf=sdG["model.1.weight"].shape[0], ndf=sdD["layer0.0.weight"].shape[0],
+    opt = vts_b200.default_options(netG=netG, ngf=sdG[wkey].shape[0], ndf=sdD["layer0.0.weight"].shape[0],
                                    batch_size_G2=NT, add_fake_T_sample_size=NF, run_full_res_D2=True)
     m = vts_b200.SinSKITGModel(opt)
     m.netG.load_state_dict(sdG)

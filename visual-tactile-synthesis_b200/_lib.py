@@ -41,6 +41,11 @@ SIGNATURES = {
     "skit_conv2d_wgrad": [_OP, _I, _OP, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "skit_stats_finalize": [_P, _I, _I, _D, _F, _P, _P, _P, _F, _P],
     "skit_norm_act_pad": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _OP, _I, _I, _P],
+    "skit_norm_act_pad_ex": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _OP, _I, _I, _I, _P],
+    "skit_act_norm_bwd_reduce_ex": [_P, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P],
+    "skit_conv_transpose2d_fwd": [_P, _I, _I, _I, _I, _WT, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P],
+    "skit_dbias": [_OP, _I, _I, _I, _P, _P],
+    "skit_g_head_bwd_split": [_P, _P, _P, _P, _I, _I, _I, _OP, _OP, _I, _P],
     "skit_act_norm_bwd_reduce": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P],
     "skit_norm_bwd_apply": [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _D, _P, _P, _OP, _I, _P],
     "skit_blur_down_fwd": [_P, _I, _I, _I, _I, _P, _P],

@@ -132,6 +132,35 @@ __global__ void __launch_bounds__(256) g_head_bwd_kernel(const float* __restrict
     }
 }
 
+// Same gradient, written as two zero-haloed operands: the RGB (3 ch) and the touch (2 ch) decoders of the default
+// U-Net generator end in separate transposed convs (networks.py:1635-1644).
+__global__ void __launch_bounds__(256) g_head_bwd_split_kernel(const float* __restrict__ raw, const float* __restrict__ mask,
+                                                               const float* __restrict__ dI, const float* __restrict__ dT,
+                                                               int n, int h, int w, float* dstI, float* dstT, int pad) {
+    const int hp = h + 2 * pad, wp = w + 2 * pad;
+    const long long hw = (long long)h * w, total = (long long)n * hp * wp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int px = (int)(i % wp);
+        long long t = i / wp;
+        const int py = (int)(t % hp);
+        const long long b = t / hp;
+        const int y = py - pad, x = px - pad;
+        float v[5] = {0, 0, 0, 0, 0};
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+            const long long pix = (long long)y * w + x;
+            const float m = mask ? mask[b * hw + pix] : 1.f;
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const float th = tanhf(raw[(b * hw + pix) * 5 + j]);
+                const float d = j < 3 ? (dI ? dI[(b * 3 + j) * hw + pix] : 0.f) : (dT ? dT[(b * 2 + (j - 3)) * hw + pix] : 0.f);
+                v[j] = d * m * (1.f - th * th);
+            }
+        }
+        dstI[i * 3 + 0] = v[0]; dstI[i * 3 + 1] = v[1]; dstI[i * 3 + 2] = v[2];
+        dstT[i * 2 + 0] = v[3]; dstT[i * 2 + 1] = v[4];
+    }
+}
+
 // ------------------------------------------------------------------------------ DiffAugment 'bs' * M
 __global__ void __launch_bounds__(256) diffaug_kernel(const float* __restrict__ x, const float* __restrict__ mask,
                                                       const float* __restrict__ ub, const float* __restrict__ us, int n, int h, int w, float* y) {
@@ -452,6 +481,17 @@ extern "C" int skit_g_head_bwd(const float* raw, const float* mask, const float*
     SKIT_REQUIRE(op->n == n && op->hp == h + 2 * pad && op->wp == w + 2 * pad && op->c == 5, "g_head_bwd: operand dims mismatch");
     g_head_bwd_kernel<<<grid_for((long long)n * op->hp * op->wp, 256), 256, 0, as_stream(stream)>>>(raw, mask, dI, dT, n, h, w, (float*)op->p0, pad);
     return check_launch("g_head_bwd_kernel");
+}
+
+extern "C" int skit_g_head_bwd_split(const float* raw, const float* mask, const float* dI, const float* dT,
+                                     int n, int h, int w, const skit_operand* opI, const skit_operand* opT, int pad, void* stream) {
+    SKIT_REQUIRE(raw && (dI || dT) && opI && opT && opI->p0 && opT->p0 && opI->fmt == SKIT_FMT_F32 && opT->fmt == SKIT_FMT_F32,
+                 "g_head_bwd_split: bad arguments (fp32 operands required)");
+    SKIT_REQUIRE(opI->n == n && opI->hp == h + 2 * pad && opI->wp == w + 2 * pad && opI->c == 3 &&
+                 opT->n == n && opT->hp == h + 2 * pad && opT->wp == w + 2 * pad && opT->c == 2, "g_head_bwd_split: operand dims mismatch");
+    g_head_bwd_split_kernel<<<grid_for((long long)n * opI->hp * opI->wp, 256), 256, 0, as_stream(stream)>>>(
+        raw, mask, dI, dT, n, h, w, (float*)opI->p0, (float*)opT->p0, pad);
+    return check_launch("g_head_bwd_split_kernel");
 }
 
 extern "C" int skit_diffaug_bs_mask(const float* x, const float* mask, const float* u_b, const float* u_s,

@@ -41,6 +41,7 @@ struct PrepP {
     float* out;                      // dense [n][h][w][c] or NULL
     float* o0; __nv_bfloat16* oh; __nv_bfloat16* ol; int fmt;  // operand planes or NULL
     int pad, pad_mode;
+    int oc, ooff;                    // operand channel count and the channel offset this call fills (concat slices)
 };
 
 template <int VEC>
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(PrepP p) {
                 else p.out[src] = v[0];
             }
         }
-        const long long dst = (((long long)n * hp + py) * wp + px) * p.c + ch;
+        const long long dst = (((long long)n * hp + py) * wp + px) * p.oc + p.ooff + ch;
         if (p.o0 && p.fmt == SKIT_FMT_F32) {
             if (VEC == 4) *reinterpret_cast<float4*>(p.o0 + dst) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
             else p.o0[dst] = v[0];
@@ -106,6 +107,8 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(PrepP p) {
 struct BwdAP {
     const float* dpad; int pad, pad_mode;
     const float* dadd;
+    const float* dadd2;        // optional second dense gradient with the same slice geometry
+    int dc0, dctot, dmask;     // dadd/dadd2 are channel slices [dc0, dc0+c) of [n][h][w][dctot]; dmask: multiply them by [pre > 0]
     const float* raw; int n, h, w, c;
     const float* mr; int per_n;
     const float* gamma; const float* beta;
@@ -160,8 +163,16 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_kernel(BwdAP p) {
                 const int y = pix / p.w, x = pix - y * p.w;
                 const long long src = (((long long)n * p.h + y) * p.w + x) * p.c + ch;
                 float d[VEC];
+                const long long dsrc = (((long long)n * p.h + y) * p.w + x) * p.dctot + p.dc0 + ch;
 #pragma unroll
-                for (int j = 0; j < VEC; j++) d[j] = p.dadd ? p.dadd[src + j] : 0.f;
+                for (int j = 0; j < VEC; j++) d[j] = (p.dadd ? p.dadd[dsrc + j] : 0.f) + (p.dadd2 ? p.dadd2[dsrc + j] : 0.f);
+                if (p.dmask) {
+#pragma unroll
+                    for (int j = 0; j < VEC; j++) {
+                        const float xh = ((p.raw ? p.raw[src + j] : 0.f) - mean[j]) * rstd[j];
+                        if (!(xh * gam[j] + bet[j] > 0.f)) d[j] = 0.f;
+                    }
+                }
                 if (p.dpad) {
                     int ys[3], xs[3];
                     const int ny = fold_coords(y, p.pad, p.h, p.pad_mode, ys);
@@ -430,17 +441,19 @@ extern "C" int skit_stats_finalize(const double* stats, int groups, int c, doubl
     return check_launch("stats_finalize_kernel");
 }
 
-extern "C" int skit_norm_act_pad(const float* raw, int n, int h, int w, int c,
-                                 const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
-                                 int act, const float* residual, float* out,
-                                 const skit_operand* op, int pad, int pad_mode, void* stream) {
+extern "C" int skit_norm_act_pad_ex(const float* raw, int n, int h, int w, int c,
+                                    const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                    int act, const float* residual, float* out,
+                                    const skit_operand* op, int c_off, int pad, int pad_mode, void* stream) {
     SKIT_REQUIRE(raw && n > 0 && h > 0 && w > 0 && c > 0, "norm_act_pad: bad arguments");
     SKIT_REQUIRE(out || op, "norm_act_pad: nothing to write");
     SKIT_REQUIRE((norm_mode == SKIT_NORM_NONE) == (mean_rstd == nullptr), "norm_act_pad: mean_rstd must be given iff norm_mode != none");
     SKIT_REQUIRE((gamma == nullptr) == (beta == nullptr), "norm_act_pad: gamma/beta must come in pairs");
     SKIT_REQUIRE(pad >= 0 && (pad_mode != SKIT_PAD_REFLECT || (pad < h && pad < w)), "norm_act_pad: reflect pad %d too large for %dx%d", pad, h, w);
     if (!op) pad = 0;
-    int rc = check_operand(op, n, h, w, c, pad, "norm_act_pad");
+    const int oc = op ? op->c : c;
+    SKIT_REQUIRE(c_off >= 0 && c_off + c <= oc, "norm_act_pad: channel slice [%d, %d) exceeds the operand's %d channels", c_off, c_off + c, oc);
+    int rc = check_operand(op, n, h, w, oc, pad, "norm_act_pad");
     if (rc) return rc;
     PrepP p{};
     p.raw = raw; p.n = n; p.h = h; p.w = w; p.c = c;
@@ -451,27 +464,39 @@ extern "C" int skit_norm_act_pad(const float* raw, int n, int h, int w, int c,
         if (op->fmt == SKIT_FMT_F32) p.o0 = (float*)op->p0;
         else { p.oh = (__nv_bfloat16*)op->p0; p.ol = (__nv_bfloat16*)op->p1; }
     }
-    p.pad = pad; p.pad_mode = pad_mode;
+    p.pad = pad; p.pad_mode = pad_mode; p.oc = oc; p.ooff = c_off;
     const long long pix = (long long)n * (h + 2 * pad) * (w + 2 * pad);
-    if (c % 4 == 0) norm_act_pad_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
+    if (c % 4 == 0 && oc % 4 == 0 && c_off % 4 == 0) norm_act_pad_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
     else norm_act_pad_kernel<1><<<grid_for(pix * c, 256), 256, 0, as_stream(stream)>>>(p);
     return check_launch("norm_act_pad_kernel");
 }
 
-extern "C" int skit_act_norm_bwd_reduce(const float* dpad, int pad, int pad_mode, const float* dadd,
-                                        const float* raw, int n, int h, int w, int c,
-                                        const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
-                                        int act, float* g, double* sums, void* stream) {
+extern "C" int skit_norm_act_pad(const float* raw, int n, int h, int w, int c,
+                                 const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                 int act, const float* residual, float* out,
+                                 const skit_operand* op, int pad, int pad_mode, void* stream) {
+    SKIT_REQUIRE(!op || op->c == c, "norm_act_pad: operand has %d channels, expected %d", op ? op->c : 0, c);
+    return skit_norm_act_pad_ex(raw, n, h, w, c, mean_rstd, norm_mode, gamma, beta, act, residual, out, op, 0, pad, pad_mode, stream);
+}
+
+extern "C" int skit_act_norm_bwd_reduce_ex(const float* dpad, int pad, int pad_mode,
+                                           const float* dadd, const float* dadd2, int dadd_c0, int dadd_ctot, int dadd_relu_mask,
+                                           const float* raw, int n, int h, int w, int c,
+                                           const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                           int act, float* g, double* sums, void* stream) {
     SKIT_REQUIRE(g && (dpad || dadd) && n > 0 && h > 0 && w > 0 && c > 0, "act_norm_bwd_reduce: bad arguments");
-    SKIT_REQUIRE(raw || (norm_mode == SKIT_NORM_NONE && act == SKIT_ACT_NONE), "act_norm_bwd_reduce: raw required unless norm and act are both none");
+    SKIT_REQUIRE(raw || (norm_mode == SKIT_NORM_NONE && act == SKIT_ACT_NONE && !dadd_relu_mask), "act_norm_bwd_reduce: raw required unless norm, act and mask are all none");
     SKIT_REQUIRE((norm_mode == SKIT_NORM_NONE) == (mean_rstd == nullptr), "act_norm_bwd_reduce: mean_rstd must be given iff norm_mode != none");
     SKIT_REQUIRE(norm_mode == SKIT_NORM_NONE || sums, "act_norm_bwd_reduce: sums required with a norm");
     SKIT_REQUIRE(pad_mode == SKIT_PAD_ZERO || pad_mode == SKIT_PAD_REFLECT, "act_norm_bwd_reduce: unsupported pad mode");
     SKIT_REQUIRE((gamma == nullptr) == (beta == nullptr), "act_norm_bwd_reduce: gamma/beta must come in pairs");
+    SKIT_REQUIRE(!dadd2 || dadd, "act_norm_bwd_reduce: dadd2 without dadd");
+    SKIT_REQUIRE(dadd_c0 >= 0 && dadd_c0 + c <= dadd_ctot, "act_norm_bwd_reduce: dadd slice [%d, %d) exceeds %d channels", dadd_c0, dadd_c0 + c, dadd_ctot);
     const int vec = (c % 4 == 0) ? 4 : 1;
     SKIT_REQUIRE(c / vec <= 256, "act_norm_bwd_reduce: channel count %d too large", c);
     BwdAP p{};
-    p.dpad = dpad; p.pad = dpad ? pad : 0; p.pad_mode = pad_mode; p.dadd = dadd;
+    p.dpad = dpad; p.pad = dpad ? pad : 0; p.pad_mode = pad_mode; p.dadd = dadd; p.dadd2 = dadd2;
+    p.dc0 = dadd_c0; p.dctot = dadd_ctot; p.dmask = dadd_relu_mask;
     p.raw = raw; p.n = n; p.h = h; p.w = w; p.c = c;
     p.mr = mean_rstd; p.per_n = norm_mode == SKIT_NORM_INSTANCE; p.gamma = gamma; p.beta = beta;
     p.act = act; p.g = g; p.sums = sums;
@@ -483,6 +508,14 @@ extern "C" int skit_act_norm_bwd_reduce(const float* dpad, int pad, int pad_mode
     if (vec == 4) act_norm_bwd_reduce_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(p);
     else act_norm_bwd_reduce_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(p);
     return check_launch("act_norm_bwd_reduce_kernel");
+}
+
+extern "C" int skit_act_norm_bwd_reduce(const float* dpad, int pad, int pad_mode, const float* dadd,
+                                        const float* raw, int n, int h, int w, int c,
+                                        const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                        int act, float* g, double* sums, void* stream) {
+    return skit_act_norm_bwd_reduce_ex(dpad, pad, pad_mode, dadd, nullptr, 0, c, 0, raw, n, h, w, c, mean_rstd, norm_mode,
+                                       gamma, beta, act, g, sums, stream);
 }
 
 extern "C" int skit_norm_bwd_apply(const float* g, const float* raw, int n, int h, int w, int c,

@@ -23,6 +23,8 @@ struct ConvP {
     int arows;            // dgrad: channels of dy (co)
     int flat;             // 1: rows run over the whole batch (n*M), grid.z == 1 (batch statistics only)
     int n_img;
+    int crop;             // dgrad as a transposed conv: output row m maps to padded coordinate (y + crop, x + crop)
+    int yc, yoff;         // output channel stride / offset (0: dense ncol) — writes a channel slice of a wider map
 };
 
 constexpr int BM = 128, BN = 64, BK = 16;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
             ry[i] = 0; rx[i] = 0;
         } else {
             int iy = m / p.wp, ix = m - iy * p.wp;
-            ry[i] = iy; rx[i] = ix;
+            ry[i] = iy + p.crop; rx[i] = ix + p.crop;
             base[i] = 0;
         }
     }
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
             int col = n0 + tx * 4 + j;
             if (col >= p.ncol) continue;
             float v = acc[i][j] + (p.bias ? p.bias[col] : 0.f);
-            p.y[((long long)(p.flat ? 0 : nz) * p.M + m) * p.ncol + col] = v;
+            p.y[((long long)(p.flat ? 0 : nz) * p.M + m) * (p.yc ? p.yc : p.ncol) + p.yoff + col] = v;
             s[j] += v; q[j] += v * v;
         }
     }
@@ -491,6 +493,44 @@ extern "C" int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, 
     dim3 grid(p.flat ? cdiv(n * p.M, BM) : cdiv(p.M, BM), cdiv(p.ncol, BN), p.flat ? 1 : n);
     conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
     return check_launch("conv_simt_kernel<dgrad>");
+}
+
+// ConvTranspose2d forward (thirdparty/unet/unet_parts_custom.py:63; F.conv_transpose2d k4 s2 p1 of the default
+// U-Net generator) = the gather form of a strided conv's input gradient, cropped by `pad`, plus bias, with the
+// InstanceNorm statistics of the result accumulated in the same epilogue.
+extern "C" int skit_conv_transpose2d_fwd(const float* x, int n, int h, int w, int ci, const skit_weights* wg, int stride, int pad,
+                                         int ho, int wo, const float* bias, float* y, int y_ctot, int y_c0,
+                                         double* stats, int stats_mode, void* stream) {
+    SKIT_REQUIRE(x && wg && wg->f32 && y && n > 0 && h > 0 && w > 0 && ci > 0, "conv_transpose2d_fwd: bad arguments");
+    SKIT_REQUIRE(wg->ci == ci, "conv_transpose2d_fwd: weight pack reduces over %d channels but x has %d", wg->ci, ci);
+    SKIT_REQUIRE(ho == (h - 1) * stride - 2 * pad + wg->k && wo == (w - 1) * stride - 2 * pad + wg->k,
+                 "conv_transpose2d_fwd: output %dx%d does not match (in-1)*stride - 2*pad + k", ho, wo);
+    SKIT_REQUIRE(y_c0 >= 0 && y_c0 + wg->co <= y_ctot, "conv_transpose2d_fwd: output slice exceeds y_ctot");
+    SKIT_REQUIRE(stats == nullptr || stats_mode == SKIT_NORM_INSTANCE || stats_mode == SKIT_NORM_BATCH, "conv_transpose2d_fwd: stats without mode");
+    ConvP p{};
+    p.x0 = x; p.hp = ho; p.wp = wo; p.ci = wg->co;
+    p.w = wg->f32; p.bias = bias; p.y = y; p.stats = stats; p.stats_per_n = stats_mode == SKIT_NORM_INSTANCE;
+    p.k = wg->k; p.stride = stride; p.org = 0; p.ho = h; p.wo = w;
+    p.ncol = wg->co; p.K = wg->k * wg->k * ci; p.M = ho * wo; p.arows = ci;
+    p.crop = pad; p.yc = y_ctot; p.yoff = y_c0;
+    p.n_img = n; p.flat = 0;
+    dim3 grid(cdiv(p.M, BM), cdiv(p.ncol, BN), n);
+    conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
+    return check_launch("conv_simt_kernel<convT>");
+}
+
+// dbias[o] += sum over (n, pixels) of an operand's interior (bias gradient of layers without a norm).
+extern "C" int skit_dbias(const skit_operand* dy, int dy_org, int ho, int wo, float* dbias, void* stream) {
+    SKIT_REQUIRE(dy && dy->p0 && dbias && ho > 0 && wo > 0, "dbias: bad arguments");
+    SKIT_REQUIRE(dy_org + ho <= dy->hp && dy_org + wo <= dy->wp, "dbias: window exceeds the operand");
+    const int P = ho * wo, n = dy->n;
+    int chunk = max(64, cdiv(P, max(1, (148 * 4) / n)));
+    dim3 grid(cdiv(P, chunk), n);
+    if (dy->fmt == SKIT_FMT_F32)
+        dbias_kernel<0><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, dy->c, dy_org, ho, wo, chunk, dbias);
+    else
+        dbias_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(nullptr, (const __nv_bfloat16*)dy->p0, (const __nv_bfloat16*)dy->p1, dy->hp, dy->wp, dy->c, dy_org, ho, wo, chunk, dbias);
+    return check_launch("dbias_kernel");
 }
 
 namespace skit {

@@ -38,6 +38,7 @@ class Conv2d(nn.Module):
     def __init__(self, ci, co, k, stride=1, bias=True):
         super().__init__()
         self.ci, self.co, self.k, self.stride = ci, co, k, stride
+        self.allow_tc = True   # the U-Net generator keeps its (mostly thin) layers on the fp32 CUDA-core kernels
         self.weight = nn.Parameter(torch.empty(co, ci, k, k))
         self.bias = nn.Parameter(torch.zeros(co)) if bias else None
         self.reset_parameters()
@@ -51,7 +52,7 @@ class Conv2d(nn.Module):
 
     @property
     def use_tc(self):
-        return TC_ENABLED and self.stride in (1, 2) and self.ci % 64 == 0 and self.co % 64 == 0 and (self.stride == 1 or self.k % 2 == 0)
+        return TC_ENABLED and self.allow_tc and self.stride in (1, 2) and self.ci % 64 == 0 and self.co % 64 == 0 and (self.stride == 1 or self.k % 2 == 0)
 
     def pack(self, mode):
         """mode 0 forward, 1 stride-1 dgrad (tensor-core), 2 gather dgrad (CUDA-core), 3 stride-2 phase dgrad (tensor-core)."""
@@ -127,7 +128,7 @@ class _FlatParamsMixin:
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
         for m in self.modules():
-            if isinstance(m, Conv2d):
+            if hasattr(m, "drop_packs"):
                 m.drop_packs()
         return self
 
@@ -145,7 +146,7 @@ class _FlatParamsMixin:
 
     def refresh_packs(self):
         for m in self.modules():
-            if isinstance(m, Conv2d):
+            if isinstance(m, Conv2d) or (m is not self and hasattr(m, "refresh_packs") and hasattr(m, "_packs")):
                 m.refresh_packs()
 
 
@@ -222,8 +223,8 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         object.__setattr__(self, "_blocks", [self.model[12 + b] for b in range(nb)])
 
     # -- explicit forward.  srcs: list of NCHW fp32 tensors whose channel concat is the input.
-    def fwd(self, srcs, mask=None, scale_nz=0.25, save=True, want_normal=True, taps=None):
-        _require_cuda(srcs[0], "ResnetGenerator")
+    def fwd(self, srcs, mask=None, scale_nz=0.25, save=True, want_normal=True, taps=None, style_code=None):
+        _require_cuda(srcs[0], "ResnetGenerator")   # style_code: accepted and ignored like the reference (networks.py:1131)
         IN = NORM_INSTANCE
         n, _, S_h, S_w = srcs[0].shape
         ctx = {}
@@ -345,6 +346,275 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
             fl = [feats[i].permute(0, 3, 1, 2) for i in layers if i in feats]  # NHWC storage, NCHW view
             return fl if encode_only else (out, fl)
         return out
+
+
+# ----------------------------------------------------------------------------- default generator (U-Net)
+class ConvTranspose2d(nn.Module):
+    """Parameter holder with nn.ConvTranspose2d's state_dict keys: weight [ci][co][k][k], bias [co]
+    (thirdparty/unet/unet_parts_custom.py:63).  Read as a conv weight with (out, in) = (ci, co) this is exactly
+    the filter of the strided conv whose input gradient the transposed conv computes."""
+
+    def __init__(self, ci, co, k=4, stride=2, padding=1):
+        super().__init__()
+        self.ci, self.co, self.k, self.stride, self.padding = ci, co, k, stride, padding
+        self.weight = nn.Parameter(torch.empty(ci, co, k, k))
+        self.bias = nn.Parameter(torch.zeros(co))
+        init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        self._packs = {}
+
+    def pack(self, mode):
+        """mode 2: forward (gather form); mode 0: input gradient (strided conv of the haloed output gradient)."""
+        pk = self._packs.get(mode)
+        if pk is None:
+            pk = ops.PackedWeights(self.weight, mode, want_f32=True, want_bf16=False)
+            self._packs[mode] = pk
+        return pk
+
+    def refresh_packs(self):
+        for pk in self._packs.values():
+            pk.refresh(self.weight)
+
+    def drop_packs(self):
+        self._packs = {}
+
+
+class _UnetDown(nn.Module):
+    """Down (unet_parts_custom.py:9-37): [LeakyReLU(0.2, inplace)] -> Conv2d k4 s2 p1 -> [InstanceNorm2d]."""
+
+    def __init__(self, ci, co, outermost=False, innermost=False):
+        super().__init__()
+        conv = Conv2d(ci, co, 4, stride=2)
+        conv.allow_tc = False
+        if outermost:
+            seq = [conv]
+        elif innermost:
+            seq = [_Placeholder("LeakyReLU(0.2)"), conv]
+        else:
+            seq = [_Placeholder("LeakyReLU(0.2)"), conv, _Placeholder("InstanceNorm2d")]
+        self.model = nn.Sequential(*seq)
+        object.__setattr__(self, "conv", conv)
+
+
+class _UnetUp(nn.Module):
+    """Up (unet_parts_custom.py:40-80): ReLU(inplace) -> ConvTranspose2d k4 s2 p1 -> InstanceNorm2d | Tanh."""
+
+    def __init__(self, ci, co, outermost=False):
+        super().__init__()
+        conv = ConvTranspose2d(ci, co)
+        self.model = nn.Sequential(_Placeholder("ReLU"), conv, _Placeholder("Tanh" if outermost else "InstanceNorm2d"))
+        object.__setattr__(self, "conv", conv)
+
+
+class CustomUnetGenerator(_FlatParamsMixin, nn.Module):
+    """`unet256_custom` (networks.py:1430-1645), the skitG / sinskitG default generator: 8 x Down, 8 x Up with twin
+    RGB / touch decoders on the `num_layer_separate` outermost levels, InstanceNorm, 5 output channels.  Quirks kept:
+    every skip tensor is the LeakyReLU'd activation (in-place aliasing), the outermost Up
+    ignores its skip, skitG's style code is tiled and concatenated to the decoder input of the innermost
+    `num_layer_style_code` levels.  All layers run on the fp32 CUDA-core kernels (channel counts 2..160)."""
+
+    def __init__(self, input_nc, output_nc, num_downs=8, ngf=64, num_layer_separate=0, opt=None, input_size=1536, **unused):
+        super().__init__()
+        assert output_nc == 5, "current architecture is designed specifiacally for 5 output channels, 3 - RGB, 2 - touch"
+        self.n_channels, self.output_nc, self.num_downs, self.opt, self.ngf = input_nc, output_nc, num_downs, opt, ngf
+        o = vars(opt) if opt is not None else {}
+        self.num_layer_style_code = num_downs if o.get("num_layer_style_code", -1) == -1 else o["num_layer_style_code"]
+        use_style = bool(o.get("use_style_code", False))
+        self.style_code_ncs = 0
+        if use_style:
+            if o.get("style_code_mode", "concat") != "concat" or o.get("style_code_mapping_mode", "tile") != "tile":
+                raise NotImplementedError("B200 path: style code is built for style_code_mode='concat' with style_code_mapping_mode='tile' (the skitG default)")
+            self.style_code_ncs = [o["style_code_dim"]] * self.num_layer_style_code
+            for i in range(self.num_layer_style_code):   # unused in 'tile' mode; kept for checkpoint compatibility (A.1)
+                out_sz = input_size // (2 ** (num_downs - i))
+                setattr(self, "style_code_mapping%d" % i, nn.Sequential(
+                    nn.Linear(o["style_code_dim"], out_sz * out_sz * o["style_code_dim"], bias=False),
+                    _Placeholder("InstanceNorm1d"), _Placeholder("ReLU")))
+        assert 0 <= num_layer_separate <= num_downs, "num_layer_separate should be in range [0, num_downs]"
+        self.num_layer_separate = num_layer_separate
+        out_main = output_nc - 2 if num_layer_separate > 0 else output_nc
+
+        def style_nc(i):
+            return self.style_code_ncs[num_downs - i - 1] if use_style and i >= num_downs - self.num_layer_style_code else 0
+
+        def chans(i):   # (down in, down out) of level i
+            if i == 0:
+                return input_nc, ngf
+            if i < num_downs // 2:
+                return ngf * 2 ** (i - 1), ngf * 2 ** i
+            return ngf * 8, ngf * 8
+
+        self._style_nc = [style_nc(i) for i in range(num_downs)]
+        for i in range(num_downs):
+            ci, co = chans(i)
+            setattr(self, "down%d" % i, _UnetDown(ci, co, outermost=i == 0, innermost=i == num_downs - 1))
+            scaler = 1 if i in (0, num_downs - 1) else 2
+            up_in = scaler * co + self._style_nc[i]
+            up_out = (out_main if i == 0 else ci)
+            setattr(self, "up%d" % i, _UnetUp(up_in, up_out, outermost=i == 0))
+            if num_layer_separate >= i + 1:
+                setattr(self, "up%d_T" % i, _UnetUp(up_in, 2 if i == 0 else ci, outermost=i == 0))
+
+    def _up(self, i, T=False):
+        m = getattr(self, "up%d%s" % (i, "_T" if T else ""), None)
+        return None if m is None else m.conv
+
+    def refresh_packs(self):
+        for m in self.modules():
+            if isinstance(m, (Conv2d, ConvTranspose2d)):
+                m.refresh_packs()
+
+    def tappable_layers(self):
+        return set()
+
+    # -- explicit forward.  srcs: NCHW fp32 tensors whose channel concat is the input.
+    def fwd(self, srcs, mask=None, scale_nz=0.25, save=True, want_normal=True, taps=None, style_code=None):
+        _require_cuda(srcs[0], "CustomUnetGenerator")
+        IN = NORM_INSTANCE
+        nd = self.num_downs
+        n, _, S_h, S_w = srcs[0].shape
+        dev = srcs[0].device
+        if S_h % (1 << nd) or S_w % (1 << nd):
+            raise ValueError("CustomUnetGenerator: input %dx%d is not divisible by 2^%d" % (S_h, S_w, nd))
+        op = ops.nchw_cat_to_operand(srcs, 1, PAD_ZERO)
+        downs, h, w = [], S_h, S_w
+        for i in range(nd):
+            conv = getattr(self, "down%d" % i).conv
+            h, w = h // 2, w // 2
+            mode = IN if 0 < i < nd - 1 else NORM_NONE
+            raw, st = ops.conv2d_fwd(op, conv.pack(0), 2, 0, h, w, bias=conv.bias, stats_mode=mode, impl=ops.IMPL_SIMT)
+            mr = ops.stats_finalize(st, h * w) if mode != NORM_NONE else None
+            downs.append((op, raw, mr, mode))
+            if i < nd - 1:   # next level's input = LeakyReLU(norm(raw)), zero halo 1 — also the (aliased) skip tensor
+                _, op = ops.norm_act_pad(raw, mr, mode, act=ACT_LRELU, pad=1, pad_mode=PAD_ZERO, fmt=FMT_F32)
+        style = None
+        if style_code is not None:
+            style = torch.relu(style_code.to(dev, torch.float32))   # the decoder's ReLU acts on the concatenated input
+        raw30 = torch.empty((n, S_h, S_w, 5), dtype=torch.float32, device=dev)
+        # x / x_T: the current decoder activations as (raw, mean_rstd, norm_mode), normalised lazily on load
+        x = (downs[nd - 1][1], None, NORM_NONE)
+        xT = None
+        ups = [None] * nd
+        for i in range(nd - 1, -1, -1):
+            has_skip = 0 < i < nd - 1
+            cst = self._style_nc[i] if style is not None else 0
+            if self._style_nc[i] and style is None:
+                raise RuntimeError("CustomUnetGenerator was built with use_style_code but forward got style_code=None")
+
+            def build(xx):
+                craw = xx[0].shape[3]
+                hh, ww = xx[0].shape[1:3]
+                ctot = craw + cst + (downs[i][1].shape[3] if has_skip else 0)
+                U = ops.Operand(n, hh, ww, ctot, 0, FMT_F32, dev)
+                ops.norm_act_pad_into(U, 0, xx[0], xx[1], xx[2], act=ACT_RELU)
+                if cst:
+                    U.data[..., craw:craw + cst] = style[:, None, None, :]
+                if has_skip:
+                    ops.norm_act_pad_into(U, craw + cst, downs[i][1], downs[i][2], downs[i][3], act=ACT_RELU)
+                return U, craw
+
+            U, cx = build(x)
+            convT = self._up(i, T=True)
+            recT = None
+            if convT is not None:
+                shared = xT is None
+                UT = U if shared else build(xT)[0]
+                if i == 0:
+                    ops.conv_transpose2d_fwd(UT.data, convT.pack(2), 2, 1, bias=convT.bias, out=raw30, out_c0=3)
+                    xT = None
+                else:
+                    rT, st = ops.conv_transpose2d_fwd(UT.data, convT.pack(2), 2, 1, bias=convT.bias, stats_mode=IN)
+                    xT = (rT, ops.stats_finalize(st, rT.shape[1] * rT.shape[2]), IN)
+                recT = (UT, shared, xT)
+            conv = self._up(i)
+            if i == 0:
+                ops.conv_transpose2d_fwd(U.data, conv.pack(2), 2, 1, bias=conv.bias, out=raw30, out_c0=0)
+                x = None
+            else:
+                r, st = ops.conv_transpose2d_fwd(U.data, conv.pack(2), 2, 1, bias=conv.bias, stats_mode=IN)
+                x = (r, ops.stats_finalize(st, r.shape[1] * r.shape[2]), IN)
+            ups[i] = (U, cx, cst, x, recT)
+        fI, fT, fN = ops.g_head_fwd(raw30, mask, scale_nz, want_normal)
+        ctx = dict(downs=downs, ups=ups, raw30=raw30, mask=mask, dims=(n, S_h, S_w)) if save else {}
+        return (fI, fT, fN), ctx, {}
+
+    @staticmethod
+    def _convT_bwd(layer, U, d_op, hin, win, want_dbias):
+        """Backward of y = convT(U): d_op is dy haloed by 1 (fp32).  -> dU dense [n, hin, win, C_U]."""
+        ops.conv2d_wgrad(d_op, 0, U, 0, layer.k, layer.stride, hin, win, layer.weight.grad, None, impl=ops.IMPL_SIMT)
+        if want_dbias:
+            ops.dbias(d_op, 1, 2 * hin, 2 * win, layer.bias.grad)
+        dU, _ = ops.conv2d_fwd(d_op, layer.pack(0), layer.stride, 0, hin, win, impl=ops.IMPL_SIMT)
+        return dU
+
+    # -- explicit backward: dI [n,3,h,w], dT [n,2,h,w] are gradients w.r.t. fake_I / fake_T (after *M).
+    def bwd(self, ctx, dI, dT):
+        IN = NORM_INSTANCE
+        nd = self.num_downs
+        n, S_h, S_w = ctx["dims"]
+        downs, ups = ctx["downs"], ctx["ups"]
+        twin0 = self._up(0, T=True) is not None
+        if twin0:
+            d_main, d_T = ops.g_head_bwd_split(ctx["raw30"], ctx["mask"], dI, dT, 1)
+        else:
+            d_main, d_T = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, 1), None
+        # decoder, outermost level first.  dU[i] = list of (dense gradient of level i's decoder input, owner) pairs
+        dU = [None] * nd
+        for i in range(nd):
+            U, cx, cst, x_out, recT = ups[i]
+            hin, win = U.h, U.w
+            gm = self._convT_bwd(self._up(i), U, d_main, hin, win, want_dbias=i == 0)
+            gT, shared = None, False
+            if recT is not None:
+                UT, shared, _ = recT
+                gT = self._convT_bwd(self._up(i, T=True), UT, d_T, hin, win, want_dbias=i == 0)
+            dU[i] = (gm, gT, shared)
+            if i == nd - 1:
+                break
+            # gradients w.r.t. the raw outputs of level i+1's transposed convs (the x-part of U / U_T)
+            nxt = ups[i + 1]
+            ctot = U.c
+
+            def raw_grad(xrec, g1, g2):
+                raw, mr, mode = xrec
+                g, sums = ops.act_norm_bwd_reduce_ex(raw.shape, dadd=g1, dadd2=g2, dadd_c0=0, dadd_ctot=ctot, raw=raw, mr=mr,
+                                                     norm_mode=mode, act=ACT_RELU)
+                return ops.norm_bwd_apply(g, raw, mr, mode, None, sums, raw.shape[1] * raw.shape[2], pad=1, fmt=FMT_F32)
+
+            x_next, recT_next = nxt[3], nxt[4]
+            if recT is not None and shared:        # first split level: one shared input, both decoders feed level i+1's main output
+                d_main, d_T = raw_grad(x_next, gm, gT), None
+            else:
+                d_main = raw_grad(x_next, gm, None)
+                d_T = raw_grad(recT_next[2], gT, None) if gT is not None else None
+        # encoder, innermost level first
+        dpad = None
+        for i in range(nd - 1, -1, -1):
+            op_in, raw, mr, mode = downs[i]
+            conv = getattr(self, "down%d" % i).conv
+            _, ho, wo, _ = raw.shape
+            gm, gT, shared = dU[i]
+            U, cx, cst = ups[i][0], ups[i][1], ups[i][2]
+            if i == nd - 1:      # consumed by up_{nd-1} only, through ReLU (x-part of U)
+                g, sums = ops.act_norm_bwd_reduce_ex(raw.shape, dadd=gm, dadd2=gT, dadd_c0=0, dadd_ctot=U.c, raw=raw, act=ACT_RELU)
+            elif i == 0:         # consumed by down1 only (the outermost Up ignores its skip)
+                g, sums = ops.act_norm_bwd_reduce_ex(raw.shape, dpad=dpad, pad=1, pad_mode=PAD_ZERO, raw=raw, act=ACT_LRELU)
+            else:                # LeakyReLU'd tensor feeds down_{i+1} and, through the decoder's ReLU, the skip slice of U_i
+                g, sums = ops.act_norm_bwd_reduce_ex(raw.shape, dpad=dpad, pad=1, pad_mode=PAD_ZERO, dadd=gm, dadd2=gT,
+                                                     dadd_c0=cx + cst, dadd_ctot=U.c, dadd_relu_mask=True, raw=raw, mr=mr,
+                                                     norm_mode=mode, act=ACT_LRELU)
+            d_op = ops.norm_bwd_apply(g, raw, mr, mode, None, sums, ho * wo, pad=0, fmt=FMT_F32)
+            ops.conv2d_wgrad(op_in, 0, d_op, 0, conv.k, 2, ho, wo, conv.weight.grad,
+                             conv.bias.grad if mode == NORM_NONE else None, impl=ops.IMPL_SIMT)
+            if i > 0:
+                dpad = ops.conv2d_dgrad_gather(d_op.data, conv.pack(2), 2, op_in.hp, op_in.wp)
+
+    # -- reference module API (networks.py:1538): returns the tanh output [n, 5, h, w]
+    def forward(self, x, verbose=False, style_code=None):
+        _require_cuda(x, "CustomUnetGenerator")
+        self.ensure_flat()
+        self.refresh_packs()
+        (fI, fT, _), _, _ = self.fwd([x.contiguous().float()], mask=None, save=False, want_normal=False, style_code=style_code)
+        return torch.cat([fI, fT], dim=1)
 
 
 # ----------------------------------------------------------------------------- discriminators
@@ -670,7 +940,13 @@ def define_G(input_nc, output_nc, ngf, netG, norm="batch", use_dropout=False, in
         if use_dropout or no_antialias or no_antialias_up:
             raise NotImplementedError("B200 path: dropout / no_antialias variants of the resnet generator are not built")
         net = ResnetGenerator(input_nc, output_nc, ngf, n_blocks=blocks[netG], opt=opt)
-    elif netG in ("unet_128", "unet_256", "unet256_custom", "stylegan2", "smallstylegan2"):
+    elif netG == "unet256_custom":
+        if norm != "instance":
+            raise NotImplementedError("B200 path: unet256_custom is built with norm='instance' (got %r)" % norm)
+        if use_dropout:
+            raise NotImplementedError("B200 path: dropout is not built")
+        net = CustomUnetGenerator(input_nc, output_nc, num_downs=8, ngf=ngf, num_layer_separate=num_layer_separate, opt=opt)
+    elif netG in ("unet_128", "unet_256", "stylegan2", "smallstylegan2"):
         raise NotImplementedError("Generator model name [%s] is on the roadmap of the B200 path but not built yet" % netG)
     else:
         raise NotImplementedError("Generator model name [%s] is not recognized" % netG)

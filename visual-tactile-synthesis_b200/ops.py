@@ -128,6 +128,54 @@ def act_norm_bwd_reduce(shape, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None, r
     return g, sums
 
 
+def norm_act_pad_into(op, c_off, raw, mr=None, norm_mode=NORM_NONE, act=ACT_NONE, pad=0, pad_mode=PAD_ZERO):
+    """Fill channels [c_off, c_off + c) of an existing haloed operand (decoder concat, slice by slice)."""
+    n, h, w, c = raw.shape
+    L.call("skit_norm_act_pad_ex", _p(raw), n, h, w, c, _p(mr), norm_mode, None, None, act, None, None,
+           op.ref(), c_off, pad, pad_mode, L.stream())
+
+
+def act_norm_bwd_reduce_ex(shape, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None, dadd2=None, dadd_c0=0, dadd_ctot=None,
+                           dadd_relu_mask=False, raw=None, mr=None, norm_mode=NORM_NONE, act=ACT_NONE):
+    """act_norm_bwd_reduce with sliced / doubled / ReLU-masked dense gradients -> (g, sums)."""
+    n, h, w, c = shape
+    dev = (dpad if dpad is not None else dadd).device
+    g = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
+    sums = None
+    if norm_mode != NORM_NONE:
+        sums = torch.zeros((n if norm_mode == NORM_INSTANCE else 1, c, 2), dtype=torch.float64, device=dev)
+    L.call("skit_act_norm_bwd_reduce_ex", _p(dpad), pad, pad_mode, _p(dadd), _p(dadd2), dadd_c0,
+           c if dadd_ctot is None else dadd_ctot, int(dadd_relu_mask), _p(raw), n, h, w, c, _p(mr), norm_mode,
+           None, None, act, _p(g), _p(sums), L.stream())
+    return g, sums
+
+
+def conv_transpose2d_fwd(x, wg, stride, pad, bias=None, stats_mode=NORM_NONE, out=None, out_c0=0):
+    """x: dense NHWC fp32; wg: mode-2 PackedWeights of the [ci][co][k][k] weight -> (y NHWC (or `out` slice), stats)."""
+    n, h, w, ci = x.shape
+    co, k = wg.rco, wg.k
+    ho, wo = (h - 1) * stride - 2 * pad + k, (w - 1) * stride - 2 * pad + k
+    y = out if out is not None else torch.empty((n, ho, wo, co), dtype=torch.float32, device=x.device)
+    stats = None
+    if stats_mode != NORM_NONE:
+        stats = torch.zeros((n if stats_mode == NORM_INSTANCE else 1, co, 2), dtype=torch.float64, device=x.device)
+    L.call("skit_conv_transpose2d_fwd", _p(x), n, h, w, ci, wg.ref(), stride, pad, ho, wo, _p(bias), _p(y), y.shape[3], out_c0,
+           _p(stats), stats_mode, L.stream())
+    return y, stats
+
+
+def dbias(dy_op, org, ho, wo, db):
+    L.call("skit_dbias", dy_op.ref(), org, ho, wo, _p(db), L.stream())
+
+
+def g_head_bwd_split(raw, mask, dI, dT, pad):
+    n, h, w, _ = raw.shape
+    opI = Operand(n, h, w, 3, pad, FMT_F32, raw.device)
+    opT = Operand(n, h, w, 2, pad, FMT_F32, raw.device)
+    L.call("skit_g_head_bwd_split", _p(raw), _p(mask), _p(dI), _p(dT), n, h, w, opI.ref(), opT.ref(), pad, L.stream())
+    return opI, opT
+
+
 def norm_bwd_apply(g, raw=None, mr=None, norm_mode=NORM_NONE, gamma=None, sums=None, count=0.0, dgamma=None, dbeta=None,
                    pad=0, fmt=FMT_F32):
     n, h, w, c = g.shape

@@ -34,6 +34,8 @@ def default_options(**kw):
         gan_mode="nonsaturating",
         lambda_G1_GAN=1.0, lambda_G1_L1=100.0, lambda_G1_lpips=0.0, lambda_G2_GAN=5.0, lambda_G2_L1=10.0,
         lambda_G2_lpips=0.0, use_vision_aided_loss=False,
+        num_layer_separate=4, use_style_code=False, style_code_mode="concat", style_code_mapping_mode="tile",
+        style_code_dim=512, num_layer_style_code=1,
         batch_size=1, batch_size_G2=64, add_fake_T_sample_size=32, scale_nz=0.25, T_resolution_multiplier=1,
         lr=1e-3, lr_G2=5e-4, beta1=0.0, beta2=0.99, lr_policy="linear", n_epochs=5, n_epochs_decay=400, epoch_count=1,
         run_full_res_D2=False,  # the reference's visualisation-only netD2(full image) pass (:1495); off on the hot path
@@ -69,7 +71,8 @@ class SinSKITGModel:
         g_in = opt.input_nc + (8 if opt.use_positional_encoding else 0)
         gpu = [dev_index]
         self.netG = networks.define_G(g_in, opt.output_nc, opt.ngf, opt.netG, opt.normG, not opt.no_dropout, opt.init_type,
-                                      opt.init_gain, opt.no_antialias, opt.no_antialias_up, gpu, opt)
+                                      opt.init_gain, opt.no_antialias, opt.no_antialias_up, gpu, opt,
+                                      num_layer_separate=getattr(opt, "num_layer_separate", 4))
         self.netG.flatten_parameters()
         if self.isTrain:
             self.netD = networks.define_D(opt.input_nc + 3, opt.ndf, opt.netD, opt.n_layers_D, opt.normD, opt.init_type,
@@ -210,7 +213,8 @@ class SinSKITGModel:
         save = self.isTrain if save is None else save
         srcs = [self.real_S] + ([self.S_pe] if self.S_pe is not None else [])
         (self.fake_I, self.fake_T, self.fake_N), self._g_ctx, _ = self.netG.fwd(
-            srcs, mask=self.M if opt.use_bg_mask else None, scale_nz=opt.scale_nz, save=save)
+            srcs, mask=self.M if opt.use_bg_mask else None, scale_nz=opt.scale_nz, save=save,
+            style_code=self.style_code if getattr(opt, "use_style_code", False) else None)
         if hasattr(self, "real_I"):
             if opt.use_diffaug:
                 if not staged:
