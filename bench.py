@@ -250,6 +250,16 @@ def run_b200(a):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "CPU oracle train step at %dx%d (NT=%d NF=%d), %.2f s/step, scaled by (%d/%d)^2" % (s, s, nt, nf, t, s, a.size)}
         print(json.dumps(line), flush=True)
+    if ctx.world_size > 1:
+        # Tearing NCCL down while a captured CUDA graph still holds its collectives can block forever in
+        # destroy_process_group: drop the graph, drain the device, meet at a barrier, then leave without the
+        # communicator teardown (the process is exiting anyway).
+        model._graph = None
+        torch.cuda.synchronize()
+        ctx.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     ctx.shutdown()
 
 
