@@ -81,6 +81,10 @@ int skit_built_arch(void);
  * f32 / hi / lo may each be NULL to skip that product.  hi/lo are [tap][N][K] K-major bf16.  */
 int skit_pack_conv_weights(const float* w, int co, int ci, int k, int mode,
                            float* f32, void* hi, void* lo, void* stream);
+/* bf16 hi/lo pack with the reduction axis zero-padded to kpad channels (a multiple of 8 >= the real count): lets layers
+ * with thin inputs (the 9-channel generator stem, the 5-channel head's input gradient) run on the tcgen05 path, whose
+ * TMA rows must be 16-byte multiples.  The matching operand carries the same number of (zero) padding channels. */
+int skit_pack_conv_weights_padded(const float* w, int co, int ci, int k, int mode, int kpad, void* hi, void* lo, void* stream);
 /* Inverse of the forward pack for gradients: dWf [(tap*ci+c)][o] fp32 -> dw[o][c][ky][kx] (+= if accumulate). */
 int skit_unpack_conv_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, void* stream);
 
@@ -132,6 +136,12 @@ int skit_dbias(const skit_operand* dy, int dy_org, int ho, int wo, float* dbias,
  * counts are multiples of 64 and one of them of 128 (both GEMM operands MN-major straight from NHWC). */
 int skit_conv2d_wgrad(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
                       int k, int stride, int ho, int wo, float* scratch, float* dw, float* dbias, int impl, void* stream);
+
+/* Same, for channel-padded operands: x->c >= ci_real and dy->c >= co_real (padding channels are zero); scratch is
+ * k*k*x->c*dy->c floats; dw has the real shape [co_real][ci_real][k][k]; dbias (may be NULL): [co_real]. */
+int skit_conv2d_wgrad_ex(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
+                         int k, int stride, int ho, int wo, float* scratch, float* dw, float* dbias, int impl,
+                         int co_real, int ci_real, void* stream);
 
 /* ---------------------------------------------------------------- normalisation + activation + halo
  * Turn double (sum, sumsq) into float (mean, rstd), eps 1e-5, biased variance
@@ -194,7 +204,8 @@ int skit_blur_up_bwd(const float* dy, int n, int h, int w, int c, float* dx, voi
 
 /* ---------------------------------------------------------------- image-level ops (NCHW fp32 planar)
  * Concatenate up to 4 NCHW sources along channels into a haloed NHWC fp32 operand
- * (torch.cat + ReflectionPad2d(3) at networks.py:1077 / zero padding 2 of the PatchGAN convs :1703). */
+ * (torch.cat + ReflectionPad2d(3) at networks.py:1077 / zero padding 2 of the PatchGAN convs :1703).
+ * The operand may be fp32 or bf16x2 and may have MORE channels than the sources provide (zero channel padding). */
 int skit_nchw_cat_to_operand(const float* const* srcs, const int* chans, int nsrc,
                              int n, int h, int w, const skit_operand* op, int pad, int pad_mode, void* stream);
 /* Adjoint for one channel slice: dst[n][cs][h][w] (+)= fold(dpad)[.., c0:c0+cs]. */
@@ -205,7 +216,8 @@ int skit_operand_grad_to_nchw(const float* dpad, int n, int h, int w, int c, int
  * fake_N = normalize([gx, gy, scale_nz]) (networks.py:1127; sinskitG_model.py:1309-1319; model_utils.py:418-425). */
 int skit_g_head_fwd(const float* raw, const float* mask, int n, int h, int w, float scale_nz,
                     float* fake_I, float* fake_T, float* fake_N, void* stream);
-/* d_raw[n][h][w][5] = [dI, dT] * M * (1 - tanh(raw)^2), written as a zero-haloed fp32 operand (pad q). */
+/* d_raw[n][h][w][5] = [dI, dT] * M * (1 - tanh(raw)^2), written as a zero-haloed operand (pad q), fp32 or bf16x2,
+ * with op->c >= 5 channels (zero channel padding for the tensor-core input-gradient / weight-gradient kernels). */
 int skit_g_head_bwd(const float* raw, const float* mask, const float* dI, const float* dT,
                     int n, int h, int w, const skit_operand* op, int pad, void* stream);
 
@@ -265,6 +277,12 @@ int skit_patch_sample_l2norm_bwd(const float* dout, const float* pre, int b, int
  * sum_i loss[i]*gscale w.r.t. q; k is detached in the reference). */
 int skit_patchnce(const float* q, const float* k, int b, int np, int dim, float inv_T,
                   float* loss, float* dq, float gscale, void* stream);
+
+/* ---------------------------------------------------------------- profiling aid
+ * When buf != NULL the halo-tile conv kernel stores clock64() stamps per CTA into buf[cta][8]
+ * (start, setup done, first activation tile landed, last MMA issued, accumulator ready, stores done, end).
+ * Pass NULL to switch it off (the default).  Never enabled on the product path. */
+int skit_debug_set_buffer(long long* buf);
 
 #ifdef __cplusplus
 }

@@ -11,13 +11,20 @@ from vts_b200 import ops  # noqa: E402
 
 
 def timeit(fn, iters=20, warm=3):
+    """Device time per call: the calls are captured into one CUDA graph so that host-side launch cost
+    (ctypes, tensor-map encoding) does not bound the measurement of short kernels."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
     b.record()
     torch.cuda.synchronize()
     return a.elapsed_time(b) / iters

@@ -34,6 +34,8 @@ _OP, _WT = C.POINTER(SkitOperand), C.POINTER(SkitWeights)
 # name -> argtypes; must list every symbol include/skit_b200.h declares (tests/test_abi.py checks).
 SIGNATURES = {
     "skit_pack_conv_weights": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "skit_pack_conv_weights_padded": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "skit_conv2d_wgrad_ex": [_OP, _I, _OP, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P],
     "skit_unpack_conv_wgrad": [_P, _I, _I, _I, _P, _I, _P],
     "skit_conv2d_fwd": [_OP, _WT, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "skit_conv2d_dgrad_gather": [_P, _I, _I, _I, _I, _WT, _I, _I, _I, _P, _P],
@@ -65,6 +67,7 @@ SIGNATURES = {
     "skit_l1_loss": [_P, _P, _LL, _F, _P, _P, _F, _I, _P],
     "skit_adam_step": [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _P],
     "skit_adam_step_dev": [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _P],
+    "skit_debug_set_buffer": [_P],
     "skit_patch_sample_l2norm": [_P, _I, _I, _I, _P, _I, _P, _P, _P],
     "skit_patch_sample_l2norm_bwd": [_P, _P, _I, _I, _I, _P, _I, _P, _P],
     "skit_patchnce": [_P, _P, _I, _I, _I, _F, _P, _P, _F, _P],

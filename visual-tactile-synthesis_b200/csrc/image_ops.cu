@@ -39,7 +39,10 @@ struct Srcs4 {
 };
 
 // ------------------------------------------------------------------------------ layout staging
-__global__ void __launch_bounds__(256) nchw_cat_to_operand_kernel(Srcs4 s, int n, int h, int w, int ctot, float* dst, int pad, int pad_mode) {
+// cop >= ctot: channels beyond the sources are zero (channel padding for the tensor-core path, whose TMA rows must be
+// 16-byte multiples).  fmt selects fp32 or bf16 hi/lo planes.
+__global__ void __launch_bounds__(256) nchw_cat_to_operand_kernel(Srcs4 s, int n, int h, int w, int ctot, int cop, int fmt,
+                                                                  float* dst, __nv_bfloat16* dh, __nv_bfloat16* dl, int pad, int pad_mode) {
     const int hp = h + 2 * pad, wp = w + 2 * pad;
     const long long total = (long long)n * hp * wp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -48,11 +51,17 @@ __global__ void __launch_bounds__(256) nchw_cat_to_operand_kernel(Srcs4 s, int n
         const int py = (int)(t % hp);
         const int b = (int)(t / hp);
         const int sy = pad_src(py, pad, h, pad_mode), sx = pad_src(px, pad, w, pad_mode);
-        float* o = dst + i * ctot;
         int c = 0;
         for (int k = 0; k < s.n; k++)
-            for (int j = 0; j < s.ch[k]; j++, c++)
-                o[c] = (sy < 0 || sx < 0) ? 0.f : __ldg(s.p[k] + (((long long)b * s.ch[k] + j) * h + sy) * w + sx);
+            for (int j = 0; j < s.ch[k]; j++, c++) {
+                const float v = (sy < 0 || sx < 0) ? 0.f : __ldg(s.p[k] + (((long long)b * s.ch[k] + j) * h + sy) * w + sx);
+                if (fmt == SKIT_FMT_F32) dst[i * cop + c] = v;
+                else { __nv_bfloat16 hi, lo; split_bf16(v, hi, lo); dh[i * cop + c] = hi; dl[i * cop + c] = lo; }
+            }
+        for (; c < cop; c++) {
+            if (fmt == SKIT_FMT_F32) dst[i * cop + c] = 0.f;
+            else { dh[i * cop + c] = __float2bfloat16_rn(0.f); dl[i * cop + c] = __float2bfloat16_rn(0.f); }
+        }
     }
 }
 
@@ -107,7 +116,8 @@ __global__ void __launch_bounds__(256) g_head_fwd_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) g_head_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ mask,
                                                          const float* __restrict__ dI, const float* __restrict__ dT,
-                                                         int n, int h, int w, float* dst, int pad) {
+                                                         int n, int h, int w, float* dst, __nv_bfloat16* dh, __nv_bfloat16* dl,
+                                                         int cop, int fmt, int pad) {
     const int hp = h + 2 * pad, wp = w + 2 * pad;
     const long long hw = (long long)h * w, total = (long long)n * hp * wp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -127,8 +137,11 @@ __global__ void __launch_bounds__(256) g_head_bwd_kernel(const float* __restrict
                 v[j] = d * m * (1.f - th * th);
             }
         }
-#pragma unroll
-        for (int j = 0; j < 5; j++) dst[i * 5 + j] = v[j];
+        for (int j = 0; j < cop; j++) {   // cop >= 5: zero channel padding for the tensor-core path
+            const float x = j < 5 ? v[j] : 0.f;
+            if (fmt == SKIT_FMT_F32) dst[i * cop + j] = x;
+            else { __nv_bfloat16 hi, lo; split_bf16(x, hi, lo); dh[i * cop + j] = hi; dl[i * cop + j] = lo; }
+        }
     }
 }
 
@@ -450,12 +463,13 @@ extern "C" int skit_nchw_cat_to_operand(const float* const* srcs, const int* cha
                                         int n, int h, int w, const skit_operand* op, int pad, int pad_mode, void* stream) {
     Srcs4 s{};
     int ctot = fill_srcs(s, srcs, chans, nullptr, nsrc);
-    SKIT_REQUIRE(ctot > 0 && op && op->p0 && op->fmt == SKIT_FMT_F32, "nchw_cat_to_operand: bad sources or operand (fp32 operand required)");
-    SKIT_REQUIRE(op->n == n && op->hp == h + 2 * pad && op->wp == w + 2 * pad && op->c == ctot,
+    SKIT_REQUIRE(ctot > 0 && op && op->p0 && (op->fmt == SKIT_FMT_F32 || (op->fmt == SKIT_FMT_BF16X2 && op->p1)), "nchw_cat_to_operand: bad sources or operand");
+    SKIT_REQUIRE(op->n == n && op->hp == h + 2 * pad && op->wp == w + 2 * pad && op->c >= ctot,
                  "nchw_cat_to_operand: operand dims [%d,%d,%d,%d] != [%d,%d,%d,%d]", op->n, op->hp, op->wp, op->c, n, h + 2 * pad, w + 2 * pad, ctot);
     SKIT_REQUIRE(pad_mode != SKIT_PAD_REFLECT || (pad < h && pad < w), "nchw_cat_to_operand: reflect pad too large");
     const long long total = (long long)n * (h + 2 * pad) * (w + 2 * pad);
-    nchw_cat_to_operand_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(s, n, h, w, ctot, (float*)op->p0, pad, pad_mode);
+    nchw_cat_to_operand_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(s, n, h, w, ctot, op->c, op->fmt, (float*)op->p0,
+                                                                                    (__nv_bfloat16*)op->p0, (__nv_bfloat16*)op->p1, pad, pad_mode);
     return check_launch("nchw_cat_to_operand_kernel");
 }
 
@@ -477,9 +491,10 @@ extern "C" int skit_g_head_fwd(const float* raw, const float* mask, int n, int h
 
 extern "C" int skit_g_head_bwd(const float* raw, const float* mask, const float* dI, const float* dT,
                                int n, int h, int w, const skit_operand* op, int pad, void* stream) {
-    SKIT_REQUIRE(raw && (dI || dT) && op && op->p0 && op->fmt == SKIT_FMT_F32, "g_head_bwd: bad arguments (fp32 operand required)");
-    SKIT_REQUIRE(op->n == n && op->hp == h + 2 * pad && op->wp == w + 2 * pad && op->c == 5, "g_head_bwd: operand dims mismatch");
-    g_head_bwd_kernel<<<grid_for((long long)n * op->hp * op->wp, 256), 256, 0, as_stream(stream)>>>(raw, mask, dI, dT, n, h, w, (float*)op->p0, pad);
+    SKIT_REQUIRE(raw && (dI || dT) && op && op->p0 && (op->fmt == SKIT_FMT_F32 || (op->fmt == SKIT_FMT_BF16X2 && op->p1)), "g_head_bwd: bad arguments");
+    SKIT_REQUIRE(op->n == n && op->hp == h + 2 * pad && op->wp == w + 2 * pad && op->c >= 5, "g_head_bwd: operand dims mismatch");
+    g_head_bwd_kernel<<<grid_for((long long)n * op->hp * op->wp, 256), 256, 0, as_stream(stream)>>>(
+        raw, mask, dI, dT, n, h, w, (float*)op->p0, (__nv_bfloat16*)op->p0, (__nv_bfloat16*)op->p1, op->c, op->fmt, pad);
     return check_launch("g_head_bwd_kernel");
 }
 

@@ -103,6 +103,77 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(PrepP p) {
     }
 }
 
+
+// Row-tiled variant for channel counts whose float4 lanes divide the 256-thread block (c = 4..1024, power-of-two lanes):
+// a block owns whole padded rows of one image, a thread owns 4 fixed channels (its normalisation constants live in
+// registers) and walks the row in steps of the block's pixel lanes — no integer divisions, no fp64, 4 independent
+// 16-byte loads in flight per thread.
+template <int FMT>
+__global__ void __launch_bounds__(256) norm_act_pad_rows_kernel(PrepP p, int cv, int rows_per_block) {
+    const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
+    const int n = blockIdx.y;
+    const int cl = threadIdx.x % cv, pl = threadIdx.x / cv, PL = 256 / cv;
+    const int ch = cl * 4;
+    float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1}, gam[4] = {1, 1, 1, 1}, bet[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (p.mr) {
+            const float* mr = p.mr + ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
+            mean[j] = mr[0]; rstd[j] = mr[1];
+        }
+        if (p.gamma) { gam[j] = p.gamma[ch + j]; bet[j] = p.beta[ch + j]; }
+    }
+    const int py_end = min(hp, (int)(blockIdx.x + 1) * rows_per_block);
+    for (int py = blockIdx.x * rows_per_block; py < py_end; py++) {
+        const int sy = pad_src(py, p.pad, p.h, p.pad_mode);
+        const long long srow = ((long long)n * p.h + (sy < 0 ? 0 : sy)) * p.w;
+        const long long drow = ((long long)n * hp + py) * wp;
+        for (int px0 = pl; px0 < wp; px0 += 4 * PL) {
+            float4 r[4], res[4];
+            int sx[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int px = px0 + u * PL;
+                sx[u] = px < wp ? pad_src(px, p.pad, p.w, p.pad_mode) : -1;
+                const bool ok = sy >= 0 && sx[u] >= 0;
+                r[u] = ok ? *reinterpret_cast<const float4*>(p.raw + (srow + sx[u]) * p.c + ch) : make_float4(0, 0, 0, 0);
+                if (p.residual) res[u] = ok ? *reinterpret_cast<const float4*>(p.residual + (srow + sx[u]) * p.c + ch) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int px = px0 + u * PL;
+                if (px >= wp) continue;
+                const bool ok = sy >= 0 && sx[u] >= 0;
+                float v[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+                if (ok) {
+                    const float rs[4] = {res[u].x, res[u].y, res[u].z, res[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float x = v[j];
+                        if (p.mr) x = (x - mean[j]) * rstd[j];
+                        if (p.gamma) x = x * gam[j] + bet[j];
+                        x = act_fwd(x, p.act);
+                        if (p.residual) x += rs[j];
+                        v[j] = x;
+                    }
+                    if (p.out && py - p.pad == sy && px - p.pad == sx[u])
+                        *reinterpret_cast<float4*>(p.out + (srow + sx[u]) * p.c + ch) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                const long long dst = (drow + px) * p.oc + p.ooff + ch;
+                if (FMT == SKIT_FMT_F32) {
+                    if (p.o0) *reinterpret_cast<float4*>(p.o0 + dst) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+                    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) split_bf16(v[j], hi[j], lo[j]);
+                    *reinterpret_cast<uint2*>(p.oh + dst) = *reinterpret_cast<uint2*>(hi);
+                    *reinterpret_cast<uint2*>(p.ol + dst) = *reinterpret_cast<uint2*>(lo);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ backward phase A
 struct BwdAP {
     const float* dpad; int pad, pad_mode;
@@ -216,6 +287,90 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_kernel(BwdAP p) {
     }
 }
 
+
+// Row-tiled variant of phase A (see norm_act_pad_rows_kernel): float4 loads of every stream, the halo fold without
+// per-pixel divisions, per-thread register sums reduced across the block's pixel lanes, one fp64 atomic per channel per CTA.
+__global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, int cv, int rows_per_block) {
+    __shared__ float red[256 * 8];
+    const int n = blockIdx.y;
+    const int cl = threadIdx.x % cv, pl = threadIdx.x / cv, PL = 256 / cv;
+    const int ch = cl * 4;
+    const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
+    float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1}, gam[4] = {1, 1, 1, 1}, bet[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (p.mr) {
+            const float* mr = p.mr + ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
+            mean[j] = mr[0]; rstd[j] = mr[1];
+        }
+        if (p.gamma) { gam[j] = p.gamma[ch + j]; bet[j] = p.beta[ch + j]; }
+    }
+    float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+    const int y_end = min(p.h, (int)(blockIdx.x + 1) * rows_per_block);
+    for (int y = blockIdx.x * rows_per_block; y < y_end; y++) {
+        int ys[3];
+        const int ny = p.dpad ? fold_coords(y, p.pad, p.h, p.pad_mode, ys) : 0;
+        const long long srow = ((long long)n * p.h + y) * p.w;
+        for (int x = pl; x < p.w; x += PL) {
+            const long long src = (srow + x) * p.c + ch;
+            float4 d = make_float4(0, 0, 0, 0);
+            if (p.dadd) {
+                const long long dsrc = (srow + x) * p.dctot + p.dc0 + ch;
+                d = *reinterpret_cast<const float4*>(p.dadd + dsrc);
+                if (p.dadd2) {
+                    const float4 e = *reinterpret_cast<const float4*>(p.dadd2 + dsrc);
+                    d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
+                }
+            }
+            float4 rw = make_float4(0, 0, 0, 0);
+            if (p.raw) rw = *reinterpret_cast<const float4*>(p.raw + src);
+            const float r4[4] = {rw.x, rw.y, rw.z, rw.w};
+            float xhat[4], pre[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { xhat[j] = (r4[j] - mean[j]) * rstd[j]; pre[j] = xhat[j] * gam[j] + bet[j]; }
+            float dv[4] = {d.x, d.y, d.z, d.w};
+            if (p.dmask) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (!(pre[j] > 0.f)) dv[j] = 0.f;
+            }
+            if (p.dpad) {
+                int xs[3];
+                const int nx = fold_coords(x, p.pad, p.w, p.pad_mode, xs);
+                for (int a = 0; a < ny; a++)
+                    for (int b = 0; b < nx; b++) {
+                        const float4 q = *reinterpret_cast<const float4*>(p.dpad + (((long long)n * hp + ys[a]) * wp + xs[b]) * p.c + ch);
+                        dv[0] += q.x; dv[1] += q.y; dv[2] += q.z; dv[3] += q.w;
+                    }
+            }
+            float go[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                go[j] = act_grad(pre[j], p.act) * dv[j];
+                s0[j] += go[j]; s1[j] = fmaf(go[j], xhat[j], s1[j]);
+            }
+            *reinterpret_cast<float4*>(p.g + src) = make_float4(go[0], go[1], go[2], go[3]);
+        }
+    }
+    if (p.sums) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { red[threadIdx.x * 8 + j] = s0[j]; red[threadIdx.x * 8 + 4 + j] = s1[j]; }
+        __syncthreads();
+        if (pl == 0) {
+            float t0[4] = {0, 0, 0, 0}, t1[4] = {0, 0, 0, 0};
+            for (int q = 0; q < PL; q++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) { t0[j] += red[(q * cv + cl) * 8 + j]; t1[j] += red[(q * cv + cl) * 8 + 4 + j]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double* dst = p.sums + ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
+                atomicAdd(dst, (double)t0[j]);
+                atomicAdd(dst + 1, (double)t1[j]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ backward phase B
 struct BwdBP {
     const float* g; const float* raw; int n, h, w, c;
@@ -270,6 +425,70 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(BwdBP p) {
                 *reinterpret_cast<uint2*>(p.ol + dst) = *reinterpret_cast<uint2*>(lo);
             } else {
                 p.oh[dst] = hi[0]; p.ol[dst] = lo[0];
+            }
+        }
+    }
+}
+
+
+// Row-tiled variant (see norm_act_pad_rows_kernel): the per-channel terms of the norm backward (mean, rstd, gamma and
+// the two reduced sums, converted from double ONCE per thread) stay in registers.
+template <int FMT>
+__global__ void __launch_bounds__(256) norm_bwd_apply_rows_kernel(BwdBP p, int cv, int rows_per_block) {
+    const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
+    const int n = blockIdx.y;
+    const int cl = threadIdx.x % cv, pl = threadIdx.x / cv, PL = 256 / cv;
+    const int ch = cl * 4;
+    float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1}, gam[4] = {1, 1, 1, 1}, m0[4] = {0, 0, 0, 0}, m1[4] = {0, 0, 0, 0};
+    if (p.mr) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long gi = ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
+            mean[j] = p.mr[gi]; rstd[j] = p.mr[gi + 1];
+            m0[j] = (float)(p.sums[gi] * p.inv_count); m1[j] = (float)(p.sums[gi + 1] * p.inv_count);
+            if (p.gamma) gam[j] = p.gamma[ch + j];
+        }
+    }
+    const int py_end = min(hp, (int)(blockIdx.x + 1) * rows_per_block);
+    for (int py = blockIdx.x * rows_per_block; py < py_end; py++) {
+        const int y = py - p.pad;
+        const bool yin = y >= 0 && y < p.h;
+        const long long srow = ((long long)n * p.h + (yin ? y : 0)) * p.w;
+        const long long drow = ((long long)n * hp + py) * wp;
+        for (int px0 = pl; px0 < wp; px0 += 4 * PL) {
+            float4 gg[4], rw[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int x = px0 + u * PL - p.pad;
+                const bool ok = yin && x >= 0 && x < p.w && px0 + u * PL < wp;
+                gg[u] = ok ? *reinterpret_cast<const float4*>(p.g + (srow + x) * p.c + ch) : make_float4(0, 0, 0, 0);
+                if (p.mr) rw[u] = ok ? *reinterpret_cast<const float4*>(p.raw + (srow + x) * p.c + ch) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int px = px0 + u * PL;
+                if (px >= wp) continue;
+                const int x = px - p.pad;
+                const bool ok = yin && x >= 0 && x < p.w;
+                float v[4] = {gg[u].x, gg[u].y, gg[u].z, gg[u].w};
+                if (ok && p.mr) {
+                    const float r4[4] = {rw[u].x, rw[u].y, rw[u].z, rw[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const float xhat = (r4[j] - mean[j]) * rstd[j];
+                        v[j] = gam[j] * rstd[j] * (v[j] - m0[j] - xhat * m1[j]);
+                    }
+                }
+                const long long dst = (drow + px) * p.c + ch;
+                if (FMT == SKIT_FMT_F32) {
+                    *reinterpret_cast<float4*>(p.o0 + dst) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+                    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) split_bf16(v[j], hi[j], lo[j]);
+                    *reinterpret_cast<uint2*>(p.oh + dst) = *reinterpret_cast<uint2*>(hi);
+                    *reinterpret_cast<uint2*>(p.ol + dst) = *reinterpret_cast<uint2*>(lo);
+                }
             }
         }
     }
@@ -415,6 +634,14 @@ __global__ void __launch_bounds__(256) blur_up_bwd_kernel(const float* __restric
     }
 }
 
+// channel counts the row-tiled kernels take: float4 lanes c/4 must divide the 256-thread block
+static inline bool rows_layout_ok(int c) { return c % 4 == 0 && c / 4 <= 256 && 256 % (c / 4) == 0; }
+// rows per block so that the grid has a few CTAs per SM
+static inline int rows_per_block_for(int rows, int n) {
+    const int want_blocks = max(1, (kSMs * 6) / max(1, n));
+    return max(1, cdiv(rows, want_blocks));
+}
+
 static int check_operand(const skit_operand* op, int n, int h, int w, int c, int pad, const char* who) {
     if (!op) return SKIT_OK;
     if (!op->p0 || (op->fmt == SKIT_FMT_BF16X2 && !op->p1) || (op->fmt != SKIT_FMT_F32 && op->fmt != SKIT_FMT_BF16X2)) {
@@ -466,6 +693,14 @@ extern "C" int skit_norm_act_pad_ex(const float* raw, int n, int h, int w, int c
     }
     p.pad = pad; p.pad_mode = pad_mode; p.oc = oc; p.ooff = c_off;
     const long long pix = (long long)n * (h + 2 * pad) * (w + 2 * pad);
+    if (rows_layout_ok(c) && (!op || (oc % 4 == 0 && c_off % 4 == 0))) {
+        const int hp = h + 2 * pad;
+        const int rpb = rows_per_block_for(hp, n);
+        dim3 grid(cdiv(hp, rpb), n);
+        if (!op || op->fmt == SKIT_FMT_F32) norm_act_pad_rows_kernel<SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb);
+        else norm_act_pad_rows_kernel<SKIT_FMT_BF16X2><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb);
+        return check_launch("norm_act_pad_rows_kernel");
+    }
     if (c % 4 == 0 && oc % 4 == 0 && c_off % 4 == 0) norm_act_pad_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
     else norm_act_pad_kernel<1><<<grid_for(pix * c, 256), 256, 0, as_stream(stream)>>>(p);
     return check_launch("norm_act_pad_kernel");
@@ -501,6 +736,12 @@ extern "C" int skit_act_norm_bwd_reduce_ex(const float* dpad, int pad, int pad_m
     p.mr = mean_rstd; p.per_n = norm_mode == SKIT_NORM_INSTANCE; p.gamma = gamma; p.beta = beta;
     p.act = act; p.g = g; p.sums = sums;
     const int P = h * w;
+    if (rows_layout_ok(c) && dadd_c0 % 4 == 0 && dadd_ctot % 4 == 0) {
+        const int rpb = rows_per_block_for(h, n);
+        dim3 grid(cdiv(h, rpb), n);
+        act_norm_bwd_reduce_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb);
+        return check_launch("act_norm_bwd_reduce_rows_kernel");
+    }
     const int lanes_c = min(c / vec, 256), PL = 256 / lanes_c;
     int blocks_per_n = max(1, min(cdiv(P, PL * 4), cdiv(kSMs * 8, n)));
     p.chunk = cdiv(P, blocks_per_n);
@@ -536,7 +777,13 @@ extern "C" int skit_norm_bwd_apply(const float* g, const float* raw, int n, int 
     else { p.oh = (__nv_bfloat16*)op->p0; p.ol = (__nv_bfloat16*)op->p1; }
     p.pad = pad;
     const long long pix = (long long)n * (h + 2 * pad) * (w + 2 * pad);
-    if (c % 4 == 0) norm_bwd_apply_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
+    if (rows_layout_ok(c)) {
+        const int hp = h + 2 * pad;
+        const int rpb = rows_per_block_for(hp, n);
+        dim3 grid(cdiv(hp, rpb), n);
+        if (op->fmt == SKIT_FMT_F32) norm_bwd_apply_rows_kernel<SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb);
+        else norm_bwd_apply_rows_kernel<SKIT_FMT_BF16X2><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb);
+    } else if (c % 4 == 0) norm_bwd_apply_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
     else norm_bwd_apply_kernel<1><<<grid_for(pix * c, 256), 256, 0, as_stream(stream)>>>(p);
     rc = check_launch("norm_bwd_apply_kernel");
     if (rc) return rc;

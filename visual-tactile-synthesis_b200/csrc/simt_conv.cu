@@ -350,8 +350,8 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
 // lanes are combined through shared memory before one atomic per channel per CTA.
 template <int DFMT>
 __global__ void __launch_bounds__(256) dbias_kernel(const float* d0, const __nv_bfloat16* dh, const __nv_bfloat16* dl,
-                                                    int dhp, int dwp, int co, int dorg, int ho, int wo,
-                                                    int chunk, float* dbias) {
+                                                    int dhp, int dwp, int co, int cs, int dorg, int ho, int wo,
+                                                    int chunk, float* dbias) {   // co channels summed, cs = channel stride
     __shared__ float red[8][33];
     const int n = blockIdx.y;
     const int P = ho * wo;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) dbias_kernel(const float* d0, const __nv_
         if (o < co) {
             for (int pix = pbeg + pl; pix < pend; pix += 8) {
                 int oy = pix / wo, ox = pix - oy * wo;
-                long long a = (((long long)n * dhp + dorg + oy) * dwp + dorg + ox) * co + o;
+                long long a = (((long long)n * dhp + dorg + oy) * dwp + dorg + ox) * cs + o;
                 s += (DFMT == SKIT_FMT_F32) ? d0[a] : (__bfloat162float(dh[a]) + __bfloat162float(dl[a]));
             }
         }
@@ -396,20 +396,21 @@ __device__ __forceinline__ long long pack_src_index(int mode, int k, int co, int
 }
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci, int k, int mode,
-                                    float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    const long long total = (long long)co * ci * k * k;
+                                    float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo, int kpad) {
     const int Kd = mode == 0 ? ci : co, Nd = mode == 0 ? co : ci;
+    const int Kp = kpad > Kd ? kpad : Kd;     // bf16 packs may pad the reduction axis with zeros (TMA row alignment)
+    const long long total = (long long)k * k * Nd * Kp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        if (hi) {   // [tap][N][K]
-            const int kk = (int)(i % Kd); long long t = i / Kd;
+        if (hi) {   // [tap][N][Kp]
+            const int kk = (int)(i % Kp); long long t = i / Kp;
             const int nn = (int)(t % Nd); const int tap = (int)(t / Nd);
             const int o = mode == 0 ? nn : kk, c = mode == 0 ? kk : nn;
-            const float v = __ldg(w + pack_src_index(mode, k, co, ci, tap, o, c));
+            const float v = kk < Kd ? __ldg(w + pack_src_index(mode, k, co, ci, tap, o, c)) : 0.f;
             __nv_bfloat16 h, l;
             split_bf16(v, h, l);
             hi[i] = h; lo[i] = l;
         }
-        if (f32) {  // [tap][K][N]
+        if (f32 && i < (long long)k * k * Nd * Kd) {  // [tap][K][N]
             const int nn = (int)(i % Nd); long long t = i / Nd;
             const int kk = (int)(t % Kd); const int tap = (int)(t / Kd);
             const int o = mode == 0 ? nn : kk, c = mode == 0 ? kk : nn;
@@ -418,15 +419,17 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci,
     }
 }
 
-// layout 0: dwf[(tap*ci + c)*co + o]   layout 1: dwf[(tap*co + o)*ci + c]
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int co, int ci, int k, float* dw, int accumulate, int layout) {
+// layout 0: dwf[(tap*cip + c)*cop + o]   layout 1: dwf[(tap*cop + o)*cip + c]   (cop/cip: channel counts of the
+// operands the partial sums were computed on, >= the real co/ci when those were zero-padded)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int co, int ci, int k, float* dw, int accumulate, int layout,
+                                    int cop, int cip) {
     const long long total = (long long)co * ci * k * k;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int kx = i % k; long long t = i / k;
         int ky = t % k; t /= k;
         int c = t % ci; int o = t / ci;
         const long long tap = ky * k + kx;
-        float v = layout == 0 ? dwf[(tap * ci + c) * co + o] : dwf[(tap * co + o) * ci + c];
+        float v = layout == 0 ? dwf[(tap * cip + c) * cop + o] : dwf[(tap * cop + o) * cip + c];
         dw[i] = accumulate ? dw[i] + v : v;
     }
 }
@@ -461,14 +464,25 @@ extern "C" int skit_pack_conv_weights(const float* w, int co, int ci, int k, int
     SKIT_REQUIRE((hi == nullptr) == (lo == nullptr), "pack_conv_weights: hi and lo must be given together");
     long long total = (long long)co * ci * k * k;
     int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
-    pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, co, ci, k, mode, f32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, co, ci, k, mode, f32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, 0);
     return check_launch("pack_weights_kernel");
 }
 
-static int unpack_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, int layout, cudaStream_t st) {
+extern "C" int skit_pack_conv_weights_padded(const float* w, int co, int ci, int k, int mode, int kpad, void* hi, void* lo, void* stream) {
+    SKIT_REQUIRE(w && hi && lo && co > 0 && ci > 0 && k > 0 && mode >= 0 && mode <= 3 && (mode != 3 || k % 2 == 0), "pack_conv_weights_padded: bad arguments");
+    const int Kd = mode == 0 ? ci : co, Nd = mode == 0 ? co : ci;
+    SKIT_REQUIRE(kpad >= Kd && kpad % 8 == 0, "pack_conv_weights_padded: kpad %d must be a multiple of 8 and >= %d", kpad, Kd);
+    long long total = (long long)k * k * Nd * kpad;
+    int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
+    pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, co, ci, k, mode, nullptr, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, kpad);
+    return check_launch("pack_weights_kernel");
+}
+
+static int unpack_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, int layout, cudaStream_t st,
+                        int cop = 0, int cip = 0) {
     long long total = (long long)co * ci * k * k;
     int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
-    unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(dwf, co, ci, k, dw, accumulate, layout);
+    unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(dwf, co, ci, k, dw, accumulate, layout, cop ? cop : co, cip ? cip : ci);
     return check_launch("unpack_wgrad_kernel");
 }
 
@@ -527,9 +541,9 @@ extern "C" int skit_dbias(const skit_operand* dy, int dy_org, int ho, int wo, fl
     int chunk = max(64, cdiv(P, max(1, (148 * 4) / n)));
     dim3 grid(cdiv(P, chunk), n);
     if (dy->fmt == SKIT_FMT_F32)
-        dbias_kernel<0><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, dy->c, dy_org, ho, wo, chunk, dbias);
+        dbias_kernel<0><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, dy->c, dy->c, dy_org, ho, wo, chunk, dbias);
     else
-        dbias_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(nullptr, (const __nv_bfloat16*)dy->p0, (const __nv_bfloat16*)dy->p1, dy->hp, dy->wp, dy->c, dy_org, ho, wo, chunk, dbias);
+        dbias_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(nullptr, (const __nv_bfloat16*)dy->p0, (const __nv_bfloat16*)dy->p1, dy->hp, dy->wp, dy->c, dy->c, dy_org, ho, wo, chunk, dbias);
     return check_launch("dbias_kernel");
 }
 
@@ -539,9 +553,21 @@ int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
 bool wgrad_tc_eligible(const skit_operand* x, const skit_operand* dy, int k, int stride, int ho, int wo);
 }
 
+extern "C" int skit_conv2d_wgrad_ex(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
+                                    int k, int stride, int ho, int wo, float* scratch, float* dw, float* dbias, int impl,
+                                    int co_real, int ci_real, void* stream);
+
 extern "C" int skit_conv2d_wgrad(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
                                  int k, int stride, int ho, int wo, float* scratch, float* dw, float* dbias, int impl, void* stream) {
+    SKIT_REQUIRE(x && dy, "conv2d_wgrad: null pointer");
+    return skit_conv2d_wgrad_ex(x, org, dy, dy_org, k, stride, ho, wo, scratch, dw, dbias, impl, dy->c, x->c, stream);
+}
+
+extern "C" int skit_conv2d_wgrad_ex(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
+                                    int k, int stride, int ho, int wo, float* scratch, float* dw, float* dbias, int impl,
+                                    int co_real, int ci_real, void* stream) {
     SKIT_REQUIRE(x && dy && scratch && dw && x->p0 && dy->p0, "conv2d_wgrad: null pointer");
+    SKIT_REQUIRE(co_real > 0 && co_real <= dy->c && ci_real > 0 && ci_real <= x->c, "conv2d_wgrad: real channel counts exceed the operands'");
     float* dwf = scratch;
     int layout = 0;
     SKIT_REQUIRE(x->n == dy->n, "conv2d_wgrad: batch mismatch");
@@ -576,16 +602,16 @@ extern "C" int skit_conv2d_wgrad(const skit_operand* x, int org, const skit_oper
         if (rc) return rc;
     }
     {
-        int rc = unpack_wgrad(dwf, co, ci, k, dw, 1, layout, st);
+        int rc = unpack_wgrad(dwf, co_real, ci_real, k, dw, 1, layout, st, co, ci);
         if (rc) return rc;
     }
     if (dbias) {
         int chunk = max(64, cdiv(P, max(1, (148 * 4) / n)));
         dim3 grid(cdiv(P, chunk), n);
         if (dy->fmt == SKIT_FMT_F32)
-            dbias_kernel<0><<<grid, 256, 0, st>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, co, dy_org, ho, wo, chunk, dbias);
+            dbias_kernel<0><<<grid, 256, 0, st>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, co_real, co, dy_org, ho, wo, chunk, dbias);
         else
-            dbias_kernel<1><<<grid, 256, 0, st>>>(nullptr, (const __nv_bfloat16*)dy->p0, (const __nv_bfloat16*)dy->p1, dy->hp, dy->wp, co, dy_org, ho, wo, chunk, dbias);
+            dbias_kernel<1><<<grid, 256, 0, st>>>(nullptr, (const __nv_bfloat16*)dy->p0, (const __nv_bfloat16*)dy->p1, dy->hp, dy->wp, co_real, co, dy_org, ho, wo, chunk, dbias);
         return check_launch("dbias_kernel");
     }
     return SKIT_OK;

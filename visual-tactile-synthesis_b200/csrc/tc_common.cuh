@@ -171,4 +171,9 @@ int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
                     const uint32_t* box, const uint32_t* estrides);
 
 }  // namespace tc
+
+struct TcOut {  // where a conv's tile results land (defaults: dense [n][ho][wo][co])
+    int OH, OW, osy, osx, ooy, oox;
+};
+
 }  // namespace skit

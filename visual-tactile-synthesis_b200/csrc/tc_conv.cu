@@ -14,6 +14,7 @@
 //
 // Warp roles (128 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer,
 // warp 1 = TMEM allocator, all four warps = epilogue (warp w owns TMEM lanes 32w..32w+31).
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace skit {
@@ -225,20 +226,35 @@ static int launch_conv_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
 
 }  // namespace tc
 
+static bool halo_enabled();
+
 bool conv_tc_eligible(const skit_operand* x, const skit_weights* w, int stride) {
-    return x->fmt == SKIT_FMT_BF16X2 && w->hi && w->lo && (stride == 1 || stride == 2) && x->c % 64 == 0 &&
-           w->co % 64 == 0 && w->ci == x->c;
+    if (x->fmt != SKIT_FMT_BF16X2 || !w->hi || !w->lo || w->ci != x->c) return false;
+    if (stride == 1 && halo_enabled())   // halo kernel: any output width; input channels a multiple of 8, whole 64-chunks or a single thin chunk
+        return x->c % 8 == 0 && (x->c % 64 == 0 || x->c < 64);
+    return (stride == 1 || stride == 2) && x->c % 64 == 0 && w->co % 64 == 0;
 }
 
-struct TcOut {  // where the tile results land (defaults: dense [n][ho][wo][co])
-    int OH, OW, osy, osx, ooy, oox;
-};
+int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_lo, int ci_pack, int co, int kh, int kw,
+                        int ntaps_total, int tap_base, int org, int ho, int wo, const float* bias, float* y,
+                        const TcOut* out, double* stats, int stats_mode, cudaStream_t st);  // tc_conv_halo.cu
+
+static bool halo_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SKIT_TC_HALO");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
 
 // k: taps per side of THIS launch; ntaps_total: taps in the packed filter (weight map extent); tap_base: first tap.
 int conv_tc_launch(const skit_operand* x, const void* w_hi, const void* w_lo, int ci, int co, int k, int ntaps_total,
                    int tap_base, int stride, int org, int ho, int wo, const float* bias, float* y, const TcOut* out,
                    double* stats, int stats_mode, cudaStream_t st) {
     using namespace tc;
+    if (stride == 1 && halo_enabled())   // halo-tile kernel: every tap re-uses one staged activation tile
+        return conv_tc_halo_launch(x, w_hi, w_lo, ci, co, k, k, ntaps_total, tap_base, org, ho, wo, bias, y, out, stats, stats_mode, st);
     TcConvP p{};
     p.k = k; p.kc = ci / 64; p.org = org; p.stride = stride; p.tap_base = tap_base; p.ho = ho; p.wo = wo; p.co = co;
     p.tw = (wo <= 8) ? 8 : 16; p.th = 128 / p.tw;

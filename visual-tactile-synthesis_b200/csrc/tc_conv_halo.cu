@@ -1,0 +1,391 @@
+// tcgen05 + TMA implicit-GEMM convolution, stride 1, with the activation HALO TILE staged once per
+// 64-channel chunk and re-used by every filter tap.
+//
+//   D[pixel][co] = sum_{chunk, tap, c} A[pixel + tap][chunk*64 + c] * W[tap][co][chunk*64 + c]
+//
+// The per-tap kernel in tc_conv.cu re-reads the 128-pixel activation box from L2 for every tap (9x for a
+// 3x3, 49x for a 7x7 filter) and is L2->smem-fill bound (ncu: tensor pipe 64 % of active cycles, see
+// profiles/).  Here a CTA owns an 8 (x) by 16 (y) pixel tile and loads the (8+kw-1) x (16+kh-1) halo
+// tile of one 64-channel chunk with ONE TMA box (hi and lo planes); the UMMA A descriptor of tap (ky,kx)
+// simply starts (ky*pitch + kx) rows further into that tile with SBO = pitch*128 B, because an 8-pixel row
+// of the output tile is 8 consecutive 128-byte smem rows (the SWIZZLE_128B XOR acts on absolute smem
+// address bits, so row-granular start offsets read back exactly what TMA wrote).  Weights stream
+// through their own ring of (tap, chunk) stages (BN rows x 64 channels, hi + lo, SWIZZLE_128B — a first
+// version with 32-channel SWIZZLE_64B stages was correct but slower: 64-byte rows halve the useful
+// bytes per shared-memory wavefront of the B operand).  fp32 fidelity: 3 bf16 MMAs per product
+// (A_lo*W_hi + A_hi*W_lo + A_hi*W_hi), fp32 accumulation in TMEM.
+//
+// Warp roles (128 threads): warp 0 lane 0 = weight TMA producer, warp 2 lane 0 = activation TMA
+// producer, warp 1 = TMEM allocator + (lane 0) MMA issuer, all four warps = epilogue.
+// Channel counts: ci any multiple of 8 (TMA zero-fills the box beyond the tensor, the K loop only issues
+// the 16-channel steps that exist), co any value with N tile in {16, 64, 128, 256} (rows beyond co are
+// zero-filled by TMA and never stored).
+#include "tc_common.cuh"
+
+namespace skit {
+namespace tc {
+
+struct TcHaloP {
+    int kh, kw;        // filter taps (rows, cols)
+    int kc;            // 64-channel chunks (ceil(ci/64))
+    int kk_last;       // 16-channel K steps in the last chunk (1..4)
+    int org, tap_base;
+    int ho, wo, co;
+    int tiles_x;
+    int OH, OW, osy, osx, ooy, oox;   // output placement (phase-wise dgrad writes interleaved quarters)
+    const float* bias;
+    float* y;
+    double* stats;
+    int stats_per_n;
+    int pitch;         // halo tile width in pixels = 8 + kw - 1
+    int a_rows;        // halo tile rows*cols
+    int a_plane;       // bytes reserved per A plane (a_rows*128 rounded up to 1024)
+    int nw;            // weight stages
+    long long* dbg;    // optional per-CTA clock64 stamps [cta][8] (skit_debug_set_buffer), NULL in production
+};
+
+constexpr int NA = 2;  // activation stages
+
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;  // LBO unused for swizzled K-major
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+    return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(128, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, TcHaloP p) {
+    constexpr int W_PLANE = BN * 128;       // BN rows x 64 channels x 2 B
+    constexpr int W_STAGE = 2 * W_PLANE;
+    constexpr int TCOLS = BN < 32 ? 32 : BN;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+    const int a_stage = 2 * p.a_plane;
+    const uint32_t w0 = smem0 + NA * a_stage;
+    const uint32_t bar0 = w0 + p.nw * W_STAGE;
+    auto a_full = [&](int s) { return bar0 + 8u * s; };
+    auto a_empty = [&](int s) { return bar0 + 8u * (NA + s); };
+    auto w_full = [&](int s) { return bar0 + 8u * (2 * NA + s); };
+    auto w_empty = [&](int s) { return bar0 + 8u * (2 * NA + p.nw + s); };
+    const uint32_t tmem_full_bar = bar0 + 8u * (2 * NA + 2 * p.nw);
+    const uint32_t tmem_slot = tmem_full_bar + 8u;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem0));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.z;
+    const int n0 = blockIdx.y * BN;
+    const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
+    const int y0 = tile_y * 16, x0 = tile_x * 8;
+    long long* dbg = p.dbg ? p.dbg + 8ll * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
+        tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
+        for (int s = 0; s < NA; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < p.nw; s++) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+    const int ntaps = p.kh * p.kw;
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+
+    if (warp == 2 && lane == 0) {
+        // ---------------- activation producer: one halo box (hi + lo) per 64-channel chunk
+        const uint32_t bytes = 2u * (uint32_t)p.a_rows * 128u;
+        for (int c = 0; c < p.kc; c++) {
+            const int s = c % NA, ph = (c / NA) & 1;
+            mbar_wait(a_empty(s), ph ^ 1);
+            mbar_expect_tx(a_full(s), bytes);
+            const uint32_t sa = smem0 + s * a_stage;
+            tma_load_4d(sa, &tmA_hi, a_full(s), c * 64, p.org + x0, p.org + y0, n);
+            tma_load_4d(sa + p.a_plane, &tmA_lo, a_full(s), c * 64, p.org + x0, p.org + y0, n);
+        }
+    } else if (warp == 0 && lane == 0) {
+        // ---------------- weight producer: (chunk, tap) stages
+        int it = 0;
+        for (int c = 0; c < p.kc; c++)
+            for (int tap = 0; tap < ntaps; tap++, it++) {
+                const int s = it % p.nw, ph = (it / p.nw) & 1;
+                mbar_wait(w_empty(s), ph ^ 1);
+                mbar_expect_tx(w_full(s), W_STAGE);
+                const uint32_t sw = w0 + s * W_STAGE;
+                tma_load_3d(sw, &tmW_hi, w_full(s), c * 64, n0, p.tap_base + tap);
+                tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, n0, p.tap_base + tap);
+            }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+        const uint32_t sbo_a = (uint32_t)p.pitch * 128u;
+        int it = 0;
+        uint32_t acc = 0;
+        for (int c = 0; c < p.kc; c++) {
+            const int s = c % NA, ph = (c / NA) & 1;
+            const int kkc = (c == p.kc - 1) ? p.kk_last : 4;
+            mbar_wait(a_full(s), ph);
+            tc_fence_after();
+            if (dbg && c == 0) dbg[2] = clock64();
+            const uint32_t sa = smem0 + s * a_stage;
+            for (int ky = 0; ky < p.kh; ky++)
+                for (int kx = 0; kx < p.kw; kx++, it++) {
+                    const uint32_t arow = sa + (uint32_t)(ky * p.pitch + kx) * 128u;
+                    const int ws = it % p.nw, wph = (it / p.nw) & 1;
+                    mbar_wait(w_full(ws), wph);
+                    tc_fence_after();
+                    const uint32_t sw = w0 + ws * W_STAGE;
+                    for (int kk = 0; kk < kkc; kk++) {
+                        const uint32_t ko = (uint32_t)kk * 32u;
+                        const uint64_t a_hi = make_desc(arow + ko, 16, sbo_a);
+                        const uint64_t a_lo = make_desc(arow + p.a_plane + ko, 16, sbo_a);
+                        const uint64_t w_hi = make_desc(sw + ko, 16, 1024);
+                        const uint64_t w_lo = make_desc(sw + W_PLANE + ko, 16, 1024);
+                        mma_bf16(tmem_base, a_lo, w_hi, idesc, acc);
+                        acc = 1u;
+                        mma_bf16(tmem_base, a_hi, w_lo, idesc, 1u);
+                        mma_bf16(tmem_base, a_hi, w_hi, idesc, 1u);
+                    }
+                    mma_commit(w_empty(ws));
+                }
+            mma_commit(a_empty(s));
+        }
+        mma_commit(tmem_full_bar);
+        if (dbg) dbg[3] = clock64();
+    }
+    __syncwarp();
+
+    // ---------------- epilogue (all 4 warps): TMEM lane r = ty*8 + tx
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    __syncwarp();
+    if (dbg && threadIdx.x == 0) dbg[4] = clock64();
+    // The stage memory is free now: per-warp staging tile [32 rows][36 floats] (16-byte aligned rows whose stride
+    // keeps both the float4 row writes and the float4 row reads bank-conflict free), then the statistics scratch.
+    constexpr int STG = 36;
+    float* stg = reinterpret_cast<float*>(smem_gen) + warp * (32 * STG);
+    float* red = reinterpret_cast<float*>(smem_gen) + 4 * 32 * STG;  // [4 warps][TCOLS][2]
+    {
+        const int r = warp * 32 + lane;
+        const int ty = r >> 3, tx = r & 7;
+        const int oy = y0 + ty, ox = x0 + tx;
+        const int py = oy * p.osy + p.ooy, px = ox * p.osx + p.oox;
+        const bool valid = oy < p.ho && ox < p.wo && py < p.OH && px < p.OW;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        float* yrow = p.y + (((long long)n * p.OH + py) * p.OW + px) * p.co + n0;
+#pragma unroll 1
+        for (int c = 0; c < TCOLS; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+            if (BN >= 32 && n0 + c + 32 <= p.co) {
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] += __ldg(p.bias + n0 + c + j);
+                }
+                // registers (one pixel row per lane) -> smem tile -> coalesced 128-byte rows in global memory
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * STG + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                const int q = lane & 7;
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int rr = it * 4 + (lane >> 3);
+                    if ((vmask >> rr) & 1u) {
+                        const int g = warp * 32 + rr;
+                        const int gy = (y0 + (g >> 3)) * p.osy + p.ooy, gx = (x0 + (g & 7)) * p.osx + p.oox;
+                        float* dst = p.y + (((long long)n * p.OH + gy) * p.OW + gx) * p.co + n0 + c + q * 4;
+                        *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(stg + rr * STG + q * 4);
+                    }
+                }
+                if (p.stats) {   // lane j owns column c + j: sum it down the 32 staged rows
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < 32; rr++) {
+                        const float x = ((vmask >> rr) & 1u) ? stg[rr * STG + lane] : 0.f;
+                        s1 += x; s2 = fmaf(x, x, s2);
+                    }
+                    red[(warp * TCOLS + c + lane) * 2 + 0] = s1;
+                    red[(warp * TCOLS + c + lane) * 2 + 1] = s2;
+                }
+                __syncwarp();
+            } else {  // ragged channel tail (co not a multiple of 32, e.g. the 5-channel generator head)
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const bool cv = n0 + c + j < p.co;
+                    v[j] = cv ? v[j] + (p.bias ? __ldg(p.bias + n0 + c + j) : 0.f) : 0.f;
+                    if (valid && cv) yrow[c + j] = v[j];
+                }
+                if (p.stats) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        v[j] = valid ? v[j] : 0.f;
+                        sq[j] = v[j] * v[j];
+                    }
+                    const float s1 = col_reduce32(v, lane);
+                    const float s2 = col_reduce32(sq, lane);
+                    red[(warp * TCOLS + c + lane) * 2 + 0] = s1;
+                    red[(warp * TCOLS + c + lane) * 2 + 1] = s2;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[5] = clock64();
+    if (p.stats) {
+        for (int col = threadIdx.x; col < TCOLS; col += 128) {
+            if (n0 + col >= p.co) continue;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; w++) { s1 += red[(w * TCOLS + col) * 2]; s2 += red[(w * TCOLS + col) * 2 + 1]; }
+            double* dst = p.stats + ((long long)(p.stats_per_n ? n : 0) * p.co + n0 + col) * 2;
+            atomicAdd(dst, (double)s1);
+            atomicAdd(dst + 1, (double)s2);
+        }
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TCOLS>(tmem_base);
+    }
+    if (dbg && threadIdx.x == 0) dbg[6] = clock64();
+}
+
+long long* g_dbg_buffer = nullptr;
+
+int encode_bf16_map_sw(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, CUtensorMapSwizzle swz) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return SKIT_ERR_CUDA;
+    }
+    cuuint64_t gd[5], gs[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; i++) gs[i] = strides_bytes[i];
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu] box=[%u,%u,%u]", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                  box[0], box[1], rank > 2 ? box[2] : 0);
+        return SKIT_ERR_CUDA;
+    }
+    return SKIT_OK;
+}
+
+template <int BN>
+static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                       TcHaloP& p, dim3 grid, cudaStream_t st) {
+    constexpr int W_STAGE = 2 * BN * 128;
+    constexpr int MAX_SMEM = 227 * 1024;
+    const int fixed = NA * 2 * p.a_plane + 1024 + 512;
+    int nw = (MAX_SMEM - fixed) / W_STAGE;
+    if (nw > 8) nw = 8;
+    if (nw < 2) {
+        set_error("conv_tc_halo: halo tile of a %dx%d filter leaves no room for weight stages", p.kh, p.kw);
+        return SKIT_ERR_UNSUPPORTED;
+    }
+    p.nw = nw;
+    const int smem = fixed + nw * W_STAGE;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_tc_halo_kernel<%d>) failed: %s", BN, cudaGetErrorString(e));
+            return SKIT_ERR_CUDA;
+        }
+        attr_smem = MAX_SMEM;
+    }
+    conv_tc_halo_kernel<BN><<<grid, 128, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+    return check_launch("conv_tc_halo_kernel");
+}
+
+}  // namespace tc
+
+// Stride-1 valid convolution of a haloed bf16x2 operand.  kh x kw taps of THIS launch; ntaps_total = taps in the
+// packed filter [tap][co][ci_pack]; ci_pack = channel count of the weight pack rows (>= x->c, multiple of 8).
+int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_lo, int ci_pack, int co, int kh, int kw,
+                        int ntaps_total, int tap_base, int org, int ho, int wo, const float* bias, float* y,
+                        const TcOut* out, double* stats, int stats_mode, cudaStream_t st) {
+    using namespace tc;
+    const int ci = x->c;
+    TcHaloP p{};
+    p.kh = kh; p.kw = kw; p.kc = cdiv(ci, 64);
+    p.kk_last = cdiv(ci - (p.kc - 1) * 64, 16);
+    p.org = org; p.tap_base = tap_base; p.ho = ho; p.wo = wo; p.co = co;
+    p.tiles_x = cdiv(wo, 8);
+    const int tiles_y = cdiv(ho, 16);
+    if (out) { p.OH = out->OH; p.OW = out->OW; p.osy = out->osy; p.osx = out->osx; p.ooy = out->ooy; p.oox = out->oox; }
+    else { p.OH = ho; p.OW = wo; p.osy = 1; p.osx = 1; p.ooy = 0; p.oox = 0; }
+    p.bias = bias; p.y = y; p.stats = stats; p.stats_per_n = stats_mode == SKIT_NORM_INSTANCE;
+    p.pitch = 8 + kw - 1;
+    p.a_rows = p.pitch * (16 + kh - 1);
+    p.a_plane = ((p.a_rows * 128 + 1023) / 1024) * 1024;
+    p.dbg = g_dbg_buffer;
+
+    // N tile: as wide as possible (the weight stream is the L2 traffic that remains), narrower when that fills more SMs
+    int BN = 16;
+    if (co > 16) {
+        const long long tiles = (long long)p.tiles_x * tiles_y * x->n;
+        double best = 1e30;
+        const int avail = 227 * 1024 - (NA * 2 * p.a_plane + 1024 + 512);
+        for (int cand = 256; cand >= 64; cand >>= 1) {
+            if (cand > 64 && co % cand) continue;
+            if (cand > 64 && avail / (cand * 256) < 2) continue;   // needs two weight stages next to the halo tiles
+            const int ntile = cdiv(co, cand);
+            // cycles per 64-channel tap step: the MMAs (128 x cand x 16 at ~cand/2 cycles), or the shared-memory reads that
+            // feed them (A 4 KB + B cand*32 B per MMA at ~110 B/cycle) — narrow tiles re-read A and become smem bound
+            const double mma = cand * 0.53, rd = (4096.0 + cand * 32.0) / 80.0;
+            const double ksteps = (double)p.kc * kh * kw;
+            const double per = ksteps * (12.0 * (mma > rd ? mma : rd) + 100.0) + 3000.0 + 16.0 * cand;   // + prologue and epilogue
+            const double cost = (double)((tiles * ntile + 147) / 148) * per;
+            if (cost < best * 0.97) { best = cost; BN = cand; }
+        }
+    }
+    CUtensorMap a_hi, a_lo, m_hi, m_lo;
+    {
+        uint64_t dims[4] = {(uint64_t)ci, (uint64_t)x->wp, (uint64_t)x->hp, (uint64_t)x->n};
+        uint64_t strides[3] = {(uint64_t)ci * 2, (uint64_t)ci * 2 * x->wp, (uint64_t)ci * 2 * x->wp * x->hp};
+        uint32_t box[4] = {64, (uint32_t)p.pitch, (uint32_t)(16 + kh - 1), 1};
+        int rc = encode_bf16_map_sw(&a_hi, x->p0, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        rc = encode_bf16_map_sw(&a_lo, x->p1, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)ci_pack, (uint64_t)co, (uint64_t)ntaps_total};
+        uint64_t strides[2] = {(uint64_t)ci_pack * 2, (uint64_t)ci_pack * 2 * co};
+        uint32_t box[3] = {64, (uint32_t)BN, 1};
+        int rc = encode_bf16_map_sw(&m_hi, w_hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        rc = encode_bf16_map_sw(&m_lo, w_lo, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    dim3 grid(p.tiles_x * tiles_y, cdiv(co, BN), x->n);
+    if (BN == 256) return launch_halo<256>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
+    if (BN == 128) return launch_halo<128>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
+    if (BN == 64) return launch_halo<64>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
+    return launch_halo<16>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
+}
+
+}  // namespace skit
+
+/* Debug aid (not part of the product path): when set, the halo conv kernel writes clock64() stamps per CTA into
+ * buf[cta][8] = {start, setup done, first A tile landed, last MMA issued, accumulator ready, epilogue stores done, end}. */
+extern "C" int skit_debug_set_buffer(long long* buf) {
+    skit::tc::g_dbg_buffer = buf;
+    return SKIT_OK;
+}

@@ -33,8 +33,10 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(128, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
                 const __grid_constant__ CUtensorMap tmN_hi, const __grid_constant__ CUtensorMap tmN_lo, TcWgradP p) {
-    constexpr int M_BYTES = 2 * BOX_BYTES;          // 128 M-channels = 2 boxes
-    constexpr int N_BYTES = (BN / 64) * BOX_BYTES;
+    constexpr int M_BYTES = 2 * BOX_BYTES;          // 128 M-channels = 2 boxes (the second is TMA zero fill when Mdim == 64)
+    constexpr int NBOX = BN >= 64 ? BN / 64 : 1;    // a thin N side (<= 16 channels) still lands as one 64-channel box, zero-filled
+    constexpr int N_BYTES = NBOX * BOX_BYTES;
+    constexpr int TCOLS = BN < 32 ? 32 : BN;
     constexpr int STAGE_BYTES = 2 * M_BYTES + 2 * N_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -62,7 +64,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
         mbar_fence_init();
         fence_proxy_async();
     }
-    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -91,7 +93,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
                     tma_load_4d(sa + M_BYTES + g * BOX_BYTES, &tmM_lo, full_bar(s), mt * 128 + g * 64, mx, my, img);
                 }
 #pragma unroll
-                for (int g = 0; g < BN / 64; g++) {
+                for (int g = 0; g < NBOX; g++) {
                     tma_load_4d(sa + 2 * M_BYTES + g * BOX_BYTES, &tmN_hi, full_bar(s), n0 + g * 64, nx, ny, img);
                     tma_load_4d(sa + 2 * M_BYTES + N_BYTES + g * BOX_BYTES, &tmN_lo, full_bar(s), n0 + g * 64, nx, ny, img);
                 }
@@ -127,25 +129,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
         const int m = mt * 128 + warp * 32 + lane;
         float* obase = p.out + ((long long)tap * p.Ndim + n0) * p.Mdim + m;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = 0; c < TCOLS; c += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+            if (m < p.Mdim) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) atomicAdd(obase + (long long)(c + j) * p.Mdim, v[j]);
+                for (int j = 0; j < 32; j++)
+                    if (n0 + c + j < p.Ndim) atomicAdd(obase + (long long)(c + j) * p.Mdim, v[j]);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<BN>(tmem_base);
+        tmem_dealloc<TCOLS>(tmem_base);
     }
 }
 
 template <int BN, int STAGES>
 static int launch_wgrad_tc(const CUtensorMap& m_hi, const CUtensorMap& m_lo, const CUtensorMap& n_hi, const CUtensorMap& n_lo,
                            const TcWgradP& p, dim3 grid, cudaStream_t st) {
-    constexpr int SMEM = STAGES * (4 * BOX_BYTES + 2 * (BN / 64) * BOX_BYTES) + 1024 + 256;
+    constexpr int SMEM = STAGES * (4 * BOX_BYTES + 2 * (BN >= 64 ? BN / 64 : 1) * BOX_BYTES) + 1024 + 256;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -174,9 +179,12 @@ static int encode_act_map(CUtensorMap* hi, CUtensorMap* lo, const skit_operand* 
 // layout of the partial-sum buffer the kernel fills: 0 = [tap][ci][co] (M = co), 1 = [tap][co][ci] (M = ci)
 bool wgrad_tc_eligible(const skit_operand* x, const skit_operand* dy, int k, int stride, int ho, int wo) {
     if (x->fmt != SKIT_FMT_BF16X2 || dy->fmt != SKIT_FMT_BF16X2 || (stride != 1 && stride != 2)) return false;
+    // M side: the larger channel count, a multiple of 64 (a 64-channel M side pads to the 128-row UMMA tile with TMA
+    // zero fill); N side: a multiple of 64, or thin (<= 16 channels, a multiple of 8: N = 16 MMAs on a zero-filled box)
     const int ci = x->c, co = dy->c;
-    if (ci % 64 || co % 64) return false;
-    return co % 128 == 0 || ci % 128 == 0;
+    const int big = ci > co ? ci : co, small = ci > co ? co : ci;
+    if (big % 64) return false;
+    return small % 64 == 0 || (small <= 16 && small % 8 == 0);
 }
 
 int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org, int k, int stride,
@@ -188,14 +196,20 @@ int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
     p.tiles_x = cdiv(wo, 8); p.tiles_y = cdiv(ho, 8);
     p.n_img = x->n;
     p.total_tiles = p.tiles_x * p.tiles_y * x->n;
-    p.m_is_x = (co % 128 == 0) ? 0 : 1;
+    // M = whichever side fills 128-row tiles best: prefer a multiple of 128, else the larger one
+    if (co % 128 == 0 && co >= ci) p.m_is_x = 0;
+    else if (ci % 128 == 0 && ci >= co) p.m_is_x = 1;
+    else if (co % 128 == 0 && ci % 64 == 0) p.m_is_x = 0;
+    else if (ci % 128 == 0 && co % 64 == 0) p.m_is_x = 1;
+    else p.m_is_x = ci > co ? 1 : 0;
     p.x_org = org; p.x_stride = stride; p.d_org = dy_org;
     p.Mdim = p.m_is_x ? ci : co;
     p.Ndim = p.m_is_x ? co : ci;
     p.out = partial;
     *layout = p.m_is_x;
-    const int BN = (p.Ndim % 256 == 0) ? 256 : (p.Ndim % 128 == 0) ? 128 : 64;
-    const int items = k * k * (p.Mdim / 128) * (p.Ndim / BN);
+    const int BN = (p.Ndim % 256 == 0) ? 256 : (p.Ndim % 128 == 0) ? 128 : (p.Ndim % 64 == 0) ? 64 : 16;
+    const int mtiles = cdiv(p.Mdim, 128), ntiles = cdiv(p.Ndim, BN);
+    const int items = k * k * mtiles * ntiles;
     int splits = max(1, min(cdiv(2 * 148, items), p.total_tiles));
     p.tiles_per_cta = cdiv(p.total_tiles, splits);
     splits = cdiv(p.total_tiles, p.tiles_per_cta);
@@ -205,12 +219,13 @@ int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
     if (rc) return rc;
     rc = encode_act_map(&d_hi, &d_lo, dy, 1);
     if (rc) return rc;
-    dim3 grid(k * k * (p.Mdim / 128), p.Ndim / BN, splits);
+    dim3 grid(k * k * mtiles, ntiles, splits);
     const CUtensorMap &mh = p.m_is_x ? x_hi : d_hi, &ml = p.m_is_x ? x_lo : d_lo;
     const CUtensorMap &nh = p.m_is_x ? d_hi : x_hi, &nl = p.m_is_x ? d_lo : x_lo;
     if (BN == 256) return launch_wgrad_tc<256, 2>(mh, ml, nh, nl, p, grid, st);
     if (BN == 128) return launch_wgrad_tc<128, 3>(mh, ml, nh, nl, p, grid, st);
-    return launch_wgrad_tc<64, 4>(mh, ml, nh, nl, p, grid, st);
+    if (BN == 64) return launch_wgrad_tc<64, 4>(mh, ml, nh, nl, p, grid, st);
+    return launch_wgrad_tc<16, 4>(mh, ml, nh, nl, p, grid, st);
 }
 
 }  // namespace skit

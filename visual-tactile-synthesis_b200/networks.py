@@ -39,6 +39,7 @@ class Conv2d(nn.Module):
         super().__init__()
         self.ci, self.co, self.k, self.stride = ci, co, k, stride
         self.allow_tc = True   # the U-Net generator keeps its (mostly thin) layers on the fp32 CUDA-core kernels
+        self.tc_thin = False   # stride-1 layer with a thin side (9-channel stem, 5-channel head) routed to the halo tcgen05 kernel
         self.weight = nn.Parameter(torch.empty(co, ci, k, k))
         self.bias = nn.Parameter(torch.zeros(co)) if bias else None
         self.reset_parameters()
@@ -52,14 +53,31 @@ class Conv2d(nn.Module):
 
     @property
     def use_tc(self):
-        return TC_ENABLED and self.allow_tc and self.stride in (1, 2) and self.ci % 64 == 0 and self.co % 64 == 0 and (self.stride == 1 or self.k % 2 == 0)
+        if not (TC_ENABLED and self.allow_tc):
+            return False
+        if self.tc_thin and self.stride == 1:
+            return True
+        return self.stride in (1, 2) and self.ci % 64 == 0 and self.co % 64 == 0 and (self.stride == 1 or self.k % 2 == 0)
+
+    @property
+    def ci_pad(self):
+        """Input channels of the tensor-core operand (zero-padded to a multiple of 16 for thin inputs)."""
+        return self.ci if self.ci % 64 == 0 else -(-self.ci // 16) * 16
+
+    @property
+    def co_pad(self):
+        """Channels of the tensor-core output-gradient operand (zero-padded to a multiple of 8 for thin outputs)."""
+        return self.co if self.co % 64 == 0 else -(-self.co // 8) * 8
 
     def pack(self, mode):
         """mode 0 forward, 1 stride-1 dgrad (tensor-core), 2 gather dgrad (CUDA-core), 3 stride-2 phase dgrad (tensor-core)."""
         pk = self._packs.get(mode)
         if pk is None:
             bf16 = self.use_tc and mode in (0, 1, 3)
-            pk = ops.PackedWeights(self.weight, mode, want_f32=not bf16, want_bf16=bf16)
+            kpad = 0
+            if bf16 and self.tc_thin:
+                kpad = self.ci_pad if mode == 0 else self.co_pad
+            pk = ops.PackedWeights(self.weight, mode, want_f32=not bf16, want_bf16=bf16, kpad=kpad)
             self._packs[mode] = pk
         return pk
 
@@ -164,7 +182,7 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
     n, ho, wo, co = raw.shape
     g, sums = ops.act_norm_bwd_reduce(raw.shape, dpad, pad, pad_mode, dadd, raw, mr, norm_mode, gamma, beta, act)
     tc = layer.use_tc
-    q = 0 if not tc else (layer.k - 1 if layer.stride == 1 else layer.k // 2 - 1)
+    q = 0 if (not tc or not need_dgrad) else (layer.k - 1 if layer.stride == 1 else layer.k // 2 - 1)
     d_op = ops.norm_bwd_apply(g, raw, mr, norm_mode, gamma, sums, count, dgamma, dbeta, pad=q,
                               fmt=FMT_BF16X2 if tc else FMT_F32)
     if need_wgrad:
@@ -221,6 +239,9 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         for name, idx in (("_c1", 1), ("_c4", 4), ("_c8", 8), ("_u1", 12 + nb + 1), ("_u2", 12 + nb + 5), ("_out", 12 + nb + 9)):
             object.__setattr__(self, name, self.model[idx])
         object.__setattr__(self, "_blocks", [self.model[12 + b] for b in range(nb)])
+        if ngf % 64 == 0:   # tensor-core configuration: the thin 7x7 stem / head convs join the tcgen05 path (channel-padded)
+            self._c1.tc_thin = True
+            self._out.tc_thin = True
 
     # -- explicit forward.  srcs: list of NCHW fp32 tensors whose channel concat is the input.
     def fwd(self, srcs, mask=None, scale_nz=0.25, save=True, want_normal=True, taps=None, style_code=None):
@@ -234,8 +255,9 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
             if taps is not None and i in taps:
                 feats[i] = fn()
 
-        op0 = ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT)
-        tap(0, lambda: op0.data)
+        tc1 = self._c1.use_tc
+        op0 = ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT, fmt=FMT_BF16X2 if tc1 else FMT_F32, cpad=self._c1.ci_pad if tc1 else 0)
+        tap(0, lambda: ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT).data if tc1 else op0.data)
         raw1, st = _conv_fwd(self._c1, op0, 0, S_h, S_w, IN)
         mr1 = ops.stats_finalize(st, S_h * S_w)
         tap(1, lambda: raw1)
@@ -307,10 +329,16 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         IN = NORM_INSTANCE
         n, S_h, S_w = ctx["dims"]
         h2, w2, h4, w4 = S_h // 2, S_w // 2, S_h // 4, S_w // 4
-        d30 = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, 0)
         lo = self._out
-        ops.conv2d_wgrad(ctx["op26"], 0, d30, 0, lo.k, 1, S_h, S_w, lo.weight.grad, lo.bias.grad)
-        dpad26 = ops.conv2d_dgrad_gather(d30.data, lo.pack(2), 1, S_h + 6, S_w + 6)
+        if lo.use_tc:   # 5-channel gradient, zero-padded to 8 channels and haloed by k-1 for the flipped-filter input gradient
+            q = lo.k - 1
+            d30 = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, q, fmt=FMT_BF16X2, cpad=lo.co_pad)
+            ops.conv2d_wgrad(ctx["op26"], 0, d30, q, lo.k, 1, S_h, S_w, lo.weight.grad, lo.bias.grad)
+            dpad26, _ = ops.conv2d_fwd(d30, lo.pack(1), 1, 0, S_h + 6, S_w + 6)
+        else:
+            d30 = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, 0)
+            ops.conv2d_wgrad(ctx["op26"], 0, d30, 0, lo.k, 1, S_h, S_w, lo.weight.grad, lo.bias.grad)
+            dpad26 = ops.conv2d_dgrad_gather(d30.data, lo.pack(2), 1, S_h + 6, S_w + 6)
         dpad_u2 = _stage_bwd(self._u2, ctx["op_u2"], ctx["raw26"], ctx["mr26"], IN, ACT_RELU, S_h * S_w,
                              dpad=dpad26, pad=3, pad_mode=PAD_REFLECT)
         du2, _ = ops.act_norm_bwd_reduce((n, S_h, S_w, dpad_u2.shape[3]), dpad=dpad_u2, pad=1, pad_mode=PAD_ZERO)

@@ -39,11 +39,15 @@ class Operand:
 class PackedWeights:
     """Per-step repack of one conv's reference-layout weight (skit_pack_conv_weights)."""
 
-    def __init__(self, w, mode, want_f32=True, want_bf16=False):
+    def __init__(self, w, mode, want_f32=True, want_bf16=False, kpad=0):
         co, ci, k, _ = w.shape
         self.k, self.mode = k, mode
         # the GEMM reduces over `rci` channels per tap and produces `rco` columns
         self.rci, self.rco = (ci, co) if mode == 0 else (co, ci)
+        self.kpad = 0
+        if kpad and kpad > self.rci:     # bf16 pack with a zero-padded reduction axis (thin layers on tcgen05)
+            assert want_bf16 and not want_f32 and kpad % 8 == 0
+            self.kpad, self.rci = kpad, kpad
         dev = w.device
         self.f32 = torch.empty((k * k * self.rci, self.rco), dtype=torch.float32, device=dev) if want_f32 else None
         self.hi = torch.empty((k * k, self.rco, self.rci), dtype=torch.bfloat16, device=dev) if want_bf16 else None
@@ -55,6 +59,10 @@ class PackedWeights:
         self.refresh(w)
 
     def refresh(self, w):
+        if self.kpad:
+            L.call("skit_pack_conv_weights_padded", _p(w.detach()), self.co, self.ci, self.k, self.mode, self.kpad,
+                   _p(self.hi), _p(self.lo), L.stream())
+            return
         L.call("skit_pack_conv_weights", _p(w.detach()), self.co, self.ci, self.k, self.mode,
                _p(self.f32), _p(self.hi), _p(self.lo), L.stream())
 
@@ -90,10 +98,12 @@ def conv2d_dgrad_s2(dy_op, dy_pad, wp, k, ho, wo, hp, wp_):
 
 
 def conv2d_wgrad(x, org, dy, dy_org, k, stride, ho, wo, dw, dbias=None, impl=IMPL_AUTO):
-    """Accumulates into dw ([co][ci][k][k] view of the flat grad bucket) and dbias."""
+    """Accumulates into dw ([co][ci][k][k] view of the flat grad bucket) and dbias.  Operands may carry zero padding
+    channels beyond dw's real (co, ci)."""
     co, ci = dy.c, x.c
     scratch = torch.zeros((k * k * ci * co,), dtype=torch.float32, device=x.data.device)
-    L.call("skit_conv2d_wgrad", x.ref(), org, dy.ref(), dy_org, k, stride, ho, wo, _p(scratch), _p(dw), _p(dbias), impl, L.stream())
+    L.call("skit_conv2d_wgrad_ex", x.ref(), org, dy.ref(), dy_org, k, stride, ho, wo, _p(scratch), _p(dw), _p(dbias), impl,
+           int(dw.shape[0]), int(dw.shape[1]), L.stream())
 
 
 def stats_finalize(stats, count, eps=1e-5, running_mean=None, running_var=None, momentum=0.1):
@@ -226,13 +236,14 @@ def _src_arrays(srcs):
     return ptrs, chans
 
 
-def nchw_cat_to_operand(srcs, pad, pad_mode):
-    """srcs: list of contiguous NCHW fp32 tensors with equal N,H,W -> fp32 Operand of the channel concat."""
+def nchw_cat_to_operand(srcs, pad, pad_mode, fmt=FMT_F32, cpad=0):
+    """srcs: list of contiguous NCHW fp32 tensors with equal N,H,W -> Operand of the channel concat (fp32 or bf16x2),
+    zero-padded to `cpad` channels when given."""
     for s in srcs:
         assert s.is_cuda and s.is_contiguous() and s.dtype == torch.float32
     n, _, h, w = srcs[0].shape
     ctot = sum(int(s.shape[1]) for s in srcs)
-    op = Operand(n, h, w, ctot, pad, FMT_F32, srcs[0].device)
+    op = Operand(n, h, w, max(ctot, cpad), pad, fmt, srcs[0].device)
     ptrs, chans = _src_arrays(srcs)
     L.call("skit_nchw_cat_to_operand", ptrs, chans, len(srcs), n, h, w, op.ref(), pad, pad_mode, L.stream())
     return op
@@ -257,9 +268,9 @@ def g_head_fwd(raw, mask, scale_nz=0.25, want_normal=True):
     return fI, fT, fN
 
 
-def g_head_bwd(raw, mask, dI, dT, pad):
+def g_head_bwd(raw, mask, dI, dT, pad, fmt=FMT_F32, cpad=5):
     n, h, w, _ = raw.shape
-    op = Operand(n, h, w, 5, pad, FMT_F32, raw.device)
+    op = Operand(n, h, w, max(5, cpad), pad, fmt, raw.device)
     L.call("skit_g_head_bwd", _p(raw), _p(mask), _p(dI), _p(dT), n, h, w, op.ref(), pad, L.stream())
     return op
 
