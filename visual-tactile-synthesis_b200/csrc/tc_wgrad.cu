@@ -210,7 +210,8 @@ int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
     const int BN = (p.Ndim % 256 == 0) ? 256 : (p.Ndim % 128 == 0) ? 128 : (p.Ndim % 64 == 0) ? 64 : 16;
     const int mtiles = cdiv(p.Mdim, 128), ntiles = cdiv(p.Ndim, BN);
     const int items = k * k * mtiles * ntiles;
-    int splits = max(1, min(cdiv(2 * 148, items), p.total_tiles));
+    // split-K so that one wave of CTAs covers the SMs: every extra split adds a full tile of fp32 atomics to L2
+    int splits = max(1, min(items >= 148 ? 1 : 148 / items, p.total_tiles));
     p.tiles_per_cta = cdiv(p.total_tiles, splits);
     splits = cdiv(p.total_tiles, p.tiles_per_cta);
 

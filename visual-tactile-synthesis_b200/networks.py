@@ -22,6 +22,7 @@ from .ops import (ACT_LRELU, ACT_NONE, ACT_RELU, FMT_BF16X2, FMT_F32, NORM_BATCH
                   PAD_REFLECT, PAD_ZERO)
 
 TC_ENABLED = True  # tcgen05 path for eligible layers (64-multiple channels, stride 1)
+PARALLEL_SCALES = True  # run the scales of a multiscale discriminator on parallel streams
 
 
 def _require_cuda(t, who):
@@ -775,16 +776,32 @@ class MultiscaleDiscriminator(_FlatParamsMixin, nn.Module):
             setattr(self, "layer%d" % i, nn.Sequential(*NLayerDiscriminator._build(input_nc, ndf, n_layers, norm)))
         self._scales = [_d_stages(getattr(self, "layer%d" % i), norm) for i in range(num_D)]
 
+    def _side_streams(self, device):
+        """One side stream per extra scale: the scales own disjoint parameters and buffers, and their (small, latency
+        bound) kernels overlap when each scale runs on its own stream — also inside a captured CUDA graph, where
+        the fork / join becomes parallel branches."""
+        ss = getattr(self, "_streams", None)
+        if ss is None or ss[0].device != device:
+            ss = [torch.cuda.Stream(device=device) for _ in range(self.num_D - 1)]
+            object.__setattr__(self, "_streams", ss)
+        return ss
+
     def fwd(self, srcs, save=True, update_running=True):
         """-> (list of pred NHWC per scale i (full res first), ctx)"""
-        preds, ctxs = [], []
-        cur = srcs
+        pyramid = [srcs]
+        for i in range(1, self.num_D):
+            pyramid.append([ops.avgpool3s2_fwd(s) for s in pyramid[-1]])
+        main = torch.cuda.current_stream()
+        sides = self._side_streams(srcs[0].device) if PARALLEL_SCALES and self.num_D > 1 else []
+        preds, ctxs = [None] * self.num_D, [None] * self.num_D
         for i in range(self.num_D):
-            pred, c = _d_fwd(self._scales[self.num_D - 1 - i], self.norm, cur, save, update_running)
-            preds.append(pred)
-            ctxs.append(c)
-            if i != self.num_D - 1:
-                cur = [ops.avgpool3s2_fwd(s) for s in cur]
+            st = sides[i - 1] if (sides and i > 0) else main
+            if st is not main:
+                st.wait_stream(main)
+            with torch.cuda.stream(st):
+                preds[i], ctxs[i] = _d_fwd(self._scales[self.num_D - 1 - i], self.norm, pyramid[i], save, update_running)
+        for st in sides:
+            main.wait_stream(st)
         hw = [tuple(s.shape[-2:]) for s in srcs[:1]]
         return preds, dict(scales=ctxs, in_hw=hw[0], chans=[int(s.shape[1]) for s in srcs])
 
@@ -795,11 +812,18 @@ class MultiscaleDiscriminator(_FlatParamsMixin, nn.Module):
         sizes = [(H, W)]
         for _ in range(1, self.num_D):
             sizes.append(((sizes[-1][0] - 1) // 2 + 1, (sizes[-1][1] - 1) // 2 + 1))
-        dins = []
+        main = torch.cuda.current_stream()
+        sides = self._side_streams(dpreds[0].device) if PARALLEL_SCALES and self.num_D > 1 else []
+        dins = [None] * self.num_D
         for i in range(self.num_D):
-            d = _d_bwd(self._scales[self.num_D - 1 - i], self.norm, ctx["scales"][i], dpreds[i], need_wgrad,
-                       need_input_grad=input_slice is not None)
-            dins.append(d)
+            st = sides[i - 1] if (sides and i > 0) else main
+            if st is not main:
+                st.wait_stream(main)
+            with torch.cuda.stream(st):
+                dins[i] = _d_bwd(self._scales[self.num_D - 1 - i], self.norm, ctx["scales"][i], dpreds[i], need_wgrad,
+                                 need_input_grad=input_slice is not None)
+        for st in sides:
+            main.wait_stream(st)
         if input_slice is None:
             return None
         c0, cs = input_slice
