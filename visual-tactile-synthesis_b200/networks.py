@@ -169,6 +169,39 @@ class _FlatParamsMixin:
                 m.refresh_packs()
 
 
+# ----------------------------------------------------------------------------- weight gradients off the critical path
+ASYNC_WGRAD = True
+_WG = {}   # id of the launching stream -> (side stream, tensors kept alive until the join)
+
+
+def _wgrad_async(fn, keep):
+    """Nothing consumes a weight gradient before the optimiser, while the input-gradient chain is strictly serial:
+    launch the wgrad kernels on a side stream (a parallel branch of the captured graph) so they fill the SMs the
+    dgrad / elementwise kernels leave idle.  `keep`: the operands the side stream reads — held until `_wgrad_join`
+    so that the caching allocator cannot hand their memory to a later main-stream allocation."""
+    if not ASYNC_WGRAD:
+        fn()
+        return
+    cur = torch.cuda.current_stream()
+    ent = _WG.get(cur.cuda_stream)
+    if ent is None:
+        ent = (torch.cuda.Stream(device=cur.device), [])
+        _WG[cur.cuda_stream] = ent
+    side, ka = ent
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        fn()
+    ka.extend(keep)
+
+
+def _wgrad_join():
+    cur = torch.cuda.current_stream()
+    ent = _WG.get(cur.cuda_stream)
+    if ent is not None:
+        cur.wait_stream(ent[0])
+        ent[1].clear()
+
+
 # ----------------------------------------------------------------------------- shared conv stage helpers
 def _conv_fwd(layer, x_op, org, ho, wo, stats_mode, with_bias=True):
     pk = layer.pack(0)
@@ -191,8 +224,8 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
         # per-channel shift; d_raw sums to zero over the normalised axes) — the reference only accumulates
         # rounding noise there — so its reduction is skipped and the zeroed flat-grad entry stands.
         want_db = layer.bias is not None and norm_mode == NORM_NONE
-        ops.conv2d_wgrad(x_op, 0, d_op, q, layer.k, layer.stride, ho, wo, layer.weight.grad,
-                         layer.bias.grad if want_db else None)
+        _wgrad_async(lambda: ops.conv2d_wgrad(x_op, 0, d_op, q, layer.k, layer.stride, ho, wo, layer.weight.grad,
+                                              layer.bias.grad if want_db else None), (x_op, d_op))
     if not need_dgrad:
         return None
     if tc and layer.stride == 2:
@@ -359,6 +392,7 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         dpad1 = _stage_bwd(self._c4, ctx["op1"], ctx["raw4"], ctx["mr4"], IN, ACT_RELU, S_h * S_w, dadd=da4)
         _stage_bwd(self._c1, ctx["op0"], ctx["raw1"], ctx["mr1"], IN, ACT_RELU, S_h * S_w, dpad=dpad1, pad=1,
                    pad_mode=PAD_ZERO, need_dgrad=False)
+        _wgrad_join()
 
     # -- reference module API (networks.py:1131-1154): returns tanh output [n, 5, h, w]
     def forward(self, input, layers=[], encode_only=False, style_code=None):
@@ -759,6 +793,7 @@ def _d_bwd(stages, norm, ctx, dpred, need_wgrad=True, need_input_grad=False):
                         dbeta=bn.bias.grad if (bn is not None and need_wgrad) else None,
                         need_dgrad=dgrad, need_wgrad=need_wgrad)
         dpad, dadd = dx, None
+    _wgrad_join()
     return dpad
 
 
