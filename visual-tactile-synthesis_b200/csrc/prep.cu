@@ -497,8 +497,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_rows_kernel(BwdBP p, int c
 __global__ void bn_param_grad_kernel(const double* sums, int c, float* dgamma, float* dbeta) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
-    if (dbeta) dbeta[i] += (float)sums[2 * i];
-    if (dgamma) dgamma[i] += (float)sums[2 * i + 1];
+    if (dbeta) atomicAdd(dbeta + i, (float)sums[2 * i]);
+    if (dgamma) atomicAdd(dgamma + i, (float)sums[2 * i + 1]);
 }
 
 // ------------------------------------------------------------------------------ blur resamplers

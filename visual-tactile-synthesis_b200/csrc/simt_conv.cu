@@ -430,7 +430,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int co, int c
         int c = t % ci; int o = t / ci;
         const long long tap = ky * k + kx;
         float v = layout == 0 ? dwf[(tap * cip + c) * cop + o] : dwf[(tap * cop + o) * cip + c];
-        dw[i] = accumulate ? dw[i] + v : v;
+        if (accumulate) atomicAdd(dw + i, v);   // passes running on parallel streams accumulate into the same bucket
+        else dw[i] = v;
     }
 }
 

@@ -744,8 +744,11 @@ def _d_stages(seq, norm):
     return stages
 
 
-def _d_fwd(stages, norm, srcs, save, update_running=True):
-    """srcs: NCHW tensors (channel concat = D input).  Returns (pred NHWC [n,h,w,1], ctx)."""
+def _d_fwd(stages, norm, srcs, save, update_running=True, deferred=None):
+    """srcs: NCHW tensors (channel concat = D input).  Returns (pred NHWC [n,h,w,1], ctx).
+    deferred: a list — BatchNorm running-stat updates are appended to it as (stats, count, bn) instead of being applied,
+    so that passes running on parallel streams can apply them afterwards in the reference's order
+    (`apply_running_updates`)."""
     _require_cuda(srcs[0], "discriminator")
     n, _, h, w = srcs[0].shape
     x_op = ops.nchw_cat_to_operand(srcs, 2, PAD_ZERO)
@@ -757,6 +760,9 @@ def _d_fwd(stages, norm, srcs, save, update_running=True):
         if mode != NORM_NONE:
             cnt = n * ho * wo if mode == NORM_BATCH else ho * wo
             upd = bn is not None and update_running
+            if upd and deferred is not None:
+                deferred.append((st, cnt, bn))
+                upd = False
             mr = ops.stats_finalize(st, cnt, bn.eps if bn is not None else 1e-5,
                                     bn.running_mean if upd else None, bn.running_var if upd else None,
                                     bn.momentum if bn is not None else 0.1)
@@ -772,6 +778,14 @@ def _d_fwd(stages, norm, srcs, save, update_running=True):
                                    act, pad=2, pad_mode=PAD_ZERO, fmt=FMT_BF16X2 if nxt.use_tc else FMT_F32)
         h, w = ho, wo
     return pred, dict(saved=saved, n=n)
+
+
+def apply_running_updates(deferred):
+    """Apply the BatchNorm running-stat updates collected by `_d_fwd(..., deferred=...)`, in list order."""
+    for st, cnt, bn in deferred:
+        ops.stats_finalize(st, cnt, bn.eps, bn.running_mean, bn.running_var, bn.momentum)
+        bn.num_batches_tracked += 1
+    deferred.clear()
 
 
 def _d_bwd(stages, norm, ctx, dpred, need_wgrad=True, need_input_grad=False):
@@ -815,13 +829,16 @@ class MultiscaleDiscriminator(_FlatParamsMixin, nn.Module):
         """One side stream per extra scale: the scales own disjoint parameters and buffers, and their (small, latency
         bound) kernels overlap when each scale runs on its own stream — also inside a captured CUDA graph, where
         the fork / join becomes parallel branches."""
-        ss = getattr(self, "_streams", None)
-        if ss is None or ss[0].device != device:
-            ss = [torch.cuda.Stream(device=device) for _ in range(self.num_D - 1)]
-            object.__setattr__(self, "_streams", ss)
-        return ss
+        tab = getattr(self, "_streams", None)
+        if tab is None:
+            tab = {}
+            object.__setattr__(self, "_streams", tab)
+        key = (str(device), torch.cuda.current_stream().cuda_stream)   # passes launched from different streams do not share
+        if key not in tab:
+            tab[key] = [torch.cuda.Stream(device=device) for _ in range(self.num_D - 1)]
+        return tab[key]
 
-    def fwd(self, srcs, save=True, update_running=True):
+    def fwd(self, srcs, save=True, update_running=True, deferred=None):
         """-> (list of pred NHWC per scale i (full res first), ctx)"""
         pyramid = [srcs]
         for i in range(1, self.num_D):
@@ -834,7 +851,10 @@ class MultiscaleDiscriminator(_FlatParamsMixin, nn.Module):
             if st is not main:
                 st.wait_stream(main)
             with torch.cuda.stream(st):
-                preds[i], ctxs[i] = _d_fwd(self._scales[self.num_D - 1 - i], self.norm, pyramid[i], save, update_running)
+                dl = [] if deferred is not None else None
+                preds[i], ctxs[i] = _d_fwd(self._scales[self.num_D - 1 - i], self.norm, pyramid[i], save, update_running, dl)
+                if dl:
+                    deferred.extend(dl)
         for st in sides:
             main.wait_stream(st)
         hw = [tuple(s.shape[-2:]) for s in srcs[:1]]

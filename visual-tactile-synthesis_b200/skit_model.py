@@ -207,7 +207,7 @@ class SinSKITGModel:
         self._blob_evt[i] = evt
 
     # ------------------------------------------------------------------ forward
-    def forward(self, save=None, rand=None, staged=False):
+    def forward(self, save=None, rand=None, staged=False, real_aug=True):
         """sinskitG_model.py:1293-1344: G, channel split, *M, normal, DiffAugment('bs') real + fake, *M."""
         opt = self.opt
         save = self.isTrain if save is None else save
@@ -220,7 +220,8 @@ class SinSKITGModel:
                 if not staged:
                     self._stage_rand(rand)
                 u = self._u_dev
-                self.aug_real_I = ops.diffaug_bs_mask(self.real_I, self.M, u[0], u[1])
+                if real_aug:    # the train step computes it on the real-data branch instead
+                    self.aug_real_I = ops.diffaug_bs_mask(self.real_I, self.M, u[0], u[1])
                 self.aug_fake_I = ops.diffaug_bs_mask(self.fake_I, self.M, u[2], u[3])
             else:
                 self.aug_real_I, self.aug_fake_I = self.real_I, self.fake_I
@@ -292,64 +293,102 @@ class SinSKITGModel:
             return self._loss_raw[0]
         return self._step_body()
 
+    # -- parallel branches of the step (side streams; parallel branches of the captured graph)
+    def _fork(self, i):
+        bs = getattr(self, "_bstreams", None)
+        if bs is None:
+            bs = self._bstreams = [torch.cuda.Stream(device=self.device) for _ in range(5)]
+        bs[i].wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(bs[i])
+
+    def _join(self, *idx):
+        cur = torch.cuda.current_stream()
+        for i in idx:
+            cur.wait_stream(self._bstreams[i])
+
+    def _d_pass(self, net, srcs, sign, slot, gscale, deferred):
+        """One discriminator pass of a D step: forward, softplus GAN loss, full backward (weight gradients accumulate
+        atomically into the net's flat bucket, so passes on parallel streams may overlap)."""
+        preds, ctx = net.fwd(srcs, deferred=deferred)
+        net.bwd(ctx, self._gan(preds, sign, slot, gscale))
+
     def _step_body(self):
-        """All device work of one train step; reads only persistent device buffers (graph-capturable)."""
+        """All device work of one train step; reads only persistent device buffers (graph-capturable).
+        Dependency structure used for overlap: the real-data passes of D and D2 do not depend on the generator, the
+        D2 passes do not depend on D, and nothing but the optimiser consumes weight gradients.  BatchNorm running
+        statistics are applied after the joins in the reference's order (fake, [full-res], more, real)."""
         opt = self.opt
         G, D, D2 = self.netG, self.netD, self.netD2
         NT, NF = self.NT, opt.add_fake_T_sample_size
         n = self.real_S.shape[0]
-        self.forward(save=True, staged=True)
-        fake_I, fake_T = self.fake_I, self.fake_T
         ox, oy = self.ox, self.oy
-        # compute_additional_output (:1268-1291): patch gathers, written straight into the D2 input buffers
-        fake_T_p = ops.patch_gather([fake_T], ox, oy, 32)
-        ops.patch_gather([fake_T, self.real_S, self.aug_fake_I], ox, oy, 32, ctot=7, dst=self.fake_in)
-        ops.patch_gather([self.real_S, self.aug_real_I], ox, oy, 32, ctot=7, coffs=[2, 3], dst=self.real_in)
         L = torch.zeros(8 + 3 * NT + NF, dtype=torch.float32, device=self.device)
         sl = dict(D_fake=L[0:1], D_real=L[1:2], G_GAN=L[2:3], G_L1=L[3:4], G2_L1=L[4:5],
                   D2_fake=L[8:8 + NT], D2_real=L[8 + NT:8 + 2 * NT], G2_GAN=L[8 + 2 * NT:8 + 3 * NT], D2_more=L[8 + 3 * NT:])
-
-        # ---- D1 step (:648-653, compute_D1_loss): un-augmented fake/real, conditioned on the sketch
         D.zero_grad()
-        pf, cf = D.fwd([self.real_S, fake_I])
-        dpf = self._gan(pf, +1.0, sl["D_fake"], 0.5 * opt.lambda_G1_GAN / n)
-        D.bwd(cf, dpf)
-        del cf
-        pr, cr = D.fwd([self.real_S, self.real_I])
-        dpr = self._gan(pr, -1.0, sl["D_real"], 0.5 * opt.lambda_G1_GAN / n)
-        D.bwd(cr, dpr)
-        del cr
+        D2.zero_grad()
+        run_D, run_D2 = {}, {}
+        more = opt.use_more_fakeT and NF
+
+        # ---- real-data passes: independent of G, start them first
+        with self._fork(0):     # D1 real (compute_D1_loss :1346-1407)
+            run_D["real"] = []
+            self._d_pass(D, [self.real_S, self.real_I], -1.0, sl["D_real"], 0.5 * opt.lambda_G1_GAN / n, run_D["real"])
+        with self._fork(1):     # D2 real (compute_D2_loss :1409-1617); its conditioning image is the DiffAugmented real
+            if opt.use_diffaug:
+                self.aug_real_I = ops.diffaug_bs_mask(self.real_I, self.M, self._u_dev[0], self._u_dev[1])
+            else:
+                self.aug_real_I = self.real_I
+            ops.patch_gather([self.real_S, self.aug_real_I], ox, oy, 32, ctot=7, coffs=[2, 3], dst=self.real_in)
+            run_D2["real"] = []
+            self._d_pass(D2, [self.real_in], -1.0, sl["D2_real"], 0.5 * opt.lambda_G2_GAN / NT, run_D2["real"])
+
+        # ---- generator forward + compute_additional_output (:1268-1291): patch gathers straight into the D2 inputs
+        self.forward(save=True, staged=True, real_aug=False)
+        fake_I, fake_T = self.fake_I, self.fake_T
+        fake_T_p = ops.patch_gather([fake_T], ox, oy, 32)
+        ops.patch_gather([fake_T, self.real_S, self.aug_fake_I], ox, oy, 32, ctot=7, dst=self.fake_in)
+        if more:
+            ops.patch_gather([fake_T, self.real_S, fake_I], self._fo_dev[0], self._fo_dev[1], 32, ctot=7, dst=self.more_in)
+
+        # ---- fake passes: D2 (patches) and D2 (random patches) beside D1 (full image)
+        with self._fork(2):
+            run_D2["fake"] = []
+            self._d_pass(D2, [self.fake_in], +1.0, sl["D2_fake"], 0.5 * opt.lambda_G2_GAN / NT, run_D2["fake"])
+            if opt.run_full_res_D2:  # visualisation only in the reference (:1495-1500); updates BN running stats
+                self.pred_fake_T_full = D2.fwd([fake_T, self.real_S, self.aug_fake_I, self.M], save=False, deferred=run_D2["fake"])[0][-1]
+        if more:
+            with self._fork(3):
+                run_D2["more"] = []
+                self._d_pass(D2, [self.more_in], +1.0, sl["D2_more"], 0.5 * opt.lambda_G2_GAN / NF, run_D2["more"])
+        run_D["fake"] = []
+        self._d_pass(D, [self.real_S, fake_I], +1.0, sl["D_fake"], 0.5 * opt.lambda_G1_GAN / n, run_D["fake"])
+
+        # ---- D1 update (:648-653)
+        self._join(0)
+        for k in ("fake", "real"):
+            networks.apply_running_updates(run_D[k])
         self._allreduce(D)
         self._adam(D, 0)
 
-        # ---- D2 step (:654-667, compute_D2_loss): touch patches conditioned on sketch + augmented image + mask
-        D2.zero_grad()
-        p2f, c2f = D2.fwd([self.fake_in])
-        D2.bwd(c2f, self._gan(p2f, +1.0, sl["D2_fake"], 0.5 * opt.lambda_G2_GAN / NT))
-        del c2f
-        if opt.run_full_res_D2:  # visualisation only in the reference (:1495-1500); updates BN running stats
-            self.pred_fake_T_full = D2.fwd([fake_T, self.real_S, self.aug_fake_I, self.M], save=False)[0][-1]
-        if opt.use_more_fakeT and NF:
-            fox_d, foy_d = self._fo_dev[0], self._fo_dev[1]
-            ops.patch_gather([fake_T, self.real_S, fake_I], fox_d, foy_d, 32, ctot=7, dst=self.more_in)
-            p2m, c2m = D2.fwd([self.more_in])
-            D2.bwd(c2m, self._gan(p2m, +1.0, sl["D2_more"], 0.5 * opt.lambda_G2_GAN / NF))
-            del c2m
-        p2r, c2r = D2.fwd([self.real_in])
-        D2.bwd(c2r, self._gan(p2r, -1.0, sl["D2_real"], 0.5 * opt.lambda_G2_GAN / NT))
-        del c2r
+        # ---- D2 update (:654-667)
+        self._join(1, 2, *([3] if more else []))
+        for k in ("fake", "more", "real"):
+            if k in run_D2:
+                networks.apply_running_updates(run_D2[k])
         self._allreduce(D2)
         self._adam(D2, 1)
 
         # ---- G step (:680-694): GAN through the updated (frozen) D, L1, patch L1; G2 GAN is value-only
         G.zero_grad()
+        with self._fork(4):
+            pg2, _ = D2.fwd([self.fake_in], save=False)           # detached clone in the reference (:1751,1781)
+            self._gan(pg2, -1.0, sl["G2_GAN"])
         pg, cg = D.fwd([self.real_S, fake_I])
         dpg = self._gan(pg, -1.0, sl["G_GAN"], opt.lambda_G1_GAN / n)
         dI = D.bwd(cg, dpg, need_wgrad=False, input_slice=(opt.input_nc, 3))
         del cg
         ops.l1_loss(fake_I, self.real_I, opt.lambda_G1_L1 / fake_I.numel(), sl["G_L1"], dI, opt.lambda_G1_L1 / fake_I.numel(), accumulate=True)
-        pg2, _ = D2.fwd([self.fake_in], save=False)           # detached clone in the reference (:1751,1781)
-        self._gan(pg2, -1.0, sl["G2_GAN"])
         per_patch = fake_T_p.numel() // NT
         dTp = torch.empty_like(fake_T_p)
         ops.l1_loss(fake_T_p, self.real_T, opt.lambda_G2_L1 / per_patch / n, sl["G2_L1"], dTp, opt.lambda_G2_L1 / per_patch / n)
@@ -357,6 +396,7 @@ class SinSKITGModel:
         ops.patch_scatter_add(dTp, 0, 2, ox, oy, dT)
         G.bwd(self._g_ctx, dI, dT)
         self._g_ctx = None
+        self._join(4)
         self._allreduce(G)
         self._adam(G, 2)
         self._loss_raw = (L, NT, NF)
