@@ -194,6 +194,13 @@ int skit_norm_bwd_apply(const float* g, const float* raw, int n, int h, int w, i
                         const double* sums, double count, float* dgamma, float* dbeta,
                         const skit_operand* op, int pad, void* stream);
 
+/* Same, with an optional dense gradient `extra` [n][h][w][c] added to d_raw: the gradient of a feature tapped on the raw
+ * conv output (ResnetGenerator.forward(layers=...), networks.py:1131-1150, as used by the PatchNCE wiring). */
+int skit_norm_bwd_apply_ex(const float* g, const float* raw, int n, int h, int w, int c,
+                           const float* mean_rstd, int norm_mode, const float* gamma,
+                           const double* sums, double count, float* dgamma, float* dbeta,
+                           const float* extra, const skit_operand* op, int pad, void* stream);
+
 /* Antialiased resamplers (networks.py:51-74 Downsample, :87-107 Upsample), NHWC fp32 dense.
  * down: reflect pad 1, depthwise [1,2,1]^2/16, stride 2  ([h][w] -> [h/2][w/2], even h,w)
  * up:   replicate pad 1, depthwise conv_transpose [1,3,3,1]^2*4/64 stride 2, cropped -> [2h][2w] */
@@ -225,6 +232,11 @@ int skit_g_head_bwd(const float* raw, const float* mask, const float* dI, const 
  * default U-Net generator, whose last layers are separate transposed convs (networks.py:1635-1644). raw: [n][h][w][5]. */
 int skit_g_head_bwd_split(const float* raw, const float* mask, const float* dI, const float* dT,
                           int n, int h, int w, const skit_operand* opI, const skit_operand* opT, int pad, void* stream);
+
+/* y[n][0][h][w] = mean_c x[n][c][h][w] and its adjoint dx[n][c][h][w] += dy[n][0][h][w] / c  (NCHW planes): the
+ * 1-channel view of the generated image that the PatchNCE query branch re-encodes (PatchNCE wiring). */
+int skit_channel_mean(const float* x, int n, int c, int h, int w, float* y, void* stream);
+int skit_channel_mean_bwd(const float* dy, int n, int c, int h, int w, float* dx, void* stream);
 
 /* DiffAugment policy 'bs' followed by *M (thirdparty/DiffAugment.py:25-33; sinskitG_model.py:1330-1340).
  * u_b, u_s: [n] device floats (the host's torch.rand draws). x: [n][3][h][w]. */

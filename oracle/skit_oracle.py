@@ -517,6 +517,20 @@ def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.
     l_l1_2 = ((fake_T_p - real_T).abs() * cfg.lambda_G2_L1).view(-1, NT, *fake_T_p.shape[1:]).sum(dim=1).mean()
     losses.update(G_GAN=l_gan.item(), G_L1=l_l1.item(), G2_GAN=l_g2.item(), G2_L1=l_l1_2.item())
     loss_G = l_gan + l_l1 + l_g2 + l_l1_2
+    if cfg.lambda_NCE > 0:
+        # CUT-style PatchNCE wiring (NEW behaviour: PatchNCELoss / PatchSampleF are dead code in the reference, SURVEY.md 0.4;
+        # the functions themselves are pinned against the reference in tests/golden/ops.npz).  keys: generator features of
+        # the input; query: the same encoder on the channel mean of the generated image (+ the same positional encoding).
+        layers = sorted(cfg.nce_layers)
+        with torch.no_grad():
+            feat_k = resnet_g_forward(sdG_run, torch.cat([real_S, S_pe], 1), cfg.n_blocks, layers=layers, encode_only=True)
+        S_q = fake_I.mean(1, keepdim=True)
+        feat_q = resnet_g_forward(sdG_run, torch.cat([S_q, S_pe], 1), cfg.n_blocks, layers=layers, encode_only=True)
+        kp = patch_sample_f(feat_k, rand["nce_ids"])
+        qp = patch_sample_f(feat_q, rand["nce_ids"])
+        l_nce = sum(patchnce_loss(q, k, cfg.nce_T, batch_size=real_S.shape[0]).mean() for q, k in zip(qp, kp)) / len(layers) * cfg.lambda_NCE
+        losses["NCE"] = l_nce.item()
+        loss_G = loss_G + l_nce
     for k in gp:
         sdG[k] = gp[k]
     grads_G = run_opt("G", sdG, cfg.lr, loss_G)

@@ -181,3 +181,38 @@ def test_cuda_graph_replay_matches_eager_step():
             # beta1 = 0: each weight moves by ~lr whatever the gradient size; only sign-ambiguous (near-zero
             # gradient) entries may differ between two runs of the same arithmetic with reordered atomics
             assert ((pa - pb).abs() > 2e-4).float().mean().item() < 0.02
+
+
+def test_train_step_with_patchnce_vs_oracle():
+    """BASELINE.json configs[2] wiring at a small size: GAN + L1 + patch-L1 + PatchNCE (5 feature layers, netF='sample').
+    The PatchNCE term's value and its gradient contribution to G (through the query encoder pass and through fake_I)."""
+    import vts_b200
+    from oracle import skit_oracle as O
+    S, NT, NF, P = 64, 8, 4, 64
+    torch.manual_seed(1)
+    opt = vts_b200.default_options(batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_NCE=1.0, num_patches=P)
+    m = vts_b200.SinSKITGModel(opt)
+    sds = [{k: v.detach().cpu().clone() for k, v in net.state_dict().items()} for net in (m.netG, m.netD, m.netD2)]
+    batch = O.synthetic_batch(S, NT=NT, seed=0, ellipse_mask=True)
+    rs = np.random.RandomState(5)
+    sizes = [m.netG.feature_hw(l, S, S) for l in m.nce_layers]
+    rand = dict(real_b=[0.3], real_s=[0.8], fake_b=[0.6], fake_s=[0.2],
+                fake_ox=np.array([3, 10, 20, 7], dtype=np.int32), fake_oy=np.array([5, 1, 12, 30], dtype=np.int32),
+                nce_ids=[rs.permutation(h * w)[:min(P, h * w)] for h, w in sizes])
+    m.set_input(batch)
+    m.optimize_parameters(1, rand=rand)
+    torch.cuda.synchronize()
+    cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_NCE=1.0, num_patches=P)
+    sdG, sdD, sdD2 = [copy.deepcopy(s) for s in sds]
+    res = O.train_step(cfg, sdG, sdD, sdD2, {}, O.step_inputs_from_batch(batch), rand, step=1)
+    losses = m.get_current_losses()
+    assert "NCE" in losses and "NCE" in res["losses"]
+    for k, v in res["losses"].items():
+        assert abs(losses[k] - v) <= GATE * max(1.0, abs(v)), (k, losses[k], v)
+    print("G worst grad rel err vs oracle (with PatchNCE)", check_grads(m.netG, {k: v.numpy() for k, v in res["grads_G"].items()}, "G"))
+    # the NCE term must actually move the gradient: compare with a run without it
+    cfg0 = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF)
+    sdG0, sdD0, sdD20 = [copy.deepcopy(s) for s in sds]
+    res0 = O.train_step(cfg0, sdG0, sdD0, sdD20, {}, O.step_inputs_from_batch(batch), rand, step=1)
+    k = "model.12.conv_block.1.weight"
+    assert rel(res["grads_G"][k], res0["grads_G"][k]) > 1e-3

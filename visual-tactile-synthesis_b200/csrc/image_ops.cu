@@ -174,6 +174,25 @@ __global__ void __launch_bounds__(256) g_head_bwd_split_kernel(const float* __re
     }
 }
 
+// Channel mean of an NCHW image and its adjoint (the 1-channel "sketch-like" view of the generated RGB image that the
+// PatchNCE query branch feeds back through the generator's encoder).
+__global__ void __launch_bounds__(256) channel_mean_kernel(const float* __restrict__ x, int n, int c, long long hw, float* __restrict__ y) {
+    const long long total = (long long)n * hw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / hw, pix = i - b * hw;
+        float s = 0.f;
+        for (int j = 0; j < c; j++) s += x[(b * c + j) * hw + pix];
+        y[i] = s / (float)c;
+    }
+}
+__global__ void __launch_bounds__(256) channel_mean_bwd_kernel(const float* __restrict__ dy, int n, int c, long long hw, float* __restrict__ dx) {
+    const long long total = (long long)n * c * hw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i % hw, b = i / (hw * c);
+        dx[i] += dy[b * hw + pix] / (float)c;
+    }
+}
+
 // ------------------------------------------------------------------------------ DiffAugment 'bs' * M
 __global__ void __launch_bounds__(256) diffaug_kernel(const float* __restrict__ x, const float* __restrict__ mask,
                                                       const float* __restrict__ ub, const float* __restrict__ us, int n, int h, int w, float* y) {
@@ -507,6 +526,18 @@ extern "C" int skit_g_head_bwd_split(const float* raw, const float* mask, const 
     g_head_bwd_split_kernel<<<grid_for((long long)n * opI->hp * opI->wp, 256), 256, 0, as_stream(stream)>>>(
         raw, mask, dI, dT, n, h, w, (float*)opI->p0, (float*)opT->p0, pad);
     return check_launch("g_head_bwd_split_kernel");
+}
+
+extern "C" int skit_channel_mean(const float* x, int n, int c, int h, int w, float* y, void* stream) {
+    SKIT_REQUIRE(x && y && n > 0 && c > 0 && h > 0 && w > 0, "channel_mean: bad arguments");
+    channel_mean_kernel<<<grid_for((long long)n * h * w, 256), 256, 0, as_stream(stream)>>>(x, n, c, (long long)h * w, y);
+    return check_launch("channel_mean_kernel");
+}
+
+extern "C" int skit_channel_mean_bwd(const float* dy, int n, int c, int h, int w, float* dx, void* stream) {
+    SKIT_REQUIRE(dy && dx && n > 0 && c > 0 && h > 0 && w > 0, "channel_mean_bwd: bad arguments");
+    channel_mean_bwd_kernel<<<grid_for((long long)n * c * h * w, 256), 256, 0, as_stream(stream)>>>(dy, n, c, (long long)h * w, dx);
+    return check_launch("channel_mean_bwd_kernel");
 }
 
 extern "C" int skit_diffaug_bs_mask(const float* x, const float* mask, const float* u_b, const float* u_s,

@@ -379,6 +379,7 @@ struct BwdBP {
     const double* sums; double inv_count;
     float* o0; __nv_bfloat16* oh; __nv_bfloat16* ol; int fmt;
     int pad;
+    const float* extra;   // optional dense [n][h][w][c] gradient added to d_raw (a feature tap on the raw conv output)
 };
 
 template <int VEC>
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(BwdBP p) {
                     const float gam = p.gamma ? p.gamma[ch + j] : 1.f;
                     gg = gam * rstd * (gg - m0 - xhat * m1);
                 }
+                if (p.extra) gg += p.extra[src + j];
                 v[j] = gg;
             }
         }
@@ -478,6 +480,10 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_rows_kernel(BwdBP p, int c
                         const float xhat = (r4[j] - mean[j]) * rstd[j];
                         v[j] = gam[j] * rstd[j] * (v[j] - m0[j] - xhat * m1[j]);
                     }
+                }
+                if (ok && p.extra) {
+                    const float4 e = *reinterpret_cast<const float4*>(p.extra + (srow + x) * p.c + ch);
+                    v[0] += e.x; v[1] += e.y; v[2] += e.z; v[3] += e.w;
                 }
                 const long long dst = (drow + px) * p.c + ch;
                 if (FMT == SKIT_FMT_F32) {
@@ -759,10 +765,22 @@ extern "C" int skit_act_norm_bwd_reduce(const float* dpad, int pad, int pad_mode
                                        gamma, beta, act, g, sums, stream);
 }
 
+extern "C" int skit_norm_bwd_apply_ex(const float* g, const float* raw, int n, int h, int w, int c,
+                                      const float* mean_rstd, int norm_mode, const float* gamma,
+                                      const double* sums, double count, float* dgamma, float* dbeta,
+                                      const float* extra, const skit_operand* op, int pad, void* stream);
+
 extern "C" int skit_norm_bwd_apply(const float* g, const float* raw, int n, int h, int w, int c,
                                    const float* mean_rstd, int norm_mode, const float* gamma,
                                    const double* sums, double count, float* dgamma, float* dbeta,
                                    const skit_operand* op, int pad, void* stream) {
+    return skit_norm_bwd_apply_ex(g, raw, n, h, w, c, mean_rstd, norm_mode, gamma, sums, count, dgamma, dbeta, nullptr, op, pad, stream);
+}
+
+extern "C" int skit_norm_bwd_apply_ex(const float* g, const float* raw, int n, int h, int w, int c,
+                                      const float* mean_rstd, int norm_mode, const float* gamma,
+                                      const double* sums, double count, float* dgamma, float* dbeta,
+                                      const float* extra, const skit_operand* op, int pad, void* stream) {
     SKIT_REQUIRE(g && op && n > 0 && h > 0 && w > 0 && c > 0 && pad >= 0, "norm_bwd_apply: bad arguments");
     SKIT_REQUIRE((norm_mode == SKIT_NORM_NONE) == (mean_rstd == nullptr), "norm_bwd_apply: mean_rstd must be given iff norm_mode != none");
     SKIT_REQUIRE(norm_mode == SKIT_NORM_NONE || (sums && raw && count > 0), "norm_bwd_apply: sums/raw/count required with a norm");
@@ -772,6 +790,7 @@ extern "C" int skit_norm_bwd_apply(const float* g, const float* raw, int n, int 
     p.g = g; p.raw = raw; p.n = n; p.h = h; p.w = w; p.c = c;
     p.mr = mean_rstd; p.per_n = norm_mode == SKIT_NORM_INSTANCE; p.gamma = gamma;
     p.sums = sums; p.inv_count = count > 0 ? 1.0 / count : 0.0;
+    p.extra = extra;
     p.fmt = op->fmt;
     if (op->fmt == SKIT_FMT_F32) p.o0 = (float*)op->p0;
     else { p.oh = (__nv_bfloat16*)op->p0; p.ol = (__nv_bfloat16*)op->p1; }

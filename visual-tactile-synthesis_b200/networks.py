@@ -209,21 +209,23 @@ def _conv_fwd(layer, x_op, org, ho, wo, stats_mode, with_bias=True):
 
 
 def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None,
-               gamma=None, beta=None, dgamma=None, dbeta=None, need_dgrad=True, need_wgrad=True):
+               gamma=None, beta=None, dgamma=None, dbeta=None, need_dgrad=True, need_wgrad=True, draw_add=None):
     """Backward of [conv -> norm -> act] given the gradient w.r.t. the activated output, either as
     a halo'd tensor `dpad` (gradient of the next conv's operand) and/or a dense `dadd`.
     Returns the gradient w.r.t. the conv's own haloed operand (NHWC fp32 [n, hp, wp, ci]) or None."""
     n, ho, wo, co = raw.shape
+    if dpad is None and dadd is None:   # only a tapped-feature gradient on the raw output reaches this stage
+        dadd = torch.zeros_like(raw)
     g, sums = ops.act_norm_bwd_reduce(raw.shape, dpad, pad, pad_mode, dadd, raw, mr, norm_mode, gamma, beta, act)
     tc = layer.use_tc
     q = 0 if (not tc or not need_dgrad) else (layer.k - 1 if layer.stride == 1 else layer.k // 2 - 1)
     d_op = ops.norm_bwd_apply(g, raw, mr, norm_mode, gamma, sums, count, dgamma, dbeta, pad=q,
-                              fmt=FMT_BF16X2 if tc else FMT_F32)
+                              fmt=FMT_BF16X2 if tc else FMT_F32, extra=draw_add)
     if need_wgrad:
         # A conv bias that feeds a norm layer has an identically zero gradient (the norm removes any constant
         # per-channel shift; d_raw sums to zero over the normalised axes) — the reference only accumulates
         # rounding noise there — so its reduction is skipped and the zeroed flat-grad entry stands.
-        want_db = layer.bias is not None and norm_mode == NORM_NONE
+        want_db = layer.bias is not None and (norm_mode == NORM_NONE or draw_add is not None)   # a raw-output tap sees the bias
         _wgrad_async(lambda: ops.conv2d_wgrad(x_op, 0, d_op, q, layer.k, layer.stride, ho, wo, layer.weight.grad,
                                               layer.bias.grad if want_db else None), (x_op, d_op))
     if not need_dgrad:
@@ -393,6 +395,136 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         _stage_bwd(self._c1, ctx["op0"], ctx["raw1"], ctx["mr1"], IN, ACT_RELU, S_h * S_w, dpad=dpad1, pad=1,
                    pad_mode=PAD_ZERO, need_dgrad=False)
         _wgrad_join()
+
+    # -- encoder-only pass with saved activations (the PatchNCE query branch): features at `layers` (nn.Sequential
+    #    indices from tappable_layers()), computed up to the deepest one only.
+    def encode(self, srcs, layers):
+        _require_cuda(srcs[0], "ResnetGenerator")
+        IN = NORM_INSTANCE
+        layers = sorted(set(int(i) for i in layers))
+        bad = [i for i in layers if i not in self.tappable_layers()]
+        if bad:
+            raise NotImplementedError("feature taps %s are not exposed by the fused path (available: %s)" % (bad, sorted(self.tappable_layers())))
+        top = layers[-1]
+        n, _, S_h, S_w = srcs[0].shape
+        feats, ctx = {}, dict(dims=(n, S_h, S_w), top=top)
+        tc1 = self._c1.use_tc
+        op0 = ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT, fmt=FMT_BF16X2 if tc1 else FMT_F32, cpad=self._c1.ci_pad if tc1 else 0)
+        ctx["op0"] = op0
+        if 0 in layers:
+            feats[0] = ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT).data if tc1 else op0.data
+        if top == 0:
+            return feats, ctx
+        raw1, st = _conv_fwd(self._c1, op0, 0, S_h, S_w, IN)
+        mr1 = ops.stats_finalize(st, S_h * S_w)
+        ctx.update(raw1=raw1, mr1=mr1)
+        if 1 in layers:
+            feats[1] = raw1
+        if top == 1:
+            return feats, ctx
+        _, op1 = ops.norm_act_pad(raw1, mr1, IN, act=ACT_RELU, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c4))
+        raw4, st = _conv_fwd(self._c4, op1, 0, S_h, S_w, IN)
+        mr4 = ops.stats_finalize(st, S_h * S_w)
+        ctx.update(op1=op1, raw4=raw4, mr4=mr4)
+        if 4 in layers:
+            feats[4] = raw4
+        if top == 4:
+            return feats, ctx
+        a4, _ = ops.norm_act_pad(raw4, mr4, IN, act=ACT_RELU, want_dense=True)
+        d4 = ops.blur_down_fwd(a4)
+        del a4
+        _, op4 = ops.norm_act_pad(d4, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c8))
+        h2, w2 = S_h // 2, S_w // 2
+        raw8, st = _conv_fwd(self._c8, op4, 0, h2, w2, IN)
+        mr8 = ops.stats_finalize(st, h2 * w2)
+        ctx.update(op4=op4, raw8=raw8, mr8=mr8)
+        if 8 in layers:
+            feats[8] = raw8
+        if top == 8:
+            return feats, ctx
+        a8, _ = ops.norm_act_pad(raw8, mr8, IN, act=ACT_RELU, want_dense=True)
+        t = ops.blur_down_fwd(a8)
+        del a8
+        h4, w4 = h2 // 2, w2 // 2
+        nblk = top - 12 + 1
+        fmt_b = self._fmt(self._blocks[0].conv_block[1])
+        _, op_t = ops.norm_act_pad(t, pad=1, pad_mode=PAD_REFLECT, fmt=fmt_b)
+        blocks = []
+        for b in range(nblk):
+            ca, cb = self._blocks[b].conv_block[1], self._blocks[b].conv_block[5]
+            rawA, st = _conv_fwd(ca, op_t, 0, h4, w4, IN)
+            mrA = ops.stats_finalize(st, h4 * w4)
+            _, opA = ops.norm_act_pad(rawA, mrA, IN, act=ACT_RELU, pad=1, pad_mode=PAD_REFLECT, fmt=self._fmt(cb))
+            rawB, st = _conv_fwd(cb, opA, 0, h4, w4, IN)
+            mrB = ops.stats_finalize(st, h4 * w4)
+            last = b == nblk - 1
+            t, op_next = ops.norm_act_pad(rawB, mrB, IN, residual=t, want_dense=True, pad=1, pad_mode=PAD_REFLECT,
+                                          fmt=None if last else fmt_b)
+            blocks.append((op_t, rawA, mrA, opA, rawB, mrB))
+            op_t = op_next
+            if 12 + b in layers:
+                feats[12 + b] = t
+        ctx["blocks"] = blocks
+        return feats, ctx
+
+    def encode_bwd(self, ctx, dfeats):
+        """dfeats: {layer: NHWC gradient of that tapped feature}.  Accumulates weight gradients and returns the gradient
+        w.r.t. the reflect-padded input operand, NHWC [n, S+6, S+6, input_nc] (or None if nothing reaches it)."""
+        IN = NORM_INSTANCE
+        n, S_h, S_w = ctx["dims"]
+        h2, w2, h4, w4 = S_h // 2, S_w // 2, S_h // 4, S_w // 4
+        top = ctx["top"]
+        dt = None
+        if top >= 12:
+            blocks = ctx["blocks"]
+            for b in range(len(blocks) - 1, -1, -1):
+                op_t, rawA, mrA, opA, rawB, mrB = blocks[b]
+                ca, cb = self._blocks[b].conv_block[1], self._blocks[b].conv_block[5]
+                tap = dfeats.get(12 + b)
+                if dt is None:
+                    dt = tap
+                elif tap is not None:
+                    dt, _ = ops.act_norm_bwd_reduce_ex(dt.shape, dadd=dt, dadd2=tap)
+                if dt is None:
+                    continue
+                dpadA = _stage_bwd(cb, opA, rawB, mrB, IN, ACT_NONE, h4 * w4, dadd=dt)
+                dpad_t = _stage_bwd(ca, op_t, rawA, mrA, IN, ACT_RELU, h4 * w4, dpad=dpadA, pad=1, pad_mode=PAD_REFLECT)
+                dt, _ = ops.act_norm_bwd_reduce(dt.shape, dpad=dpad_t, pad=1, pad_mode=PAD_REFLECT, dadd=dt)
+        dpad1 = None
+        if top >= 8:
+            da8 = ops.blur_down_bwd(dt, h2, w2) if dt is not None else None
+            if da8 is not None or dfeats.get(8) is not None:
+                dpad4 = _stage_bwd(self._c8, ctx["op4"], ctx["raw8"], ctx["mr8"], IN, ACT_RELU, h2 * w2, dadd=da8, draw_add=dfeats.get(8))
+                dd4, _ = ops.act_norm_bwd_reduce((n, h2, w2, dpad4.shape[3]), dpad=dpad4, pad=1, pad_mode=PAD_ZERO)
+            else:
+                dd4 = None
+        else:
+            dd4 = None
+        if top >= 4:
+            da4 = ops.blur_down_bwd(dd4, S_h, S_w) if dd4 is not None else None
+            if da4 is not None or dfeats.get(4) is not None:
+                dpad1 = _stage_bwd(self._c4, ctx["op1"], ctx["raw4"], ctx["mr4"], IN, ACT_RELU, S_h * S_w, dadd=da4, draw_add=dfeats.get(4))
+        dpad0 = None
+        if top >= 1 and (dpad1 is not None or dfeats.get(1) is not None):
+            dpad0 = _stage_bwd(self._c1, ctx["op0"], ctx["raw1"], ctx["mr1"], IN, ACT_RELU, S_h * S_w, dpad=dpad1, pad=1,
+                               pad_mode=PAD_ZERO, need_dgrad=True, draw_add=dfeats.get(1))
+        _wgrad_join()
+        if dfeats.get(0) is not None:
+            if dpad0 is None:
+                dpad0 = dfeats[0]
+            else:
+                dpad0, _ = ops.act_norm_bwd_reduce_ex(dpad0.shape, dadd=dpad0, dadd2=dfeats[0])
+        return dpad0
+
+    def feature_hw(self, layer, S_h, S_w):
+        """Spatial size of a tapped feature (for drawing PatchSampleF ids on the host before the step)."""
+        if layer == 0:
+            return S_h + 6, S_w + 6
+        if layer in (1, 4):
+            return S_h, S_w
+        if layer == 8:
+            return S_h // 2, S_w // 2
+        return S_h // 4, S_w // 4
 
     # -- reference module API (networks.py:1131-1154): returns tanh output [n, 5, h, w]
     def forward(self, input, layers=[], encode_only=False, style_code=None):

@@ -187,12 +187,24 @@ def g_head_bwd_split(raw, mask, dI, dT, pad):
 
 
 def norm_bwd_apply(g, raw=None, mr=None, norm_mode=NORM_NONE, gamma=None, sums=None, count=0.0, dgamma=None, dbeta=None,
-                   pad=0, fmt=FMT_F32):
+                   pad=0, fmt=FMT_F32, extra=None):
     n, h, w, c = g.shape
     op = Operand(n, h, w, c, pad, fmt, g.device)
-    L.call("skit_norm_bwd_apply", _p(g), _p(raw), n, h, w, c, _p(mr), norm_mode, _p(gamma), _p(sums), float(count),
-           _p(dgamma), _p(dbeta), op.ref(), pad, L.stream())
+    L.call("skit_norm_bwd_apply_ex", _p(g), _p(raw), n, h, w, c, _p(mr), norm_mode, _p(gamma), _p(sums), float(count),
+           _p(dgamma), _p(dbeta), _p(extra), op.ref(), pad, L.stream())
     return op
+
+
+def channel_mean(x):
+    n, c, h, w = x.shape
+    y = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
+    L.call("skit_channel_mean", _p(x), n, c, h, w, _p(y), L.stream())
+    return y
+
+
+def channel_mean_bwd(dy, dx):
+    n, c, h, w = dx.shape
+    L.call("skit_channel_mean_bwd", _p(dy), n, c, h, w, _p(dx), L.stream())
 
 
 def _resample(name, x, out_hw):

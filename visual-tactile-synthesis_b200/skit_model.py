@@ -40,6 +40,9 @@ def default_options(**kw):
         lr=1e-3, lr_G2=5e-4, beta1=0.0, beta2=0.99, lr_policy="linear", n_epochs=5, n_epochs_decay=400, epoch_count=1,
         run_full_res_D2=False,  # the reference's visualisation-only netD2(full image) pass (:1495); off on the hot path
         checkpoints_dir="./checkpoints", name="experiment",
+        # PatchNCE (models/patchnce.py + PatchSampleF; dead code in the reference, wired CUT-style here: DESIGN.md section 4.3)
+        lambda_NCE=0.0, nce_layers="0,4,8,12,16", num_patches=256, nce_T=0.07, netF="sample", netF_nc=256,
+        nce_includes_all_negatives_from_minibatch=False,
         cuda_graph=True,         # replay the whole train step as one CUDA graph once shapes are stable
         cuda_graph_warmup=2,     # eager steps before capture (lazy weight packs, kernel attributes, NCCL warm-up)
     )
@@ -85,6 +88,16 @@ class SinSKITGModel:
                 net.flatten_parameters()
             self.step_count = 0
             self.lr_factor = 1.0
+            self.nce_layers = [int(i) for i in str(opt.nce_layers).split(",")] if getattr(opt, "lambda_NCE", 0.0) > 0 else []
+            if self.nce_layers:
+                if not isinstance(self.netG, networks.ResnetGenerator):
+                    raise NotImplementedError("PatchNCE needs a generator with feature taps (forward(layers=..., encode_only=True)): the resnet family "
+                                              "(the reference's U-Net generators do not support it either, networks.py:1538)")
+                if opt.netF != "sample":
+                    raise NotImplementedError("train-step PatchNCE wiring is built for netF='sample' (PatchSampleF without MLP)")
+                bad = [i for i in self.nce_layers if i not in self.netG.tappable_layers()]
+                if bad:
+                    raise NotImplementedError("nce_layers %s are not exposed by the fused generator (available: %s)" % (bad, sorted(self.netG.tappable_layers())))
             self.loss_buf = torch.zeros(16, dtype=torch.float32, device=self.device)
         self._spe_cache = {}
         self._losses = {}
@@ -202,6 +215,25 @@ class SinSKITGModel:
                 hhy[j, 0] = lr * self.lr_factor / bc1
                 hhy[j, 1] = 1.0 / math.sqrt(bc2)
         self._blob_dev.copy_(h, non_blocking=True)
+        if self.isTrain and getattr(self, "nce_layers", None):
+            # PatchSampleF ids (networks.py:703-705: np.random.permutation(H*W)[:num_patches], shared over the batch)
+            S_h, S_w = self.real_S.shape[2:]
+            P = opt.num_patches
+            if getattr(self, "_ids_dev", None) is None or self._ids_dev.shape != (len(self.nce_layers), P):
+                self._ids_host = [torch.zeros(len(self.nce_layers), P, dtype=torch.int32).pin_memory() for _ in range(self._RING)]
+                self._ids_dev = torch.zeros(len(self.nce_layers), P, dtype=torch.int32, device=self.device)
+                self._input_gen += 1
+            hi = self._ids_host[i]
+            self._ids_count = []
+            for li, l in enumerate(self.nce_layers):
+                fh, fw = self.netG.feature_hw(l, S_h, S_w)
+                if rand is not None and "nce_ids" in rand:
+                    ids = np.asarray(rand["nce_ids"][li], dtype=np.int64)
+                else:
+                    ids = np.random.permutation(fh * fw)[:int(min(P, fh * fw))]
+                self._ids_count.append(len(ids))
+                hi[li, :len(ids)].copy_(torch.from_numpy(ids.astype(np.int32)))
+            self._ids_dev.copy_(hi, non_blocking=True)
         evt = torch.cuda.Event()
         evt.record()
         self._blob_evt[i] = evt
@@ -212,8 +244,9 @@ class SinSKITGModel:
         opt = self.opt
         save = self.isTrain if save is None else save
         srcs = [self.real_S] + ([self.S_pe] if self.S_pe is not None else [])
-        (self.fake_I, self.fake_T, self.fake_N), self._g_ctx, _ = self.netG.fwd(
-            srcs, mask=self.M if opt.use_bg_mask else None, scale_nz=opt.scale_nz, save=save,
+        taps = set(self.nce_layers) if (save and getattr(self, "nce_layers", None)) else None
+        (self.fake_I, self.fake_T, self.fake_N), self._g_ctx, self._g_feats = self.netG.fwd(
+            srcs, mask=self.M if opt.use_bg_mask else None, scale_nz=opt.scale_nz, save=save, taps=taps,
             style_code=self.style_code if getattr(opt, "use_style_code", False) else None)
         if hasattr(self, "real_I"):
             if opt.use_diffaug:
@@ -394,6 +427,8 @@ class SinSKITGModel:
         ops.l1_loss(fake_T_p, self.real_T, opt.lambda_G2_L1 / per_patch / n, sl["G2_L1"], dTp, opt.lambda_G2_L1 / per_patch / n)
         dT = torch.zeros_like(fake_T)
         ops.patch_scatter_add(dTp, 0, 2, ox, oy, dT)
+        if self.nce_layers:
+            self._nce_step(dI, n)
         G.bwd(self._g_ctx, dI, dT)
         self._g_ctx = None
         self._join(4)
@@ -402,13 +437,45 @@ class SinSKITGModel:
         self._loss_raw = (L, NT, NF)
         return L
 
+    def _nce_step(self, dI, n):
+        """CUT-style PatchNCE term (new wiring: PatchNCELoss / PatchSampleF are dead code in the reference).
+        keys  = generator features of the input (sketch + positional encoding) at nce_layers — tapped from the main forward;
+        query = the same encoder run on the 1-channel mean of the generated RGB image (+ the same positional encoding);
+        loss  = lambda_NCE * mean_layers mean_patches PatchNCE(q, k);  its gradient flows into the encoder weights (query
+        pass) and, through the channel mean, into fake_I."""
+        opt, G = self.opt, self.netG
+        S_h, S_w = self.real_S.shape[2:]
+        Sq = ops.channel_mean(self.fake_I)
+        fq, cq = G.encode([Sq] + ([self.S_pe] if self.S_pe is not None else []), self.nce_layers)
+        nl = len(self.nce_layers)
+        dfeats, chunks = {}, []
+        for li, l in enumerate(self.nce_layers):
+            ids = self._ids_dev[li][:self._ids_count[li]]
+            k_pool, _ = ops.patch_sample_l2norm(self._g_feats[l], ids)
+            q_pool, pre = ops.patch_sample_l2norm(fq[l], ids, keep_pre=True)
+            rows = q_pool.shape[0]
+            b = 1 if opt.nce_includes_all_negatives_from_minibatch else n
+            loss_l, dq = ops.patchnce(q_pool, k_pool, b, opt.nce_T, want_grad=True, gscale=opt.lambda_NCE / (nl * rows))
+            dfeats[l] = ops.patch_sample_l2norm_bwd(dq, pre, ids, tuple(fq[l].shape))
+            chunks.append(loss_l)
+        dpad0 = G.encode_bwd(cq, dfeats)
+        if dpad0 is not None:
+            dSq = ops.operand_grad_to_nchw(dpad0, S_h, S_w, 3, ops.PAD_REFLECT, 0, 1)
+            ops.channel_mean_bwd(dSq, dI)
+        self._nce_losses = chunks
+        self._g_feats = None
+
     def get_current_losses(self):
         """Device -> host read of the step's loss scalars (the reference does ~12 .item() syncs per step,
         sinskitG_model.py:1389-1838; here it is one D2H copy, only when somebody asks)."""
         L, NT, NF = self._loss_raw
         v = L.detach().cpu().numpy()
         o = self.opt
-        return dict(
+        extra = {}
+        if getattr(self, "nce_layers", None) and getattr(self, "_nce_losses", None):
+            per_layer = torch.stack([c.mean() for c in self._nce_losses]).cpu().numpy()
+            extra["NCE"] = float(per_layer.mean()) * o.lambda_NCE
+        return dict(extra,
             D_fake_I=float(v[0]) * o.lambda_G1_GAN, D_real_I=float(v[1]) * o.lambda_G1_GAN,
             G_GAN=float(v[2]) * o.lambda_G1_GAN, G_L1=float(v[3]), G2_L1=float(v[4]),
             D_fake_T_concat=float(v[8:8 + NT].mean()) * o.lambda_G2_GAN,
