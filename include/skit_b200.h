@@ -233,6 +233,10 @@ int skit_g_head_bwd(const float* raw, const float* mask, const float* dI, const 
 int skit_g_head_bwd_split(const float* raw, const float* mask, const float* dI, const float* dT,
                           int n, int h, int w, const skit_operand* opI, const skit_operand* opT, int pad, void* stream);
 
+/* x[n][c][h][w] *= m[n][0][h][w] in place: the `S *= M`, `I *= M`, `T *= I_masks` of set_input
+ * (sinskitG_model.py:724,734,789-790) on the device, after the pinned H2D copy of the raw tensors. */
+int skit_mask_mul(float* x, const float* m, int n, int c, int h, int w, void* stream);
+
 /* y[n][0][h][w] = mean_c x[n][c][h][w] and its adjoint dx[n][c][h][w] += dy[n][0][h][w] / c  (NCHW planes): the
  * 1-channel view of the generated image that the PatchNCE query branch re-encodes (PatchNCE wiring). */
 int skit_channel_mean(const float* x, int n, int c, int h, int w, float* y, void* stream);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "skit_g_head_bwd_split": [_P, _P, _P, _P, _I, _I, _I, _OP, _OP, _I, _P],
     "skit_act_norm_bwd_reduce": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P],
     "skit_norm_bwd_apply_ex": [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _D, _P, _P, _P, _OP, _I, _P],
+    "skit_mask_mul": [_P, _P, _I, _I, _I, _I, _P],
     "skit_channel_mean": [_P, _I, _I, _I, _I, _P, _P],
     "skit_channel_mean_bwd": [_P, _I, _I, _I, _I, _P, _P],
     "skit_norm_bwd_apply": [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _D, _P, _P, _OP, _I, _P],

@@ -174,6 +174,16 @@ __global__ void __launch_bounds__(256) g_head_bwd_split_kernel(const float* __re
     }
 }
 
+// x[n][c][hw] *= m[n][0][hw]  (set_input's background / contact masking, sinskitG_model.py:724,734,789-790, done on the
+// device after the H2D copy of the raw tensors instead of on the host before it)
+__global__ void __launch_bounds__(256) mask_mul_kernel(float* __restrict__ x, const float* __restrict__ m, int n, int c, long long hw) {
+    const long long total = (long long)n * c * hw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i % hw, b = i / (hw * c);
+        x[i] *= m[b * hw + pix];
+    }
+}
+
 // Channel mean of an NCHW image and its adjoint (the 1-channel "sketch-like" view of the generated RGB image that the
 // PatchNCE query branch feeds back through the generator's encoder).
 __global__ void __launch_bounds__(256) channel_mean_kernel(const float* __restrict__ x, int n, int c, long long hw, float* __restrict__ y) {
@@ -526,6 +536,12 @@ extern "C" int skit_g_head_bwd_split(const float* raw, const float* mask, const 
     g_head_bwd_split_kernel<<<grid_for((long long)n * opI->hp * opI->wp, 256), 256, 0, as_stream(stream)>>>(
         raw, mask, dI, dT, n, h, w, (float*)opI->p0, (float*)opT->p0, pad);
     return check_launch("g_head_bwd_split_kernel");
+}
+
+extern "C" int skit_mask_mul(float* x, const float* m, int n, int c, int h, int w, void* stream) {
+    SKIT_REQUIRE(x && m && n > 0 && c > 0 && h > 0 && w > 0, "mask_mul: bad arguments");
+    mask_mul_kernel<<<grid_for((long long)n * c * h * w, 256), 256, 0, as_stream(stream)>>>(x, m, n, c, (long long)h * w);
+    return check_launch("mask_mul_kernel");
 }
 
 extern "C" int skit_channel_mean(const float* x, int n, int c, int h, int w, float* y, void* stream) {

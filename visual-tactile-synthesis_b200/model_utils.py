@@ -27,32 +27,62 @@ def find_coords_for_patch(coords, scale_multiplier=1):
 
 
 class _OffsetTable:
-    """Candidate (row, col) offsets of the random-patch mode (model_utils.py:212-222)."""
+    """Candidate (row, col) offsets of the random-patch mode (model_utils.py:212-222): the nonzero positions, in
+    row-major order, of the dilated mask `box` ([oh, ow] bool; None = every position).  Only the sampled entries are ever
+    materialised: the k-th candidate is found through the per-row cumulative counts."""
 
-    def __init__(self, rows, cols):
-        self.rows, self.cols = rows, cols
+    def __init__(self, box, oh, ow):
+        self.box, self.oh, self.ow = box, oh, ow
+        if box is None:
+            self.n = oh * ow
+        else:
+            self.rowcum = np.cumsum(box.sum(axis=1, dtype=np.int64))
+            self.n = int(self.rowcum[-1]) if oh > 0 else 0
 
     def __len__(self):
-        return int(self.rows.shape[0])
+        return self.n
+
+    def at(self, picks):
+        picks = np.asarray(picks, dtype=np.int64)
+        if self.box is None:
+            return np.divmod(picks, self.ow)
+        rows = np.searchsorted(self.rowcum, picks, side="right")
+        before = np.where(rows > 0, self.rowcum[np.maximum(rows - 1, 0)], 0)
+        cols = np.array([np.flatnonzero(self.box[r])[k] for r, k in zip(rows, picks - before)], dtype=np.int64)
+        return rows, cols
+
+    @property
+    def rows(self):
+        return self.at(np.arange(self.n))[0] if self.box is None else np.nonzero(self.box)[0]
+
+    @property
+    def cols(self):
+        return self.at(np.arange(self.n))[1] if self.box is None else np.nonzero(self.box)[1]
 
     def sample(self, k, rng=_pyrandom):
-        pick = rng.sample(range(len(self)), k)
-        return self.cols[pick].astype(np.int32), self.rows[pick].astype(np.int32)  # (offset_x, offset_y)
+        pick = rng.sample(range(len(self)), k)          # the reference's `random.sample(range(nnz), NF)` draw
+        rows, cols = self.at(pick)
+        return cols.astype(np.int32), rows.astype(np.int32)  # (offset_x, offset_y)
 
 
 def random_patch_offset_table(M):
     """`clamp(conv2d(M, ones(1,1,17,17), padding=1), 0, 1)` then torch.nonzero in row-major order
     (model_utils.py:212-218); the map is (H-14)x(W-14) and its (row, col) are used directly as
-    (offset_y, offset_x).  Computed on the host with an integral image (exact for 0/1 masks)."""
-    m = np.asarray(M[0, 0].cpu(), dtype=np.float64)
+    (offset_y, offset_x).  Host side: for a non-negative mask "box sum > 0" is a 17x17 dilation, done separably with
+    two integer running sums (exact for the 0/1 masks the datasets produce)."""
+    m = np.asarray(M[0, 0].cpu()) > 0
     H, W = m.shape
-    p = np.zeros((H + 3, W + 3), dtype=np.float64)   # 1 zero halo + leading row/col for the integral image
-    p[2:H + 2, 2:W + 2] = m
-    ii = p.cumsum(0).cumsum(1)
     oh, ow = H + 2 - 17 + 1, W + 2 - 17 + 1
-    box = ii[17:17 + oh, 17:17 + ow] - ii[0:oh, 17:17 + ow] - ii[17:17 + oh, 0:ow] + ii[0:oh, 0:ow]
-    rows, cols = np.nonzero(box > 0.5)
-    return _OffsetTable(rows, cols)
+    if m.all():
+        return _OffsetTable(None, oh, ow)
+    p = np.zeros((H + 2, W + 3), dtype=np.int32)          # 1 zero halo (+ a leading column for the running sum)
+    p[1:H + 1, 2:W + 2] = m
+    cx = p.cumsum(1, dtype=np.int32)
+    rowbox = (cx[:, 17:17 + ow] - cx[:, 0:ow]) > 0        # any mask pixel in the 17-wide window of each row
+    q = np.zeros((H + 3, ow), dtype=np.int32)
+    q[1:, :] = rowbox
+    cy = q.cumsum(0, dtype=np.int32)
+    return _OffsetTable((cy[17:17 + oh, :] - cy[0:oh, :]) > 0, oh, ow)
 
 
 def get_patch_in_input(input, coords=None, sample_size=None, scale_multiplier=1, patch_size=32,

@@ -195,6 +195,13 @@ def norm_bwd_apply(g, raw=None, mr=None, norm_mode=NORM_NONE, gamma=None, sums=N
     return op
 
 
+def mask_mul_(x, m):
+    """x[n,c,h,w] *= m[n,1,h,w] in place."""
+    n, c, h, w = x.shape
+    L.call("skit_mask_mul", _p(x), _p(m), n, c, h, w, L.stream())
+    return x
+
+
 def channel_mean(x):
     n, c, h, w = x.shape
     y = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)

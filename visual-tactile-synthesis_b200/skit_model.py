@@ -114,22 +114,21 @@ class SinSKITGModel:
         return self._spe_cache[key]
 
     def set_input(self, input, phase="train"):
-        """Host tensors (the dataset dict, sinskitG_model.py:702-793) -> device.  Masking of S / I / T
-        (:724,734,789-790) is done on the host before the single pinned H2D copy of each tensor."""
+        """Host tensors (the dataset dict, sinskitG_model.py:702-793) -> persistent device buffers: one pinned H2D copy
+        per tensor, then the masking of S / I / T (:724,734,789-790) as in-place device kernels."""
         dev = self.device
         M = input["M"].float()
-        S = input["S"].float() * M if self.opt.use_bg_mask else input["S"].float()
-        n, _, h, w = S.shape
-        host = {"M": M, "real_S": S}
+        n, _, h, w = input["S"].shape
+        host = {"M": M, "real_S": input["S"].float()}
         if "I" in input:
-            host["real_I"] = input["I"].float() * M if self.opt.use_bg_mask else input["I"].float()
+            host["real_I"] = input["I"].float()
         pre = "" if phase == "train" else "val_"
-        if self.isTrain and (pre + "T_images") in input:
+        has_T = self.isTrain and (pre + "T_images") in input
+        if has_T:
             T = input[pre + "T_images"].float()
             NT = T.shape[1]
-            Im = input[pre + "I_masks"].float().reshape(NT, 1, 32, 32)
-            host["I_masks"] = Im
-            host["real_T"] = T.reshape(NT, 2, 32, 32) * Im
+            host["I_masks"] = input[pre + "I_masks"].float().reshape(NT, 1, 32, 32)
+            host["real_T"] = T.reshape(NT, 2, 32, 32)
             ox, oy, _ = find_coords_for_patch(input[pre + "T_coords"].numpy() if torch.is_tensor(input[pre + "T_coords"]) else input[pre + "T_coords"])
             host["ox"] = torch.from_numpy(ox.astype(np.int32))
             host["oy"] = torch.from_numpy(oy.astype(np.int32))
@@ -141,6 +140,13 @@ class SinSKITGModel:
                 v = v.pin_memory()
             self.h2d_bytes += v.numel() * v.element_size()
             self._stage(k, v)
+        # background / contact masking on the device (the reference does it after its own .to(device): :724,734,789-790)
+        if self.opt.use_bg_mask:
+            ops.mask_mul_(self.real_S, self.M)
+            if "I" in input:
+                ops.mask_mul_(self.real_I, self.M)
+        if has_T:
+            ops.mask_mul_(self.real_T, self.I_masks)
         self.S_pe = self._spe(n, h, w) if self.opt.use_positional_encoding else None
         self.style_code = input.get("style_code")
         if self.isTrain and hasattr(self, "real_T"):
