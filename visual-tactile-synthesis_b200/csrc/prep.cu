@@ -109,8 +109,9 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(PrepP p) {
 // registers) and walks the row in steps of the block's pixel lanes — no integer divisions, no fp64, 4 independent
 // 16-byte loads in flight per thread.
 template <int FMT>
-__global__ void __launch_bounds__(256) norm_act_pad_rows_kernel(PrepP p, int cv, int rows_per_block) {
+__global__ void __launch_bounds__(256) norm_act_pad_rows_kernel(PrepP p, int cv, int rows_per_block, int xseg) {
     const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
+    const int xbeg = blockIdx.z * xseg, xend = min(wp, xbeg + xseg);   // blockIdx.z: segment of the row (small maps)
     const int n = blockIdx.y;
     const int cl = threadIdx.x % cv, pl = threadIdx.x / cv, PL = 256 / cv;
     const int ch = cl * 4;
@@ -128,13 +129,13 @@ __global__ void __launch_bounds__(256) norm_act_pad_rows_kernel(PrepP p, int cv,
         const int sy = pad_src(py, p.pad, p.h, p.pad_mode);
         const long long srow = ((long long)n * p.h + (sy < 0 ? 0 : sy)) * p.w;
         const long long drow = ((long long)n * hp + py) * wp;
-        for (int px0 = pl; px0 < wp; px0 += 4 * PL) {
+        for (int px0 = xbeg + pl; px0 < xend; px0 += 4 * PL) {
             float4 r[4], res[4];
             int sx[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int px = px0 + u * PL;
-                sx[u] = px < wp ? pad_src(px, p.pad, p.w, p.pad_mode) : -1;
+                sx[u] = px < xend ? pad_src(px, p.pad, p.w, p.pad_mode) : -1;
                 const bool ok = sy >= 0 && sx[u] >= 0;
                 r[u] = ok ? *reinterpret_cast<const float4*>(p.raw + (srow + sx[u]) * p.c + ch) : make_float4(0, 0, 0, 0);
                 if (p.residual) res[u] = ok ? *reinterpret_cast<const float4*>(p.residual + (srow + sx[u]) * p.c + ch) : make_float4(0, 0, 0, 0);
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) norm_act_pad_rows_kernel(PrepP p, int cv,
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int px = px0 + u * PL;
-                if (px >= wp) continue;
+                if (px >= xend) continue;
                 const bool ok = sy >= 0 && sx[u] >= 0;
                 float v[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
                 if (ok) {
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_kernel(BwdAP p) {
 
 // Row-tiled variant of phase A (see norm_act_pad_rows_kernel): float4 loads of every stream, the halo fold without
 // per-pixel divisions, per-thread register sums reduced across the block's pixel lanes, one fp64 atomic per channel per CTA.
-__global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, int cv, int rows_per_block) {
+__global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, int cv, int rows_per_block, int xseg) {
     __shared__ float red[256 * 8];
     const int n = blockIdx.y;
     const int cl = threadIdx.x % cv, pl = threadIdx.x / cv, PL = 256 / cv;
@@ -311,7 +312,8 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, 
         int ys[3];
         const int ny = p.dpad ? fold_coords(y, p.pad, p.h, p.pad_mode, ys) : 0;
         const long long srow = ((long long)n * p.h + y) * p.w;
-        for (int x = pl; x < p.w; x += PL) {
+        const int xend = min(p.w, (int)(blockIdx.z + 1) * xseg);
+        for (int x = blockIdx.z * xseg + pl; x < xend; x += PL) {
             const long long src = (srow + x) * p.c + ch;
             float4 d = make_float4(0, 0, 0, 0);
             if (p.dadd) {
@@ -436,8 +438,9 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(BwdBP p) {
 // Row-tiled variant (see norm_act_pad_rows_kernel): the per-channel terms of the norm backward (mean, rstd, gamma and
 // the two reduced sums, converted from double ONCE per thread) stay in registers.
 template <int FMT>
-__global__ void __launch_bounds__(256) norm_bwd_apply_rows_kernel(BwdBP p, int cv, int rows_per_block) {
+__global__ void __launch_bounds__(256) norm_bwd_apply_rows_kernel(BwdBP p, int cv, int rows_per_block, int xseg) {
     const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
+    const int xbeg = blockIdx.z * xseg, xend = min(wp, xbeg + xseg);
     const int n = blockIdx.y;
     const int cl = threadIdx.x % cv, pl = threadIdx.x / cv, PL = 256 / cv;
     const int ch = cl * 4;
@@ -457,19 +460,19 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_rows_kernel(BwdBP p, int c
         const bool yin = y >= 0 && y < p.h;
         const long long srow = ((long long)n * p.h + (yin ? y : 0)) * p.w;
         const long long drow = ((long long)n * hp + py) * wp;
-        for (int px0 = pl; px0 < wp; px0 += 4 * PL) {
+        for (int px0 = xbeg + pl; px0 < xend; px0 += 4 * PL) {
             float4 gg[4], rw[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int x = px0 + u * PL - p.pad;
-                const bool ok = yin && x >= 0 && x < p.w && px0 + u * PL < wp;
+                const bool ok = yin && x >= 0 && x < p.w && px0 + u * PL < xend;
                 gg[u] = ok ? *reinterpret_cast<const float4*>(p.g + (srow + x) * p.c + ch) : make_float4(0, 0, 0, 0);
                 if (p.mr) rw[u] = ok ? *reinterpret_cast<const float4*>(p.raw + (srow + x) * p.c + ch) : make_float4(0, 0, 0, 0);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int px = px0 + u * PL;
-                if (px >= wp) continue;
+                if (px >= xend) continue;
                 const int x = px - p.pad;
                 const bool ok = yin && x >= 0 && x < p.w;
                 float v[4] = {gg[u].x, gg[u].y, gg[u].z, gg[u].w};
@@ -647,6 +650,15 @@ static inline int rows_per_block_for(int rows, int n) {
     const int want_blocks = max(1, (kSMs * 6) / max(1, n));
     return max(1, cdiv(rows, want_blocks));
 }
+// when one row per block still leaves the grid short (small maps), split each row into segments (grid.z)
+static inline int xseg_for(int rows, int width, int n, int pixel_lanes) {
+    const int want_blocks = max(1, (kSMs * 6) / max(1, n));
+    const int rpb = rows_per_block_for(rows, n);
+    const int row_blocks = cdiv(rows, rpb);
+    int segs = max(1, want_blocks / row_blocks);
+    int seg = max(4 * pixel_lanes, cdiv(width, segs));   // at least one full unrolled pass per thread
+    return min(seg, width);
+}
 
 static int check_operand(const skit_operand* op, int n, int h, int w, int c, int pad, const char* who) {
     if (!op) return SKIT_OK;
@@ -700,11 +712,12 @@ extern "C" int skit_norm_act_pad_ex(const float* raw, int n, int h, int w, int c
     p.pad = pad; p.pad_mode = pad_mode; p.oc = oc; p.ooff = c_off;
     const long long pix = (long long)n * (h + 2 * pad) * (w + 2 * pad);
     if (rows_layout_ok(c) && (!op || (oc % 4 == 0 && c_off % 4 == 0))) {
-        const int hp = h + 2 * pad;
+        const int hp = h + 2 * pad, wp = w + 2 * pad;
         const int rpb = rows_per_block_for(hp, n);
-        dim3 grid(cdiv(hp, rpb), n);
-        if (!op || op->fmt == SKIT_FMT_F32) norm_act_pad_rows_kernel<SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb);
-        else norm_act_pad_rows_kernel<SKIT_FMT_BF16X2><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb);
+        const int xs = xseg_for(hp, wp, n, 256 / (c / 4));
+        dim3 grid(cdiv(hp, rpb), n, cdiv(wp, xs));
+        if (!op || op->fmt == SKIT_FMT_F32) norm_act_pad_rows_kernel<SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
+        else norm_act_pad_rows_kernel<SKIT_FMT_BF16X2><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
         return check_launch("norm_act_pad_rows_kernel");
     }
     if (c % 4 == 0 && oc % 4 == 0 && c_off % 4 == 0) norm_act_pad_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
@@ -744,8 +757,9 @@ extern "C" int skit_act_norm_bwd_reduce_ex(const float* dpad, int pad, int pad_m
     const int P = h * w;
     if (rows_layout_ok(c) && dadd_c0 % 4 == 0 && dadd_ctot % 4 == 0) {
         const int rpb = rows_per_block_for(h, n);
-        dim3 grid(cdiv(h, rpb), n);
-        act_norm_bwd_reduce_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb);
+        const int xs = xseg_for(h, w, n, 256 / (c / 4));
+        dim3 grid(cdiv(h, rpb), n, cdiv(w, xs));
+        act_norm_bwd_reduce_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
         return check_launch("act_norm_bwd_reduce_rows_kernel");
     }
     const int lanes_c = min(c / vec, 256), PL = 256 / lanes_c;
@@ -797,11 +811,12 @@ extern "C" int skit_norm_bwd_apply_ex(const float* g, const float* raw, int n, i
     p.pad = pad;
     const long long pix = (long long)n * (h + 2 * pad) * (w + 2 * pad);
     if (rows_layout_ok(c)) {
-        const int hp = h + 2 * pad;
+        const int hp = h + 2 * pad, wp = w + 2 * pad;
         const int rpb = rows_per_block_for(hp, n);
-        dim3 grid(cdiv(hp, rpb), n);
-        if (op->fmt == SKIT_FMT_F32) norm_bwd_apply_rows_kernel<SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb);
-        else norm_bwd_apply_rows_kernel<SKIT_FMT_BF16X2><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb);
+        const int xs = xseg_for(hp, wp, n, 256 / (c / 4));
+        dim3 grid(cdiv(hp, rpb), n, cdiv(wp, xs));
+        if (op->fmt == SKIT_FMT_F32) norm_bwd_apply_rows_kernel<SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
+        else norm_bwd_apply_rows_kernel<SKIT_FMT_BF16X2><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
     } else if (c % 4 == 0) norm_bwd_apply_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
     else norm_bwd_apply_kernel<1><<<grid_for(pix * c, 256), 256, 0, as_stream(stream)>>>(p);
     rc = check_launch("norm_bwd_apply_kernel");

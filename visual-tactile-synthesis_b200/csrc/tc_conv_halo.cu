@@ -41,10 +41,11 @@ struct TcHaloP {
     int a_rows;        // halo tile rows*cols
     int a_plane;       // bytes reserved per A plane (a_rows*128 rounded up to 1024)
     int nw;            // weight stages
+    int na;            // activation stages (2, or 1 when a large halo tile must leave room for wide weight stages)
     long long* dbg;    // optional per-CTA clock64 stamps [cta][8] (skit_debug_set_buffer), NULL in production
 };
 
-constexpr int NA = 2;  // activation stages
+constexpr int NA_MAX = 2;  // activation stages
 
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -67,6 +68,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
     const int a_stage = 2 * p.a_plane;
+    const int NA = p.na;
     const uint32_t w0 = smem0 + NA * a_stage;
     const uint32_t bar0 = w0 + p.nw * W_STAGE;
     auto a_full = [&](int s) { return bar0 + 8u * s; };
@@ -291,7 +293,9 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
                        TcHaloP& p, dim3 grid, cudaStream_t st) {
     constexpr int W_STAGE = 2 * BN * 128;
     constexpr int MAX_SMEM = 227 * 1024;
-    const int fixed = NA * 2 * p.a_plane + 1024 + 512;
+    // two activation stages unless a large halo tile would squeeze the weight ring below two stages (k4 with BN = 256)
+    p.na = (MAX_SMEM - (NA_MAX * 2 * p.a_plane + 1024 + 512)) / W_STAGE >= 2 ? NA_MAX : 1;
+    const int fixed = p.na * 2 * p.a_plane + 1024 + 512;
     int nw = (MAX_SMEM - fixed) / W_STAGE;
     if (nw > 8) nw = 8;
     if (nw < 2) {
@@ -341,10 +345,10 @@ int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_l
     if (co > 16) {
         const long long tiles = (long long)p.tiles_x * tiles_y * x->n;
         double best = 1e30;
-        const int avail = 227 * 1024 - (NA * 2 * p.a_plane + 1024 + 512);
+        const int avail1 = 227 * 1024 - (2 * p.a_plane + 1024 + 512);   // with a single activation stage
         for (int cand = 256; cand >= 64; cand >>= 1) {
             if (cand > 64 && co % cand) continue;
-            if (cand > 64 && avail / (cand * 256) < 2) continue;   // needs two weight stages next to the halo tiles
+            if (cand > 64 && avail1 / (cand * 256) < 2) continue;   // needs two weight stages next to the halo tile
             const int ntile = cdiv(co, cand);
             // cycles per 64-channel tap step: the MMAs (128 x cand x 16 at ~cand/2 cycles), or the shared-memory reads that
             // feed them (A 4 KB + B cand*32 B per MMA at ~110 B/cycle) — narrow tiles re-read A and become smem bound
