@@ -289,6 +289,9 @@ int skit_patch_sample_l2norm(const float* feat, int b, int hw, int c, const int*
 /* Backward of the normalisation + gather: dfeat[b][ids[i]][c] += d(pre) */
 int skit_patch_sample_l2norm_bwd(const float* dout, const float* pre, int b, int hw, int c,
                                  const int* ids, int np, float* dfeat, void* stream);
+/* Adjoint of the plain row gather (PatchSampleF with an MLP, networks.py:706-712: the MLP sits between the gather and
+ * the normalisation): dfeat[b][ids[i]][c] += drows[b*np + i][c]. */
+int skit_rows_scatter_add(const float* drows, int b, int hw, int c, const int* ids, int np, float* dfeat, void* stream);
 /* PatchNCELoss.forward (patchnce.py:13-55): q,k [b*np][dim]; loss[b*np]; optional dq (gradient of
  * sum_i loss[i]*gscale w.r.t. q; k is detached in the reference). */
 int skit_patchnce(const float* q, const float* k, int b, int np, int dim, float inv_T,

@@ -418,7 +418,7 @@ def model_forward(cfg, sdG, real_S, S_pe, M, real_I=None, rand=None):
     return res
 
 
-def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.0, grad_hook=None):
+def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.0, grad_hook=None, sdF=None):
     """SinSKITGModel.optimize_parameters (models/sinskitG_model.py:601-700) with
     compute_D1_loss (:1346-1407), compute_D2_loss (:1409-1617), compute_G1_loss (:1660-1726),
     compute_G2_loss (:1728-1842); LPIPS / vision-aided terms off (SURVEY.md §8c flags).
@@ -451,9 +451,10 @@ def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.
     afake_p = torch.cat([gather_patches(fw["aug_fake_I"], ox, oy, cs).detach(), I_masks], 1)
     losses = {}
 
-    def run_opt(name, sd, lr, loss):
+    def run_opt(name, sd, lr, loss, grads=None):
         params = {k: v for k, v in sd.items() if v.requires_grad}
-        grads = torch.autograd.grad(loss, list(params.values()), allow_unused=True, retain_graph=(name == "G_never"))
+        if grads is None:
+            grads = torch.autograd.grad(loss, list(params.values()), allow_unused=True)
         gd = {k: g for k, g in zip(params.keys(), grads) if g is not None}
         if grad_hook is not None:
             grad_hook(name, gd)
@@ -526,19 +527,31 @@ def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.
             feat_k = resnet_g_forward(sdG_run, torch.cat([real_S, S_pe], 1), cfg.n_blocks, layers=layers, encode_only=True)
         S_q = fake_I.mean(1, keepdim=True)
         feat_q = resnet_g_forward(sdG_run, torch.cat([S_q, S_pe], 1), cfg.n_blocks, layers=layers, encode_only=True)
-        kp = patch_sample_f(feat_k, rand["nce_ids"])
-        qp = patch_sample_f(feat_q, rand["nce_ids"])
+        mlps = None
+        if sdF is not None:   # netF = 'mlp_sample': per-layer Linear-ReLU-Linear (networks.py:678-686), trained by its own Adam
+            for v in sdF.values():
+                v.requires_grad_(True)
+            mlps = [(sdF["mlp_%d.0.weight" % i], sdF["mlp_%d.0.bias" % i], sdF["mlp_%d.2.weight" % i], sdF["mlp_%d.2.bias" % i])
+                    for i in range(len(layers))]
+        kp = patch_sample_f(feat_k, rand["nce_ids"], mlps)
+        qp = patch_sample_f(feat_q, rand["nce_ids"], mlps)
         l_nce = sum(patchnce_loss(q, k, cfg.nce_T, batch_size=real_S.shape[0]).mean() for q, k in zip(qp, kp)) / len(layers) * cfg.lambda_NCE
         losses["NCE"] = l_nce.item()
         loss_G = loss_G + l_nce
     for k in gp:
         sdG[k] = gp[k]
+    grads_F = None
+    use_F = cfg.lambda_NCE > 0 and sdF is not None
+    if use_F:   # both gradient sets come from the same graph: take F's first, apply its Adam after G's
+        f_raw = torch.autograd.grad(loss_G, [v for v in sdF.values() if v.requires_grad], allow_unused=True, retain_graph=True)
     grads_G = run_opt("G", sdG, cfg.lr, loss_G)
+    if use_F:
+        grads_F = run_opt("F", sdF, cfg.lr, None, grads=f_raw)
 
     return dict(losses=losses, fake_I=fake_I.detach(), fake_T=fake_T.detach(), fake_N=fw["fake_N"],
                 aug_fake_I=fw["aug_fake_I"].detach(), aug_real_I=fw["aug_real_I"].detach(),
                 fake_T_patches=fake_T_p.detach(), pred_fake_T_full=pred_full,
-                grads_G=grads_G, grads_D=grads_D, grads_D2=grads_D2)
+                grads_G=grads_G, grads_D=grads_D, grads_D2=grads_D2, grads_F=grads_F)
 
 
 # --------------------------------------------------------------------------- synthetic data

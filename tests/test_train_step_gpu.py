@@ -216,3 +216,43 @@ def test_train_step_with_patchnce_vs_oracle():
     res0 = O.train_step(cfg0, sdG0, sdD0, sdD20, {}, O.step_inputs_from_batch(batch), rand, step=1)
     k = "model.12.conv_block.1.weight"
     assert rel(res["grads_G"][k], res0["grads_G"][k]) > 1e-3
+
+
+def test_train_step_with_patchnce_mlp_vs_oracle():
+    """netF = 'mlp_sample' (CUT's default projection head): the per-layer MLP's forward, its weight gradients, the
+    gradient it passes back to the generator, and its own Adam update."""
+    import vts_b200
+    from oracle import skit_oracle as O
+    S, NT, NF, P = 64, 8, 4, 64
+    torch.manual_seed(1)
+    opt = vts_b200.default_options(batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_NCE=1.0, num_patches=P, netF="mlp_sample",
+                                   netF_nc=64, nce_layers="0,4,12")
+    m = vts_b200.SinSKITGModel(opt)
+    chans = [9, 128, 256]
+    m.netF.create_mlp(channels=chans, device=m.device)
+    m.netF.flatten_parameters()
+    with torch.no_grad():
+        m.netF.flat_param.mul_(20.0)       # gain-0.02 init gives a nearly flat projection; scale up for a conditioned test
+    sds = [{k: v.detach().cpu().clone() for k, v in net.state_dict().items()} for net in (m.netG, m.netD, m.netD2, m.netF)]
+    batch = O.synthetic_batch(S, NT=NT, seed=0, ellipse_mask=True)
+    rs = np.random.RandomState(5)
+    sizes = [m.netG.feature_hw(l, S, S) for l in m.nce_layers]
+    rand = dict(real_b=[0.3], real_s=[0.8], fake_b=[0.6], fake_s=[0.2],
+                fake_ox=np.array([3, 10, 20, 7], dtype=np.int32), fake_oy=np.array([5, 1, 12, 30], dtype=np.int32),
+                nce_ids=[rs.permutation(h * w)[:min(P, h * w)] for h, w in sizes])
+    m.set_input(batch)
+    m.optimize_parameters(1, rand=rand)
+    torch.cuda.synchronize()
+    cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_NCE=1.0, num_patches=P, nce_layers=(0, 4, 12))
+    sdG, sdD, sdD2, sdF = [copy.deepcopy(s) for s in sds]
+    res = O.train_step(cfg, sdG, sdD, sdD2, {}, O.step_inputs_from_batch(batch), rand, step=1, sdF=sdF)
+    losses = m.get_current_losses()
+    for k, v in res["losses"].items():
+        assert abs(losses[k] - v) <= GATE * max(1.0, abs(v)), (k, losses[k], v)
+    print("G worst grad rel err", check_grads(m.netG, {k: v.numpy() for k, v in res["grads_G"].items()}, "G"))
+    print("F worst grad rel err", check_grads(m.netF, {k: v.numpy() for k, v in res["grads_F"].items()}, "F"))
+    for k, v in m.netF.state_dict().items():   # Adam moved the MLP weights like the oracle's
+        g = res["grads_F"][k].reshape(-1)
+        ok = g.abs() > max(1e-7, 0.05 * float(g.pow(2).mean().sqrt()))
+        bad = ((v.detach().cpu().reshape(-1) - sdF[k].detach().reshape(-1)).abs() > 2e-4)[ok]
+        assert bad.float().mean().item() < 0.02, k

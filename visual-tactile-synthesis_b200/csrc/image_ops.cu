@@ -406,6 +406,17 @@ __global__ void __launch_bounds__(256) patch_sample_l2norm_kernel(const float* _
     }
 }
 
+// dfeat[b][ids[i]][c] += drows[b*np + i][c]   (adjoint of the plain row gather of PatchSampleF, networks.py:706)
+__global__ void __launch_bounds__(256) rows_scatter_add_kernel(const float* __restrict__ drows, int b, int hw, int c, const int* ids, int np, float* dfeat) {
+    const long long total = (long long)b * np * c;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c);
+        const long long row = i / c;
+        const int bi = (int)(row / np), pi = (int)(row - (long long)bi * np);
+        atomicAdd(dfeat + ((long long)bi * hw + ids[pi]) * c + ch, drows[i]);
+    }
+}
+
 // y = x/(|x|+e): dx = dy/(|x|+e) - x * (x.dy) / (|x| (|x|+e)^2)
 __global__ void __launch_bounds__(256) patch_sample_l2norm_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ pre, int b, int hw, int c,
                                                                       const int* ids, int np, float* dfeat) {
@@ -637,6 +648,12 @@ extern "C" int skit_patch_sample_l2norm_bwd(const float* dout, const float* pre,
     SKIT_REQUIRE(dout && pre && ids && dfeat && b > 0 && hw > 0 && c > 0 && np > 0, "patch_sample_l2norm_bwd: bad arguments");
     patch_sample_l2norm_bwd_kernel<<<cdiv(b * np, 8), 256, 0, as_stream(stream)>>>(dout, pre, b, hw, c, ids, np, dfeat);
     return check_launch("patch_sample_l2norm_bwd_kernel");
+}
+
+extern "C" int skit_rows_scatter_add(const float* drows, int b, int hw, int c, const int* ids, int np, float* dfeat, void* stream) {
+    SKIT_REQUIRE(drows && ids && dfeat && b > 0 && hw > 0 && c > 0 && np > 0, "rows_scatter_add: bad arguments");
+    rows_scatter_add_kernel<<<grid_for((long long)b * np * c, 256), 256, 0, as_stream(stream)>>>(drows, b, hw, c, ids, np, dfeat);
+    return check_launch("rows_scatter_add_kernel");
 }
 
 extern "C" int skit_patchnce(const float* q, const float* k, int b, int np, int dim, float inv_T,

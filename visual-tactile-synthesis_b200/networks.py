@@ -1076,20 +1076,112 @@ class Normalize(nn.Module):
         return x.div(norm + 1e-7)
 
 
-class PatchSampleF(nn.Module):
-    """PatchSampleF (networks.py:667-719), netF='sample': gather `num_patches` spatial positions
-    (shared across the batch) from each feature map and L2-normalise — one warp per sampled row."""
+class Linear(nn.Module):
+    """Parameter holder with nn.Linear's keys (weight [out, in], bias [out]); runs as a 1x1 convolution over the
+    sampled rows laid out as an NHWC map [1, rows, 1, in].  The class name keeps init_weights' 'Linear' dispatch."""
+
+    def __init__(self, ci, co):
+        super().__init__()
+        self.ci, self.co = ci, co
+        self.weight = nn.Parameter(torch.empty(co, ci))
+        self.bias = nn.Parameter(torch.zeros(co))
+        init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        self._packs = {}
+
+    def pack(self, mode):
+        pk = self._packs.get(mode)
+        if pk is None:
+            pk = ops.PackedWeights(self.weight.view(self.co, self.ci, 1, 1), mode, want_f32=True, want_bf16=False)
+            self._packs[mode] = pk
+        return pk
+
+    def refresh_packs(self):
+        for pk in self._packs.values():
+            pk.refresh(self.weight.view(self.co, self.ci, 1, 1))
+
+    def drop_packs(self):
+        self._packs = {}
+
+
+class PatchSampleF(_FlatParamsMixin, nn.Module):
+    """PatchSampleF (networks.py:667-719): gather `num_patches` spatial positions (shared across the batch) from each
+    feature map, optionally run them through a per-layer 2-layer MLP created on first use (netF='mlp_sample'), and
+    L2-normalise — one warp per sampled row for the gather / normalisation, 1x1-conv kernels for the MLP."""
 
     def __init__(self, use_mlp=False, init_type="normal", init_gain=0.02, nc=256, gpu_ids=[]):
         super().__init__()
         self.l2norm = Normalize(2)
         self.use_mlp, self.nc, self.mlp_init = use_mlp, nc, False
         self.init_type, self.init_gain, self.gpu_ids = init_type, init_gain, gpu_ids
-        if use_mlp:
-            raise NotImplementedError("netF='mlp_sample' is not built on the B200 path yet (netF='sample' is)")
+
+    def create_mlp(self, feats=None, channels=None, device=None):
+        """networks.py:678-686.  feats: NCHW feature list (reference signature) or `channels`: their channel counts."""
+        if channels is None:
+            channels = [int(f.shape[1]) for f in feats]
+            device = feats[0].device
+        for mlp_id, input_nc in enumerate(channels):
+            setattr(self, "mlp_%d" % mlp_id, nn.Sequential(Linear(input_nc, self.nc), _Placeholder("ReLU"), Linear(self.nc, self.nc)))
+        init_weights(self, self.init_type, init_gain=self.init_gain)
+        if device is not None:
+            self.to(device)
+        self.mlp_init = True
+        self.flat_param = None
+
+    def refresh_packs(self):
+        for m in self.modules():
+            if isinstance(m, Linear):
+                m.refresh_packs()
+
+    # -- explicit forward / backward on one NHWC feature map
+    def sample_fwd(self, feat, ids, feat_id=0, save=False):
+        """feat: NHWC [b, h, w, c]; ids: int32 device tensor [P] -> (normalised rows [b*P, nc or c], ctx)."""
+        out0, rows = ops.patch_sample_l2norm(feat, ids, keep_pre=True)
+        if not self.use_mlp:
+            return out0, (dict(rows=rows, ids=ids, shape=tuple(feat.shape)) if save else None)
+        mlp = getattr(self, "mlp_%d" % feat_id)
+        l1, l2 = mlp[0], mlp[2]
+        R = rows.shape[0]
+        op1 = ops.DenseOperand(rows.view(1, R, 1, rows.shape[1]))
+        h1, _ = ops.conv2d_fwd(op1, l1.pack(0), 1, 0, R, 1, bias=l1.bias, impl=ops.IMPL_SIMT)
+        _, op2 = ops.norm_act_pad(h1, act=ACT_RELU, pad=0, fmt=FMT_F32)
+        h2, _ = ops.conv2d_fwd(op2, l2.pack(0), 1, 0, R, 1, bias=l2.bias, impl=ops.IMPL_SIMT)
+        eye = self._arange(R, feat.device)
+        out, _ = ops.patch_sample_l2norm(h2, eye)
+        ctx = dict(rows=rows, ids=ids, shape=tuple(feat.shape), op1=op1, h1=h1, op2=op2, h2=h2, eye=eye, feat_id=feat_id) if save else None
+        return out, ctx
+
+    def sample_bwd(self, ctx, dout):
+        """dout: gradient w.r.t. the normalised rows -> gradient w.r.t. the NHWC feature map (weight grads accumulate)."""
+        if not self.use_mlp:
+            return ops.patch_sample_l2norm_bwd(dout, ctx["rows"], ctx["ids"], ctx["shape"])
+        mlp = getattr(self, "mlp_%d" % ctx["feat_id"])
+        l1, l2 = mlp[0], mlp[2]
+        h1, h2 = ctx["h1"], ctx["h2"]
+        R = h2.shape[1]
+        dh2 = ops.patch_sample_l2norm_bwd(dout, h2.view(R, -1), ctx["eye"], tuple(h2.shape))
+        d2 = ops.DenseOperand(dh2)
+        ops.conv2d_wgrad(ctx["op2"], 0, d2, 0, 1, 1, R, 1, l2.weight.grad.view(l2.co, l2.ci, 1, 1), l2.bias.grad, impl=ops.IMPL_SIMT)
+        da1 = ops.conv2d_dgrad_gather(dh2, l2.pack(2), 1, R, 1)
+        g1, _ = ops.act_norm_bwd_reduce(tuple(h1.shape), dadd=da1, raw=h1, act=ACT_RELU)
+        d1 = ops.DenseOperand(g1)
+        ops.conv2d_wgrad(ctx["op1"], 0, d1, 0, 1, 1, R, 1, l1.weight.grad.view(l1.co, l1.ci, 1, 1), l1.bias.grad, impl=ops.IMPL_SIMT)
+        drows = ops.conv2d_dgrad_gather(g1, l1.pack(2), 1, R, 1)
+        return ops.rows_scatter_add(drows.view(R, -1), ctx["ids"], ctx["shape"])
+
+    def _arange(self, n, device):
+        tab = self.__dict__.setdefault("_eyes", {})
+        key = (n, str(device))
+        if key not in tab:
+            tab[key] = torch.arange(n, dtype=torch.int32, device=device)
+        return tab[key]
 
     def forward(self, feats, num_patches=64, patch_ids=None):
         return_ids, return_feats = [], []
+        if self.use_mlp and not self.mlp_init:
+            self.create_mlp(feats)
+        if self.use_mlp:
+            self.ensure_flat()
+            self.refresh_packs()
         for feat_id, feat in enumerate(feats):
             _require_cuda(feat, "PatchSampleF")
             B, C_, H, W = feat.shape
@@ -1100,11 +1192,12 @@ class PatchSampleF(nn.Module):
             else:
                 patch_id = np.random.permutation(H * W)
                 patch_id = patch_id[:int(min(num_patches, patch_id.shape[0]))]
-            ids = torch.as_tensor(np.asarray(patch_id.cpu() if torch.is_tensor(patch_id) else patch_id), dtype=torch.int32).to(feat.device)
+            host_ids = np.asarray(patch_id.cpu() if torch.is_tensor(patch_id) else patch_id)
+            ids = torch.as_tensor(host_ids, dtype=torch.int32).to(feat.device)
             # features produced by our generators are NHWC in memory (NCHW views): no copy then
             nhwc = feat.permute(0, 2, 3, 1).contiguous().float()
-            out, _ = ops.patch_sample_l2norm(nhwc, ids)
-            return_ids.append(torch.as_tensor(np.asarray(patch_id.cpu() if torch.is_tensor(patch_id) else patch_id), dtype=torch.long, device=feat.device))
+            out, _ = self.sample_fwd(nhwc, ids, feat_id)
+            return_ids.append(torch.as_tensor(host_ids, dtype=torch.long, device=feat.device))
             return_feats.append(out)
         return return_feats, return_ids
 

@@ -377,6 +377,27 @@ def patch_sample_l2norm_bwd(dout, pre, ids, feat_shape):
     return dfeat
 
 
+def rows_scatter_add(drows, ids, feat_shape):
+    b, h, w, c = feat_shape
+    dfeat = torch.zeros(feat_shape, dtype=torch.float32, device=drows.device)
+    L.call("skit_rows_scatter_add", _p(drows), b, h * w, c, _p(ids), int(ids.numel()), _p(dfeat), L.stream())
+    return dfeat
+
+
+class DenseOperand:
+    """An existing dense NHWC fp32 tensor viewed as a halo-free conv operand (no copy)."""
+
+    def __init__(self, t):
+        n, h, w, c = t.shape
+        assert t.is_contiguous() and t.dtype == torch.float32
+        self.data, self.n, self.h, self.w, self.c, self.pad, self.fmt = t, n, h, w, c, 0, FMT_F32
+        self.hp, self.wp = h, w
+        self.struct = L.SkitOperand(t.data_ptr(), None, FMT_F32, n, h, w, c)
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
 def patchnce(q, k, b, nce_T, want_grad=False, gscale=1.0):
     rows, dim = q.shape
     npatch = rows // b

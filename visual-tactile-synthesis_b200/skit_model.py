@@ -93,8 +93,12 @@ class SinSKITGModel:
                 if not isinstance(self.netG, networks.ResnetGenerator):
                     raise NotImplementedError("PatchNCE needs a generator with feature taps (forward(layers=..., encode_only=True)): the resnet family "
                                               "(the reference's U-Net generators do not support it either, networks.py:1538)")
-                if opt.netF != "sample":
-                    raise NotImplementedError("train-step PatchNCE wiring is built for netF='sample' (PatchSampleF without MLP)")
+                if opt.netF not in ("sample", "mlp_sample"):
+                    raise NotImplementedError("train-step PatchNCE wiring is built for netF='sample' / 'mlp_sample' (PatchSampleF)")
+                self.netF = networks.define_F(g_in, opt.netF, opt.normG, not opt.no_dropout, opt.init_type, opt.init_gain,
+                                              opt.no_antialias, gpu, opt)
+                if self.netF.use_mlp:
+                    self.model_names = self.model_names + ["F"]
                 bad = [i for i in self.nce_layers if i not in self.netG.tappable_layers()]
                 if bad:
                     raise NotImplementedError("nce_layers %s are not exposed by the fused generator (available: %s)" % (bad, sorted(self.netG.tappable_layers())))
@@ -183,7 +187,7 @@ class SinSKITGModel:
         opt = self.opt
         n = self.real_S.shape[0]
         NF = opt.add_fake_T_sample_size if self.isTrain else 0
-        words = 4 * n + 2 * max(NF, 1) + 6
+        words = 4 * n + 2 * max(NF, 1) + 8
         if getattr(self, "_blob_dev", None) is None or self._blob_dev.numel() != words:
             self._blob_host = [torch.zeros(words, dtype=torch.float32).pin_memory() for _ in range(self._RING)]
             self._blob_evt = [None] * self._RING
@@ -191,7 +195,7 @@ class SinSKITGModel:
             self._blob_dev = torch.zeros(words, dtype=torch.float32, device=self.device)
             self._u_dev = self._blob_dev[:4 * n].view(4, n)
             self._fo_dev = self._blob_dev[4 * n:4 * n + 2 * max(NF, 1)].view(torch.int32).view(2, max(NF, 1))
-            self._hy_dev = self._blob_dev[4 * n + 2 * max(NF, 1):].view(3, 2)
+            self._hy_dev = self._blob_dev[4 * n + 2 * max(NF, 1):].view(4, 2)
             self._input_gen += 1
         i = self._blob_i
         self._blob_i = (i + 1) % self._RING
@@ -200,7 +204,7 @@ class SinSKITGModel:
         h = self._blob_host[i]
         hu = h[:4 * n].view(4, n)
         hfo = h[4 * n:4 * n + 2 * max(NF, 1)].view(torch.int32).view(2, max(NF, 1))
-        hhy = h[4 * n + 2 * max(NF, 1):].view(3, 2)
+        hhy = h[4 * n + 2 * max(NF, 1):].view(4, 2)
         if opt.use_diffaug:
             for j, k in enumerate(("real_b", "real_s", "fake_b", "fake_s")):
                 # the reference's torch.rand draws, in its order: real (b, s) then fake (b, s)
@@ -217,7 +221,7 @@ class SinSKITGModel:
             t = max(1, self.step_count)
             bc1 = 1.0 - opt.beta1 ** t
             bc2 = 1.0 - opt.beta2 ** t
-            for j, lr in enumerate((opt.lr, opt.lr_G2, opt.lr)):   # rows: D, D2, G
+            for j, lr in enumerate((opt.lr, opt.lr_G2, opt.lr, opt.lr)):   # rows: D, D2, G, F
                 hhy[j, 0] = lr * self.lr_factor / bc1
                 hhy[j, 1] = 1.0 / math.sqrt(bc2)
         self._blob_dev.copy_(h, non_blocking=True)
@@ -309,7 +313,8 @@ class SinSKITGModel:
                 net.refresh_packs()
         self._stage_rand(rand)
         key = (self._input_gen, tuple(self.real_S.shape), self.NT, opt.add_fake_T_sample_size,
-               tuple(net.flat_param.data_ptr() for net in (G, D, D2)))
+               tuple(net.flat_param.data_ptr() for net in (G, D, D2)),
+               getattr(getattr(self, "netF", None), "flat_param", None) is not None)
         if self._graph is not None and self._graph_key == key:
             self._graph.replay()
             L_.launches += self._graph_launches   # kernel-launching ABI calls the replayed graph stands for
@@ -440,6 +445,9 @@ class SinSKITGModel:
         self._join(4)
         self._allreduce(G)
         self._adam(G, 2)
+        if self.nce_layers and self.netF.use_mlp:
+            self._allreduce(self.netF)
+            self._adam(self.netF, 3)
         self._loss_raw = (L, NT, NF)
         return L
 
@@ -455,14 +463,26 @@ class SinSKITGModel:
         fq, cq = G.encode([Sq] + ([self.S_pe] if self.S_pe is not None else []), self.nce_layers)
         nl = len(self.nce_layers)
         dfeats, chunks = {}, []
+        F_ = self.netF
+        if F_.use_mlp:
+            if not F_.mlp_init:   # created on first use like the reference (networks.py:678-686); eager warm-up step
+                F_.create_mlp(channels=[int(self._g_feats[l].shape[3]) for l in self.nce_layers], device=self.device)
+                F_.flatten_parameters()
+                if self.dist is not None:
+                    self.dist.broadcast_params([F_])
+            F_.ensure_flat()
+            if not getattr(F_, "_packed_once", False):
+                F_.refresh_packs()
+                F_._packed_once = True
+            F_.zero_grad()
         for li, l in enumerate(self.nce_layers):
             ids = self._ids_dev[li][:self._ids_count[li]]
-            k_pool, _ = ops.patch_sample_l2norm(self._g_feats[l], ids)
-            q_pool, pre = ops.patch_sample_l2norm(fq[l], ids, keep_pre=True)
+            k_pool, _ = F_.sample_fwd(self._g_feats[l], ids, li)
+            q_pool, qctx = F_.sample_fwd(fq[l], ids, li, save=True)
             rows = q_pool.shape[0]
             b = 1 if opt.nce_includes_all_negatives_from_minibatch else n
             loss_l, dq = ops.patchnce(q_pool, k_pool, b, opt.nce_T, want_grad=True, gscale=opt.lambda_NCE / (nl * rows))
-            dfeats[l] = ops.patch_sample_l2norm_bwd(dq, pre, ids, tuple(fq[l].shape))
+            dfeats[l] = F_.sample_bwd(qctx, dq)
             chunks.append(loss_l)
         dpad0 = G.encode_bwd(cq, dfeats)
         if dpad0 is not None:
