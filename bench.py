@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-size", type=int, default=256, help="image side of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"], help="infer: generator forward only (BASELINE.json configs[4])")
+    ap.add_argument("--batch", type=int, default=1, help="images per rank per step (infer mode)")
     ap.add_argument("--nce", action="store_true", help="PatchNCE on (BASELINE.json configs[2] wiring: use with --size 768)")
     return ap.parse_args()
 
@@ -311,10 +313,69 @@ def run_b200(a):
     ctx.shutdown()
 
 
+def run_infer(a):
+    """BASELINE.json configs[4]: sketch -> (RGB, normal, height-gradient) generator forward throughput, batch B per rank,
+    replicas only (no collective).  `value`: inputs resident; `e2e`: set_input (pinned H2D of S, M) + test() + D2H of fake_N."""
+    import vts_b200
+    from vts_b200.dist import DistContext
+    ctx = DistContext()
+    torch.cuda.set_device(ctx.local_rank)
+    size = a.size
+    opt = vts_b200.default_options(gpu_ids=[ctx.local_rank], isTrain=False)
+    torch.manual_seed(0)
+    model = vts_b200.SinSKITGModel(opt)
+    g = torch.Generator().manual_seed(ctx.rank)
+    B = a.batch
+    batch = {"S": (torch.rand(B, 1, size, size, generator=g) * 2 - 1).pin_memory(), "M": torch.ones(B, 1, size, size).pin_memory()}
+    out_host = torch.empty(B, 3, size, size).pin_memory()
+    model.set_input(batch, phase="test")
+    for _ in range(max(a.warmup, 3)):
+        model.test()
+    ctx.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = vts_b200._lib.launches
+    with ClockSampler(ctx.local_rank) as clk:
+        e0.record()
+        for _ in range(a.steps):
+            model.test()
+        e1.record()
+        torch.cuda.synchronize()
+    launches = vts_b200._lib.launches - l0
+    t_res = ctx.max_over_ranks(e0.elapsed_time(e1) / 1e3)
+    ctx.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        model.set_input(batch, phase="test")
+        model.test()
+        out_host.copy_(model.fake_N, non_blocking=True)
+        torch.cuda.synchronize()
+    t_e2e = ctx.max_over_ranks(time.perf_counter() - t0)
+    n = ctx.world_size
+    line = {"metric": "skitG generator forward images/sec", "value": n * B * a.steps / t_res, "unit": UNIT, "n_gpus": n, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": 1e3 * t_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 split operands, fp32 accumulate; fp32 elsewhere", "data": "synthetic",
+            "config": {"workload": "generator forward %dx%d, batch %d per rank, resnet_9blocks ngf64 (BASELINE.json configs[4])" % (size, size, B),
+                       "size": size, "batch_per_rank": B, "parallelism": "replicas x%d (no collective)" % n,
+                       "l2": "activations per forward exceed the 126 MB L2"},
+            "e2e": {"value": n * B * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(model.h2d_bytes), "d2h_bytes_per_step": int(out_host.numel() * 4)},
+            "gpu_launches": int(launches), "clocks": clk.summary()}
+    if ctx.rank == 0:
+        print(json.dumps(line), flush=True)
+    if n > 1:
+        torch.cuda.synchronize()
+        ctx.barrier()
+        sys.stdout.flush()
+        os._exit(0)
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.mode == "infer":
+        run_infer(a)
     else:
         run_b200(a)
 

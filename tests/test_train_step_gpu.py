@@ -256,3 +256,24 @@ def test_train_step_with_patchnce_mlp_vs_oracle():
         ok = g.abs() > max(1e-7, 0.05 * float(g.pow(2).mean().sqrt()))
         bad = ((v.detach().cpu().reshape(-1) - sdF[k].detach().reshape(-1)).abs() > 2e-4)[ok]
         assert bad.float().mean().item() < 0.02, k
+
+
+def test_inference_forward_graph_and_batches():
+    """test() (generator forward, BASELINE.json configs[0]/[4]) with batch > 1 and CUDA-graph replay vs the oracle."""
+    import vts_b200
+    from oracle import skit_oracle as O
+    torch.manual_seed(4)
+    opt = vts_b200.default_options(isTrain=False, ngf=64)
+    m = vts_b200.SinSKITGModel(opt)
+    sd = {k: v.detach().cpu().clone() for k, v in m.netG.state_dict().items()}
+    B, S = 3, 64
+    g = torch.Generator().manual_seed(9)
+    batch = {"S": torch.rand(B, 1, S, S, generator=g) * 2 - 1, "M": (torch.rand(B, 1, S, S, generator=g) > 0.1).float()}
+    pe = O.spe_grid(S, S, 4, B)
+    ref = O.model_forward(O.StepConfig(), sd, batch["S"] * batch["M"], pe, batch["M"])
+    for i in range(3):          # eager, capture, replay
+        m.set_input(batch, phase="test")
+        fI, fT, fN = m.test()
+        torch.cuda.synchronize()
+        assert rel(fI, ref["fake_I"]) < GATE and rel(fT, ref["fake_T"]) < GATE and rel(fN, ref["fake_N"]) < GATE, i
+    assert m._tgraph is not None
