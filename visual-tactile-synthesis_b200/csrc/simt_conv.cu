@@ -187,8 +187,12 @@ __global__ void __launch_bounds__(256) conv_thin_kernel(ConvP p, int n_img, int 
 #pragma unroll
         for (int j = 0; j < NOUT; j++) acc[i][j] = 0.f;
 
-    for (int ky = 0; ky < p.k; ky++) {
-        for (int kx = 0; kx < p.k; kx++) {
+    // input-gradient mode visits only the taps that can hit an output sample: (y - ky) % stride == 0 (and the same in x
+    // when the warp owns a single column) — a stride-2 k4 layer has 4 such taps per pixel, not 16
+    const int ky0 = (MODE == 1) ? (y % p.stride) : 0, kys = (MODE == 1) ? p.stride : 1;
+    const int kx0 = (MODE == 1 && PIX == 1) ? (x0 % p.stride) : 0, kxs = (MODE == 1 && PIX == 1) ? p.stride : 1;
+    for (int ky = ky0; ky < p.k; ky += kys) {
+        for (int kx = kx0; kx < p.k; kx += kxs) {
             long long abase[PIX];
             bool av[PIX];
 #pragma unroll

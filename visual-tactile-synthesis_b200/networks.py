@@ -369,7 +369,8 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         if lo.use_tc:   # 5-channel gradient, zero-padded to 8 channels and haloed by k-1 for the flipped-filter input gradient
             q = lo.k - 1
             d30 = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, q, fmt=FMT_BF16X2, cpad=lo.co_pad)
-            ops.conv2d_wgrad(ctx["op26"], 0, d30, q, lo.k, 1, S_h, S_w, lo.weight.grad, lo.bias.grad)
+            op26 = ctx["op26"]
+            _wgrad_async(lambda: ops.conv2d_wgrad(op26, 0, d30, q, lo.k, 1, S_h, S_w, lo.weight.grad, lo.bias.grad), (op26, d30))
             dpad26, _ = ops.conv2d_fwd(d30, lo.pack(1), 1, 0, S_h + 6, S_w + 6)
         else:
             d30 = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, 0)
