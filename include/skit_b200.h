@@ -85,6 +85,18 @@ int skit_pack_conv_weights(const float* w, int co, int ci, int k, int mode,
  * with thin inputs (the 9-channel generator stem, the 5-channel head's input gradient) run on the tcgen05 path, whose
  * TMA rows must be 16-byte multiples.  The matching operand carries the same number of (zero) padding channels. */
 int skit_pack_conv_weights_padded(const float* w, int co, int ci, int k, int mode, int kpad, void* hi, void* lo, void* stream);
+/* All packs of a net in ONE launch (after each Adam step): descs_dev is a DEVICE array of n descriptors; a descriptor
+ * fills either the fp32 pack (hi == NULL) or the bf16 hi/lo pack (with kpad as in the padded variant).  `start` is the
+ * prefix sum of the packs' element counts (k*k*N*K, K padded for bf16), `total` their sum. */
+typedef struct skit_pack_desc {
+    const float* w;   /* reference-layout weight [co][ci][k][k] */
+    float* f32;
+    void* hi;
+    void* lo;
+    long long start;
+    int co, ci, k, mode, kpad, reserved;
+} skit_pack_desc;
+int skit_pack_conv_weights_batched(const skit_pack_desc* descs_dev, int n, long long total, void* stream);
 /* Inverse of the forward pack for gradients: dWf [(tap*ci+c)][o] fp32 -> dw[o][c][ky][kx] (+= if accumulate). */
 int skit_unpack_conv_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, void* stream);
 

@@ -23,6 +23,11 @@ class SkitOperand(C.Structure):
                 ("n", C.c_int), ("hp", C.c_int), ("wp", C.c_int), ("c", C.c_int)]
 
 
+class SkitPackDesc(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("f32", C.c_void_p), ("hi", C.c_void_p), ("lo", C.c_void_p), ("start", C.c_longlong),
+                ("co", C.c_int), ("ci", C.c_int), ("k", C.c_int), ("mode", C.c_int), ("kpad", C.c_int), ("reserved", C.c_int)]
+
+
 class SkitWeights(C.Structure):
     _fields_ = [("f32", C.c_void_p), ("hi", C.c_void_p), ("lo", C.c_void_p),
                 ("k", C.c_int), ("ci", C.c_int), ("co", C.c_int)]
@@ -36,6 +41,7 @@ SIGNATURES = {
     "skit_pack_conv_weights": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     "skit_pack_conv_weights_padded": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
     "skit_conv2d_wgrad_ex": [_OP, _I, _OP, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P],
+    "skit_pack_conv_weights_batched": [_P, _I, _LL, _P],
     "skit_unpack_conv_wgrad": [_P, _I, _I, _I, _P, _I, _P],
     "skit_conv2d_fwd": [_OP, _WT, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "skit_conv2d_dgrad_gather": [_P, _I, _I, _I, _I, _WT, _I, _I, _I, _P, _P],

@@ -423,6 +423,36 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci,
     }
 }
 
+// One launch for every pack of a net: `descs` (device) lists the packs with their prefix offsets into a single index space.
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const skit_pack_desc* __restrict__ descs, int n, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {   // last descriptor whose start <= i
+            const int mid = (lo + hi + 1) >> 1;
+            if (descs[mid].start <= i) lo = mid; else hi = mid - 1;
+        }
+        const skit_pack_desc d = descs[lo];
+        const long long j = i - d.start;
+        const int mode = d.mode, k = d.k, co = d.co, ci = d.ci;
+        const int Kd = mode == 0 ? ci : co, Nd = mode == 0 ? co : ci;
+        if (d.hi) {   // bf16 hi/lo [tap][N][Kp]
+            const int Kp = d.kpad > Kd ? d.kpad : Kd;
+            const int kk = (int)(j % Kp); long long t = j / Kp;
+            const int nn = (int)(t % Nd); const int tap = (int)(t / Nd);
+            const int o = mode == 0 ? nn : kk, c = mode == 0 ? kk : nn;
+            const float v = kk < Kd ? __ldg(d.w + pack_src_index(mode, k, co, ci, tap, o, c)) : 0.f;
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            ((__nv_bfloat16*)d.hi)[j] = h; ((__nv_bfloat16*)d.lo)[j] = l;
+        } else {      // fp32 [tap][K][N]
+            const int nn = (int)(j % Nd); long long t = j / Nd;
+            const int kk = (int)(t % Kd); const int tap = (int)(t / Kd);
+            const int o = mode == 0 ? nn : kk, c = mode == 0 ? kk : nn;
+            d.f32[j] = __ldg(d.w + pack_src_index(mode, k, co, ci, tap, o, c));
+        }
+    }
+}
+
 // layout 0: dwf[(tap*cip + c)*cop + o]   layout 1: dwf[(tap*cop + o)*cip + c]   (cop/cip: channel counts of the
 // operands the partial sums were computed on, >= the real co/ci when those were zero-padded)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int co, int ci, int k, float* dw, int accumulate, int layout,
@@ -471,6 +501,13 @@ extern "C" int skit_pack_conv_weights(const float* w, int co, int ci, int k, int
     int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
     pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, co, ci, k, mode, f32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, 0);
     return check_launch("pack_weights_kernel");
+}
+
+extern "C" int skit_pack_conv_weights_batched(const skit_pack_desc* descs_dev, int n, long long total, void* stream) {
+    SKIT_REQUIRE(descs_dev && n > 0 && total > 0, "pack_conv_weights_batched: bad arguments");
+    int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
+    pack_weights_batched_kernel<<<blocks, 256, 0, as_stream(stream)>>>(descs_dev, n, total);
+    return check_launch("pack_weights_batched_kernel");
 }
 
 extern "C" int skit_pack_conv_weights_padded(const float* w, int co, int ci, int k, int mode, int kpad, void* hi, void* lo, void* stream) {

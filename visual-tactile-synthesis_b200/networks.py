@@ -164,9 +164,26 @@ class _FlatParamsMixin:
             super().zero_grad(set_to_none=False)
 
     def refresh_packs(self):
+        """Re-pack every weight of the net (after an optimiser step): one batched launch over a device table of all
+        existing packs; the table is rebuilt (host -> device, outside any graph capture) only when a new pack appeared."""
+        pairs = []
         for m in self.modules():
-            if isinstance(m, Conv2d) or (m is not self and hasattr(m, "refresh_packs") and hasattr(m, "_packs")):
-                m.refresh_packs()
+            if m is not self and hasattr(m, "_packs"):
+                w = m.weight if m.weight.dim() == 4 else m.weight.view(m.weight.shape[0], m.weight.shape[1], 1, 1)
+                for mode in sorted(m._packs):
+                    pairs.append((w, m._packs[mode]))
+        if not pairs:
+            return
+        key = tuple((w.data_ptr(), id(pk)) for w, pk in pairs)
+        tab = self.__dict__.get("_pack_table")
+        if tab is None or tab.key != key:
+            if torch.cuda.is_current_stream_capturing():
+                for w, pk in pairs:     # a pack created during capture: fall back to per-pack launches for this capture
+                    pk.refresh(w)
+                return
+            tab = ops.PackTable(pairs, pairs[0][0].device)
+            self.__dict__["_pack_table"] = tab
+        tab.refresh()
 
 
 # ----------------------------------------------------------------------------- weight gradients off the critical path
@@ -654,11 +671,6 @@ class CustomUnetGenerator(_FlatParamsMixin, nn.Module):
         m = getattr(self, "up%d%s" % (i, "_T" if T else ""), None)
         return None if m is None else m.conv
 
-    def refresh_packs(self):
-        for m in self.modules():
-            if isinstance(m, (Conv2d, ConvTranspose2d)):
-                m.refresh_packs()
-
     def tappable_layers(self):
         return set()
 
@@ -1127,11 +1139,6 @@ class PatchSampleF(_FlatParamsMixin, nn.Module):
             self.to(device)
         self.mlp_init = True
         self.flat_param = None
-
-    def refresh_packs(self):
-        for m in self.modules():
-            if isinstance(m, Linear):
-                m.refresh_packs()
 
     # -- explicit forward / backward on one NHWC feature map
     def sample_fwd(self, feat, ids, feat_id=0, save=False):

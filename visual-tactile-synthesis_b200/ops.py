@@ -69,6 +69,35 @@ class PackedWeights:
     def ref(self):
         return C.byref(self.struct)
 
+    def desc(self, w, start):
+        """Descriptor of this pack for the batched refresh (skit_pack_conv_weights_batched)."""
+        return L.SkitPackDesc(w.data_ptr(), self.f32.data_ptr() if self.f32 is not None else None,
+                              self.hi.data_ptr() if self.hi is not None else None,
+                              self.lo.data_ptr() if self.lo is not None else None, start,
+                              self.co, self.ci, self.k, self.mode, self.kpad, 0)
+
+    def numel(self):
+        return self.k * self.k * self.rco * self.rci
+
+
+class PackTable:
+    """All packs of one net refreshed by a single kernel launch."""
+
+    def __init__(self, pairs, device):
+        """pairs: [(weight tensor [co,ci,k,k], PackedWeights)]"""
+        arr = (L.SkitPackDesc * len(pairs))()
+        start = 0
+        for i, (w, pk) in enumerate(pairs):
+            arr[i] = pk.desc(w, start)
+            start += pk.numel()
+        self.total, self.n = start, len(pairs)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+        self.dev = raw.to(device)
+        self.key = tuple((w.data_ptr(), id(pk)) for w, pk in pairs)
+
+    def refresh(self):
+        L.call("skit_pack_conv_weights_batched", _p(self.dev), self.n, self.total, L.stream())
+
 
 def conv2d_fwd(x, w, stride, org, ho, wo, bias=None, stats_mode=NORM_NONE, impl=IMPL_AUTO, out=None):
     """Valid conv over a haloed operand -> (y NHWC fp32, stats double [groups, co, 2] or None)."""

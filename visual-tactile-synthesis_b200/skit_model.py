@@ -438,19 +438,22 @@ class SinSKITGModel:
         self._allreduce(D)
         self._adam(D, 0)
 
-        # ---- D2 update (:654-667)
-        self._join(1, 2, *([3] if more else []))
-        for k in ("fake", "more", "real"):
-            if k in run_D2:
-                networks.apply_running_updates(run_D2[k])
-        self._allreduce(D2)
-        self._adam(D2, 1)
-
-        # ---- G step (:680-694): GAN through the updated (frozen) D, L1, patch L1; G2 GAN is value-only
-        G.zero_grad()
-        with self._fork(4):
-            pg2, _ = D2.fwd([self.fake_in], save=False)           # detached clone in the reference (:1751,1781)
+        # ---- D2 update (:654-667) and the G step's value-only D2 pass stay on branch 1, off the launching stream: the
+        #      generator's backward does not depend on them (G2 GAN is computed on a detached clone, :1751,1781)
+        b1 = self._bstreams[1]
+        for i in (2, 3) if more else (2,):
+            b1.wait_stream(self._bstreams[i])
+        with torch.cuda.stream(b1):
+            for k in ("fake", "more", "real"):
+                if k in run_D2:
+                    networks.apply_running_updates(run_D2[k])
+            self._allreduce(D2)
+            self._adam(D2, 1)
+            pg2, _ = D2.fwd([self.fake_in], save=False)
             self._gan(pg2, -1.0, sl["G2_GAN"])
+
+        # ---- G step (:680-694): GAN through the updated (frozen) D, L1, patch L1
+        G.zero_grad()
         pg, cg = D.fwd([self.real_S, fake_I])
         dpg = self._gan(pg, -1.0, sl["G_GAN"], opt.lambda_G1_GAN / n)
         dI = D.bwd(cg, dpg, need_wgrad=False, input_slice=(opt.input_nc, 3))
@@ -465,7 +468,7 @@ class SinSKITGModel:
             self._nce_step(dI, n)
         G.bwd(self._g_ctx, dI, dT)
         self._g_ctx = None
-        self._join(4)
+        self._join(1)
         self._allreduce(G)
         self._adam(G, 2)
         if self.nce_layers and self.netF.use_mlp:
