@@ -349,6 +349,39 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
     }
 }
 
+// Weight gradient of a layer with very few output channels (PatchGAN head 512 -> 1, generator head on the fp32 path):
+// dwf[(tap*ci + c)*co + o] += sum_pix dy[pix][o] * x[pix + tap][c].  The 64x64 GEMM tile of wgrad_simt_kernel would carry
+// one useful row; here a thread owns one input channel of one tap (coalesced 128-channel runs of x), keeps co (<= 4)
+// accumulators, and walks a slice of the pixels.  grid: (taps, channel chunks of 128, n * pixel splits).
+template <int XFMT, int DFMT, int CO>
+__global__ void __launch_bounds__(128) wgrad_thin_co_kernel(WgradP p) {
+    const int tap = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x;
+    const int n = blockIdx.z / p.splits, sp = blockIdx.z - n * p.splits;
+    const int P = p.ho * p.wo;
+    const int pbeg = sp * p.chunk, pend = min(P, pbeg + p.chunk);
+    const int ky = tap / p.k, kx = tap - ky * p.k;
+    if (c >= p.ci) return;
+    float acc[CO];
+#pragma unroll
+    for (int o = 0; o < CO; o++) acc[o] = 0.f;
+    for (int pix = pbeg; pix < pend; pix++) {
+        const int oy = pix / p.wo, ox = pix - oy * p.wo;
+        const long long dbase = (((long long)n * p.dhp + p.dorg + oy) * p.dwp + p.dorg + ox) * p.co;
+        const long long xa = (((long long)n * p.hp + p.org + oy * p.stride + ky) * p.wp + p.org + ox * p.stride + kx) * p.ci + c;
+        const float xv = (XFMT == SKIT_FMT_F32) ? __ldg(p.x0 + xa) : (__bfloat162float(p.xh[xa]) + __bfloat162float(p.xl[xa]));
+#pragma unroll
+        for (int o = 0; o < CO; o++) {
+            if (o < p.co) {
+                const float dv = (DFMT == SKIT_FMT_F32) ? __ldg(p.d0 + dbase + o) : (__bfloat162float(p.dh[dbase + o]) + __bfloat162float(p.dl[dbase + o]));
+                acc[o] = fmaf(dv, xv, acc[o]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < CO; o++)
+        if (o < p.co) atomicAdd(p.dwf + ((long long)tap * p.ci + c) * p.co + o, acc[o]);
+}
+
 // dbias[o] += sum over pixels of dy (operand with halo).  grid: (pixel chunks, n), block 256 = 8 pixel
 // lanes x 32 channel lanes: a warp reads 32 consecutive channels of one pixel (coalesced), the 8 pixel
 // lanes are combined through shared memory before one atomic per channel per CTA.
@@ -630,6 +663,19 @@ extern "C" int skit_conv2d_wgrad_ex(const skit_operand* x, int org, const skit_o
         p.d0 = (const float*)dy->p0; p.dh = (const __nv_bfloat16*)dy->p0; p.dl = (const __nv_bfloat16*)dy->p1;
         p.dhp = dy->hp; p.dwp = dy->wp; p.co = co; p.dorg = dy_org;
         p.k = k; p.stride = stride; p.ho = ho; p.wo = wo; p.Kf = k * k * ci; p.dwf = dwf;
+        if (co <= 4 && ci >= 64) {   // thin output side: channel-parallel reduction instead of a GEMM tile
+            const int blocks = k * k * cdiv(ci, 128);
+            int splits = max(1, min(cdiv(cdiv(148 * 8, blocks), n), cdiv(P, 32)));
+            p.chunk = cdiv(P, splits);
+            p.splits = cdiv(P, p.chunk);
+            dim3 grid(k * k, cdiv(ci, 128), n * p.splits);
+            if (x->fmt == SKIT_FMT_F32 && dy->fmt == SKIT_FMT_F32) wgrad_thin_co_kernel<0, 0, 4><<<grid, 128, 0, st>>>(p);
+            else if (x->fmt == SKIT_FMT_F32) wgrad_thin_co_kernel<0, 1, 4><<<grid, 128, 0, st>>>(p);
+            else if (dy->fmt == SKIT_FMT_F32) wgrad_thin_co_kernel<1, 0, 4><<<grid, 128, 0, st>>>(p);
+            else wgrad_thin_co_kernel<1, 1, 4><<<grid, 128, 0, st>>>(p);
+            int rc = check_launch("wgrad_thin_co_kernel");
+            if (rc) return rc;
+        } else {
         int tiles = cdiv(co, WM) * cdiv(p.Kf, WN);
         int want = cdiv(148 * 4, tiles);
         int splits = max(1, min(cdiv(want, n), cdiv(P, 64)));
@@ -642,6 +688,7 @@ extern "C" int skit_conv2d_wgrad_ex(const skit_operand* x, int org, const skit_o
         else wgrad_simt_kernel<1, 1><<<grid, 256, 0, st>>>(p);
         int rc = check_launch("wgrad_simt_kernel");
         if (rc) return rc;
+        }
     }
     {
         int rc = unpack_wgrad(dwf, co_real, ci_real, k, dw, 1, layout, st, co, ci);
