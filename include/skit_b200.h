@@ -63,6 +63,8 @@ typedef struct skit_weights {
     int k;
     int ci; /* channels the GEMM reduces over per tap (forward pack: conv ci; dgrad packs: conv co) */
     int co; /* GEMM output columns               (forward pack: conv co; dgrad packs: conv ci) */
+    int kw; /* filter columns; 0 = square (k x k).  1 for x-folded packs (modes 4 / 5): the filter's columns live in the
+               operand's channel axis, see skit_fold_x_operand */
 } skit_weights;
 
 const char* skit_last_error(void);
@@ -97,6 +99,20 @@ typedef struct skit_pack_desc {
     int co, ci, k, mode, kpad, reserved;
 } skit_pack_desc;
 int skit_pack_conv_weights_batched(const skit_pack_desc* descs_dev, int n, long long total, void* stream);
+/* x-folded packs for thin k x k layers on the tensor cores (the 9-channel 7x7 generator stem, the input gradient of the
+ * 5-channel 7x7 head): the filter's kw columns move into the 64-wide channel axis, leaving a (k x 1) filter:
+ *   mode 4 (forward):        Wf[ky][o][kx*cp + c]  = w[o][c][ky][kx]            (N = co, K = 64, zero beyond kw*cp and c >= ci)
+ *   mode 5 (input gradient): Wg[ky][c][kx*cp + o]  = w[o][c][k-1-ky][k-1-kx]    (N = ci, K = 64)
+ * cp = channels per folded column (>= ci resp. co, k*cp <= 64).  hi/lo: bf16 [k][N][64]. */
+int skit_pack_conv_weights_folded(const float* w, int co, int ci, int k, int mode, int cp, void* hi, void* lo, void* stream);
+/* thin: haloed operand [n][hp][wp][cp] (fp32 or bf16x2).  folded: bf16x2 operand [n][hp][wp-kw+1][64] with
+ * folded[n][y][x][kx*cp + c] = thin[n][y][x + kx][c] (zero for channels >= kw*cp): a (k x kw) valid conv over `thin` equals a
+ * (k x 1) valid conv over `folded` with a mode-4 / mode-5 pack — 64-channel K steps instead of kw thin ones. */
+int skit_fold_x_operand(const skit_operand* thin, int kw, const skit_operand* folded, void* stream);
+/* Weight gradient against an x-folded input operand: dw[o][c][ky][kx] += sum dy[pix][o] * folded[pix + ky][kx*cp + c].
+ * xf: folded operand (c = 64), dy: bf16x2 operand with 64-multiple channels; scratch: k*64*dy->c floats, zeroed. */
+int skit_conv2d_wgrad_folded(const skit_operand* xf, int org, const skit_operand* dy, int dy_org, int k, int kw, int cp,
+                             int ho, int wo, float* scratch, float* dw, int co_real, int ci_real, void* stream);
 /* Inverse of the forward pack for gradients: dWf [(tap*ci+c)][o] fp32 -> dw[o][c][ky][kx] (+= if accumulate). */
 int skit_unpack_conv_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, void* stream);
 

@@ -30,7 +30,7 @@ class SkitPackDesc(C.Structure):
 
 class SkitWeights(C.Structure):
     _fields_ = [("f32", C.c_void_p), ("hi", C.c_void_p), ("lo", C.c_void_p),
-                ("k", C.c_int), ("ci", C.c_int), ("co", C.c_int)]
+                ("k", C.c_int), ("ci", C.c_int), ("co", C.c_int), ("kw", C.c_int)]
 
 
 _P, _I, _F, _D, _LL = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong
@@ -42,6 +42,9 @@ SIGNATURES = {
     "skit_pack_conv_weights_padded": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
     "skit_conv2d_wgrad_ex": [_OP, _I, _OP, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P],
     "skit_pack_conv_weights_batched": [_P, _I, _LL, _P],
+    "skit_pack_conv_weights_folded": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "skit_fold_x_operand": [_OP, _I, _OP, _P],
+    "skit_conv2d_wgrad_folded": [_OP, _I, _OP, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
     "skit_unpack_conv_wgrad": [_P, _I, _I, _I, _P, _I, _P],
     "skit_conv2d_fwd": [_OP, _WT, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "skit_conv2d_dgrad_gather": [_P, _I, _I, _I, _I, _WT, _I, _I, _I, _P, _P],

@@ -175,6 +175,38 @@ __global__ void __launch_bounds__(256) norm_act_pad_rows_kernel(PrepP p, int cv,
     }
 }
 
+// ------------------------------------------------------------------------------ x-fold of a thin operand
+// folded[n][y][x][kx*cp + c] = thin[n][y][x + kx][c]; one thread per (pixel, 4 folded channels).
+struct FoldP {
+    const float* t0; const __nv_bfloat16* th; const __nv_bfloat16* tl; int tfmt;
+    int n, hp, wp, cp, kw, wf;
+    __nv_bfloat16* oh; __nv_bfloat16* ol;
+};
+__global__ void __launch_bounds__(256) fold_x_kernel(FoldP p) {
+    const long long total = (long long)p.n * p.hp * p.wf * 16;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j0 = (int)(i % 16) * 4;
+        long long t = i / 16;
+        const int x = (int)(t % p.wf); t /= p.wf;
+        const int y = (int)(t % p.hp);
+        const int b = (int)(t / p.hp);
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int j = j0 + q, kx = j / p.cp, c = j - kx * p.cp;
+            float v = 0.f;
+            if (kx < p.kw) {
+                const long long a = (((long long)b * p.hp + y) * p.wp + x + kx) * p.cp + c;
+                v = p.tfmt == SKIT_FMT_F32 ? p.t0[a] : (__bfloat162float(p.th[a]) + __bfloat162float(p.tl[a]));
+            }
+            split_bf16(v, hi[q], lo[q]);
+        }
+        const long long dst = (((long long)b * p.hp + y) * p.wf + x) * 64 + j0;
+        *reinterpret_cast<uint2*>(p.oh + dst) = *reinterpret_cast<uint2*>(hi);
+        *reinterpret_cast<uint2*>(p.ol + dst) = *reinterpret_cast<uint2*>(lo);
+    }
+}
+
 // ------------------------------------------------------------------------------ backward phase A
 struct BwdAP {
     const float* dpad; int pad, pad_mode;
@@ -684,6 +716,19 @@ extern "C" int skit_stats_finalize(const double* stats, int groups, int c, doubl
     SKIT_REQUIRE(!running_mean || groups == 1, "stats_finalize: running stats only for batch statistics (groups == 1)");
     stats_finalize_kernel<<<cdiv(groups * c, 128), 128, 0, as_stream(stream)>>>(stats, groups, c, count, eps, mean_rstd, running_mean, running_var, momentum);
     return check_launch("stats_finalize_kernel");
+}
+
+extern "C" int skit_fold_x_operand(const skit_operand* thin, int kw, const skit_operand* folded, void* stream) {
+    SKIT_REQUIRE(thin && folded && thin->p0 && folded->p0 && folded->p1 && folded->fmt == SKIT_FMT_BF16X2, "fold_x_operand: bad operands (bf16x2 destination required)");
+    SKIT_REQUIRE(thin->fmt == SKIT_FMT_F32 || (thin->fmt == SKIT_FMT_BF16X2 && thin->p1), "fold_x_operand: bad source format");
+    SKIT_REQUIRE(kw >= 1 && kw * thin->c <= 64 && folded->c == 64, "fold_x_operand: kw*c = %d*%d must fit the 64 folded channels", kw, thin->c);
+    SKIT_REQUIRE(folded->n == thin->n && folded->hp == thin->hp && folded->wp == thin->wp - kw + 1, "fold_x_operand: destination dims mismatch");
+    FoldP p{};
+    p.t0 = (const float*)thin->p0; p.th = (const __nv_bfloat16*)thin->p0; p.tl = (const __nv_bfloat16*)thin->p1; p.tfmt = thin->fmt;
+    p.n = thin->n; p.hp = thin->hp; p.wp = thin->wp; p.cp = thin->c; p.kw = kw; p.wf = folded->wp;
+    p.oh = (__nv_bfloat16*)folded->p0; p.ol = (__nv_bfloat16*)folded->p1;
+    fold_x_kernel<<<grid_for((long long)p.n * p.hp * p.wf * 16, 256), 256, 0, as_stream(stream)>>>(p);
+    return check_launch("fold_x_kernel");
 }
 
 extern "C" int skit_norm_act_pad_ex(const float* raw, int n, int h, int w, int c,

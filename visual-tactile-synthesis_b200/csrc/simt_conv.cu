@@ -432,6 +432,27 @@ __device__ __forceinline__ long long pack_src_index(int mode, int k, int co, int
     return (((long long)o * ci + c) * k + ky) * k + kx;
 }
 
+// x-folded packs (modes 4 / 5, bf16 only): [ky][N][64], K index j = kx*cp + ch
+__device__ __forceinline__ float folded_pack_value(const float* __restrict__ w, int mode, int k, int co, int ci, int cp, int ky, int nn, int j) {
+    const int kx = j / cp, ch = j - kx * cp;
+    if (kx >= k) return 0.f;
+    if (mode == 4) { return ch < ci ? __ldg(w + (((long long)nn * ci + ch) * k + ky) * k + kx) : 0.f; }
+    return ch < co ? __ldg(w + (((long long)ch * ci + nn) * k + (k - 1 - ky)) * k + (k - 1 - kx)) : 0.f;
+}
+
+__global__ void pack_weights_folded_kernel(const float* __restrict__ w, int co, int ci, int k, int mode, int cp,
+                                           __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const int Nd = mode == 4 ? co : ci;
+    const long long total = (long long)k * Nd * 64;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % 64); long long t = i / 64;
+        const int nn = (int)(t % Nd); const int ky = (int)(t / Nd);
+        __nv_bfloat16 h, l;
+        split_bf16(folded_pack_value(w, mode, k, co, ci, cp, ky, nn, j), h, l);
+        hi[i] = h; lo[i] = l;
+    }
+}
+
 __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci, int k, int mode,
                                     float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo, int kpad) {
     const int Kd = mode == 0 ? ci : co, Nd = mode == 0 ? co : ci;
@@ -467,6 +488,15 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const skit_pa
         const skit_pack_desc d = descs[lo];
         const long long j = i - d.start;
         const int mode = d.mode, k = d.k, co = d.co, ci = d.ci;
+        if (mode >= 4) {   // x-folded bf16 pack [ky][N][64]; d.reserved = channels per folded column
+            const int Nd4 = mode == 4 ? co : ci;
+            const int jj = (int)(j % 64); long long t4 = j / 64;
+            const int nn4 = (int)(t4 % Nd4); const int ky4 = (int)(t4 / Nd4);
+            __nv_bfloat16 h4, l4;
+            split_bf16(folded_pack_value(d.w, mode, k, co, ci, d.reserved, ky4, nn4, jj), h4, l4);
+            ((__nv_bfloat16*)d.hi)[j] = h4; ((__nv_bfloat16*)d.lo)[j] = l4;
+            continue;
+        }
         const int Kd = mode == 0 ? ci : co, Nd = mode == 0 ? co : ci;
         if (d.hi) {   // bf16 hi/lo [tap][N][Kp]
             const int Kp = d.kpad > Kd ? d.kpad : Kd;
@@ -499,6 +529,19 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int co, int c
         float v = layout == 0 ? dwf[(tap * cip + c) * cop + o] : dwf[(tap * cop + o) * cip + c];
         if (accumulate) atomicAdd(dw + i, v);   // passes running on parallel streams accumulate into the same bucket
         else dw[i] = v;
+    }
+}
+
+// dwf from wgrad_tc on a folded operand: taps = ky, x channels j = kx*cp + c.  layout 0: [(ky*64 + j)*cop + o], 1: [(ky*cop + o)*64 + j]
+__global__ void unpack_wgrad_folded_kernel(const float* __restrict__ dwf, int co, int ci, int k, int kw, int cp, float* dw, int layout, int cop) {
+    const long long total = (long long)co * ci * k * kw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int kx = i % kw; long long t = i / kw;
+        int ky = t % k; t /= k;
+        int c = t % ci; int o = t / ci;
+        const int j = kx * cp + c;
+        const float v = layout == 0 ? dwf[((long long)ky * 64 + j) * cop + o] : dwf[((long long)ky * cop + o) * 64 + j];
+        atomicAdd(dw + i, v);
     }
 }
 
@@ -541,6 +584,15 @@ extern "C" int skit_pack_conv_weights_batched(const skit_pack_desc* descs_dev, i
     int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
     pack_weights_batched_kernel<<<blocks, 256, 0, as_stream(stream)>>>(descs_dev, n, total);
     return check_launch("pack_weights_batched_kernel");
+}
+
+extern "C" int skit_pack_conv_weights_folded(const float* w, int co, int ci, int k, int mode, int cp, void* hi, void* lo, void* stream) {
+    SKIT_REQUIRE(w && hi && lo && co > 0 && ci > 0 && k > 0 && (mode == 4 || mode == 5), "pack_conv_weights_folded: bad arguments");
+    SKIT_REQUIRE(cp >= (mode == 4 ? ci : co) && k * cp <= 64, "pack_conv_weights_folded: cp %d must hold the thin side and k*cp <= 64", cp);
+    long long total = (long long)k * (mode == 4 ? co : ci) * 64;
+    int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
+    pack_weights_folded_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, co, ci, k, mode, cp, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    return check_launch("pack_weights_folded_kernel");
 }
 
 extern "C" int skit_pack_conv_weights_padded(const float* w, int co, int ci, int k, int mode, int kpad, void* hi, void* lo, void* stream) {
@@ -624,7 +676,7 @@ extern "C" int skit_dbias(const skit_operand* dy, int dy_org, int ho, int wo, fl
 
 namespace skit {
 int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org, int k, int stride,
-             int ho, int wo, float* partial, int* layout, cudaStream_t st);  // tc_wgrad.cu
+             int ho, int wo, float* partial, int* layout, cudaStream_t st, int kw = 0);  // tc_wgrad.cu
 bool wgrad_tc_eligible(const skit_operand* x, const skit_operand* dy, int k, int stride, int ho, int wo);
 }
 
@@ -704,4 +756,20 @@ extern "C" int skit_conv2d_wgrad_ex(const skit_operand* x, int org, const skit_o
         return check_launch("dbias_kernel");
     }
     return SKIT_OK;
+}
+
+
+extern "C" int skit_conv2d_wgrad_folded(const skit_operand* xf, int org, const skit_operand* dy, int dy_org, int k, int kw, int cp,
+                                        int ho, int wo, float* scratch, float* dw, int co_real, int ci_real, void* stream) {
+    SKIT_REQUIRE(xf && dy && scratch && dw && xf->p0 && xf->p1 && dy->p0 && dy->p1, "conv2d_wgrad_folded: null pointer");
+    SKIT_REQUIRE(xf->fmt == SKIT_FMT_BF16X2 && dy->fmt == SKIT_FMT_BF16X2 && xf->c == 64 && dy->c % 64 == 0, "conv2d_wgrad_folded: needs bf16x2 operands, 64 folded channels");
+    SKIT_REQUIRE(kw * cp <= 64 && ci_real <= cp && co_real <= dy->c && xf->n == dy->n, "conv2d_wgrad_folded: bad fold geometry");
+    cudaStream_t st = as_stream(stream);
+    int layout = 0;
+    int rc = wgrad_tc(xf, org, dy, dy_org, k, 1, ho, wo, scratch, &layout, st, 1);
+    if (rc) return rc;
+    long long total = (long long)co_real * ci_real * k * kw;
+    int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
+    unpack_wgrad_folded_kernel<<<blocks, 256, 0, st>>>(scratch, co_real, ci_real, k, kw, cp, dw, layout, dy->c);
+    return check_launch("unpack_wgrad_folded_kernel");
 }

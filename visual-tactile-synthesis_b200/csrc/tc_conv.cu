@@ -251,10 +251,15 @@ static bool halo_enabled() {
 // k: taps per side of THIS launch; ntaps_total: taps in the packed filter (weight map extent); tap_base: first tap.
 int conv_tc_launch(const skit_operand* x, const void* w_hi, const void* w_lo, int ci, int co, int k, int ntaps_total,
                    int tap_base, int stride, int org, int ho, int wo, const float* bias, float* y, const TcOut* out,
-                   double* stats, int stats_mode, cudaStream_t st) {
+                   double* stats, int stats_mode, cudaStream_t st, int kw = 0) {
     using namespace tc;
+    if (kw <= 0) kw = k;
     if (stride == 1 && halo_enabled())   // halo-tile kernel: every tap re-uses one staged activation tile
-        return conv_tc_halo_launch(x, w_hi, w_lo, ci, co, k, k, ntaps_total, tap_base, org, ho, wo, bias, y, out, stats, stats_mode, st);
+        return conv_tc_halo_launch(x, w_hi, w_lo, ci, co, k, kw, ntaps_total, tap_base, org, ho, wo, bias, y, out, stats, stats_mode, st);
+    if (kw != k) {
+        set_error("conv2d_fwd: rectangular (x-folded) filters need the halo-tile kernel (stride 1, SKIT_TC_HALO != 0)");
+        return SKIT_ERR_UNSUPPORTED;
+    }
     TcConvP p{};
     p.k = k; p.kc = ci / 64; p.org = org; p.stride = stride; p.tap_base = tap_base; p.ho = ho; p.wo = wo; p.co = co;
     p.tw = (wo <= 8) ? 8 : 16; p.th = 128 / p.tw;
@@ -310,8 +315,9 @@ int conv_tc_launch(const skit_operand* x, const void* w_hi, const void* w_lo, in
 
 int conv_fwd_tc(const skit_operand* x, const skit_weights* w, int stride, int org, int ho, int wo,
                 const float* bias, float* y, double* stats, int stats_mode, cudaStream_t st) {
-    return conv_tc_launch(x, w->hi, w->lo, x->c, w->co, w->k, w->k * w->k, 0, stride, org, ho, wo, bias, y, nullptr,
-                          stats, stats_mode, st);
+    const int kw = w->kw > 0 ? w->kw : w->k;
+    return conv_tc_launch(x, w->hi, w->lo, x->c, w->co, w->k, w->k * kw, 0, stride, org, ho, wo, bias, y, nullptr,
+                          stats, stats_mode, st, kw);
 }
 
 int conv_fwd_simt(const skit_operand* x, const skit_weights* w, int stride, int org, int ho, int wo,
@@ -328,7 +334,7 @@ extern "C" int skit_conv2d_fwd(const skit_operand* x, const skit_weights* w, int
     SKIT_REQUIRE(x->fmt == SKIT_FMT_F32 || (x->fmt == SKIT_FMT_BF16X2 && x->p1), "conv2d_fwd: bad operand format");
     SKIT_REQUIRE(w->ci == x->c, "conv2d_fwd: weight ci=%d != operand channels %d", w->ci, x->c);
     SKIT_REQUIRE(stride >= 1 && ho > 0 && wo > 0 && org >= 0, "conv2d_fwd: bad geometry");
-    SKIT_REQUIRE(org + (ho - 1) * stride + w->k <= x->hp && org + (wo - 1) * stride + w->k <= x->wp,
+    SKIT_REQUIRE(org + (ho - 1) * stride + w->k <= x->hp && org + (wo - 1) * stride + (w->kw > 0 ? w->kw : w->k) <= x->wp,
                  "conv2d_fwd: window exceeds the haloed operand (hp=%d wp=%d k=%d stride=%d ho=%d wo=%d org=%d)",
                  x->hp, x->wp, w->k, stride, ho, wo, org);
     SKIT_REQUIRE(stats == nullptr || stats_mode == SKIT_NORM_INSTANCE || stats_mode == SKIT_NORM_BATCH,

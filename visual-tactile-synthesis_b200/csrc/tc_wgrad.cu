@@ -15,7 +15,8 @@ namespace skit {
 namespace tc {
 
 struct TcWgradP {
-    int k;                 // taps per side
+    int k;                 // filter rows
+    int kw;                // filter columns (== k for square filters; 1 for x-folded operands)
     int tiles_x, tiles_y;  // 8x8-pixel tiles per image
     int n_img;
     int tiles_per_cta;     // split-K chunk (in pixel tiles, over all images)
@@ -49,12 +50,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tap = blockIdx.x % (p.k * p.k);
-    const int mt = blockIdx.x / (p.k * p.k);          // 128-row M tile
+    const int tap = blockIdx.x % (p.k * p.kw);
+    const int mt = blockIdx.x / (p.k * p.kw);         // 128-row M tile
     const int n0 = blockIdx.y * BN;
     const int t_beg = blockIdx.z * p.tiles_per_cta;
     const int t_end = min(p.total_tiles, t_beg + p.tiles_per_cta);
-    const int ky = tap / p.k, kx = tap - ky * p.k;
+    const int ky = tap / p.kw, kx = tap - ky * p.kw;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmM_hi); tma_prefetch_desc(&tmM_lo);
@@ -188,11 +189,12 @@ bool wgrad_tc_eligible(const skit_operand* x, const skit_operand* dy, int k, int
 }
 
 int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org, int k, int stride,
-             int ho, int wo, float* partial, int* layout, cudaStream_t st) {
+             int ho, int wo, float* partial, int* layout, cudaStream_t st, int kw = 0) {
     using namespace tc;
     const int ci = x->c, co = dy->c;
     TcWgradP p{};
-    p.k = k;
+    if (kw <= 0) kw = k;
+    p.k = k; p.kw = kw;
     p.tiles_x = cdiv(wo, 8); p.tiles_y = cdiv(ho, 8);
     p.n_img = x->n;
     p.total_tiles = p.tiles_x * p.tiles_y * x->n;
@@ -209,7 +211,7 @@ int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
     *layout = p.m_is_x;
     const int BN = (p.Ndim % 256 == 0) ? 256 : (p.Ndim % 128 == 0) ? 128 : (p.Ndim % 64 == 0) ? 64 : 16;
     const int mtiles = cdiv(p.Mdim, 128), ntiles = cdiv(p.Ndim, BN);
-    const int items = k * k * mtiles * ntiles;
+    const int items = k * kw * mtiles * ntiles;
     // split-K so that one wave of CTAs covers the SMs: every extra split adds a full tile of fp32 atomics to L2
     int splits = max(1, min(items >= 148 ? 1 : 148 / items, p.total_tiles));
     p.tiles_per_cta = cdiv(p.total_tiles, splits);
@@ -220,7 +222,7 @@ int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
     if (rc) return rc;
     rc = encode_act_map(&d_hi, &d_lo, dy, 1);
     if (rc) return rc;
-    dim3 grid(k * k * mtiles, ntiles, splits);
+    dim3 grid(k * kw * mtiles, ntiles, splits);
     const CUtensorMap &mh = p.m_is_x ? x_hi : d_hi, &ml = p.m_is_x ? x_lo : d_lo;
     const CUtensorMap &nh = p.m_is_x ? d_hi : x_hi, &nl = p.m_is_x ? d_lo : x_lo;
     if (BN == 256) return launch_wgrad_tc<256, 2>(mh, ml, nh, nl, p, grid, st);

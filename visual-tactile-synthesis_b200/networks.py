@@ -41,6 +41,8 @@ class Conv2d(nn.Module):
         self.ci, self.co, self.k, self.stride = ci, co, k, stride
         self.allow_tc = True   # the U-Net generator keeps its (mostly thin) layers on the fp32 CUDA-core kernels
         self.tc_thin = False   # stride-1 layer with a thin side (9-channel stem, 5-channel head) routed to the halo tcgen05 kernel
+        self.fold_in_cp = 0    # > 0: forward / wgrad run on the x-folded input operand (k*cp <= 64 channels, filter k x 1)
+        self.fold_out_cp = 0   # > 0: the input gradient runs on the x-folded output-gradient operand
         self.weight = nn.Parameter(torch.empty(co, ci, k, k))
         self.bias = nn.Parameter(torch.zeros(co)) if bias else None
         self.reset_parameters()
@@ -78,7 +80,12 @@ class Conv2d(nn.Module):
             kpad = 0
             if bf16 and self.tc_thin:
                 kpad = self.ci_pad if mode == 0 else self.co_pad
-            pk = ops.PackedWeights(self.weight, mode, want_f32=not bf16, want_bf16=bf16, kpad=kpad)
+            if bf16 and mode == 0 and self.fold_in_cp:
+                pk = ops.PackedWeights(self.weight, 4, want_f32=False, want_bf16=True, cp=self.fold_in_cp)
+            elif bf16 and mode == 1 and self.fold_out_cp:
+                pk = ops.PackedWeights(self.weight, 5, want_f32=False, want_bf16=True, cp=self.fold_out_cp)
+            else:
+                pk = ops.PackedWeights(self.weight, mode, want_f32=not bf16, want_bf16=bf16, kpad=kpad)
             self._packs[mode] = pk
         return pk
 
@@ -243,14 +250,22 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
         # per-channel shift; d_raw sums to zero over the normalised axes) — the reference only accumulates
         # rounding noise there — so its reduction is skipped and the zeroed flat-grad entry stands.
         want_db = layer.bias is not None and (norm_mode == NORM_NONE or draw_add is not None)   # a raw-output tap sees the bias
-        _wgrad_async(lambda: ops.conv2d_wgrad(x_op, 0, d_op, q, layer.k, layer.stride, ho, wo, layer.weight.grad,
-                                              layer.bias.grad if want_db else None), (x_op, d_op))
+        if tc and layer.fold_in_cp:
+            def wg():
+                ops.conv2d_wgrad_folded(x_op, d_op, q, layer.k, layer.k, layer.fold_in_cp, ho, wo, layer.weight.grad)
+                if want_db:
+                    ops.dbias(d_op, q, ho, wo, layer.bias.grad)
+            _wgrad_async(wg, (x_op, d_op))
+        else:
+            _wgrad_async(lambda: ops.conv2d_wgrad(x_op, 0, d_op, q, layer.k, layer.stride, ho, wo, layer.weight.grad,
+                                                  layer.bias.grad if want_db else None), (x_op, d_op))
     if not need_dgrad:
         return None
     if tc and layer.stride == 2:
         return ops.conv2d_dgrad_s2(d_op, q, layer.pack(3), layer.k, ho, wo, x_op.hp, x_op.wp)
     if tc:
-        dx, _ = ops.conv2d_fwd(d_op, layer.pack(1), 1, 0, x_op.hp, x_op.wp)
+        wp_in = x_op.wp + (layer.k - 1 if layer.fold_in_cp else 0)     # a folded operand is k-1 columns narrower than the input
+        dx, _ = ops.conv2d_fwd(d_op, layer.pack(1), 1, 0, x_op.hp, wp_in)
         return dx
     return ops.conv2d_dgrad_gather(d_op.data, layer.pack(2), layer.stride, x_op.hp, x_op.wp)
 
@@ -295,6 +310,10 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         if ngf % 64 == 0:   # tensor-core configuration: the thin 7x7 stem / head convs join the tcgen05 path (channel-padded)
             self._c1.tc_thin = True
             self._out.tc_thin = True
+            if 7 * input_nc <= 64:      # 7x7 stem: fold the filter columns into the channel axis (7 x 64-channel K steps, not 49 thin ones)
+                self._c1.fold_in_cp = input_nc
+            if output_nc <= 8:          # 7x7 head: the same for its input gradient
+                self._out.fold_out_cp = 8
 
     # -- explicit forward.  srcs: list of NCHW fp32 tensors whose channel concat is the input.
     def fwd(self, srcs, mask=None, scale_nz=0.25, save=True, want_normal=True, taps=None, style_code=None):
@@ -308,9 +327,8 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
             if taps is not None and i in taps:
                 feats[i] = fn()
 
-        tc1 = self._c1.use_tc
-        op0 = ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT, fmt=FMT_BF16X2 if tc1 else FMT_F32, cpad=self._c1.ci_pad if tc1 else 0)
-        tap(0, lambda: ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT).data if tc1 else op0.data)
+        op0, thin0 = self._stem_operand(srcs)
+        tap(0, lambda: thin0.data if thin0 is not None else (ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT).data if self._c1.use_tc else op0.data))
         raw1, st = _conv_fwd(self._c1, op0, 0, S_h, S_w, IN)
         mr1 = ops.stats_finalize(st, S_h * S_w)
         tap(1, lambda: raw1)
@@ -372,6 +390,17 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
     def _fmt(layer):
         return FMT_BF16X2 if layer.use_tc else FMT_F32
 
+    def _stem_operand(self, srcs):
+        """Operand of the 7x7 stem conv: reflect-padded channel concat of the NCHW sources -> (operand, thin fp32 operand or
+        None).  Tensor-core path: x-folded bf16x2 (fold_in_cp) or channel-padded bf16x2; otherwise plain fp32."""
+        c1 = self._c1
+        if c1.use_tc and c1.fold_in_cp:
+            thin = ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT)
+            return ops.fold_x(thin, c1.k), thin
+        if c1.use_tc:
+            return ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT, fmt=FMT_BF16X2, cpad=c1.ci_pad), None
+        return ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT), None
+
     def tappable_layers(self):
         """nn.Sequential indices whose output the fused path materialises: padded input, the three
         stem convs (pre-norm) and every ResnetBlock output (CUT's nce_layers 0,4,8,12,16 are included)."""
@@ -388,7 +417,8 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
             d30 = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, q, fmt=FMT_BF16X2, cpad=lo.co_pad)
             op26 = ctx["op26"]
             _wgrad_async(lambda: ops.conv2d_wgrad(op26, 0, d30, q, lo.k, 1, S_h, S_w, lo.weight.grad, lo.bias.grad), (op26, d30))
-            dpad26, _ = ops.conv2d_fwd(d30, lo.pack(1), 1, 0, S_h + 6, S_w + 6)
+            d30f = ops.fold_x(d30, lo.k) if lo.fold_out_cp else d30
+            dpad26, _ = ops.conv2d_fwd(d30f, lo.pack(1), 1, 0, S_h + 6, S_w + 6)
         else:
             d30 = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, 0)
             ops.conv2d_wgrad(ctx["op26"], 0, d30, 0, lo.k, 1, S_h, S_w, lo.weight.grad, lo.bias.grad)
@@ -426,11 +456,10 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         top = layers[-1]
         n, _, S_h, S_w = srcs[0].shape
         feats, ctx = {}, dict(dims=(n, S_h, S_w), top=top)
-        tc1 = self._c1.use_tc
-        op0 = ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT, fmt=FMT_BF16X2 if tc1 else FMT_F32, cpad=self._c1.ci_pad if tc1 else 0)
+        op0, thin0 = self._stem_operand(srcs)
         ctx["op0"] = op0
         if 0 in layers:
-            feats[0] = ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT).data if tc1 else op0.data
+            feats[0] = thin0.data if thin0 is not None else (ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT).data if self._c1.use_tc else op0.data)
         if top == 0:
             return feats, ctx
         raw1, st = _conv_fwd(self._c1, op0, 0, S_h, S_w, IN)

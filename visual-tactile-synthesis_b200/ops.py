@@ -39,26 +39,34 @@ class Operand:
 class PackedWeights:
     """Per-step repack of one conv's reference-layout weight (skit_pack_conv_weights)."""
 
-    def __init__(self, w, mode, want_f32=True, want_bf16=False, kpad=0):
+    def __init__(self, w, mode, want_f32=True, want_bf16=False, kpad=0, cp=0):
         co, ci, k, _ = w.shape
-        self.k, self.mode = k, mode
+        self.k, self.mode, self.cp = k, mode, cp
         # the GEMM reduces over `rci` channels per tap and produces `rco` columns
-        self.rci, self.rco = (ci, co) if mode == 0 else (co, ci)
-        self.kpad = 0
-        if kpad and kpad > self.rci:     # bf16 pack with a zero-padded reduction axis (thin layers on tcgen05)
+        self.rci, self.rco = (ci, co) if mode in (0, 4) else (co, ci)
+        self.kpad, self.kw = 0, 0
+        if mode in (4, 5):               # x-folded bf16 pack [k][N][64]: the filter columns live in the channel axis
+            assert want_bf16 and not want_f32 and cp >= self.rci and k * cp <= 64
+            self.rci, self.kw, self.kpad = 64, 1, 64
+        elif kpad and kpad > self.rci:     # bf16 pack with a zero-padded reduction axis (thin layers on tcgen05)
             assert want_bf16 and not want_f32 and kpad % 8 == 0
             self.kpad, self.rci = kpad, kpad
         dev = w.device
-        self.f32 = torch.empty((k * k * self.rci, self.rco), dtype=torch.float32, device=dev) if want_f32 else None
-        self.hi = torch.empty((k * k, self.rco, self.rci), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+        taps = k if mode in (4, 5) else k * k
+        self.f32 = torch.empty((taps * self.rci, self.rco), dtype=torch.float32, device=dev) if want_f32 else None
+        self.hi = torch.empty((taps, self.rco, self.rci), dtype=torch.bfloat16, device=dev) if want_bf16 else None
         self.lo = torch.empty_like(self.hi) if want_bf16 else None
         self.co, self.ci = co, ci
         self.struct = L.SkitWeights(self.f32.data_ptr() if want_f32 else None,
                                     self.hi.data_ptr() if want_bf16 else None,
-                                    self.lo.data_ptr() if want_bf16 else None, k, self.rci, self.rco)
+                                    self.lo.data_ptr() if want_bf16 else None, k, self.rci, self.rco, self.kw)
         self.refresh(w)
 
     def refresh(self, w):
+        if self.mode in (4, 5):
+            L.call("skit_pack_conv_weights_folded", _p(w.detach()), self.co, self.ci, self.k, self.mode, self.cp,
+                   _p(self.hi), _p(self.lo), L.stream())
+            return
         if self.kpad:
             L.call("skit_pack_conv_weights_padded", _p(w.detach()), self.co, self.ci, self.k, self.mode, self.kpad,
                    _p(self.hi), _p(self.lo), L.stream())
@@ -74,10 +82,10 @@ class PackedWeights:
         return L.SkitPackDesc(w.data_ptr(), self.f32.data_ptr() if self.f32 is not None else None,
                               self.hi.data_ptr() if self.hi is not None else None,
                               self.lo.data_ptr() if self.lo is not None else None, start,
-                              self.co, self.ci, self.k, self.mode, self.kpad, 0)
+                              self.co, self.ci, self.k, self.mode, self.kpad, self.cp)
 
     def numel(self):
-        return self.k * self.k * self.rco * self.rci
+        return (self.k if self.mode in (4, 5) else self.k * self.k) * self.rco * self.rci
 
 
 class PackTable:
@@ -132,6 +140,21 @@ def conv2d_wgrad(x, org, dy, dy_org, k, stride, ho, wo, dw, dbias=None, impl=IMP
     co, ci = dy.c, x.c
     scratch = torch.zeros((k * k * ci * co,), dtype=torch.float32, device=x.data.device)
     L.call("skit_conv2d_wgrad_ex", x.ref(), org, dy.ref(), dy_org, k, stride, ho, wo, _p(scratch), _p(dw), _p(dbias), impl,
+           int(dw.shape[0]), int(dw.shape[1]), L.stream())
+
+
+def fold_x(thin, kw):
+    """thin: haloed Operand with few channels -> bf16x2 Operand [n, hp, wp-kw+1, 64] whose channel axis holds the kw shifted
+    copies (skit_fold_x_operand): a (k x kw) conv over `thin` = a (k x 1) conv over the result with a folded pack."""
+    f = Operand(thin.n, thin.hp, thin.wp - kw + 1, 64, 0, FMT_BF16X2, thin.data.device)
+    L.call("skit_fold_x_operand", thin.ref(), kw, f.ref(), L.stream())
+    return f
+
+
+def conv2d_wgrad_folded(xf, dy, dy_org, k, kw, cp, ho, wo, dw):
+    """Weight gradient against an x-folded input operand; accumulates into dw [co][ci][k][kw]."""
+    scratch = torch.zeros((k * 64 * dy.c,), dtype=torch.float32, device=xf.data.device)
+    L.call("skit_conv2d_wgrad_folded", xf.ref(), 0, dy.ref(), dy_org, k, kw, cp, ho, wo, _p(scratch), _p(dw),
            int(dw.shape[0]), int(dw.shape[1]), L.stream())
 
 
