@@ -478,41 +478,54 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci,
 }
 
 // One launch for every pack of a net: `descs` (device) lists the packs with their prefix offsets into a single index space.
+// A block owns a contiguous chunk of that space: one descriptor search per chunk, then it only steps forward.
+constexpr int kPackChunk = 4096;
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const skit_pack_desc* __restrict__ descs, int n, long long total) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int lo = 0, hi = n - 1;
-        while (lo < hi) {   // last descriptor whose start <= i
-            const int mid = (lo + hi + 1) >> 1;
-            if (descs[mid].start <= i) lo = mid; else hi = mid - 1;
+    __shared__ int s_first;
+    for (long long base = (long long)blockIdx.x * kPackChunk; base < total; base += (long long)gridDim.x * kPackChunk) {
+        if (threadIdx.x == 0) {
+            int lo = 0, hi = n - 1;
+            while (lo < hi) {   // last descriptor whose start <= base
+                const int mid = (lo + hi + 1) >> 1;
+                if (descs[mid].start <= base) lo = mid; else hi = mid - 1;
+            }
+            s_first = lo;
         }
-        const skit_pack_desc d = descs[lo];
-        const long long j = i - d.start;
-        const int mode = d.mode, k = d.k, co = d.co, ci = d.ci;
-        if (mode >= 4) {   // x-folded bf16 pack [ky][N][64]; d.reserved = channels per folded column
-            const int Nd4 = mode == 4 ? co : ci;
-            const int jj = (int)(j % 64); long long t4 = j / 64;
-            const int nn4 = (int)(t4 % Nd4); const int ky4 = (int)(t4 / Nd4);
-            __nv_bfloat16 h4, l4;
-            split_bf16(folded_pack_value(d.w, mode, k, co, ci, d.reserved, ky4, nn4, jj), h4, l4);
-            ((__nv_bfloat16*)d.hi)[j] = h4; ((__nv_bfloat16*)d.lo)[j] = l4;
-            continue;
+        __syncthreads();
+        int di = s_first;
+        const long long end = min(total, base + kPackChunk);
+        for (long long i = base + threadIdx.x; i < end; i += 256) {
+            while (di + 1 < n && descs[di + 1].start <= i) di++;
+            const skit_pack_desc& d = descs[di];
+            const long long j = i - d.start;
+            const int mode = d.mode, k = d.k, co = d.co, ci = d.ci;
+            if (mode >= 4) {   // x-folded bf16 pack [ky][N][64]; d.reserved = channels per folded column
+                const int Nd4 = mode == 4 ? co : ci;
+                const int jj = (int)(j % 64); long long t4 = j / 64;
+                const int nn4 = (int)(t4 % Nd4); const int ky4 = (int)(t4 / Nd4);
+                __nv_bfloat16 h4, l4;
+                split_bf16(folded_pack_value(d.w, mode, k, co, ci, d.reserved, ky4, nn4, jj), h4, l4);
+                ((__nv_bfloat16*)d.hi)[j] = h4; ((__nv_bfloat16*)d.lo)[j] = l4;
+                continue;
+            }
+            const int Kd = mode == 0 ? ci : co, Nd = mode == 0 ? co : ci;
+            if (d.hi) {   // bf16 hi/lo [tap][N][Kp]
+                const int Kp = d.kpad > Kd ? d.kpad : Kd;
+                const int kk = (int)(j % Kp); long long t = j / Kp;
+                const int nn = (int)(t % Nd); const int tap = (int)(t / Nd);
+                const int o = mode == 0 ? nn : kk, c = mode == 0 ? kk : nn;
+                const float v = kk < Kd ? __ldg(d.w + pack_src_index(mode, k, co, ci, tap, o, c)) : 0.f;
+                __nv_bfloat16 h, l;
+                split_bf16(v, h, l);
+                ((__nv_bfloat16*)d.hi)[j] = h; ((__nv_bfloat16*)d.lo)[j] = l;
+            } else {      // fp32 [tap][K][N]
+                const int nn = (int)(j % Nd); long long t = j / Nd;
+                const int kk = (int)(t % Kd); const int tap = (int)(t / Kd);
+                const int o = mode == 0 ? nn : kk, c = mode == 0 ? kk : nn;
+                d.f32[j] = __ldg(d.w + pack_src_index(mode, k, co, ci, tap, o, c));
+            }
         }
-        const int Kd = mode == 0 ? ci : co, Nd = mode == 0 ? co : ci;
-        if (d.hi) {   // bf16 hi/lo [tap][N][Kp]
-            const int Kp = d.kpad > Kd ? d.kpad : Kd;
-            const int kk = (int)(j % Kp); long long t = j / Kp;
-            const int nn = (int)(t % Nd); const int tap = (int)(t / Nd);
-            const int o = mode == 0 ? nn : kk, c = mode == 0 ? kk : nn;
-            const float v = kk < Kd ? __ldg(d.w + pack_src_index(mode, k, co, ci, tap, o, c)) : 0.f;
-            __nv_bfloat16 h, l;
-            split_bf16(v, h, l);
-            ((__nv_bfloat16*)d.hi)[j] = h; ((__nv_bfloat16*)d.lo)[j] = l;
-        } else {      // fp32 [tap][K][N]
-            const int nn = (int)(j % Nd); long long t = j / Nd;
-            const int kk = (int)(t % Kd); const int tap = (int)(t / Kd);
-            const int o = mode == 0 ? nn : kk, c = mode == 0 ? kk : nn;
-            d.f32[j] = __ldg(d.w + pack_src_index(mode, k, co, ci, tap, o, c));
-        }
+        __syncthreads();
     }
 }
 
@@ -581,7 +594,7 @@ extern "C" int skit_pack_conv_weights(const float* w, int co, int ci, int k, int
 
 extern "C" int skit_pack_conv_weights_batched(const skit_pack_desc* descs_dev, int n, long long total, void* stream) {
     SKIT_REQUIRE(descs_dev && n > 0 && total > 0, "pack_conv_weights_batched: bad arguments");
-    int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
+    int blocks = (int)min((long long)148 * 8, cdivll(total, kPackChunk));
     pack_weights_batched_kernel<<<blocks, 256, 0, as_stream(stream)>>>(descs_dev, n, total);
     return check_launch("pack_weights_batched_kernel");
 }

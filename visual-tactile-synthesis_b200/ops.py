@@ -14,6 +14,49 @@ from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, FMT_BF16X2, FMT_F32, IMPL_AUTO
 _p = L.ptr
 
 
+class ZeroArena:
+    """Zero-initialised small scratch of one train step (norm statistics of every conv, the sums of every norm backward):
+    ~170 tiny memsets on the critical path become one.  (The split-K partials of the weight gradients are large and
+    live on the side stream: they keep their own memsets.)  Slices are bump-allocated in launch order — deterministic from
+    step to step — and `begin()` clears exactly the bytes the previous step used; a slice beyond that mark is cleared
+    on its own.  Only active inside SinSKITGModel._step_body; everywhere else `zeros()` is torch.zeros."""
+
+    def __init__(self, device, nbytes=8 << 20):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.off, self.clean, self.high = 0, 0, 0
+
+    def begin(self):
+        if self.high:
+            self.buf[:self.high].view(torch.float32).zero_()
+        self.clean, self.off = self.high, 0
+
+    def take(self, shape, dtype):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        start, end = self.off, self.off + ((nbytes + 255) // 256) * 256
+        if end > self.buf.numel():
+            return None
+        view = self.buf[start:start + nbytes].view(dtype).view(shape)
+        if end > self.clean:
+            view.zero_()
+        self.off = end
+        self.high = max(self.high, end)
+        return view
+
+
+ARENA = None   # the active ZeroArena (set by the model around a train step)
+
+
+def zeros(shape, dtype, device):
+    if ARENA is not None:
+        t = ARENA.take(tuple(shape), dtype)
+        if t is not None:
+            return t
+    return torch.zeros(tuple(shape), dtype=dtype, device=device)
+
+
 class Operand:
     """A haloed NHWC conv operand on the device (fp32, or bf16 hi/lo planes for tcgen05)."""
 
@@ -115,7 +158,7 @@ def conv2d_fwd(x, w, stride, org, ho, wo, bias=None, stats_mode=NORM_NONE, impl=
     stats = None
     if stats_mode != NORM_NONE:
         groups = x.n if stats_mode == NORM_INSTANCE else 1
-        stats = torch.zeros((groups, co, 2), dtype=torch.float64, device=dev)
+        stats = zeros((groups, co, 2), torch.float64, dev)
     L.call("skit_conv2d_fwd", x.ref(), w.ref(), stride, org, ho, wo, _p(bias), _p(y), _p(stats), stats_mode, impl, L.stream())
     return y, stats
 
@@ -138,7 +181,7 @@ def conv2d_wgrad(x, org, dy, dy_org, k, stride, ho, wo, dw, dbias=None, impl=IMP
     """Accumulates into dw ([co][ci][k][k] view of the flat grad bucket) and dbias.  Operands may carry zero padding
     channels beyond dw's real (co, ci)."""
     co, ci = dy.c, x.c
-    scratch = torch.zeros((k * k * ci * co,), dtype=torch.float32, device=x.data.device)
+    scratch = torch.zeros((k * k * ci * co,), dtype=torch.float32, device=x.data.device)   # big, and off the critical path
     L.call("skit_conv2d_wgrad_ex", x.ref(), org, dy.ref(), dy_org, k, stride, ho, wo, _p(scratch), _p(dw), _p(dbias), impl,
            int(dw.shape[0]), int(dw.shape[1]), L.stream())
 
@@ -184,7 +227,7 @@ def act_norm_bwd_reduce(shape, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None, r
     g = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
     sums = None
     if norm_mode != NORM_NONE:
-        sums = torch.zeros((n if norm_mode == NORM_INSTANCE else 1, c, 2), dtype=torch.float64, device=dev)
+        sums = zeros((n if norm_mode == NORM_INSTANCE else 1, c, 2), torch.float64, dev)
     L.call("skit_act_norm_bwd_reduce", _p(dpad), pad, pad_mode, _p(dadd), _p(raw), n, h, w, c, _p(mr), norm_mode,
            _p(gamma), _p(beta), act, _p(g), _p(sums), L.stream())
     return g, sums
@@ -205,7 +248,7 @@ def act_norm_bwd_reduce_ex(shape, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None
     g = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
     sums = None
     if norm_mode != NORM_NONE:
-        sums = torch.zeros((n if norm_mode == NORM_INSTANCE else 1, c, 2), dtype=torch.float64, device=dev)
+        sums = zeros((n if norm_mode == NORM_INSTANCE else 1, c, 2), torch.float64, dev)
     L.call("skit_act_norm_bwd_reduce_ex", _p(dpad), pad, pad_mode, _p(dadd), _p(dadd2), dadd_c0,
            c if dadd_ctot is None else dadd_ctot, int(dadd_relu_mask), _p(raw), n, h, w, c, _p(mr), norm_mode,
            None, None, act, _p(g), _p(sums), L.stream())
@@ -220,7 +263,7 @@ def conv_transpose2d_fwd(x, wg, stride, pad, bias=None, stats_mode=NORM_NONE, ou
     y = out if out is not None else torch.empty((n, ho, wo, co), dtype=torch.float32, device=x.device)
     stats = None
     if stats_mode != NORM_NONE:
-        stats = torch.zeros((n if stats_mode == NORM_INSTANCE else 1, co, 2), dtype=torch.float64, device=x.device)
+        stats = zeros((n if stats_mode == NORM_INSTANCE else 1, co, 2), torch.float64, x.device)
     L.call("skit_conv_transpose2d_fwd", _p(x), n, h, w, ci, wg.ref(), stride, pad, ho, wo, _p(bias), _p(y), y.shape[3], out_c0,
            _p(stats), stats_mode, L.stream())
     return y, stats

@@ -380,6 +380,16 @@ class SinSKITGModel:
         net.bwd(ctx, self._gan(preds, sign, slot, gscale))
 
     def _step_body(self):
+        if getattr(self, "_arena", None) is None:
+            self._arena = ops.ZeroArena(self.device)
+        ops.ARENA = self._arena
+        self._arena.begin()
+        try:
+            return self._step_body_inner()
+        finally:
+            ops.ARENA = None
+
+    def _step_body_inner(self):
         """All device work of one train step; reads only persistent device buffers (graph-capturable).
         Dependency structure used for overlap: the real-data passes of D and D2 do not depend on the generator, the
         D2 passes do not depend on D, and nothing but the optimiser consumes weight gradients.  BatchNorm running
