@@ -43,6 +43,13 @@ extern "C" {
 #define SKIT_NORM_INSTANCE 1 /* statistics per (n, c) */
 #define SKIT_NORM_BATCH 2    /* statistics per c over (n, h, w) */
 
+/* The (sum g, sum g*xhat) buffers of the norm backward hold this many replicas, [R][groups][c][2] doubles: a producer CTA adds
+ * into replica (its index mod R), consumers add the replicas up.  Hundreds of CTAs hitting the same few hundred fp64
+ * addresses serialise in L2 (measured: 25 of 39 us of the phase-A kernel at the trunk shape); R copies divide that.
+ * Full layout in doubles: [R][groups][c][2] partial sums | [groups][c] finals (two floats: sum/count each) | 1 ticket slot —
+ * (2R + 1) * groups * c + 1 doubles, zeroed by the caller; the last CTA of phase A writes the finals phase B reads. */
+#define SKIT_SUM_REPLICAS 8
+
 #define SKIT_IMPL_AUTO 0
 #define SKIT_IMPL_SIMT 1
 #define SKIT_IMPL_TC 2 /* tcgen05 + TMA; fails with SKIT_ERR_UNSUPPORTED if the shape is not eligible */
@@ -197,7 +204,7 @@ int skit_norm_act_pad_ex(const float* raw, int n, int h, int w, int c,
 /* Backward, phase A: fold the halo gradient back (adjoint of the padding), add an optional dense
  * gradient, apply act', and reduce the two norm-backward sums.
  *   g = act'(pre) * ( fold(dpad) + dadd ),  pre = norm(raw)*gamma+beta
- *   sums[group][c][0] += sum g ; sums[group][c][1] += sum g * xhat        (double)
+ *   sums[r][group][c][0] += sum g ; sums[r][group][c][1] += sum g * xhat   (double; r = one of SKIT_SUM_REPLICAS copies)
  * dpad: NHWC fp32 [n][h+2pad][w+2pad][c] or NULL; dadd: NHWC fp32 [n][h][w][c] or NULL. */
 int skit_act_norm_bwd_reduce(const float* dpad, int pad, int pad_mode, const float* dadd,
                              const float* raw, int n, int h, int w, int c,

@@ -56,3 +56,12 @@ def test_sass_is_blackwell_native(lib_path):
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in sass
+
+
+def test_python_constants_match_header():
+    """Constants the Python host mirrors from include/skit_b200.h."""
+    import re
+    import vts_b200
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "skit_b200.h")).read()
+    m = re.search(r"#define\s+SKIT_SUM_REPLICAS\s+(\d+)", hdr)
+    assert m and int(m.group(1)) == vts_b200.ops.SUM_REPLICAS

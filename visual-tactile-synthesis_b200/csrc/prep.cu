@@ -208,6 +208,32 @@ __global__ void __launch_bounds__(256) fold_x_kernel(FoldP p) {
 }
 
 // ------------------------------------------------------------------------------ backward phase A
+// Layout of a `sums` buffer (doubles): [R][G][C][2] partial sums | [G][C] float2 finals (sum/count, packed in one double
+// slot each) | 1 slot holding the int ticket counter.  The last CTA of the phase-A kernel adds the replicas up and writes
+// the finals, so phase B reads two floats per channel and does no fp64 arithmetic at all.
+__host__ __device__ inline long long sums_finals_offset(int groups, int c) { return (long long)SKIT_SUM_REPLICAS * groups * c * 2; }
+__host__ __device__ inline long long sums_counter_offset(int groups, int c) { return sums_finals_offset(groups, c) + (long long)groups * c; }
+
+__device__ inline void sums_last_block_finalize(double* sums, int groups, int c, double inv_count, unsigned total_blocks) {
+    __shared__ unsigned s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(reinterpret_cast<unsigned*>(sums + sums_counter_offset(groups, c)), 1u);
+    __syncthreads();
+    if (s_ticket != total_blocks - 1) return;
+    __threadfence();
+    float2* fin = reinterpret_cast<float2*>(sums + sums_finals_offset(groups, c));
+    const long long rstride = (long long)groups * c * 2;
+    for (int i = threadIdx.x; i < groups * c; i += blockDim.x) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int r = 0; r < SKIT_SUM_REPLICAS; r++) {
+            a0 += __ldcg(sums + r * rstride + 2 * i);
+            a1 += __ldcg(sums + r * rstride + 2 * i + 1);
+        }
+        fin[i] = make_float2((float)(a0 * inv_count), (float)(a1 * inv_count));
+    }
+}
+
 struct BwdAP {
     const float* dpad; int pad, pad_mode;
     const float* dadd;
@@ -220,6 +246,7 @@ struct BwdAP {
     float* g;
     double* sums;
     int chunk;  // pixels per block
+    double inv_count;   // 1 / (elements per statistics group)
 };
 
 // number of halo positions that alias source coordinate y on an axis of length len (reflect): returns
@@ -313,10 +340,12 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_kernel(BwdAP p) {
     __syncthreads();
     if (p.sums) {
         for (int t = threadIdx.x; t < lanes_c * VEC; t += 256) {
-            double* dst = p.sums + ((long long)(p.per_n ? n : 0) * p.c + t) * 2;
+            const long long rep = (long long)(blockIdx.x % SKIT_SUM_REPLICAS) * (p.per_n ? p.n : 1) * p.c * 2;
+            double* dst = p.sums + rep + ((long long)(p.per_n ? n : 0) * p.c + t) * 2;
             atomicAdd(dst, (double)red[t * 2]);
             atomicAdd(dst + 1, (double)red[t * 2 + 1]);
         }
+        sums_last_block_finalize(p.sums, p.per_n ? p.n : 1, p.c, p.inv_count, gridDim.x * gridDim.y);
     }
 }
 
@@ -345,44 +374,61 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, 
         const int ny = p.dpad ? fold_coords(y, p.pad, p.h, p.pad_mode, ys) : 0;
         const long long srow = ((long long)n * p.h + y) * p.w;
         const int xend = min(p.w, (int)(blockIdx.z + 1) * xseg);
-        for (int x = blockIdx.z * xseg + pl; x < xend; x += PL) {
-            const long long src = (srow + x) * p.c + ch;
-            float4 d = make_float4(0, 0, 0, 0);
-            if (p.dadd) {
-                const long long dsrc = (srow + x) * p.dctot + p.dc0 + ch;
-                d = *reinterpret_cast<const float4*>(p.dadd + dsrc);
-                if (p.dadd2) {
-                    const float4 e = *reinterpret_cast<const float4*>(p.dadd2 + dsrc);
-                    d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
-                }
-            }
-            float4 rw = make_float4(0, 0, 0, 0);
-            if (p.raw) rw = *reinterpret_cast<const float4*>(p.raw + src);
-            const float r4[4] = {rw.x, rw.y, rw.z, rw.w};
-            float xhat[4], pre[4];
+        for (int x0 = blockIdx.z * xseg + pl; x0 < xend; x0 += 4 * PL) {
+            // 4 pixels per pass: every independent 16-byte load is issued before the first use
+            float4 d[4], rw[4], q0[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { xhat[j] = (r4[j] - mean[j]) * rstd[j]; pre[j] = xhat[j] * gam[j] + bet[j]; }
-            float dv[4] = {d.x, d.y, d.z, d.w};
-            if (p.dmask) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) if (!(pre[j] > 0.f)) dv[j] = 0.f;
-            }
-            if (p.dpad) {
-                int xs[3];
-                const int nx = fold_coords(x, p.pad, p.w, p.pad_mode, xs);
-                for (int a = 0; a < ny; a++)
-                    for (int b = 0; b < nx; b++) {
-                        const float4 q = *reinterpret_cast<const float4*>(p.dpad + (((long long)n * hp + ys[a]) * wp + xs[b]) * p.c + ch);
-                        dv[0] += q.x; dv[1] += q.y; dv[2] += q.z; dv[3] += q.w;
+            for (int u = 0; u < 4; u++) {
+                const int x = x0 + u * PL;
+                const bool ok = x < xend;
+                d[u] = make_float4(0, 0, 0, 0); rw[u] = d[u]; q0[u] = d[u];
+                if (!ok) continue;
+                if (p.dadd) {
+                    const long long dsrc = (srow + x) * p.dctot + p.dc0 + ch;
+                    d[u] = *reinterpret_cast<const float4*>(p.dadd + dsrc);
+                    if (p.dadd2) {
+                        const float4 e = *reinterpret_cast<const float4*>(p.dadd2 + dsrc);
+                        d[u].x += e.x; d[u].y += e.y; d[u].z += e.z; d[u].w += e.w;
                     }
+                }
+                if (p.raw) rw[u] = *reinterpret_cast<const float4*>(p.raw + (srow + x) * p.c + ch);
+                if (p.dpad) q0[u] = *reinterpret_cast<const float4*>(p.dpad + (((long long)n * hp + ys[0]) * wp + x + p.pad) * p.c + ch);
             }
-            float go[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                go[j] = act_grad(pre[j], p.act) * dv[j];
-                s0[j] += go[j]; s1[j] = fmaf(go[j], xhat[j], s1[j]);
+            for (int u = 0; u < 4; u++) {
+                const int x = x0 + u * PL;
+                if (x >= xend) continue;
+                const long long src = (srow + x) * p.c + ch;
+                const float r4[4] = {rw[u].x, rw[u].y, rw[u].z, rw[u].w};
+                float xhat[4], pre[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { xhat[j] = (r4[j] - mean[j]) * rstd[j]; pre[j] = xhat[j] * gam[j] + bet[j]; }
+                float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+                if (p.dmask) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (!(pre[j] > 0.f)) dv[j] = 0.f;
+                }
+                if (p.dpad) {
+                    dv[0] += q0[u].x; dv[1] += q0[u].y; dv[2] += q0[u].z; dv[3] += q0[u].w;   // the interior position (ys[0], x + pad)
+                    int xs[3];
+                    const int nx = fold_coords(x, p.pad, p.w, p.pad_mode, xs);
+                    if (ny > 1 || nx > 1) {     // border pixels also collect their reflected halo positions
+                        for (int a = 0; a < ny; a++)
+                            for (int b = 0; b < nx; b++) {
+                                if (a == 0 && b == 0) continue;
+                                const float4 q = *reinterpret_cast<const float4*>(p.dpad + (((long long)n * hp + ys[a]) * wp + xs[b]) * p.c + ch);
+                                dv[0] += q.x; dv[1] += q.y; dv[2] += q.z; dv[3] += q.w;
+                            }
+                    }
+                }
+                float go[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    go[j] = act_grad(pre[j], p.act) * dv[j];
+                    s0[j] += go[j]; s1[j] = fmaf(go[j], xhat[j], s1[j]);
+                }
+                *reinterpret_cast<float4*>(p.g + src) = make_float4(go[0], go[1], go[2], go[3]);
             }
-            *reinterpret_cast<float4*>(p.g + src) = make_float4(go[0], go[1], go[2], go[3]);
         }
     }
     if (p.sums) {
@@ -397,11 +443,13 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, 
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                double* dst = p.sums + ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
+                const long long rep = (long long)((blockIdx.x + 3 * blockIdx.z) % SKIT_SUM_REPLICAS) * (p.per_n ? p.n : 1) * p.c * 2;
+                double* dst = p.sums + rep + ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
                 atomicAdd(dst, (double)t0[j]);
                 atomicAdd(dst + 1, (double)t1[j]);
             }
         }
+        sums_last_block_finalize(p.sums, p.per_n ? p.n : 1, p.c, p.inv_count, gridDim.x * gridDim.y * gridDim.z);
     }
 }
 
@@ -440,7 +488,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(BwdBP p) {
                     const long long gi = ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
                     const float mean = p.mr[gi], rstd = p.mr[gi + 1];
                     const float xhat = (p.raw[src + j] - mean) * rstd;
-                    const float m0 = (float)(p.sums[gi] * p.inv_count), m1 = (float)(p.sums[gi + 1] * p.inv_count);
+                    const float2 fm = reinterpret_cast<const float2*>(p.sums + sums_finals_offset(p.per_n ? p.n : 1, p.c))[gi / 2];
+                    const float m0 = fm.x, m1 = fm.y;
                     const float gam = p.gamma ? p.gamma[ch + j] : 1.f;
                     gg = gam * rstd * (gg - m0 - xhat * m1);
                 }
@@ -482,7 +531,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_rows_kernel(BwdBP p, int c
         for (int j = 0; j < 4; j++) {
             const long long gi = ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
             mean[j] = p.mr[gi]; rstd[j] = p.mr[gi + 1];
-            m0[j] = (float)(p.sums[gi] * p.inv_count); m1[j] = (float)(p.sums[gi + 1] * p.inv_count);
+            const float2 fm = reinterpret_cast<const float2*>(p.sums + sums_finals_offset(p.per_n ? p.n : 1, p.c))[gi / 2];
+            m0[j] = fm.x; m1[j] = fm.y;
             if (p.gamma) gam[j] = p.gamma[ch + j];
         }
     }
@@ -535,11 +585,12 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_rows_kernel(BwdBP p, int c
     }
 }
 
-__global__ void bn_param_grad_kernel(const double* sums, int c, float* dgamma, float* dbeta) {
+__global__ void bn_param_grad_kernel(const double* sums, int c, float count, float* dgamma, float* dbeta) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
-    if (dbeta) atomicAdd(dbeta + i, (float)sums[2 * i]);
-    if (dgamma) atomicAdd(dgamma + i, (float)sums[2 * i + 1]);
+    const float2 fm = reinterpret_cast<const float2*>(sums + sums_finals_offset(1, c))[i];   // (S0, S1) / count
+    if (dbeta) atomicAdd(dbeta + i, fm.x * count);
+    if (dgamma) atomicAdd(dgamma + i, fm.y * count);
 }
 
 // ------------------------------------------------------------------------------ blur resamplers
@@ -799,6 +850,7 @@ extern "C" int skit_act_norm_bwd_reduce_ex(const float* dpad, int pad, int pad_m
     p.raw = raw; p.n = n; p.h = h; p.w = w; p.c = c;
     p.mr = mean_rstd; p.per_n = norm_mode == SKIT_NORM_INSTANCE; p.gamma = gamma; p.beta = beta;
     p.act = act; p.g = g; p.sums = sums;
+    p.inv_count = 1.0 / ((double)h * w * (norm_mode == SKIT_NORM_BATCH ? n : 1));
     const int P = h * w;
     if (rows_layout_ok(c) && dadd_c0 % 4 == 0 && dadd_ctot % 4 == 0) {
         const int rpb = rows_per_block_for(h, n);
@@ -867,7 +919,7 @@ extern "C" int skit_norm_bwd_apply_ex(const float* g, const float* raw, int n, i
     rc = check_launch("norm_bwd_apply_kernel");
     if (rc) return rc;
     if (norm_mode == SKIT_NORM_BATCH && (dgamma || dbeta)) {
-        bn_param_grad_kernel<<<cdiv(c, 128), 128, 0, as_stream(stream)>>>(sums, c, dgamma, dbeta);
+        bn_param_grad_kernel<<<cdiv(c, 128), 128, 0, as_stream(stream)>>>(sums, c, (float)count, dgamma, dbeta);
         return check_launch("bn_param_grad_kernel");
     }
     return SKIT_OK;

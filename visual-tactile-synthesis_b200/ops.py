@@ -46,6 +46,7 @@ class ZeroArena:
         return view
 
 
+SUM_REPLICAS = 8   # SKIT_SUM_REPLICAS of include/skit_b200.h (tests/test_abi.py checks the two agree)
 ARENA = None   # the active ZeroArena (set by the model around a train step)
 
 
@@ -227,7 +228,7 @@ def act_norm_bwd_reduce(shape, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None, r
     g = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
     sums = None
     if norm_mode != NORM_NONE:
-        sums = zeros((n if norm_mode == NORM_INSTANCE else 1, c, 2), torch.float64, dev)
+        sums = zeros(((2 * SUM_REPLICAS + 1) * (n if norm_mode == NORM_INSTANCE else 1) * c + 1,), torch.float64, dev)
     L.call("skit_act_norm_bwd_reduce", _p(dpad), pad, pad_mode, _p(dadd), _p(raw), n, h, w, c, _p(mr), norm_mode,
            _p(gamma), _p(beta), act, _p(g), _p(sums), L.stream())
     return g, sums
@@ -248,7 +249,7 @@ def act_norm_bwd_reduce_ex(shape, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None
     g = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
     sums = None
     if norm_mode != NORM_NONE:
-        sums = zeros((n if norm_mode == NORM_INSTANCE else 1, c, 2), torch.float64, dev)
+        sums = zeros(((2 * SUM_REPLICAS + 1) * (n if norm_mode == NORM_INSTANCE else 1) * c + 1,), torch.float64, dev)
     L.call("skit_act_norm_bwd_reduce_ex", _p(dpad), pad, pad_mode, _p(dadd), _p(dadd2), dadd_c0,
            c if dadd_ctot is None else dadd_ctot, int(dadd_relu_mask), _p(raw), n, h, w, c, _p(mr), norm_mode,
            None, None, act, _p(g), _p(sums), L.stream())
