@@ -356,7 +356,8 @@ extern "C" int skit_conv2d_dgrad_s2(const skit_operand* dy, int dy_pad, const sk
                                     int ho, int wo, int hp, int wp_, float* dx, void* stream) {
     SKIT_REQUIRE(dy && wp && dx && dy->p0 && dy->p1 && wp->hi && wp->lo, "conv2d_dgrad_s2: null pointer");
     SKIT_REQUIRE(dy->fmt == SKIT_FMT_BF16X2 && k % 2 == 0 && dy_pad == k / 2 - 1, "conv2d_dgrad_s2: needs a bf16x2 dy operand with halo k/2-1");
-    SKIT_REQUIRE(dy->c % 64 == 0 && wp->co % 64 == 0 && wp->ci == dy->c, "conv2d_dgrad_s2: channel counts must be multiples of 64");
+    SKIT_REQUIRE(dy->c % 64 == 0 && wp->ci == dy->c && (wp->co % 64 == 0 || halo_enabled()),
+                 "conv2d_dgrad_s2: the gradient's channels must be a multiple of 64 (and so the input's, without the halo kernel)");
     SKIT_REQUIRE(dy->hp == ho + 2 * dy_pad && dy->wp == wo + 2 * dy_pad, "conv2d_dgrad_s2: dy operand dims mismatch");
     const int kh = k / 2;
     for (int py = 0; py < 2; py++)

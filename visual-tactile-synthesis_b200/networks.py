@@ -43,6 +43,8 @@ class Conv2d(nn.Module):
         self.tc_thin = False   # stride-1 layer with a thin side (9-channel stem, 5-channel head) routed to the halo tcgen05 kernel
         self.fold_in_cp = 0    # > 0: forward / wgrad run on the x-folded input operand (k*cp <= 64 channels, filter k x 1)
         self.fold_out_cp = 0   # > 0: the input gradient runs on the x-folded output-gradient operand
+        self.tc_dgrad_s2 = False   # stride-2 layer with a thin input (PatchGAN stem 4/7 -> 64): only its INPUT GRADIENT runs on
+                                   # tcgen05 (four parity sub-convolutions, K = co = 64, N = ci), forward and wgrad stay fp32
         self.weight = nn.Parameter(torch.empty(co, ci, k, k))
         self.bias = nn.Parameter(torch.zeros(co)) if bias else None
         self.reset_parameters()
@@ -76,7 +78,7 @@ class Conv2d(nn.Module):
         """mode 0 forward, 1 stride-1 dgrad (tensor-core), 2 gather dgrad (CUDA-core), 3 stride-2 phase dgrad (tensor-core)."""
         pk = self._packs.get(mode)
         if pk is None:
-            bf16 = self.use_tc and mode in (0, 1, 3)
+            bf16 = (self.use_tc and mode in (0, 1, 3)) or (self.tc_dgrad_s2 and mode == 3)
             kpad = 0
             if bf16 and self.tc_thin:
                 kpad = self.ci_pad if mode == 0 else self.co_pad
@@ -242,9 +244,10 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
         dadd = torch.zeros_like(raw)
     g, sums = ops.act_norm_bwd_reduce(raw.shape, dpad, pad, pad_mode, dadd, raw, mr, norm_mode, gamma, beta, act)
     tc = layer.use_tc
-    q = 0 if (not tc or not need_dgrad) else (layer.k - 1 if layer.stride == 1 else layer.k // 2 - 1)
+    s2_only = (not tc) and need_dgrad and layer.tc_dgrad_s2 and TC_ENABLED and co % 64 == 0
+    q = 0 if (not (tc or s2_only) or not need_dgrad) else (layer.k - 1 if layer.stride == 1 else layer.k // 2 - 1)
     d_op = ops.norm_bwd_apply(g, raw, mr, norm_mode, gamma, sums, count, dgamma, dbeta, pad=q,
-                              fmt=FMT_BF16X2 if tc else FMT_F32, extra=draw_add)
+                              fmt=FMT_BF16X2 if (tc or s2_only) else FMT_F32, extra=draw_add)
     if need_wgrad:
         # A conv bias that feeds a norm layer has an identically zero gradient (the norm removes any constant
         # per-channel shift; d_raw sums to zero over the normalised axes) — the reference only accumulates
@@ -261,7 +264,7 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
                                                   layer.bias.grad if want_db else None), (x_op, d_op))
     if not need_dgrad:
         return None
-    if tc and layer.stride == 2:
+    if (tc or s2_only) and layer.stride == 2:
         return ops.conv2d_dgrad_s2(d_op, q, layer.pack(3), layer.k, ho, wo, x_op.hp, x_op.wp)
     if tc:
         wp_in = x_op.wp + (layer.k - 1 if layer.fold_in_cp else 0)     # a folded operand is k-1 columns narrower than the input
@@ -868,7 +871,9 @@ class NLayerDiscriminator(_FlatParamsMixin, nn.Module):
     def _build(input_nc, ndf, n_layers, norm):
         def nl(c):
             return BatchNorm2d(c) if norm == "batch" else _Placeholder("InstanceNorm2d" if norm == "instance" else "Identity")
-        seq = [Conv2d(input_nc, ndf, 4, stride=2), _Placeholder("LeakyReLU(0.2)")]
+        stem = Conv2d(input_nc, ndf, 4, stride=2)
+        stem.tc_dgrad_s2 = ndf % 64 == 0
+        seq = [stem, _Placeholder("LeakyReLU(0.2)")]
         nf = ndf
         for _ in range(1, n_layers):
             nf_prev, nf = nf, min(nf * 2, 512)
