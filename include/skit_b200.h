@@ -221,6 +221,14 @@ int skit_act_norm_bwd_reduce_ex(const float* dpad, int pad, int pad_mode,
                                 const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
                                 int act, float* g, double* sums, void* stream);
 
+/* Same, with an optional second output dsum [n][h][w][c] = fold(dpad) + dadd (+ dadd2): the incoming gradient itself, before
+ * act'.  A ResnetBlock's output gradient feeds both its conv branch and the skip path (networks.py:1322): one pass writes both. */
+int skit_act_norm_bwd_reduce_ex2(const float* dpad, int pad, int pad_mode,
+                                 const float* dadd, const float* dadd2, int dadd_c0, int dadd_ctot, int dadd_relu_mask,
+                                 const float* raw, int n, int h, int w, int c,
+                                 const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                 int act, float* g, double* sums, float* dsum, void* stream);
+
 /* Backward, phase B: d_raw = gamma*rstd*( g - S0/count - xhat*S1/count )  (norm none: d_raw = g),
  * written as a zero-haloed operand (pad q) in fmt, ready for dgrad/wgrad.
  * For BatchNorm, dgamma[c] += S1, dbeta[c] += S0 when non-NULL. */

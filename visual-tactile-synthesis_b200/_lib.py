@@ -54,6 +54,7 @@ SIGNATURES = {
     "skit_norm_act_pad": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _OP, _I, _I, _P],
     "skit_norm_act_pad_ex": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _OP, _I, _I, _I, _P],
     "skit_act_norm_bwd_reduce_ex": [_P, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P],
+    "skit_act_norm_bwd_reduce_ex2": [_P, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P],
     "skit_conv_transpose2d_fwd": [_P, _I, _I, _I, _I, _WT, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P],
     "skit_dbias": [_OP, _I, _I, _I, _P, _P],
     "skit_g_head_bwd_split": [_P, _P, _P, _P, _I, _I, _I, _OP, _OP, _I, _P],

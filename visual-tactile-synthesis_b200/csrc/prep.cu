@@ -247,6 +247,7 @@ struct BwdAP {
     double* sums;
     int chunk;  // pixels per block
     double inv_count;   // 1 / (elements per statistics group)
+    float* dsum;        // optional second output: the incoming gradient itself, fold(dpad) + dadd (+ dadd2), before act'
 };
 
 // number of halo positions that alias source coordinate y on an axis of length len (reflect): returns
@@ -314,6 +315,10 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_kernel(BwdAP p) {
 #pragma unroll
                             for (int j = 0; j < VEC; j++) d[j] += p.dpad[q + j];
                         }
+                }
+                if (p.dsum) {
+#pragma unroll
+                    for (int j = 0; j < VEC; j++) p.dsum[src + j] = d[j];
                 }
                 float gout[VEC];
 #pragma unroll
@@ -421,6 +426,7 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, 
                             }
                     }
                 }
+                if (p.dsum) *reinterpret_cast<float4*>(p.dsum + src) = make_float4(dv[0], dv[1], dv[2], dv[3]);
                 float go[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -829,11 +835,26 @@ extern "C" int skit_norm_act_pad(const float* raw, int n, int h, int w, int c,
     return skit_norm_act_pad_ex(raw, n, h, w, c, mean_rstd, norm_mode, gamma, beta, act, residual, out, op, 0, pad, pad_mode, stream);
 }
 
+extern "C" int skit_act_norm_bwd_reduce_ex2(const float* dpad, int pad, int pad_mode,
+                                            const float* dadd, const float* dadd2, int dadd_c0, int dadd_ctot, int dadd_relu_mask,
+                                            const float* raw, int n, int h, int w, int c,
+                                            const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                            int act, float* g, double* sums, float* dsum, void* stream);
+
 extern "C" int skit_act_norm_bwd_reduce_ex(const float* dpad, int pad, int pad_mode,
                                            const float* dadd, const float* dadd2, int dadd_c0, int dadd_ctot, int dadd_relu_mask,
                                            const float* raw, int n, int h, int w, int c,
                                            const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
                                            int act, float* g, double* sums, void* stream) {
+    return skit_act_norm_bwd_reduce_ex2(dpad, pad, pad_mode, dadd, dadd2, dadd_c0, dadd_ctot, dadd_relu_mask, raw, n, h, w, c,
+                                        mean_rstd, norm_mode, gamma, beta, act, g, sums, nullptr, stream);
+}
+
+extern "C" int skit_act_norm_bwd_reduce_ex2(const float* dpad, int pad, int pad_mode,
+                                            const float* dadd, const float* dadd2, int dadd_c0, int dadd_ctot, int dadd_relu_mask,
+                                            const float* raw, int n, int h, int w, int c,
+                                            const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                            int act, float* g, double* sums, float* dsum, void* stream) {
     SKIT_REQUIRE(g && (dpad || dadd) && n > 0 && h > 0 && w > 0 && c > 0, "act_norm_bwd_reduce: bad arguments");
     SKIT_REQUIRE(raw || (norm_mode == SKIT_NORM_NONE && act == SKIT_ACT_NONE && !dadd_relu_mask), "act_norm_bwd_reduce: raw required unless norm, act and mask are all none");
     SKIT_REQUIRE((norm_mode == SKIT_NORM_NONE) == (mean_rstd == nullptr), "act_norm_bwd_reduce: mean_rstd must be given iff norm_mode != none");
@@ -849,7 +870,7 @@ extern "C" int skit_act_norm_bwd_reduce_ex(const float* dpad, int pad, int pad_m
     p.dc0 = dadd_c0; p.dctot = dadd_ctot; p.dmask = dadd_relu_mask;
     p.raw = raw; p.n = n; p.h = h; p.w = w; p.c = c;
     p.mr = mean_rstd; p.per_n = norm_mode == SKIT_NORM_INSTANCE; p.gamma = gamma; p.beta = beta;
-    p.act = act; p.g = g; p.sums = sums;
+    p.act = act; p.g = g; p.sums = sums; p.dsum = dsum;
     p.inv_count = 1.0 / ((double)h * w * (norm_mode == SKIT_NORM_BATCH ? n : 1));
     const int P = h * w;
     if (rows_layout_ok(c) && dadd_c0 % 4 == 0 && dadd_ctot % 4 == 0) {

@@ -235,14 +235,19 @@ def _conv_fwd(layer, x_op, org, ho, wo, stats_mode, with_bias=True):
 
 
 def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None,
-               gamma=None, beta=None, dgamma=None, dbeta=None, need_dgrad=True, need_wgrad=True, draw_add=None):
+               gamma=None, beta=None, dgamma=None, dbeta=None, need_dgrad=True, need_wgrad=True, draw_add=None, dsum_out=None):
     """Backward of [conv -> norm -> act] given the gradient w.r.t. the activated output, either as
     a halo'd tensor `dpad` (gradient of the next conv's operand) and/or a dense `dadd`.
     Returns the gradient w.r.t. the conv's own haloed operand (NHWC fp32 [n, hp, wp, ci]) or None."""
     n, ho, wo, co = raw.shape
     if dpad is None and dadd is None:   # only a tapped-feature gradient on the raw output reaches this stage
         dadd = torch.zeros_like(raw)
-    g, sums = ops.act_norm_bwd_reduce(raw.shape, dpad, pad, pad_mode, dadd, raw, mr, norm_mode, gamma, beta, act)
+    if dsum_out is not None:   # also materialise the incoming gradient fold(dpad) + dadd (a ResnetBlock's skip path needs it)
+        g, sums, ds = ops.act_norm_bwd_reduce_ex(raw.shape, dpad=dpad, pad=pad, pad_mode=pad_mode, dadd=dadd, raw=raw, mr=mr,
+                                                 norm_mode=norm_mode, act=act, gamma=gamma, beta=beta, want_dsum=True)
+        dsum_out.append(ds)
+    else:
+        g, sums = ops.act_norm_bwd_reduce(raw.shape, dpad, pad, pad_mode, dadd, raw, mr, norm_mode, gamma, beta, act)
     tc = layer.use_tc
     s2_only = (not tc) and need_dgrad and layer.tc_dgrad_s2 and TC_ENABLED and co % 64 == 0
     q = 0 if (not (tc or s2_only) or not need_dgrad) else (layer.k - 1 if layer.stride == 1 else layer.k // 2 - 1)
@@ -433,11 +438,20 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         dpad_u1 = _stage_bwd(self._u1, ctx["op_u1"], ctx["raw22"], ctx["mr22"], IN, ACT_RELU, h2 * w2, dadd=da22)
         du1, _ = ops.act_norm_bwd_reduce((n, h2, w2, dpad_u1.shape[3]), dpad=dpad_u1, pad=1, pad_mode=PAD_ZERO)
         dt = ops.blur_up_bwd(du1)
+        # per block: the output gradient dt feeds the conv branch and the skip; the next (earlier) block's output gradient is
+        # fold(dpad_t) + dt, produced as a side output of that block's first norm-backward pass instead of a pass of its own
+        pend = None   # dpad_t of the block processed before (the later block), not yet folded into dt
         for blk, (op_t, rawA, mrA, opA, rawB, mrB) in zip(reversed(self._blocks), reversed(ctx["blocks"])):
             ca, cb = blk.conv_block[1], blk.conv_block[5]
-            dpadA = _stage_bwd(cb, opA, rawB, mrB, IN, ACT_NONE, h4 * w4, dadd=dt)
-            dpad_t = _stage_bwd(ca, op_t, rawA, mrA, IN, ACT_RELU, h4 * w4, dpad=dpadA, pad=1, pad_mode=PAD_REFLECT)
-            dt, _ = ops.act_norm_bwd_reduce(dt.shape, dpad=dpad_t, pad=1, pad_mode=PAD_REFLECT, dadd=dt)
+            if pend is None:
+                dpadA = _stage_bwd(cb, opA, rawB, mrB, IN, ACT_NONE, h4 * w4, dadd=dt)
+            else:
+                out = []
+                dpadA = _stage_bwd(cb, opA, rawB, mrB, IN, ACT_NONE, h4 * w4, dpad=pend, pad=1, pad_mode=PAD_REFLECT, dadd=dt, dsum_out=out)
+                dt = out[0]
+            pend = _stage_bwd(ca, op_t, rawA, mrA, IN, ACT_RELU, h4 * w4, dpad=dpadA, pad=1, pad_mode=PAD_REFLECT)
+        if pend is not None:
+            dt, _ = ops.act_norm_bwd_reduce(dt.shape, dpad=pend, pad=1, pad_mode=PAD_REFLECT, dadd=dt)
         da8 = ops.blur_down_bwd(dt, h2, w2)
         dpad4 = _stage_bwd(self._c8, ctx["op4"], ctx["raw8"], ctx["mr8"], IN, ACT_RELU, h2 * w2, dadd=da8)
         dd4, _ = ops.act_norm_bwd_reduce((n, h2, w2, dpad4.shape[3]), dpad=dpad4, pad=1, pad_mode=PAD_ZERO)
