@@ -142,6 +142,13 @@ int skit_conv2d_fwd(const skit_operand* x, const skit_weights* w, int stride, in
 int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, int co,
                              const skit_weights* wg, int stride, int hp, int wp, float* dx, void* stream);
 
+/* Input gradient of a stride-1 conv (autograd of F.conv2d, e.g. the ResnetBlock convs networks.py:1281-1310):
+ *   dx[n][y][x][c] = sum_{a,b,o} dz[n][y+a][x+b][o] * w[o][c][k-1-a][k-1-b],  dz = dy with a zero halo of k-1
+ * dy: operand carrying that halo (dy->hp = H + k - 1 for an H x W gradient w.r.t. the conv's padded input); w1: mode-1 pack;
+ * dx: NHWC fp32 [n][dy->hp - k + 1][dy->wp - k + 1][w1->co].  On the halo-tile tcgen05 kernel the one-pixel border strips
+ * (whose windows touch the data through a single filter row / column) run as extra regions of the same grid. */
+int skit_conv2d_dgrad_s1(const skit_operand* dy, const skit_weights* w1, float* dx, void* stream);
+
 /* Input gradient of a stride-2, even-k conv on the tensor cores (PatchGAN k4 s2 layers, networks.py:1706-1716):
  * the four parities (iy%2, ix%2) of dx are four stride-1 (k/2 x k/2) convolutions of dy — which must be a
  * bf16x2 operand zero-haloed by dy_pad = k/2-1 — with the mode-3 sub-filters; each writes its interleaved

@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libskit_b200.so")
+LIB_PATH = os.environ.get("SKIT_B200_LIB") or os.path.join(_HERE, "csrc", "libskit_b200.so")   # override: A/B a previous build
 
 FMT_F32, FMT_BF16X2 = 0, 1
 PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
@@ -48,6 +48,7 @@ SIGNATURES = {
     "skit_unpack_conv_wgrad": [_P, _I, _I, _I, _P, _I, _P],
     "skit_conv2d_fwd": [_OP, _WT, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "skit_conv2d_dgrad_gather": [_P, _I, _I, _I, _I, _WT, _I, _I, _I, _P, _P],
+    "skit_conv2d_dgrad_s1": [_OP, _WT, _P, _P],
     "skit_conv2d_dgrad_s2": [_OP, _I, _WT, _I, _I, _I, _I, _I, _P, _P],
     "skit_conv2d_wgrad": [_OP, _I, _OP, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "skit_stats_finalize": [_P, _I, _I, _D, _F, _P, _P, _P, _F, _P],
@@ -104,6 +105,8 @@ def load():
             "(nvcc, sm_100a). There is no CPU/PyTorch fallback for the hot path." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, argtypes in SIGNATURES.items():
+        if not hasattr(lib, name) and os.environ.get("SKIT_B200_LIB"):
+            continue    # an older build loaded for an A/B measurement may lack the newest entry points
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = _I

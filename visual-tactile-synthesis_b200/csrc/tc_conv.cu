@@ -227,6 +227,7 @@ static int launch_conv_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
 }  // namespace tc
 
 static bool halo_enabled();
+int conv_tc_halo_dgrad_full(const skit_operand* d, const void* w_hi, const void* w_lo, int co, int k, float* dx, cudaStream_t st);  // tc_conv_halo.cu
 
 bool conv_tc_eligible(const skit_operand* x, const skit_weights* w, int stride) {
     if (x->fmt != SKIT_FMT_BF16X2 || !w->hi || !w->lo || w->ci != x->c) return false;
@@ -370,4 +371,17 @@ extern "C" int skit_conv2d_dgrad_s2(const skit_operand* dy, int dy_pad, const sk
             if (rc) return rc;
         }
     return SKIT_OK;
+}
+
+
+// Stride-1 input gradient on the tensor cores: dx = full correlation of the zero-haloed (k-1) gradient operand with the
+// mode-1 (flipped, transposed) pack.  With the halo-tile kernel the border strips run as cheap extra regions of the same grid.
+extern "C" int skit_conv2d_dgrad_s1(const skit_operand* dy, const skit_weights* w1, float* dx, void* stream) {
+    SKIT_REQUIRE(dy && w1 && dx && dy->p0, "conv2d_dgrad_s1: null pointer");
+    const int k = w1->k;
+    SKIT_REQUIRE(w1->ci == dy->c && dy->hp >= k && dy->wp >= k, "conv2d_dgrad_s1: pack / operand mismatch");
+    const int H = dy->hp - k + 1, W = dy->wp - k + 1;
+    if (halo_enabled() && dy->fmt == SKIT_FMT_BF16X2 && w1->hi && w1->lo && w1->kw == 0 && dy->c % 64 == 0)
+        return conv_tc_halo_dgrad_full(dy, w1->hi, w1->lo, w1->co, k, dx, as_stream(stream));
+    return skit_conv2d_fwd(dy, w1, 1, 0, H, W, nullptr, dx, nullptr, SKIT_NORM_NONE, SKIT_IMPL_AUTO, stream);
 }

@@ -25,21 +25,41 @@
 namespace skit {
 namespace tc {
 
+// One launch may cover several rectangular REGIONS of the output, each with its own sub-filter (a rectangle of taps of the
+// packed filter), operand origin and halo-box shape.  A plain convolution is one region.  The stride-1 input gradient — a full
+// correlation of the zero-haloed output gradient — is an interior region with all taps plus four one-pixel border strips whose
+// windows only reach the data through one filter row / column: the strips cost a third of a tile and fill the SMs the interior
+// leaves idle, instead of pushing a 130x130 map to 153 tiles = two waves on 148 SMs.
+struct HaloRegion {
+    int first;                       // first CTA (blockIdx.x) of this region
+    int kh, kw;                      // sub-filter taps
+    int tap_base, tap_sy, tap_sx;    // tap index in the packed filter = tap_base + ky*tap_sy + kx*tap_sx
+    int org_y, org_x;                // operand coordinate read by output (0,0) of the region through sub-filter tap (0,0)
+    int ho, wo, tiles_x;             // region size in output pixels, tiles per row
+    int ooy, oox;                    // where the region's output (0,0) lands in the output map (before osy/osx scaling)
+    int amap;                        // which activation tensor-map pair (box shape) it uses
+    int pitch, a_rows;               // halo tile width in pixels = 8 + kw - 1; rows*cols of the halo tile
+};
+constexpr int MAX_REGIONS = 5;
+constexpr int MAX_AMAPS = 3;
+
+struct AMaps {
+    CUtensorMap hi[MAX_AMAPS];
+    CUtensorMap lo[MAX_AMAPS];
+};
+
 struct TcHaloP {
-    int kh, kw;        // filter taps (rows, cols)
+    int nreg;
+    HaloRegion reg[MAX_REGIONS];
     int kc;            // 64-channel chunks (ceil(ci/64))
     int kk_last;       // 16-channel K steps in the last chunk (1..4)
-    int org, tap_base;
-    int ho, wo, co;
-    int tiles_x;
-    int OH, OW, osy, osx, ooy, oox;   // output placement (phase-wise dgrad writes interleaved quarters)
+    int co;
+    int OH, OW, osy, osx, poy, pox;   // output map, placement stride and phase offset (stride-2 dgrad writes interleaved quarters)
     const float* bias;
     float* y;
     double* stats;
     int stats_per_n;
-    int pitch;         // halo tile width in pixels = 8 + kw - 1
-    int a_rows;        // halo tile rows*cols
-    int a_plane;       // bytes reserved per A plane (a_rows*128 rounded up to 1024)
+    int a_plane;       // bytes reserved per A plane (largest region's a_rows*128 rounded up to 1024)
     int nw;            // weight stages
     int na;            // activation stages (2, or 1 when a large halo tile must leave room for wide weight stages)
     long long* dbg;    // optional per-CTA clock64 stamps [cta][8] (skit_debug_set_buffer), NULL in production
@@ -59,8 +79,8 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, uint32_t sbo_
 
 template <int BN>
 __global__ void __launch_bounds__(128, 1)
-conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, TcHaloP p) {
+conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
+                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcHaloP p) {
     constexpr int W_PLANE = BN * 128;       // BN rows x 64 channels x 2 B
     constexpr int W_STAGE = 2 * W_PLANE;
     constexpr int TCOLS = BN < 32 ? 32 : BN;
@@ -82,13 +102,34 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.z;
     const int n0 = blockIdx.y * BN;
-    const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
+    int ri = 0;
+    for (int r = 1; r < p.nreg; r++)
+        if ((int)blockIdx.x >= p.reg[r].first) ri = r;
+    // the region's fields go to registers once: a reference into the parameter array with a runtime index would be re-read
+    // through indexed constant loads (or a local copy) inside the epilogue's store loop
+    HaloRegion R;
+    {
+        const int* src = reinterpret_cast<const int*>(&p.reg[0]);
+        int* dst = reinterpret_cast<int*>(&R);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(HaloRegion) / sizeof(int)); i++) {
+            int v = src[i];
+#pragma unroll
+            for (int r = 1; r < MAX_REGIONS; r++)
+                if (r == ri) v = src[r * (int)(sizeof(HaloRegion) / sizeof(int)) + i];
+            dst[i] = v;
+        }
+    }
+    const int lt = blockIdx.x - R.first;
+    const int tile_y = lt / R.tiles_x, tile_x = lt - tile_y * R.tiles_x;
     const int y0 = tile_y * 16, x0 = tile_x * 8;
+    const CUtensorMap* tmA_hi = &tmA.hi[R.amap];
+    const CUtensorMap* tmA_lo = &tmA.lo[R.amap];
     long long* dbg = p.dbg ? p.dbg + 8ll * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
+        tma_prefetch_desc(tmA_hi); tma_prefetch_desc(tmA_lo);
         tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
         for (int s = 0; s < NA; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < p.nw; s++) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
@@ -101,36 +142,37 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    const int ntaps = p.kh * p.kw;
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     if (warp == 2 && lane == 0) {
         // ---------------- activation producer: one halo box (hi + lo) per 64-channel chunk
-        const uint32_t bytes = 2u * (uint32_t)p.a_rows * 128u;
+        const uint32_t bytes = 2u * (uint32_t)R.a_rows * 128u;
         for (int c = 0; c < p.kc; c++) {
             const int s = c % NA, ph = (c / NA) & 1;
             mbar_wait(a_empty(s), ph ^ 1);
             mbar_expect_tx(a_full(s), bytes);
             const uint32_t sa = smem0 + s * a_stage;
-            tma_load_4d(sa, &tmA_hi, a_full(s), c * 64, p.org + x0, p.org + y0, n);
-            tma_load_4d(sa + p.a_plane, &tmA_lo, a_full(s), c * 64, p.org + x0, p.org + y0, n);
+            tma_load_4d(sa, tmA_hi, a_full(s), c * 64, R.org_x + x0, R.org_y + y0, n);
+            tma_load_4d(sa + p.a_plane, tmA_lo, a_full(s), c * 64, R.org_x + x0, R.org_y + y0, n);
         }
     } else if (warp == 0 && lane == 0) {
         // ---------------- weight producer: (chunk, tap) stages
         int it = 0;
         for (int c = 0; c < p.kc; c++)
-            for (int tap = 0; tap < ntaps; tap++, it++) {
-                const int s = it % p.nw, ph = (it / p.nw) & 1;
-                mbar_wait(w_empty(s), ph ^ 1);
-                mbar_expect_tx(w_full(s), W_STAGE);
-                const uint32_t sw = w0 + s * W_STAGE;
-                tma_load_3d(sw, &tmW_hi, w_full(s), c * 64, n0, p.tap_base + tap);
-                tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, n0, p.tap_base + tap);
-            }
+            for (int ky = 0; ky < R.kh; ky++)
+                for (int kx = 0; kx < R.kw; kx++, it++) {
+                    const int s = it % p.nw, ph = (it / p.nw) & 1;
+                    const int tap = R.tap_base + ky * R.tap_sy + kx * R.tap_sx;
+                    mbar_wait(w_empty(s), ph ^ 1);
+                    mbar_expect_tx(w_full(s), W_STAGE);
+                    const uint32_t sw = w0 + s * W_STAGE;
+                    tma_load_3d(sw, &tmW_hi, w_full(s), c * 64, n0, tap);
+                    tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, n0, tap);
+                }
     } else if (warp == 1 && lane == 0) {
         // ---------------- MMA issuer
         constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
-        const uint32_t sbo_a = (uint32_t)p.pitch * 128u;
+        const uint32_t sbo_a = (uint32_t)R.pitch * 128u;
         int it = 0;
         uint32_t acc = 0;
         for (int c = 0; c < p.kc; c++) {
@@ -140,9 +182,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             tc_fence_after();
             if (dbg && c == 0) dbg[2] = clock64();
             const uint32_t sa = smem0 + s * a_stage;
-            for (int ky = 0; ky < p.kh; ky++)
-                for (int kx = 0; kx < p.kw; kx++, it++) {
-                    const uint32_t arow = sa + (uint32_t)(ky * p.pitch + kx) * 128u;
+            for (int ky = 0; ky < R.kh; ky++)
+                for (int kx = 0; kx < R.kw; kx++, it++) {
+                    const uint32_t arow = sa + (uint32_t)(ky * R.pitch + kx) * 128u;
                     const int ws = it % p.nw, wph = (it / p.nw) & 1;
                     mbar_wait(w_full(ws), wph);
                     tc_fence_after();
@@ -181,10 +223,21 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int r = warp * 32 + lane;
         const int ty = r >> 3, tx = r & 7;
         const int oy = y0 + ty, ox = x0 + tx;
-        const int py = oy * p.osy + p.ooy, px = ox * p.osx + p.oox;
-        const bool valid = oy < p.ho && ox < p.wo && py < p.OH && px < p.OW;
+        const int py = (oy + R.ooy) * p.osy + p.poy, px = (ox + R.oox) * p.osx + p.pox;
+        const bool valid = oy < R.ho && ox < R.wo && py < p.OH && px < p.OW;
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
         float* yrow = p.y + (((long long)n * p.OH + py) * p.OW + px) * p.co + n0;
+        // the 8 output rows this lane stores (4 rows per pass, 8 lanes per 128-byte row): pointers and validity once per tile
+        float* rowp[8];
+        uint32_t rowok = 0;
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int rr = it * 4 + (lane >> 3);
+            const int g = warp * 32 + rr;
+            const int gy = (y0 + (g >> 3) + R.ooy) * p.osy + p.poy, gx = (x0 + (g & 7) + R.oox) * p.osx + p.pox;
+            rowp[it] = p.y + (((long long)n * p.OH + gy) * p.OW + gx) * p.co + n0 + (lane & 7) * 4;
+            rowok |= ((vmask >> rr) & 1u) << it;
+        }
 #pragma unroll 1
         for (int c = 0; c < TCOLS; c += 32) {
             float v[32];
@@ -199,17 +252,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * STG + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
-                const int q = lane & 7;
+                float4 t4[8];
 #pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    const int rr = it * 4 + (lane >> 3);
-                    if ((vmask >> rr) & 1u) {
-                        const int g = warp * 32 + rr;
-                        const int gy = (y0 + (g >> 3)) * p.osy + p.ooy, gx = (x0 + (g & 7)) * p.osx + p.oox;
-                        float* dst = p.y + (((long long)n * p.OH + gy) * p.OW + gx) * p.co + n0 + c + q * 4;
-                        *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(stg + rr * STG + q * 4);
-                    }
-                }
+                for (int it = 0; it < 8; it++)      // 8 independent 16-byte shared loads first ...
+                    t4[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * STG + (lane & 7) * 4);
+#pragma unroll
+                for (int it = 0; it < 8; it++)      // ... then the 8 coalesced row stores
+                    if ((rowok >> it) & 1u) *reinterpret_cast<float4*>(rowp[it] + c) = t4[it];
                 if (p.stats) {   // lane j owns column c + j: sum it down the 32 staged rows
                     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -289,8 +338,7 @@ int encode_bf16_map_sw(CUtensorMap* m, const void* base, int rank, const uint64_
 }
 
 template <int BN>
-static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
-                       TcHaloP& p, dim3 grid, cudaStream_t st) {
+static int launch_halo(const AMaps& amaps, const CUtensorMap& w_hi, const CUtensorMap& w_lo, TcHaloP& p, dim3 grid, cudaStream_t st) {
     constexpr int W_STAGE = 2 * BN * 128;
     constexpr int MAX_SMEM = 227 * 1024;
     // two activation stages unless a large halo tile would squeeze the weight ring below two stages (k4 with BN = 256)
@@ -299,7 +347,7 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     int nw = (MAX_SMEM - fixed) / W_STAGE;
     if (nw > 8) nw = 8;
     if (nw < 2) {
-        set_error("conv_tc_halo: halo tile of a %dx%d filter leaves no room for weight stages", p.kh, p.kw);
+        set_error("conv_tc_halo: the halo tile (%d bytes per plane) leaves no room for weight stages", p.a_plane);
         return SKIT_ERR_UNSUPPORTED;
     }
     p.nw = nw;
@@ -313,8 +361,54 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
         }
         attr_smem = MAX_SMEM;
     }
-    conv_tc_halo_kernel<BN><<<grid, 128, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+    conv_tc_halo_kernel<BN><<<grid, 128, smem, st>>>(amaps, w_hi, w_lo, p);
     return check_launch("conv_tc_halo_kernel");
+}
+
+// N tile for `tiles` pixel tiles of `ksteps` (chunk, tap) steps each: as wide as possible (the weight stream is the L2 traffic
+// that remains), narrower when that fills more SMs.  Cost per CTA: K steps x max(MMA, shared-memory reads feeding them)
+// + prologue and epilogue; total = waves x per-CTA cost.
+static int pick_bn(int co, long long tiles, double ksteps, int a_plane) {
+    if (co <= 16) return 16;
+    int BN = 64;
+    double best = 1e30;
+    const int avail1 = 227 * 1024 - (2 * a_plane + 1024 + 512);   // with a single activation stage
+    for (int cand = 256; cand >= 64; cand >>= 1) {
+        if (cand > 64 && co % cand) continue;
+        if (cand > 64 && avail1 / (cand * 256) < 2) continue;      // needs two weight stages next to the halo tile
+        const int ntile = cdiv(co, cand);
+        const double mma = cand * 0.53, rd = (4096.0 + cand * 32.0) / 80.0;
+        const double per = ksteps * (12.0 * (mma > rd ? mma : rd) + 100.0) + 3000.0 + 16.0 * cand;
+        const double cost = (double)((tiles * ntile + 147) / 148) * per;
+        if (cost < best * 0.97) { best = cost; BN = cand; }
+    }
+    return BN;
+}
+
+static int encode_a_maps(tc::AMaps* am, int slot, const skit_operand* x, int pitch, int rows) {
+    uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->wp, (uint64_t)x->hp, (uint64_t)x->n};
+    uint64_t strides[3] = {(uint64_t)x->c * 2, (uint64_t)x->c * 2 * x->wp, (uint64_t)x->c * 2 * x->wp * x->hp};
+    uint32_t box[4] = {64, (uint32_t)pitch, (uint32_t)rows, 1};
+    int rc = tc::encode_bf16_map_sw(&am->hi[slot], x->p0, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    return tc::encode_bf16_map_sw(&am->lo[slot], x->p1, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+static int encode_w_maps(CUtensorMap* m_hi, CUtensorMap* m_lo, const void* w_hi, const void* w_lo, int ci_pack, int co, int ntaps_total, int BN) {
+    uint64_t dims[3] = {(uint64_t)ci_pack, (uint64_t)co, (uint64_t)ntaps_total};
+    uint64_t strides[2] = {(uint64_t)ci_pack * 2, (uint64_t)ci_pack * 2 * co};
+    uint32_t box[3] = {64, (uint32_t)BN, 1};
+    int rc = tc::encode_bf16_map_sw(m_hi, w_hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    return tc::encode_bf16_map_sw(m_lo, w_lo, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+static int dispatch_halo(int BN, const tc::AMaps& am, const CUtensorMap& m_hi, const CUtensorMap& m_lo, tc::TcHaloP& p, dim3 grid, cudaStream_t st) {
+    using namespace tc;
+    if (BN == 256) return launch_halo<256>(am, m_hi, m_lo, p, grid, st);
+    if (BN == 128) return launch_halo<128>(am, m_hi, m_lo, p, grid, st);
+    if (BN == 64) return launch_halo<64>(am, m_hi, m_lo, p, grid, st);
+    return launch_halo<16>(am, m_hi, m_lo, p, grid, st);
 }
 
 }  // namespace tc
@@ -327,62 +421,89 @@ int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_l
     using namespace tc;
     const int ci = x->c;
     TcHaloP p{};
-    p.kh = kh; p.kw = kw; p.kc = cdiv(ci, 64);
+    p.kc = cdiv(ci, 64);
     p.kk_last = cdiv(ci - (p.kc - 1) * 64, 16);
-    p.org = org; p.tap_base = tap_base; p.ho = ho; p.wo = wo; p.co = co;
-    p.tiles_x = cdiv(wo, 8);
-    const int tiles_y = cdiv(ho, 16);
-    if (out) { p.OH = out->OH; p.OW = out->OW; p.osy = out->osy; p.osx = out->osx; p.ooy = out->ooy; p.oox = out->oox; }
-    else { p.OH = ho; p.OW = wo; p.osy = 1; p.osx = 1; p.ooy = 0; p.oox = 0; }
+    p.co = co;
+    if (out) { p.OH = out->OH; p.OW = out->OW; p.osy = out->osy; p.osx = out->osx; p.poy = out->ooy; p.pox = out->oox; }
+    else { p.OH = ho; p.OW = wo; p.osy = 1; p.osx = 1; p.poy = 0; p.pox = 0; }
     p.bias = bias; p.y = y; p.stats = stats; p.stats_per_n = stats_mode == SKIT_NORM_INSTANCE;
-    p.pitch = 8 + kw - 1;
-    p.a_rows = p.pitch * (16 + kh - 1);
-    p.a_plane = ((p.a_rows * 128 + 1023) / 1024) * 1024;
     p.dbg = g_dbg_buffer;
+    p.nreg = 1;
+    HaloRegion& R = p.reg[0];
+    R.first = 0; R.kh = kh; R.kw = kw; R.tap_base = tap_base; R.tap_sy = kw; R.tap_sx = 1;
+    R.org_y = org; R.org_x = org; R.ho = ho; R.wo = wo; R.tiles_x = cdiv(wo, 8); R.ooy = 0; R.oox = 0; R.amap = 0;
+    R.pitch = 8 + kw - 1; R.a_rows = R.pitch * (16 + kh - 1);
+    p.a_plane = ((R.a_rows * 128 + 1023) / 1024) * 1024;
+    const int tiles_y = cdiv(ho, 16);
+    const int BN = pick_bn(co, (long long)R.tiles_x * tiles_y * x->n, (double)p.kc * kh * kw, p.a_plane);
+    AMaps am;
+    CUtensorMap m_hi, m_lo;
+    int rc = encode_a_maps(&am, 0, x, R.pitch, 16 + kh - 1);
+    if (rc) return rc;
+    for (int i = 1; i < MAX_AMAPS; i++) { am.hi[i] = am.hi[0]; am.lo[i] = am.lo[0]; }
+    rc = encode_w_maps(&m_hi, &m_lo, w_hi, w_lo, ci_pack, co, ntaps_total, BN);
+    if (rc) return rc;
+    dim3 grid(R.tiles_x * tiles_y, cdiv(co, BN), x->n);
+    return dispatch_halo(BN, am, m_hi, m_lo, p, grid, st);
+}
 
-    // N tile: as wide as possible (the weight stream is the L2 traffic that remains), narrower when that fills more SMs
-    int BN = 16;
-    if (co > 16) {
-        const long long tiles = (long long)p.tiles_x * tiles_y * x->n;
-        double best = 1e30;
-        const int avail1 = 227 * 1024 - (2 * p.a_plane + 1024 + 512);   // with a single activation stage
-        for (int cand = 256; cand >= 64; cand >>= 1) {
-            if (cand > 64 && co % cand) continue;
-            if (cand > 64 && avail1 / (cand * 256) < 2) continue;   // needs two weight stages next to the halo tile
-            const int ntile = cdiv(co, cand);
-            // cycles per 64-channel tap step: the MMAs (128 x cand x 16 at ~cand/2 cycles), or the shared-memory reads that
-            // feed them (A 4 KB + B cand*32 B per MMA at ~110 B/cycle) — narrow tiles re-read A and become smem bound
-            const double mma = cand * 0.53, rd = (4096.0 + cand * 32.0) / 80.0;
-            const double ksteps = (double)p.kc * kh * kw;
-            const double per = ksteps * (12.0 * (mma > rd ? mma : rd) + 100.0) + 3000.0 + 16.0 * cand;   // + prologue and epilogue
-            const double cost = (double)((tiles * ntile + 147) / 148) * per;
-            if (cost < best * 0.97) { best = cost; BN = cand; }
-        }
+// Stride-1 INPUT GRADIENT of a k x k conv: dx[n][H][W][co] = full correlation of the gradient operand d (zero halo of k-1, so
+// d->hp = H + k - 1 ... i.e. dx is (d->hp - k + 1) x (d->wp - k + 1)) with the flipped filter pack [k*k][co][ci].  When the
+// one-region tiling would spill into an extra wave and the interior + four border strips fit better, it is launched as five
+// regions of ONE grid: the strips' windows reach the data only through one filter row / column (the rest of the window is the
+// zero halo), so they run a third of the K loop.
+int conv_tc_halo_dgrad_full(const skit_operand* d, const void* w_hi, const void* w_lo, int co, int k, float* dx, cudaStream_t st) {
+    using namespace tc;
+    const int ci = d->c;
+    const int H = d->hp - k + 1, W = d->wp - k + 1;
+    const int q = k - 1;
+    const long long full_tiles = (long long)cdiv(W, 8) * cdiv(H, 16) * d->n;
+    const int hi_ = H - 2, wi_ = W - 2;          // interior: outputs whose window holds at least ... every tap row/col may matter
+    const long long int_tiles = (long long)cdiv(wi_, 8) * cdiv(hi_, 16) * d->n;
+    const long long strip_tiles = (long long)(2 * cdiv(W, 8) + 2 * cdiv(hi_, 16)) * d->n;
+    const bool split = k == 3 && d->n == 1 && H > 18 && W > 10 && ci % 64 == 0 &&
+                       (full_tiles + 147) / 148 > (int_tiles + 147) / 148 &&                 // the interior saves a wave ...
+                       int_tiles + (strip_tiles + 2) / 3 <= ((int_tiles + 147) / 148) * 148;   // ... and the strips fit in its slack
+    if (!split)
+        return conv_tc_halo_launch(d, w_hi, w_lo, ci, co, k, k, k * k, 0, 0, H, W, nullptr, dx, nullptr, nullptr, SKIT_NORM_NONE, st);
+    TcHaloP p{};
+    p.kc = cdiv(ci, 64); p.kk_last = 4; p.co = co;
+    p.OH = H; p.OW = W; p.osy = 1; p.osx = 1; p.poy = 0; p.pox = 0;
+    p.bias = nullptr; p.y = dx; p.stats = nullptr; p.stats_per_n = 0; p.dbg = g_dbg_buffer;
+    p.nreg = 5;
+    auto set = [&](int i, int kh, int kw, int tb, int sy, int sx, int oy, int ox, int ho, int wo, int ooy, int oox, int amap) {
+        HaloRegion& R = p.reg[i];
+        R.kh = kh; R.kw = kw; R.tap_base = tb; R.tap_sy = sy; R.tap_sx = sx; R.org_y = oy; R.org_x = ox; R.ho = ho; R.wo = wo;
+        R.tiles_x = cdiv(wo, 8); R.ooy = ooy; R.oox = oox; R.amap = amap; R.pitch = 8 + kw - 1; R.a_rows = R.pitch * (16 + kh - 1);
+    };
+    // dx[i][x] = sum_{a,b} dz[i+a][x+b] * wf[a*3+b], dz = d with its zero halo of 2.  Row 0 sees data only through a = 2,
+    // row H-1 only through a = 0; column 0 only through b = 2, column W-1 only through b = 0.
+    set(0, 3, 3, 0, 3, 1, 1, 1, hi_, wi_, 1, 1, 0);                 // interior rows 1..H-2, cols 1..W-2, all 9 taps
+    set(1, 1, 3, 6, 3, 1, 2, 0, 1, W, 0, 0, 1);                     // top row:    taps (2, b), operand row 0 + 2
+    set(2, 1, 3, 0, 3, 1, H - 1, 0, 1, W, H - 1, 0, 1);             // bottom row: taps (0, b), operand row H-1 + 0
+    set(3, 3, 1, 2, 3, 1, 1, 2, hi_, 1, 1, 0, 2);                   // left col:   taps (a, 2), operand col 0 + 2, rows 1..H-2
+    set(4, 3, 1, 0, 3, 1, 1, W - 1, hi_, 1, 1, W - 1, 2);           // right col:  taps (a, 0)
+    int first = 0, amax = 0;
+    for (int i = 0; i < 5; i++) {
+        p.reg[i].first = first;
+        first += p.reg[i].tiles_x * cdiv(p.reg[i].ho, 16);
+        amax = max(amax, p.reg[i].a_rows);
     }
-    CUtensorMap a_hi, a_lo, m_hi, m_lo;
-    {
-        uint64_t dims[4] = {(uint64_t)ci, (uint64_t)x->wp, (uint64_t)x->hp, (uint64_t)x->n};
-        uint64_t strides[3] = {(uint64_t)ci * 2, (uint64_t)ci * 2 * x->wp, (uint64_t)ci * 2 * x->wp * x->hp};
-        uint32_t box[4] = {64, (uint32_t)p.pitch, (uint32_t)(16 + kh - 1), 1};
-        int rc = encode_bf16_map_sw(&a_hi, x->p0, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-        rc = encode_bf16_map_sw(&a_lo, x->p1, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-    }
-    {
-        uint64_t dims[3] = {(uint64_t)ci_pack, (uint64_t)co, (uint64_t)ntaps_total};
-        uint64_t strides[2] = {(uint64_t)ci_pack * 2, (uint64_t)ci_pack * 2 * co};
-        uint32_t box[3] = {64, (uint32_t)BN, 1};
-        int rc = encode_bf16_map_sw(&m_hi, w_hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-        rc = encode_bf16_map_sw(&m_lo, w_lo, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-    }
-    dim3 grid(p.tiles_x * tiles_y, cdiv(co, BN), x->n);
-    if (BN == 256) return launch_halo<256>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
-    if (BN == 128) return launch_halo<128>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
-    if (BN == 64) return launch_halo<64>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
-    return launch_halo<16>(a_hi, a_lo, m_hi, m_lo, p, grid, st);
+    p.a_plane = ((amax * 128 + 1023) / 1024) * 1024;
+    (void)q;
+    const int BN = (co % 256 == 0) ? 256 : pick_bn(co, int_tiles, (double)p.kc * 9, p.a_plane);
+    AMaps am;
+    CUtensorMap m_hi, m_lo;
+    int rc = encode_a_maps(&am, 0, d, 10, 18);
+    if (rc) return rc;
+    rc = encode_a_maps(&am, 1, d, 10, 16);
+    if (rc) return rc;
+    rc = encode_a_maps(&am, 2, d, 8, 18);
+    if (rc) return rc;
+    rc = encode_w_maps(&m_hi, &m_lo, w_hi, w_lo, ci, co, k * k, BN);
+    if (rc) return rc;
+    dim3 grid(first, cdiv(co, BN), 1);
+    return dispatch_halo(BN, am, m_hi, m_lo, p, grid, st);
 }
 
 }  // namespace skit

@@ -272,6 +272,8 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
     if (tc or s2_only) and layer.stride == 2:
         return ops.conv2d_dgrad_s2(d_op, q, layer.pack(3), layer.k, ho, wo, x_op.hp, x_op.wp)
     if tc:
+        if layer.fold_out_cp == 0 and layer.pack(1).kw == 0:
+            return ops.conv2d_dgrad_s1(d_op, layer.pack(1))     # dx has the size of the conv's own (haloed) input operand
         wp_in = x_op.wp + (layer.k - 1 if layer.fold_in_cp else 0)     # a folded operand is k-1 columns narrower than the input
         dx, _ = ops.conv2d_fwd(d_op, layer.pack(1), 1, 0, x_op.hp, wp_in)
         return dx

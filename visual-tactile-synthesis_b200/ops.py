@@ -171,6 +171,14 @@ def conv2d_dgrad_gather(dy, wg, stride, hp, wp):
     return dx
 
 
+def conv2d_dgrad_s1(dy_op, w1):
+    """Stride-1 input gradient on tcgen05: dy_op carries a zero halo of k-1; w1 = mode-1 pack -> dx NHWC fp32."""
+    k = w1.k
+    dx = torch.empty((dy_op.n, dy_op.hp - k + 1, dy_op.wp - k + 1, w1.rco), dtype=torch.float32, device=dy_op.data.device)
+    L.call("skit_conv2d_dgrad_s1", dy_op.ref(), w1.ref(), _p(dx), L.stream())
+    return dx
+
+
 def conv2d_dgrad_s2(dy_op, dy_pad, wp, k, ho, wo, hp, wp_):
     """Stride-2 input gradient on tcgen05 (four parity sub-convolutions); dy_op: bf16x2, halo k/2-1."""
     dx = torch.empty((dy_op.n, hp, wp_, wp.rco), dtype=torch.float32, device=dy_op.data.device)
