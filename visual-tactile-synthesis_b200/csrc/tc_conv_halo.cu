@@ -20,6 +20,7 @@
 // Channel counts: ci any multiple of 8 (TMA zero-fills the box beyond the tensor, the K loop only issues
 // the 16-channel steps that exist), co any value with N tile in {16, 64, 128, 256} (rows beyond co are
 // zero-filled by TMA and never stored).
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace skit {
@@ -313,6 +314,288 @@ conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
     if (dbg && threadIdx.x == 0) dbg[6] = clock64();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant for layers that run several waves with N tiles of 128 or less (64 -> 128 / 128 -> 64 convs at full
+// resolution and their input gradients): one CTA per SM walks a strided list of (image, N tile, pixel tile) units.  Two TMEM
+// accumulators alternate, so the epilogue of unit i (dedicated warps 4..7: TMEM -> registers -> smem staging -> coalesced
+// stores + statistics) overlaps the main loop of unit i+1, and barrier / TMEM / descriptor setup is paid once per SM instead of
+// once per tile.  For these layers the K loop is short (9..18 tap steps), so prologue + epilogue were ~40 % of a tile.
+// Warp roles (256 threads): 0 = weight TMA, 1 = MMA issuer + TMEM allocator, 2 = activation TMA, 3 idle, 4..7 = epilogue.
+struct TcPersistP {
+    TcHaloP h;            // single region in h.reg[0]
+    int tiles, ntiles, n_img;   // pixel tiles per image, N tiles, images
+    int units;            // tiles * ntiles * n_img
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_halo_persist_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmW_hi,
+                            const __grid_constant__ CUtensorMap tmW_lo, const TcPersistP pp) {
+    constexpr int W_PLANE = BN * 128;
+    constexpr int W_STAGE = 2 * W_PLANE;
+    constexpr int TCOLS = BN < 32 ? 32 : BN;
+    constexpr int STG = 36;
+    constexpr int EPI_BYTES = 4 * 32 * STG * 4 + 4 * TCOLS * 2 * 4;   // staging tiles + statistics scratch of the 4 epilogue warps
+    const TcHaloP& p = pp.h;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+    const int a_stage = 2 * p.a_plane;
+    const int NA = p.na;
+    const uint32_t w0 = smem0 + NA * a_stage;
+    const uint32_t epi0 = w0 + p.nw * W_STAGE;
+    const uint32_t bar0 = epi0 + EPI_BYTES;
+    auto a_full = [&](int s) { return bar0 + 8u * s; };
+    auto a_empty = [&](int s) { return bar0 + 8u * (NA + s); };
+    auto w_full = [&](int s) { return bar0 + 8u * (2 * NA + s); };
+    auto w_empty = [&](int s) { return bar0 + 8u * (2 * NA + p.nw + s); };
+    auto acc_full = [&](int b) { return bar0 + 8u * (2 * NA + 2 * p.nw + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (2 * NA + 2 * p.nw + 2 + b); };
+    const uint32_t tmem_slot = bar0 + 8u * (2 * NA + 2 * p.nw + 4);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem0));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const HaloRegion R = p.reg[0];
+    const CUtensorMap* tmA_hi = &tmA.hi[0];
+    const CUtensorMap* tmA_lo = &tmA.lo[0];
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(tmA_hi); tma_prefetch_desc(tmA_lo);
+        tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
+        for (int s = 0; s < NA; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < p.nw; s++) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc<2 * TCOLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+    const int tiles_per_n = pp.tiles * pp.ntiles;
+
+    // unit u -> (image, N tile, pixel tile): pixel tiles fastest, so neighbouring CTAs share the weight tile in L2
+    auto decode = [&](int u, int& n, int& n0, int& y0, int& x0) {
+        n = u / tiles_per_n;
+        const int r = u - n * tiles_per_n;
+        const int nt = r / pp.tiles, t = r - nt * pp.tiles;
+        n0 = nt * BN;
+        const int ty = t / R.tiles_x;
+        y0 = ty * 16; x0 = (t - ty * R.tiles_x) * 8;
+    };
+
+    if (warp == 2 && lane == 0) {
+        // ---------------- activation producer
+        const uint32_t bytes = 2u * (uint32_t)R.a_rows * 128u;
+        int it = 0;
+        for (int u = blockIdx.x; u < pp.units; u += gridDim.x) {
+            int n, n0, y0, x0;
+            decode(u, n, n0, y0, x0);
+            for (int c = 0; c < p.kc; c++, it++) {
+                const int s = it % NA, ph = (it / NA) & 1;
+                mbar_wait(a_empty(s), ph ^ 1);
+                mbar_expect_tx(a_full(s), bytes);
+                const uint32_t sa = smem0 + s * a_stage;
+                tma_load_4d(sa, tmA_hi, a_full(s), c * 64, R.org_x + x0, R.org_y + y0, n);
+                tma_load_4d(sa + p.a_plane, tmA_lo, a_full(s), c * 64, R.org_x + x0, R.org_y + y0, n);
+            }
+        }
+    } else if (warp == 0 && lane == 0) {
+        // ---------------- weight producer
+        int it = 0;
+        for (int u = blockIdx.x; u < pp.units; u += gridDim.x) {
+            int n, n0, y0, x0;
+            decode(u, n, n0, y0, x0);
+            for (int c = 0; c < p.kc; c++)
+                for (int ky = 0; ky < R.kh; ky++)
+                    for (int kx = 0; kx < R.kw; kx++, it++) {
+                        const int s = it % p.nw, ph = (it / p.nw) & 1;
+                        const int tap = R.tap_base + ky * R.tap_sy + kx * R.tap_sx;
+                        mbar_wait(w_empty(s), ph ^ 1);
+                        mbar_expect_tx(w_full(s), W_STAGE);
+                        const uint32_t sw = w0 + s * W_STAGE;
+                        tma_load_3d(sw, &tmW_hi, w_full(s), c * 64, n0, tap);
+                        tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, n0, tap);
+                    }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer: accumulator (unit index & 1)
+        constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+        const uint32_t sbo_a = (uint32_t)R.pitch * 128u;
+        int ita = 0, itw = 0, ui = 0;
+        for (int u = blockIdx.x; u < pp.units; u += gridDim.x, ui++) {
+            const int b = ui & 1;
+            mbar_wait(acc_empty(b), ((ui >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator (first two uses pass)
+            tc_fence_after();
+            const uint32_t dacc = tmem_base + (uint32_t)(b * TCOLS);
+            uint32_t acc = 0;
+            for (int c = 0; c < p.kc; c++, ita++) {
+                const int s = ita % NA, ph = (ita / NA) & 1;
+                const int kkc = (c == p.kc - 1) ? p.kk_last : 4;
+                mbar_wait(a_full(s), ph);
+                tc_fence_after();
+                const uint32_t sa = smem0 + s * a_stage;
+                for (int ky = 0; ky < R.kh; ky++)
+                    for (int kx = 0; kx < R.kw; kx++, itw++) {
+                        const uint32_t arow = sa + (uint32_t)(ky * R.pitch + kx) * 128u;
+                        const int ws = itw % p.nw, wph = (itw / p.nw) & 1;
+                        mbar_wait(w_full(ws), wph);
+                        tc_fence_after();
+                        const uint32_t sw = w0 + ws * W_STAGE;
+                        for (int kk = 0; kk < kkc; kk++) {
+                            const uint32_t ko = (uint32_t)kk * 32u;
+                            const uint64_t a_hi = make_desc(arow + ko, 16, sbo_a);
+                            const uint64_t a_lo = make_desc(arow + p.a_plane + ko, 16, sbo_a);
+                            const uint64_t w_hi = make_desc(sw + ko, 16, 1024);
+                            const uint64_t w_lo = make_desc(sw + W_PLANE + ko, 16, 1024);
+                            mma_bf16(dacc, a_lo, w_hi, idesc, acc);
+                            acc = 1u;
+                            mma_bf16(dacc, a_hi, w_lo, idesc, 1u);
+                            mma_bf16(dacc, a_hi, w_hi, idesc, 1u);
+                        }
+                        mma_commit(w_empty(ws));
+                    }
+                mma_commit(a_empty(s));
+            }
+            mma_commit(acc_full(b));
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue warps: TMEM lanes 32*(warp-4) .. +31, pixel r = ty*8 + tx of the unit's tile
+        const int ew = warp - 4;
+        float* stg = reinterpret_cast<float*>(smem_gen + (epi0 - smem0)) + ew * (32 * STG);
+        float* red = reinterpret_cast<float*>(smem_gen + (epi0 - smem0)) + 4 * 32 * STG;   // [4][TCOLS][2]
+        int ui = 0;
+        for (int u = blockIdx.x; u < pp.units; u += gridDim.x, ui++) {
+            int n, n0, y0, x0;
+            decode(u, n, n0, y0, x0);
+            const int b = ui & 1;
+            mbar_wait(acc_full(b), (ui >> 1) & 1);
+            tc_fence_after();
+            const int r = ew * 32 + lane;
+            const int oy = y0 + (r >> 3), ox = x0 + (r & 7);
+            const int py = (oy + R.ooy) * p.osy + p.poy, px = (ox + R.oox) * p.osx + p.pox;
+            const bool valid = oy < R.ho && ox < R.wo && py < p.OH && px < p.OW;
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+            float* yrow = p.y + (((long long)n * p.OH + py) * p.OW + px) * p.co + n0;
+            float* rowp[8];
+            uint32_t rowok = 0;
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int rr = it * 4 + (lane >> 3);
+                const int g = ew * 32 + rr;
+                const int gy = (y0 + (g >> 3) + R.ooy) * p.osy + p.poy, gx = (x0 + (g & 7) + R.oox) * p.osx + p.pox;
+                rowp[it] = p.y + (((long long)n * p.OH + gy) * p.OW + gx) * p.co + n0 + (lane & 7) * 4;
+                rowok |= ((vmask >> rr) & 1u) << it;
+            }
+#pragma unroll 1
+            for (int c = 0; c < TCOLS; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(b * TCOLS + c), v);
+                if (c + 32 >= TCOLS) {      // last read of this accumulator: hand it back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(b));
+                }
+                if (BN >= 32 && n0 + c + 32 <= p.co) {
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] += __ldg(p.bias + n0 + c + j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(stg + lane * STG + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    __syncwarp();
+                    float4 t4[8];
+#pragma unroll
+                    for (int it = 0; it < 8; it++)
+                        t4[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * STG + (lane & 7) * 4);
+#pragma unroll
+                    for (int it = 0; it < 8; it++)
+                        if ((rowok >> it) & 1u) *reinterpret_cast<float4*>(rowp[it] + c) = t4[it];
+                    if (p.stats) {
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 32; rr++) {
+                            const float x = ((vmask >> rr) & 1u) ? stg[rr * STG + lane] : 0.f;
+                            s1 += x; s2 = fmaf(x, x, s2);
+                        }
+                        red[(ew * TCOLS + c + lane) * 2 + 0] = s1;
+                        red[(ew * TCOLS + c + lane) * 2 + 1] = s2;
+                    }
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const bool cv = n0 + c + j < p.co;
+                        v[j] = cv ? v[j] + (p.bias ? __ldg(p.bias + n0 + c + j) : 0.f) : 0.f;
+                        if (valid && cv) yrow[c + j] = v[j];
+                    }
+                    if (p.stats) {
+                        float sq[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            v[j] = valid ? v[j] : 0.f;
+                            sq[j] = v[j] * v[j];
+                        }
+                        const float s1 = col_reduce32(v, lane);
+                        const float s2 = col_reduce32(sq, lane);
+                        red[(ew * TCOLS + c + lane) * 2 + 0] = s1;
+                        red[(ew * TCOLS + c + lane) * 2 + 1] = s2;
+                    }
+                }
+            }
+            if (p.stats) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+                for (int col = threadIdx.x - 128; col < TCOLS; col += 128) {
+                    if (n0 + col >= p.co) continue;
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) { s1 += red[(w * TCOLS + col) * 2]; s2 += red[(w * TCOLS + col) * 2 + 1]; }
+                    double* dst = p.stats + ((long long)(p.stats_per_n ? n : 0) * p.co + n0 + col) * 2;
+                    atomicAdd(dst, (double)s1);
+                    atomicAdd(dst + 1, (double)s2);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // red is rewritten by the next unit
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * TCOLS>(tmem_base);
+    }
+}
+
+template <int BN>
+static int launch_halo_persist(const AMaps& amaps, const CUtensorMap& w_hi, const CUtensorMap& w_lo, TcPersistP& pp, cudaStream_t st) {
+    constexpr int W_STAGE = 2 * BN * 128;
+    constexpr int TCOLS = BN < 32 ? 32 : BN;
+    constexpr int EPI_BYTES = 4 * 32 * 36 * 4 + 4 * TCOLS * 2 * 4;
+    constexpr int MAX_SMEM = 227 * 1024;
+    TcHaloP& p = pp.h;
+    p.na = NA_MAX;
+    const int fixed = p.na * 2 * p.a_plane + EPI_BYTES + 1024 + 512;
+    int nw = (MAX_SMEM - fixed) / W_STAGE;
+    if (nw > 8) nw = 8;
+    if (nw < 2) return SKIT_ERR_UNSUPPORTED;
+    p.nw = nw;
+    const int smem = fixed + nw * W_STAGE;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_tc_halo_persist_kernel<%d>) failed: %s", BN, cudaGetErrorString(e));
+            return SKIT_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const int grid = pp.units < 148 ? pp.units : 148;
+    conv_tc_halo_persist_kernel<BN><<<grid, 256, smem, st>>>(amaps, w_hi, w_lo, pp);
+    return check_launch("conv_tc_halo_persist_kernel");
+}
+
 long long* g_dbg_buffer = nullptr;
 
 int encode_bf16_map_sw(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -403,6 +686,15 @@ static int encode_w_maps(CUtensorMap* m_hi, CUtensorMap* m_lo, const void* w_hi,
     return tc::encode_bf16_map_sw(m_lo, w_lo, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+static bool persist_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SKIT_TC_PERSIST");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 static int dispatch_halo(int BN, const tc::AMaps& am, const CUtensorMap& m_hi, const CUtensorMap& m_lo, tc::TcHaloP& p, dim3 grid, cudaStream_t st) {
     using namespace tc;
     if (BN == 256) return launch_halo<256>(am, m_hi, m_lo, p, grid, st);
@@ -444,6 +736,18 @@ int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_l
     rc = encode_w_maps(&m_hi, &m_lo, w_hi, w_lo, ci_pack, co, ntaps_total, BN);
     if (rc) return rc;
     dim3 grid(R.tiles_x * tiles_y, cdiv(co, BN), x->n);
+    const long long units = (long long)grid.x * grid.y * grid.z;
+    if (BN <= 128 && units >= 2 * 148 && units < (1ll << 30) && persist_enabled() && !p.dbg) {
+        // several waves of short tiles: persistent CTAs with two accumulators overlap each tile's epilogue with the next main loop
+        TcPersistP pp{};
+        pp.h = p;
+        pp.tiles = grid.x; pp.ntiles = grid.y; pp.n_img = grid.z; pp.units = (int)units;
+        int prc = SKIT_ERR_UNSUPPORTED;
+        if (BN == 128) prc = launch_halo_persist<128>(am, m_hi, m_lo, pp, st);
+        else if (BN == 64) prc = launch_halo_persist<64>(am, m_hi, m_lo, pp, st);
+        else prc = launch_halo_persist<16>(am, m_hi, m_lo, pp, st);
+        if (prc != SKIT_ERR_UNSUPPORTED) return prc;
+    }
     return dispatch_halo(BN, am, m_hi, m_lo, p, grid, st);
 }
 
