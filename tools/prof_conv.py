@@ -26,7 +26,7 @@ for _ in range(8):
     if which == "fwd":
         ops.conv2d_fwd(op, pk, 1, 0, s, s, stats_mode=ops.NORM_INSTANCE, impl=ops.IMPL_TC)
     elif which == "dgrad":
-        ops.conv2d_fwd(dop, pk1, 1, 0, s + 2, s + 2, impl=ops.IMPL_TC)
+        ops.conv2d_dgrad_s1(dop, pk1)     # interior + border-strip regions in one grid
     else:
         ops.conv2d_wgrad(op, 0, dop0, 0, 3, 1, s, s, dw, None, impl=ops.IMPL_TC)
 torch.cuda.synchronize()
