@@ -11,7 +11,8 @@ import vts_b200  # noqa: E402
 from oracle import skit_oracle as O  # noqa: E402  (synthetic batch factory only)
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-opt = vts_b200.default_options()
+arch = sys.argv[2] if len(sys.argv) > 2 else "B"
+opt = vts_b200.default_options() if arch == "B" else vts_b200.default_options(netG="unet256_custom", ngf=10, ndf=8)
 torch.manual_seed(0)
 m = vts_b200.SinSKITGModel(opt)
 m.set_input(O.synthetic_batch(size, NT=64, seed=0))

@@ -24,6 +24,8 @@ struct ConvP {
     int flat;             // 1: rows run over the whole batch (n*M), grid.z == 1 (batch statistics only)
     int n_img;
     int crop;             // dgrad as a transposed conv: output row m maps to padded coordinate (y + crop, x + crop)
+    int phased;           // MODE 1, stride > 1: grid.z = image * stride^2 + parity class; a block's rows share the parity of
+                          // (y + crop, x + crop), so only the (k/stride)^2 taps that can hit an output sample are visited
     int yc, yoff;         // output channel stride / offset (0: dense ncol) — writes a channel slice of a wider map
 };
 
@@ -35,12 +37,27 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
-    const int nz = blockIdx.z;
+    int nz = blockIdx.z;
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int kk = tid & 15, rg = tid >> 4;
     const int ty = tid >> 4, tx = tid & 15;
-    const long long Mtot = p.flat ? (long long)p.n_img * p.M : p.M;
+    long long Mtot = p.flat ? (long long)p.n_img * p.M : p.M;
+    // parity-class geometry (phased gather dgrad): class (py, px) of (y + crop, x + crop) mod stride
+    int ph_py = 0, ph_px = 0, ph_y0 = 0, ph_x0 = 0, ph_nx = 1, ph_kty = 1, ph_ktx = 1, Keff = p.K;
+    if (MODE == 1 && p.phased) {
+        const int s = p.stride, cls = blockIdx.z % (s * s);
+        nz = blockIdx.z / (s * s);
+        ph_py = cls / s; ph_px = cls - ph_py * s;
+        ph_y0 = ((ph_py - p.crop) % s + s) % s;      // first output row of this class
+        ph_x0 = ((ph_px - p.crop) % s + s) % s;
+        const int ny = p.hp > ph_y0 ? (p.hp - ph_y0 + s - 1) / s : 0;
+        ph_nx = p.wp > ph_x0 ? (p.wp - ph_x0 + s - 1) / s : 0;
+        Mtot = (long long)ny * ph_nx;
+        ph_kty = (p.k - ph_py + s - 1) / s; ph_ktx = (p.k - ph_px + s - 1) / s;
+        Keff = ph_kty * ph_ktx * p.arows;
+        if (m0 >= Mtot) return;
+    }
 
     long long base[8];
     int ry[8], rx[8], rn[8];
@@ -56,6 +73,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
             int oy = m / p.wo, ox = m - oy * p.wo;
             base[i] = (((long long)n * p.hp + p.org + oy * p.stride) * p.wp + p.org + ox * p.stride) * p.ci;
             ry[i] = 0; rx[i] = 0;
+        } else if (p.phased) {
+            const int jy = ph_nx ? m / ph_nx : 0, jx = m - jy * ph_nx;
+            ry[i] = ph_y0 + jy * p.stride + p.crop; rx[i] = ph_x0 + jx * p.stride + p.crop;
+            base[i] = 0;
         } else {
             int iy = m / p.wp, ix = m - iy * p.wp;
             ry[i] = iy + p.crop; rx[i] = ix + p.crop;
@@ -70,9 +91,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
 
     const int brow = tid >> 4, bcol = (tid & 15) * 4;
 
-    for (int k0 = 0; k0 < p.K; k0 += BK) {
+    for (int k0 = 0; k0 < Keff; k0 += BK) {
         const int kg = k0 + kk;
-        const bool kvalid = kg < p.K;
+        const bool kvalid = kg < Keff;
         if (MODE == 0) {
             int tap = kg / p.ci, c = kg - tap * p.ci;
             int ky = tap / p.k, kx = tap - ky * p.k;
@@ -89,6 +110,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
         } else {
             int tap = kg / p.arows, o = kg - tap * p.arows;
             int ky = tap / p.k, kx = tap - ky * p.k;
+            if (p.phased) {     // tap = index among the class's valid taps
+                const int tyi = tap / ph_ktx, txi = tap - tyi * ph_ktx;
+                ky = ph_py + tyi * p.stride; kx = ph_px + txi * p.stride;
+            }
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 float v = 0.f;
@@ -105,10 +130,16 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
         }
         {
             const int kgb = k0 + brow;
+            long long wrow = kgb;
+            if (MODE == 1 && p.phased) {    // row of the [(ky*k + kx)*arows + o][ncol] pack for this class-local K index
+                const int tap = kgb / p.arows, o = kgb - tap * p.arows;
+                const int tyi = tap / ph_ktx, txi = tap - tyi * ph_ktx;
+                wrow = (long long)((ph_py + tyi * p.stride) * p.k + ph_px + txi * p.stride) * p.arows + o;
+            }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 int col = n0 + bcol + j;
-                Bs[brow][bcol + j] = (kgb < p.K && col < p.ncol) ? __ldg(p.w + (long long)kgb * p.ncol + col) : 0.f;
+                Bs[brow][bcol + j] = (kgb < Keff && col < p.ncol) ? __ldg(p.w + wrow * p.ncol + col) : 0.f;
             }
         }
         __syncthreads();
@@ -134,12 +165,17 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
     for (int i = 0; i < 8; i++) {
         int m = m0 + ty * 8 + i;
         if (m >= Mtot) continue;
+        long long mout = m;
+        if (MODE == 1 && p.phased) {    // class-local row -> position in the full output map
+            const int jy = m / ph_nx, jx = m - jy * ph_nx;
+            mout = (long long)(ph_y0 + jy * p.stride) * p.wp + ph_x0 + jx * p.stride;
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int col = n0 + tx * 4 + j;
             if (col >= p.ncol) continue;
             float v = acc[i][j] + (p.bias ? p.bias[col] : 0.f);
-            p.y[((long long)(p.flat ? 0 : nz) * p.M + m) * (p.yc ? p.yc : p.ncol) + p.yoff + col] = v;
+            p.y[((long long)(p.flat ? 0 : nz) * p.M + mout) * (p.yc ? p.yc : p.ncol) + p.yoff + col] = v;
             s[j] += v; q[j] += v * v;
         }
     }
@@ -643,6 +679,13 @@ extern "C" int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, 
     p.ncol = wg->co; p.K = wg->k * wg->k * co; p.M = hp * wp; p.arows = co;
     if (p.ncol <= 8 && co % 32 == 0) return launch_thin<1, SKIT_FMT_F32>(p, n, as_stream(stream));
     p.n_img = n;
+    if (stride > 1 && wg->k % stride == 0) {   // parity classes: 1/stride^2 of the taps per class
+        p.phased = 1; p.flat = 0;
+        const int mclass = cdiv(hp, stride) * cdiv(wp, stride);
+        dim3 grid(cdiv(mclass, BM), cdiv(p.ncol, BN), n * stride * stride);
+        conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
+        return check_launch("conv_simt_kernel<dgrad,phased>");
+    }
     p.flat = (n > 1 && p.M < 4 * BM) ? 1 : 0;
     dim3 grid(p.flat ? cdiv(n * p.M, BM) : cdiv(p.M, BM), cdiv(p.ncol, BN), p.flat ? 1 : n);
     conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
@@ -668,6 +711,13 @@ extern "C" int skit_conv_transpose2d_fwd(const float* x, int n, int h, int w, in
     p.ncol = wg->co; p.K = wg->k * wg->k * ci; p.M = ho * wo; p.arows = ci;
     p.crop = pad; p.yc = y_ctot; p.yoff = y_c0;
     p.n_img = n; p.flat = 0;
+    if (stride > 1 && wg->k % stride == 0) {
+        p.phased = 1;
+        const int mclass = cdiv(ho, stride) * cdiv(wo, stride);
+        dim3 grid(cdiv(mclass, BM), cdiv(p.ncol, BN), n * stride * stride);
+        conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
+        return check_launch("conv_simt_kernel<convT,phased>");
+    }
     dim3 grid(cdiv(p.M, BM), cdiv(p.ncol, BN), n);
     conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
     return check_launch("conv_simt_kernel<convT>");
