@@ -30,10 +30,15 @@ struct ConvP {
 };
 
 constexpr int BM = 128, BN = 64, BK = 16;
+// 16-wide column tiles when that covers the columns with at most half the padding of 64-wide ones
+static inline bool narrow_tile(int ncol) { return ((ncol + 15) / 16) * 16 * 2 <= ((ncol + 63) / 64) * 64; }
 
-// MODE 0: forward valid conv.  MODE 1: gather dgrad.
-template <int MODE, int FMT>
+// MODE 0: forward valid conv.  MODE 1: gather dgrad.  CPT = output columns per thread: the tile is 128 rows x 16*CPT
+// columns (64 wide by default; 16 wide for the default U-Net's thin layers, whose 2..20 output channels would leave a
+// 64-wide tile mostly empty).
+template <int MODE, int FMT, int CPT = 4>
 __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
+    constexpr int BN = 16 * CPT;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -83,13 +88,13 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
             base[i] = 0;
         }
     }
-    float acc[8][4];
+    float acc[8][CPT];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+        for (int j = 0; j < CPT; j++) acc[i][j] = 0.f;
 
-    const int brow = tid >> 4, bcol = (tid & 15) * 4;
+    const int brow = tid >> 4, bcol = (tid & 15) * CPT;
 
     for (int k0 = 0; k0 < Keff; k0 += BK) {
         const int kg = k0 + kk;
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
                 wrow = (long long)((ph_py + tyi * p.stride) * p.k + ph_px + txi * p.stride) * p.arows + o;
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < CPT; j++) {
                 int col = n0 + bcol + j;
                 Bs[brow][bcol + j] = (kgb < Keff && col < p.ncol) ? __ldg(p.w + wrow * p.ncol + col) : 0.f;
             }
@@ -145,22 +150,25 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
         __syncthreads();
 #pragma unroll
         for (int k2 = 0; k2 < BK; k2++) {
-            float a[8], b[4];
+            float a[8], b[CPT];
             const float4 a0 = *reinterpret_cast<const float4*>(&As[k2][ty * 8]);
             const float4 a1 = *reinterpret_cast<const float4*>(&As[k2][ty * 8 + 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k2][tx * 4]);
+
             a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
             a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+#pragma unroll
+            for (int j = 0; j < CPT; j++) b[j] = Bs[k2][tx * CPT + j];
 #pragma unroll
             for (int i = 0; i < 8; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < CPT; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 
-    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    float s[CPT], q[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; j++) { s[j] = 0.f; q[j] = 0.f; }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         int m = m0 + ty * 8 + i;
@@ -171,8 +179,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
             mout = (long long)(ph_y0 + jy * p.stride) * p.wp + ph_x0 + jx * p.stride;
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int col = n0 + tx * 4 + j;
+        for (int j = 0; j < CPT; j++) {
+            int col = n0 + tx * CPT + j;
             if (col >= p.ncol) continue;
             float v = acc[i][j] + (p.bias ? p.bias[col] : 0.f);
             p.y[((long long)(p.flat ? 0 : nz) * p.M + mout) * (p.yc ? p.yc : p.ncol) + p.yoff + col] = v;
@@ -184,9 +192,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
         if (tid < 2 * BN) red[tid] = 0.f;
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            atomicAdd(&red[tx * 4 + j], s[j]);
-            atomicAdd(&red[BN + tx * 4 + j], q[j]);
+        for (int j = 0; j < CPT; j++) {
+            atomicAdd(&red[tx * CPT + j], s[j]);
+            atomicAdd(&red[BN + tx * CPT + j], q[j]);
         }
         __syncthreads();
         if (tid < BN && n0 + tid < p.ncol) {
@@ -608,9 +616,12 @@ int conv_fwd_simt(const skit_operand* x, const skit_weights* w, int stride, int 
     }
     p.n_img = x->n;
     p.flat = (x->n > 1 && p.M < 4 * BM && !p.stats_per_n) ? 1 : 0;  // many small images: tile over the whole batch
-    dim3 grid(p.flat ? cdiv(x->n * p.M, BM) : cdiv(p.M, BM), cdiv(p.ncol, BN), p.flat ? 1 : x->n);
-    if (x->fmt == SKIT_FMT_F32) conv_simt_kernel<0, SKIT_FMT_F32><<<grid, 256, 0, st>>>(p);
-    else conv_simt_kernel<0, SKIT_FMT_BF16X2><<<grid, 256, 0, st>>>(p);
+    const int bn = narrow_tile(p.ncol) ? 16 : BN;
+    dim3 grid(p.flat ? cdiv(x->n * p.M, BM) : cdiv(p.M, BM), cdiv(p.ncol, bn), p.flat ? 1 : x->n);
+    if (x->fmt == SKIT_FMT_F32) {
+        if (bn == 16) conv_simt_kernel<0, SKIT_FMT_F32, 1><<<grid, 256, 0, st>>>(p);
+        else conv_simt_kernel<0, SKIT_FMT_F32><<<grid, 256, 0, st>>>(p);
+    } else conv_simt_kernel<0, SKIT_FMT_BF16X2><<<grid, 256, 0, st>>>(p);
     return check_launch("conv_simt_kernel<fwd>");
 }
 
@@ -682,8 +693,10 @@ extern "C" int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, 
     if (stride > 1 && wg->k % stride == 0) {   // parity classes: 1/stride^2 of the taps per class
         p.phased = 1; p.flat = 0;
         const int mclass = cdiv(hp, stride) * cdiv(wp, stride);
-        dim3 grid(cdiv(mclass, BM), cdiv(p.ncol, BN), n * stride * stride);
-        conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
+        const int bn = narrow_tile(p.ncol) ? 16 : BN;
+        dim3 grid(cdiv(mclass, BM), cdiv(p.ncol, bn), n * stride * stride);
+        if (bn == 16) conv_simt_kernel<1, SKIT_FMT_F32, 1><<<grid, 256, 0, as_stream(stream)>>>(p);
+        else conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
         return check_launch("conv_simt_kernel<dgrad,phased>");
     }
     p.flat = (n > 1 && p.M < 4 * BM) ? 1 : 0;
@@ -714,8 +727,10 @@ extern "C" int skit_conv_transpose2d_fwd(const float* x, int n, int h, int w, in
     if (stride > 1 && wg->k % stride == 0) {
         p.phased = 1;
         const int mclass = cdiv(ho, stride) * cdiv(wo, stride);
-        dim3 grid(cdiv(mclass, BM), cdiv(p.ncol, BN), n * stride * stride);
-        conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
+        const int bn = narrow_tile(p.ncol) ? 16 : BN;
+        dim3 grid(cdiv(mclass, BM), cdiv(p.ncol, bn), n * stride * stride);
+        if (bn == 16) conv_simt_kernel<1, SKIT_FMT_F32, 1><<<grid, 256, 0, as_stream(stream)>>>(p);
+        else conv_simt_kernel<1, SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p);
         return check_launch("conv_simt_kernel<convT,phased>");
     }
     dim3 grid(cdiv(p.M, BM), cdiv(p.ncol, BN), n);
