@@ -301,6 +301,142 @@ static int launch_thin(const ConvP& p, int n_img, cudaStream_t st) {
     return check_launch("conv_thin_kernel");
 }
 
+// ---------------------------------------------------------------------------------- thin-output 7x7 head
+// Generator head: Conv2d(64 -> 5, k7) over the reflect-padded activation (networks.py:1124-1126).  On the tensor cores this
+// layer wastes >95 % of every MMA (5 useful columns) and is bound by the per-MMA operand fetch (0.55 ms at 512x512); its
+// 8.2 GFLOP fit the fp32 pipes better.  A block owns a 32x32 output tile; a thread owns the 2x2 pixels (tx + 16a, ty + 16b)
+// so that a warp's shared-memory reads are consecutive 16-byte pixel quads (conflict free), and walks the 64 input channels in
+// chunks of 8: the (32+6)^2 x 8 input tile and the chunk's 49 x 8 x CO weights sit in shared memory as channel quads.  Per
+// (tap, quad): 4 input float4 + CO broadcast weight float4 feed 4*CO*4 FMAs — FMA bound, not LDS bound.
+// Operand: fp32 or bf16 hi/lo; weights: the tcgen05 pack (bf16 hi/lo [tap][co][ci]) or nullptr planes -> fp32 pack.
+template <int CO>
+__global__ void __launch_bounds__(256) conv_head7_kernel(const float* __restrict__ x0, const __nv_bfloat16* __restrict__ xh,
+                                                         const __nv_bfloat16* __restrict__ xl, int fmt, int hp, int wp, int ci, int org,
+                                                         const __nv_bfloat16* __restrict__ wh, const __nv_bfloat16* __restrict__ wl, int wci,
+                                                         const float* __restrict__ bias, float* __restrict__ y, int ho, int wo, int co) {
+    constexpr int T = 32, HT = T + 6, CH = 8;
+    extern __shared__ float4 sm4[];
+    float4* sx = sm4;                              // [2 quads][HT][HT]
+    float4* sw = sm4 + 2 * HT * HT;                // [49 taps][2 quads][CO]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int n = blockIdx.z;
+    const int x_0 = blockIdx.x * T, y_0 = blockIdx.y * T;
+    float acc[2][2][CO];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int o = 0; o < CO; o++) acc[a][b][o] = 0.f;
+
+    for (int c0 = 0; c0 < ci; c0 += CH) {
+        // stage the input tile: one (pixel, quad) per thread-iteration
+        for (int i = threadIdx.x; i < 2 * HT * HT; i += 256) {
+            const int q = i / (HT * HT), r = i - q * HT * HT;
+            const int py = r / HT, px = r - py * HT;
+            const int gy = org + y_0 + py, gx = org + x_0 + px;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy < hp && gx < wp) {
+                const long long a = (((long long)n * hp + gy) * wp + gx) * ci + c0 + q * 4;
+                if (fmt == SKIT_FMT_F32) v = *reinterpret_cast<const float4*>(x0 + a);
+                else {
+                    const uint2 h = *reinterpret_cast<const uint2*>(xh + a), l = *reinterpret_cast<const uint2*>(xl + a);
+                    const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&h.y);
+                    const __nv_bfloat162 l0 = *reinterpret_cast<const __nv_bfloat162*>(&l.x), l1 = *reinterpret_cast<const __nv_bfloat162*>(&l.y);
+                    v.x = __bfloat162float(h0.x) + __bfloat162float(l0.x); v.y = __bfloat162float(h0.y) + __bfloat162float(l0.y);
+                    v.z = __bfloat162float(h1.x) + __bfloat162float(l1.x); v.w = __bfloat162float(h1.y) + __bfloat162float(l1.y);
+                }
+            }
+            sx[i] = v;
+        }
+        // stage the chunk's weights: sw[(tap*2 + q)*CO + o] = w[tap][o][c0 + 4q .. +3]
+        for (int i = threadIdx.x; i < 49 * 2 * CO; i += 256) {
+            const int o = i % CO, t = i / CO;
+            const int q = t & 1, tap = t >> 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o < co) {
+                const long long a = ((long long)tap * co + o) * wci + c0 + q * 4;
+                float f[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) f[j] = __bfloat162float(wh[a + j]) + __bfloat162float(wl[a + j]);
+                v = make_float4(f[0], f[1], f[2], f[3]);
+            }
+            sw[i] = v;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int ky = 0; ky < 7; ky++) {
+#pragma unroll
+            for (int kx = 0; kx < 7; kx++) {
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    float4 in[2][2];
+#pragma unroll
+                    for (int a = 0; a < 2; a++)
+#pragma unroll
+                        for (int b = 0; b < 2; b++)
+                            in[a][b] = sx[(q * HT + ty + 16 * b + ky) * HT + tx + 16 * a + kx];
+                    const float4* wq = sw + ((ky * 7 + kx) * 2 + q) * CO;
+#pragma unroll
+                    for (int o = 0; o < CO; o++) {
+                        const float4 w4 = wq[o];
+#pragma unroll
+                        for (int a = 0; a < 2; a++)
+#pragma unroll
+                            for (int b = 0; b < 2; b++) {
+                                float t = acc[a][b][o];
+                                t = fmaf(in[a][b].x, w4.x, t); t = fmaf(in[a][b].y, w4.y, t);
+                                t = fmaf(in[a][b].z, w4.z, t); t = fmaf(in[a][b].w, w4.w, t);
+                                acc[a][b][o] = t;
+                            }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const int ox = x_0 + tx + 16 * a, oy = y_0 + ty + 16 * b;
+            if (ox >= wo || oy >= ho) continue;
+            float* dst = y + (((long long)n * ho + oy) * wo + ox) * co;
+#pragma unroll
+            for (int o = 0; o < CO; o++)
+                if (o < co) dst[o] = acc[a][b][o] + (bias ? bias[o] : 0.f);
+        }
+}
+
+bool conv_head7_eligible(const skit_operand* x, const skit_weights* w, int stride, const double* stats) {
+    return w->k == 7 && w->kw == 0 && stride == 1 && w->co <= 8 && !stats && w->hi && w->lo && x->c % 8 == 0 && w->ci == x->c &&
+           (x->fmt == SKIT_FMT_F32 || x->fmt == SKIT_FMT_BF16X2);
+}
+
+int conv_head7_launch(const skit_operand* x, const skit_weights* w, int org, int ho, int wo, const float* bias, float* y, cudaStream_t st) {
+    constexpr int T = 32, HT = T + 6;
+    const size_t smem = (size_t)(2 * HT * HT + 49 * 2 * 8) * sizeof(float4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_head7_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_head7_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_head7_kernel) failed: %s", cudaGetErrorString(e));
+            return SKIT_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid(cdiv(wo, T), cdiv(ho, T), x->n);
+    const __nv_bfloat16 *wh = (const __nv_bfloat16*)w->hi, *wl = (const __nv_bfloat16*)w->lo;
+    if (w->co <= 5)
+        conv_head7_kernel<5><<<grid, 256, smem, st>>>((const float*)x->p0, (const __nv_bfloat16*)x->p0, (const __nv_bfloat16*)x->p1, x->fmt,
+                                                     x->hp, x->wp, x->c, org, wh, wl, w->ci, bias, y, ho, wo, w->co);
+    else
+        conv_head7_kernel<8><<<grid, 256, smem, st>>>((const float*)x->p0, (const __nv_bfloat16*)x->p0, (const __nv_bfloat16*)x->p1, x->fmt,
+                                                     x->hp, x->wp, x->c, org, wh, wl, w->ci, bias, y, ho, wo, w->co);
+    return check_launch("conv_head7_kernel");
+}
+
 // ---------------------------------------------------------------------------------- wgrad
 struct WgradP {
     const float* x0; const __nv_bfloat16* xh; const __nv_bfloat16* xl;

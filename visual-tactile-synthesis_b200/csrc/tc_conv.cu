@@ -323,6 +323,8 @@ int conv_fwd_tc(const skit_operand* x, const skit_weights* w, int stride, int or
 
 int conv_fwd_simt(const skit_operand* x, const skit_weights* w, int stride, int org, int ho, int wo,
                   const float* bias, float* y, double* stats, int stats_mode, cudaStream_t st);
+bool conv_head7_eligible(const skit_operand* x, const skit_weights* w, int stride, const double* stats);   // simt_conv.cu
+int conv_head7_launch(const skit_operand* x, const skit_weights* w, int org, int ho, int wo, const float* bias, float* y, cudaStream_t st);
 
 }  // namespace skit
 
@@ -345,6 +347,8 @@ extern "C" int skit_conv2d_fwd(const skit_operand* x, const skit_weights* w, int
         set_error("conv2d_fwd: shape not eligible for the tcgen05 path (fmt=%d ci=%d co=%d stride=%d)", x->fmt, x->c, w->co, stride);
         return SKIT_ERR_UNSUPPORTED;
     }
+    if (impl == SKIT_IMPL_AUTO && conv_head7_eligible(x, w, stride, stats))    // 7x7 with <= 8 output channels: fp32 pipes beat the MMA waste
+        return conv_head7_launch(x, w, org, ho, wo, bias, y, as_stream(stream));
     if (tc_ok && impl != SKIT_IMPL_SIMT) return conv_fwd_tc(x, w, stride, org, ho, wo, bias, y, stats, stats_mode, as_stream(stream));
     SKIT_REQUIRE(w->f32, "conv2d_fwd: CUDA-core path needs the fp32 weight pack");
     return conv_fwd_simt(x, w, stride, org, ho, wo, bias, y, stats, stats_mode, as_stream(stream));
