@@ -36,7 +36,7 @@ UNIT = "images/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -75,7 +75,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05)
 
     def __enter__(self):
         self.t.start()
