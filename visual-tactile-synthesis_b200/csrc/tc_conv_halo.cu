@@ -68,16 +68,6 @@ struct TcHaloP {
 
 constexpr int NA_MAX = 2;  // activation stages
 
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;  // LBO unused for swizzled K-major
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;  // SWIZZLE_64B
-    return d;
-}
-
 template <int BN>
 __global__ void __launch_bounds__(128, 1)
 conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,

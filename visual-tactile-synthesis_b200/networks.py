@@ -211,6 +211,9 @@ def _wgrad_async(fn, keep):
     cur = torch.cuda.current_stream()
     ent = _WG.get(cur.cuda_stream)
     if ent is None:
+        if len(_WG) > 64:      # every graph capture runs on a fresh stream: drop idle entries of streams long gone
+            for k in [k for k, v in _WG.items() if not v[1]]:
+                del _WG[k]
         ent = (torch.cuda.Stream(device=cur.device), [])
         _WG[cur.cuda_stream] = ent
     side, ka = ent
