@@ -120,6 +120,14 @@ int skit_fold_x_operand(const skit_operand* thin, int kw, const skit_operand* fo
  * xf: folded operand (c = 64), dy: bf16x2 operand with 64-multiple channels; scratch: k*64*dy->c floats, zeroed. */
 int skit_conv2d_wgrad_folded(const skit_operand* xf, int org, const skit_operand* dy, int dy_org, int k, int kw, int cp,
                              int ho, int wo, float* scratch, float* dw, int co_real, int ci_real, void* stream);
+/* Weight gradient of a thin-OUTPUT k x k layer against the x-folded GRADIENT operand (the one its input gradient uses):
+ *   dw[o][c][ky][kx] += sum_{y, X} dyf[y + k-1][X][(k-1-kx)*cp + o] * x[y + ky][X][c],  y < ho, X < wo + k - 1
+ * x: the layer's haloed bf16x2 input operand (64-multiple channels); dyf = skit_fold_x_operand(dy haloed by k-1, k);
+ * scratch: k*64*x->c floats, zeroed.  k row taps instead of k*k passes over x. */
+int skit_conv2d_wgrad_dyfolded(const skit_operand* x, const skit_operand* dyf, int k, int cp, int ho, int wo,
+                               float* scratch, float* dw, int co_real, int ci_real, void* stream);
+/* skit_dbias over the first nch channels only (channel-padded gradient operands). */
+int skit_dbias_n(const skit_operand* dy, int dy_org, int ho, int wo, int nch, float* dbias, void* stream);
 /* Inverse of the forward pack for gradients: dWf [(tap*ci+c)][o] fp32 -> dw[o][c][ky][kx] (+= if accumulate). */
 int skit_unpack_conv_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, void* stream);
 

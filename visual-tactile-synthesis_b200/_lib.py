@@ -45,6 +45,8 @@ SIGNATURES = {
     "skit_pack_conv_weights_folded": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
     "skit_fold_x_operand": [_OP, _I, _OP, _P],
     "skit_conv2d_wgrad_folded": [_OP, _I, _OP, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
+    "skit_conv2d_wgrad_dyfolded": [_OP, _OP, _I, _I, _I, _I, _P, _P, _I, _I, _P],
+    "skit_dbias_n": [_OP, _I, _I, _I, _I, _P, _P],
     "skit_unpack_conv_wgrad": [_P, _I, _I, _I, _P, _I, _P],
     "skit_conv2d_fwd": [_OP, _WT, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "skit_conv2d_dgrad_gather": [_P, _I, _I, _I, _I, _WT, _I, _I, _I, _P, _P],

@@ -738,6 +738,20 @@ __global__ void unpack_wgrad_folded_kernel(const float* __restrict__ dwf, int co
     }
 }
 
+// dwf from wgrad_tc with an x-folded GRADIENT operand (taps = ky; gradient channels j = (kw-1-kx)*cp + o):
+// layout 0: [(ky*cip + c)*64 + j], layout 1: [(ky*64 + j)*cip + c]
+__global__ void unpack_wgrad_dyfolded_kernel(const float* __restrict__ dwf, int co, int ci, int k, int kw, int cp, float* dw, int layout, int cip) {
+    const long long total = (long long)co * ci * k * kw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int kx = i % kw; long long t = i / kw;
+        int ky = t % k; t /= k;
+        int c = t % ci; int o = t / ci;
+        const int j = (kw - 1 - kx) * cp + o;
+        const float v = layout == 0 ? dwf[((long long)ky * cip + c) * 64 + j] : dwf[((long long)ky * 64 + j) * cip + c];
+        atomicAdd(dw + i, v);
+    }
+}
+
 int conv_fwd_simt(const skit_operand* x, const skit_weights* w, int stride, int org, int ho, int wo,
                   const float* bias, float* y, double* stats, int stats_mode, cudaStream_t st) {
     ConvP p{};
@@ -890,7 +904,7 @@ extern "C" int skit_dbias(const skit_operand* dy, int dy_org, int ho, int wo, fl
 
 namespace skit {
 int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org, int k, int stride,
-             int ho, int wo, float* partial, int* layout, cudaStream_t st, int kw = 0);  // tc_wgrad.cu
+             int ho, int wo, float* partial, int* layout, cudaStream_t st, int kw = 0, int dy_org_y = -1);  // tc_wgrad.cu
 bool wgrad_tc_eligible(const skit_operand* x, const skit_operand* dy, int k, int stride, int ho, int wo);
 }
 
@@ -986,4 +1000,38 @@ extern "C" int skit_conv2d_wgrad_folded(const skit_operand* xf, int org, const s
     int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
     unpack_wgrad_folded_kernel<<<blocks, 256, 0, st>>>(scratch, co_real, ci_real, k, kw, cp, dw, layout, dy->c);
     return check_launch("unpack_wgrad_folded_kernel");
+}
+
+
+/* Weight gradient of a thin-OUTPUT k x k layer (generator head 64 -> 5, k7) against the x-folded gradient operand that its input
+ * gradient already uses:  dw[o][c][ky][kx] += sum_{y,X} dyf[y + k-1][X][(k-1-kx)*cp + o] * x[y + ky][X][c],  X over W + k - 1
+ * columns — 7 row taps with the column taps inside the folded channels, instead of 49 passes over x. */
+extern "C" int skit_conv2d_wgrad_dyfolded(const skit_operand* x, const skit_operand* dyf, int k, int cp, int ho, int wo,
+                                          float* scratch, float* dw, int co_real, int ci_real, void* stream) {
+    SKIT_REQUIRE(x && dyf && scratch && dw && x->p0 && x->p1 && dyf->p0 && dyf->p1, "conv2d_wgrad_dyfolded: null pointer");
+    SKIT_REQUIRE(x->fmt == SKIT_FMT_BF16X2 && dyf->fmt == SKIT_FMT_BF16X2 && dyf->c == 64 && x->c % 64 == 0, "conv2d_wgrad_dyfolded: needs bf16x2 operands, 64 folded channels");
+    SKIT_REQUIRE(k * cp <= 64 && co_real <= cp && ci_real <= x->c && x->n == dyf->n, "conv2d_wgrad_dyfolded: bad fold geometry");
+    SKIT_REQUIRE(x->hp >= ho + k - 1 && x->wp >= wo + k - 1 && dyf->hp >= ho + k - 1 && dyf->wp >= wo + k - 1, "conv2d_wgrad_dyfolded: operands too small");
+    cudaStream_t st = as_stream(stream);
+    int layout = 0;
+    // pixel domain: ho rows x (wo + k - 1) columns; x is read at (y + ky, X), the folded gradient at (y + k - 1, X)
+    int rc = wgrad_tc(x, 0, dyf, 0, k, 1, ho, wo + k - 1, scratch, &layout, st, 1, k - 1);
+    if (rc) return rc;
+    long long total = (long long)co_real * ci_real * k * k;
+    int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
+    unpack_wgrad_dyfolded_kernel<<<blocks, 256, 0, st>>>(scratch, co_real, ci_real, k, k, cp, dw, layout, x->c);
+    return check_launch("unpack_wgrad_dyfolded_kernel");
+}
+
+extern "C" int skit_dbias_n(const skit_operand* dy, int dy_org, int ho, int wo, int nch, float* dbias, void* stream) {
+    SKIT_REQUIRE(dy && dy->p0 && dbias && ho > 0 && wo > 0 && nch > 0 && nch <= dy->c, "dbias_n: bad arguments");
+    SKIT_REQUIRE(dy_org + ho <= dy->hp && dy_org + wo <= dy->wp, "dbias_n: window exceeds the operand");
+    const int P = ho * wo, n = dy->n;
+    int chunk = max(64, cdiv(P, max(1, (148 * 4) / n)));
+    dim3 grid(cdiv(P, chunk), n);
+    if (dy->fmt == SKIT_FMT_F32)
+        dbias_kernel<0><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, nch, dy->c, dy_org, ho, wo, chunk, dbias);
+    else
+        dbias_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(nullptr, (const __nv_bfloat16*)dy->p0, (const __nv_bfloat16*)dy->p1, dy->hp, dy->wp, nch, dy->c, dy_org, ho, wo, chunk, dbias);
+    return check_launch("dbias_kernel");
 }

@@ -22,7 +22,7 @@ struct TcWgradP {
     int tiles_per_cta;     // split-K chunk (in pixel tiles, over all images)
     int total_tiles;
     int m_is_x;            // 1: M operand is the (tap-shifted, strided) input, N operand the gradient; 0: the reverse
-    int x_org, x_stride, d_org;
+    int x_org, x_stride, d_org, d_org_y;   // d_org: gradient-side column origin; d_org_y: its row origin
     int Mdim, Ndim;        // channel counts of the M / N side
     float* out;            // [tap][Ndim][Mdim] fp32 partial sums (zeroed by the caller)
 };
@@ -84,7 +84,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
                 const int img = t / tpi, r = t - img * tpi;
                 const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
                 const int xx = p.x_org + tx * 8 * p.x_stride + kx, xy = p.x_org + ty * 8 * p.x_stride + ky;  // input side
-                const int dx = p.d_org + tx * 8, dy = p.d_org + ty * 8;                                       // gradient side
+                const int dx = p.d_org + tx * 8, dy = p.d_org_y + ty * 8;                                       // gradient side
                 const int mx = p.m_is_x ? xx : dx, my = p.m_is_x ? xy : dy;
                 const int nx = p.m_is_x ? dx : xx, ny = p.m_is_x ? dy : xy;
                 const uint32_t sa = smem0 + s * STAGE_BYTES;
@@ -189,7 +189,7 @@ bool wgrad_tc_eligible(const skit_operand* x, const skit_operand* dy, int k, int
 }
 
 int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org, int k, int stride,
-             int ho, int wo, float* partial, int* layout, cudaStream_t st, int kw = 0) {
+             int ho, int wo, float* partial, int* layout, cudaStream_t st, int kw = 0, int dy_org_y = -1) {
     using namespace tc;
     const int ci = x->c, co = dy->c;
     TcWgradP p{};
@@ -204,7 +204,7 @@ int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
     else if (co % 128 == 0 && ci % 64 == 0) p.m_is_x = 0;
     else if (ci % 128 == 0 && co % 64 == 0) p.m_is_x = 1;
     else p.m_is_x = ci > co ? 1 : 0;
-    p.x_org = org; p.x_stride = stride; p.d_org = dy_org;
+    p.x_org = org; p.x_stride = stride; p.d_org = dy_org; p.d_org_y = dy_org_y >= 0 ? dy_org_y : dy_org;
     p.Mdim = p.m_is_x ? ci : co;
     p.Ndim = p.m_is_x ? co : ci;
     p.out = partial;

@@ -429,8 +429,14 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
             q = lo.k - 1
             d30 = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, q, fmt=FMT_BF16X2, cpad=lo.co_pad)
             op26 = ctx["op26"]
-            _wgrad_async(lambda: ops.conv2d_wgrad(op26, 0, d30, q, lo.k, 1, S_h, S_w, lo.weight.grad, lo.bias.grad), (op26, d30))
             d30f = ops.fold_x(d30, lo.k) if lo.fold_out_cp else d30
+            if lo.fold_out_cp and op26.c % 64 == 0:     # 7 row taps against the folded gradient instead of 49 passes over op26
+                def wg():
+                    ops.conv2d_wgrad_dyfolded(op26, d30f, lo.k, lo.fold_out_cp, S_h, S_w, lo.weight.grad)
+                    ops.dbias_n(d30, q, S_h, S_w, lo.co, lo.bias.grad)
+                _wgrad_async(wg, (op26, d30, d30f))
+            else:
+                _wgrad_async(lambda: ops.conv2d_wgrad(op26, 0, d30, q, lo.k, 1, S_h, S_w, lo.weight.grad, lo.bias.grad), (op26, d30))
             dpad26, _ = ops.conv2d_fwd(d30f, lo.pack(1), 1, 0, S_h + 6, S_w + 6)
         else:
             d30 = ops.g_head_bwd(ctx["raw30"], ctx["mask"], dI, dT, 0)

@@ -210,6 +210,16 @@ def conv2d_wgrad_folded(xf, dy, dy_org, k, kw, cp, ho, wo, dw):
            int(dw.shape[0]), int(dw.shape[1]), L.stream())
 
 
+def conv2d_wgrad_dyfolded(x, dyf, k, cp, ho, wo, dw):
+    """Weight gradient of a thin-output k x k layer against its x-folded gradient operand; accumulates into dw [co][ci][k][k]."""
+    scratch = torch.zeros((k * 64 * x.c,), dtype=torch.float32, device=x.data.device)
+    L.call("skit_conv2d_wgrad_dyfolded", x.ref(), dyf.ref(), k, cp, ho, wo, _p(scratch), _p(dw), int(dw.shape[0]), int(dw.shape[1]), L.stream())
+
+
+def dbias_n(dy_op, org, ho, wo, nch, db):
+    L.call("skit_dbias_n", dy_op.ref(), org, ho, wo, nch, _p(db), L.stream())
+
+
 def stats_finalize(stats, count, eps=1e-5, running_mean=None, running_var=None, momentum=0.1):
     groups, c, _ = stats.shape
     mr = torch.empty((groups, c, 2), dtype=torch.float32, device=stats.device)
