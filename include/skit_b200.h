@@ -106,6 +106,10 @@ typedef struct skit_pack_desc {
     int co, ci, k, mode, kpad, reserved;
 } skit_pack_desc;
 int skit_pack_conv_weights_batched(const skit_pack_desc* descs_dev, int n, long long total, void* stream);
+/* Same refresh for packs with k <= 4 (modes 0-3), staged through shared memory in [32 co][32 ci][k*k] bricks so that the
+ * reference-layout source is read with unit stride.  Here descs[i].start is the prefix sum of TILES,
+ * ceil(N/32) * ceil(Kpadded/32) per pack (N, K as in skit_pack_conv_weights); a pack may carry fp32 and bf16 outputs. */
+int skit_pack_conv_weights_tiled(const skit_pack_desc* descs_dev, int n, int total_tiles, int max_k, void* stream);
 /* x-folded packs for thin k x k layers on the tensor cores (the 9-channel 7x7 generator stem, the input gradient of the
  * 5-channel 7x7 head): the filter's kw columns move into the 64-wide channel axis, leaving a (k x 1) filter:
  *   mode 4 (forward):        Wf[ky][o][kx*cp + c]  = w[o][c][ky][kx]            (N = co, K = 64, zero beyond kw*cp and c >= ci)

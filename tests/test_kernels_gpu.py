@@ -303,3 +303,38 @@ def test_patchnce_and_sampler(V):
         assert rel(q, q_ref) < 1e-6
         assert rel(loss, loss_ref) < 1e-5
         assert rel(nchw(dfeat), feat.grad) < 1e-4
+
+
+def test_pack_table_matches_single_pack_refresh(V):
+    """The batched refresh (shared-memory tiled kernel for k <= 4, element-wise for the rest) writes exactly what the
+    per-layer skit_pack_conv_weights* calls write — ragged channel counts, padded reduction axes, every pack mode."""
+    ops = V.ops
+    torch.manual_seed(3)
+    cases = [  # (co, ci, k, mode, f32, bf16, kpad, cp)
+        (256, 256, 3, 0, False, True, 0, 0), (256, 256, 3, 1, False, True, 0, 0), (128, 64, 4, 3, False, True, 0, 0),
+        (64, 128, 4, 0, False, True, 0, 0), (70, 36, 3, 0, True, True, 0, 0), (36, 70, 3, 1, True, True, 0, 0),
+        (5, 64, 3, 2, True, False, 0, 0), (20, 9, 4, 0, True, False, 0, 0), (20, 9, 4, 3, True, False, 0, 0),
+        (64, 9, 4, 0, False, True, 64, 0), (1, 512, 4, 0, True, False, 0, 0), (1, 512, 4, 1, True, False, 0, 0),
+        (64, 9, 7, 4, False, True, 0, 9), (5, 64, 7, 5, False, True, 0, 8), (5, 64, 7, 0, True, False, 0, 0),
+    ]
+    ws, ref, new = [], [], []
+    for co, ci, k, mode, f32, bf16, kpad, cp in cases:
+        w = torch.randn(co, ci, k, k, device="cuda")
+        ws.append(w)
+        ref.append(ops.PackedWeights(w, mode, want_f32=f32, want_bf16=bf16, kpad=kpad, cp=cp))
+        pk = ops.PackedWeights(w, mode, want_f32=f32, want_bf16=bf16, kpad=kpad, cp=cp)
+        for t in (pk.f32, pk.hi, pk.lo):
+            if t is not None:
+                t.fill_(float("nan"))
+        new.append(pk)
+    table = ops.PackTable(list(zip(ws, new)), "cuda")
+    assert table.tiled is not None and table.flat is not None
+    table.refresh()
+    torch.cuda.synchronize()
+    for case, a, b in zip(cases, ref, new):
+        for name in ("f32", "hi", "lo"):
+            ta, tb = getattr(a, name), getattr(b, name)
+            if ta is None or (name == "f32" and a.hi is not None and b.tiles() == 0):
+                continue   # the element-wise batched kernel fills one output kind per pack
+            assert torch.equal(ta.view(torch.int16 if ta.dtype == torch.bfloat16 else torch.int32),
+                               tb.view(torch.int16 if tb.dtype == torch.bfloat16 else torch.int32)), (case, name)

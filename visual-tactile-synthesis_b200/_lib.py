@@ -42,6 +42,7 @@ SIGNATURES = {
     "skit_pack_conv_weights_padded": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
     "skit_conv2d_wgrad_ex": [_OP, _I, _OP, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P],
     "skit_pack_conv_weights_batched": [_P, _I, _LL, _P],
+    "skit_pack_conv_weights_tiled": [_P, _I, _I, _I, _P],
     "skit_pack_conv_weights_folded": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
     "skit_fold_x_operand": [_OP, _I, _OP, _P],
     "skit_conv2d_wgrad_folded": [_OP, _I, _OP, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],

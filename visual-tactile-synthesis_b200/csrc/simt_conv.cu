@@ -709,6 +709,85 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const skit_pa
     }
 }
 
+// Tiled refresh for k*k <= 16 packs (modes 0-3): a block stages a [32 o][32 c][k*k] brick of the reference-layout weight in
+// shared memory with coalesced loads (a brick row is 32*k*k contiguous floats) and writes every tap's 32x32 slab of the
+// pack from there — the element-wise kernel above reads the source at a k*k-float stride, one useful float per sector.
+// descs[i].start = prefix sum of TILES (ceil(N/32) * ceil(Kpadded/32) per pack).
+constexpr int kPackTileRow = 33, kPackTilePlane = 32 * kPackTileRow + 4;
+__device__ __forceinline__ int pack_dst_tap(int mode, int k, int t) {
+    if (mode == 0 || mode == 2) return t;
+    if (mode == 1) return k * k - 1 - t;
+    const int ky = t / k, kx = t - ky * k, kh = k / 2;
+    return ((ky & 1) * 2 + (kx & 1)) * kh * kh + (kh - 1 - ky / 2) * kh + (kh - 1 - kx / 2);
+}
+__global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const skit_pack_desc* __restrict__ descs, int n, int total_tiles) {
+    extern __shared__ float tile[];   // [k*k][32 o][33] (+4 per plane)
+    __shared__ int s_desc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+        if (tid == 0) {
+            int lo = 0, hi = n - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (descs[mid].start <= tix) lo = mid; else hi = mid - 1;
+            }
+            s_desc = lo;
+        }
+        __syncthreads();
+        const skit_pack_desc& d = descs[s_desc];
+        const int mode = d.mode, k = d.k, co = d.co, ci = d.ci, kk = k * k;
+        const int Kd = mode == 0 ? ci : co, Nd = mode == 0 ? co : ci;
+        const int Kp = (d.hi && d.kpad > Kd) ? d.kpad : Kd;
+        const int tilesK = (Kp + 31) >> 5;
+        const int local = tix - (int)d.start;
+        const int tn = local / tilesK, tk = local - tn * tilesK;
+        const int o0 = (mode == 0 ? tn : tk) * 32, c0 = (mode == 0 ? tk : tn) * 32;
+        // stage: rows i (o), each 32*kk contiguous source floats
+        const int rowlen = 32 * kk;
+        for (int i = warp; i < 32; i += 8) {
+            const int o = o0 + i;
+            const float* src = d.w + ((long long)o * ci + c0) * kk;
+            const int valid = o < co ? min(32, ci - c0) * kk : 0;
+            for (int e = lane; e < rowlen; e += 32) {
+                const int j = e / kk, t = e - j * kk;
+                tile[t * kPackTilePlane + i * kPackTileRow + j] = e < valid ? __ldg(src + e) : 0.f;
+            }
+        }
+        __syncthreads();
+        const bool lanes_along_c = (mode == 0);   // bf16 pack: K innermost (c for mode 0, o otherwise)
+        if (d.hi) {
+            __nv_bfloat16* hi = (__nv_bfloat16*)d.hi; __nv_bfloat16* lo = (__nv_bfloat16*)d.lo;
+            // a warp writes two N rows per pass: 16 lanes x bf16x2 each
+            const int q = lane & 15, half = lane >> 4;
+            for (int pr = warp; pr < kk * 16; pr += 8) {
+                const int t = pr >> 4, r = (pr & 15) * 2 + half;     // r: index along N within the tile
+                const int nn = (mode == 0 ? o0 : c0) + r, kbase = (mode == 0 ? c0 : o0) + 2 * q;
+                if (nn >= Nd || kbase >= Kp) continue;
+                float v0, v1;
+                if (lanes_along_c) { v0 = tile[t * kPackTilePlane + r * kPackTileRow + 2 * q]; v1 = tile[t * kPackTilePlane + r * kPackTileRow + 2 * q + 1]; }
+                else { v0 = tile[t * kPackTilePlane + (2 * q) * kPackTileRow + r]; v1 = tile[t * kPackTilePlane + (2 * q + 1) * kPackTileRow + r]; }
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(v0, h0, l0); split_bf16(v1, h1, l1);
+                const long long off = ((long long)pack_dst_tap(mode, k, t) * Nd + nn) * Kp + kbase;
+                if (kbase + 1 < Kp) {
+                    *reinterpret_cast<__nv_bfloat162*>(hi + off) = __halves2bfloat162(h0, h1);
+                    *reinterpret_cast<__nv_bfloat162*>(lo + off) = __halves2bfloat162(l0, l1);
+                } else { hi[off] = h0; lo[off] = l0; }
+            }
+        }
+        if (d.f32 && (!d.hi || tk * 32 < Kd)) {   // fp32 pack [tap][K][N]: N innermost (o for mode 0, c otherwise)
+            for (int pr = warp; pr < kk * 32; pr += 8) {
+                const int t = pr >> 5, r = pr & 31;                   // r: index along K within the tile
+                const int kidx = (mode == 0 ? c0 : o0) + r, nn = (mode == 0 ? o0 : c0) + lane;
+                if (kidx >= Kd || nn >= Nd) continue;
+                const float v = mode == 0 ? tile[t * kPackTilePlane + lane * kPackTileRow + r] : tile[t * kPackTilePlane + r * kPackTileRow + lane];
+                d.f32[((long long)pack_dst_tap(mode, k, t) * Kd + kidx) * Nd + nn] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // layout 0: dwf[(tap*cip + c)*cop + o]   layout 1: dwf[(tap*cop + o)*cip + c]   (cop/cip: channel counts of the
 // operands the partial sums were computed on, >= the real co/ci when those were zero-padded)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int co, int ci, int k, float* dw, int accumulate, int layout,
@@ -794,6 +873,23 @@ extern "C" int skit_pack_conv_weights_batched(const skit_pack_desc* descs_dev, i
     int blocks = (int)min((long long)148 * 8, cdivll(total, kPackChunk));
     pack_weights_batched_kernel<<<blocks, 256, 0, as_stream(stream)>>>(descs_dev, n, total);
     return check_launch("pack_weights_batched_kernel");
+}
+
+extern "C" int skit_pack_conv_weights_tiled(const skit_pack_desc* descs_dev, int n, int total_tiles, int max_k, void* stream) {
+    SKIT_REQUIRE(descs_dev && n > 0 && total_tiles > 0 && max_k > 0 && max_k <= 4, "pack_conv_weights_tiled: bad arguments");
+    static bool attr_set = false;
+    const int smem = max_k * max_k * kPackTilePlane * (int)sizeof(float);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(pack_weights_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * kPackTilePlane * (int)sizeof(float));
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(pack_weights_tiled_kernel) failed: %s", cudaGetErrorString(e));
+            return SKIT_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const int blocks = min(total_tiles, 148 * 4);
+    pack_weights_tiled_kernel<<<blocks, 256, smem, as_stream(stream)>>>(descs_dev, n, total_tiles);
+    return check_launch("pack_weights_tiled_kernel");
 }
 
 extern "C" int skit_pack_conv_weights_folded(const float* w, int co, int ci, int k, int mode, int cp, void* hi, void* lo, void* stream) {

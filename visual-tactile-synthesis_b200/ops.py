@@ -131,24 +131,45 @@ class PackedWeights:
     def numel(self):
         return (self.k if self.mode in (4, 5) else self.k * self.k) * self.rco * self.rci
 
+    def tiles(self):
+        """32x32 (N x K) tiles of the shared-memory staged refresh; 0 when the pack is not eligible for it."""
+        if self.mode in (4, 5) or self.k > 4 or (self.hi is not None and self.rci % 2):
+            return 0
+        return -(-self.rco // 32) * -(-self.rci // 32)
+
 
 class PackTable:
-    """All packs of one net refreshed by a single kernel launch."""
+    """All packs of one net refreshed by at most two kernel launches: the k <= 4 packs through the shared-memory tiled
+    kernel (skit_pack_conv_weights_tiled), the rest (7x7, x-folded) element-wise (skit_pack_conv_weights_batched)."""
 
     def __init__(self, pairs, device):
         """pairs: [(weight tensor [co,ci,k,k], PackedWeights)]"""
+        tiled = [(w, pk) for w, pk in pairs if pk.tiles() > 0]
+        flat = [(w, pk) for w, pk in pairs if pk.tiles() == 0]
+        self.tiled = self._table(tiled, lambda pk: pk.tiles(), device)
+        self.flat = self._table(flat, lambda pk: pk.numel(), device)
+        self.max_k = max([pk.k for _, pk in tiled], default=0)
+        self.key = tuple((w.data_ptr(), id(pk)) for w, pk in pairs)
+
+    @staticmethod
+    def _table(pairs, size, device):
+        if not pairs:
+            return None
         arr = (L.SkitPackDesc * len(pairs))()
         start = 0
         for i, (w, pk) in enumerate(pairs):
             arr[i] = pk.desc(w, start)
-            start += pk.numel()
-        self.total, self.n = start, len(pairs)
+            start += size(pk)
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
-        self.dev = raw.to(device)
-        self.key = tuple((w.data_ptr(), id(pk)) for w, pk in pairs)
+        return raw.to(device), len(pairs), start
 
     def refresh(self):
-        L.call("skit_pack_conv_weights_batched", _p(self.dev), self.n, self.total, L.stream())
+        if self.tiled is not None:
+            dev, n, total = self.tiled
+            L.call("skit_pack_conv_weights_tiled", _p(dev), n, total, self.max_k, L.stream())
+        if self.flat is not None:
+            dev, n, total = self.flat
+            L.call("skit_pack_conv_weights_batched", _p(dev), n, total, L.stream())
 
 
 def conv2d_fwd(x, w, stride, org, ho, wo, bias=None, stats_mode=NORM_NONE, impl=IMPL_AUTO, out=None):
