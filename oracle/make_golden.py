@@ -146,6 +146,44 @@ def make_networks():
     print("networks.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
 
 
+def make_stylegan2():
+    """StyleGAN2Generator (a4) through the reference's define_G.  ModulatedConv2d builds its unit style with `.cuda()`
+    (stylegan_networks.py:310); on this CPU-only container Tensor.cuda is patched to the identity for the duration of the
+    call — the reference source is untouched."""
+    N = ref_networks()
+    out = {}
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for tag, netG, res, ngf, batch in (("sg2", "stylegan2", 128, 4, 1), ("sg2small", "smallstylegan2", 64, 4, 2)):
+            opt = argparse.Namespace(load_size=res, crop_size=res, stylegan2_G_num_downsampling=1, netG=netG)
+            torch.manual_seed(21)
+            with quiet():
+                G = N.define_G(9, 5, ngf, netG, "instance", False, "xavier", 0.02, False, False, [], opt)
+            with torch.no_grad():   # biases and the noise strength start at zero: perturb so they are exercised
+                for k, p in G.named_parameters():
+                    if k.endswith("bias"):
+                        p.normal_(0, 0.3)
+                    elif k.endswith("noise.weight"):
+                        p.fill_(0.37)
+            x = rand_input(22, batch, 9, res, res)
+            # NoiseInjection draws image.new_empty(n,1,H,W).normal_() from the global CPU generator: same seed, same draw
+            torch.manual_seed(23)
+            noise = torch.empty(batch, 1, res, res).normal_()
+            torch.manual_seed(23)
+            with torch.no_grad():
+                y, feats = G(x, layers=[1, 2, 3])
+            out.update(sd_np(G.state_dict(), tag + "."))
+            out[tag + "_noise"] = noise.numpy()
+            out[tag + "_out"] = y.numpy()
+            for i, f in enumerate(feats):
+                out[tag + "_feat%d" % i], out[tag + "_feat%d_norm" % i] = sub(f, 4)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    np.savez_compressed(os.path.join(OUT, "stylegan2.npz"), **out)
+    print("stylegan2.npz:", len(out), "arrays")
+
+
 def make_ops():
     load_reference()
     with quiet():
@@ -293,7 +331,9 @@ def make_step(tag, S, NT, NF, extra):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["networks", "ops", "step"]
+    which = sys.argv[1:] or ["networks", "ops", "step", "stylegan2"]
+    if "stylegan2" in which:
+        make_stylegan2()
     if "networks" in which:
         make_networks()
     if "ops" in which:

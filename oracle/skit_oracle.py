@@ -170,6 +170,107 @@ def unet_custom_forward(sd, x, num_downs=8, style_code=None, num_layer_style_cod
 
 
 # --------------------------------------------------------------------------- discriminators
+# --------------------------------------------------------------------------- StyleGAN2 generator (a4)
+def sg2_channels(ngf):
+    """Channel table of StyleGAN2Encoder / StyleGAN2Decoder (models/stylegan_networks.py:805-816, 862-873)."""
+    m = ngf / 32
+    t = {4: min(512, int(round(4096 * m))), 8: min(512, int(round(2048 * m))), 16: min(512, int(round(1024 * m))),
+         32: min(512, int(round(512 * m)))}
+    t.update({64: int(round(256 * m)), 128: int(round(128 * m)), 256: int(round(64 * m)), 512: int(round(32 * m)),
+              1024: int(round(16 * m))})
+    return t
+
+
+def sg2_blur(x, pad0, pad1, gain=1.0):
+    """Blur([1,3,3,1], pad) = upfirdn2d(up=1, down=1) (stylegan_networks.py:38-72, 140-157): zero pad by (pad0, pad1) on
+    both axes, then a VALID 4x4 correlation with the flipped (symmetric) normalised kernel, per channel."""
+    k1 = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    k = (k1[None, :] * k1[:, None])
+    k = k / k.sum() * gain
+    c = x.shape[1]
+    xp = F.pad(x, [pad0, pad1, pad0, pad1])
+    return F.conv2d(xp, torch.flip(k, [0, 1])[None, None].repeat(c, 1, 1, 1), groups=c)
+
+
+def sg2_flrelu(x, bias):
+    """FusedLeakyReLU (stylegan_networks.py:18-35): leaky_relu(x + b, 0.2) * sqrt(2)."""
+    return F.leaky_relu(x + bias.view(1, -1, 1, 1), 0.2) * (2 ** 0.5)
+
+
+def sg2_conv_layer(sd, pre, x, k, downsample=False, activate=True):
+    """ConvLayer (stylegan_networks.py:613-665): [Blur] + EqualConv2d (weight * 1/sqrt(ci*k*k), :179-190) [+ FusedLeakyReLU].
+    Sequential indices: blur 0 / conv 1 / act 2 when downsampling, conv 0 / act 1 otherwise; every ConvLayer of the
+    generator has bias=True, so the conv itself carries a bias only when there is no activation — never here (skip convs
+    are built with bias=False)."""
+    i = 0
+    if downsample:
+        p = (4 - 2) + (k - 1)
+        x = sg2_blur(x, (p + 1) // 2, p // 2)
+        i = 1
+    w = sd[pre + "%d.weight" % i]
+    scale = 1.0 / math.sqrt(w.shape[1] * k * k)
+    x = F.conv2d(x, w * scale, None, stride=2 if downsample else 1, padding=0 if downsample else k // 2)
+    if activate:
+        x = sg2_flrelu(x, sd[pre + "%d.bias" % (i + 1)])
+    return x
+
+
+def sg2_resblock(sd, pre, x, downsample):
+    """ResBlock (stylegan_networks.py:668-689), skip_gain 1: (conv2(conv1(x)) + skip(x)) / sqrt(2); the skip is a 1x1
+    ConvLayer (blur + stride 2, no bias, no activation) when the block downsamples or changes width, identity otherwise."""
+    out = sg2_conv_layer(sd, pre + "conv1.", x, 3)
+    out = sg2_conv_layer(sd, pre + "conv2.", out, 3, downsample=downsample)
+    skip = x
+    if (pre + "skip.1.weight") in sd or (pre + "skip.0.weight") in sd:
+        skip = sg2_conv_layer(sd, pre + "skip.", x, 1, downsample=downsample, activate=False)
+    return (out + skip) / math.sqrt(2.0)
+
+
+def sg2_styled_conv_up(sd, pre, x, noise=None):
+    """StyledConv(upsample=True, style=None) (stylegan_networks.py:375-412) around ModulatedConv2d (:248-348): style = ones,
+    weight = W / sqrt(ci*9), demodulated per output channel (rsqrt(sum w^2 + 1e-8)); conv_transpose2d stride 2, no padding;
+    Blur(pad=(1, 1)) with the kernel scaled by 4; + noise_weight * noise; FusedLeakyReLU."""
+    w = sd[pre + "conv.weight"][0]                      # [co, ci, 3, 3]
+    co, ci, k, _ = w.shape
+    w = w * (1.0 / math.sqrt(ci * k * k))
+    w = w * torch.rsqrt(w.pow(2).sum([1, 2, 3]) + 1e-8).view(co, 1, 1, 1)
+    out = F.conv_transpose2d(x, w.transpose(0, 1), padding=0, stride=2)
+    p = (4 - 2) - (k - 1)
+    out = sg2_blur(out, (p + 1) // 2 + 1, p // 2 + 1, gain=4.0)
+    if noise is not None:
+        out = out + sd[pre + "noise.weight"] * noise
+    return sg2_flrelu(out, sd[pre + "activate.bias"])
+
+
+def stylegan2_g_forward(sd, x, n_blocks=6, num_downsampling=1, layers=(), encode_only=False, noises=None):
+    """StyleGAN2Generator.forward (models/stylegan_networks.py:912-929; encoder :800-851, decoder :854-909).
+    sd: reference state_dict.  noises: one [n,1,H,W] tensor per StyledConv, or None for the noise-free ('small') variant /
+    zero noise weights — the reference draws them from the global RNG inside NoiseInjection (:351-362).
+    Returns fake [n,3,S,S] (and the encoder features at `layers`, indices into encoder.convs)."""
+    layers = list(layers)
+    feat, feats = x, []
+    n_enc = 2 + num_downsampling + n_blocks // 2
+    if -1 in layers:
+        layers.append(n_enc - 1)
+    for li in range(n_enc):
+        pre = "encoder.convs.%d." % li
+        if li == 1:
+            feat = sg2_conv_layer(sd, pre, feat, 1)
+        elif li >= 2:
+            feat = sg2_resblock(sd, pre, feat, downsample=li < 2 + num_downsampling)
+        if li in layers:
+            feats.append(feat)
+    if encode_only:
+        return feats
+    for li in range(n_blocks // 2):
+        feat = sg2_resblock(sd, "decoder.convs.%d." % li, feat, downsample=False)
+    for j in range(num_downsampling):
+        li = n_blocks // 2 + j
+        feat = sg2_styled_conv_up(sd, "decoder.convs.%d." % li, feat, None if noises is None else noises[j])
+    feat = sg2_conv_layer(sd, "decoder.convs.%d." % (n_blocks // 2 + num_downsampling), feat, 1)
+    return (feat, feats) if len(layers) > 0 else feat
+
+
 def nlayer_d_forward(sd, prefix, x, n_layers=3, bn_momentum=0.1, update_running=True):
     """NLayerDiscriminator.forward, BatchNorm2d in training mode
     (models/networks.py:1702-1750; index map SURVEY.md A.5).  Running stats in `sd` are

@@ -60,6 +60,21 @@ def test_unet_generator(golden_dir):
     close(sub(ys, 4), z["Gunet_style_out"])
 
 
+@pytest.mark.parametrize("tag,n_blocks,res,batch", [("sg2", 6, 128, 1), ("sg2small", 2, 64, 2)])
+def test_stylegan2_generator(golden_dir, tag, n_blocks, res, batch):
+    z = load(golden_dir, "stylegan2.npz")
+    sd = sd_from(z, tag + ".")
+    x = rand_input(22, batch, 9, res, res)
+    noises = [torch.from_numpy(z[tag + "_noise"])] if tag == "sg2" else None   # 'small' variant: no noise injection
+    y, feats = O.stylegan2_g_forward(sd, x, n_blocks=n_blocks, layers=[1, 2, 3], noises=noises)
+    close(y, z[tag + "_out"])
+    assert len(feats) == 3
+    for i, f in enumerate(feats):
+        close(sub(f, 4), z[tag + "_feat%d" % i])
+        assert abs(f.double().norm().item() / z[tag + "_feat%d_norm" % i] - 1) < 1e-5
+    assert len(O.stylegan2_g_forward(sd, x, n_blocks=n_blocks, layers=[1, 2], encode_only=True)) == 2
+
+
 def test_multiscale_discriminator_and_ganloss(golden_dir):
     z = load(golden_dir, "networks.npz")
     sd = sd_from(z, "D_before.")
