@@ -365,6 +365,26 @@ int skit_patchnce(const float* q, const float* k, int b, int np, int dim, float 
  * Pass NULL to switch it off (the default).  Never enabled on the product path. */
 int skit_debug_set_buffer(long long* buf);
 
+/* ---- StyleGAN2 generator (models/stylegan_networks.py; `--netG stylegan2 | smallstylegan2`) ------------------------------
+ * Effective conv filters, rebuilt on the device whenever the parameters change.  w: reference layout [co][ci][k][k]
+ * (ModulatedConv2d's [1][co][ci][k][k] is the same memory).
+ *   mode 0  EqualConv2d (:179-190):        out[co][ci][k][k]   = w / sqrt(ci k k)
+ *   mode 1  Blur + stride-2 conv (:625-643) folded into one filter: out[co][ci][k+3][k+3] = (w / sqrt(ci k k)) (*) blur4x4,
+ *           run as a stride-2 conv with zero padding 2 (k = 3) or 1 (k = 1, the ResBlock's blur + 1x1 stride-2 skip, :677).
+ *   mode 2  ModulatedConv2d(upsample, style = 1) (:304-334): weights demodulated per output channel, then
+ *           conv_transpose2d(stride 2) + Blur(pad 1,1, x4) folded into four 3x3 pad-1 filters, one per output parity:
+ *           out[(py*2+px)*co + o][ci][3][3]; the conv's 4 co output channels are the 2x2 sub-pixels (depth-to-space). */
+int skit_sg2_weight_prep(const float* w, int co, int ci, int k, int mode, float* out, void* stream);
+/* FusedLeakyReLU / NoiseInjection / ResBlock merge (:18-35, :351-362, :683-689) in one pass over a conv's raw output:
+ *   out = (lrelu_0.2(raw + bias + *noise_w * noise) * gain + skip) * post      (act = 0: no lrelu / gain)
+ * raw [n][h][w][craw]; shuffle = 1 reads it as 2x2 sub-pixel groups of c channels (mode-2 filters) and writes 2h x 2w;
+ * skip: dense [n][H][W][c].  noise [n][H][W].  Outputs (any subset): dense NHWC fp32,
+ * a zero-haloed operand (fp32 or bf16x2) for the next conv, NCHW fp32 with the first nchw_c channels.  c % 4 == 0. */
+int skit_sg2_bias_act(const float* raw, int n, int h, int w, int craw, int c, const float* bias,
+                      const float* noise, const float* noise_w, const float* skip, int shuffle,
+                      int act, float gain, float post, float* dense, const skit_operand* op, int pad, float* nchw,
+                      int nchw_c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,11 +3,13 @@
 (2) the CPU oracle on the same seeded inputs.  Gate: 1e-3 relative L2 per output tensor
 (BASELINE.json north_star); observed values are ~1e-5, asserted at 2e-4."""
 import argparse
+import math
 import os
 
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
@@ -250,3 +252,85 @@ def test_multiscale_discriminator_backward(V, ndf, hw, n):
         if is_bias_before_bn:
             continue
         assert rel(p.grad, ps[k].grad) < GRAD_REL and cos(p.grad, ps[k].grad) > GRAD_COS, k
+
+
+# ------------------------------------------------------------------------------------------ StyleGAN2 generator (a4)
+def _sg2_opt(netG, res, nd=1):
+    import argparse
+    return argparse.Namespace(load_size=res, crop_size=res, stylegan2_G_num_downsampling=nd, netG=netG)
+
+
+@pytest.mark.parametrize("tag,netG,n_blocks,res,batch", [("sg2", "stylegan2", 6, 128, 1), ("sg2small", "smallstylegan2", 2, 64, 2)])
+def test_stylegan2_generator_matches_reference_golden(V, golden_dir, tag, netG, n_blocks, res, batch):
+    """define_G('stylegan2') forward and encoder feature taps against the real reference's outputs (tests/golden/stylegan2.npz,
+    oracle/make_golden.py): folded blur filters, noise injection, residual merges — 2e-4 relative L2."""
+    z = dict(np.load(os.path.join(golden_dir, "stylegan2.npz")))
+    sd = {k[len(tag) + 1:]: torch.from_numpy(v.copy()) for k, v in z.items() if k.startswith(tag + ".")}
+    G = V.networks.define_G(9, 5, 4, netG, "instance", False, "xavier", 0.02, False, False, [0], _sg2_opt(netG, res))
+    assert sorted(G.state_dict().keys()) == sorted(sd.keys())
+    G.load_state_dict(sd)
+    g = torch.Generator().manual_seed(22)
+    x = (torch.rand(batch, 9, res, res, generator=g) * 2 - 1).cuda()
+    noises = [torch.from_numpy(z[tag + "_noise"]).cuda()] if netG == "stylegan2" else None
+    y, feats = G(x, layers=[1, 2, 3], noises=noises)
+    assert rel(y, torch.from_numpy(z[tag + "_out"])) < 2e-4
+    assert len(feats) == 3
+    for i, f in enumerate(feats):
+        ref_sub = torch.from_numpy(z[tag + "_feat%d" % i])
+        assert rel(f[..., ::4, ::4], ref_sub) < 2e-4
+        assert abs(f.double().norm().item() / float(z[tag + "_feat%d_norm" % i]) - 1) < 1e-4
+    assert len(G(x, layers=[1, 2], encode_only=True)) == 2
+
+
+def test_stylegan2_generator_tensor_core_widths_vs_oracle(V):
+    """ngf 64 at 128x128 (64 / 128-channel layers: every 3x3, 6x6-s2, 4x4-s2 and sub-pixel conv on the tcgen05 path) against the
+    CPU oracle with the same weights; north-star tolerance 1e-3 relative on the output."""
+    from oracle import skit_oracle as O
+    torch.manual_seed(5)
+    G = V.networks.define_G(9, 5, 64, "stylegan2", "instance", False, "xavier", 0.02, False, False, [0], _sg2_opt("stylegan2", 512))
+    with torch.no_grad():
+        for k, p in G.named_parameters():
+            if k.endswith("bias"):
+                p.normal_(0, 0.3)
+            elif k.endswith("noise.weight"):
+                p.fill_(0.21)
+    assert any(e.use_tc for e in (G.refresh_packs() or G._eff).values())
+    x = torch.rand(1, 9, 128, 128) * 2 - 1
+    noise = torch.randn(1, 1, 128, 128)
+    sd = {k: v.detach().cpu().clone() for k, v in G.state_dict().items()}
+    want = O.stylegan2_g_forward(sd, x, n_blocks=6, noises=[noise])
+    got = G(x.cuda(), noises=[noise.cuda()])
+    assert got.shape == (1, 3, 128, 128)
+    assert rel(got, want) < 1e-3
+    # default noise path: drawn on the device, different every call, same statistics
+    a, b = G(x.cuda()), G(x.cuda())
+    assert not torch.equal(a, b)
+    # parameters changed in place -> folded filters are rebuilt
+    with torch.no_grad():
+        G.decoder.convs[-1][0].weight.mul_(2.0)
+    sd2 = {k: v.detach().cpu().clone() for k, v in G.state_dict().items()}
+    assert rel(G(x.cuda(), noises=[noise.cuda()]), O.stylegan2_g_forward(sd2, x, n_blocks=6, noises=[noise])) < 1e-3
+
+
+def test_stylegan2_folded_filters_match_blur_then_conv(V):
+    """skit_sg2_weight_prep against the two-pass statement (upfirdn blur, then strided / transposed conv) in torch."""
+    from oracle import skit_oracle as O
+    sg = V.sg2_generator
+    torch.manual_seed(9)
+    x = torch.randn(2, 8, 16, 16)
+    conv3 = sg.EqualConv2d(8, 12, 3).cuda()
+    e = sg._EffConv(conv3, 1, 2, 2); e.refresh()
+    ref = F.conv2d(O.sg2_blur(x, 2, 2), conv3.weight.detach().cpu() / math.sqrt(72), stride=2)
+    assert rel(F.conv2d(x, e.weight.cpu(), stride=2, padding=2), ref) < 1e-6
+    conv1 = sg.EqualConv2d(8, 12, 1).cuda()
+    e = sg._EffConv(conv1, 1, 2, 1); e.refresh()
+    ref = F.conv2d(O.sg2_blur(x, 1, 1), conv1.weight.detach().cpu() / math.sqrt(8), stride=2)
+    assert rel(F.conv2d(x, e.weight.cpu(), stride=2, padding=1), ref) < 1e-6
+    mod = sg.ModulatedConv2d(8, 6, 3).cuda()
+    e = sg._EffConv(mod, 2, 1, 1); e.refresh()
+    wd = mod.weight.detach().cpu()[0] / math.sqrt(72)
+    wd = wd * torch.rsqrt(wd.pow(2).sum([1, 2, 3]) + 1e-8).view(-1, 1, 1, 1)
+    ref = O.sg2_blur(F.conv_transpose2d(x, wd.transpose(0, 1), stride=2), 1, 1, gain=4.0)
+    raw = F.conv2d(x, e.weight.cpu(), padding=1)
+    got = raw.view(2, 2, 2, 6, 16, 16).permute(0, 3, 4, 1, 5, 2).reshape(2, 6, 32, 32)
+    assert rel(got, ref) < 1e-6

@@ -1345,7 +1345,10 @@ def define_G(input_nc, output_nc, ngf, netG, norm="batch", use_dropout=False, in
         if use_dropout:
             raise NotImplementedError("B200 path: dropout is not built")
         net = CustomUnetGenerator(input_nc, output_nc, num_downs=8, ngf=ngf, num_layer_separate=num_layer_separate, opt=opt)
-    elif netG in ("unet_128", "unet_256", "stylegan2", "smallstylegan2"):
+    elif netG in ("stylegan2", "smallstylegan2"):
+        from .sg2_generator import StyleGAN2Generator   # forward / feature taps only; no explicit backward yet
+        net = StyleGAN2Generator(input_nc, output_nc, ngf, use_dropout=use_dropout, n_blocks=6 if netG == "stylegan2" else 2, opt=opt)
+    elif netG in ("unet_128", "unet_256"):
         raise NotImplementedError("Generator model name [%s] is on the roadmap of the B200 path but not built yet" % netG)
     else:
         raise NotImplementedError("Generator model name [%s] is not recognized" % netG)

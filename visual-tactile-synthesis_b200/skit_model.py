@@ -73,6 +73,10 @@ class SinSKITGModel:
             raise NotImplementedError("batch_size is forced to 1 by the reference (sinskitG_model.py:342)")
         g_in = opt.input_nc + (8 if opt.use_positional_encoding else 0)
         gpu = [dev_index]
+        if "stylegan2" in opt.netG:
+            raise NotImplementedError("netG=%r: the StyleGAN2 generator is built forward-only on the B200 path "
+                                      "(networks.define_G(...)(x)); its 3-channel output does not feed the 5-channel skitG "
+                                      "step (stylegan_networks.py:892) and it has no explicit backward yet" % opt.netG)
         self.netG = networks.define_G(g_in, opt.output_nc, opt.ngf, opt.netG, opt.normG, not opt.no_dropout, opt.init_type,
                                       opt.init_gain, opt.no_antialias, opt.no_antialias_up, gpu, opt,
                                       num_layer_separate=getattr(opt, "num_layer_separate", 4))
