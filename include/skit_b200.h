@@ -385,6 +385,23 @@ int skit_sg2_bias_act(const float* raw, int n, int h, int w, int craw, int c, co
                       int act, float gain, float post, float* dense, const skit_operand* op, int pad, float* nchw,
                       int nchw_c, void* stream);
 
+/* ---- LPIPS-VGG16 perceptual loss (pip `lpips` 0.1.4 LPIPS(net='vgg'); call sites models/sinskitG_model.py:495, 1639-1645, 1711)
+ * The VGG16 trunk runs on skit_conv2d_fwd / skit_conv2d_dgrad_* with frozen packs; these are the pieces around it.
+ * ScalingLayer: op[n][h+2][w+2][3] (fp32, zero halo) = (x - shift) / scale, x NCHW with 1 (broadcast) or 3 channels. */
+int skit_lpips_scale_fwd(const float* x, int n, int cin, int h, int w, const skit_operand* op, void* stream);
+/* its transpose: dx[n][dx_c0 .. dx_c0+cin)[h][w] of an [n][dx_ctot][h][w] tensor (+)= gscale * dop / scale (3 channels summed when cin = 1) */
+int skit_lpips_scale_bwd(const float* dop, int n, int cin, int h, int w, float gscale, float* dx, int dx_ctot, int dx_c0,
+                         int accumulate, void* stream);
+/* MaxPool2d(2, 2) of a dense NHWC map into the next conv's zero-haloed operand (fp32 or bf16x2), and its backward:
+ * df = add (optional, dense) + dpool routed to the first maximum of each window (ATen's tie rule); dpool is the gradient
+ * w.r.t. the pooled haloed operand [n][h/2+2p][w/2+2p][c]. */
+int skit_maxpool2_fwd(const float* f, int n, int h, int w, int c, const skit_operand* op, int pad, void* stream);
+int skit_maxpool2_bwd(const float* f, const float* dpool, int n, int h, int w, int c, int pad, const float* add, float* df, void* stream);
+/* One LPIPS layer: loss[b] += mean_pixels sum_c lin_w[c] (u0 - u1)^2, u = f / (|f|_2 over channels + 1e-10);
+ * df0 (optional) = gscale * d loss[b] / d f0.  f0, f1: [n][h][w][c] fp32. */
+int skit_lpips_layer(const float* f0, const float* f1, const float* lin_w, int n, int h, int w, int c, float gscale,
+                     float* loss, float* df0, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -271,6 +271,64 @@ def stylegan2_g_forward(sd, x, n_blocks=6, num_downsampling=1, layers=(), encode
     return (feat, feats) if len(layers) > 0 else feat
 
 
+# --------------------------------------------------------------------------- LPIPS (third-party: pip lpips 0.1.4)
+# The reference builds `lpips.LPIPS(net="vgg")` (models/sinskitG_model.py:495) and calls it on (fake_I, real_I) (:1711) and on
+# single-channel 32x32 touch patches (:1639-1645).  The package is NOT vendored under /root/reference and not installed in
+# this image; the algorithm below restates its published code (lpips/lpips.py: ScalingLayer, normalize_tensor, NetLinLayer,
+# spatial_average; lpips/pretrained_networks.py: vgg16 slices = torchvision vgg16.features[0:4], [4:9], [9:16], [16:23],
+# [23:30]).  Pinning: the VGG16 trunk is checked against torchvision's own vgg16 module (tests/test_oracle_golden.py);
+# the LPIPS head has no fixture to check against -> "parity unpinned" for the head.  Weights: the pretrained VGG16 / lin
+# checkpoints are not available offline; tests and bench use random weights with the package's state_dict keys.
+LPIPS_SHIFT = (-0.030, -0.088, -0.188)
+LPIPS_SCALE = (0.458, 0.448, 0.450)
+VGG_SLICES = ((0, 2), (5, 7), (10, 12, 14), (17, 19, 21), (24, 26, 28))   # conv indices in vgg16.features per slice
+VGG_CHNS = (64, 128, 256, 512, 512)
+
+
+def vgg16_features(sd, x, prefix="net."):
+    """relu1_2, relu2_2, relu3_3, relu4_3, relu5_3 of a VGG16 whose convs live at `net.slice{s}.{idx}.{weight,bias}`."""
+    outs = []
+    h = x
+    for s, idxs in enumerate(VGG_SLICES):
+        if s > 0:
+            h = F.max_pool2d(h, 2, 2)
+        for i in idxs:
+            h = F.relu(F.conv2d(h, sd["%sslice%d.%d.weight" % (prefix, s + 1, i)], sd["%sslice%d.%d.bias" % (prefix, s + 1, i)], padding=1))
+        outs.append(h)
+    return outs
+
+
+def lpips_vgg(sd, in0, in1):
+    """LPIPS(net='vgg', lpips=True, spatial=False).forward(in0, in1, normalize=False) -> [N,1,1,1]."""
+    shift = torch.tensor(LPIPS_SHIFT).view(1, 3, 1, 1)
+    scale = torch.tensor(LPIPS_SCALE).view(1, 3, 1, 1)
+    f0 = vgg16_features(sd, (in0 - shift) / scale)      # a 1-channel input broadcasts to 3 channels here
+    f1 = vgg16_features(sd, (in1 - shift) / scale)
+    val = 0
+    for k in range(5):
+        n0 = f0[k] / (torch.sqrt(torch.sum(f0[k] ** 2, dim=1, keepdim=True)) + 1e-10)
+        n1 = f1[k] / (torch.sqrt(torch.sum(f1[k] ** 2, dim=1, keepdim=True)) + 1e-10)
+        d = (n0 - n1) ** 2
+        val = val + F.conv2d(d, sd["lin%d.model.1.weight" % k]).mean([2, 3], keepdim=True)
+    return val
+
+
+def lpips_random_state(seed=0, weight_gain=1.0):
+    """Random LPIPS-VGG weights with the package's state_dict keys (no pretrained checkpoint offline): He-normal convs,
+    small biases, non-negative lin weights (the trained ones are clamped to >= 0)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    cin = 3
+    for s, idxs in enumerate(VGG_SLICES):
+        for i in idxs:
+            co = VGG_CHNS[s]
+            sd["net.slice%d.%d.weight" % (s + 1, i)] = torch.randn(co, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cin * 9)) * weight_gain
+            sd["net.slice%d.%d.bias" % (s + 1, i)] = torch.randn(co, generator=g) * 0.05
+            cin = co
+        sd["lin%d.model.1.weight" % s] = torch.rand(1, VGG_CHNS[s], 1, 1, generator=g) / VGG_CHNS[s] * 4
+    return sd
+
+
 def nlayer_d_forward(sd, prefix, x, n_layers=3, bn_momentum=0.1, update_running=True):
     """NLayerDiscriminator.forward, BatchNorm2d in training mode
     (models/networks.py:1702-1750; index map SURVEY.md A.5).  Running stats in `sd` are

@@ -334,3 +334,40 @@ def test_stylegan2_folded_filters_match_blur_then_conv(V):
     raw = F.conv2d(x, e.weight.cpu(), padding=1)
     got = raw.view(2, 2, 2, 6, 16, 16).permute(0, 3, 4, 1, 5, 2).reshape(2, 6, 32, 32)
     assert rel(got, ref) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ LPIPS-VGG16
+def _lpips_module(V, sd):
+    m = V.lpips_vgg.LPIPS(net="vgg").cuda()
+    full = dict(sd)
+    for k in range(5):
+        full["lins.%d.model.1.weight" % k] = sd["lin%d.model.1.weight" % k]
+    full["scaling_layer.shift"] = m.scaling_layer.shift.cpu()
+    full["scaling_layer.scale"] = m.scaling_layer.scale.cpu()
+    assert sorted(m.state_dict().keys()) == sorted(full.keys())
+    m.load_state_dict(full)
+    return m
+
+
+@pytest.mark.parametrize("n,cin,h,w", [(2, 3, 64, 48), (6, 1, 32, 32)])
+def test_lpips_value_and_input_gradient_vs_oracle(V, n, cin, h, w):
+    """LPIPS(fake, real) per sample and d/d fake against autograd through the CPU restatement (oracle/skit_oracle.py:
+    lpips_vgg) with the same random weights: RGB images and the 1-channel touch-patch form.  Value 1e-3 relative; the
+    gradient crosses 13 ReLU layers and 4 max-pools (discontinuous masks), so it is gated by cosine + relative L2 like the
+    whole-network gradients above."""
+    from oracle import skit_oracle as O
+    sd = O.lpips_random_state(7)
+    m = _lpips_module(V, sd)
+    fake = rand_input(41, n, cin, h, w)
+    real = (fake + 0.3 * rand_input(42, n, cin, h, w)).clamp(-1, 1)
+    fr = fake.clone().requires_grad_(True)
+    want = O.lpips_vgg(sd, fr, real).view(-1)
+    want.sum().backward()
+    got, dx = m.loss_and_grad(fake.cuda(), real.cuda(), gscale=1.0)
+    assert rel(got, want) < GATE
+    assert rel(m(fake.cuda(), real.cuda()).view(-1), want) < GATE
+    assert cos(dx, fr.grad) > GRAD_COS and rel(dx, fr.grad) < GRAD_REL
+    # accumulate into a channel slice of a wider NCHW gradient with a scale (how the train step uses it)
+    wide = torch.ones(n, cin + 2, h, w, device="cuda")
+    m.loss_and_grad(fake.cuda(), real.cuda(), gscale=0.5, dx=wide, dx_c0=1, accumulate=True)
+    assert rel(wide[:, 1:1 + cin] - 1, 0.5 * fr.grad) < GRAD_REL and torch.equal(wide[:, 0], torch.ones_like(wide[:, 0]))

@@ -75,6 +75,33 @@ def test_stylegan2_generator(golden_dir, tag, n_blocks, res, batch):
     assert len(O.stylegan2_g_forward(sd, x, n_blocks=n_blocks, layers=[1, 2], encode_only=True)) == 2
 
 
+def test_lpips_trunk_matches_torchvision_vgg16():
+    """The oracle's VGG16 feature slices against torchvision's vgg16 module carrying the same weights (the LPIPS package
+    wraps exactly that module); then the LPIPS value is checked for its defining properties."""
+    tv = pytest.importorskip("torchvision")
+    sd = O.lpips_random_state(3)
+    net = tv.models.vgg16(weights=None).features.eval()
+    with torch.no_grad():
+        for s, idxs in enumerate(O.VGG_SLICES):
+            for i in idxs:
+                net[i].weight.copy_(sd["net.slice%d.%d.weight" % (s + 1, i)])
+                net[i].bias.copy_(sd["net.slice%d.%d.bias" % (s + 1, i)])
+    x = rand_input(31, 2, 3, 32, 48)
+    feats = O.vgg16_features(sd, x)
+    ends = (4, 9, 16, 23, 30)
+    h = x
+    with torch.no_grad():
+        for k, e in enumerate(ends):
+            h = net[(0 if k == 0 else ends[k - 1]):e](h)
+            close(feats[k], h)
+    y = rand_input(32, 2, 3, 32, 48)
+    v = O.lpips_vgg(sd, x, y)
+    assert v.shape == (2, 1, 1, 1) and (v > 0).all()
+    assert O.lpips_vgg(sd, x, x).abs().max() == 0
+    close(O.lpips_vgg(sd, x, y), O.lpips_vgg(sd, y, x))                       # symmetric
+    close(O.lpips_vgg(sd, x[:, :1], y[:, :1]), O.lpips_vgg(sd, x[:, :1].repeat(1, 3, 1, 1), y[:, :1].repeat(1, 3, 1, 1)))
+
+
 def test_multiscale_discriminator_and_ganloss(golden_dir):
     z = load(golden_dir, "networks.npz")
     sd = sd_from(z, "D_before.")
