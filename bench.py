@@ -45,13 +45,17 @@ def parse():
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="infer: generator forward only (BASELINE.json configs[4])")
     ap.add_argument("--batch", type=int, default=1, help="images per rank per step (infer mode)")
     ap.add_argument("--nce", action="store_true", help="PatchNCE on (BASELINE.json configs[2] wiring: use with --size 768)")
+    ap.add_argument("--lpips", action="store_true", help="LPIPS-VGG16 terms on with the reference's default weights (lambda_G1_lpips 1, "
+                                                         "lambda_G2_lpips 10; random VGG weights: no checkpoint offline)")
     return ap.parse_args()
 
 
 def workload_config(a):
     return {"workload": "skitG/sinskitG train step, single material, %dx%d, resnet_9blocks ngf64 + multiscale PatchGAN ndf64, "
-                        "NT=64 NF=32, GAN+L1+patch-L1, PatchNCE %s, LPIPS/VAL off (BASELINE.json configs[%d])"
-                        % (a.size, a.size, "on (5 layers, 256 patches, T=0.07)" if a.nce else "off", 2 if a.nce else 1),
+                        "NT=64 NF=32, GAN+L1+patch-L1, PatchNCE %s, LPIPS %s, VAL off (BASELINE.json configs[%d]%s)"
+                        % (a.size, a.size, "on (5 layers, 256 patches, T=0.07)" if a.nce else "off",
+                           "on (VGG16, full image + touch patches, random weights)" if a.lpips else "off", 2 if a.nce else 1,
+                           " + the reference's default LPIPS terms" if a.lpips else ""),
             "size": a.size, "images_per_rank_per_step": 1, "NT": 64, "NF": 32, "netG": "resnet_9blocks", "ngf": 64,
             "netD": "multiscale", "ndf": 64, "parallelism": "dp%d (flat grad bucket all-reduce, NCCL)" % a.gpus,
             "l2": "per-step working set (saved activations + operands) is several GB >> 126 MB L2; no flush needed"}
@@ -233,7 +237,8 @@ def run_b200(a):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    opt = vts_b200.default_options(gpu_ids=[ctx.local_rank], lambda_NCE=1.0 if a.nce else 0.0)
+    opt = vts_b200.default_options(gpu_ids=[ctx.local_rank], lambda_NCE=1.0 if a.nce else 0.0,
+                                   lambda_G1_lpips=1.0 if a.lpips else 0.0, lambda_G2_lpips=10.0 if a.lpips else 0.0)
     torch.manual_seed(0)
     model = vts_b200.SinSKITGModel(opt, dist_ctx=ctx if ctx.world_size > 1 else None)
     ctx.broadcast_params([model.netG, model.netD, model.netD2])

@@ -545,6 +545,9 @@ class StepConfig:
         self.use_diffaug = True
         self.use_more_fakeT = True
         # PatchNCE wiring (new behaviour): CUT-style, off by default
+        # LPIPS-VGG terms (reference defaults 1.0 / 10.0, sinskitG_model.py:69-72, 105-108); off unless sdL is given
+        self.lambda_G1_lpips = 0.0
+        self.lambda_G2_lpips = 0.0
         self.lambda_NCE = 0.0
         self.nce_layers = (0, 4, 8, 12, 16)
         self.nce_T = 0.07
@@ -577,7 +580,7 @@ def model_forward(cfg, sdG, real_S, S_pe, M, real_I=None, rand=None):
     return res
 
 
-def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.0, grad_hook=None, sdF=None):
+def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.0, grad_hook=None, sdF=None, sdL=None):
     """SinSKITGModel.optimize_parameters (models/sinskitG_model.py:601-700) with
     compute_D1_loss (:1346-1407), compute_D2_loss (:1409-1617), compute_G1_loss (:1660-1726),
     compute_G2_loss (:1728-1842); LPIPS / vision-aided terms off (SURVEY.md §8c flags).
@@ -677,6 +680,16 @@ def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.
     l_l1_2 = ((fake_T_p - real_T).abs() * cfg.lambda_G2_L1).view(-1, NT, *fake_T_p.shape[1:]).sum(dim=1).mean()
     losses.update(G_GAN=l_gan.item(), G_L1=l_l1.item(), G2_GAN=l_g2.item(), G2_L1=l_l1_2.item())
     loss_G = l_gan + l_l1 + l_g2 + l_l1_2
+    if sdL is not None and cfg.lambda_G1_lpips > 0:      # compute_G1_loss :1707-1715
+        l_lp = lpips_vgg(sdL, fake_I, real_I).mean() * cfg.lambda_G1_lpips
+        losses["G_lpips"] = l_lp.item()
+        loss_G = loss_G + l_lp
+    if sdL is not None and cfg.lambda_G2_lpips > 0:      # _compute_touch_lpips_loss :1619-1658: gx and gy separately, 1 channel each
+        l_gx = lpips_vgg(sdL, fake_T_p[:, 0:1], real_T[:, 0:1]).view(-1, NT, 1, 1, 1).sum(dim=1).mean()
+        l_gy = lpips_vgg(sdL, fake_T_p[:, 1:2], real_T[:, 1:2]).view(-1, NT, 1, 1, 1).sum(dim=1).mean()
+        l_lp2 = cfg.lambda_G2_lpips * (l_gx + l_gy)
+        losses["G2_lpips"] = l_lp2.item()
+        loss_G = loss_G + l_lp2
     if cfg.lambda_NCE > 0:
         # CUT-style PatchNCE wiring (NEW behaviour: PatchNCELoss / PatchSampleF are dead code in the reference, SURVEY.md 0.4;
         # the functions themselves are pinned against the reference in tests/golden/ops.npz).  keys: generator features of

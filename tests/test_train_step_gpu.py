@@ -218,6 +218,46 @@ def test_train_step_with_patchnce_vs_oracle():
     assert rel(res["grads_G"][k], res0["grads_G"][k]) > 1e-3
 
 
+def test_train_step_with_lpips_vs_oracle():
+    """The reference's default perceptual terms (lambda_G1_lpips 1, lambda_G2_lpips 10): LPIPS-VGG16 on
+    (fake_I, real_I) and on the single-channel touch patches, value and gradient contribution to G, against the oracle's
+    train step with the same random LPIPS weights.  Then the same step captured and replayed as a CUDA graph."""
+    import vts_b200
+    from oracle import skit_oracle as O
+    S, NT, NF = 64, 8, 4
+    torch.manual_seed(2)
+    sdL = O.lpips_random_state(11)
+    opt = vts_b200.default_options(batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_G1_lpips=1.0, lambda_G2_lpips=10.0,
+                                   lpips_state=sdL)
+    m = vts_b200.SinSKITGModel(opt)
+    sds = [{k: v.detach().cpu().clone() for k, v in net.state_dict().items()} for net in (m.netG, m.netD, m.netD2)]
+    batch = O.synthetic_batch(S, NT=NT, seed=0, ellipse_mask=True)
+    rand = dict(real_b=[0.3], real_s=[0.8], fake_b=[0.6], fake_s=[0.2],
+                fake_ox=np.array([3, 10, 20, 7], dtype=np.int32), fake_oy=np.array([5, 1, 12, 30], dtype=np.int32))
+    m.set_input(batch)
+    m.optimize_parameters(1, rand=rand)
+    torch.cuda.synchronize()
+    cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_G1_lpips=1.0, lambda_G2_lpips=10.0)
+    sdG, sdD, sdD2 = [copy.deepcopy(s) for s in sds]
+    res = O.train_step(cfg, sdG, sdD, sdD2, {}, O.step_inputs_from_batch(batch), rand, step=1, sdL=sdL)
+    losses = m.get_current_losses()
+    assert "G_lpips" in losses and "G2_lpips" in losses and losses["G_lpips"] > 0 and losses["G2_lpips"] > 0
+    for k, v in res["losses"].items():
+        assert abs(losses[k] - v) <= GATE * max(1.0, abs(v)), (k, losses[k], v)
+    print("G worst grad rel err vs oracle (with LPIPS)", check_grads(m.netG, {k: v.numpy() for k, v in res["grads_G"].items()}, "G"))
+    cfg0 = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF)
+    sdG0, sdD0, sdD20 = [copy.deepcopy(s) for s in sds]
+    res0 = O.train_step(cfg0, sdG0, sdD0, sdD20, {}, O.step_inputs_from_batch(batch), rand, step=1)
+    k = "model.%d.weight" % (12 + 9 + 9)     # the 7x7 head: sees the perceptual gradient directly
+    assert rel(res["grads_G"][k], res0["grads_G"][k]) > 1e-3
+    # graph capture + replay of the LPIPS step (device-side losses stay finite and close to the eager value)
+    for _ in range(4):
+        m.set_input(batch)
+        m.optimize_parameters(1)
+    l2 = m.get_current_losses()
+    assert np.isfinite(l2["G_lpips"]) and np.isfinite(l2["G2_lpips"]) and l2["G_lpips"] > 0
+
+
 def test_train_step_with_patchnce_mlp_vs_oracle():
     """netF = 'mlp_sample' (CUT's default projection head): the per-layer MLP's forward, its weight gradients, the
     gradient it passes back to the generator, and its own Adam update."""

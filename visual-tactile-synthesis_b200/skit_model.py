@@ -64,9 +64,9 @@ class SinSKITGModel:
         dev_index = opt.gpu_ids[0] if len(opt.gpu_ids) else 0
         self.device = torch.device("cuda", dev_index)
         torch.cuda.set_device(self.device)
-        if opt.lambda_G1_lpips != 0 or opt.lambda_G2_lpips != 0 or opt.use_vision_aided_loss:
-            raise NotImplementedError("LPIPS / vision-aided losses are third-party networks outside the B200 hot path; "
-                                      "run with --lambda_G1_lpips 0 --lambda_G2_lpips 0 --use_vision_aided_loss False")
+        if opt.use_vision_aided_loss:
+            raise NotImplementedError("the vision-aided discriminator (CLIP / DINO backbones) is a third-party network outside the "
+                                      "B200 hot path; run with --use_vision_aided_loss False")
         if opt.T_resolution_multiplier != 1:
             raise NotImplementedError("T_resolution_multiplier != 1 (real bicubic resampling) is not built")
         if opt.batch_size != 1:
@@ -92,6 +92,15 @@ class SinSKITGModel:
                 net.flatten_parameters()
             self.step_count = 0
             self.lr_factor = 1.0
+            self.lpips = None
+            if opt.lambda_G1_lpips > 0 or opt.lambda_G2_lpips > 0:
+                # criterionLPIPS_vgg (sinskitG_model.py:495).  The pretrained VGG16 / lin checkpoints are not available offline:
+                # random weights unless `opt.lpips_state` (a state_dict with the lpips package's keys) is given.
+                from .lpips_vgg import LPIPS
+                self.lpips = LPIPS(net="vgg").to(self.device)
+                if getattr(opt, "lpips_state", None) is not None:
+                    self.lpips.load_state_dict(opt.lpips_state, strict=False)
+                self.lpips.refresh_packs_once()
             self.nce_layers = [int(i) for i in str(opt.nce_layers).split(",")] if getattr(opt, "lambda_NCE", 0.0) > 0 else []
             if self.nce_layers:
                 if not isinstance(self.netG, networks.ResnetGenerator):
@@ -404,7 +413,7 @@ class SinSKITGModel:
         n = self.real_S.shape[0]
         ox, oy = self.ox, self.oy
         L = torch.zeros(8 + 3 * NT + NF, dtype=torch.float32, device=self.device)
-        sl = dict(D_fake=L[0:1], D_real=L[1:2], G_GAN=L[2:3], G_L1=L[3:4], G2_L1=L[4:5],
+        sl = dict(D_fake=L[0:1], D_real=L[1:2], G_GAN=L[2:3], G_L1=L[3:4], G2_L1=L[4:5], G_lpips=L[5:6], G2_lpips=L[6:7],
                   D2_fake=L[8:8 + NT], D2_real=L[8 + NT:8 + 2 * NT], G2_GAN=L[8 + 2 * NT:8 + 3 * NT], D2_more=L[8 + 3 * NT:])
         D.zero_grad()
         D2.zero_grad()
@@ -415,6 +424,11 @@ class SinSKITGModel:
         with self._fork(0):     # D1 real (compute_D1_loss :1346-1407)
             run_D["real"] = []
             self._d_pass(D, [self.real_S, self.real_I], -1.0, sl["D_real"], 0.5 * opt.lambda_G1_GAN / n, run_D["real"])
+            if self.lpips is not None:      # VGG features of the real image / real touch patches: independent of G as well
+                if opt.lambda_G1_lpips > 0:
+                    self._lp_real_I = self.lpips.fwd(self.real_I)
+                if opt.lambda_G2_lpips > 0:   # gx patches then gy patches, one channel each (:1639-1645)
+                    self._lp_real_T = self.lpips.fwd(self.real_T.transpose(0, 1).reshape(-1, 1, 32, 32))
         with self._fork(1):     # D2 real (compute_D2_loss :1409-1617); its conditioning image is the DiffAugmented real
             if opt.use_diffaug:
                 self.aug_real_I = ops.diffaug_bs_mask(self.real_I, self.M, self._u_dev[0], self._u_dev[1])
@@ -476,8 +490,17 @@ class SinSKITGModel:
         per_patch = fake_T_p.numel() // NT
         dTp = torch.empty_like(fake_T_p)
         ops.l1_loss(fake_T_p, self.real_T, opt.lambda_G2_L1 / per_patch / n, sl["G2_L1"], dTp, opt.lambda_G2_L1 / per_patch / n)
+        if self.lpips is not None and opt.lambda_G2_lpips > 0:      # _compute_touch_lpips_loss :1619-1658: sum over the NT patches, mean over images
+            ln2, dxp = self.lpips.loss_and_grad(fake_T_p.transpose(0, 1).reshape(-1, 1, 32, 32), None, gscale=opt.lambda_G2_lpips / n,
+                                                real_feats=self._lp_real_T)
+            dTp.add_(dxp.view(2, -1, 32, 32).transpose(0, 1))
+            sl["G2_lpips"].add_(ln2.sum() * (opt.lambda_G2_lpips / n))
         dT = torch.zeros_like(fake_T)
         ops.patch_scatter_add(dTp, 0, 2, ox, oy, dT)
+        if self.lpips is not None and opt.lambda_G1_lpips > 0:      # compute_G1_loss :1707-1715: LPIPS(fake_I, real_I).mean() * lambda
+            ln, _ = self.lpips.loss_and_grad(fake_I, None, gscale=opt.lambda_G1_lpips / n, dx=dI, dx_c0=0, accumulate=True,
+                                             real_feats=self._lp_real_I)
+            sl["G_lpips"].add_(ln.sum() * (opt.lambda_G1_lpips / n))
         if self.nce_layers:
             self._nce_step(dI, n)
         G.bwd(self._g_ctx, dI, dT)
@@ -541,6 +564,11 @@ class SinSKITGModel:
         if getattr(self, "nce_layers", None) and getattr(self, "_nce_losses", None):
             per_layer = torch.stack([c.mean() for c in self._nce_losses]).cpu().numpy()
             extra["NCE"] = float(per_layer.mean()) * o.lambda_NCE
+        if getattr(self, "lpips", None) is not None:
+            if o.lambda_G1_lpips > 0:
+                extra["G_lpips"] = float(v[5])
+            if o.lambda_G2_lpips > 0:
+                extra["G2_lpips"] = float(v[6])
         return dict(extra,
             D_fake_I=float(v[0]) * o.lambda_G1_GAN, D_real_I=float(v[1]) * o.lambda_G1_GAN,
             G_GAN=float(v[2]) * o.lambda_G1_GAN, G_L1=float(v[3]), G2_L1=float(v[4]),
