@@ -12,7 +12,12 @@ from oracle import skit_oracle as O  # noqa: E402  (synthetic batch factory only
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 arch = sys.argv[2] if len(sys.argv) > 2 else "B"
-opt = vts_b200.default_options() if arch == "B" else vts_b200.default_options(netG="unet256_custom", ngf=10, ndf=8)
+if arch == "B":
+    opt = vts_b200.default_options()
+elif arch == "L":      # arch B + the reference's default LPIPS terms
+    opt = vts_b200.default_options(lambda_G1_lpips=1.0, lambda_G2_lpips=10.0)
+else:
+    opt = vts_b200.default_options(netG="unet256_custom", ngf=10, ndf=8)
 torch.manual_seed(0)
 m = vts_b200.SinSKITGModel(opt)
 m.set_input(O.synthetic_batch(size, NT=64, seed=0))

@@ -288,9 +288,8 @@ __global__ void __launch_bounds__(256) conv_thin_kernel(ConvP p, int n_img, int 
     }
 }
 
-template <int MODE, int FMT>
-static int launch_thin(const ConvP& p, int n_img, cudaStream_t st) {
-    constexpr int PIX = (MODE == 0) ? 4 : 1;
+template <int MODE, int FMT, int PIX>
+static int launch_thin_pix(const ConvP& p, int n_img, cudaStream_t st) {
     const int row_w = (MODE == 0) ? p.wo : p.wp, rows_y = (MODE == 0) ? p.ho : p.hp;
     const int gpr = cdiv(row_w, PIX);
     const long long warps = (long long)n_img * rows_y * gpr;
@@ -299,6 +298,14 @@ static int launch_thin(const ConvP& p, int n_img, cudaStream_t st) {
     else if (p.ncol <= 4) conv_thin_kernel<MODE, FMT, 4, PIX><<<blocks, 256, 0, st>>>(p, n_img, gpr);
     else conv_thin_kernel<MODE, FMT, 8, PIX><<<blocks, 256, 0, st>>>(p, n_img, gpr);
     return check_launch("conv_thin_kernel");
+}
+
+// Pixels per warp: 4 for forward convs and for stride-1 input gradients (weights and the shuffle reduction amortised over
+// four outputs); strided input gradients keep one pixel per warp so that both tap parities can be skipped.
+template <int MODE, int FMT>
+static int launch_thin(const ConvP& p, int n_img, cudaStream_t st) {
+    if (MODE == 0 || p.stride == 1) return launch_thin_pix<MODE, FMT, 4>(p, n_img, st);
+    return launch_thin_pix<MODE, FMT, 1>(p, n_img, st);
 }
 
 // ---------------------------------------------------------------------------------- thin-output 7x7 head

@@ -377,7 +377,7 @@ class SinSKITGModel:
     def _fork(self, i):
         bs = getattr(self, "_bstreams", None)
         if bs is None:
-            bs = self._bstreams = [torch.cuda.Stream(device=self.device) for _ in range(5)]
+            bs = self._bstreams = [torch.cuda.Stream(device=self.device) for _ in range(6)]
         bs[i].wait_stream(torch.cuda.current_stream())
         return torch.cuda.stream(bs[i])
 
@@ -446,6 +446,21 @@ class SinSKITGModel:
         if more:
             ops.patch_gather([fake_T, self.real_S, fake_I], self._fo_dev[0], self._fo_dev[1], 32, ctot=7, dst=self.more_in)
 
+        # ---- perceptual terms on the generated image / patches: they need only G's output and the real features from
+        #      branch 0, so the whole VGG forward + input gradient runs on its own branch beside both discriminator
+        #      steps; its gradients are added to dI / dTp just before G's backward
+        if self.lpips is not None:
+            lp = self._lp_out = {}
+            if opt.lambda_G1_lpips > 0:      # compute_G1_loss :1707-1715: LPIPS(fake_I, real_I).mean() * lambda
+                with self._fork(4):
+                    torch.cuda.current_stream().wait_stream(self._bstreams[0])
+                    lp["I"] = self.lpips.loss_and_grad(fake_I, None, gscale=opt.lambda_G1_lpips / n, real_feats=self._lp_real_I)
+            if opt.lambda_G2_lpips > 0:      # _compute_touch_lpips_loss :1619-1658: sum over the NT patches, mean over images
+                with self._fork(5):          # 128 images of 32x32: launch-latency bound, so beside the full-image pass
+                    torch.cuda.current_stream().wait_stream(self._bstreams[0])
+                    lp["T"] = self.lpips.loss_and_grad(fake_T_p.transpose(0, 1).reshape(-1, 1, 32, 32), None,
+                                                       gscale=opt.lambda_G2_lpips / n, real_feats=self._lp_real_T)
+
         # ---- fake passes: D2 (patches) and D2 (random patches) beside D1 (full image)
         with self._fork(2):
             run_D2["fake"] = []
@@ -490,17 +505,19 @@ class SinSKITGModel:
         per_patch = fake_T_p.numel() // NT
         dTp = torch.empty_like(fake_T_p)
         ops.l1_loss(fake_T_p, self.real_T, opt.lambda_G2_L1 / per_patch / n, sl["G2_L1"], dTp, opt.lambda_G2_L1 / per_patch / n)
-        if self.lpips is not None and opt.lambda_G2_lpips > 0:      # _compute_touch_lpips_loss :1619-1658: sum over the NT patches, mean over images
-            ln2, dxp = self.lpips.loss_and_grad(fake_T_p.transpose(0, 1).reshape(-1, 1, 32, 32), None, gscale=opt.lambda_G2_lpips / n,
-                                                real_feats=self._lp_real_T)
-            dTp.add_(dxp.view(2, -1, 32, 32).transpose(0, 1))
-            sl["G2_lpips"].add_(ln2.sum() * (opt.lambda_G2_lpips / n))
+        if self.lpips is not None:
+            self._join(*([4] if "I" in self._lp_out else []), *([5] if "T" in self._lp_out else []))
+            if "T" in self._lp_out:
+                ln2, dxp = self._lp_out["T"]
+                dTp.add_(dxp.view(2, -1, 32, 32).transpose(0, 1))
+                sl["G2_lpips"].add_(ln2.sum() * (opt.lambda_G2_lpips / n))
+            if "I" in self._lp_out:
+                ln, dI_lp = self._lp_out["I"]
+                dI.add_(dI_lp)
+                sl["G_lpips"].add_(ln.sum() * (opt.lambda_G1_lpips / n))
+            self._lp_out = None
         dT = torch.zeros_like(fake_T)
         ops.patch_scatter_add(dTp, 0, 2, ox, oy, dT)
-        if self.lpips is not None and opt.lambda_G1_lpips > 0:      # compute_G1_loss :1707-1715: LPIPS(fake_I, real_I).mean() * lambda
-            ln, _ = self.lpips.loss_and_grad(fake_I, None, gscale=opt.lambda_G1_lpips / n, dx=dI, dx_c0=0, accumulate=True,
-                                             real_feats=self._lp_real_I)
-            sl["G_lpips"].add_(ln.sum() * (opt.lambda_G1_lpips / n))
         if self.nce_layers:
             self._nce_step(dI, n)
         G.bwd(self._g_ctx, dI, dT)
