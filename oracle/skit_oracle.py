@@ -12,6 +12,10 @@ oracle is pinned against *outputs of the real reference code* run in the build c
 the full `SinSKITGModel.optimize_parameters`, and commits the results under tests/golden/.
 tests/test_oracle_golden.py checks every function here against those fixtures.
 
+Exception: `lpips_vgg` restates the third-party pip package lpips 0.1.4 (absent from /root/reference and from this image);
+its VGG16 trunk is pinned against torchvision's vgg16 module, its head is PARITY UNPINNED (no fixture exists to check it).
+The StyleGAN2 generator restatement is pinned by tests/golden/stylegan2.npz (bit-identical to the reference on CPU).
+
 Everything is a pure function over a flat `state` dict {reference state_dict key: tensor}
 (fp32, NCHW, reference shapes), so the same weights drive the oracle and the CUDA path.
 Each function cites the reference file:line it restates (paths relative to /root/reference).
