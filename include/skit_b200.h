@@ -384,6 +384,18 @@ int skit_sg2_bias_act(const float* raw, int n, int h, int w, int craw, int c, co
                       const float* noise, const float* noise_w, const float* skip, int shuffle,
                       int act, float gain, float post, float* dense, const skit_operand* op, int pad, float* nchw,
                       int nchw_c, void* stream);
+/* Backward of skit_sg2_bias_act.  The gradient w.r.t. its OUTPUT arrives as up to two zero-haloed tensors
+ * ([n][H+2p][W+2p][c] fp32: input gradients of the convs that consumed it) and / or a dense one; d_out is their sum.
+ *   draw  (operand [n][h+2q][w+2q][c or 4c], zero halo, fp32 or bf16x2) = d_out * post * (act ? gain * lrelu'(raw + bias + nw noise) : 1),
+ *         written in the RAW conv output's layout (space-to-depth when shuffle) — the conv's backward operand;
+ *   dskip (optional, dense) = d_out * post;  dbias[c] += sum draw;  *dnoise_w += sum draw * noise. */
+int skit_sg2_bias_act_bwd(const float* raw, int n, int h, int w, int craw, int c, const float* bias,
+                          const float* noise, const float* noise_w, int shuffle, int act, float gain, float post,
+                          const float* dpad_a, int pad_a, const float* dpad_b, int pad_b, const float* ddense,
+                          const skit_operand* draw, int q, float* dskip, float* dbias, float* dnoise_w, void* stream);
+/* Transpose of skit_sg2_weight_prep: dw[co][ci][k][k] += (d eff / d w)^T deff, through the blur fold, the EqualConv scale and
+ * (mode 2) the demodulation. */
+int skit_sg2_weight_prep_bwd(const float* w, int co, int ci, int k, int mode, const float* deff, float* dw, void* stream);
 
 /* ---- LPIPS-VGG16 perceptual loss (pip `lpips` 0.1.4 LPIPS(net='vgg'); call sites models/sinskitG_model.py:495, 1639-1645, 1711)
  * The VGG16 trunk runs on skit_conv2d_fwd / skit_conv2d_dgrad_* with frozen packs; these are the pieces around it.

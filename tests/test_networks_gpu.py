@@ -371,3 +371,47 @@ def test_lpips_value_and_input_gradient_vs_oracle(V, n, cin, h, w):
     wide = torch.ones(n, cin + 2, h, w, device="cuda")
     m.loss_and_grad(fake.cuda(), real.cuda(), gscale=0.5, dx=wide, dx_c0=1, accumulate=True)
     assert rel(wide[:, 1:1 + cin] - 1, 0.5 * fr.grad) < GRAD_REL and torch.equal(wide[:, 0], torch.ones_like(wide[:, 0]))
+
+
+@pytest.mark.parametrize("ngf,opt_res,S,n,gate", [(4, 128, 64, 2, 2e-3), (64, 512, 64, 1, GRAD_REL)])
+def test_stylegan2_generator_backward_vs_oracle(V, ngf, opt_res, S, n, gate):
+    """Explicit backward of the StyleGAN2 generator (fwd(save) / bwd): the gradient of sum(fake * R) w.r.t. every parameter —
+    EqualConv / modulated weights through the transposed blur, scale and demodulation fold, FusedLeakyReLU biases, the noise
+    strength — against autograd through the CPU oracle.  ngf 4: fp32 CUDA-core convs; ngf 64: tcgen05 convs, stride-2
+    parity-class and sub-pixel input gradients (LeakyReLU mask flips: gated like the other whole-network gradients)."""
+    from oracle import skit_oracle as O
+    torch.manual_seed(13)
+    G = V.networks.define_G(9, 5, ngf, "stylegan2", "instance", False, "xavier", 0.02, False, False, [0], _sg2_opt("stylegan2", opt_res))
+    with torch.no_grad():
+        for k, p in G.named_parameters():
+            if k.endswith("bias"):
+                p.normal_(0, 0.3)
+            elif k.endswith("noise.weight"):
+                p.fill_(0.29)
+    x = rand_input(51, n, 9, S, S)
+    noise = torch.randn(n, 1, S, S, generator=torch.Generator().manual_seed(52))
+    R = torch.randn(n, 3, S, S, generator=torch.Generator().manual_seed(53))
+    sdr = {k: v.detach().cpu().clone() for k, v in G.state_dict().items()}
+    for k, v in sdr.items():
+        if not k.endswith("kernel"):
+            v.requires_grad_(True)
+    want = O.stylegan2_g_forward(sdr, x, n_blocks=6, noises=[noise])
+    (want * R).sum().backward()
+    fake, _, ctx = G.fwd(x.cuda(), noises=[noise.cuda()], save=True)
+    assert rel(fake, want) < GATE
+    G.zero_grad()
+    G.bwd(ctx, R.cuda())
+    torch.cuda.synchronize()
+    worst = 0.0
+    for k, p in G.named_parameters():
+        g_ref = sdr[k].grad
+        assert p.grad is not None, k
+        r, c = rel(p.grad, g_ref), cos(p.grad, g_ref)
+        worst = max(worst, r)
+        assert r < gate and c > GRAD_COS, (k, r, c)
+    print("stylegan2 ngf %d worst parameter-gradient rel err %.2e" % (ngf, worst))
+    # a second backward accumulates (the folded-filter gradients were cleared)
+    _, _, ctx = G.fwd(x.cuda(), noises=[noise.cuda()], save=True)
+    G.bwd(ctx, R.cuda())
+    k0, p0 = next(iter(G.named_parameters()))
+    assert rel(p0.grad, 2 * sdr[k0].grad) < gate

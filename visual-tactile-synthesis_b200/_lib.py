@@ -48,6 +48,8 @@ SIGNATURES = {
     "skit_maxpool2_fwd": [_P, _I, _I, _I, _I, _OP, _I, _P],
     "skit_maxpool2_bwd": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "skit_lpips_layer": [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P],
+    "skit_sg2_weight_prep_bwd": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "skit_sg2_bias_act_bwd": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _F, _F, _P, _I, _P, _I, _P, _OP, _I, _P, _P, _P, _P],
     "skit_sg2_weight_prep": [_P, _I, _I, _I, _I, _P, _P],
     "skit_sg2_bias_act": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _F, _F, _P, _OP, _I, _P, _I, _P],
     "skit_pack_conv_weights_folded": [_P, _I, _I, _I, _I, _I, _P, _P, _P],

@@ -152,6 +152,160 @@ __global__ void __launch_bounds__(256) sg2_bias_act_kernel(Sg2ActP p) {
     }
 }
 
+// Transpose of sg2_weight_prep_kernel: dw[o] += (d eff / d w[o])^T deff.  One block per output channel; mode 2 stages the
+// gradient w.r.t. the demodulated filter in shared memory (ci * 9 floats) for the demodulation's rank-1 correction
+//   v = scale w, wd = v d, d = rsqrt(sum v^2 + eps):  dL/dv = d G - d^3 v sum(G v).
+__global__ void __launch_bounds__(256) sg2_weight_prep_bwd_kernel(const float* __restrict__ w, int co, int ci, int k, int mode,
+                                                                  const float* __restrict__ deff, float* __restrict__ dw) {
+    extern __shared__ float sG[];
+    __shared__ float red[2][8];
+    __shared__ float s_tot[2];
+    const int o = blockIdx.x;
+    const int kk = k * k;
+    const float scale = rsqrtf((float)(ci * kk));
+    const float* wo = w + (long long)o * ci * kk;
+    float* dwo = dw + (long long)o * ci * kk;
+    if (mode == 0) {
+        for (int i = threadIdx.x; i < ci * kk; i += 256) dwo[i] += scale * deff[(long long)o * ci * kk + i];
+        return;
+    }
+    if (mode == 1) {
+        const int K = k + 3;
+        for (int i = threadIdx.x; i < ci * kk; i += 256) {
+            const int c = i / kk, r = i - c * kk, t = r / k, s = r - t * k;
+            const float* e = deff + ((long long)o * ci + c) * K * K;
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) acc = fmaf(e[(t + j) * K + s + jj], blur_tap(j) * blur_tap(jj), acc);
+            dwo[i] += scale * acc;
+        }
+        return;
+    }
+    // mode 2
+    float sv2 = 0.f, sgv = 0.f;
+    for (int i = threadIdx.x; i < ci * 9; i += 256) {
+        const int c = i / 9, r = i - c * 9, t = r / 3, s = r - t * 3;
+        float g = 0.f;
+        for (int ph = 0; ph < 4; ph++) {
+            const int py = ph >> 1, px = ph & 1;
+            const float* e = deff + (((long long)ph * co + o) * ci + c) * 9;
+            for (int a = 0; a < 3; a++) {
+                const int jy = t - 1 - py + 2 * a;
+                if (jy < 0 || jy > 3) continue;
+                for (int b = 0; b < 3; b++) {
+                    const int jx = s - 1 - px + 2 * b;
+                    if (jx < 0 || jx > 3) continue;
+                    g = fmaf(e[a * 3 + b], 4.f * blur_tap(jy) * blur_tap(jx), g);
+                }
+            }
+        }
+        sG[i] = g;
+        const float v = scale * wo[i];
+        sv2 = fmaf(v, v, sv2); sgv = fmaf(g, v, sgv);
+    }
+    sv2 = warp_sum(sv2); sgv = warp_sum(sgv);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sv2; red[1][threadIdx.x >> 5] = sgv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 8; i++) { a += red[0][i]; b += red[1][i]; }
+        s_tot[0] = rsqrtf(a + 1e-8f); s_tot[1] = b;
+    }
+    __syncthreads();
+    const float d = s_tot[0], S = s_tot[1];
+    for (int i = threadIdx.x; i < ci * 9; i += 256) {
+        const float v = scale * wo[i];
+        dwo[i] += scale * (d * sG[i] - d * d * d * v * S);
+    }
+}
+
+struct Sg2BwdP {
+    const float* raw; int n, h, w, craw, c;     // as in the forward pass (h, w: raw resolution)
+    const float* bias; const float* noise; const float* noise_w;
+    int shuffle, act; float gain, post;
+    const float* dpa; int pa;                   // gradient w.r.t. the OUTPUT as haloed tensors [n][H+2p][W+2p][c] ...
+    const float* dpb; int pb;
+    const float* dd;                            // ... and / or dense [n][H][W][c]; d_out = sum of those given
+    float* o0; __nv_bfloat16* oh; __nv_bfloat16* ol; int fmt, q;     // d_raw operand [n][h+2q][w+2q][craw_eff], zero halo
+    float* dskip;                               // optional dense [n][H][W][c] = d_out * post (gradient of the skip input)
+    float* dbias; float* dnoise_w;              // optional accumulators (+=)
+};
+
+// One thread per channel quad of a padded RAW-operand pixel.  d_raw = d_out * post * (act ? gain * lrelu'(t) : 1),
+// t = raw + bias + nw * noise.
+__global__ void __launch_bounds__(256) sg2_bias_act_bwd_kernel(Sg2BwdP p) {
+    __shared__ float s_db[512];
+    __shared__ float s_red[8];
+    const int ce = p.shuffle ? 4 * p.c : p.c;            // channels of the raw gradient operand
+    const int cv = ce >> 2, cq = p.c >> 2;
+    const int H = p.shuffle ? 2 * p.h : p.h, W = p.shuffle ? 2 * p.w : p.w;
+    const int hq = p.h + 2 * p.q, wq = p.w + 2 * p.q;
+    const long long total = (long long)p.n * hq * wq * cv;
+    for (int i = threadIdx.x; i < p.c; i += 256) s_db[i] = 0.f;
+    __syncthreads();
+    const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+    float dn = 0.f;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int qd = (int)(i % cv); long long t = i / cv;
+        const int xq = (int)(t % wq); t /= wq;
+        const int yq = (int)(t % hq); const int n = (int)(t / hq);
+        const int yr = yq - p.q, xr = xq - p.q;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yr >= 0 && yr < p.h && xr >= 0 && xr < p.w) {
+            const int ph = p.shuffle ? qd / cq : 0, ch = (p.shuffle ? qd - ph * cq : qd) * 4;
+            const int y = p.shuffle ? 2 * yr + (ph >> 1) : yr, x = p.shuffle ? 2 * xr + (ph & 1) : xr;
+            const long long pix = ((long long)n * H + y) * W + x;
+            if (p.dd) g = *reinterpret_cast<const float4*>(p.dd + pix * p.c + ch);
+            if (p.dpa) {
+                const float4 a = *reinterpret_cast<const float4*>(p.dpa + (((long long)n * (H + 2 * p.pa) + y + p.pa) * (W + 2 * p.pa) + x + p.pa) * p.c + ch);
+                g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+            }
+            if (p.dpb) {
+                const float4 a = *reinterpret_cast<const float4*>(p.dpb + (((long long)n * (H + 2 * p.pb) + y + p.pb) * (W + 2 * p.pb) + x + p.pb) * p.c + ch);
+                g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+            }
+            g.x *= p.post; g.y *= p.post; g.z *= p.post; g.w *= p.post;
+            if (p.dskip) *reinterpret_cast<float4*>(p.dskip + pix * p.c + ch) = g;
+            if (p.act) {
+                float4 v = *reinterpret_cast<const float4*>(p.raw + (((long long)n * p.h + yr) * p.w + xr) * p.craw + (p.shuffle ? ph * p.c : 0) + ch);
+                if (p.bias) { const float4 b = *reinterpret_cast<const float4*>(p.bias + ch); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+                float nz = 0.f;
+                if (p.noise) { nz = p.noise[pix]; const float a = nw * nz; v.x += a; v.y += a; v.z += a; v.w += a; }
+                g.x *= p.gain * (v.x > 0.f ? 1.f : 0.2f); g.y *= p.gain * (v.y > 0.f ? 1.f : 0.2f);
+                g.z *= p.gain * (v.z > 0.f ? 1.f : 0.2f); g.w *= p.gain * (v.w > 0.f ? 1.f : 0.2f);
+                if (p.noise) dn += nz * (g.x + g.y + g.z + g.w);
+            }
+            if (p.dbias) {
+                atomicAdd(&s_db[ch], g.x); atomicAdd(&s_db[ch + 1], g.y); atomicAdd(&s_db[ch + 2], g.z); atomicAdd(&s_db[ch + 3], g.w);
+            }
+        }
+        const long long dst = i * 4;
+        if (p.fmt == SKIT_FMT_F32) *reinterpret_cast<float4*>(p.o0 + dst) = g;
+        else {
+            const float vv[4] = {g.x, g.y, g.z, g.w};
+            __align__(8) __nv_bfloat16 hh[4];
+            __align__(8) __nv_bfloat16 ll[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) split_bf16(vv[j], hh[j], ll[j]);
+            *reinterpret_cast<uint2*>(p.oh + dst) = *reinterpret_cast<uint2*>(hh);
+            *reinterpret_cast<uint2*>(p.ol + dst) = *reinterpret_cast<uint2*>(ll);
+        }
+    }
+    if (p.dnoise_w) {
+        dn = warp_sum(dn);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dn;
+    }
+    __syncthreads();
+    if (p.dbias) for (int i = threadIdx.x; i < p.c; i += 256) if (s_db[i] != 0.f) atomicAdd(p.dbias + i, s_db[i]);
+    if (p.dnoise_w && threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; i++) t += s_red[i];
+        atomicAdd(p.dnoise_w, t);
+    }
+}
+
 }  // namespace skit
 
 using namespace skit;
@@ -189,4 +343,39 @@ extern "C" int skit_sg2_bias_act(const float* raw, int n, int h, int w, int craw
     const int blocks = (int)min((long long)148 * 16, cdivll(total, 256));
     sg2_bias_act_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p);
     return check_launch("sg2_bias_act_kernel");
+}
+
+extern "C" int skit_sg2_weight_prep_bwd(const float* w, int co, int ci, int k, int mode, const float* deff, float* dw, void* stream) {
+    SKIT_REQUIRE(w && deff && dw && co > 0 && ci > 0 && k > 0 && mode >= 0 && mode <= 2 && (mode != 2 || k == 3), "sg2_weight_prep_bwd: bad arguments");
+    const size_t smem = mode == 2 ? (size_t)ci * 9 * sizeof(float) : 0;
+    SKIT_REQUIRE(smem <= 48 * 1024, "sg2_weight_prep_bwd: ci = %d too wide for the shared-memory stage", ci);
+    sg2_weight_prep_bwd_kernel<<<co, 256, smem, as_stream(stream)>>>(w, co, ci, k, mode, deff, dw);
+    return check_launch("sg2_weight_prep_bwd_kernel");
+}
+
+extern "C" int skit_sg2_bias_act_bwd(const float* raw, int n, int h, int w, int craw, int c, const float* bias,
+                                     const float* noise, const float* noise_w, int shuffle, int act, float gain, float post,
+                                     const float* dpad_a, int pad_a, const float* dpad_b, int pad_b, const float* ddense,
+                                     const skit_operand* draw, int q, float* dskip, float* dbias, float* dnoise_w, void* stream) {
+    SKIT_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0 && c <= 512 && draw && draw->p0, "sg2_bias_act_bwd: bad arguments (c a multiple of 4, at most 512)");
+    SKIT_REQUIRE(dpad_a || dpad_b || ddense, "sg2_bias_act_bwd: no incoming gradient");
+    SKIT_REQUIRE(!act || raw, "sg2_bias_act_bwd: the activation's backward needs the saved raw conv output");
+    SKIT_REQUIRE((noise == nullptr) == (noise_w == nullptr), "sg2_bias_act_bwd: noise and its strength go together");
+    SKIT_REQUIRE(!(shuffle && dskip), "sg2_bias_act_bwd: no skip on the up-sampling layer");
+    const int ce = shuffle ? 4 * c : c;
+    SKIT_REQUIRE(draw->n == n && draw->c == ce && draw->hp == h + 2 * q && draw->wp == w + 2 * q && q >= 0,
+                 "sg2_bias_act_bwd: gradient operand dims mismatch (want [%d][%d][%d][%d])", n, h + 2 * q, w + 2 * q, ce);
+    SKIT_REQUIRE(draw->fmt == SKIT_FMT_F32 || draw->p1, "sg2_bias_act_bwd: bf16x2 operand without its lo plane");
+    Sg2BwdP p{};
+    p.raw = raw; p.n = n; p.h = h; p.w = w; p.craw = craw; p.c = c; p.bias = bias; p.noise = noise; p.noise_w = noise_w;
+    p.shuffle = shuffle; p.act = act; p.gain = gain; p.post = post;
+    p.dpa = dpad_a; p.pa = pad_a; p.dpb = dpad_b; p.pb = pad_b; p.dd = ddense;
+    p.fmt = draw->fmt; p.q = q;
+    if (draw->fmt == SKIT_FMT_F32) p.o0 = (float*)draw->p0;
+    else { p.oh = (__nv_bfloat16*)draw->p0; p.ol = (__nv_bfloat16*)draw->p1; }
+    p.dskip = dskip; p.dbias = act ? dbias : nullptr; p.dnoise_w = (act && noise) ? dnoise_w : nullptr;
+    const long long total = (long long)n * (h + 2 * q) * (w + 2 * q) * (ce / 4);
+    const int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
+    sg2_bias_act_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p);
+    return check_launch("sg2_bias_act_bwd_kernel");
 }

@@ -11,7 +11,8 @@ Parameter tree and state_dict keys are the reference's (`encoder.convs.2.conv2.1
 * FusedLeakyReLU, NoiseInjection, the ResBlock merge, depth-to-space, zero halo and the bf16 hi/lo split of the next
   conv's operand are one element-wise pass (`skit_sg2_bias_act`).
 
-Training through this generator (explicit backward) is not built: `SinSKITGModel(netG='stylegan2')` raises.
+`fwd` / `bwd` are the explicit training pair (every parameter's gradient, through the transposed fold); the skitG train
+step itself is not wired to this generator (3 output channels, stylegan_networks.py:892): `SinSKITGModel(netG='stylegan2')` raises.
 """
 import math
 
@@ -21,6 +22,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops
 from .ops import FMT_BF16X2, FMT_F32, PAD_ZERO, _p
+from .networks import _FlatParamsMixin
 
 SQRT2 = math.sqrt(2.0)
 
@@ -133,7 +135,8 @@ class _Convs(nn.Module):
 
 # ----------------------------------------------------------------------------- effective (folded) filters
 class _EffConv:
-    """One launchable conv: the folded filter tensor built by skit_sg2_weight_prep and its pack."""
+    """One launchable conv: the folded filter tensor built by skit_sg2_weight_prep, its packs, and (for training) the
+    gradient w.r.t. the folded filter, folded back into the parameter's gradient by skit_sg2_weight_prep_bwd."""
 
     def __init__(self, src, mode, stride, pad, co_pad=0):
         w = src.weight
@@ -144,18 +147,71 @@ class _EffConv:
         self.co = 4 * co if mode == 2 else max(co, co_pad)
         self.weight = torch.zeros(self.co, ci, self.k, self.k, dtype=torch.float32, device=w.device)
         self.use_tc = ops_tc_enabled() and ci % 64 == 0 and self.co % 64 == 0 and (stride == 1 or self.k % 2 == 0)
-        self.pack = None
+        self.packs = {}
+        self.grad = None
+
+    def pack_mode(self, mode):
+        """0 forward, 1 stride-1 tcgen05 input gradient, 2 gather input gradient (CUDA cores), 3 stride-2 tcgen05 input gradient."""
+        pk = self.packs.get(mode)
+        if pk is None:
+            pk = self.packs[mode] = ops.PackedWeights(self.weight, mode, want_f32=not self.use_tc, want_bf16=self.use_tc)
+        return pk
 
     def refresh(self):
         L.call("skit_sg2_weight_prep", _p(self.src.weight), self.co_src, self.ci, self.k_src, self.mode, _p(self.weight), L.stream())
-        if self.pack is None:
-            self.pack = ops.PackedWeights(self.weight, 0, want_f32=not self.use_tc, want_bf16=self.use_tc)
+        if not self.packs:
+            self.pack_mode(0)
         else:
-            self.pack.refresh(self.weight)
+            for pk in self.packs.values():
+                pk.refresh(self.weight)
 
     def __call__(self, x_op, ho, wo):
-        y, _ = ops.conv2d_fwd(x_op, self.pack, self.stride, x_op.pad - self.pad, ho, wo)
+        y, _ = ops.conv2d_fwd(x_op, self.pack_mode(0), self.stride, x_op.pad - self.pad, ho, wo)
         return y
+
+    # -- backward
+    @property
+    def q(self):
+        """Zero halo the raw-output gradient operand needs for this conv's input-gradient kernel."""
+        if not self.use_tc:
+            return 0
+        return self.k - 1 if self.stride == 1 else self.k // 2 - 1
+
+    @property
+    def dfmt(self):
+        return FMT_BF16X2 if self.use_tc else FMT_F32
+
+    def bwd(self, x_op, d_op, ho, wo, need_dgrad=True):
+        """d_op: gradient w.r.t. the raw output (halo self.q).  Accumulates the folded filter's gradient; returns the gradient
+        w.r.t. the haloed input operand [n][hp][wp][ci] (fp32)."""
+        if self.grad is None:
+            self.grad = torch.zeros_like(self.weight)
+        ops.conv2d_wgrad(x_op, x_op.pad - self.pad, d_op, self.q, self.k, self.stride, ho, wo, self.grad)
+        if not need_dgrad:
+            return None
+        assert x_op.pad == self.pad
+        if self.use_tc and self.stride == 1:
+            return ops.conv2d_dgrad_s1(d_op, self.pack_mode(1))
+        if self.use_tc:
+            return ops.conv2d_dgrad_s2(d_op, self.q, self.pack_mode(3), self.k, ho, wo, x_op.hp, x_op.wp)
+        return ops.conv2d_dgrad_gather(d_op.data, self.pack_mode(2), self.stride, x_op.hp, x_op.wp)
+
+    def fold_grad(self):
+        """param.grad += (d folded / d param)^T grad, then clear."""
+        if self.grad is None:
+            return
+        w = self.src.weight
+        if w.grad is None:
+            w.grad = torch.zeros_like(w)
+        L.call("skit_sg2_weight_prep_bwd", _p(w), self.co_src, self.ci, self.k_src, self.mode, _p(self.grad), _p(w.grad), L.stream())
+        self.grad.zero_()
+
+
+def _grad(p):
+    """p.grad, allocated (zeros) on first use."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
 
 
 def ops_tc_enabled():
@@ -177,8 +233,22 @@ def bias_act(raw, c, bias=None, noise=None, noise_w=None, skip=None, shuffle=Fal
     return dense, op, nchw
 
 
+def bias_act_bwd(raw, n, h, w, c, eff, bias=None, noise=None, noise_w=None, shuffle=False, act=True, gain=SQRT2, post=1.0,
+                 dpa=None, pa=0, dpb=None, pb=0, dd=None, want_dskip=False, dbias=None, dnoise_w=None):
+    """skit_sg2_bias_act_bwd -> (gradient operand for `eff`'s backward, dskip or None).  h, w: raw resolution."""
+    dev = (dpa if dpa is not None else dd if dd is not None else dpb).device
+    ce = 4 * c if shuffle else c
+    d_op = ops.Operand(n, h, w, ce, eff.q, eff.dfmt, dev)
+    H, W = (2 * h, 2 * w) if shuffle else (h, w)
+    dskip = torch.empty((n, H, W, c), dtype=torch.float32, device=dev) if want_dskip else None
+    L.call("skit_sg2_bias_act_bwd", _p(raw), n, h, w, raw.shape[3] if raw is not None else ce, c, _p(bias), _p(noise),
+           _p(noise_w) if noise is not None else None, int(shuffle), int(act), gain, post, _p(dpa), pa, _p(dpb), pb, _p(dd),
+           d_op.ref(), eff.q, _p(dskip), _p(dbias), _p(dnoise_w) if noise is not None else None, L.stream())
+    return d_op, dskip
+
+
 # ----------------------------------------------------------------------------- the generator
-class StyleGAN2Generator(nn.Module):
+class StyleGAN2Generator(_FlatParamsMixin, nn.Module):
     """define_G('stylegan2' | 'smallstylegan2') (networks.py:307-310).  forward(input, layers=[], encode_only=False)."""
 
     def __init__(self, input_nc, output_nc, ngf=64, use_dropout=False, n_blocks=6, opt=None, **unused):
@@ -251,7 +321,7 @@ class StyleGAN2Generator(nn.Module):
     def _fmt(self, *consumers):
         return FMT_BF16X2 if any(self._eff[c].use_tc for c in consumers) else FMT_F32
 
-    def _resblock(self, m, x_op, x_dense, h, w, nxt):
+    def _resblock(self, m, x_op, x_dense, h, w, nxt, saved=None):
         """x_op: zero-haloed (pad 1) operand of the block input; returns (dense, operand pad 1 in the format `nxt` wants)."""
         E = self._eff
         raw1 = E[m.conv1](x_op, h, w)
@@ -267,7 +337,29 @@ class StyleGAN2Generator(nn.Module):
             skip = E[m.skip](x_op, ho, wo) if isinstance(m.skip, ConvLayer) else x_dense
         dense, op, _ = bias_act(raw2, m.co, bias=m.conv2.act_bias, skip=skip, gain=SQRT2, post=1.0 / SQRT2,
                                 want_dense=True, op_pad=1, op_fmt=nxt)
+        if saved is not None:
+            saved.append(("res", m, x_op, h, w, raw1, h1, raw2, ho, wo))
         return dense, op, ho, wo
+
+    def _resblock_bwd(self, rec, grads):
+        """grads = (dpa, pa, dpb, pb, dd): gradient w.r.t. the block output as haloed tensors and / or dense.  Returns the
+        same tuple for the block input."""
+        _, m, x_op, h, w, raw1, h1, raw2, ho, wo = rec
+        E = self._eff
+        e1, e2 = E[m.conv1], E[m.conv2]
+        n = x_op.n
+        dpa, pa, dpb, pb, dd = grads
+        _grad(m.conv2.act_bias), _grad(m.conv1.act_bias)
+        d2, dskip = bias_act_bwd(raw2, n, ho, wo, m.co, e2, bias=m.conv2.act_bias, gain=SQRT2, post=1.0 / SQRT2, dpa=dpa, pa=pa,
+                                 dpb=dpb, pb=pb, dd=dd, want_dskip=True, dbias=m.conv2.act_bias.grad)
+        dp_h1 = e2.bwd(h1, d2, ho, wo)
+        d1, _ = bias_act_bwd(raw1, n, h, w, m.ci, e1, bias=m.conv1.act_bias, dpa=dp_h1, pa=h1.pad, dbias=m.conv1.act_bias.grad)
+        dp_x = e1.bwd(x_op, d1, h, w)
+        if isinstance(m.skip, ConvLayer):
+            es = E[m.skip]
+            ds, _ = bias_act_bwd(None, n, ho, wo, m.co, es, act=False, dd=dskip)     # dense -> the skip conv's gradient operand
+            return dp_x, x_op.pad, es.bwd(x_op, ds, ho, wo), x_op.pad, None
+        return dp_x, x_op.pad, None, 0, dskip
 
     def _next_fmt(self, seq, i):
         """Operand format the consumer(s) of block i's output want."""
@@ -282,6 +374,13 @@ class StyleGAN2Generator(nn.Module):
     def forward(self, input, layers=[], encode_only=False, noises=None):
         """input NCHW fp32 -> fake [n,3,S,S] (+ encoder features at `layers`, indices into encoder.convs).
         noises: optional list of [n,1,H,W] tensors, one per StyledConv (default: drawn on the device like NoiseInjection)."""
+        fake, feats, _ = self.fwd(input, layers=layers, encode_only=encode_only, noises=noises, save=False)
+        if encode_only:
+            return feats
+        return (fake, feats) if len(layers) > 0 else fake
+
+    def fwd(self, input, layers=(), encode_only=False, noises=None, save=True):
+        """Explicit forward -> (fake NCHW or None, encoder features, ctx for `bwd` when save)."""
         if not input.is_cuda:
             raise RuntimeError("StyleGAN2Generator runs only on a CUDA device through libskit_b200.so; there is no CPU fallback")
         self.refresh_packs()
@@ -293,6 +392,7 @@ class StyleGAN2Generator(nn.Module):
         x = input.contiguous().float()
         n, _, h, w = x.shape
         feats = []
+        saved = [] if save else None
         if 0 in layers:
             feats.append(x)
         # stem: 1x1 conv on the raw input (thin: CUDA-core fp32 conv), activation writes the first block's operand
@@ -300,20 +400,22 @@ class StyleGAN2Generator(nn.Module):
         raw = E[enc[1]](x_op, h, w)
         seq = enc + dec
         dense, op, _ = bias_act(raw, enc[1].co, bias=enc[1].act_bias, want_dense=True, op_pad=1, op_fmt=self._next_fmt(seq, 1))
+        if save:
+            saved.append(("stem", enc[1], x_op, h, w, raw))
         if 1 in layers:
             feats.append(dense.permute(0, 3, 1, 2))
         for i in range(2, len(enc)):
             # the encoder's last block feeds the decoder's first: one sequence
-            dense, op, h, w = self._resblock(enc[i], op, dense, h, w, self._next_fmt(seq, i))
+            dense, op, h, w = self._resblock(enc[i], op, dense, h, w, self._next_fmt(seq, i), saved)
             if i in layers:
                 feats.append(dense.permute(0, 3, 1, 2))
         if encode_only:
-            return feats
+            return None, feats, saved
         si = 0
         for j, m in enumerate(dec[:-1]):
             i = len(enc) + j
             if isinstance(m, ResBlock):
-                dense, op, h, w = self._resblock(m, op, dense, h, w, self._next_fmt(seq, i))
+                dense, op, h, w = self._resblock(m, op, dense, h, w, self._next_fmt(seq, i), saved)
                 continue
             raw = E[m](op, h, w)                                  # [n, h, w, 4*co]: 2x2 sub-pixels of the up-sampled map
             nz = None
@@ -323,9 +425,47 @@ class StyleGAN2Generator(nn.Module):
                 si += 1
             last = j + 1 == len(dec) - 1
             nxt = FMT_F32 if last else self._next_fmt(seq, i)
+            if save:
+                saved.append(("up", m, op, h, w, raw, nz))
             dense, op, _ = bias_act(raw, m.conv.co, bias=m.activate.bias, noise=nz, noise_w=m.noise.weight if nz is not None else None,
                                     shuffle=True, want_dense=not last, op_pad=0 if last else 1, op_fmt=nxt)
             h, w = 2 * h, 2 * w
         raw = E[dec[-1]](op, h, w)                                # 1x1 conv to 3 (+1 zero) channels
+        if save:
+            saved.append(("head", dec[-1], op, h, w, raw))
         _, _, fake = bias_act(raw, 4, bias=self._head_bias, nchw_c=3)
-        return (fake, feats) if len(layers) > 0 else fake
+        return fake, feats, saved
+
+    def bwd(self, saved, dfake):
+        """dfake: gradient w.r.t. `fake` (NCHW [n,3,S,S]).  Accumulates into every parameter's .grad (weights through the
+        transposed blur / scale / demodulation fold, FusedLeakyReLU biases, noise strengths)."""
+        E = self._eff
+        n = dfake.shape[0]
+        grads = None
+        for rec in reversed(saved):
+            kind = rec[0]
+            if kind == "head":
+                _, m, op, h, w, raw = rec
+                dd = torch.zeros((n, h, w, 4), dtype=torch.float32, device=dfake.device)
+                dd[..., :3] = dfake.permute(0, 2, 3, 1)
+                db = torch.zeros(4, dtype=torch.float32, device=dfake.device)
+                d, _ = bias_act_bwd(raw, n, h, w, 4, E[m], bias=self._head_bias, dd=dd, dbias=db)
+                dp = E[m].bwd(op, d, h, w)
+                _grad(m.act_bias).view(-1).add_(db[:3])
+                grads = (dp, op.pad, None, 0, None)
+            elif kind == "up":
+                _, m, op, h, w, raw, nz = rec
+                dpa, pa, dpb, pb, dd = grads
+                d, _ = bias_act_bwd(raw, n, h, w, m.conv.co, E[m], bias=m.activate.bias, noise=nz,
+                                    noise_w=m.noise.weight if nz is not None else None, shuffle=True, dpa=dpa, pa=pa, dpb=dpb, pb=pb,
+                                    dd=dd, dbias=_grad(m.activate.bias), dnoise_w=_grad(m.noise.weight) if nz is not None else None)
+                grads = (E[m].bwd(op, d, h, w), op.pad, None, 0, None)
+            elif kind == "res":
+                grads = self._resblock_bwd(rec, grads)
+            else:
+                _, m, x_op, h, w, raw = rec
+                dpa, pa, dpb, pb, dd = grads
+                d, _ = bias_act_bwd(raw, n, h, w, m.co, E[m], bias=m.act_bias, dpa=dpa, pa=pa, dpb=dpb, pb=pb, dd=dd, dbias=_grad(m.act_bias))
+                E[m].bwd(x_op, d, h, w, need_dgrad=False)
+        for e in E.values():
+            e.fold_grad()
