@@ -153,3 +153,48 @@ def test_linear_lr_rule_and_default_options():
 def test_tappable_layers_cover_cut_defaults():
     G = N.define_G(9, 5, 8, "resnet_9blocks", "instance", False, "xavier", 0.02, False, False, [], ns())
     assert {0, 4, 8, 12, 16} <= G.tappable_layers()
+
+
+def _sg2_opt(netG, res):
+    return argparse.Namespace(load_size=res, crop_size=res, stylegan2_G_num_downsampling=1, netG=netG)
+
+
+@pytest.mark.parametrize("tag,netG,res", [("sg2", "stylegan2", 128), ("sg2small", "smallstylegan2", 64)])
+def test_stylegan2_state_dict_matches_reference(golden_dir, tag, netG, res):
+    """define_G('stylegan2' | 'smallstylegan2'): parameter / buffer names and shapes of the real reference (fixture written by
+    oracle/make_golden.py), the blur buffers' values, the channel table, and the loud CPU failure."""
+    g = z(golden_dir, "stylegan2.npz")
+    ref = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + ".")}
+    G = N.define_G(9, 5, 4, netG, "instance", False, "xavier", 0.02, False, False, [], _sg2_opt(netG, res))
+    sd = G.state_dict()
+    assert sorted(sd.keys()) == sorted(ref.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(ref[k].shape), k
+        if k.endswith("kernel"):
+            np.testing.assert_allclose(v.numpy(), ref[k], rtol=0, atol=1e-7)
+    G.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in ref.items()})
+    assert vts_b200.sg2_generator.channel_table(64)[512] == 64 and vts_b200.sg2_generator.channel_table(64)[256] == 128
+    assert vts_b200.sg2_generator.channel_table(10)[1024] == 5      # int(round(16 * 10 / 32))
+    with pytest.raises(KeyError):                                    # crop 1536 -> 2048: no such resolution, like the reference (:820)
+        N.define_G(9, 5, 64, "stylegan2", "instance", False, "xavier", 0.02, False, False, [], _sg2_opt("stylegan2", 1536))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G(torch.zeros(1, 9, res, res))
+
+
+def test_lpips_module_keys_and_cpu_behaviour():
+    """vts_b200.lpips_vgg.LPIPS carries the lpips package's state_dict keys (so its checkpoints load), is frozen, and fails
+    loudly without a CUDA device; the oracle's random state uses the same keys."""
+    m = vts_b200.lpips_vgg.LPIPS(net="vgg")
+    sd = m.state_dict()
+    want = set(O.lpips_random_state(0).keys())
+    assert want <= set(sd.keys())
+    assert {"lins.%d.model.1.weight" % k for k in range(5)} <= set(sd.keys())
+    assert {"scaling_layer.shift", "scaling_layer.scale"} <= set(sd.keys())
+    assert sd["net.slice1.0.weight"].shape == (64, 3, 3, 3) and sd["net.slice5.28.weight"].shape == (512, 512, 3, 3)
+    assert sd["lin3.model.1.weight"].shape == (1, 512, 1, 1)
+    assert not any(p.requires_grad for p in m.parameters()) and not m.training
+    np.testing.assert_allclose(sd["scaling_layer.shift"].flatten().numpy(), O.LPIPS_SHIFT, atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        vts_b200.lpips_vgg.LPIPS(net="alex")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 32, 32), torch.zeros(1, 3, 32, 32))
