@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) sg2_bias_act_kernel(Sg2ActP p) {
             if (p.shuffle) src = (((long long)n * p.h + (y >> 1)) * p.w + (x >> 1)) * p.craw + ((y & 1) * 2 + (x & 1)) * p.c + ch;
             else src = (((long long)n * p.h + y) * p.w + x) * p.craw + ch;
             v = *reinterpret_cast<const float4*>(p.raw + src);
-            if (p.bias) { const float4 b = *reinterpret_cast<const float4*>(p.bias + ch); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+            if (p.bias) { v.x += __ldg(p.bias + ch); v.y += __ldg(p.bias + ch + 1); v.z += __ldg(p.bias + ch + 2); v.w += __ldg(p.bias + ch + 3); }   // scalar loads: a bias inside a flat parameter bucket is only 4-byte aligned
             if (p.noise) { const float nz = nw * p.noise[((long long)n * H + y) * W + x]; v.x += nz; v.y += nz; v.z += nz; v.w += nz; }
             if (p.act) {
                 v.x = (v.x > 0.f ? v.x : 0.2f * v.x) * p.gain; v.y = (v.y > 0.f ? v.y : 0.2f * v.y) * p.gain;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) sg2_bias_act_bwd_kernel(Sg2BwdP p) {
             if (p.dskip) *reinterpret_cast<float4*>(p.dskip + pix * p.c + ch) = g;
             if (p.act) {
                 float4 v = *reinterpret_cast<const float4*>(p.raw + (((long long)n * p.h + yr) * p.w + xr) * p.craw + (p.shuffle ? ph * p.c : 0) + ch);
-                if (p.bias) { const float4 b = *reinterpret_cast<const float4*>(p.bias + ch); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+                if (p.bias) { v.x += __ldg(p.bias + ch); v.y += __ldg(p.bias + ch + 1); v.z += __ldg(p.bias + ch + 2); v.w += __ldg(p.bias + ch + 3); }   // scalar loads: a bias inside a flat parameter bucket is only 4-byte aligned
                 float nz = 0.f;
                 if (p.noise) { nz = p.noise[pix]; const float a = nw * nz; v.x += a; v.y += a; v.z += a; v.w += a; }
                 g.x *= p.gain * (v.x > 0.f ? 1.f : 0.2f); g.y *= p.gain * (v.y > 0.f ? 1.f : 0.2f);
