@@ -100,7 +100,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- CPU oracle legs
-def oracle_step_time(size, steps, warmup, nt, nf, threads):
+def oracle_step_time(size, steps, warmup, nt, nf, threads, nce=False, lpips=False):
     """Times the CPU oracle's train step (oracle/skit_oracle.py, pinned to the real reference) — the checker
     run as a baseline, never as the product."""
     from oracle import skit_oracle as O
@@ -112,16 +112,21 @@ def oracle_step_time(size, steps, warmup, nt, nf, threads):
     D = vts_b200.networks.define_D(4, 64, "multiscale", 3, "batch", "xavier", 0.02, False, 3, [], opt)
     D2 = vts_b200.networks.define_D(7, 64, "multiscale", 3, "batch", "xavier", 0.02, False, 3, [], opt)
     sds = [{k: v.detach().clone() for k, v in n.state_dict().items()} for n in (G, D, D2)]
-    cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=nt, add_fake_T_sample_size=nf)
+    cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=nt, add_fake_T_sample_size=nf, lambda_NCE=1.0 if nce else 0.0,
+                       lambda_G1_lpips=1.0 if lpips else 0.0, lambda_G2_lpips=10.0 if lpips else 0.0)
+    sdL = O.lpips_random_state(0) if lpips else None
     batch = O.step_inputs_from_batch(O.synthetic_batch(size, NT=nt, seed=0))
     rs = np.random.RandomState(0)
+    nce_sizes = [G.feature_hw(l, size, size) for l in cfg.nce_layers] if nce else []
     times = []
     state = {}
     for i in range(warmup + steps):
         rand = dict(real_b=[0.3], real_s=[0.8], fake_b=[0.6], fake_s=[0.2],
                     fake_ox=rs.randint(0, size - 32, nf).astype(np.int32), fake_oy=rs.randint(0, size - 32, nf).astype(np.int32))
+        if nce:
+            rand["nce_ids"] = [rs.permutation(h * w)[:min(cfg.num_patches, h * w)] for h, w in nce_sizes]
         t0 = time.perf_counter()
-        O.train_step(cfg, sds[0], sds[1], sds[2], state, batch, rand, step=i + 1)
+        O.train_step(cfg, sds[0], sds[1], sds[2], state, batch, rand, step=i + 1, sdL=sdL)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return float(np.mean(times))
@@ -134,7 +139,7 @@ def run_reference(a):
     cores = os.cpu_count() or 1
     s = a.cpu_sample_size
     nt, nf = 16, 8
-    t = oracle_step_time(s, max(1, min(a.steps, 3)), min(a.warmup, 1), nt, nf, cores)
+    t = oracle_step_time(s, max(1, min(a.steps, 3)), min(a.warmup, 1), nt, nf, cores, nce=a.nce, lpips=a.lpips)
     # bounded sample: a step at s x s; conv work scales with pixels, so images/s at the full size is scaled by (s/size)^2
     value = (1.0 / t) * (s * s) / float(a.size * a.size)
     sample = "CPU oracle train step at %dx%d (NT=%d NF=%d), %.2f s/step, scaled by (%d/%d)^2 to the %dx%d workload" % (s, s, nt, nf, t, s, a.size, a.size, a.size)
@@ -300,7 +305,7 @@ def run_b200(a):
         if n == 1 and not a.no_cpu_baseline:
             cores = os.cpu_count() or 1
             s, nt, nf = a.cpu_sample_size, 16, 8
-            t = oracle_step_time(s, 1, 1, nt, nf, cores)
+            t = oracle_step_time(s, 1, 1, nt, nf, cores, nce=a.nce, lpips=a.lpips)
             v = (1.0 / t) * (s * s) / float(a.size * a.size)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "CPU oracle train step at %dx%d (NT=%d NF=%d), %.2f s/step, scaled by (%d/%d)^2" % (s, s, nt, nf, t, s, a.size)}
