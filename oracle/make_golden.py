@@ -146,6 +146,26 @@ def make_networks():
     print("networks.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
 
 
+def make_options():
+    """Defaults of the reference's own option parser (TrainOptions + sinskitG model options) as JSON."""
+    import json
+    load_reference()
+    cwd = os.getcwd()
+    os.chdir(os.environ.get("VTS_REFERENCE_ROOT", "/root/reference"))
+    try:
+        with quiet():
+            from options.train_options import TrainOptions
+            to = TrainOptions()
+            to.cmd_line = "--model sinskitG --gpu_ids -1 --name golden --checkpoints_dir /tmp/vts_golden".split()
+            opt = to.parse()
+    finally:
+        os.chdir(cwd)
+    d = {k: v for k, v in vars(opt).items() if isinstance(v, (int, float, str, bool, list, type(None)))}
+    with open(os.path.join(OUT, "options.json"), "w") as f:
+        json.dump(d, f, indent=0, sort_keys=True)
+    print("options.json:", len(d), "options")
+
+
 def make_stylegan2():
     """StyleGAN2Generator (a4) through the reference's define_G.  ModulatedConv2d builds its unit style with `.cuda()`
     (stylegan_networks.py:310); on this CPU-only container Tensor.cuda is patched to the identity for the duration of the
@@ -331,7 +351,9 @@ def make_step(tag, S, NT, NF, extra):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["networks", "ops", "step", "stylegan2"]
+    which = sys.argv[1:] or ["networks", "ops", "step", "stylegan2", "options"]
+    if "options" in which:
+        make_options()
     if "stylegan2" in which:
         make_stylegan2()
     if "networks" in which:

@@ -198,3 +198,18 @@ def test_lpips_module_keys_and_cpu_behaviour():
         vts_b200.lpips_vgg.LPIPS(net="alex")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 3, 32, 32), torch.zeros(1, 3, 32, 32))
+
+
+def test_default_options_against_the_reference_parser(golden_dir):
+    """Every option the step reads carries the reference parser's default (fixture: oracle/make_golden.py options), except
+    the documented benchmark-architecture / third-party-loss overrides; reference_default_options() restores those."""
+    import json
+    ref = json.load(open(os.path.join(golden_dir, "options.json")))
+    mine = vars(vts_b200.default_options())
+    differs = {k for k in mine if k in ref and ref[k] != mine[k]}
+    assert differs == {"checkpoints_dir", "gpu_ids", "name", "netG", "ngf", "ndf", "lambda_G1_lpips", "lambda_G2_lpips",
+                       "use_vision_aided_loss"}
+    r = vars(vts_b200.reference_default_options())
+    for k in ("netG", "ngf", "ndf", "lambda_G1_lpips", "lambda_G2_lpips"):
+        assert r[k] == ref[k], k
+    assert r["use_vision_aided_loss"] is False and ref["use_vision_aided_loss"] is True

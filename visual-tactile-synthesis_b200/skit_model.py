@@ -23,8 +23,11 @@ from .model_utils import find_coords_for_patch, random_patch_offset_table, spe_g
 
 
 def default_options(**kw):
-    """The options the step reads, with the reference's defaults
-    (models/sinskitG_model.py:50-357, options/base_options.py, options/train_options.py)."""
+    """The options the step reads.  Every value is the reference parser's default (models/sinskitG_model.py:50-357,
+    options/base_options.py, options/train_options.py; pinned by tests/golden/options.json) EXCEPT the benchmark
+    architecture of BASELINE.json configs[1]: netG resnet_9blocks / ngf 64 / ndf 64 (reference: unet256_custom / 10 / 8) and the
+    third-party terms off: lambda_G1_lpips 0 / lambda_G2_lpips 0 (reference: 1 / 10) and use_vision_aided_loss False
+    (reference: True).  `reference_default_options()` gives the reference's own defaults."""
     o = dict(
         model="sinskitG", isTrain=True, gpu_ids=[0],
         netG="resnet_9blocks", ngf=64, normG="instance", no_dropout=True, no_antialias=False, no_antialias_up=False,
@@ -48,6 +51,14 @@ def default_options(**kw):
     )
     o.update(kw)
     return argparse.Namespace(**o)
+
+
+def reference_default_options(**kw):
+    """default_options() with the reference's own architecture and loss defaults: the unet256_custom generator (ngf 10),
+    PatchGANs with ndf 8, LPIPS-VGG16 terms on (1, 10).  The vision-aided discriminator stays off (not built)."""
+    o = dict(netG="unet256_custom", ngf=10, ndf=8, lambda_G1_lpips=1.0, lambda_G2_lpips=10.0)
+    o.update(kw)
+    return default_options(**o)
 
 
 class SinSKITGModel:
