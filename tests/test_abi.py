@@ -65,3 +65,20 @@ def test_python_constants_match_header():
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "skit_b200.h")).read()
     m = re.search(r"#define\s+SKIT_SUM_REPLICAS\s+(\d+)", hdr)
     assert m and int(m.group(1)) == vts_b200.ops.SUM_REPLICAS
+
+
+def test_c_host_binds_the_library_without_python(lib_path, tmp_path):
+    """examples/abi_smoke.c: a plain C program compiled against include/skit_b200.h and linked with the library; it checks the
+    boundary's error behaviour (negative code + skit_last_error text, argument validation before any CUDA call)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(lib_path)
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "abi_smoke.c"), "-o", exe,
+                    "-L", libdir, "-lskit_b200", "-Wl,-rpath," + libdir], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "conv2d_fwd: null pointer" in r.stdout and r.stdout.strip().endswith("ok")
