@@ -146,6 +146,70 @@ def make_networks():
     print("networks.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
 
 
+def make_step_lpips(S=64, NT=8, NF=4):
+    """The REAL reference's optimize_parameters with its LPIPS terms on (lambda_G1_lpips 1, lambda_G2_lpips 10, the parser's
+    defaults).  The pip package `lpips` is absent, so `lpips.LPIPS` is replaced by a module that evaluates the oracle's
+    restatement (skit_oracle.lpips_vgg) with seeded random weights: everything AROUND the criterion — the reference's call
+    sites, the per-channel touch-patch form, the view/sum/mean reductions, the loss weights and the backward into G — is the
+    reference's own code (sinskitG_model.py:1619-1658, 1707-1715, 1826-1840).  Same seeds and architecture as
+    make_step('resnet', 64, 8, 4, ...): the initial weights are those of step_resnet.npz, so only the results are stored."""
+    load_reference()
+    import torch.nn as nn
+    sys.path.insert(0, ROOT)
+    from oracle import skit_oracle as O
+
+    class OracleLPIPS(nn.Module):
+        def __init__(self, net="vgg", **kw):
+            super().__init__()
+            self.sd = O.lpips_random_state(11)
+
+        def forward(self, a, b):
+            return O.lpips_vgg(self.sd, a, b)
+
+    cwd = os.getcwd()
+    os.chdir(os.environ.get("VTS_REFERENCE_ROOT", "/root/reference"))
+    old = sys.modules["lpips"].LPIPS
+    sys.modules["lpips"].LPIPS = OracleLPIPS
+    try:
+        with quiet():
+            from options.train_options import TrainOptions
+            from models import create_model
+        cmd = ("--model sinskitG --gpu_ids -1 --name golden --checkpoints_dir /tmp/vts_golden "
+               "--crop_size %d --center_w %d --center_h %d --lambda_G1_lpips 1 --lambda_G2_lpips 10 "
+               "--use_vision_aided_loss False --batch_size_G2 %d --add_fake_T_sample_size %d "
+               "--netG resnet_9blocks --ngf 8" % (S, S, S, NT, NF)).split()
+        torch.manual_seed(100)
+        with quiet():
+            to = TrainOptions()
+            to.cmd_line = cmd
+            opt = to.parse()
+            model = create_model(opt)
+            model.setup(opt)
+        model.train()
+        out = {"G_before_norm": np.float64(sum(v.double().pow(2).sum().item() for v in model.netG.state_dict().values()) ** 0.5)}
+        batch = O.synthetic_batch(S, NT=NT, seed=0, ellipse_mask=True)
+        torch.manual_seed(200)
+        random.seed(300)
+        with quiet():
+            model.set_input(batch, phase="train")
+            model.optimize_parameters(1)
+        torch.manual_seed(200)
+        out["rand_u"] = np.array([torch.rand(1, 1, 1, 1).item() for _ in range(4)], dtype=np.float32)
+        out["fake_ox"] = model.fake_sample_offset_x.numpy().reshape(-1).astype(np.int32)
+        out["fake_oy"] = model.fake_sample_offset_y.numpy().reshape(-1).astype(np.int32)
+        for k, v in model.get_current_losses().items():
+            out["loss_" + k] = np.float64(v)
+        for k, p in model.netG.named_parameters():
+            if p.grad is not None:
+                out["G_grad." + k] = p.grad.numpy()
+        out["meta"] = np.array([S, NT, NF, 11])
+    finally:
+        sys.modules["lpips"].LPIPS = old
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "step_resnet_lpips.npz"), **out)
+    print("step_resnet_lpips.npz:", len(out), "arrays;", {k: float(v) for k, v in out.items() if k.startswith("loss_") and "lpips" in k})
+
+
 def make_options():
     """Defaults of the reference's own option parser (TrainOptions + sinskitG model options) as JSON."""
     import json
@@ -351,9 +415,11 @@ def make_step(tag, S, NT, NF, extra):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["networks", "ops", "step", "stylegan2", "options"]
+    which = sys.argv[1:] or ["networks", "ops", "step", "stylegan2", "options", "step_lpips"]
     if "options" in which:
         make_options()
+    if "step_lpips" in which:
+        make_step_lpips()
     if "stylegan2" in which:
         make_stylegan2()
     if "networks" in which:

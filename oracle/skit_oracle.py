@@ -13,7 +13,8 @@ the full `SinSKITGModel.optimize_parameters`, and commits the results under test
 tests/test_oracle_golden.py checks every function here against those fixtures.
 
 Exception: `lpips_vgg` restates the third-party pip package lpips 0.1.4 (absent from /root/reference and from this image);
-its VGG16 trunk is pinned against torchvision's vgg16 module, its head is PARITY UNPINNED (no fixture exists to check it).
+its VGG16 trunk is pinned against torchvision's vgg16 module, its head is PARITY UNPINNED (no fixture exists to check it);
+the train step's USE of it is pinned against the real reference's call sites (tests/golden/step_resnet_lpips.npz).
 The StyleGAN2 generator restatement is pinned by tests/golden/stylegan2.npz (bit-identical to the reference on CPU).
 
 Everything is a pure function over a flat `state` dict {reference state_dict key: tensor}

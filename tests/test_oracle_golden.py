@@ -224,3 +224,35 @@ def test_train_step_matches_reference(golden_dir, tag, netG):
                 # running means inherit +-lr*0.1 of noise from the zero-gradient conv biases that Adam
                     # moved by +-lr in the D step (sign of rounding noise) -> absolute tolerance 3e-4
                     close(v, z["%s_after.%s" % (net, k)], rtol=1e-4, atol=3e-4)
+
+
+def test_train_step_lpips_wiring_matches_reference(golden_dir):
+    """The oracle's LPIPS wiring (full-image term, per-channel touch-patch term, reductions, weights, backward into G)
+    against the REAL reference's optimize_parameters run with the same criterion plugged into its `lpips.LPIPS` call sites
+    (tests/golden/step_resnet_lpips.npz, oracle/make_golden.py: make_step_lpips).  Initial weights: step_resnet.npz."""
+    z0 = load(golden_dir, "step_resnet.npz")
+    z = load(golden_dir, "step_resnet_lpips.npz")
+    S, NT, NF, lp_seed = [int(v) for v in z["meta"]]
+    sdG, sdD, sdD2 = sd_from(z0, "G_before."), sd_from(z0, "D_before."), sd_from(z0, "D2_before.")
+    norm = sum(v.double().pow(2).sum().item() for v in sdG.values()) ** 0.5
+    assert abs(norm / float(z["G_before_norm"]) - 1) < 1e-6          # same initial generator as the fixture's run
+    cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_G1_lpips=1.0, lambda_G2_lpips=10.0)
+    batch = O.step_inputs_from_batch(O.synthetic_batch(S, NT=NT, seed=0, ellipse_mask=True))
+    u = z["rand_u"]
+    rand = dict(real_b=u[0], real_s=u[1], fake_b=u[2], fake_s=u[3], fake_ox=z["fake_ox"], fake_oy=z["fake_oy"])
+    res = O.train_step(cfg, sdG, sdD, sdD2, {}, batch, rand, step=1, sdL=O.lpips_random_state(lp_seed))
+    assert "G_lpips" in res["losses"] and "G2_lpips" in res["losses"]
+    for k, v in res["losses"].items():
+        ref = float(z["loss_l_" + k])
+        assert abs(v - ref) <= 2e-5 * max(1.0, abs(v)), (k, v, ref)
+    keys = [k[len("G_grad."):] for k in z if k.startswith("G_grad.")]
+    assert len(keys) > 40
+    for k in keys:
+        g_ref = z["G_grad." + k]
+        err = np.linalg.norm(res["grads_G"][k].numpy() - g_ref) / max(np.linalg.norm(g_ref), 1e-30)
+        wk = "G_grad." + k.replace(".bias", ".weight")
+        noise = k.endswith(".bias") and wk in z and np.linalg.norm(g_ref) < 1e-3 * np.linalg.norm(z[wk])
+        assert err < 2e-3 or noise, (k, err)
+    # the perceptual terms moved the generator's gradient (they are not a no-op in this fixture)
+    k = "model.30.weight"
+    assert np.linalg.norm(z["G_grad." + k] - z0["G_grad." + k]) > 1e-3 * np.linalg.norm(z0["G_grad." + k])
