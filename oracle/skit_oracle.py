@@ -418,9 +418,9 @@ def gather_patches(img, ox, oy, cutout):
     assert img.shape[0] == 1
     H, W = img.shape[-2:]
     ps = int(np.max(cutout))
-    ar = torch.arange(ps)
-    ys = (torch.as_tensor(np.asarray(oy), dtype=torch.long)[:, None] + ar[None]).clamp(0, H - 1)  # [P, ps]
-    xs = (torch.as_tensor(np.asarray(ox), dtype=torch.long)[:, None] + ar[None]).clamp(0, W - 1)
+    ar = torch.arange(ps, device=img.device)
+    ys = (torch.as_tensor(np.asarray(oy), dtype=torch.long, device=img.device)[:, None] + ar[None]).clamp(0, H - 1)  # [P, ps]
+    xs = (torch.as_tensor(np.asarray(ox), dtype=torch.long, device=img.device)[:, None] + ar[None]).clamp(0, W - 1)
     out = img[0][:, ys[:, :, None], xs[:, None, :]]  # [C, P, ps, ps]
     return out.permute(1, 0, 2, 3).contiguous()
 
@@ -470,8 +470,8 @@ def compute_normal(T, scale_nz=0.25):
 def diffaugment_bs(x, u_b, u_s):
     """DiffAugment policy 'bs' (thirdparty/DiffAugment.py:25-33): brightness x + (U_b - 0.5),
     then saturation (x - mean_c) * 2 U_s + mean_c.  U_* are the per-sample torch.rand draws."""
-    u_b = torch.as_tensor(u_b, dtype=x.dtype).view(-1, 1, 1, 1)
-    u_s = torch.as_tensor(u_s, dtype=x.dtype).view(-1, 1, 1, 1)
+    u_b = torch.as_tensor(u_b, dtype=x.dtype, device=x.device).view(-1, 1, 1, 1)
+    u_s = torch.as_tensor(u_s, dtype=x.dtype, device=x.device).view(-1, 1, 1, 1)
     x = x + (u_b - 0.5)
     m = x.mean(dim=1, keepdim=True)
     return ((x - m) * (u_s * 2) + m).contiguous()
@@ -485,7 +485,7 @@ def patch_sample_f(feats, patch_ids, mlps=None):
     for i, f in enumerate(feats):
         B, C, H, W = f.shape
         fr = f.permute(0, 2, 3, 1).flatten(1, 2)
-        ids = torch.as_tensor(np.asarray(patch_ids[i]), dtype=torch.long)
+        ids = torch.as_tensor(np.asarray(patch_ids[i]), dtype=torch.long, device=f.device)
         xs = fr[:, ids, :].flatten(0, 1)
         if mlps is not None:
             W1, b1, W2, b2 = mlps[i]
@@ -505,7 +505,7 @@ def patchnce_loss(feat_q, feat_k, nce_T=0.07, batch_size=1, all_negatives_from_m
     k = feat_k.view(b, -1, dim)
     n = q.shape[1]
     l_neg = torch.bmm(q, k.transpose(1, 2))
-    l_neg = l_neg.masked_fill(torch.eye(n, dtype=torch.bool)[None], -10.0).view(-1, n)
+    l_neg = l_neg.masked_fill(torch.eye(n, dtype=torch.bool, device=q.device)[None], -10.0).view(-1, n)
     logits = torch.cat([l_pos, l_neg], dim=1) / nce_T
     return torch.logsumexp(logits, dim=1) - logits[:, 0]
 
@@ -568,10 +568,13 @@ def g_forward(cfg, sdG, x, **kw):
     raise NotImplementedError("Generator model name [%s] is not recognized" % cfg.netG)
 
 
-def model_forward(cfg, sdG, real_S, S_pe, M, real_I=None, rand=None):
+def model_forward(cfg, sdG, real_S, S_pe, M, real_I=None, rand=None, style_code=None):
     """SinSKITGModel.forward (models/sinskitG_model.py:1293-1344).  `real_S`/`real_I` are
     already mask-multiplied by set_input (:724,734).  rand = dict(real_b, real_s, fake_b, fake_s)."""
-    out = g_forward(cfg, sdG, torch.cat([real_S, S_pe], 1))
+    kw = {}
+    if style_code is not None and cfg.netG == "unet256_custom":   # skitG: the style code enters the U-Net generators only
+        kw = dict(style_code=style_code, num_layer_style_code=getattr(cfg, "num_layer_style_code", 1))
+    out = g_forward(cfg, sdG, torch.cat([real_S, S_pe], 1), **kw)
     fake_I = out[:, 0:3] * M
     fake_T = out[:, -2:] * M
     res = dict(fake_I=fake_I, fake_T=fake_T, fake_N=compute_normal(fake_T.detach(), cfg.scale_nz))
@@ -602,13 +605,13 @@ def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.
     real_T = batch["T_images"] * batch["I_masks"]
     I_masks = batch["I_masks"]
     coords = batch["T_coords"]
-    S_pe = spe_grid(real_S.shape[2], real_S.shape[3], 4, real_S.shape[0])
+    S_pe = spe_grid(real_S.shape[2], real_S.shape[3], 4, real_S.shape[0]).to(real_S.device)
     NT = cfg.batch_size_G2
 
-    gp = {k: v.requires_grad_(True) for k, v in sdG.items() if v.dtype.is_floating_point and "filt" not in k}
+    gp = {k: v.requires_grad_(True) for k, v in sdG.items() if v.dtype.is_floating_point and "filt" not in k and "style_code_mapping" not in k}
     sdG_run = dict(sdG)
     sdG_run.update(gp)
-    fw = model_forward(cfg, sdG_run, real_S, S_pe, M, real_I, rand)
+    fw = model_forward(cfg, sdG_run, real_S, S_pe, M, real_I, rand, style_code=batch.get("style_code"))
     fake_I, fake_T = fw["fake_I"], fw["fake_T"]
 
     ox, oy, cs = patch_offsets_from_coords(coords)
@@ -627,11 +630,26 @@ def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.
             grad_hook(name, gd)
         st = opt_state.setdefault(name, {})
         with torch.no_grad():
-            for k, g in gd.items():
-                p = sd[k]
+            for k in gd:
                 if k not in st:
-                    st[k] = (torch.zeros_like(p), torch.zeros_like(p))
-                adam_step(p, g, st[k][0], st[k][1], step, lr * lr_factor, cfg.beta1, cfg.beta2)
+                    st[k] = (torch.zeros_like(sd[k]), torch.zeros_like(sd[k]))
+            if getattr(cfg, "foreach_adam", False) and gd:
+                # the same update through torch's multi-tensor primitives, as torch.optim.Adam(foreach=True) — the default on
+                # CUDA — issues it (bench.py's eager-PyTorch-on-B200 arm; one launch per op instead of one per tensor)
+                ks = list(gd)
+                ps, gs = [sd[k] for k in ks], [gd[k] for k in ks]
+                ms, vs = [st[k][0] for k in ks], [st[k][1] for k in ks]
+                torch._foreach_mul_(ms, cfg.beta1)
+                torch._foreach_add_(ms, gs, alpha=1 - cfg.beta1)
+                torch._foreach_mul_(vs, cfg.beta2)
+                torch._foreach_addcmul_(vs, gs, gs, value=1 - cfg.beta2)
+                den = torch._foreach_sqrt(vs)
+                torch._foreach_div_(den, math.sqrt(1 - cfg.beta2 ** step))
+                torch._foreach_add_(den, 1e-8)
+                torch._foreach_addcdiv_(ps, ms, den, value=-(lr * lr_factor) / (1 - cfg.beta1 ** step))
+            else:
+                for k, g in gd.items():
+                    adam_step(sd[k], g, st[k][0], st[k][1], step, lr * lr_factor, cfg.beta1, cfg.beta2)
         for v in sd.values():
             if v.dtype.is_floating_point:
                 v.requires_grad_(False)
@@ -667,7 +685,7 @@ def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.
         more = torch.cat([gather_patches(fake_T.detach(), fox, foy, csf),
                           gather_patches(real_S, fox, foy, csf),
                           gather_patches(fake_I.detach(), fox, foy, csf),
-                          torch.ones(NF, 1, 32, 32)], 1)
+                          torch.ones(NF, 1, 32, 32, device=real_S.device)], 1)
         l_m2 = gan_loss(multiscale_d_forward(sdD2, more, cfg.num_D, cfg.n_layers_D), False).mean() * cfg.lambda_G2_GAN
         losses["D_more_fake_T"] = l_m2.item()
     real_in = torch.cat([real_T, S_p, areal_p], 1)
@@ -768,10 +786,91 @@ def synthetic_batch(S, NT=64, seed=0, ellipse_mask=False):
     }
 
 
-def step_inputs_from_batch(b):
-    """What train_step() reads, from the set_input-style dict."""
+def step_inputs_from_batch(b, device=None):
+    """What train_step() reads, from the set_input-style dict (`device`: move the tensors there, e.g. 'cuda' for the
+    eager-PyTorch-on-B200 baseline arm of bench.py)."""
     NT = b["T_images"].shape[1]
-    return dict(real_S=b["S"], real_I=b["I"], M=b["M"],
-                T_images=b["T_images"].reshape(NT, 2, 32, 32).float(),
-                I_masks=b["I_masks"].reshape(NT, 1, 32, 32).float(),
-                T_coords=b["T_coords"].numpy())
+    d = dict(real_S=b["S"], real_I=b["I"], M=b["M"],
+             T_images=b["T_images"].reshape(NT, 2, 32, 32).float(),
+             I_masks=b["I_masks"].reshape(NT, 1, 32, 32).float())
+    if b.get("style_code") is not None:
+        d["style_code"] = torch.as_tensor(b["style_code"]).float()
+    if device is not None:
+        d = {k: v.to(device) for k, v in d.items()}
+    d["T_coords"] = b["T_coords"].numpy()
+    return d
+
+
+# --------------------------------------------------------------------------- stand-alone initial weights
+def _xavier(shape, gen, gain=0.02):
+    """init.xavier_normal_(w, gain) for a conv / linear weight (models/networks.py:204-222: gain 0.02, bias 0)."""
+    rf = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+    std = gain * math.sqrt(2.0 / float(shape[1] * rf + shape[0] * rf))
+    return torch.randn(*shape, generator=gen) * std
+
+
+def init_resnet_g(input_nc=9, output_nc=5, ngf=64, n_blocks=9, seed=0):
+    """A state_dict with the keys / shapes of define_G(..., 'resnet_9blocks', norm='instance') (models/networks.py:1057-1129;
+    index map SURVEY.md A.2), initialised like init_weights('xavier', 0.02).  Lets bench.py's reference arm build its weights
+    without importing the product package; tests/test_oracle_golden.py checks keys and shapes against the reference golden."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, co, ci, k):
+        sd[name + ".weight"] = _xavier((co, ci, k, k), g)
+        sd[name + ".bias"] = torch.zeros(co)
+
+    def filt(name, c, taps, up):
+        a = torch.tensor(taps)
+        f = a[:, None] * a[None, :]
+        f = f / f.sum() * (4.0 if up else 1.0)
+        sd[name + ".filt"] = f[None, None].repeat(c, 1, 1, 1)
+
+    conv("model.1", ngf, input_nc, 7)
+    conv("model.4", ngf * 2, ngf, 3)
+    filt("model.7", ngf * 2, [1.0, 2.0, 1.0], False)
+    conv("model.8", ngf * 4, ngf * 2, 3)
+    filt("model.11", ngf * 4, [1.0, 2.0, 1.0], False)
+    for b in range(n_blocks):
+        conv("model.%d.conv_block.1" % (12 + b), ngf * 4, ngf * 4, 3)
+        conv("model.%d.conv_block.5" % (12 + b), ngf * 4, ngf * 4, 3)
+    m = 12 + n_blocks
+    filt("model.%d" % m, ngf * 4, [1.0, 3.0, 3.0, 1.0], True)
+    conv("model.%d" % (m + 1), ngf * 2, ngf * 4, 3)
+    filt("model.%d" % (m + 4), ngf * 2, [1.0, 3.0, 3.0, 1.0], True)
+    conv("model.%d" % (m + 5), ngf, ngf * 2, 3)
+    conv("model.%d" % (m + 9), output_nc, ngf, 7)
+    return sd
+
+
+def init_multiscale_d(input_nc, ndf=64, n_layers=3, num_D=3, seed=0):
+    """State_dict of define_D(..., 'multiscale', norm='batch') (models/networks.py:1649-1750; index map SURVEY.md A.5):
+    conv weights xavier(0.02), biases 0, BatchNorm weight ~ N(1, 0.02), bias 0 (:223-226), fresh running statistics."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for d in range(num_D):
+        pre = "layer%d." % d
+
+        def conv(i, co, ci):
+            sd["%s%d.weight" % (pre, i)] = _xavier((co, ci, 4, 4), g)
+            sd["%s%d.bias" % (pre, i)] = torch.zeros(co)
+
+        def bn(i, c):
+            sd["%s%d.weight" % (pre, i)] = 1.0 + 0.02 * torch.randn(c, generator=g)
+            sd["%s%d.bias" % (pre, i)] = torch.zeros(c)
+            sd["%s%d.running_mean" % (pre, i)] = torch.zeros(c)
+            sd["%s%d.running_var" % (pre, i)] = torch.ones(c)
+            sd["%s%d.num_batches_tracked" % (pre, i)] = torch.tensor(0, dtype=torch.long)
+
+        conv(0, ndf, input_nc)
+        nf, i = ndf, 2
+        for _ in range(1, n_layers):
+            nf_prev, nf = nf, min(nf * 2, 512)
+            conv(i, nf, nf_prev)
+            bn(i + 1, nf)
+            i += 3
+        nf_prev, nf = nf, min(nf * 2, 512)
+        conv(i, nf, nf_prev)
+        bn(i + 1, nf)
+        conv(i + 3, 1, nf)
+    return sd

@@ -115,7 +115,7 @@ def test_train_step_512_graph_equals_eager_and_moves_by_lr(V):
         m.set_input(batch)
         m.optimize_parameters(1, rand=rand)
         torch.cuda.synchronize()
-        return m.get_current_losses(), [n.flat_param.clone() for n in nets]
+        return m.current_losses(), [n.flat_param.clone() for n in nets]
 
     lg, pg = run()                                # step 2: captured + replayed
     assert m._graph is not None

@@ -1,5 +1,6 @@
 """Pin the oracle (oracle/skit_oracle.py) against fixtures generated from the REAL reference
 code by oracle/make_golden.py (the reference ships no golden vectors)."""
+import math
 import os
 import random
 
@@ -256,3 +257,21 @@ def test_train_step_lpips_wiring_matches_reference(golden_dir):
     # the perceptual terms moved the generator's gradient (they are not a no-op in this fixture)
     k = "model.30.weight"
     assert np.linalg.norm(z["G_grad." + k] - z0["G_grad." + k]) > 1e-3 * np.linalg.norm(z0["G_grad." + k])
+
+
+def test_standalone_init_tables_match_reference_keys_and_shapes(golden_dir):
+    """O.init_resnet_g / O.init_multiscale_d (the weights bench.py's reference arm starts from, built without the product
+    package) carry exactly the reference networks' state_dict keys, shapes and blur buffers, and its xavier(0.02) statistics."""
+    g = np.load(os.path.join(golden_dir, "networks.npz"))
+    for prefix, sd in (("Gres.", O.init_resnet_g(9, 5, 8, 9, seed=3)), ("D_before.", O.init_multiscale_d(7, 8, 3, 3, seed=3))):
+        ref = {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)}
+        assert set(sd) == set(ref), prefix
+        for k, v in sd.items():
+            assert tuple(v.shape) == ref[k].shape, (prefix, k)
+            if k.endswith(".filt"):
+                np.testing.assert_allclose(v.numpy(), ref[k], rtol=1e-6)
+    sd = O.init_resnet_g(9, 5, 64, 9, seed=0)
+    w = sd["model.12.conv_block.1.weight"]
+    assert abs(float(w.std()) - 0.02 * math.sqrt(2.0 / (2 * 256 * 9))) < 2e-6 and float(sd["model.12.conv_block.1.bias"].abs().max()) == 0.0
+    y = O.resnet_g_forward(sd, torch.rand(1, 9, 32, 32) * 2 - 1)
+    assert y.shape == (1, 5, 32, 32) and torch.isfinite(y).all()

@@ -65,7 +65,7 @@ def test_train_step_matches_reference_golden(golden_dir, tag, netG, wkey):
     rand = dict(real_b=u[0], real_s=u[1], fake_b=u[2], fake_s=u[3], fake_ox=z["fake_ox"], fake_oy=z["fake_oy"])
     m.optimize_parameters(1, rand=rand)
     torch.cuda.synchronize()
-    losses = m.get_current_losses()
+    losses = m.current_losses()
     for k, v in losses.items():
         ref = float(z["loss_l_" + k])
         assert abs(v - ref) <= GATE * max(1.0, abs(ref)), (k, v, ref)
@@ -116,7 +116,7 @@ def test_train_step_ngf64_tcgen05_vs_oracle():
     cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF)
     sdG, sdD, sdD2 = [copy.deepcopy(s) for s in sds]
     res = O.train_step(cfg, sdG, sdD, sdD2, {}, O.step_inputs_from_batch(batch), rand, step=1)
-    losses = m.get_current_losses()
+    losses = m.current_losses()
     for k, v in res["losses"].items():
         assert abs(losses[k] - v) <= GATE * max(1.0, abs(v)), (k, losses[k], v)
     for nm in ("fake_I", "fake_T", "fake_N", "aug_fake_I"):
@@ -160,7 +160,7 @@ def test_cuda_graph_replay_matches_eager_step():
         m.set_input(batch)
         m.optimize_parameters(1, rand=rands[2])
         torch.cuda.synchronize()
-        return m.get_current_losses(), m.fake_I.clone(), m.fake_T.clone(), [n.flat_param.clone() for n in nets]
+        return m.current_losses(), m.fake_I.clone(), m.fake_T.clone(), [n.flat_param.clone() for n in nets]
 
     snap = snapshot()
     res_g = run()                      # captures, then replays once
@@ -205,7 +205,7 @@ def test_train_step_with_patchnce_vs_oracle():
     cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_NCE=1.0, num_patches=P)
     sdG, sdD, sdD2 = [copy.deepcopy(s) for s in sds]
     res = O.train_step(cfg, sdG, sdD, sdD2, {}, O.step_inputs_from_batch(batch), rand, step=1)
-    losses = m.get_current_losses()
+    losses = m.current_losses()
     assert "NCE" in losses and "NCE" in res["losses"]
     for k, v in res["losses"].items():
         assert abs(losses[k] - v) <= GATE * max(1.0, abs(v)), (k, losses[k], v)
@@ -240,7 +240,7 @@ def test_train_step_with_lpips_vs_oracle():
     cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_G1_lpips=1.0, lambda_G2_lpips=10.0)
     sdG, sdD, sdD2 = [copy.deepcopy(s) for s in sds]
     res = O.train_step(cfg, sdG, sdD, sdD2, {}, O.step_inputs_from_batch(batch), rand, step=1, sdL=sdL)
-    losses = m.get_current_losses()
+    losses = m.current_losses()
     assert "G_lpips" in losses and "G2_lpips" in losses and losses["G_lpips"] > 0 and losses["G2_lpips"] > 0
     for k, v in res["losses"].items():
         assert abs(losses[k] - v) <= GATE * max(1.0, abs(v)), (k, losses[k], v)
@@ -254,7 +254,7 @@ def test_train_step_with_lpips_vs_oracle():
     for _ in range(4):
         m.set_input(batch)
         m.optimize_parameters(1)
-    l2 = m.get_current_losses()
+    l2 = m.current_losses()
     assert np.isfinite(l2["G_lpips"]) and np.isfinite(l2["G2_lpips"]) and l2["G_lpips"] > 0
 
 
@@ -286,7 +286,7 @@ def test_train_step_with_patchnce_mlp_vs_oracle():
     cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_NCE=1.0, num_patches=P, nce_layers=(0, 4, 12))
     sdG, sdD, sdD2, sdF = [copy.deepcopy(s) for s in sds]
     res = O.train_step(cfg, sdG, sdD, sdD2, {}, O.step_inputs_from_batch(batch), rand, step=1, sdF=sdF)
-    losses = m.get_current_losses()
+    losses = m.current_losses()
     for k, v in res["losses"].items():
         assert abs(losses[k] - v) <= GATE * max(1.0, abs(v)), (k, losses[k], v)
     print("G worst grad rel err", check_grads(m.netG, {k: v.numpy() for k, v in res["grads_G"].items()}, "G"))

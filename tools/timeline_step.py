@@ -14,8 +14,10 @@ size = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 arch = sys.argv[2] if len(sys.argv) > 2 else "B"
 if arch == "B":
     opt = vts_b200.default_options()
+elif arch == "N":      # arch B + PatchNCE (BASELINE.json configs[2] when size = 768)
+    opt = vts_b200.default_options(lambda_NCE=1.0)
 elif arch == "L":      # arch B + the reference's default LPIPS terms
-    opt = vts_b200.default_options(lambda_G1_lpips=1.0, lambda_G2_lpips=10.0)
+    opt = vts_b200.default_options(lambda_G1_lpips=1.0, lambda_G2_lpips=10.0, allow_random_lpips=True)
 else:
     opt = vts_b200.default_options(netG="unet256_custom", ngf=10, ndf=8)
 torch.manual_seed(0)
@@ -80,5 +82,5 @@ agg = collections.Counter()
 for s, e, name, _ in ks:
     agg[name[:60]] += e - s
 print("kernel time by name:")
-for name, v in agg.most_common(14):
+for name, v in agg.most_common(30):
     print("   %8.1f us  %s" % (v, name))

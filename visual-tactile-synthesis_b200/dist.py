@@ -12,6 +12,11 @@ import torch
 import torch.distributed as dist
 
 
+def launched_by_torchrun():
+    """True when the process was started by torchrun / torch.distributed.run with more than one rank."""
+    return int(os.environ.get("WORLD_SIZE", "1")) > 1 and "RANK" in os.environ
+
+
 class DistContext:
     def __init__(self, backend=None):
         self.world_size = int(os.environ.get("WORLD_SIZE", "1"))

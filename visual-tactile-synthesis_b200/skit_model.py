@@ -6,9 +6,16 @@ compute_D1_loss :1346-1407, compute_D2_loss :1409-1617, compute_G1_loss :1660-17
 compute_G2_loss :1728-1842, set_input :702-793, optimizers :590-599;  models/skitG_model.py
 (:1284-1336 forward, style code / M_T) is the multi-material twin whose own optimize_parameters is
 broken as shipped — SKITGModel here reuses the sinskitG step.
-LPIPS / vision-aided (CLIP) terms are third-party networks outside the hot path:
-their lambdas must be 0 / False, anything else raises.
+The LPIPS-VGG16 terms run on the library's own kernels (lpips_vgg.py) and need the package's checkpoint passed as
+`opt.lpips_state` (no pretrained weights exist offline: random weights only behind `opt.allow_random_lpips`); the
+vision-aided (CLIP) discriminator and the CLIP style encoder are third-party networks outside the hot path
+(SURVEY.md §8f): `use_vision_aided_loss=True` raises, the style code is taken precomputed or from a user-supplied encoder.
+The BaseModel contract train.py / test.py drive (models/base_model.py:71-230: setup, parallelize, train / eval,
+get_current_visuals / losses / metrics, get_image_paths, update_learning_rate, save / load_networks) is mirrored below;
+`integration/b200sinskitG_model.py` is the adapter the reference's `models/__init__.py:54-67` discovers.
 """
+import collections
+import warnings
 import argparse
 import math
 import os
@@ -32,7 +39,8 @@ def default_options(**kw):
         model="sinskitG", isTrain=True, gpu_ids=[0],
         netG="resnet_9blocks", ngf=64, normG="instance", no_dropout=True, no_antialias=False, no_antialias_up=False,
         netD="multiscale", netD2="multiscale", ndf=64, normD="batch", n_layers_D=3, num_D=3,
-        init_type="xavier", init_gain=0.02, input_nc=1, output_nc=5,
+        init_type="xavier", init_gain=0.02, input_nc=1, output_nc=5, sketch_nc=1, image_nc=3, touch_nc=2,
+        num_D_D1=3, num_D_D2=3, n_layers_D2=3, use_cGAN=True, use_cGAN_G2_S=True, use_cGAN_G2_I=True,
         use_positional_encoding=True, use_bg_mask=True, use_diffaug=True, diffaugment="bs", use_more_fakeT=True,
         gan_mode="nonsaturating",
         lambda_G1_GAN=1.0, lambda_G1_L1=100.0, lambda_G1_lpips=0.0, lambda_G2_GAN=5.0, lambda_G2_L1=10.0,
@@ -48,6 +56,10 @@ def default_options(**kw):
         nce_includes_all_negatives_from_minibatch=False,
         cuda_graph=True,         # replay the whole train step as one CUDA graph once shapes are stable
         cuda_graph_warmup=2,     # eager steps before capture (lazy weight packs, kernel attributes, NCCL warm-up)
+        lpips_state=None,        # state_dict of lpips.LPIPS(net='vgg') (the package's own checkpoint keys)
+        allow_random_lpips=False,  # benchmarks / parity tests only: run the LPIPS terms on randomly initialised VGG16 weights
+        continue_train=False, epoch="latest", verbose=False, pretrained_name=None, train_for_each_epoch=True,
+        positional_encoding_mode="spe", positional_encoding_dim=4,
     )
     o.update(kw)
     return argparse.Namespace(**o)
@@ -61,20 +73,56 @@ def reference_default_options(**kw):
     return default_options(**o)
 
 
+def _opt(opt, name, default):
+    """Options the reference's parsers do not define (B200-path extras) fall back to their default_options() value."""
+    return getattr(opt, name, default)
+
+
 class SinSKITGModel:
     loss_names = ["D_fake_I", "D_real_I", "D_fake_T_concat", "D_more_fake_T", "D_real_T_concat",
                   "G_GAN", "G_L1", "G2_GAN", "G2_L1"]
     model_names = ["G", "D", "D2"]
+    model_name = "sinskitG"
+
+    @staticmethod
+    def modify_commandline_options(parser, is_train=True):
+        """The B200-path extras on top of the reference model's own options (models/sinskitG_model.py:34-357; the adapter in
+        integration/ chains the reference's setter first).  Existing arguments are left alone."""
+        have = {a.dest for a in parser._actions}
+
+        def add(name, **kw):
+            if name.lstrip("-") not in have:
+                parser.add_argument(name, **kw)
+
+        b = lambda v: str(v).lower() in ("1", "true", "yes")   # noqa: E731
+        add("--cuda_graph", type=b, default=True, help="replay the train step / test forward as one CUDA graph")
+        add("--cuda_graph_warmup", type=int, default=2, help="eager steps before the graph capture")
+        add("--run_full_res_D2", type=b, default=False, help="also run the reference's visualisation-only netD2(full image) pass")
+        add("--lambda_NCE", type=float, default=0.0, help="weight of the CUT-style PatchNCE term (0 = off, the reference's behaviour)")
+        add("--nce_layers", type=str, default="0,4,8,12,16")
+        add("--num_patches", type=int, default=256)
+        add("--nce_T", type=float, default=0.07)
+        add("--netF", type=str, default="sample")
+        add("--netF_nc", type=int, default=256)
+        add("--nce_includes_all_negatives_from_minibatch", type=b, default=False)
+        add("--allow_random_lpips", type=b, default=False)
+        return parser
 
     def __init__(self, opt, dist_ctx=None):
         self.opt = opt
         self.isTrain = opt.isTrain
+        self.gpu_ids = opt.gpu_ids
         self.dist = dist_ctx
         if not torch.cuda.is_available():
             raise RuntimeError("SinSKITGModel (B200 path) needs a CUDA device; there is no CPU fallback")
         dev_index = opt.gpu_ids[0] if len(opt.gpu_ids) else 0
         self.device = torch.device("cuda", dev_index)
         torch.cuda.set_device(self.device)
+        self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
+        self.image_paths = []
+        self.optimizers, self.schedulers = [], []     # Adam lives in the fused kernel; kept for the BaseModel attribute contract
+        self.metric = 0
+        self.metric_names = []
         if opt.use_vision_aided_loss:
             raise NotImplementedError("the vision-aided discriminator (CLIP / DINO backbones) is a third-party network outside the "
                                       "B200 hot path; run with --use_vision_aided_loss False")
@@ -82,21 +130,35 @@ class SinSKITGModel:
             raise NotImplementedError("T_resolution_multiplier != 1 (real bicubic resampling) is not built")
         if opt.batch_size != 1:
             raise NotImplementedError("batch_size is forced to 1 by the reference (sinskitG_model.py:342)")
-        g_in = opt.input_nc + (8 if opt.use_positional_encoding else 0)
+        if _opt(opt, "use_diffaug", False) and _opt(opt, "diffaugment", "bs") != "bs":
+            raise NotImplementedError("DiffAugment policy %r: only 'bs' (brightness + saturation, the model default, "
+                                      "sinskitG_model.py:226-231) is built on the B200 path" % opt.diffaugment)
+        if _opt(opt, "use_positional_encoding", False) and _opt(opt, "positional_encoding_mode", "spe") != "spe":
+            raise NotImplementedError("positional_encoding_mode %r: only 'spe' is built" % opt.positional_encoding_mode)
+        # channel counts / discriminator depth under the reference parser's names (sketch_nc, image_nc, touch_nc, num_D_D1,
+        # num_D_D2, n_layers_D2: sinskitG_model.py:137-200,505-573), falling back to default_options()'s older spellings
+        s_nc = self.sketch_nc = _opt(opt, "sketch_nc", _opt(opt, "input_nc", 1))
+        out_nc = _opt(opt, "image_nc", 3) + _opt(opt, "touch_nc", 2) if hasattr(opt, "image_nc") else _opt(opt, "output_nc", 5)
+        if (s_nc, out_nc) != (1, 5):
+            raise NotImplementedError("the explicit step is built for sketch_nc 1, image_nc 3, touch_nc 2 (the model defaults)")
+        if not (_opt(opt, "use_cGAN", True) and _opt(opt, "use_cGAN_G2_S", True) and _opt(opt, "use_cGAN_G2_I", True)):
+            raise NotImplementedError("the explicit step is built for the conditional discriminators (use_cGAN / use_cGAN_G2_S / "
+                                      "use_cGAN_G2_I = True, the model defaults)")
+        g_in = s_nc + (2 * _opt(opt, "positional_encoding_dim", 4) if opt.use_positional_encoding else 0)
         gpu = [dev_index]
         if "stylegan2" in opt.netG:
-            raise NotImplementedError("netG=%r: the StyleGAN2 generator is built forward-only on the B200 path "
-                                      "(networks.define_G(...)(x)); its 3-channel output does not feed the 5-channel skitG "
-                                      "step (stylegan_networks.py:892) and it has no explicit backward yet" % opt.netG)
-        self.netG = networks.define_G(g_in, opt.output_nc, opt.ngf, opt.netG, opt.normG, not opt.no_dropout, opt.init_type,
+            raise NotImplementedError("netG=%r: the StyleGAN2 generator (forward + explicit backward, sg2_generator.py) is available "
+                                      "through networks.define_G, but its decoder is hard-wired to 3 output channels "
+                                      "(stylegan_networks.py:892), which does not feed the 5-channel skitG step" % opt.netG)
+        self.netG = networks.define_G(g_in, out_nc, opt.ngf, opt.netG, opt.normG, not opt.no_dropout, opt.init_type,
                                       opt.init_gain, opt.no_antialias, opt.no_antialias_up, gpu, opt,
                                       num_layer_separate=getattr(opt, "num_layer_separate", 4))
         self.netG.flatten_parameters()
         if self.isTrain:
-            self.netD = networks.define_D(opt.input_nc + 3, opt.ndf, opt.netD, opt.n_layers_D, opt.normD, opt.init_type,
-                                          opt.init_gain, opt.no_antialias, opt.num_D, gpu, opt)
-            self.netD2 = networks.define_D(2 + opt.input_nc + 3 + 1, opt.ndf, opt.netD2, opt.n_layers_D, opt.normD,
-                                           opt.init_type, opt.init_gain, opt.no_antialias, opt.num_D, gpu, opt)
+            self.netD = networks.define_D(s_nc + 3, opt.ndf, opt.netD, opt.n_layers_D, opt.normD, opt.init_type,
+                                          opt.init_gain, opt.no_antialias, _opt(opt, "num_D_D1", _opt(opt, "num_D", 3)), gpu, opt)
+            self.netD2 = networks.define_D(2 + s_nc + 3 + 1, opt.ndf, opt.netD2, _opt(opt, "n_layers_D2", opt.n_layers_D), opt.normD,
+                                           opt.init_type, opt.init_gain, opt.no_antialias, _opt(opt, "num_D_D2", _opt(opt, "num_D", 3)), gpu, opt)
             for net in (self.netD, self.netD2):
                 if not isinstance(net, networks.MultiscaleDiscriminator):
                     raise NotImplementedError("the explicit train step is built for netD/netD2 = 'multiscale' (the model default)")
@@ -108,11 +170,19 @@ class SinSKITGModel:
                 # criterionLPIPS_vgg (sinskitG_model.py:495).  The pretrained VGG16 / lin checkpoints are not available offline:
                 # random weights unless `opt.lpips_state` (a state_dict with the lpips package's keys) is given.
                 from .lpips_vgg import LPIPS
+                state = _opt(opt, "lpips_state", None)
+                if state is None and not _opt(opt, "allow_random_lpips", False):
+                    raise ValueError("lambda_G1_lpips / lambda_G2_lpips > 0 need the lpips package's VGG16 checkpoint as opt.lpips_state "
+                                     "(lpips.LPIPS(net='vgg').state_dict()); without it the perceptual terms would optimise a randomly "
+                                     "initialised network.  Benchmarks may pass allow_random_lpips=True.")
                 self.lpips = LPIPS(net="vgg").to(self.device)
-                if getattr(opt, "lpips_state", None) is not None:
-                    self.lpips.load_state_dict(opt.lpips_state, strict=False)
+                if state is not None:
+                    res = self.lpips.load_state_dict(state, strict=False)
+                    if res.missing_keys:
+                        raise RuntimeError("opt.lpips_state does not cover the LPIPS-VGG16 parameters; missing keys: %s"
+                                           % ", ".join(res.missing_keys[:8]))
                 self.lpips.refresh_packs_once()
-            self.nce_layers = [int(i) for i in str(opt.nce_layers).split(",")] if getattr(opt, "lambda_NCE", 0.0) > 0 else []
+            self.nce_layers = [int(i) for i in str(_opt(opt, "nce_layers", "0,4,8,12,16")).split(",")] if _opt(opt, "lambda_NCE", 0.0) > 0 else []
             if self.nce_layers:
                 if not isinstance(self.netG, networks.ResnetGenerator):
                     raise NotImplementedError("PatchNCE needs a generator with feature taps (forward(layers=..., encode_only=True)): the resnet family "
@@ -141,26 +211,40 @@ class SinSKITGModel:
             self._spe_cache[key] = spe_grid(h, w, 4, n).to(self.device)
         return self._spe_cache[key]
 
-    def set_input(self, input, phase="train"):
+    def set_input(self, input, phase="train", timing=False, verbose=False):
         """Host tensors (the dataset dict, sinskitG_model.py:702-793) -> persistent device buffers: one pinned H2D copy
-        per tensor, then the masking of S / I / T (:724,734,789-790) as in-place device kernels."""
+        per tensor, then the masking of S / I / T (:724,734,789-790) as in-place device kernels.  `timing` / `verbose` are the
+        reference's logging switches (accepted, nothing to print)."""
         dev = self.device
-        M = input["M"].float()
+        opt = self.opt
+        self.data_phase = phase
         n, _, h, w = input["S"].shape
+        # without use_bg_mask the reference skips every mask multiply (:721-726,1317-1319,1339-1341): an all-ones mask is the same
+        M = input["M"].float() if opt.use_bg_mask else torch.ones(n, 1, h, w)
         host = {"M": M, "real_S": input["S"].float()}
         if "I" in input:
             host["real_I"] = input["I"].float()
         pre = "" if phase == "train" else "val_"
-        has_T = self.isTrain and (pre + "T_images") in input
+        has_T = self.isTrain and (pre + "T_images") in input and len(input[pre + "T_images"]) > 0
         if has_T:
             T = input[pre + "T_images"].float()
             NT = T.shape[1]
+            if tuple(T.shape[-2:]) != (32, 32) or T.shape[2] != 2:
+                raise NotImplementedError("touch patches must be [N, NT, 2, 32, 32] (patch_crop_size 32, T_resolution_multiplier 1); got %s"
+                                          % (tuple(T.shape),))
             host["I_masks"] = input[pre + "I_masks"].float().reshape(NT, 1, 32, 32)
             host["real_T"] = T.reshape(NT, 2, 32, 32)
-            ox, oy, _ = find_coords_for_patch(input[pre + "T_coords"].numpy() if torch.is_tensor(input[pre + "T_coords"]) else input[pre + "T_coords"])
+            ox, oy, cs = find_coords_for_patch(input[pre + "T_coords"].numpy() if torch.is_tensor(input[pre + "T_coords"]) else input[pre + "T_coords"])
+            if np.any(np.asarray(cs) != 32 * opt.T_resolution_multiplier):
+                # the reference then cuts a smaller / larger window and resizes it (model_utils.py:337-341): not built
+                raise NotImplementedError("patch cutout size %s != patch size 32 (resize_ratio != 1): the resampling gather of "
+                                          "get_patch_in_input is not built on the B200 path" % sorted(set(np.asarray(cs).tolist())))
             host["ox"] = torch.from_numpy(ox.astype(np.int32))
             host["oy"] = torch.from_numpy(oy.astype(np.int32))
             self.NT = NT
+        sc = self._style_code_from(input) if _opt(opt, "use_style_code", False) else None
+        if sc is not None:
+            host["style_code"] = sc
         self.h2d_bytes = 0
         for k, v in host.items():
             v = v.contiguous()
@@ -168,17 +252,19 @@ class SinSKITGModel:
                 v = v.pin_memory()
             self.h2d_bytes += v.numel() * v.element_size()
             self._stage(k, v)
+        if sc is None:
+            self.style_code = None
+        self.M_T = self.M      # mask of the touch output: F.interpolate(M, size * T_resolution_multiplier) with multiplier 1 (:725)
         # background / contact masking on the device (the reference does it after its own .to(device): :724,734,789-790)
-        if self.opt.use_bg_mask:
+        if opt.use_bg_mask:
             ops.mask_mul_(self.real_S, self.M)
             if "I" in input:
                 ops.mask_mul_(self.real_I, self.M)
         if has_T:
             ops.mask_mul_(self.real_T, self.I_masks)
-        self.S_pe = self._spe(n, h, w) if self.opt.use_positional_encoding else None
-        self.style_code = input.get("style_code")
-        if self.isTrain and hasattr(self, "real_T"):
-            NT, NF = self.NT, self.opt.add_fake_T_sample_size
+        self.S_pe = self._spe(n, h, w) if opt.use_positional_encoding else None
+        if self.isTrain and has_T:
+            NT, NF = self.NT, opt.add_fake_T_sample_size
             if getattr(self, "fake_in", None) is None or self.fake_in.shape[0] != NT or self.more_in.shape[0] != NF:
                 self.fake_in = torch.zeros(NT, 7, 32, 32, device=dev)
                 self.real_in = torch.zeros(NT, 7, 32, 32, device=dev)
@@ -187,8 +273,32 @@ class SinSKITGModel:
             self.fake_in[:, 6:7] = self.I_masks
             self.real_in[:, 6:7] = self.I_masks
             self.real_in[:, 0:2] = self.real_T
-            self._offset_table = random_patch_offset_table(M) if self.opt.use_more_fakeT else None
-        self.image_paths = input.get("S_paths")
+            self._offset_table = random_patch_offset_table(M) if opt.use_more_fakeT else None
+        self.name = input.get("name")
+        self.image_paths = input.get("S_paths", [])
+        self.augmentation_params = input.get("augmentation_params")
+        self.full_T_coords = input.get("full_T_coords")
+
+    def _style_code_from(self, input):
+        """The generator's style code as a host fp32 [N, style_code_dim] tensor.  The reference computes it in forward() with CLIP
+        ViT-B/32 in fp16 (skitG_model.py:483-489,705-724,1294-1298) and torch.cat promotes it to fp32 inside the U-Net; CLIP is a
+        third-party network that is absent here, so the code is taken precomputed (`input['style_code']`) or from a
+        user-supplied encoder (`self.style_encoder(style_I or real_I) -> [N, dim]`)."""
+        if input.get("style_code") is not None:
+            sc = input["style_code"]
+        elif getattr(self, "style_encoder", None) is not None:
+            img = input.get("style_I", input.get("I"))
+            if img is not None and "style_M" in input and self.opt.use_bg_mask:
+                img = img * input["style_M"]
+            with torch.no_grad():
+                sc = self.style_encoder(img)
+        else:
+            raise RuntimeError("use_style_code is on but the batch carries no 'style_code' and the model has no style_encoder "
+                               "(the reference's CLIP ViT-B/32 image encoder is a third-party network outside the B200 path)")
+        sc = torch.as_tensor(sc).detach().to("cpu", torch.float32)
+        if sc.dim() != 2 or sc.shape[1] != _opt(self.opt, "style_code_dim", 512):
+            raise ValueError("style_code must be [N, %d], got %s" % (_opt(self.opt, "style_code_dim", 512), tuple(sc.shape)))
+        return sc
 
     def _stage(self, name, host_t):
         """Host tensor -> a persistent device buffer of the same name (same address every step, so the
@@ -294,8 +404,8 @@ class SinSKITGModel:
                 self.aug_real_I, self.aug_fake_I = self.real_I, self.fake_I
         return self.fake_I, self.fake_T, self.fake_N
 
-    def test(self):
-        """sinskitG_model.py:795-807: forward without saving anything for backward.  With opt.cuda_graph the forward is
+    def test(self, timing=False):
+        """sinskitG_model.py:795-807: forward without saving anything for backward (`timing`: the reference's print switch).  With opt.cuda_graph the forward is
         captured once per input shape and replayed (inputs live in the persistent buffers set_input fills)."""
         self.netG.ensure_flat()
         key = (self._input_gen, tuple(self.real_S.shape), self.netG.flat_param.data_ptr())
@@ -307,7 +417,7 @@ class SinSKITGModel:
         self._tgraph = None
         self.netG.refresh_packs()
         self._test_calls = getattr(self, "_test_calls", 0) + 1
-        if getattr(self.opt, "cuda_graph", False) and self._test_calls > 1:
+        if _opt(self.opt, "cuda_graph", True) and self._test_calls > 1:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             before = dict(self.__dict__)
@@ -368,7 +478,7 @@ class SinSKITGModel:
             self.__dict__.update(self._graph_attrs)
             return self._loss_raw[0]
         self._graph = None
-        if opt.cuda_graph and self.step_count > opt.cuda_graph_warmup:
+        if _opt(opt, "cuda_graph", True) and self.step_count > _opt(opt, "cuda_graph_warmup", 2):
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             before = dict(self.__dict__)
@@ -402,6 +512,7 @@ class SinSKITGModel:
         atomically into the net's flat bucket, so passes on parallel streams may overlap)."""
         preds, ctx = net.fwd(srcs, deferred=deferred)
         net.bwd(ctx, self._gan(preds, sign, slot, gscale))
+        return preds
 
     def _step_body(self):
         if getattr(self, "_arena", None) is None:
@@ -476,14 +587,14 @@ class SinSKITGModel:
         with self._fork(2):
             run_D2["fake"] = []
             self._d_pass(D2, [self.fake_in], +1.0, sl["D2_fake"], 0.5 * opt.lambda_G2_GAN / NT, run_D2["fake"])
-            if opt.run_full_res_D2:  # visualisation only in the reference (:1495-1500); updates BN running stats
+            if _opt(opt, "run_full_res_D2", False):  # visualisation only in the reference (:1495-1500); updates BN running stats
                 self.pred_fake_T_full = D2.fwd([fake_T, self.real_S, self.aug_fake_I, self.M], save=False, deferred=run_D2["fake"])[0][-1]
         if more:
             with self._fork(3):
                 run_D2["more"] = []
                 self._d_pass(D2, [self.more_in], +1.0, sl["D2_more"], 0.5 * opt.lambda_G2_GAN / NF, run_D2["more"])
         run_D["fake"] = []
-        self._d_pass(D, [self.real_S, fake_I], +1.0, sl["D_fake"], 0.5 * opt.lambda_G1_GAN / n, run_D["fake"])
+        self.pred_fake_I = self._d_pass(D, [self.real_S, fake_I], +1.0, sl["D_fake"], 0.5 * opt.lambda_G1_GAN / n, run_D["fake"])[-1]
 
         # ---- D1 update (:648-653)
         self._join(0)
@@ -510,7 +621,7 @@ class SinSKITGModel:
         G.zero_grad()
         pg, cg = D.fwd([self.real_S, fake_I])
         dpg = self._gan(pg, -1.0, sl["G_GAN"], opt.lambda_G1_GAN / n)
-        dI = D.bwd(cg, dpg, need_wgrad=False, input_slice=(opt.input_nc, 3))
+        dI = D.bwd(cg, dpg, need_wgrad=False, input_slice=(self.sketch_nc, 3))
         del cg
         ops.l1_loss(fake_I, self.real_I, opt.lambda_G1_L1 / fake_I.numel(), sl["G_L1"], dI, opt.lambda_G1_L1 / fake_I.numel(), accumulate=True)
         per_patch = fake_T_p.numel() // NT
@@ -571,7 +682,7 @@ class SinSKITGModel:
             k_pool, _ = F_.sample_fwd(self._g_feats[l], ids, li)
             q_pool, qctx = F_.sample_fwd(fq[l], ids, li, save=True)
             rows = q_pool.shape[0]
-            b = 1 if opt.nce_includes_all_negatives_from_minibatch else n
+            b = 1 if _opt(opt, "nce_includes_all_negatives_from_minibatch", False) else n
             loss_l, dq = ops.patchnce(q_pool, k_pool, b, opt.nce_T, want_grad=True, gscale=opt.lambda_NCE / (nl * rows))
             dfeats[l] = F_.sample_bwd(qctx, dq)
             chunks.append(loss_l)
@@ -582,8 +693,8 @@ class SinSKITGModel:
         self._nce_losses = chunks
         self._g_feats = None
 
-    def get_current_losses(self):
-        """Device -> host read of the step's loss scalars (the reference does ~12 .item() syncs per step,
+    def current_losses(self):
+        """Device -> host read of the step's loss scalars, bare names (the reference does ~12 .item() syncs per step,
         sinskitG_model.py:1389-1838; here it is one D2H copy, only when somebody asks)."""
         L, NT, NF = self._loss_raw
         v = L.detach().cpu().numpy()
@@ -606,30 +717,133 @@ class SinSKITGModel:
             D_more_fake_T=float(v[8 + 3 * NT:].mean()) * o.lambda_G2_GAN if NF else 0.0,
         )
 
-    def update_learning_rate(self, epoch):
-        """get_scheduler('linear') (networks.py:161-165), stepped once per epoch (train.py:204-205)."""
+    def get_current_losses(self):
+        """BaseModel.get_current_losses (base_model.py:171-183): OrderedDict keyed 'l_' + name, in the reference model's
+        loss_names order (sinskitG_model.py:430-456); the gradient penalties are identically 0 outside gan_mode 'wgangp'."""
+        raw = self.current_losses()
+        order = ["G_GAN", "D_real_I", "D_fake_I", "D_I_grad_penalty", "G_L1", "G_lpips", "G2_GAN", "D_real_T_concat",
+                 "D_fake_T_concat", "D_T_grad_penalty", "D_more_fake_T", "G2_L1", "G2_lpips", "NCE"]
+        raw.setdefault("D_I_grad_penalty", 0.0)
+        raw.setdefault("D_T_grad_penalty", 0.0)
+        return collections.OrderedDict(("l_" + k, raw[k]) for k in order if k in raw)
+
+    # ------------------------------------------------------------------ BaseModel contract (models/base_model.py:71-230)
+    def setup(self, opt=None):
+        """base_model.py:90-102: (re)start the LR schedule, load networks for test / continue_train, print the networks."""
+        opt = self.opt if opt is None else opt
+        self._sched_count = 0
+        self.lr_factor = self._lambda_rule(0) if self.isTrain else 1.0
+        if not self.isTrain or _opt(opt, "continue_train", False):
+            self.load_networks(_opt(opt, "epoch", "latest"))
+        self.print_networks(_opt(opt, "verbose", False))
+
+    def parallelize(self):
+        """base_model.py:104-108 wraps every net in nn.DataParallel.  The B200 path is one process per GPU (torchrun) with a
+        flat-bucket NCCL all-reduce (dist.py), so there is nothing to wrap: with a DistContext the replicas are made
+        identical here instead."""
+        if self.dist is not None:
+            self.dist.broadcast_params([getattr(self, "net" + n) for n in self.model_names if getattr(self, "net" + n, None) is not None
+                                        and getattr(getattr(self, "net" + n), "flat_param", None) is not None])
+
+    def data_dependent_initialize(self, data):
+        pass
+
+    def _nets(self):
+        return [getattr(self, "net" + n) for n in self.model_names if isinstance(n, str) and getattr(self, "net" + n, None) is not None]
+
+    def train(self):
+        for net in self._nets():
+            net.train()
+
+    def eval(self):
+        for net in self._nets():
+            net.eval()
+
+    def compute_visuals(self):
+        """sinskitG_model.py:1320-1324: the two height-gradient channels as separate maps."""
+        if getattr(self, "fake_T", None) is not None:
+            self.fake_gx, self.fake_gy = self.fake_T[:, 0:1], self.fake_T[:, 1:2]
+
+    visual_names = ["real_S", "M", "real_I", "fake_I", "fake_gx", "fake_gy", "fake_N", "pred_fake_I", "pred_fake_T_full",
+                    "aug_fake_I", "aug_real_I"]
+
+    def get_current_visuals(self):
+        """The self-attribute visuals of sinskitG_model.py:811-831 (NCHW device tensors).  The patch collages and the
+        evaluation metrics the reference computes inside this call (compute_additional_visuals / compute_evaluation_metric:
+        SIFID, LPIPS, PSNR/SSIM — SURVEY.md section 8f rank 4) are not part of the hot path and are not produced."""
+        self.compute_visuals()
+        ret = collections.OrderedDict()
+        for name in self.visual_names:
+            v = getattr(self, name, None)
+            if torch.is_tensor(v):
+                ret[name] = v.permute(0, 3, 1, 2) if name.startswith("pred_") else v    # predictions are stored NHWC
+        return ret
+
+    def get_image_paths(self):
+        return self.image_paths
+
+    def get_current_metrics(self):
+        """base_model.py:185-200.  metric_names stays empty: the evaluation metrics are a 'next' row."""
+        return collections.OrderedDict(("m_" + n, float(getattr(self, "metric_" + n))) for n in self.metric_names)
+
+    def generate_visuals_for_evaluation(self, data, mode):
+        return {}
+
+    def print_networks(self, verbose=False):
+        print("---------- Networks initialized -------------")
+        for name, net in zip([n for n in self.model_names if getattr(self, "net" + n, None) is not None], self._nets()):
+            if verbose:
+                print(net)
+            print("[Network %s] Total number of parameters : %.3f M" % (name, sum(p.numel() for p in net.parameters()) / 1e6))
+        print("-----------------------------------------------")
+
+    def set_requires_grad(self, nets, requires_grad=False):
+        """base_model.py:324-335.  The explicit step decides per pass which gradients it computes (need_wgrad / dgrad-only
+        discriminator passes); the flags are still set for callers that inspect them."""
+        for net in nets if isinstance(nets, list) else [nets]:
+            if net is not None:
+                for p in net.parameters():
+                    p.requires_grad = requires_grad
+
+    def _lambda_rule(self, count):
         o = self.opt
-        self.lr_factor = 1.0 - max(0, epoch + o.epoch_count - o.n_epochs) / float(o.n_epochs_decay + 1)
+        if o.lr_policy != "linear":
+            raise NotImplementedError("lr_policy %r: the fused Adam step takes the 'linear' schedule (the model default)" % o.lr_policy)
+        return 1.0 - max(0, count + o.epoch_count - o.n_epochs) / float(o.n_epochs_decay + 1)
+
+    def update_learning_rate(self, epoch=None):
+        """BaseModel.update_learning_rate() (base_model.py:145-158): one LambdaLR step per call, i.e. after k calls the factor is
+        lambda_rule(k) (networks.py:161-165; the scheduler's counter starts at 0 in setup()).  `epoch` is not part of the
+        reference's signature: when given it SETS the counter (resuming), it is not train.py's 1-based epoch."""
+        self._sched_count = getattr(self, "_sched_count", 0) + 1 if epoch is None else int(epoch)
+        self.lr_factor = self._lambda_rule(self._sched_count)
+        print("learning rate = %.7f" % (self.opt.lr * self.lr_factor))
 
     # ------------------------------------------------------------------ checkpoints (base_model.py:205-304)
-    def save_networks(self, tag):
-        d = os.path.join(self.opt.checkpoints_dir, self.opt.name)
-        os.makedirs(d, exist_ok=True)
+    def save_networks(self, epoch):
+        os.makedirs(self.save_dir, exist_ok=True)
         for name in self.model_names:
             net = getattr(self, "net" + name, None)
             if net is not None:
-                torch.save({k: v.detach().cpu().clone() for k, v in net.state_dict().items()},
-                           os.path.join(d, "%s_net_%s.pth" % (tag, name)))
+                torch.save(collections.OrderedDict((k, v.detach().cpu().clone()) for k, v in net.state_dict().items()),
+                           os.path.join(self.save_dir, "%s_net_%s.pth" % (epoch, name)))
 
-    def load_networks(self, tag):
-        d = os.path.join(self.opt.checkpoints_dir, self.opt.name)
+    def load_networks(self, epoch):
+        """base_model.py:247-304: '<epoch>_net_<name>.pth' from save_dir (or checkpoints_dir/pretrained_name when training),
+        'module.' prefixes stripped; a missing file is skipped with a warning like the reference (:264-267), a state_dict
+        that does not fit raises (the reference only prints)."""
+        o = self.opt
+        d = self.save_dir
+        if self.isTrain and _opt(o, "pretrained_name", None) is not None:
+            d = os.path.join(o.checkpoints_dir, o.pretrained_name)
         for name in self.model_names:
             net = getattr(self, "net" + name, None)
-            path = os.path.join(d, "%s_net_%s.pth" % (tag, name))
+            path = os.path.join(d, "%s_net_%s.pth" % (epoch, name))
             if net is None:
                 continue
             if not os.path.exists(path):
-                raise FileNotFoundError(path)  # the reference silently continues (base_model.py:264-267); we fail loudly
+                warnings.warn("cannot find model path %s, skip" % path)
+                continue
             sd = torch.load(path, map_location="cpu")
             sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
             net.load_state_dict(sd)
@@ -637,7 +851,18 @@ class SinSKITGModel:
 
 
 class SKITGModel(SinSKITGModel):
-    """skitG: multi-material twin (models/skitG_model.py).  Adds a CLIP style code that only the U-Net
-    generators consume (networks.py:1600-1633); the resnet generators accept and ignore it.  M_T equals M
-    at T_resolution_multiplier = 1 (skitG_model.py:687,1313)."""
-    pass
+    """skitG: the multi-material twin (models/skitG_model.py).  Differences from sinskitG that reach the hot path:
+      * a 512-d style code per sample enters the U-Net generators, tiled and concatenated at the innermost decoder level(s)
+        (networks.py:1600-1633; skitG_model.py:1294-1302) — the resnet generators accept and ignore it (networks.py:1131).
+        The reference computes it with CLIP ViT-B/32 in fp16 inside forward(); here it comes precomputed in the batch
+        (`style_code`, any float dtype: torch.cat promotes CLIP's fp16 to fp32 in the reference too) or from `style_encoder`.
+        It is staged into a persistent device buffer like every other input, so the captured step graph reads the current
+        material's code on every replay;
+      * `M_T`, the mask of the touch output (skitG_model.py:687,1313), equals M at T_resolution_multiplier = 1;
+      * the reference's own skitG.optimize_parameters raises TypeError as shipped: the step is sinskitG's.
+    `model_defaults` are skitG's set_defaults (skitG_model.py:296-319)."""
+    model_name = "skitG"
+
+    def __init__(self, opt, dist_ctx=None, style_encoder=None):
+        self.style_encoder = style_encoder
+        super().__init__(opt, dist_ctx)
