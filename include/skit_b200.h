@@ -154,6 +154,14 @@ int skit_conv2d_fwd(const skit_operand* x, const skit_weights* w, int stride, in
 int skit_conv2d_dgrad_gather(const float* dy, int n, int ho, int wo, int co,
                              const skit_weights* wg, int stride, int hp, int wp, float* dx, void* stream);
 
+/* Precision of the BACKWARD tensor-core launches (skit_conv2d_dgrad_s1 / _s2, skit_conv2d_wgrad*): the autograd of F.conv2d
+ * the reference runs in TF32 on its own GPUs (torch.backends.cudnn.allow_tf32 default, README.md:61 torch 1.11).
+ *   terms = 3: every bf16 hi/lo pair is multiplied as A_lo*B_hi + A_hi*B_lo + A_hi*B_hi (like the forward convs, ~1e-5 of fp32);
+ *   terms = 2 (default; SKIT_BWD_TERMS=3 in the environment flips it): the filter's lo plane (dgrad) / the output gradient's lo
+ *              plane (wgrad) is neither loaded nor multiplied — gradients within ~5e-3 of fp32 (gate: 3e-2 per tensor).
+ * Forward launches (skit_conv2d_fwd) are always three-term. */
+int skit_set_backward_terms(int terms);
+
 /* Input gradient of a stride-1 conv (autograd of F.conv2d, e.g. the ResnetBlock convs networks.py:1281-1310):
  *   dx[n][y][x][c] = sum_{a,b,o} dz[n][y+a][x+b][o] * w[o][c][k-1-a][k-1-b],  dz = dy with a zero halo of k-1
  * dy: operand carrying that halo (dy->hp = H + k - 1 for an H x W gradient w.r.t. the conv's padded input); w1: mode-1 pack;
@@ -212,6 +220,17 @@ int skit_norm_act_pad(const float* raw, int n, int h, int w, int c,
                       const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
                       int act, const float* residual, float* out,
                       const skit_operand* op, int pad, int pad_mode, void* stream);
+
+/* skit_norm_act_pad_ex with the statistics finalise fused in (InstanceNorm2d / BatchNorm2d of models/networks.py:138-139 and
+ * :1712-1723 between a conv and the next one): `stats` are the fp64 [groups][c][2] (sum, sum of squares) the producing conv's
+ * epilogue accumulated over `count` elements; every thread block derives mean and 1/sqrt(var + eps) for its own channels (same
+ * arithmetic as skit_stats_finalize) and `mean_rstd_out` [groups][c][2] is written as a side output for the backward pass —
+ * no separate finalise launch sits between a conv and the operand of the next one. */
+int skit_norm_act_pad_stats(const float* raw, int n, int h, int w, int c,
+                            const double* stats, double count, float eps, float* mean_rstd_out,
+                            int norm_mode, const float* gamma, const float* beta,
+                            int act, const float* residual, float* out,
+                            const skit_operand* op, int c_off, int pad, int pad_mode, void* stream);
 
 /* Same, writing channels [c_off, c_off + c) of a wider operand (op->c >= c_off + c): builds `ReLU(cat(x, skip))`
  * of the U-Net decoder (thirdparty/unet/unet_parts_custom.py:46-79) slice by slice, never materialising the cat. */

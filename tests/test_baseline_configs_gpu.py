@@ -18,6 +18,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 GATE = 1e-3
+POST_UPDATE_GATE = 5e-3
 GRAD_REL, GRAD_COS = 3e-2, 0.9995
 
 
@@ -106,7 +107,13 @@ def test_train_step_vs_oracle_at_baseline_configs(S, nce):
     print("oracle train step %dx%d%s: %.1f s of CPU" % (S, S, " + PatchNCE" if nce else "", time.time() - t0))
     assert ("NCE" in res["losses"]) == nce
     for k, v in res["losses"].items():
-        assert abs(losses[k] - v) <= GATE * max(1.0, abs(v)), (k, losses[k], v)
+        # G_GAN / G2_GAN are evaluated through discriminators that were just updated by Adam with beta1 = 0 at step 1, i.e. by
+        # -lr * sign(g): entries whose gradient is zero to rounding move by +-lr depending on the evaluation order (true of any
+        # two fp32 implementations, CPU vs cuDNN included), and at 8.3 M discriminator weights that shows up in the fourth digit
+        # of these two values.  Everything computed before an update keeps the 1e-3 gate.
+        gate = POST_UPDATE_GATE if k in ("G_GAN", "G2_GAN") else GATE
+        assert abs(losses[k] - v) <= gate * max(1.0, abs(v)), (k, losses[k], v)
+    print("losses: max rel deviation %.2e" % max(abs(losses[k] - v) / max(1.0, abs(v)) for k, v in res["losses"].items()))
     errs = {nm: rel(getattr(m, nm), res[nm]) for nm in ("fake_I", "fake_T", "fake_N", "aug_fake_I")}
     print("outputs vs oracle:", errs)
     assert max(errs.values()) < GATE, errs
@@ -148,8 +155,9 @@ def test_conv_fwd_tcgen05_at_full_size_shapes(ci, co, hw, what):
     np.testing.assert_allclose(s[:, 1], (ref.double() ** 2).sum((0, 2, 3)), rtol=1e-4, atol=5e-2)
 
 
+@pytest.mark.parametrize("terms,tol", [(3, 5e-5), (2, 4e-3)])
 @pytest.mark.parametrize("c,hw", [(256, (128, 128)), (256, (192, 192)), (128, (256, 256))])
-def test_dgrad_s1_multi_region_at_full_size_shapes(c, hw):
+def test_dgrad_s1_multi_region_at_full_size_shapes(c, hw, terms, tol):
     """Stride-1 input gradient (interior + four border strips in one launch) of a 3x3 conv at the trunk / up-conv sizes vs
     torch's conv_transpose2d (= the autograd input gradient of the VALID conv over the haloed operand)."""
     import vts_b200 as V
@@ -160,9 +168,13 @@ def test_dgrad_s1_multi_region_at_full_size_shapes(c, hw):
     ref = F.conv_transpose2d(dy, w)                       # [1, c, h + 2, w + 2]
     _, d_op = ops.norm_act_pad(dy.permute(0, 2, 3, 1).contiguous().cuda(), pad=2, pad_mode=ops.PAD_ZERO, fmt=ops.FMT_BF16X2)
     pk = ops.PackedWeights(w.cuda(), 1, want_f32=False, want_bf16=True)
-    dx = ops.conv2d_dgrad_s1(d_op, pk)
-    torch.cuda.synchronize()
+    ops.set_backward_terms(terms)       # 3: the forward's full product; 2: the default backward precision (W_hi only)
+    try:
+        dx = ops.conv2d_dgrad_s1(d_op, pk)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_backward_terms(2)
     assert tuple(dx.shape) == (1, hw[0] + 2, hw[1] + 2, c)
     r = rel(dx.permute(0, 3, 1, 2), ref)
-    print("dgrad_s1 %d ch @%dx%d: rel err %.2e" % (c, hw[0], hw[1], r))
-    assert r < 5e-5
+    print("dgrad_s1 %d ch @%dx%d, %d-term product: rel err %.2e" % (c, hw[0], hw[1], terms, r))
+    assert r < tol

@@ -213,3 +213,20 @@ def test_default_options_against_the_reference_parser(golden_dir):
     for k in ("netG", "ngf", "ndf", "lambda_G1_lpips", "lambda_G2_lpips"):
         assert r[k] == ref[k], k
     assert r["use_vision_aided_loss"] is False and ref["use_vision_aided_loss"] is True
+
+
+def test_first_of_permutation_is_a_uniform_partial_shuffle():
+    """PatchSampleF's id draw without the O(H*W) permutation: distinct ids, in range, seedable through np.random.seed like the
+    reference's np.random.permutation, uniform marginals (chi-square-ish bound) and uniform first element."""
+    np.random.seed(3)
+    a = N.first_of_permutation(1000, 256)
+    np.random.seed(3)
+    b = N.first_of_permutation(1000, 256)
+    assert (a == b).all() and len(set(a.tolist())) == 256 and a.min() >= 0 and a.max() < 1000
+    assert sorted(N.first_of_permutation(5, 64).tolist()) == [0, 1, 2, 3, 4]          # p > n: a full permutation
+    counts, first = np.zeros(20), np.zeros(20)
+    for _ in range(4000):
+        s = N.first_of_permutation(20, 5)
+        counts[s] += 1
+        first[s[0]] += 1
+    assert np.abs(counts / 4000 - 0.25).max() < 0.04 and np.abs(first / 4000 - 0.05).max() < 0.02

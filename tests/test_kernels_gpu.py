@@ -14,9 +14,13 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def V():
+    """The kernel tests check the ARITHMETIC of every entry point, so the backward tensor-core launches run the full three-term
+    product here (tolerance 2e-4); the default two-term backward has its own test below (test_backward_two_term_product)."""
     import vts_b200
     vts_b200._lib.load()
-    return vts_b200
+    vts_b200.ops.set_backward_terms(3)
+    yield vts_b200
+    vts_b200.ops.set_backward_terms(2)
 
 
 def rel(a, b):
@@ -173,6 +177,39 @@ def test_conv_stage_fwd_bwd(V, ci, co, k, stride, pad, mode, norm, act, hw, n, t
         assert layer.bias.grad.abs().max().item() < 1e-3 * max(1.0, w.grad.abs().max().item())
     if norm == "batch":
         assert rel(dgm, gamma.grad) < tol and rel(dbt, beta.grad) < tol
+
+
+@pytest.mark.parametrize("ci,co,k,hw", [(256, 256, 3, (32, 32)), (128, 64, 3, (40, 24)), (64, 128, 4, (17, 19))])
+def test_backward_two_term_product(V, ci, co, k, hw):
+    """The default backward precision (skit_set_backward_terms(2)): dgrad = (dy_hi + dy_lo) * W_hi, wgrad = (x_hi + x_lo) * dy_hi.
+    One operand is rounded to bf16 (8 significant bits), so each gradient carries ~2^-9 / sqrt(3) of relative noise: gate 4e-3
+    (measured ~1.5e-3), against autograd's fp32 gradients."""
+    ops, N = V.ops, V.networks
+    g = torch.Generator().manual_seed(ci + co)
+    pad = k // 2
+    x = torch.randn(1, ci, *hw, generator=g, requires_grad=True)
+    w = (torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)).requires_grad_(True)
+    y = F.conv2d(F.pad(x, (pad,) * 4), w)
+    R = torch.randn(y.shape, generator=g)
+    (y * R).sum().backward()
+    layer = N.Conv2d(ci, co, k).cuda()
+    layer.weight.data.copy_(w.detach())
+    layer.weight.grad = torch.zeros_like(layer.weight)
+    layer.bias.grad = torch.zeros_like(layer.bias)
+    x_op = make_operand(V, x.detach(), pad, 0, ops.FMT_BF16X2)
+    ho, wo = y.shape[2:]
+    raw_d, _ = ops.conv2d_fwd(x_op, layer.pack(0), 1, 0, ho, wo)
+    res = {}
+    for terms in (3, 2):
+        ops.set_backward_terms(terms)
+        layer.weight.grad.zero_()
+        dx_pad = N._stage_bwd(layer, x_op, raw_d, None, ops.NORM_NONE, ops.ACT_NONE, ho * wo, dadd=nhwc(R).cuda())
+        dx = ops.operand_grad_to_nchw(dx_pad, hw[0], hw[1], pad, 0, 0, ci)
+        torch.cuda.synchronize()
+        res[terms] = (rel(dx, x.grad), rel(layer.weight.grad, w.grad))
+    ops.set_backward_terms(3)
+    print("backward product terms -> (dx, dW) rel err:", res)
+    assert max(res[3]) < 2e-4 and max(res[2]) < 4e-3 and min(res[2]) > 2e-4     # the two-term path really ran
 
 
 # ------------------------------------------------------------------------------ resamplers

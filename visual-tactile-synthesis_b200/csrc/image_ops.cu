@@ -479,6 +479,76 @@ __global__ void __launch_bounds__(256) patchnce_kernel(const float* __restrict__
     }
 }
 
+// Tiled single-pass PatchNCE for dim <= 256 (every use on the hot path: feature widths 9 / 128 / 256 and the MLP width):
+// a block owns RB query rows of one batch element (one warp per row); the keys stream through shared memory in tiles of 32
+// (row stride dim + 1: lane j reads key j conflict-free), each lane owns one key of the tile for the logits and the columns
+// t = lane + 32 u of dq, and the softmax is accumulated online (running max m, running sum s, rescaled accumulator) so K is
+// read once.  loss = logsumexp(logits) - logit_pos;  dq = (sum_j p_j k_j - k_pos) / T * gscale  with the masked diagonal
+// counted in the normaliser only (it is the constant -10 / T).
+template <int RB>
+__global__ void __launch_bounds__(RB * 32) patchnce_tiled_kernel(const float* __restrict__ q, const float* __restrict__ k, int b, int np, int dim,
+                                                                 float inv_T, float* __restrict__ loss, float* __restrict__ dq, float gscale) {
+    extern __shared__ float sm[];
+    const int ld = dim + 1;
+    float* ks = sm;                       // [32][ld]
+    float* qs = ks + 32 * ld;             // [RB][dim]
+    float* ps = qs + RB * dim;            // [RB][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_b = (np + RB - 1) / RB;
+    const int bi = blockIdx.x / tiles_per_b, i = (blockIdx.x - bi * tiles_per_b) * RB + warp;
+    const bool valid = i < np;
+    const long long row = (long long)bi * np + (valid ? i : 0);
+    const float* kb = k + (long long)bi * np * dim;
+    const float* kpos = k + row * dim;
+    for (int t = lane; t < dim; t += 32) qs[warp * dim + t] = q[row * dim + t];
+    __syncwarp();
+    float l0 = 0.f;
+    for (int t = lane; t < dim; t += 32) l0 += qs[warp * dim + t] * kpos[t];
+    l0 = warp_sum(l0) * inv_T;
+    float m = l0, ssum = 1.f, acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; acc[u] = t < dim ? kpos[t] : 0.f; }
+    for (int j0 = 0; j0 < np; j0 += 32) {
+        __syncthreads();
+        const int nk = min(32, np - j0);
+        for (int e = threadIdx.x; e < nk * dim; e += RB * 32) { const int jj = e / dim, t = e - jj * dim; ks[jj * ld + t] = kb[(long long)(j0 + jj) * dim + t]; }
+        __syncthreads();
+        const int j = j0 + lane;
+        float lg = -INFINITY;
+        if (lane < nk) {
+            float d = 0.f;
+            const float* kr = ks + lane * ld;
+            const float* qr = qs + warp * dim;
+            for (int t = 0; t < dim; t++) d += qr[t] * kr[t];
+            lg = (j == i ? -10.f : d) * inv_T;
+        }
+        float tm = lg;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+        const float mn = fmaxf(m, tm), sc = __expf(m - mn);
+        const float p = lane < nk ? __expf(lg - mn) : 0.f;
+        ssum = ssum * sc + warp_sum(p);
+        m = mn;
+        ps[warp * 32 + lane] = (j == i) ? 0.f : p;
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc[u] *= sc;
+        for (int jj = 0; jj < nk; jj++) {
+            const float pj = ps[warp * 32 + jj];
+            const float* kr = ks + jj * ld;
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; if (t < dim) acc[u] += pj * kr[t]; }
+        }
+    }
+    if (!valid) return;
+    if (lane == 0) loss[row] = m + logf(ssum) - l0;
+    if (dq) {
+        const float inv_s = 1.f / ssum;
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; if (t < dim) dq[row * dim + t] = (acc[u] * inv_s - kpos[t]) * inv_T * gscale; }
+    }
+}
+
 }  // namespace skit
 
 using namespace skit;
@@ -659,6 +729,12 @@ extern "C" int skit_rows_scatter_add(const float* drows, int b, int hw, int c, c
 extern "C" int skit_patchnce(const float* q, const float* k, int b, int np, int dim, float inv_T,
                              float* loss, float* dq, float gscale, void* stream) {
     SKIT_REQUIRE(q && k && loss && b > 0 && np > 0 && dim > 0, "patchnce: bad arguments");
+    if (dim <= 256) {
+        constexpr int RB = 4;
+        const size_t sm2 = ((size_t)32 * (dim + 1) + (size_t)RB * dim + RB * 32) * sizeof(float);
+        patchnce_tiled_kernel<RB><<<b * cdiv(np, RB), RB * 32, sm2, as_stream(stream)>>>(q, k, b, np, dim, inv_T, loss, dq, gscale);
+        return check_launch("patchnce_tiled_kernel");
+    }
     const size_t smem = (size_t)8 * (np + 1) * sizeof(float);
     SKIT_REQUIRE(smem <= 48 * 1024, "patchnce: num_patches %d too large", np);
     patchnce_kernel<<<cdiv(b * np, 8), 256, smem, as_stream(stream)>>>(q, k, b, np, dim, inv_T, loss, dq, gscale);

@@ -42,6 +42,9 @@ struct PrepP {
     float* o0; __nv_bfloat16* oh; __nv_bfloat16* ol; int fmt;  // operand planes or NULL
     int pad, pad_mode;
     int oc, ooff;                    // operand channel count and the channel offset this call fills (concat slices)
+    // fused statistics finalise (rows kernel): the fp64 (sum, sum of squares) the producing conv's epilogue accumulated; every
+    // thread derives mean / rstd of its own 4 channels in its prologue and one block per group writes them out for the backward
+    const double* stats; double count; float eps; float* mr_out;
 };
 
 template <int VEC>
@@ -116,9 +119,19 @@ __global__ void __launch_bounds__(256) norm_act_pad_rows_kernel(PrepP p, int cv,
     const int cl = threadIdx.x % cv, pl = threadIdx.x / cv, PL = 256 / cv;
     const int ch = cl * 4;
     float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1}, gam[4] = {1, 1, 1, 1}, bet[4] = {0, 0, 0, 0};
+    const bool normed = p.mr != nullptr || p.stats != nullptr;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        if (p.mr) {
+        if (p.stats) {      // same arithmetic as stats_finalize_kernel
+            const long long gi = (long long)(p.per_n ? n : 0) * p.c + ch + j;
+            const double m = p.stats[2 * gi] / p.count;
+            double var = p.stats[2 * gi + 1] / p.count - m * m;
+            if (var < 0) var = 0;
+            mean[j] = (float)m; rstd[j] = (float)(1.0 / sqrt(var + (double)p.eps));
+            if (p.mr_out && blockIdx.x == 0 && blockIdx.z == 0 && pl == 0 && (p.per_n || n == 0)) {
+                p.mr_out[2 * gi] = mean[j]; p.mr_out[2 * gi + 1] = rstd[j];
+            }
+        } else if (p.mr) {
             const float* mr = p.mr + ((long long)(p.per_n ? n : 0) * p.c + ch + j) * 2;
             mean[j] = mr[0]; rstd[j] = mr[1];
         }
@@ -151,7 +164,7 @@ __global__ void __launch_bounds__(256) norm_act_pad_rows_kernel(PrepP p, int cv,
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         float x = v[j];
-                        if (p.mr) x = (x - mean[j]) * rstd[j];
+                        if (normed) x = (x - mean[j]) * rstd[j];
                         if (p.gamma) x = x * gam[j] + bet[j];
                         x = act_fwd(x, p.act);
                         if (p.residual) x += rs[j];
@@ -788,13 +801,22 @@ extern "C" int skit_fold_x_operand(const skit_operand* thin, int kw, const skit_
     return check_launch("fold_x_kernel");
 }
 
-extern "C" int skit_norm_act_pad_ex(const float* raw, int n, int h, int w, int c,
-                                    const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
-                                    int act, const float* residual, float* out,
-                                    const skit_operand* op, int c_off, int pad, int pad_mode, void* stream) {
+static int norm_act_pad_impl(const float* raw, int n, int h, int w, int c,
+                             const float* mean_rstd, const double* stats, double count, float eps, float* mr_out,
+                             int norm_mode, const float* gamma, const float* beta,
+                             int act, const float* residual, float* out,
+                             const skit_operand* op, int c_off, int pad, int pad_mode, void* stream) {
     SKIT_REQUIRE(raw && n > 0 && h > 0 && w > 0 && c > 0, "norm_act_pad: bad arguments");
     SKIT_REQUIRE(out || op, "norm_act_pad: nothing to write");
-    SKIT_REQUIRE((norm_mode == SKIT_NORM_NONE) == (mean_rstd == nullptr), "norm_act_pad: mean_rstd must be given iff norm_mode != none");
+    SKIT_REQUIRE((norm_mode == SKIT_NORM_NONE) == (mean_rstd == nullptr && stats == nullptr), "norm_act_pad: mean_rstd / stats must be given iff norm_mode != none");
+    if (stats && !(rows_layout_ok(c) && (!op || (op->c % 4 == 0 && c_off % 4 == 0)))) {
+        // layouts the row-tiled kernel does not cover: finalise with the stand-alone kernel, then the generic pass
+        const int groups = norm_mode == SKIT_NORM_INSTANCE ? n : 1;
+        stats_finalize_kernel<<<cdiv(groups * c, 128), 128, 0, as_stream(stream)>>>(stats, groups, c, count, eps, mr_out, nullptr, nullptr, 0.f);
+        int rc0 = check_launch("stats_finalize_kernel");
+        if (rc0) return rc0;
+        mean_rstd = mr_out; stats = nullptr;
+    }
     SKIT_REQUIRE((gamma == nullptr) == (beta == nullptr), "norm_act_pad: gamma/beta must come in pairs");
     SKIT_REQUIRE(pad >= 0 && (pad_mode != SKIT_PAD_REFLECT || (pad < h && pad < w)), "norm_act_pad: reflect pad %d too large for %dx%d", pad, h, w);
     if (!op) pad = 0;
@@ -812,6 +834,7 @@ extern "C" int skit_norm_act_pad_ex(const float* raw, int n, int h, int w, int c
         else { p.oh = (__nv_bfloat16*)op->p0; p.ol = (__nv_bfloat16*)op->p1; }
     }
     p.pad = pad; p.pad_mode = pad_mode; p.oc = oc; p.ooff = c_off;
+    p.stats = stats; p.count = count; p.eps = eps; p.mr_out = mr_out;
     const long long pix = (long long)n * (h + 2 * pad) * (w + 2 * pad);
     if (rows_layout_ok(c) && (!op || (oc % 4 == 0 && c_off % 4 == 0))) {
         const int hp = h + 2 * pad, wp = w + 2 * pad;
@@ -825,6 +848,24 @@ extern "C" int skit_norm_act_pad_ex(const float* raw, int n, int h, int w, int c
     if (c % 4 == 0 && oc % 4 == 0 && c_off % 4 == 0) norm_act_pad_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
     else norm_act_pad_kernel<1><<<grid_for(pix * c, 256), 256, 0, as_stream(stream)>>>(p);
     return check_launch("norm_act_pad_kernel");
+}
+
+extern "C" int skit_norm_act_pad_ex(const float* raw, int n, int h, int w, int c,
+                                    const float* mean_rstd, int norm_mode, const float* gamma, const float* beta,
+                                    int act, const float* residual, float* out,
+                                    const skit_operand* op, int c_off, int pad, int pad_mode, void* stream) {
+    return norm_act_pad_impl(raw, n, h, w, c, mean_rstd, nullptr, 0.0, 0.f, nullptr, norm_mode, gamma, beta, act, residual, out, op, c_off,
+                             pad, pad_mode, stream);
+}
+
+extern "C" int skit_norm_act_pad_stats(const float* raw, int n, int h, int w, int c,
+                                       const double* stats, double count, float eps, float* mean_rstd_out,
+                                       int norm_mode, const float* gamma, const float* beta,
+                                       int act, const float* residual, float* out,
+                                       const skit_operand* op, int c_off, int pad, int pad_mode, void* stream) {
+    SKIT_REQUIRE(stats && mean_rstd_out && count > 0 && norm_mode != SKIT_NORM_NONE, "norm_act_pad_stats: statistics, their count and the mean/rstd output are required");
+    return norm_act_pad_impl(raw, n, h, w, c, nullptr, stats, count, eps, mean_rstd_out, norm_mode, gamma, beta, act, residual, out, op, c_off,
+                             pad, pad_mode, stream);
 }
 
 extern "C" int skit_norm_act_pad(const float* raw, int n, int h, int w, int c,

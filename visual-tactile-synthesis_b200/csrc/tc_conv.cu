@@ -249,6 +249,21 @@ static bool halo_enabled() {
     return v != 0;
 }
 
+// Products per bf16 hi/lo pair in BACKWARD tensor-core launches (input gradients and weight gradients).  The forward convs
+// always run the three-term product (A_lo*W_hi + A_hi*W_lo + A_hi*W_hi: ~1e-5 of fp32, the 1e-3 output gate).  Gradients are
+// gated at 3e-2 per tensor and the reference's own GPU runs computed them in TF32 (10-bit operands), so by default the
+// backward launches drop one cross term: dgrad = (dy_hi + dy_lo) * W_hi, wgrad = (x_hi + x_lo) * dy_hi — a third fewer MMAs,
+// half the weight-stage fill — leaving every gradient within ~5e-3 of fp32 (tests/test_baseline_configs_gpu.py prints the
+// worst value).  skit_set_backward_terms(3) or SKIT_BWD_TERMS=3 restores the full product.
+static int g_bwd_terms = 0;
+int bwd_terms() {
+    if (g_bwd_terms == 0) {
+        const char* e = getenv("SKIT_BWD_TERMS");
+        g_bwd_terms = (e && e[0] == '3') ? 3 : 2;
+    }
+    return g_bwd_terms;
+}
+
 // k: taps per side of THIS launch; ntaps_total: taps in the packed filter (weight map extent); tap_base: first tap.
 int conv_tc_launch(const skit_operand* x, const void* w_hi, const void* w_lo, int ci, int co, int k, int ntaps_total,
                    int tap_base, int stride, int org, int ho, int wo, const float* bias, float* y, const TcOut* out,
@@ -259,6 +274,10 @@ int conv_tc_launch(const skit_operand* x, const void* w_hi, const void* w_lo, in
         return conv_tc_halo_launch(x, w_hi, w_lo, ci, co, k, kw, ntaps_total, tap_base, org, ho, wo, bias, y, out, stats, stats_mode, st);
     if (kw != k) {
         set_error("conv2d_fwd: rectangular (x-folded) filters need the halo-tile kernel (stride 1, SKIT_TC_HALO != 0)");
+        return SKIT_ERR_UNSUPPORTED;
+    }
+    if (!w_lo) {
+        set_error("conv_tc: the per-tap kernel runs the three-term product only (two-term launches need the halo-tile kernel)");
         return SKIT_ERR_UNSUPPORTED;
     }
     TcConvP p{};
@@ -330,6 +349,12 @@ int conv_head7_launch(const skit_operand* x, const skit_weights* w, int org, int
 
 using namespace skit;
 
+extern "C" int skit_set_backward_terms(int terms) {
+    SKIT_REQUIRE(terms == 2 || terms == 3, "set_backward_terms: 2 or 3");
+    g_bwd_terms = terms;
+    return SKIT_OK;
+}
+
 extern "C" int skit_conv2d_fwd(const skit_operand* x, const skit_weights* w, int stride, int org,
                                int ho, int wo, const float* bias, float* y,
                                double* stats, int stats_mode, int impl, void* stream) {
@@ -370,7 +395,7 @@ extern "C" int skit_conv2d_dgrad_s2(const skit_operand* dy, int dy_pad, const sk
             const int A = (hp - py + 1) / 2, B = (wp_ - px + 1) / 2;  // outputs of this parity
             if (A <= 0 || B <= 0) continue;
             TcOut out{hp, wp_, 2, 2, py, px};
-            int rc = conv_tc_launch(dy, wp->hi, wp->lo, dy->c, wp->co, kh, 4 * kh * kh, (py * 2 + px) * kh * kh, 1, 0, A, B,
+            int rc = conv_tc_launch(dy, wp->hi, (bwd_terms() == 2 && halo_enabled()) ? nullptr : wp->lo, dy->c, wp->co, kh, 4 * kh * kh, (py * 2 + px) * kh * kh, 1, 0, A, B,
                                     nullptr, dx, &out, nullptr, SKIT_NORM_NONE, as_stream(stream));
             if (rc) return rc;
         }
@@ -386,6 +411,6 @@ extern "C" int skit_conv2d_dgrad_s1(const skit_operand* dy, const skit_weights* 
     SKIT_REQUIRE(w1->ci == dy->c && dy->hp >= k && dy->wp >= k, "conv2d_dgrad_s1: pack / operand mismatch");
     const int H = dy->hp - k + 1, W = dy->wp - k + 1;
     if (halo_enabled() && dy->fmt == SKIT_FMT_BF16X2 && w1->hi && w1->lo && w1->kw == 0 && dy->c % 64 == 0)
-        return conv_tc_halo_dgrad_full(dy, w1->hi, w1->lo, w1->co, k, dx, as_stream(stream));
+        return conv_tc_halo_dgrad_full(dy, w1->hi, bwd_terms() == 2 ? nullptr : w1->lo, w1->co, k, dx, as_stream(stream));
     return skit_conv2d_fwd(dy, w1, 1, 0, H, W, nullptr, dx, nullptr, SKIT_NORM_NONE, SKIT_IMPL_AUTO, stream);
 }

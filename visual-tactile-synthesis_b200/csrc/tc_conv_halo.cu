@@ -63,6 +63,8 @@ struct TcHaloP {
     int a_plane;       // bytes reserved per A plane (largest region's a_rows*128 rounded up to 1024)
     int nw;            // weight stages
     int na;            // activation stages (2, or 1 when a large halo tile must leave room for wide weight stages)
+    int terms;         // 3: A_lo*W_hi + A_hi*W_lo + A_hi*W_hi (fp32-parity forward);  2: (A_hi + A_lo)*W_hi only — the W_lo plane is
+                       // neither loaded nor multiplied (input-gradient launches, skit_set_backward_terms)
     long long* dbg;    // optional per-CTA clock64 stamps [cta][8] (skit_debug_set_buffer), NULL in production
 };
 
@@ -155,10 +157,10 @@ conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
                     const int s = it % p.nw, ph = (it / p.nw) & 1;
                     const int tap = R.tap_base + ky * R.tap_sy + kx * R.tap_sx;
                     mbar_wait(w_empty(s), ph ^ 1);
-                    mbar_expect_tx(w_full(s), W_STAGE);
+                    mbar_expect_tx(w_full(s), p.terms == 2 ? W_PLANE : W_STAGE);
                     const uint32_t sw = w0 + s * W_STAGE;
                     tma_load_3d(sw, &tmW_hi, w_full(s), c * 64, n0, tap);
-                    tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, n0, tap);
+                    if (p.terms != 2) tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, n0, tap);
                 }
     } else if (warp == 1 && lane == 0) {
         // ---------------- MMA issuer
@@ -188,7 +190,7 @@ conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
                         const uint64_t w_lo = make_desc(sw + W_PLANE + ko, 16, 1024);
                         mma_bf16(tmem_base, a_lo, w_hi, idesc, acc);
                         acc = 1u;
-                        mma_bf16(tmem_base, a_hi, w_lo, idesc, 1u);
+                        if (p.terms != 2) mma_bf16(tmem_base, a_hi, w_lo, idesc, 1u);
                         mma_bf16(tmem_base, a_hi, w_hi, idesc, 1u);
                     }
                     mma_commit(w_empty(ws));
@@ -403,10 +405,10 @@ conv_tc_halo_persist_kernel(const __grid_constant__ AMaps tmA, const __grid_cons
                         const int s = it % p.nw, ph = (it / p.nw) & 1;
                         const int tap = R.tap_base + ky * R.tap_sy + kx * R.tap_sx;
                         mbar_wait(w_empty(s), ph ^ 1);
-                        mbar_expect_tx(w_full(s), W_STAGE);
+                        mbar_expect_tx(w_full(s), p.terms == 2 ? W_PLANE : W_STAGE);
                         const uint32_t sw = w0 + s * W_STAGE;
                         tma_load_3d(sw, &tmW_hi, w_full(s), c * 64, n0, tap);
-                        tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, n0, tap);
+                        if (p.terms != 2) tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, n0, tap);
                     }
         }
     } else if (warp == 1 && lane == 0) {
@@ -441,7 +443,7 @@ conv_tc_halo_persist_kernel(const __grid_constant__ AMaps tmA, const __grid_cons
                             const uint64_t w_lo = make_desc(sw + W_PLANE + ko, 16, 1024);
                             mma_bf16(dacc, a_lo, w_hi, idesc, acc);
                             acc = 1u;
-                            mma_bf16(dacc, a_hi, w_lo, idesc, 1u);
+                            if (p.terms != 2) mma_bf16(dacc, a_hi, w_lo, idesc, 1u);
                             mma_bf16(dacc, a_hi, w_hi, idesc, 1u);
                         }
                         mma_commit(w_empty(ws));
@@ -673,7 +675,8 @@ static int encode_w_maps(CUtensorMap* m_hi, CUtensorMap* m_lo, const void* w_hi,
     uint32_t box[3] = {64, (uint32_t)BN, 1};
     int rc = tc::encode_bf16_map_sw(m_hi, w_hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    return tc::encode_bf16_map_sw(m_lo, w_lo, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    // two-term launches (w_lo == NULL) never touch the lo map: give it a valid encoding of the hi plane
+    return tc::encode_bf16_map_sw(m_lo, w_lo ? w_lo : w_hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 static bool persist_enabled() {
@@ -710,6 +713,7 @@ int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_l
     else { p.OH = ho; p.OW = wo; p.osy = 1; p.osx = 1; p.poy = 0; p.pox = 0; }
     p.bias = bias; p.y = y; p.stats = stats; p.stats_per_n = stats_mode == SKIT_NORM_INSTANCE;
     p.dbg = g_dbg_buffer;
+    p.terms = w_lo ? 3 : 2;
     p.nreg = 1;
     HaloRegion& R = p.reg[0];
     R.first = 0; R.kh = kh; R.kw = kw; R.tap_base = tap_base; R.tap_sy = kw; R.tap_sx = 1;
@@ -764,6 +768,7 @@ int conv_tc_halo_dgrad_full(const skit_operand* d, const void* w_hi, const void*
     p.kc = cdiv(ci, 64); p.kk_last = 4; p.co = co;
     p.OH = H; p.OW = W; p.osy = 1; p.osx = 1; p.poy = 0; p.pox = 0;
     p.bias = nullptr; p.y = dx; p.stats = nullptr; p.stats_per_n = 0; p.dbg = g_dbg_buffer;
+    p.terms = w_lo ? 3 : 2;
     p.nreg = 5;
     auto set = [&](int i, int kh, int kw, int tb, int sy, int sx, int oy, int ox, int ho, int wo, int ooy, int oox, int amap) {
         HaloRegion& R = p.reg[i];

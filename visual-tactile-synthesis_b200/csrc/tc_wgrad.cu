@@ -12,6 +12,7 @@
 #include "tc_common.cuh"
 
 namespace skit {
+int bwd_terms();   // tc_conv.cu
 namespace tc {
 
 struct TcWgradP {
@@ -25,6 +26,7 @@ struct TcWgradP {
     int x_org, x_stride, d_org, d_org_y;   // d_org: gradient-side column origin; d_org_y: its row origin
     int Mdim, Ndim;        // channel counts of the M / N side
     float* out;            // [tap][Ndim][Mdim] fp32 partial sums (zeroed by the caller)
+    int skip;              // two-term product: 1 = the M operand's lo plane is neither loaded nor multiplied, 2 = the N operand's; 0 = all three terms
 };
 
 constexpr int PIX = 64;               // pixels per K stage (8x8 box)
@@ -79,7 +81,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
             for (int it = 0; it < num_it; it++) {
                 const int s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                mbar_expect_tx(full_bar(s), STAGE_BYTES - (p.skip == 1 ? M_BYTES : p.skip == 2 ? N_BYTES : 0));
                 const int t = t_beg + it;
                 const int img = t / tpi, r = t - img * tpi;
                 const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
@@ -91,12 +93,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
 #pragma unroll
                 for (int g = 0; g < 2; g++) {
                     tma_load_4d(sa + g * BOX_BYTES, &tmM_hi, full_bar(s), mt * 128 + g * 64, mx, my, img);
-                    tma_load_4d(sa + M_BYTES + g * BOX_BYTES, &tmM_lo, full_bar(s), mt * 128 + g * 64, mx, my, img);
+                    if (p.skip != 1) tma_load_4d(sa + M_BYTES + g * BOX_BYTES, &tmM_lo, full_bar(s), mt * 128 + g * 64, mx, my, img);
                 }
 #pragma unroll
                 for (int g = 0; g < NBOX; g++) {
                     tma_load_4d(sa + 2 * M_BYTES + g * BOX_BYTES, &tmN_hi, full_bar(s), n0 + g * 64, nx, ny, img);
-                    tma_load_4d(sa + 2 * M_BYTES + N_BYTES + g * BOX_BYTES, &tmN_lo, full_bar(s), n0 + g * 64, nx, ny, img);
+                    if (p.skip != 2) tma_load_4d(sa + 2 * M_BYTES + N_BYTES + g * BOX_BYTES, &tmN_lo, full_bar(s), n0 + g * 64, nx, ny, img);
                 }
             }
         } else if (warp == 1 && lane == 0) {
@@ -114,9 +116,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
                     const uint64_t m_lo = make_desc(sa + M_BYTES + ko, BOX_BYTES, 1024);
                     const uint64_t n_hi = make_desc(sa + 2 * M_BYTES + ko, BOX_BYTES, 1024);
                     const uint64_t n_lo = make_desc(sa + 2 * M_BYTES + N_BYTES + ko, BOX_BYTES, 1024);
-                    mma_bf16(tmem_base, m_lo, n_hi, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                    mma_bf16(tmem_base, m_hi, n_lo, idesc, 1u);
-                    mma_bf16(tmem_base, m_hi, n_hi, idesc, 1u);
+                    mma_bf16(tmem_base, m_hi, n_hi, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    if (p.skip != 1) mma_bf16(tmem_base, m_lo, n_hi, idesc, 1u);
+                    if (p.skip != 2) mma_bf16(tmem_base, m_hi, n_lo, idesc, 1u);
                 }
                 mma_commit(empty_bar(s));
             }
@@ -208,6 +210,7 @@ int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
     p.Mdim = p.m_is_x ? ci : co;
     p.Ndim = p.m_is_x ? co : ci;
     p.out = partial;
+    p.skip = bwd_terms() == 2 ? (p.m_is_x ? 2 : 1) : 0;     // drop the GRADIENT operand's lo plane: dW = (x_hi + x_lo) * dy_hi
     *layout = p.m_is_x;
     const int BN = (p.Ndim % 256 == 0) ? 256 : (p.Ndim % 128 == 0) ? 128 : (p.Ndim % 64 == 0) ? 64 : 16;
     const int mtiles = cdiv(p.Mdim, 128), ntiles = cdiv(p.Ndim, BN);

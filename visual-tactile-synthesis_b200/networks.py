@@ -343,21 +343,18 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         op0, thin0 = self._stem_operand(srcs)
         tap(0, lambda: thin0.data if thin0 is not None else (ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT).data if self._c1.use_tc else op0.data))
         raw1, st = _conv_fwd(self._c1, op0, 0, S_h, S_w, IN)
-        mr1 = ops.stats_finalize(st, S_h * S_w)
         tap(1, lambda: raw1)
-        _, op1 = ops.norm_act_pad(raw1, mr1, IN, act=ACT_RELU, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c4))
+        _, op1, mr1 = ops.norm_act_pad_stats(raw1, st, S_h * S_w, IN, act=ACT_RELU, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c4))
         raw4, st = _conv_fwd(self._c4, op1, 0, S_h, S_w, IN)
-        mr4 = ops.stats_finalize(st, S_h * S_w)
         tap(4, lambda: raw4)
-        a4, _ = ops.norm_act_pad(raw4, mr4, IN, act=ACT_RELU, want_dense=True)
+        a4, _, mr4 = ops.norm_act_pad_stats(raw4, st, S_h * S_w, IN, act=ACT_RELU, want_dense=True)
         d4 = ops.blur_down_fwd(a4)
         del a4
         _, op4 = ops.norm_act_pad(d4, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c8))
         h2, w2 = S_h // 2, S_w // 2
         raw8, st = _conv_fwd(self._c8, op4, 0, h2, w2, IN)
-        mr8 = ops.stats_finalize(st, h2 * w2)
         tap(8, lambda: raw8)
-        a8, _ = ops.norm_act_pad(raw8, mr8, IN, act=ACT_RELU, want_dense=True)
+        a8, _, mr8 = ops.norm_act_pad_stats(raw8, st, h2 * w2, IN, act=ACT_RELU, want_dense=True)
         t = ops.blur_down_fwd(a8)
         del a8
         h4, w4 = h2 // 2, w2 // 2
@@ -368,13 +365,11 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         for b, blk in enumerate(self._blocks):
             ca, cb = blk.conv_block[1], blk.conv_block[5]
             rawA, st = _conv_fwd(ca, op_t, 0, h4, w4, IN)
-            mrA = ops.stats_finalize(st, h4 * w4)
-            _, opA = ops.norm_act_pad(rawA, mrA, IN, act=ACT_RELU, pad=1, pad_mode=PAD_REFLECT, fmt=self._fmt(cb))
+            _, opA, mrA = ops.norm_act_pad_stats(rawA, st, h4 * w4, IN, act=ACT_RELU, pad=1, pad_mode=PAD_REFLECT, fmt=self._fmt(cb))
             rawB, st = _conv_fwd(cb, opA, 0, h4, w4, IN)
-            mrB = ops.stats_finalize(st, h4 * w4)
             last = b == nb - 1
-            t_new, op_next = ops.norm_act_pad(rawB, mrB, IN, residual=t, want_dense=True, pad=1, pad_mode=PAD_REFLECT,
-                                              fmt=None if last else fmt_b)
+            t_new, op_next, mrB = ops.norm_act_pad_stats(rawB, st, h4 * w4, IN, residual=t, want_dense=True, pad=1, pad_mode=PAD_REFLECT,
+                                                         fmt=None if last else fmt_b)
             blocks.append((op_t, rawA, mrA, opA, rawB, mrB))
             t, op_t = t_new, op_next
             tap(12 + b, lambda: t)
@@ -382,15 +377,13 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         _, op_u1 = ops.norm_act_pad(u1, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._u1))
         del u1
         raw22, st = _conv_fwd(self._u1, op_u1, 0, h2, w2, IN)
-        mr22 = ops.stats_finalize(st, h2 * w2)
-        a22, _ = ops.norm_act_pad(raw22, mr22, IN, act=ACT_RELU, want_dense=True)
+        a22, _, mr22 = ops.norm_act_pad_stats(raw22, st, h2 * w2, IN, act=ACT_RELU, want_dense=True)
         u2 = ops.blur_up_fwd(a22)
         del a22
         _, op_u2 = ops.norm_act_pad(u2, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._u2))
         del u2
         raw26, st = _conv_fwd(self._u2, op_u2, 0, S_h, S_w, IN)
-        mr26 = ops.stats_finalize(st, S_h * S_w)
-        _, op26 = ops.norm_act_pad(raw26, mr26, IN, act=ACT_RELU, pad=3, pad_mode=PAD_REFLECT, fmt=self._fmt(self._out))
+        _, op26, mr26 = ops.norm_act_pad_stats(raw26, st, S_h * S_w, IN, act=ACT_RELU, pad=3, pad_mode=PAD_REFLECT, fmt=self._fmt(self._out))
         raw30, _ = _conv_fwd(self._out, op26, 0, S_h, S_w, NORM_NONE)
         fI, fT, fN = ops.g_head_fwd(raw30, mask, scale_nz, want_normal)
         if save:
@@ -491,33 +484,33 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         if top == 0:
             return feats, ctx
         raw1, st = _conv_fwd(self._c1, op0, 0, S_h, S_w, IN)
-        mr1 = ops.stats_finalize(st, S_h * S_w)
-        ctx.update(raw1=raw1, mr1=mr1)
         if 1 in layers:
             feats[1] = raw1
         if top == 1:
+            ctx.update(raw1=raw1, mr1=ops.stats_finalize(st, S_h * S_w))
             return feats, ctx
-        _, op1 = ops.norm_act_pad(raw1, mr1, IN, act=ACT_RELU, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c4))
+        _, op1, mr1 = ops.norm_act_pad_stats(raw1, st, S_h * S_w, IN, act=ACT_RELU, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c4))
+        ctx.update(raw1=raw1, mr1=mr1)
         raw4, st = _conv_fwd(self._c4, op1, 0, S_h, S_w, IN)
-        mr4 = ops.stats_finalize(st, S_h * S_w)
-        ctx.update(op1=op1, raw4=raw4, mr4=mr4)
         if 4 in layers:
             feats[4] = raw4
         if top == 4:
+            ctx.update(op1=op1, raw4=raw4, mr4=ops.stats_finalize(st, S_h * S_w))
             return feats, ctx
-        a4, _ = ops.norm_act_pad(raw4, mr4, IN, act=ACT_RELU, want_dense=True)
+        a4, _, mr4 = ops.norm_act_pad_stats(raw4, st, S_h * S_w, IN, act=ACT_RELU, want_dense=True)
+        ctx.update(op1=op1, raw4=raw4, mr4=mr4)
         d4 = ops.blur_down_fwd(a4)
         del a4
         _, op4 = ops.norm_act_pad(d4, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c8))
         h2, w2 = S_h // 2, S_w // 2
         raw8, st = _conv_fwd(self._c8, op4, 0, h2, w2, IN)
-        mr8 = ops.stats_finalize(st, h2 * w2)
-        ctx.update(op4=op4, raw8=raw8, mr8=mr8)
         if 8 in layers:
             feats[8] = raw8
         if top == 8:
+            ctx.update(op4=op4, raw8=raw8, mr8=ops.stats_finalize(st, h2 * w2))
             return feats, ctx
-        a8, _ = ops.norm_act_pad(raw8, mr8, IN, act=ACT_RELU, want_dense=True)
+        a8, _, mr8 = ops.norm_act_pad_stats(raw8, st, h2 * w2, IN, act=ACT_RELU, want_dense=True)
+        ctx.update(op4=op4, raw8=raw8, mr8=mr8)
         t = ops.blur_down_fwd(a8)
         del a8
         h4, w4 = h2 // 2, w2 // 2
@@ -528,13 +521,11 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         for b in range(nblk):
             ca, cb = self._blocks[b].conv_block[1], self._blocks[b].conv_block[5]
             rawA, st = _conv_fwd(ca, op_t, 0, h4, w4, IN)
-            mrA = ops.stats_finalize(st, h4 * w4)
-            _, opA = ops.norm_act_pad(rawA, mrA, IN, act=ACT_RELU, pad=1, pad_mode=PAD_REFLECT, fmt=self._fmt(cb))
+            _, opA, mrA = ops.norm_act_pad_stats(rawA, st, h4 * w4, IN, act=ACT_RELU, pad=1, pad_mode=PAD_REFLECT, fmt=self._fmt(cb))
             rawB, st = _conv_fwd(cb, opA, 0, h4, w4, IN)
-            mrB = ops.stats_finalize(st, h4 * w4)
             last = b == nblk - 1
-            t, op_next = ops.norm_act_pad(rawB, mrB, IN, residual=t, want_dense=True, pad=1, pad_mode=PAD_REFLECT,
-                                          fmt=None if last else fmt_b)
+            t, op_next, mrB = ops.norm_act_pad_stats(rawB, st, h4 * w4, IN, residual=t, want_dense=True, pad=1, pad_mode=PAD_REFLECT,
+                                                     fmt=None if last else fmt_b)
             blocks.append((op_t, rawA, mrA, opA, rawB, mrB))
             op_t = op_next
             if 12 + b in layers:
@@ -967,19 +958,25 @@ def _d_fwd(stages, norm, srcs, save, update_running=True, deferred=None):
             if upd and deferred is not None:
                 deferred.append((st, cnt, bn))
                 upd = False
-            mr = ops.stats_finalize(st, cnt, bn.eps if bn is not None else 1e-5,
-                                    bn.running_mean if upd else None, bn.running_var if upd else None,
-                                    bn.momentum if bn is not None else 0.1)
             if upd:
+                mr = ops.stats_finalize(st, cnt, bn.eps, bn.running_mean, bn.running_var, bn.momentum)
                 bn.num_batches_tracked += 1
-        if save:
-            saved.append((x_op, raw, mr, (h, w)))
         if si == len(stages) - 1:
+            if save:
+                saved.append((x_op, raw, mr, (h, w)))
             pred = raw
             break
         nxt = stages[si + 1][0]
-        _, x_op = ops.norm_act_pad(raw, mr, mode, bn.weight if bn is not None else None, bn.bias if bn is not None else None,
-                                   act, pad=2, pad_mode=PAD_ZERO, fmt=FMT_BF16X2 if nxt.use_tc else FMT_F32)
+        fmt_n = FMT_BF16X2 if nxt.use_tc else FMT_F32
+        gamma, beta = (bn.weight, bn.bias) if bn is not None else (None, None)
+        x_in = x_op
+        if mode != NORM_NONE and mr is None:     # statistics finalised inside the normalise / activate / pad pass
+            _, x_op, mr = ops.norm_act_pad_stats(raw, st, cnt, mode, gamma, beta, act, pad=2, pad_mode=PAD_ZERO, fmt=fmt_n,
+                                                 eps=bn.eps if bn is not None else 1e-5)
+        else:
+            _, x_op = ops.norm_act_pad(raw, mr, mode, gamma, beta, act, pad=2, pad_mode=PAD_ZERO, fmt=fmt_n)
+        if save:
+            saved.append((x_in, raw, mr, (h, w)))
         h, w = ho, wo
     return pred, dict(saved=saved, n=n)
 
@@ -1175,6 +1172,23 @@ class Linear(nn.Module):
         self._packs = {}
 
 
+def first_of_permutation(n, p):
+    """The first `p` entries of a uniformly random permutation of range(n) — what PatchSampleF draws with
+    `np.random.permutation(H * W)[:num_patches]` (networks.py:703-705) — in O(p) instead of O(n): Fisher-Yates from the front
+    (slot i swaps with a uniform j in [i, n)), keeping only the touched slots in a dict.  Same distribution (p distinct indices,
+    every ordered p-tuple equally likely), driven by the same legacy global NumPy stream (np.random.seed controls it); at
+    774 x 774 positions the full permutation costs ~8 ms of host time per layer per step, this ~0.1 ms."""
+    p = int(min(p, n))
+    js = np.arange(p) + np.floor(np.random.random_sample(p) * (n - np.arange(p))).astype(np.int64)
+    moved, out = {}, np.empty(p, dtype=np.int64)
+    for i in range(p):
+        j = int(js[i])
+        vi, vj = moved.get(i, i), moved.get(j, j)
+        out[i] = vj
+        moved[j] = vi
+    return out
+
+
 class PatchSampleF(_FlatParamsMixin, nn.Module):
     """PatchSampleF (networks.py:667-719): gather `num_patches` spatial positions (shared across the batch) from each
     feature map, optionally run them through a per-layer 2-layer MLP created on first use (netF='mlp_sample'), and
@@ -1257,8 +1271,7 @@ class PatchSampleF(_FlatParamsMixin, nn.Module):
             if patch_ids is not None:
                 patch_id = patch_ids[feat_id]
             else:
-                patch_id = np.random.permutation(H * W)
-                patch_id = patch_id[:int(min(num_patches, patch_id.shape[0]))]
+                patch_id = first_of_permutation(H * W, num_patches)
             host_ids = np.asarray(patch_id.cpu() if torch.is_tensor(patch_id) else patch_id)
             ids = torch.as_tensor(host_ids, dtype=torch.int32).to(feat.device)
             # features produced by our generators are NHWC in memory (NCHW views): no copy then

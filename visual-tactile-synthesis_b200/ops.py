@@ -192,6 +192,12 @@ def conv2d_dgrad_gather(dy, wg, stride, hp, wp):
     return dx
 
 
+def set_backward_terms(terms):
+    """2 (default): backward tensor-core launches drop one hi/lo cross term; 3: the forward's full three-term product."""
+    L.call("skit_set_backward_terms", int(terms))
+    L.launches -= 1     # not a kernel launch
+
+
 def conv2d_dgrad_s1(dy_op, w1):
     """Stride-1 input gradient on tcgen05: dy_op carries a zero halo of k-1; w1 = mode-1 pack -> dx NHWC fp32."""
     k = w1.k
@@ -257,6 +263,19 @@ def norm_act_pad(raw, mr=None, norm_mode=NORM_NONE, gamma=None, beta=None, act=A
     L.call("skit_norm_act_pad", _p(raw), n, h, w, c, _p(mr), norm_mode, _p(gamma), _p(beta), act, _p(residual), _p(dense),
            op.ref() if op is not None else None, pad, pad_mode, L.stream())
     return dense, op
+
+
+def norm_act_pad_stats(raw, stats, count, norm_mode, gamma=None, beta=None, act=ACT_NONE, residual=None,
+                       want_dense=False, pad=0, pad_mode=PAD_ZERO, fmt=None, eps=1e-5):
+    """norm_act_pad fed by the conv epilogue's fp64 (sum, sum of squares) directly: the statistics are finalised inside the
+    pass itself -> (dense or None, Operand or None, mean_rstd [groups, c, 2] for the backward)."""
+    n, h, w, c = raw.shape
+    dense = torch.empty_like(raw) if want_dense else None
+    op = Operand(n, h, w, c, pad, fmt, raw.device) if fmt is not None else None
+    mr = torch.empty((stats.shape[0], c, 2), dtype=torch.float32, device=raw.device)
+    L.call("skit_norm_act_pad_stats", _p(raw), n, h, w, c, _p(stats), float(count), eps, _p(mr), norm_mode, _p(gamma), _p(beta), act,
+           _p(residual), _p(dense), op.ref() if op is not None else None, 0, pad, pad_mode, L.stream())
+    return dense, op, mr
 
 
 def act_norm_bwd_reduce(shape, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None, raw=None, mr=None, norm_mode=NORM_NONE,

@@ -374,7 +374,7 @@ class SinSKITGModel:
                 if rand is not None and "nce_ids" in rand:
                     ids = np.asarray(rand["nce_ids"][li], dtype=np.int64)
                 else:
-                    ids = np.random.permutation(fh * fw)[:int(min(P, fh * fw))]
+                    ids = networks.first_of_permutation(fh * fw, P)
                 self._ids_count.append(len(ids))
                 hi[li, :len(ids)].copy_(torch.from_numpy(ids.astype(np.int32)))
             self._ids_dev.copy_(hi, non_blocking=True)
