@@ -136,7 +136,10 @@ def test_skitg_model_style_code_train_step_vs_oracle(graph):
     assert rel(m.fake_I, res["fake_I"]) < GATE and rel(m.fake_T, res["fake_T"]) < GATE
     for k, p in m.netG.named_parameters():
         if k in res["grads_G"]:
-            assert rel(p.grad, res["grads_G"][k]) < 3e-2, k
+            g_ref, wk = res["grads_G"][k], k.replace(".bias", ".weight")
+            if k.endswith(".bias") and wk in res["grads_G"] and g_ref.norm() < 1e-3 * res["grads_G"][wk].norm():
+                continue    # a conv bias feeding an InstanceNorm: mathematically zero, the reference holds rounding noise
+            assert rel(p.grad, g_ref) < 3e-2, k
         else:
             assert "style_code_mapping" in k and float(p.grad.abs().max()) == 0.0, k    # never used in 'tile' mode (A.1)
     # the next materials: the step (eager or captured-and-replayed) must read the CURRENT style code

@@ -427,6 +427,7 @@ int conv_head7_launch(const skit_operand* x, const skit_weights* w, int org, int
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_head7_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_head7_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_head7_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(conv_head7_kernel) failed: %s", cudaGetErrorString(e));
             return SKIT_ERR_CUDA;
@@ -435,7 +436,10 @@ int conv_head7_launch(const skit_operand* x, const skit_weights* w, int org, int
     }
     dim3 grid(cdiv(wo, T), cdiv(ho, T), x->n);
     const __nv_bfloat16 *wh = (const __nv_bfloat16*)w->hi, *wl = (const __nv_bfloat16*)w->lo;
-    if (w->co <= 5)
+    if (w->co == 1)     // single output channel: the stem's input gradient w.r.t. the sketch channel (PatchNCE query branch)
+        conv_head7_kernel<1><<<grid, 256, smem, st>>>((const float*)x->p0, (const __nv_bfloat16*)x->p0, (const __nv_bfloat16*)x->p1, x->fmt,
+                                                     x->hp, x->wp, x->c, org, wh, wl, w->ci, bias, y, ho, wo, w->co);
+    else if (w->co <= 5)
         conv_head7_kernel<5><<<grid, 256, smem, st>>>((const float*)x->p0, (const __nv_bfloat16*)x->p0, (const __nv_bfloat16*)x->p1, x->fmt,
                                                      x->hp, x->wp, x->c, org, wh, wl, w->ci, bias, y, ho, wo, w->co);
     else

@@ -238,7 +238,8 @@ def _conv_fwd(layer, x_op, org, ho, wo, stats_mode, with_bias=True):
 
 
 def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None,
-               gamma=None, beta=None, dgamma=None, dbeta=None, need_dgrad=True, need_wgrad=True, draw_add=None, dsum_out=None):
+               gamma=None, beta=None, dgamma=None, dbeta=None, need_dgrad=True, need_wgrad=True, draw_add=None, dsum_out=None,
+               dgrad_pack=None):
     """Backward of [conv -> norm -> act] given the gradient w.r.t. the activated output, either as
     a halo'd tensor `dpad` (gradient of the next conv's operand) and/or a dense `dadd`.
     Returns the gradient w.r.t. the conv's own haloed operand (NHWC fp32 [n, hp, wp, ci]) or None."""
@@ -272,6 +273,9 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
                                                   layer.bias.grad if want_db else None), (x_op, d_op))
     if not need_dgrad:
         return None
+    if dgrad_pack is not None:   # input gradient for a subset of the input channels only (thin mode-1 pack of a weight slice)
+        wp_in = x_op.wp + (layer.k - 1 if layer.fold_in_cp else 0)
+        return ops.conv2d_fwd(d_op, dgrad_pack, 1, 0, x_op.hp, wp_in)[0]
     if (tc or s2_only) and layer.stride == 2:
         return ops.conv2d_dgrad_s2(d_op, q, layer.pack(3), layer.k, ho, wo, x_op.hp, x_op.wp)
     if tc:
@@ -533,9 +537,13 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         ctx["blocks"] = blocks
         return feats, ctx
 
-    def encode_bwd(self, ctx, dfeats):
+    def encode_bwd(self, ctx, dfeats, input_channels=None):
         """dfeats: {layer: NHWC gradient of that tapped feature}.  Accumulates weight gradients and returns the gradient
-        w.r.t. the reflect-padded input operand, NHWC [n, S+6, S+6, input_nc] (or None if nothing reaches it)."""
+        w.r.t. the reflect-padded input operand, NHWC [n, S+6, S+6, input_nc] (or None if nothing reaches it).
+        input_channels = c: only the first c (<= 8) input channels' gradient is wanted (PatchNCE needs the sketch channel, not
+        the positional encoding): on the tensor-core configuration the stem's input gradient then runs as a 7x7, 64 -> c
+        convolution on the fp32 pipes (conv_head7_kernel) instead of an N = 16 MMA tile per 128 pixels, and a layer-0 tap
+        gradient is NOT folded in (the caller adds its channels itself)."""
         IN = NORM_INSTANCE
         n, S_h, S_w = ctx["dims"]
         h2, w2, h4, w4 = S_h // 2, S_w // 2, S_h // 4, S_w // 4
@@ -571,10 +579,16 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
             if da4 is not None or dfeats.get(4) is not None:
                 dpad1 = _stage_bwd(self._c4, ctx["op1"], ctx["raw4"], ctx["mr4"], IN, ACT_RELU, S_h * S_w, dadd=da4, draw_add=dfeats.get(4))
         dpad0 = None
+        thin = input_channels is not None and self._c1.use_tc and 0 < input_channels <= 8
         if top >= 1 and (dpad1 is not None or dfeats.get(1) is not None):
+            pk = None
+            if thin:   # per-step pack of the weight slice [co, :c, 7, 7] (two tiny launches; the weights moved since the last step)
+                pk = ops.PackedWeights(self._c1.weight.detach()[:, :input_channels].contiguous(), 1, want_f32=False, want_bf16=True)
             dpad0 = _stage_bwd(self._c1, ctx["op0"], ctx["raw1"], ctx["mr1"], IN, ACT_RELU, S_h * S_w, dpad=dpad1, pad=1,
-                               pad_mode=PAD_ZERO, need_dgrad=True, draw_add=dfeats.get(1))
+                               pad_mode=PAD_ZERO, need_dgrad=True, draw_add=dfeats.get(1), dgrad_pack=pk)
         _wgrad_join()
+        if thin:
+            return dpad0
         if dfeats.get(0) is not None:
             if dpad0 is None:
                 dpad0 = dfeats[0]

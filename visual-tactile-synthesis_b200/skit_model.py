@@ -178,7 +178,12 @@ class SinSKITGModel:
                 self.lpips = LPIPS(net="vgg").to(self.device)
                 if state is not None:
                     res = self.lpips.load_state_dict(state, strict=False)
-                    if res.missing_keys:
+                    # the ScalingLayer constants are buffers with fixed values and `lins.N` aliases `linN`: only a missing VGG16
+                    # conv or `linN` weight leaves part of the criterion randomly initialised
+                    missing = [k for k in res.missing_keys if not (k.startswith("scaling_layer.") or k.startswith("lins."))]
+                    if missing:
+                        res = argparse.Namespace(missing_keys=missing)
+                    if missing:
                         raise RuntimeError("opt.lpips_state does not cover the LPIPS-VGG16 parameters; missing keys: %s"
                                            % ", ".join(res.missing_keys[:8]))
                 self.lpips.refresh_packs_once()
@@ -498,7 +503,7 @@ class SinSKITGModel:
     def _fork(self, i):
         bs = getattr(self, "_bstreams", None)
         if bs is None:
-            bs = self._bstreams = [torch.cuda.Stream(device=self.device) for _ in range(6)]
+            bs = self._bstreams = [torch.cuda.Stream(device=self.device) for _ in range(7)]
         bs[i].wait_stream(torch.cuda.current_stream())
         return torch.cuda.stream(bs[i])
 
@@ -539,6 +544,7 @@ class SinSKITGModel:
                   D2_fake=L[8:8 + NT], D2_real=L[8 + NT:8 + 2 * NT], G2_GAN=L[8 + 2 * NT:8 + 3 * NT], D2_more=L[8 + 3 * NT:])
         D.zero_grad()
         D2.zero_grad()
+        G.zero_grad()        # before any branch: the PatchNCE query branch accumulates encoder weight gradients beside the D steps
         run_D, run_D2 = {}, {}
         more = opt.use_more_fakeT and NF
 
@@ -583,6 +589,13 @@ class SinSKITGModel:
                     lp["T"] = self.lpips.loss_and_grad(fake_T_p.transpose(0, 1).reshape(-1, 1, 32, 32), None,
                                                        gscale=opt.lambda_G2_lpips / n, real_feats=self._lp_real_T)
 
+        # ---- PatchNCE query branch (encoder forward + backward on the channel mean of fake_I): it needs only G's output and
+        #      G's (not yet updated) weights, so it runs beside both discriminator steps; its gradient w.r.t. the query sketch
+        #      (one channel) is folded into dI just before G's backward
+        if self.nce_layers:
+            with self._fork(6):
+                self._nce_dSq = self._nce_step(n)
+
         # ---- fake passes: D2 (patches) and D2 (random patches) beside D1 (full image)
         with self._fork(2):
             run_D2["fake"] = []
@@ -618,7 +631,6 @@ class SinSKITGModel:
             self._gan(pg2, -1.0, sl["G2_GAN"])
 
         # ---- G step (:680-694): GAN through the updated (frozen) D, L1, patch L1
-        G.zero_grad()
         pg, cg = D.fwd([self.real_S, fake_I])
         dpg = self._gan(pg, -1.0, sl["G_GAN"], opt.lambda_G1_GAN / n)
         dI = D.bwd(cg, dpg, need_wgrad=False, input_slice=(self.sketch_nc, 3))
@@ -641,7 +653,11 @@ class SinSKITGModel:
         dT = torch.zeros_like(fake_T)
         ops.patch_scatter_add(dTp, 0, 2, ox, oy, dT)
         if self.nce_layers:
-            self._nce_step(dI, n)
+            self._join(6)
+            if self._nce_dSq is not None:
+                ops.channel_mean_bwd(self._nce_dSq, dI)
+            self._nce_dSq = None
+            self._g_feats = None      # released on the launching stream, after the branch that read them has joined
         G.bwd(self._g_ctx, dI, dT)
         self._g_ctx = None
         self._join(1)
@@ -653,12 +669,13 @@ class SinSKITGModel:
         self._loss_raw = (L, NT, NF)
         return L
 
-    def _nce_step(self, dI, n):
+    def _nce_step(self, n):
         """CUT-style PatchNCE term (new wiring: PatchNCELoss / PatchSampleF are dead code in the reference).
         keys  = generator features of the input (sketch + positional encoding) at nce_layers — tapped from the main forward;
         query = the same encoder run on the 1-channel mean of the generated RGB image (+ the same positional encoding);
         loss  = lambda_NCE * mean_layers mean_patches PatchNCE(q, k);  its gradient flows into the encoder weights (query
-        pass) and, through the channel mean, into fake_I."""
+        pass) and, through the channel mean, into fake_I.  Returns dLoss/dSq ([n, 1, H, W]; the caller spreads it over the
+        three channels of dI with channel_mean_bwd) or None."""
         opt, G = self.opt, self.netG
         S_h, S_w = self.real_S.shape[2:]
         Sq = ops.channel_mean(self.fake_I)
@@ -686,12 +703,14 @@ class SinSKITGModel:
             loss_l, dq = ops.patchnce(q_pool, k_pool, b, opt.nce_T, want_grad=True, gscale=opt.lambda_NCE / (nl * rows))
             dfeats[l] = F_.sample_bwd(qctx, dq)
             chunks.append(loss_l)
-        dpad0 = G.encode_bwd(cq, dfeats)
+        dpad0 = G.encode_bwd(cq, dfeats, input_channels=1)      # only the query sketch channel carries a gradient (to fake_I)
+        dSq = None
         if dpad0 is not None:
             dSq = ops.operand_grad_to_nchw(dpad0, S_h, S_w, 3, ops.PAD_REFLECT, 0, 1)
-            ops.channel_mean_bwd(dSq, dI)
+        if dfeats.get(0) is not None and (dpad0 is None or dpad0.shape[3] == 1):   # the layer-0 tap is the padded input itself
+            dSq = ops.operand_grad_to_nchw(dfeats[0], S_h, S_w, 3, ops.PAD_REFLECT, 0, 1, dst=dSq, accumulate=dSq is not None)
         self._nce_losses = chunks
-        self._g_feats = None
+        return dSq
 
     def current_losses(self):
         """Device -> host read of the step's loss scalars, bare names (the reference does ~12 .item() syncs per step,
