@@ -759,9 +759,15 @@ int conv_tc_halo_dgrad_full(const skit_operand* d, const void* w_hi, const void*
     const int hi_ = H - 2, wi_ = W - 2;          // interior: outputs whose window holds at least ... every tap row/col may matter
     const long long int_tiles = (long long)cdiv(wi_, 8) * cdiv(hi_, 16) * d->n;
     const long long strip_tiles = (long long)(2 * cdiv(W, 8) + 2 * cdiv(hi_, 16)) * d->n;
-    const bool split = k == 3 && d->n == 1 && H > 18 && W > 10 && ci % 64 == 0 &&
-                       (full_tiles + 147) / 148 > (int_tiles + 147) / 148 &&                 // the interior saves a wave ...
-                       int_tiles + (strip_tiles + 2) / 3 <= ((int_tiles + 147) / 148) * 148;   // ... and the strips fit in its slack
+    // Cost in waves of 148 CTAs.  One region: ceil(full / 148).  Five regions: the interior's waves, plus — for the strips that do
+    // not fit into the slack of its last wave — a third of a wave per 148 of them (a strip runs one filter row / column: a third
+    // of the K loop).  Large maps (more than four waves) stay on the single-region path: it runs on the PERSISTENT kernel there
+    // (one CTA per SM, epilogues overlapped), which beats thousands of one-tile CTAs paying their set-up each.
+    const long long full_waves = (full_tiles + 147) / 148, int_waves = (int_tiles + 147) / 148;
+    const long long slack = int_waves * 148 - int_tiles;
+    const double split_cost = (double)int_waves + (strip_tiles > slack ? (double)((strip_tiles - slack + 147) / 148) / 3.0 : 0.0);
+    const bool split = k == 3 && d->n == 1 && H > 18 && W > 10 && ci % 64 == 0 && full_tiles <= 4 * 148 &&
+                       split_cost < (double)full_waves - 0.05;
     if (!split)
         return conv_tc_halo_launch(d, w_hi, w_lo, ci, co, k, k, k * k, 0, 0, H, W, nullptr, dx, nullptr, nullptr, SKIT_NORM_NONE, st);
     TcHaloP p{};

@@ -212,23 +212,34 @@ def _wgrad_async(fn, keep):
     ent = _WG.get(cur.cuda_stream)
     if ent is None:
         if len(_WG) > 64:      # every graph capture runs on a fresh stream: drop idle entries of streams long gone
-            for k in [k for k, v in _WG.items() if not v[1]]:
+            for k in [k for k, v in _WG.items() if not v[2]]:
                 del _WG[k]
-        ent = (torch.cuda.Stream(device=cur.device), [])
+        ent = [torch.cuda.Stream(device=cur.device), [], False]
         _WG[cur.cuda_stream] = ent
-    side, ka = ent
+    side, ka = ent[0], ent[1]
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         fn()
     ka.extend(keep)
+    ent[2] = True      # work is pending on the side stream since the last join
+
+
+def _wgrad_side_stream():
+    """The side stream carrying weight-gradient kernels launched from the current stream since its last join (or None)."""
+    ent = _WG.get(torch.cuda.current_stream().cuda_stream)
+    return ent[0] if ent is not None and ent[2] else None
 
 
 def _wgrad_join():
+    """Join only when something was launched since the last join: stream handles are recycled by the driver, so an entry may
+    belong to a stream that no longer exists — waiting on its (idle) side stream from inside a graph capture would be an
+    illegal dependency on uncaptured work."""
     cur = torch.cuda.current_stream()
     ent = _WG.get(cur.cuda_stream)
-    if ent is not None:
+    if ent is not None and ent[2]:
         cur.wait_stream(ent[0])
         ent[1].clear()
+        ent[2] = False
 
 
 # ----------------------------------------------------------------------------- shared conv stage helpers
@@ -417,7 +428,16 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         return {0, 1, 4, 8} | {12 + b for b in range(self.n_blocks)}
 
     # -- explicit backward: dI [n,3,h,w], dT [n,2,h,w] are gradients w.r.t. fake_I / fake_T (after *M).
-    def bwd(self, ctx, dI, dT):
+    def grad_split_offset(self, block):
+        """Offset (in elements of the flat buckets) of ResnetBlock `block`'s first parameter: everything from there on — the
+        later blocks, the up-convs and the head — has its final gradient once the backward pass has finished that block."""
+        first = next(self._blocks[block].parameters())
+        return (first.data_ptr() - self.flat_param.data_ptr()) // 4
+
+    def bwd(self, ctx, dI, dT, on_tail_done=None, tail_block=None):
+        """on_tail_done(offset): called once, right after ResnetBlock `tail_block` (and everything behind it) has been
+        processed: flat_grad[offset:] is final as soon as the weight-gradient side stream drains — the data-parallel step
+        starts that bucket's all-reduce there, beside the rest of the backward pass."""
         IN = NORM_INSTANCE
         n, S_h, S_w = ctx["dims"]
         h2, w2, h4, w4 = S_h // 2, S_w // 2, S_h // 4, S_w // 4
@@ -449,7 +469,7 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
         # per block: the output gradient dt feeds the conv branch and the skip; the next (earlier) block's output gradient is
         # fold(dpad_t) + dt, produced as a side output of that block's first norm-backward pass instead of a pass of its own
         pend = None   # dpad_t of the block processed before (the later block), not yet folded into dt
-        for blk, (op_t, rawA, mrA, opA, rawB, mrB) in zip(reversed(self._blocks), reversed(ctx["blocks"])):
+        for bi, blk, (op_t, rawA, mrA, opA, rawB, mrB) in zip(range(self.n_blocks - 1, -1, -1), reversed(self._blocks), reversed(ctx["blocks"])):
             ca, cb = blk.conv_block[1], blk.conv_block[5]
             if pend is None:
                 dpadA = _stage_bwd(cb, opA, rawB, mrB, IN, ACT_NONE, h4 * w4, dadd=dt)
@@ -458,6 +478,8 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
                 dpadA = _stage_bwd(cb, opA, rawB, mrB, IN, ACT_NONE, h4 * w4, dpad=pend, pad=1, pad_mode=PAD_REFLECT, dadd=dt, dsum_out=out)
                 dt = out[0]
             pend = _stage_bwd(ca, op_t, rawA, mrA, IN, ACT_RELU, h4 * w4, dpad=dpadA, pad=1, pad_mode=PAD_REFLECT)
+            if on_tail_done is not None and bi == tail_block:
+                on_tail_done(self.grad_split_offset(bi))
         if pend is not None:
             dt, _ = ops.act_norm_bwd_reduce(dt.shape, dpad=pend, pad=1, pad_mode=PAD_REFLECT, dadd=dt)
         da8 = ops.blur_down_bwd(dt, h2, w2)

@@ -196,6 +196,25 @@ def set_backward_terms(terms):
     """2 (default): backward tensor-core launches drop one hi/lo cross term; 3: the forward's full three-term product."""
     L.call("skit_set_backward_terms", int(terms))
     L.launches -= 1     # not a kernel launch
+    backward_terms.current = int(terms)
+
+
+class backward_terms:
+    """`with backward_terms(3): net.bwd(...)` — the launches issued inside use that backward precision (host-side switch read
+    at launch time, so it is safe with side streams and graph capture), the previous setting is restored on exit."""
+    current = 3 if __import__("os").environ.get("SKIT_BWD_TERMS", "2").startswith("3") else 2   # the library's own default
+
+    def __init__(self, terms):
+        self.terms = terms
+
+    def __enter__(self):
+        self.prev = backward_terms.current
+        if self.terms != self.prev:
+            set_backward_terms(self.terms)
+
+    def __exit__(self, *a):
+        if self.terms != self.prev:
+            set_backward_terms(self.prev)
 
 
 def conv2d_dgrad_s1(dy_op, w1):

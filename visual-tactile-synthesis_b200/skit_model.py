@@ -507,6 +507,11 @@ class SinSKITGModel:
         bs[i].wait_stream(torch.cuda.current_stream())
         return torch.cuda.stream(bs[i])
 
+    def _comm_stream(self):
+        if getattr(self, "_cstream", None) is None:
+            self._cstream = torch.cuda.Stream(device=self.device)
+        return self._cstream
+
     def _join(self, *idx):
         cur = torch.cuda.current_stream()
         for i in idx:
@@ -516,7 +521,11 @@ class SinSKITGModel:
         """One discriminator pass of a D step: forward, softplus GAN loss, full backward (weight gradients accumulate
         atomically into the net's flat bucket, so passes on parallel streams may overlap)."""
         preds, ctx = net.fwd(srcs, deferred=deferred)
-        net.bwd(ctx, self._gan(preds, sign, slot, gscale))
+        # the discriminators' OWN gradients keep the full three-term product: at step 1 Adam with beta1 = 0 moves every weight by
+        # lr * sign(g), and G_GAN / G2_GAN are evaluated through the discriminators right after that update — the cheaper
+        # two-term backward (ops.set_backward_terms) is for the generator's gradient, where nothing downstream amplifies it
+        with ops.backward_terms(3):
+            net.bwd(ctx, self._gan(preds, sign, slot, gscale))
         return preds
 
     def _step_body(self):
@@ -658,10 +667,32 @@ class SinSKITGModel:
                 ops.channel_mean_bwd(self._nce_dSq, dI)
             self._nce_dSq = None
             self._g_feats = None      # released on the launching stream, after the branch that read them has joined
-        G.bwd(self._g_ctx, dI, dT)
-        self._g_ctx = None
-        self._join(1)
-        self._allreduce(G)
+        if self.dist is not None and isinstance(G, networks.ResnetGenerator) and G.n_blocks >= 4:
+            # data parallel: the gradient bucket's tail (later ResnetBlocks, up-convs, head: about half of the 45.6 MB) is final
+            # half-way through the backward pass — its all-reduce starts there on a communication stream, beside the rest of the
+            # serial input-gradient chain; only the head of the bucket is reduced after the pass
+            split = {}
+
+            def tail_done(off):
+                comm = self._comm_stream()
+                comm.wait_stream(torch.cuda.current_stream())
+                side = networks._wgrad_side_stream()
+                if side is not None:
+                    comm.wait_stream(side)
+                with torch.cuda.stream(comm):
+                    self.dist.allreduce_grads(G.flat_grad[off:])
+                split["off"] = off
+
+            G.bwd(self._g_ctx, dI, dT, on_tail_done=tail_done, tail_block=G.n_blocks // 2)
+            self._g_ctx = None
+            self._join(1)
+            self.dist.allreduce_grads(G.flat_grad[:split["off"]])
+            torch.cuda.current_stream().wait_stream(self._comm_stream())
+        else:
+            G.bwd(self._g_ctx, dI, dT)
+            self._g_ctx = None
+            self._join(1)
+            self._allreduce(G)
         self._adam(G, 2)
         if self.nce_layers and self.netF.use_mlp:
             self._allreduce(self.netF)
