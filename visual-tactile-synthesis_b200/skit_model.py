@@ -521,11 +521,7 @@ class SinSKITGModel:
         """One discriminator pass of a D step: forward, softplus GAN loss, full backward (weight gradients accumulate
         atomically into the net's flat bucket, so passes on parallel streams may overlap)."""
         preds, ctx = net.fwd(srcs, deferred=deferred)
-        # the discriminators' OWN gradients keep the full three-term product: at step 1 Adam with beta1 = 0 moves every weight by
-        # lr * sign(g), and G_GAN / G2_GAN are evaluated through the discriminators right after that update — the cheaper
-        # two-term backward (ops.set_backward_terms) is for the generator's gradient, where nothing downstream amplifies it
-        with ops.backward_terms(3):
-            net.bwd(ctx, self._gan(preds, sign, slot, gscale))
+        net.bwd(ctx, self._gan(preds, sign, slot, gscale))
         return preds
 
     def _step_body(self):
