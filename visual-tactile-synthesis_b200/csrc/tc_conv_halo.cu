@@ -824,6 +824,16 @@ static bool trans_enabled() {
 static int pick_trans_shape(int pitch, int kh, int w_stage, int* a_plane, int* na, int* nw) {
     constexpr int MAX_SMEM = 227 * 1024;
     const int cand[2] = {32, 24};
+    // tuning aid: SKIT_TRANS_TY / SKIT_TRANS_NA force a shape (tools/bench_trans.py sweeps them)
+    const char* ety = getenv("SKIT_TRANS_TY");
+    const char* ena = getenv("SKIT_TRANS_NA");
+    if (ety && ena) {
+        const int TY = atoi(ety), fna = atoi(ena);
+        const int ap = ((pitch * (TY + kh - 1) * 128 + 1023) / 1024) * 1024;
+        int n = (MAX_SMEM - (fna * 2 * ap + 2048)) / w_stage;
+        if (n > 6) n = 6;
+        if ((TY == 16 || TY == 24 || TY == 32) && (fna == 1 || fna == 2) && n >= 2) { *a_plane = ap; *na = fna; *nw = n; return TY; }
+    }
     for (int want_na = 2; want_na >= 1; want_na--)
         for (int i = 0; i < 2; i++) {
             const int TY = cand[i];
