@@ -236,8 +236,13 @@ def _ncu_field(size, field):
     for rnd in ("r02", "r01"):
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "%s_conv_tc_halo_fwd%d.json" % (rnd, size))))
-            if prof.get(field) is not None:
-                return prof[field], "%s_conv_tc_halo_fwd%d.json" % (rnd, size)
+            nested = {"tensor_pipe_pct_elapsed": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                      "tensor_pipe_pct_active": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"}.get(field)
+            val = prof.get(field)
+            if val is None and nested in prof:
+                val = float(str(prof[nested]["value"]).replace(",", ""))
+            if val is not None:
+                return val, "%s_conv_tc_halo_fwd%d.json" % (rnd, size)
         except Exception:
             pass
     return None, None

@@ -32,6 +32,10 @@ for k in want:
 if "dram__bytes_read.sum" in col:
     js["dram_bytes_per_launch"] = to_bytes(*col["dram__bytes_read.sum"]) + to_bytes(*col["dram__bytes_write.sum"])
     txt.append("dram bytes per launch (read + write): %.3e" % js["dram_bytes_per_launch"])
+for short, key in (("tensor_pipe_pct_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                   ("tensor_pipe_pct_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")):
+    if key in col:
+        js[short] = float(col[key][1].replace(",", ""))
 open(out + ".txt", "w").write("\n".join(txt) + "\n")
 json.dump(js, open(out + ".json", "w"), indent=1)
 print("\n".join(txt))
