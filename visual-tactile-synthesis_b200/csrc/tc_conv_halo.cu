@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(128, 1)
 conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcHaloP p) {
     constexpr int W_PLANE = BN * 128;       // BN rows x 64 channels x 2 B
-    constexpr int W_STAGE = 2 * W_PLANE;
+    // a two-term launch stages the hi plane only: half-size stages, twice as many of them — the bytes in flight per SM (stages x
+    // stage size against ~1.7 us of L2 latency under load), not the MMA rate, bound the two-term kernel with two 64 KB stages
+    const int W_STAGE = p.terms == 2 ? W_PLANE : 2 * W_PLANE;
     constexpr int TCOLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -324,11 +326,11 @@ __global__ void __launch_bounds__(256, 1)
 conv_tc_halo_persist_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmW_hi,
                             const __grid_constant__ CUtensorMap tmW_lo, const TcPersistP pp) {
     constexpr int W_PLANE = BN * 128;
-    constexpr int W_STAGE = 2 * W_PLANE;
     constexpr int TCOLS = BN < 32 ? 32 : BN;
     constexpr int STG = 36;
     constexpr int EPI_BYTES = 4 * 32 * STG * 4 + 4 * TCOLS * 2 * 4;   // staging tiles + statistics scratch of the 4 epilogue warps
     const TcHaloP& p = pp.h;
+    const int W_STAGE = p.terms == 2 ? W_PLANE : 2 * W_PLANE;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
@@ -562,7 +564,7 @@ conv_tc_halo_persist_kernel(const __grid_constant__ AMaps tmA, const __grid_cons
 
 template <int BN>
 static int launch_halo_persist(const AMaps& amaps, const CUtensorMap& w_hi, const CUtensorMap& w_lo, TcPersistP& pp, cudaStream_t st) {
-    constexpr int W_STAGE = 2 * BN * 128;
+    const int W_STAGE = (pp.h.terms == 2 ? 1 : 2) * BN * 128;
     constexpr int TCOLS = BN < 32 ? 32 : BN;
     constexpr int EPI_BYTES = 4 * 32 * 36 * 4 + 4 * TCOLS * 2 * 4;
     constexpr int MAX_SMEM = 227 * 1024;
@@ -890,7 +892,7 @@ int encode_bf16_map_sw(CUtensorMap* m, const void* base, int rank, const uint64_
 
 template <int BN>
 static int launch_halo(const AMaps& amaps, const CUtensorMap& w_hi, const CUtensorMap& w_lo, TcHaloP& p, dim3 grid, cudaStream_t st) {
-    constexpr int W_STAGE = 2 * BN * 128;
+    const int W_STAGE = (p.terms == 2 ? 1 : 2) * BN * 128;
     constexpr int MAX_SMEM = 227 * 1024;
     // two activation stages unless a large halo tile would squeeze the weight ring below two stages (k4 with BN = 256)
     p.na = (MAX_SMEM - (NA_MAX * 2 * p.a_plane + 1024 + 512)) / W_STAGE >= 2 ? NA_MAX : 1;

@@ -26,13 +26,14 @@ struct TcWgradP {
     int x_org, x_stride, d_org, d_org_y;   // d_org: gradient-side column origin; d_org_y: its row origin
     int Mdim, Ndim;        // channel counts of the M / N side
     float* out;            // [tap][Ndim][Mdim] fp32 partial sums (zeroed by the caller)
-    int skip;              // two-term product: 1 = the M operand's lo plane is neither loaded nor multiplied, 2 = the N operand's; 0 = all three terms
+    int skip;              // two-term product: 2 = the N operand's lo plane is neither loaded, staged nor multiplied; 0 = all three terms
+    int stages;            // pipeline depth: what fits 227 KB (a two-term stage is N_BYTES smaller, so one more stage is in flight)
 };
 
 constexpr int PIX = 64;               // pixels per K stage (8x8 box)
 constexpr int BOX_BYTES = PIX * 128;  // 64 pixels x 64 bf16
 
-template <int BN, int STAGES>
+template <int BN, int STAGES_UNUSED>
 __global__ void __launch_bounds__(128, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
                 const __grid_constant__ CUtensorMap tmN_hi, const __grid_constant__ CUtensorMap tmN_lo, TcWgradP p) {
@@ -40,7 +41,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
     constexpr int NBOX = BN >= 64 ? BN / 64 : 1;    // a thin N side (<= 16 channels) still lands as one 64-channel box, zero-filled
     constexpr int N_BYTES = NBOX * BOX_BYTES;
     constexpr int TCOLS = BN < 32 ? 32 : BN;
-    constexpr int STAGE_BYTES = 2 * M_BYTES + 2 * N_BYTES;
+    const int STAGES = p.stages;
+    const int STAGE_BYTES = 2 * M_BYTES + (p.skip == 2 ? 1 : 2) * N_BYTES;      // [M hi][M lo][N hi]([N lo])
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
@@ -81,7 +83,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
             for (int it = 0; it < num_it; it++) {
                 const int s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), STAGE_BYTES - (p.skip == 1 ? M_BYTES : p.skip == 2 ? N_BYTES : 0));
+                mbar_expect_tx(full_bar(s), STAGE_BYTES);
                 const int t = t_beg + it;
                 const int img = t / tpi, r = t - img * tpi;
                 const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
@@ -93,7 +95,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
 #pragma unroll
                 for (int g = 0; g < 2; g++) {
                     tma_load_4d(sa + g * BOX_BYTES, &tmM_hi, full_bar(s), mt * 128 + g * 64, mx, my, img);
-                    if (p.skip != 1) tma_load_4d(sa + M_BYTES + g * BOX_BYTES, &tmM_lo, full_bar(s), mt * 128 + g * 64, mx, my, img);
+                    tma_load_4d(sa + M_BYTES + g * BOX_BYTES, &tmM_lo, full_bar(s), mt * 128 + g * 64, mx, my, img);
                 }
 #pragma unroll
                 for (int g = 0; g < NBOX; g++) {
@@ -117,7 +119,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
                     const uint64_t n_hi = make_desc(sa + 2 * M_BYTES + ko, BOX_BYTES, 1024);
                     const uint64_t n_lo = make_desc(sa + 2 * M_BYTES + N_BYTES + ko, BOX_BYTES, 1024);
                     mma_bf16(tmem_base, m_hi, n_hi, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                    if (p.skip != 1) mma_bf16(tmem_base, m_lo, n_hi, idesc, 1u);
+                    mma_bf16(tmem_base, m_lo, n_hi, idesc, 1u);
                     if (p.skip != 2) mma_bf16(tmem_base, m_hi, n_lo, idesc, 1u);
                 }
                 mma_commit(empty_bar(s));
@@ -152,11 +154,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
 
 template <int BN, int STAGES>
 static int launch_wgrad_tc(const CUtensorMap& m_hi, const CUtensorMap& m_lo, const CUtensorMap& n_hi, const CUtensorMap& n_lo,
-                           const TcWgradP& p, dim3 grid, cudaStream_t st) {
-    constexpr int SMEM = STAGES * (4 * BOX_BYTES + 2 * (BN >= 64 ? BN / 64 : 1) * BOX_BYTES) + 1024 + 256;
+                           TcWgradP& p, dim3 grid, cudaStream_t st) {
+    constexpr int MAX_SMEM = 227 * 1024;
+    const int stage_bytes = 4 * BOX_BYTES + (p.skip == 2 ? 1 : 2) * (BN >= 64 ? BN / 64 : 1) * BOX_BYTES;
+    int stages = (MAX_SMEM - 1024 - 256) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < STAGES) stages = STAGES;      // the three-term depth always fits
+    p.stages = stages;
+    const int SMEM = stages * stage_bytes + 1024 + 256;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(wgrad_tc_kernel<%d>) failed: %s", BN, cudaGetErrorString(e));
             return SKIT_ERR_CUDA;
@@ -210,7 +218,7 @@ int wgrad_tc(const skit_operand* x, int org, const skit_operand* dy, int dy_org,
     p.Mdim = p.m_is_x ? ci : co;
     p.Ndim = p.m_is_x ? co : ci;
     p.out = partial;
-    p.skip = bwd_terms() == 2 ? (p.m_is_x ? 2 : 1) : 0;     // drop the GRADIENT operand's lo plane: dW = (x_hi + x_lo) * dy_hi
+    p.skip = bwd_terms() == 2 ? 2 : 0;     // two-term: the N-side operand (the wider box set) enters as its hi plane only
     *layout = p.m_is_x;
     const int BN = (p.Ndim % 256 == 0) ? 256 : (p.Ndim % 128 == 0) ? 128 : (p.Ndim % 64 == 0) ? 64 : 16;
     const int mtiles = cdiv(p.Mdim, 128), ntiles = cdiv(p.Ndim, BN);
