@@ -16,7 +16,7 @@ def worker(size):
     import vts_b200  # noqa: F401
     from vts_b200 import ops
     from tools.bench_conv import timeit
-    for ci, co, k, s in ((64, 128, 3, size), (128, 64, 3, size), (256, 128, 3, size // 2), (64, 64, 7, size)):
+    for ci, co, k, s in ((256, 256, 3, size // 4), (64, 128, 3, size), (128, 64, 3, size), (256, 128, 3, size // 2), (128, 256, 3, size // 2)):
         x = torch.randn(1, s, s, ci, device="cuda")
         w = torch.randn(co, ci, 3 if k == 7 else k, 3 if k == 7 else k, device="cuda") / math.sqrt(ci * 9)
         kk = 3 if k == 7 else k
@@ -38,7 +38,6 @@ if __name__ == "__main__":
         worker(int(sys.argv[2]))
         sys.exit(0)
     size = sys.argv[1] if len(sys.argv) > 1 else "768"
-    for env in ({"SKIT_TC_TRANS": "0"}, {}, {"SKIT_TRANS_TY": "32", "SKIT_TRANS_NA": "1"}, {"SKIT_TRANS_TY": "24", "SKIT_TRANS_NA": "2"},
-                {"SKIT_TRANS_TY": "24", "SKIT_TRANS_NA": "1"}, {"SKIT_TRANS_TY": "16", "SKIT_TRANS_NA": "2"}):
+    for env in ({"SKIT_TC_TRANS": "0"}, {}, {"SKIT_DGRAD_SPLIT": "0"}, {"SKIT_TRANS_TY": "24", "SKIT_TRANS_NA": "2"}):
         print(env or "default", flush=True)
         subprocess.run([sys.executable, __file__, "--worker", size], env=dict(os.environ, **env))

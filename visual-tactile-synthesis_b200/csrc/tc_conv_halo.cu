@@ -836,8 +836,8 @@ static int pick_trans_shape(int pitch, int kh, int w_stage, int* a_plane, int* n
         if (n > 6) n = 6;
         if ((TY == 16 || TY == 24 || TY == 32) && (fna == 1 || fna == 2) && n >= 2) { *a_plane = ap; *na = fna; *nw = n; return TY; }
     }
-    for (int want_na = 2; want_na >= 1; want_na--)
-        for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 2; i++)
+        for (int want_na = 2; want_na >= 1; want_na--) {      // N = 256 first (measured never slower than N = 192), two activation stages if they fit
             const int TY = cand[i];
             const int ap = ((pitch * (TY + kh - 1) * 128 + 1023) / 1024) * 1024;
             const int fixed = want_na * 2 * ap + 1024 + 1024;
@@ -998,19 +998,23 @@ int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_l
     R.org_y = org; R.org_x = org; R.ho = ho; R.wo = wo; R.tiles_x = cdiv(wo, 8); R.ooy = 0; R.oox = 0; R.amap = 0;
     R.pitch = 8 + kw - 1; R.a_rows = R.pitch * (16 + kh - 1);
     p.a_plane = ((R.a_rows * 128 + 1023) / 1024) * 1024;
-    if (trans_enabled() && co >= 32 && co <= 128 && !p.dbg) {
-        // at most 128 output channels: channels on M, 192 / 256 pixels on N (conv_tc_halo_t_kernel) when the map fills the SMs
+    if (trans_enabled() && co >= 32 && (co <= 128 || (co <= 512 && co % 128 == 0)) && !p.dbg) {
+        // channels on M (tiles of 128), 192 / 256 pixels on N (conv_tc_halo_t_kernel) when the map fills the SMs.  For 256 / 512
+        // output channels this is the same MMA work as the pixel-major N = 256 kernel, but a unit streams only its 128 filter rows:
+        // half the L2 -> shared-memory filter traffic per pixel, which is what bounds the pixel-major kernel (ncu: 732 MB of
+        // xbar2l1tex reads per launch at 768x768, tensor pipe 66 % of elapsed)
         TcTransP pp{};
         const int w_stage = (p.terms == 2 ? 1 : 2) * 128 * 128;
         int ap = 0, na = 0, nw = 0;
         const int TY = pick_trans_shape(R.pitch, kh, w_stage, &ap, &na, &nw);
         const long long tiles_t = TY ? (long long)R.tiles_x * cdiv(ho, TY) : 0;
-        if (TY && tiles_t * x->n >= 148 && tiles_t * x->n < (1ll << 30)) {
+        const int mtiles = cdiv(co, 128);
+        if (TY && tiles_t * x->n * mtiles >= 120 && tiles_t * x->n * mtiles < (1ll << 30)) {
             pp.h = p;
             pp.h.a_plane = ap; pp.h.na = na; pp.h.nw = nw;
             pp.h.reg[0].a_rows = R.pitch * (TY + kh - 1);
             pp.ty_rows = TY; pp.w_stage = w_stage;
-            pp.tiles = (int)tiles_t; pp.mtiles = 1; pp.n_img = x->n; pp.units = (int)(tiles_t * x->n);
+            pp.tiles = (int)tiles_t; pp.mtiles = mtiles; pp.n_img = x->n; pp.units = (int)(tiles_t * x->n * mtiles);
             AMaps amt;
             CUtensorMap t_hi, t_lo;
             int rc = encode_a_maps(&amt, 0, x, R.pitch, TY + kh - 1);
@@ -1067,7 +1071,9 @@ int conv_tc_halo_dgrad_full(const skit_operand* d, const void* w_hi, const void*
     const long long full_waves = (full_tiles + 147) / 148, int_waves = (int_tiles + 147) / 148;
     const long long slack = int_waves * 148 - int_tiles;
     const double split_cost = (double)int_waves + (strip_tiles > slack ? (double)((strip_tiles - slack + 147) / 148) / 3.0 : 0.0);
-    const bool split = k == 3 && d->n == 1 && H > 18 && W > 10 && ci % 64 == 0 && full_tiles <= 4 * 148 &&
+    static int split_on = -1;      // SKIT_DGRAD_SPLIT=0: always the single-region launch (-> pixels-on-N kernel), for A/B timing
+    if (split_on < 0) { const char* e = getenv("SKIT_DGRAD_SPLIT"); split_on = (e && e[0] == '0') ? 0 : 1; }
+    const bool split = split_on && k == 3 && d->n == 1 && H > 18 && W > 10 && ci % 64 == 0 && full_tiles <= 4 * 148 &&
                        split_cost < (double)full_waves - 0.05;
     if (!split)
         return conv_tc_halo_launch(d, w_hi, w_lo, ci, co, k, k, k * k, 0, 0, H, W, nullptr, dx, nullptr, nullptr, SKIT_NORM_NONE, st);
