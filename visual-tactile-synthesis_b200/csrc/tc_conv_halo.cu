@@ -998,11 +998,13 @@ int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_l
     R.org_y = org; R.org_x = org; R.ho = ho; R.wo = wo; R.tiles_x = cdiv(wo, 8); R.ooy = 0; R.oox = 0; R.amap = 0;
     R.pitch = 8 + kw - 1; R.a_rows = R.pitch * (16 + kh - 1);
     p.a_plane = ((R.a_rows * 128 + 1023) / 1024) * 1024;
-    if (trans_enabled() && co >= 32 && (co <= 128 || (co <= 512 && co % 128 == 0)) && !p.dbg) {
+    const long long pm_tiles = (long long)R.tiles_x * cdiv(ho, 16) * x->n;      // tiles of the pixel-major kernels
+    if (trans_enabled() && co >= 32 && (co <= 128 || (co <= 512 && co % 128 == 0 && pm_tiles >= 4 * 148)) && !p.dbg) {
         // channels on M (tiles of 128), 192 / 256 pixels on N (conv_tc_halo_t_kernel) when the map fills the SMs.  For 256 / 512
-        // output channels this is the same MMA work as the pixel-major N = 256 kernel, but a unit streams only its 128 filter rows:
-        // half the L2 -> shared-memory filter traffic per pixel, which is what bounds the pixel-major kernel (ncu: 732 MB of
-        // xbar2l1tex reads per launch at 768x768, tensor pipe 66 % of elapsed)
+        // output channels it is the same MMA work as the pixel-major N = 256 kernel with half the filter streaming per pixel (a
+        // unit streams only its 128 filter rows); measured (tools/bench_trans.py, 768x768 step): 128 -> 256 at 384x384 208 -> 194 us,
+        // its input gradient 247 -> 170 us, but the 256 -> 256 trunk at 192x192 (two waves of pixel-major tiles) 88 -> 94 us: only
+        // maps of four waves or more take this path above 128 channels
         TcTransP pp{};
         const int w_stage = (p.terms == 2 ? 1 : 2) * 128 * 128;
         int ap = 0, na = 0, nw = 0;
