@@ -433,6 +433,23 @@ int skit_maxpool2_bwd(const float* f, const float* dpool, int n, int h, int w, i
 int skit_lpips_layer(const float* f0, const float* f1, const float* lin_w, int n, int h, int w, int c, float gscale,
                      float* loss, float* df0, void* stream);
 
+/* ---- Evaluation metrics (models/model_utils.py:431-561 compute_evaluation_metric).  Device-side
+ * reductions into fp64 / fp32 scalars the caller zero-initialises (minmax: {+inf, -inf}); nothing synchronises.
+ *   skit_metric_minmax        out2 = {min(x), max(x)}: the real image's range for the [0, 1] rescale (:483-487)
+ *   skit_metric_sq_err        out += sum (a' - b')^2;  minmax != NULL: a' = (a - lo)/(hi - lo), b' = clamp((b - lo)/(hi - lo), 0, 1)
+ *                             (PSNR, :494-495); else clamp_b: b' = clamp(b, 0, 1) (T_MSE, :520,553-555)
+ *   skit_metric_ssim          out += sum of the SSIM index map (11x11 Gaussian, sigma 1.5, k1 0.01, k2 0.03, reflect pad 5, border of 5
+ *                             dropped: torchmetrics functional/image/ssim.py, the pip package behind `SSIM` at :497-498) over `planes`
+ *                             contiguous h x w planes; same rescale as above when minmax is given
+ *   skit_metric_normal_angle  out += sum over pixels of the angle in degrees between F.normalize([gx, gy, scale_nz]) of the two touch
+ *                             maps [n][2][h][w] (model_utils.py:418-425 + models/normal_losses.py:10-33, mode 'evaluate') */
+int skit_metric_minmax(const float* x, long long n, float* out2, void* stream);
+int skit_metric_sq_err(const float* a, const float* b, long long n, const float* minmax, int clamp_b, double* out, void* stream);
+int skit_metric_ssim(const float* a, const float* b, int planes, int h, int w, const float* minmax, float data_range,
+                     double* out, void* stream);
+int skit_metric_normal_angle(const float* real, const float* fake, int n, int h, int w, float scale_nz, int clamp_fake,
+                             double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -413,9 +413,30 @@ def make_step(tag, S, NT, NF, extra):
         os.chdir(cwd)
 
 
+def make_metrics():
+    """The evaluation metrics that are the reference's OWN code: the surface-normal angle error (models/normal_losses.py on
+    model_utils.compute_normal, as compute_evaluation_metric calls it, model_utils.py:531-536) and the clamped touch MSE
+    (:520,553-555), on seeded touch patches.  PSNR / SSIM are torchmetrics functions (absent): no fixture."""
+    load_reference()
+    with quiet():
+        from models.model_utils import compute_normal
+        from models.normal_losses import compute_surface_normal_angle_error
+    g = torch.Generator().manual_seed(21)
+    real_T = torch.rand(6, 2, 32, 32, generator=g)
+    fake_T = torch.rand(6, 2, 32, 32, generator=g) * 1.4 - 0.2          # leaves [0, 1]: exercises the clamp
+    fc = torch.clamp(fake_T, 0, 1)
+    ae = compute_surface_normal_angle_error(compute_normal(real_T, scale_nz=1), compute_normal(fc, scale_nz=1), mode="evaluate").mean()
+    mse = torch.mean((real_T - fc) ** 2)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), real_T=real_T.numpy(), fake_T=fake_T.numpy(), T_AE=np.float64(ae.item()),
+                        T_MSE=np.float64(mse.item()))
+    print("metrics.npz: T_AE %.6f deg, T_MSE %.6f" % (ae.item(), mse.item()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["networks", "ops", "step", "stylegan2", "options", "step_lpips"]
+    which = sys.argv[1:] or ["networks", "ops", "step", "stylegan2", "options", "step_lpips", "metrics"]
+    if "metrics" in which:
+        make_metrics()
     if "options" in which:
         make_options()
     if "step_lpips" in which:

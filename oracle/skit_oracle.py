@@ -801,6 +801,55 @@ def step_inputs_from_batch(b, device=None):
     return d
 
 
+# --------------------------------------------------------------------------- evaluation metrics (models/model_utils.py:431-561)
+def normal_angle_error_deg(real_T, fake_T, scale_nz=1.0):
+    """compute_surface_normal_angle_error(compute_normal(real), compute_normal(fake), mode='evaluate').mean()
+    (models/normal_losses.py:10-33 on models/model_utils.py:418-425): cosine similarity (eps 1e-6) of the unit normals, clamped,
+    acos in degrees.  Pinned by tests/golden/metrics.npz (the reference's own functions)."""
+    rn, fn = compute_normal(real_T, scale_nz), compute_normal(fake_T, scale_nz)
+    c = F.cosine_similarity(fn, rn, dim=1, eps=1e-6).clamp(-1.0, 1.0)
+    return (torch.acos(c) * 180.0 / math.pi).mean()
+
+
+def _gauss11(sigma=1.5):
+    d = torch.arange(11, dtype=torch.float32) - 5
+    g = torch.exp(-(d / sigma) ** 2 / 2)
+    return g / g.sum()
+
+
+def ssim_torchmetrics(preds, target, data_range=1.0, k1=0.01, k2=0.03):
+    """torchmetrics.functional.structural_similarity_index_measure(preds, target, data_range=...) with its defaults (Gaussian
+    11x11, sigma 1.5, reduction 'elementwise_mean'), restated from torchmetrics 0.11 functional/image/ssim.py: reflect pad 5,
+    depthwise valid conv of (p, t, p*p, t*t, p*t), SSIM index map, its 5-pixel border dropped, mean.  torchmetrics is a pip
+    dependency of the reference (requirements.txt:18, unpinned) that is not installed here: PARITY UNPINNED."""
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    B, C = preds.shape[:2]
+    g = _gauss11().to(preds)
+    k = (g[:, None] * g[None, :])[None, None].repeat(C, 1, 1, 1)
+    p, t = F.pad(preds, (5, 5, 5, 5), mode="reflect"), F.pad(target, (5, 5, 5, 5), mode="reflect")
+    o = F.conv2d(torch.cat([p, t, p * p, t * t, p * t]), k, groups=C)
+    mp, mt, pp_, tt, pt = o.split(B)
+    sp, st_, spt = pp_ - mp * mp, tt - mt * mt, pt - mp * mt
+    idx = ((2 * mp * mt + c1) * (2 * spt + c2)) / ((mp * mp + mt * mt + c1) * (sp + st_ + c2))
+    return idx[..., 5:-5, 5:-5].reshape(B, -1).mean(-1).mean()
+
+
+def psnr_torchmetrics(preds, target, data_range=1.0):
+    """torchmetrics.functional.peak_signal_noise_ratio(preds, target, data_range): 10 log10(data_range^2 / mean squared error).
+    PARITY UNPINNED (see ssim_torchmetrics)."""
+    return 10.0 * torch.log10(data_range ** 2 / ((preds - target) ** 2).mean())
+
+
+def evaluation_metrics(real_I, fake_I, real_T, fake_T):
+    """The I_PSNR / I_SSIM / T_AE / T_MSE part of compute_evaluation_metric (models/model_utils.py:483-498, 519-555)."""
+    lo, hi = real_I.min(), real_I.max()
+    r = (real_I - lo) / (hi - lo)
+    f = ((fake_I - lo) / (hi - lo)).clamp(0, 1)
+    fT = fake_T.clamp(0, 1)
+    return dict(I_PSNR=psnr_torchmetrics(r, f).item(), I_SSIM=ssim_torchmetrics(r, f).item(),
+                T_AE=normal_angle_error_deg(real_T, fT, 1.0).item(), T_MSE=((real_T - fT) ** 2).mean().item())
+
+
 # --------------------------------------------------------------------------- stand-alone initial weights
 def _xavier(shape, gen, gain=0.02):
     """init.xavier_normal_(w, gain) for a conv / linear weight (models/networks.py:204-222: gain 0.02, bias 0)."""

@@ -52,7 +52,13 @@ def test_train_loop_body_and_test_loop_of_the_reference(tmp_path):
         model.set_input(dataset[0], phase="val", verbose=False)
         model.test()
         assert model.get_image_paths() == ["syn.png"]
-        assert model.get_current_metrics() == {}
+        if epoch == opt.epoch_count:
+            assert model.get_current_metrics() == {}
+        res = model.compute_current_metrics()          # what the reference computes inside get_current_visuals
+        assert set(res) == {"metric_I_PSNR", "metric_I_SSIM", "metric_T_AE", "metric_T_MSE"}     # validation phase: no 'train_' prefix
+        mets = model.get_current_metrics()
+        assert {"m_I_PSNR", "m_I_SSIM", "m_T_AE", "m_T_MSE"} <= set(mets) and all(np.isfinite(v) for v in mets.values())
+        assert 0.0 < mets["m_I_SSIM"] < 1.0 and 0.0 <= mets["m_T_AE"] <= 180.0
         model.save_networks(epoch)
         model.update_learning_rate()
         # LambdaLR after k steps: lambda_rule(k) (networks.py:161-165)

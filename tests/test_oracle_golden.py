@@ -275,3 +275,22 @@ def test_standalone_init_tables_match_reference_keys_and_shapes(golden_dir):
     assert abs(float(w.std()) - 0.02 * math.sqrt(2.0 / (2 * 256 * 9))) < 2e-6 and float(sd["model.12.conv_block.1.bias"].abs().max()) == 0.0
     y = O.resnet_g_forward(sd, torch.rand(1, 9, 32, 32) * 2 - 1)
     assert y.shape == (1, 5, 32, 32) and torch.isfinite(y).all()
+
+
+def test_evaluation_metrics_oracle(golden_dir):
+    """T_AE / T_MSE restatements against the reference's own functions (tests/golden/metrics.npz); the torchmetrics restatements
+    (PSNR, SSIM: parity unpinned, the package is absent) against their defining properties."""
+    z = np.load(os.path.join(golden_dir, "metrics.npz"))
+    rT, fT = torch.from_numpy(z["real_T"]), torch.from_numpy(z["fake_T"])
+    assert abs(O.normal_angle_error_deg(rT, fT.clamp(0, 1), 1.0).item() - float(z["T_AE"])) < 1e-4
+    g = torch.Generator().manual_seed(1)
+    a = torch.rand(2, 3, 40, 48, generator=g)
+    b = (a + 0.05 * torch.randn(a.shape, generator=g)).clamp(0, 1)
+    assert abs(O.ssim_torchmetrics(a, a).item() - 1.0) < 1e-6 and 0.3 < O.ssim_torchmetrics(a, b).item() < 0.999
+    assert abs(O.ssim_torchmetrics(a, b).item() - O.ssim_torchmetrics(b, a).item()) < 1e-6          # symmetric
+    assert abs(O.psnr_torchmetrics(a, b).item() - 10 * math.log10(1.0 / ((a - b) ** 2).mean().item())) < 1e-4
+    m = O.evaluation_metrics(a * 2 - 1, b * 2 - 1, rT, fT)
+    assert abs(m["T_MSE"] - float(z["T_MSE"])) < 1e-7 and abs(m["T_AE"] - float(z["T_AE"])) < 1e-4
+    # the min-max rescale uses the REAL image's range (model_utils.py:483-487): an affine change of both images is undone
+    m2 = O.evaluation_metrics((a * 2 - 1) * 3 + 1, (b * 2 - 1) * 3 + 1, rT, fT)
+    assert abs(m2["I_PSNR"] - m["I_PSNR"]) < 1e-3 and abs(m2["I_SSIM"] - m["I_SSIM"]) < 1e-5

@@ -11,8 +11,9 @@ repo root registers this package under that name).  Layout:
   model_utils.py get_patch_in_input / find_coords_for_patch / compute_normal (reference: models/model_utils.py)
   skit_model.py SinSKITGModel / SKITGModel train step + forward           (reference: models/{sinskitG,skitG}_model.py)
   dist.py       one-process-per-GPU data parallel: flat gradient buckets + NCCL all-reduce
+  eval_metrics.py compute_evaluation_metric: PSNR / SSIM / angle error / MSE reductions    (reference: models/model_utils.py:431-561)
 """
-from . import _lib, ops, networks, model_utils, patchnce, skit_model, dist, sg2_generator, lpips_vgg  # noqa: F401
+from . import _lib, ops, networks, model_utils, patchnce, skit_model, dist, sg2_generator, lpips_vgg, eval_metrics  # noqa: F401
 from .networks import define_D, define_F, define_G, GANLoss, PatchSampleF  # noqa: F401
 from .patchnce import PatchNCELoss  # noqa: F401
 from .model_utils import get_patch_in_input, compute_normal, find_coords_for_patch  # noqa: F401

@@ -828,8 +828,32 @@ class SinSKITGModel:
     def get_image_paths(self):
         return self.image_paths
 
+    eval_metrics = ["I_PSNR", "I_SSIM", "T_AE", "T_MSE"]     # the built subset of sinskitG_model.py:461-470 (eval_metrics.py)
+
+    def compute_current_metrics(self, prefix=None):
+        """The evaluation metrics of the current batch (what compute_evaluation_metric returns inside the reference's
+        get_current_visuals, sinskitG_model.py:839-1040, for the samples at hand): PSNR / SSIM of fake_I against real_I, angle
+        error / MSE of the generated touch patches against the real ones — device-side reductions, one D2H read.  Sets
+        self.metric_<prefix><name> and registers the names for get_current_metrics().  prefix: 'train_' in training, '' otherwise."""
+        from .eval_metrics import compute_evaluation_metric
+        if prefix is None:
+            prefix = "train_" if (self.isTrain and getattr(self, "data_phase", "train") == "train") else ""
+        if getattr(self, "real_I", None) is None or getattr(self, "fake_I", None) is None:
+            raise RuntimeError("compute_current_metrics needs a batch with ground truth and a forward pass (set_input + forward / test)")
+        rT = fT = None
+        if getattr(self, "real_T", None) is not None and getattr(self, "fake_T", None) is not None and hasattr(self, "ox"):
+            rT, fT = self.real_T, ops.patch_gather([self.fake_T], self.ox, self.oy, 32)
+        names = [m for m in self.eval_metrics if rT is not None or not m.startswith("T_")]
+        res = compute_evaluation_metric(self.model_names, self.real_I, self.fake_I, rT, fT, eval_metrics=names, prefix=prefix)
+        for k, v in res.items():
+            setattr(self, k, float(v))
+            if k[len("metric_"):] not in self.metric_names:
+                self.metric_names.append(k[len("metric_"):])
+        return res
+
     def get_current_metrics(self):
-        """base_model.py:185-200.  metric_names stays empty: the evaluation metrics are a 'next' row."""
+        """base_model.py:185-200: OrderedDict 'm_' + name of whatever compute_current_metrics() has produced so far (the SIFID /
+        LPIPS-alex metrics of the reference's list need third-party networks and are not produced)."""
         return collections.OrderedDict(("m_" + n, float(getattr(self, "metric_" + n))) for n in self.metric_names)
 
     def generate_visuals_for_evaluation(self, data, mode):
