@@ -71,10 +71,11 @@ def test_generator_forward_1024_batch_consistency(V):
     (aI, aT, _), _, _ = G.fwd([x1], save=False, want_normal=False)
     (bI, bT, _), _, _ = G.fwd([x1.repeat(2, 1, 1, 1)], save=False, want_normal=False)
     torch.cuda.synchronize()
-    # InstanceNorm statistics are per image: each batch element must reproduce the single-image result (up to the order of
-    # the fp64 statistics atomics)
+    # InstanceNorm statistics are per image: each batch element must reproduce the single-image result, up to the summation
+    # order of the statistics (fp32 partial sums per thread and tile, fp64 atomics across tiles: the tile -> CTA assignment of the
+    # persistent kernels changes with the batch size), ~1e-7 per layer, ~1e-5 at the output of the 20-odd normalised layers
     for i in range(2):
-        assert rel(bI[i:i + 1], aI) < 1e-5 and rel(bT[i:i + 1], aT) < 1e-5
+        assert rel(bI[i:i + 1], aI) < 5e-5 and rel(bT[i:i + 1], aT) < 5e-5
     assert torch.isfinite(aI).all() and float(aI.abs().max()) <= 1.0
 
 

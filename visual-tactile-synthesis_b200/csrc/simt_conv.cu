@@ -416,6 +416,103 @@ __global__ void __launch_bounds__(256) conv_head7_kernel(const float* __restrict
 }
 
 
+// Second formulation, used for a SINGLE output channel (CO = 1: 72 registers): a thread owns 8 CONSECUTIVE pixels of one output row, so the 7 taps of a filter row share a
+// sliding window of 14 input quads (14 + 7*CO shared-memory loads feed 7*8*CO*4 FMAs per (filter row, channel quad): ratio 1:23 for
+// CO = 5 against 1:9 above — a 16-byte shared-memory load costs a warp 4 cycles of the LDS pipe, an FMA a quarter cycle of issue,
+// so anything below 1:16 is LDS bound).  Block = 64 x 32 output pixels (8 x 32 threads); the input tile (70 x 38 pixels, 8
+// channels) is stored with one quad of skew per 8 pixels so that the 8 threads of a row, whose windows start 8 pixels apart,
+// read 8 different bank groups.
+template <int CO>
+__global__ void __launch_bounds__(256) conv_head7_row8_kernel(const float* __restrict__ x0, const __nv_bfloat16* __restrict__ xh,
+                                                              const __nv_bfloat16* __restrict__ xl, int fmt, int hp, int wp, int ci, int org,
+                                                              const __nv_bfloat16* __restrict__ wh, const __nv_bfloat16* __restrict__ wl, int wci,
+                                                              const float* __restrict__ bias, float* __restrict__ y, int ho, int wo, int co) {
+    constexpr int TX = 64, TYH = 32, HTX = TX + 6, HTY = TYH + 6, PITCH = 80, CH = 8;
+    extern __shared__ float4 sm4[];
+    float4* sx = sm4;                              // [2 quads][HTY][PITCH], pixel px at px + (px >> 3)
+    float4* sw = sm4 + 2 * HTY * PITCH;            // [49 taps][2 quads][CO]
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+    const int n = blockIdx.z;
+    const int x_0 = blockIdx.x * TX, y_0 = blockIdx.y * TYH;
+    float acc[8][CO];
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+        for (int o = 0; o < CO; o++) acc[j][o] = 0.f;
+
+    for (int c0 = 0; c0 < ci; c0 += CH) {
+        for (int i = threadIdx.x; i < 2 * HTY * HTX; i += 256) {
+            const int q = i / (HTY * HTX), r = i - q * HTY * HTX;
+            const int py = r / HTX, px = r - py * HTX;
+            const int gy = org + y_0 + py, gx = org + x_0 + px;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy < hp && gx < wp) {
+                const long long a = (((long long)n * hp + gy) * wp + gx) * ci + c0 + q * 4;
+                if (fmt == SKIT_FMT_F32) v = *reinterpret_cast<const float4*>(x0 + a);
+                else {
+                    const uint2 h = *reinterpret_cast<const uint2*>(xh + a), l = *reinterpret_cast<const uint2*>(xl + a);
+                    const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&h.y);
+                    const __nv_bfloat162 l0 = *reinterpret_cast<const __nv_bfloat162*>(&l.x), l1 = *reinterpret_cast<const __nv_bfloat162*>(&l.y);
+                    v.x = __bfloat162float(h0.x) + __bfloat162float(l0.x); v.y = __bfloat162float(h0.y) + __bfloat162float(l0.y);
+                    v.z = __bfloat162float(h1.x) + __bfloat162float(l1.x); v.w = __bfloat162float(h1.y) + __bfloat162float(l1.y);
+                }
+            }
+            sx[(q * HTY + py) * PITCH + px + (px >> 3)] = v;
+        }
+        for (int i = threadIdx.x; i < 49 * 2 * CO; i += 256) {
+            const int o = i % CO, t = i / CO;
+            const int q = t & 1, tap = t >> 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o < co) {
+                const long long a = ((long long)tap * co + o) * wci + c0 + q * 4;
+                float f[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) f[j] = __bfloat162float(wh[a + j]) + __bfloat162float(wl[a + j]);
+                v = make_float4(f[0], f[1], f[2], f[3]);
+            }
+            sw[i] = v;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int ky = 0; ky < 7; ky++) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                float4 in[14];
+                const float4* row = sx + (q * HTY + ty + ky) * PITCH + tx * 9;
+#pragma unroll
+                for (int i = 0; i < 14; i++) in[i] = row[i + (i >> 3)];
+#pragma unroll
+                for (int kx = 0; kx < 7; kx++) {
+                    const float4* wq = sw + ((ky * 7 + kx) * 2 + q) * CO;
+#pragma unroll
+                    for (int o = 0; o < CO; o++) {
+                        const float4 w4 = wq[o];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float t = acc[j][o];
+                            t = fmaf(in[j + kx].x, w4.x, t); t = fmaf(in[j + kx].y, w4.y, t);
+                            t = fmaf(in[j + kx].z, w4.z, t); t = fmaf(in[j + kx].w, w4.w, t);
+                            acc[j][o] = t;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int oy = y_0 + ty;
+    if (oy >= ho) return;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int ox = x_0 + tx * 8 + j;
+        if (ox >= wo) continue;
+        float* dst = y + (((long long)n * ho + oy) * wo + ox) * co;
+#pragma unroll
+        for (int o = 0; o < CO; o++)
+            if (o < co) dst[o] = acc[j][o] + (bias ? bias[o] : 0.f);
+    }
+}
+
 bool conv_head7_eligible(const skit_operand* x, const skit_weights* w, int stride, const double* stats) {
     return w->k == 7 && w->kw == 0 && stride == 1 && w->co <= 8 && !stats && w->hi && w->lo && x->c % 8 == 0 && w->ci == x->c &&
            (x->fmt == SKIT_FMT_F32 || x->fmt == SKIT_FMT_BF16X2);
@@ -429,6 +526,7 @@ int conv_head7_launch(const skit_operand* x, const skit_weights* w, int org, int
         cudaError_t e = cudaFuncSetAttribute(conv_head7_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_head7_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_head7_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_head7_row8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * 38 * 80 + 49 * 2) * sizeof(float4)));
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(conv_head7_kernel) failed: %s", cudaGetErrorString(e));
             return SKIT_ERR_CUDA;
@@ -439,7 +537,15 @@ int conv_head7_launch(const skit_operand* x, const skit_weights* w, int org, int
     const __nv_bfloat16 *wh = (const __nv_bfloat16*)w->hi, *wl = (const __nv_bfloat16*)w->lo;
     // (an 8-consecutive-pixels-per-thread formulation with a sliding input window was measured SLOWER: 771 vs 578 us at
     //  768x768, 128 registers and half the resident warps; the 2x2 interleaved mapping below stays)
-    if (w->co == 1)     // single output channel: the stem's input gradient w.r.t. the sketch channel (PatchNCE query branch)
+    static int row8 = -1;       // SKIT_HEAD7_ROW8=0: the 2x2 mapping for the single-channel case too (A/B timing)
+    if (row8 < 0) { const char* e = getenv("SKIT_HEAD7_ROW8"); row8 = (e && e[0] == '0') ? 0 : 1; }
+    if (w->co == 1 && row8) {   // single output channel (the stem's input gradient w.r.t. the sketch channel, PatchNCE query branch)
+        dim3 grid8(cdiv(wo, 64), cdiv(ho, 32), x->n);
+        conv_head7_row8_kernel<1><<<grid8, 256, (2 * 38 * 80 + 49 * 2) * sizeof(float4), st>>>(
+            (const float*)x->p0, (const __nv_bfloat16*)x->p0, (const __nv_bfloat16*)x->p1, x->fmt, x->hp, x->wp, x->c, org, wh, wl, w->ci, bias, y, ho, wo, w->co);
+        return check_launch("conv_head7_row8_kernel");
+    }
+    if (w->co == 1)
         conv_head7_kernel<1><<<grid, 256, smem, st>>>((const float*)x->p0, (const __nv_bfloat16*)x->p0, (const __nv_bfloat16*)x->p1, x->fmt,
                                                      x->hp, x->wp, x->c, org, wh, wl, w->ci, bias, y, ho, wo, w->co);
     else if (w->co <= 5)
