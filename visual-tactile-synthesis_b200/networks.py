@@ -357,19 +357,28 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
 
         op0, thin0 = self._stem_operand(srcs)
         tap(0, lambda: thin0.data if thin0 is not None else (ops.nchw_cat_to_operand(srcs, 3, PAD_REFLECT).data if self._c1.use_tc else op0.data))
+        # inference (save=False) drops every intermediate as soon as its consumer is enqueued: the forward then holds ~0.8 GB per
+        # 1024x1024 image instead of ~5 GB, which is what bounds the batch size of the configs[4] sweep
         raw1, st = _conv_fwd(self._c1, op0, 0, S_h, S_w, IN)
         tap(1, lambda: raw1)
         _, op1, mr1 = ops.norm_act_pad_stats(raw1, st, S_h * S_w, IN, act=ACT_RELU, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c4))
+        if not save:
+            del raw1, op0, thin0
         raw4, st = _conv_fwd(self._c4, op1, 0, S_h, S_w, IN)
         tap(4, lambda: raw4)
         a4, _, mr4 = ops.norm_act_pad_stats(raw4, st, S_h * S_w, IN, act=ACT_RELU, want_dense=True)
+        if not save:
+            del raw4, op1
         d4 = ops.blur_down_fwd(a4)
         del a4
         _, op4 = ops.norm_act_pad(d4, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._c8))
+        del d4
         h2, w2 = S_h // 2, S_w // 2
         raw8, st = _conv_fwd(self._c8, op4, 0, h2, w2, IN)
         tap(8, lambda: raw8)
         a8, _, mr8 = ops.norm_act_pad_stats(raw8, st, h2 * w2, IN, act=ACT_RELU, want_dense=True)
+        if not save:
+            del raw8, op4
         t = ops.blur_down_fwd(a8)
         del a8
         h4, w4 = h2 // 2, w2 // 2
@@ -385,20 +394,28 @@ class ResnetGenerator(_FlatParamsMixin, nn.Module):
             last = b == nb - 1
             t_new, op_next, mrB = ops.norm_act_pad_stats(rawB, st, h4 * w4, IN, residual=t, want_dense=True, pad=1, pad_mode=PAD_REFLECT,
                                                          fmt=None if last else fmt_b)
-            blocks.append((op_t, rawA, mrA, opA, rawB, mrB))
+            if save:
+                blocks.append((op_t, rawA, mrA, opA, rawB, mrB))
             t, op_t = t_new, op_next
+            del rawA, opA, rawB, t_new, op_next
             tap(12 + b, lambda: t)
         u1 = ops.blur_up_fwd(t)
         _, op_u1 = ops.norm_act_pad(u1, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._u1))
         del u1
+        if not save:
+            del t, op_t
         raw22, st = _conv_fwd(self._u1, op_u1, 0, h2, w2, IN)
         a22, _, mr22 = ops.norm_act_pad_stats(raw22, st, h2 * w2, IN, act=ACT_RELU, want_dense=True)
+        if not save:
+            del raw22, op_u1
         u2 = ops.blur_up_fwd(a22)
         del a22
         _, op_u2 = ops.norm_act_pad(u2, pad=1, pad_mode=PAD_ZERO, fmt=self._fmt(self._u2))
         del u2
         raw26, st = _conv_fwd(self._u2, op_u2, 0, S_h, S_w, IN)
         _, op26, mr26 = ops.norm_act_pad_stats(raw26, st, S_h * S_w, IN, act=ACT_RELU, pad=3, pad_mode=PAD_REFLECT, fmt=self._fmt(self._out))
+        if not save:
+            del raw26, op_u2
         raw30, _ = _conv_fwd(self._out, op26, 0, S_h, S_w, NORM_NONE)
         fI, fT, fN = ops.g_head_fwd(raw30, mask, scale_nz, want_normal)
         if save:
