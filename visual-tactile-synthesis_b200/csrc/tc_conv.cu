@@ -126,27 +126,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             tma_load_3d(sa + 2 * A_BYTES, &tmW_hi, full_bar(s), c0, n0, p.tap_base + tap);
             tma_load_3d(sa + 2 * A_BYTES + W_BYTES, &tmW_lo, full_bar(s), c0, n0, p.tap_base + tap);
         }
-    } else if (warp == 1 && lane == 0) {
-        // ---------------- MMA issuer
+    } else if (warp == 1) {
+        // ---------------- MMA issuer: whole warp, warp-uniform control flow, one elected lane issues (see tc_conv_halo.cu)
         constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+        const uint64_t dsc = make_desc(0, 16, 1024);
+        const bool leader = elect_one();
         for (int it = 0; it < num_k; it++) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
             const uint32_t sa = smem0 + s * STAGE_BYTES;
+            if (leader) {
+                const uint64_t a_hi = dsc + (sa >> 4), a_lo = dsc + ((sa + A_BYTES) >> 4);
+                const uint64_t w_hi = dsc + ((sa + 2 * A_BYTES) >> 4), w_lo = dsc + ((sa + 2 * A_BYTES + W_BYTES) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                const uint64_t a_hi = make_desc(sa + kk * 32, 16, 1024);
-                const uint64_t a_lo = make_desc(sa + A_BYTES + kk * 32, 16, 1024);
-                const uint64_t w_hi = make_desc(sa + 2 * A_BYTES + kk * 32, 16, 1024);
-                const uint64_t w_lo = make_desc(sa + 2 * A_BYTES + W_BYTES + kk * 32, 16, 1024);
-                mma_bf16(tmem_base, a_lo, w_hi, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                mma_bf16(tmem_base, a_hi, w_lo, idesc, 1u);
-                mma_bf16(tmem_base, a_hi, w_hi, idesc, 1u);
+                for (int kk = 0; kk < 4; kk++) {
+                    mma_bf16(tmem_base, a_lo + 2 * kk, w_hi + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    mma_bf16(tmem_base, a_hi + 2 * kk, w_lo + 2 * kk, idesc, 1u);
+                    mma_bf16(tmem_base, a_hi + 2 * kk, w_hi + 2 * kk, idesc, 1u);
+                }
+                mma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
             }
-            mma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+            __syncwarp();
         }
-        mma_commit(tmem_full_bar);
+        if (leader) mma_commit(tmem_full_bar);
     }
     __syncwarp();
 

@@ -66,6 +66,8 @@ struct TcHaloP {
     int terms;         // 3: A_lo*W_hi + A_hi*W_lo + A_hi*W_hi (fp32-parity forward);  2: (A_hi + A_lo)*W_hi only — the W_lo plane is
                        // neither loaded nor multiplied (input-gradient launches, skit_set_backward_terms)
     long long* dbg;    // optional per-CTA clock64 stamps [cta][8] (skit_debug_set_buffer), NULL in production
+    int dbg_mode;      // limiter experiments (SKIT_DBG_MODE, tools/bench_limiter.py; results are wrong): 1 = no MMAs issued (load pipeline
+                       // alone), 2 = no filter TMA (MMA pipeline alone, stale filter), 3 = no activation TMA
 };
 
 constexpr int NA_MAX = 2;  // activation stages
@@ -145,6 +147,7 @@ conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
         for (int c = 0; c < p.kc; c++) {
             const int s = c % NA, ph = (c / NA) & 1;
             mbar_wait(a_empty(s), ph ^ 1);
+            if (p.dbg_mode == 3) { mbar_arrive(a_full(s)); continue; }
             mbar_expect_tx(a_full(s), bytes);
             const uint32_t sa = smem0 + s * a_stage;
             tma_load_4d(sa, tmA_hi, a_full(s), c * 64, R.org_x + x0, R.org_y + y0, n);
@@ -159,15 +162,23 @@ conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
                     const int s = it % p.nw, ph = (it / p.nw) & 1;
                     const int tap = R.tap_base + ky * R.tap_sy + kx * R.tap_sx;
                     mbar_wait(w_empty(s), ph ^ 1);
+                    if (p.dbg_mode == 2) { mbar_arrive(w_full(s)); continue; }
                     mbar_expect_tx(w_full(s), p.terms == 2 ? W_PLANE : W_STAGE);
                     const uint32_t sw = w0 + s * W_STAGE;
                     tma_load_3d(sw, &tmW_hi, w_full(s), c * 64, n0, tap);
                     if (p.terms != 2) tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, n0, tap);
                 }
-    } else if (warp == 1 && lane == 0) {
-        // ---------------- MMA issuer
+    } else if (warp == 1) {
+        // ---------------- MMA issuer.  The WHOLE warp walks the loop with warp-uniform control flow and one elected lane issues:
+        // under a divergent `lane == 0` branch the compiler wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop with per-use
+        // register -> uniform-register moves, and the issue rate — not the tensor pipe — set the pace of the main loop
+        // (tools/bench_limiter.py: removing the filter TMA changed nothing, adding branches to the issue path cost 10 %).
+        // Descriptors: constant high part + (address >> 4); a K step of 16 bf16 advances the start address by 32 B = 2 units.
         constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
         const uint32_t sbo_a = (uint32_t)R.pitch * 128u;
+        const uint64_t dA = make_desc(0, 16, sbo_a), dW = make_desc(0, 16, 1024);
+        const bool leader = elect_one();
+        const int dmode = p.dbg_mode;
         int it = 0;
         uint32_t acc = 0;
         for (int c = 0; c < p.kc; c++) {
@@ -175,7 +186,7 @@ conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
             const int kkc = (c == p.kc - 1) ? p.kk_last : 4;
             mbar_wait(a_full(s), ph);
             tc_fence_after();
-            if (dbg && c == 0) dbg[2] = clock64();
+            if (dbg && c == 0 && leader) dbg[2] = clock64();
             const uint32_t sa = smem0 + s * a_stage;
             for (int ky = 0; ky < R.kh; ky++)
                 for (int kx = 0; kx < R.kw; kx++, it++) {
@@ -184,23 +195,38 @@ conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
                     mbar_wait(w_full(ws), wph);
                     tc_fence_after();
                     const uint32_t sw = w0 + ws * W_STAGE;
-                    for (int kk = 0; kk < kkc; kk++) {
-                        const uint32_t ko = (uint32_t)kk * 32u;
-                        const uint64_t a_hi = make_desc(arow + ko, 16, sbo_a);
-                        const uint64_t a_lo = make_desc(arow + p.a_plane + ko, 16, sbo_a);
-                        const uint64_t w_hi = make_desc(sw + ko, 16, 1024);
-                        const uint64_t w_lo = make_desc(sw + W_PLANE + ko, 16, 1024);
-                        mma_bf16(tmem_base, a_lo, w_hi, idesc, acc);
-                        acc = 1u;
-                        if (p.terms != 2) mma_bf16(tmem_base, a_hi, w_lo, idesc, 1u);
-                        mma_bf16(tmem_base, a_hi, w_hi, idesc, 1u);
+                    if (leader) {
+                        const uint64_t a_hi = dA + (arow >> 4), a_lo = dA + ((arow + (uint32_t)p.a_plane) >> 4);
+                        const uint64_t w_hi = dW + (sw >> 4), w_lo = dW + ((sw + W_PLANE) >> 4);
+                        if (dmode == 1) {              // limiter experiment: no MMAs beyond the first
+                            if (it == 0) mma_bf16(tmem_base, a_hi, w_hi, idesc, 0u);
+                        } else if (p.terms == 2) {
+#pragma unroll 4
+                            for (int kk = 0; kk < kkc; kk++) {
+                                mma_bf16(tmem_base, a_lo + 2 * kk, w_hi + 2 * kk, idesc, acc);
+                                acc = 1u;
+                                mma_bf16(tmem_base, a_hi + 2 * kk, w_hi + 2 * kk, idesc, 1u);
+                            }
+                        } else {
+#pragma unroll 4
+                            for (int kk = 0; kk < kkc; kk++) {
+                                mma_bf16(tmem_base, a_lo + 2 * kk, w_hi + 2 * kk, idesc, acc);
+                                acc = 1u;
+                                mma_bf16(tmem_base, a_hi + 2 * kk, w_lo + 2 * kk, idesc, 1u);
+                                mma_bf16(tmem_base, a_hi + 2 * kk, w_hi + 2 * kk, idesc, 1u);
+                            }
+                        }
+                        mma_commit(w_empty(ws));
                     }
-                    mma_commit(w_empty(ws));
+                    __syncwarp();
                 }
-            mma_commit(a_empty(s));
+            if (leader) mma_commit(a_empty(s));
+            __syncwarp();
         }
-        mma_commit(tmem_full_bar);
-        if (dbg) dbg[3] = clock64();
+        if (leader) {
+            mma_commit(tmem_full_bar);
+            if (dbg) dbg[3] = clock64();
+        }
     }
     __syncwarp();
 
@@ -413,10 +439,13 @@ conv_tc_halo_persist_kernel(const __grid_constant__ AMaps tmA, const __grid_cons
                         if (p.terms != 2) tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, n0, tap);
                     }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ---------------- MMA issuer: accumulator (unit index & 1)
+    } else if (warp == 1) {
+        // ---------------- MMA issuer: accumulator (unit index & 1).  Whole warp, warp-uniform control flow, one elected lane issues
+        // (see conv_tc_halo_kernel)
         constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
         const uint32_t sbo_a = (uint32_t)R.pitch * 128u;
+        const uint64_t dA = make_desc(0, 16, sbo_a), dW = make_desc(0, 16, 1024);
+        const bool leader = elect_one();
         int ita = 0, itw = 0, ui = 0;
         for (int u = blockIdx.x; u < pp.units; u += gridDim.x, ui++) {
             const int b = ui & 1;
@@ -437,22 +466,34 @@ conv_tc_halo_persist_kernel(const __grid_constant__ AMaps tmA, const __grid_cons
                         mbar_wait(w_full(ws), wph);
                         tc_fence_after();
                         const uint32_t sw = w0 + ws * W_STAGE;
-                        for (int kk = 0; kk < kkc; kk++) {
-                            const uint32_t ko = (uint32_t)kk * 32u;
-                            const uint64_t a_hi = make_desc(arow + ko, 16, sbo_a);
-                            const uint64_t a_lo = make_desc(arow + p.a_plane + ko, 16, sbo_a);
-                            const uint64_t w_hi = make_desc(sw + ko, 16, 1024);
-                            const uint64_t w_lo = make_desc(sw + W_PLANE + ko, 16, 1024);
-                            mma_bf16(dacc, a_lo, w_hi, idesc, acc);
-                            acc = 1u;
-                            if (p.terms != 2) mma_bf16(dacc, a_hi, w_lo, idesc, 1u);
-                            mma_bf16(dacc, a_hi, w_hi, idesc, 1u);
+                        if (leader) {
+                            const uint64_t a_hi = dA + (arow >> 4), a_lo = dA + ((arow + (uint32_t)p.a_plane) >> 4);
+                            const uint64_t w_hi = dW + (sw >> 4), w_lo = dW + ((sw + W_PLANE) >> 4);
+                            if (p.terms == 2) {
+#pragma unroll 4
+                                for (int kk = 0; kk < kkc; kk++) {
+                                    mma_bf16(dacc, a_lo + 2 * kk, w_hi + 2 * kk, idesc, acc);
+                                    acc = 1u;
+                                    mma_bf16(dacc, a_hi + 2 * kk, w_hi + 2 * kk, idesc, 1u);
+                                }
+                            } else {
+#pragma unroll 4
+                                for (int kk = 0; kk < kkc; kk++) {
+                                    mma_bf16(dacc, a_lo + 2 * kk, w_hi + 2 * kk, idesc, acc);
+                                    acc = 1u;
+                                    mma_bf16(dacc, a_hi + 2 * kk, w_lo + 2 * kk, idesc, 1u);
+                                    mma_bf16(dacc, a_hi + 2 * kk, w_hi + 2 * kk, idesc, 1u);
+                                }
+                            }
+                            mma_commit(w_empty(ws));
                         }
-                        mma_commit(w_empty(ws));
+                        __syncwarp();
                     }
-                mma_commit(a_empty(s));
+                if (leader) mma_commit(a_empty(s));
+                __syncwarp();
             }
-            mma_commit(acc_full(b));
+            if (leader) mma_commit(acc_full(b));
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ---------------- epilogue warps: TMEM lanes 32*(warp-4) .. +31, pixel r = ty*8 + tx of the unit's tile
@@ -703,10 +744,13 @@ conv_tc_halo_t_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__
                         if (p.terms != 2) tma_load_3d(sw + W_PLANE, &tmW_lo, w_full(s), c * 64, m0, tap);
                     }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ---------------- MMA issuer: D^T[co][pixel] += W[co][k] * A[pixel][k], accumulator (unit index & 1)
+    } else if (warp == 1) {
+        // ---------------- MMA issuer: D^T[co][pixel] += W[co][k] * A[pixel][k], accumulator (unit index & 1).  Whole warp,
+        // warp-uniform control flow, one elected lane issues (see conv_tc_halo_kernel)
         const uint32_t idesc = make_idesc_bf16_mn(BM, 8 * TY, 0, 0);
         const uint32_t sbo_x = (uint32_t)R.pitch * 128u;
+        const uint64_t dX = make_desc(0, 16, sbo_x), dW = make_desc(0, 16, 1024);
+        const bool leader = elect_one();
         int ita = 0, itw = 0, ui = 0;
         for (int u = blockIdx.x; u < pp.units; u += gridDim.x, ui++) {
             const int b = ui & 1;
@@ -727,22 +771,34 @@ conv_tc_halo_t_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__
                         mbar_wait(w_full(ws), wph);
                         tc_fence_after();
                         const uint32_t sw = w0 + ws * pp.w_stage;
-                        for (int kk = 0; kk < kkc; kk++) {
-                            const uint32_t ko = (uint32_t)kk * 32u;
-                            const uint64_t x_hi = make_desc(xrow + ko, 16, sbo_x);
-                            const uint64_t x_lo = make_desc(xrow + p.a_plane + ko, 16, sbo_x);
-                            const uint64_t w_hi = make_desc(sw + ko, 16, 1024);
-                            const uint64_t w_lo = make_desc(sw + W_PLANE + ko, 16, 1024);
-                            mma_bf16(dacc, w_hi, x_lo, idesc, acc);
-                            acc = 1u;
-                            if (p.terms != 2) mma_bf16(dacc, w_lo, x_hi, idesc, 1u);
-                            mma_bf16(dacc, w_hi, x_hi, idesc, 1u);
+                        if (leader) {
+                            const uint64_t x_hi = dX + (xrow >> 4), x_lo = dX + ((xrow + (uint32_t)p.a_plane) >> 4);
+                            const uint64_t w_hi = dW + (sw >> 4), w_lo = dW + ((sw + W_PLANE) >> 4);
+                            if (p.terms == 2) {
+#pragma unroll 4
+                                for (int kk = 0; kk < kkc; kk++) {
+                                    mma_bf16(dacc, w_hi + 2 * kk, x_lo + 2 * kk, idesc, acc);
+                                    acc = 1u;
+                                    mma_bf16(dacc, w_hi + 2 * kk, x_hi + 2 * kk, idesc, 1u);
+                                }
+                            } else {
+#pragma unroll 4
+                                for (int kk = 0; kk < kkc; kk++) {
+                                    mma_bf16(dacc, w_hi + 2 * kk, x_lo + 2 * kk, idesc, acc);
+                                    acc = 1u;
+                                    mma_bf16(dacc, w_lo + 2 * kk, x_hi + 2 * kk, idesc, 1u);
+                                    mma_bf16(dacc, w_hi + 2 * kk, x_hi + 2 * kk, idesc, 1u);
+                                }
+                            }
+                            mma_commit(w_empty(ws));
                         }
-                        mma_commit(w_empty(ws));
+                        __syncwarp();
                     }
-                mma_commit(a_empty(s));
+                if (leader) mma_commit(a_empty(s));
+                __syncwarp();
             }
-            mma_commit(acc_full(b));
+            if (leader) mma_commit(acc_full(b));
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ---------------- epilogue warps: TMEM lane = output channel m0 + 32*(warp-4) + lane, column = pixel ty*8 + tx of the tile
@@ -957,6 +1013,12 @@ static int encode_w_maps(CUtensorMap* m_hi, CUtensorMap* m_lo, const void* w_hi,
     return tc::encode_bf16_map_sw(m_lo, w_lo ? w_lo : w_hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+static int dbg_mode_env() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SKIT_DBG_MODE"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 static bool persist_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -991,6 +1053,7 @@ int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_l
     else { p.OH = ho; p.OW = wo; p.osy = 1; p.osx = 1; p.poy = 0; p.pox = 0; }
     p.bias = bias; p.y = y; p.stats = stats; p.stats_per_n = stats_mode == SKIT_NORM_INSTANCE;
     p.dbg = g_dbg_buffer;
+    p.dbg_mode = dbg_mode_env();
     p.terms = w_lo ? 3 : 2;
     p.nreg = 1;
     HaloRegion& R = p.reg[0];
@@ -1083,6 +1146,7 @@ int conv_tc_halo_dgrad_full(const skit_operand* d, const void* w_hi, const void*
     p.kc = cdiv(ci, 64); p.kk_last = 4; p.co = co;
     p.OH = H; p.OW = W; p.osy = 1; p.osx = 1; p.poy = 0; p.pox = 0;
     p.bias = nullptr; p.y = dx; p.stats = nullptr; p.stats_per_n = 0; p.dbg = g_dbg_buffer;
+    p.dbg_mode = dbg_mode_env();
     p.terms = w_lo ? 3 : 2;
     p.nreg = 5;
     auto set = [&](int i, int kh, int kw, int tb, int sy, int sx, int oy, int ox, int ho, int wo, int ooy, int oox, int amap) {

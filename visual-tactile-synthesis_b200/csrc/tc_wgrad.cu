@@ -103,28 +103,41 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
                     if (p.skip != 2) tma_load_4d(sa + 2 * M_BYTES + N_BYTES + g * BOX_BYTES, &tmN_lo, full_bar(s), n0 + g * 64, nx, ny, img);
                 }
             }
-        } else if (warp == 1 && lane == 0) {
-            // ---------------- MMA issuer (both operands MN-major: LBO = one 64-channel box, SBO = 8 pixel rows)
+        } else if (warp == 1) {
+            // ---------------- MMA issuer (both operands MN-major: LBO = one 64-channel box, SBO = 8 pixel rows).  Whole warp with
+            // warp-uniform control flow, one elected lane issues (see conv_tc_halo_kernel); a K step of 16 pixels advances the
+            // descriptors' start address by 16 rows x 128 B
             constexpr uint32_t idesc = make_idesc_bf16(BN, 1, 1);
+            const uint64_t dsc = make_desc(0, BOX_BYTES, 1024);
+            const bool leader = elect_one();
             for (int it = 0; it < num_it; it++) {
                 const int s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(full_bar(s), ph);
                 tc_fence_after();
                 const uint32_t sa = smem0 + s * STAGE_BYTES;
+                if (leader) {
+                    const uint64_t m_hi = dsc + (sa >> 4), m_lo = dsc + ((sa + M_BYTES) >> 4);
+                    const uint64_t n_hi = dsc + ((sa + 2 * M_BYTES) >> 4), n_lo = dsc + ((sa + 2 * M_BYTES + N_BYTES) >> 4);
+                    constexpr uint64_t KS = (16 * 128) >> 4;
+                    if (p.skip == 2) {
 #pragma unroll
-                for (int kk = 0; kk < PIX / 16; kk++) {
-                    const uint32_t ko = kk * 16 * 128;
-                    const uint64_t m_hi = make_desc(sa + ko, BOX_BYTES, 1024);
-                    const uint64_t m_lo = make_desc(sa + M_BYTES + ko, BOX_BYTES, 1024);
-                    const uint64_t n_hi = make_desc(sa + 2 * M_BYTES + ko, BOX_BYTES, 1024);
-                    const uint64_t n_lo = make_desc(sa + 2 * M_BYTES + N_BYTES + ko, BOX_BYTES, 1024);
-                    mma_bf16(tmem_base, m_hi, n_hi, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                    mma_bf16(tmem_base, m_lo, n_hi, idesc, 1u);
-                    if (p.skip != 2) mma_bf16(tmem_base, m_hi, n_lo, idesc, 1u);
+                        for (int kk = 0; kk < PIX / 16; kk++) {
+                            mma_bf16(tmem_base, m_hi + KS * kk, n_hi + KS * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                            mma_bf16(tmem_base, m_lo + KS * kk, n_hi + KS * kk, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < PIX / 16; kk++) {
+                            mma_bf16(tmem_base, m_hi + KS * kk, n_hi + KS * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                            mma_bf16(tmem_base, m_lo + KS * kk, n_hi + KS * kk, idesc, 1u);
+                            mma_bf16(tmem_base, m_hi + KS * kk, n_lo + KS * kk, idesc, 1u);
+                        }
+                    }
+                    mma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
                 }
-                mma_commit(empty_bar(s));
+                __syncwarp();
             }
-            mma_commit(tmem_full_bar);
+            if (leader) mma_commit(tmem_full_bar);
         }
         __syncwarp();
         // ---------------- epilogue: out[(tap*Ndim + n)*Mdim + m] += acc   (lanes = consecutive m: coalesced reds)
