@@ -38,6 +38,7 @@ if __name__ == "__main__":
         worker(int(sys.argv[2]))
         sys.exit(0)
     size = sys.argv[1] if len(sys.argv) > 1 else "768"
-    for env in ({"SKIT_TC_TRANS": "0"}, {}, {"SKIT_DGRAD_SPLIT": "0"}, {"SKIT_TRANS_TY": "24", "SKIT_TRANS_NA": "2"}):
+    for env in ({"SKIT_TC_TRANS": "0"}, {}, {"SKIT_TRANS_MIN_PM_TILES": "0"}, {"SKIT_TRANS_MIN_PM_TILES": "0", "SKIT_DGRAD_SPLIT": "0"},
+                {"SKIT_TRANS_MIN_PM_TILES": "0", "SKIT_TRANS_TY": "24", "SKIT_TRANS_NA": "2"}):
         print(env or "default", flush=True)
         subprocess.run([sys.executable, __file__, "--worker", size], env=dict(os.environ, **env))

@@ -1062,7 +1062,9 @@ int conv_tc_halo_launch(const skit_operand* x, const void* w_hi, const void* w_l
     R.pitch = 8 + kw - 1; R.a_rows = R.pitch * (16 + kh - 1);
     p.a_plane = ((R.a_rows * 128 + 1023) / 1024) * 1024;
     const long long pm_tiles = (long long)R.tiles_x * cdiv(ho, 16) * x->n;      // tiles of the pixel-major kernels
-    if (trans_enabled() && co >= 32 && (co <= 128 || (co <= 512 && co % 128 == 0 && pm_tiles >= 4 * 148)) && !p.dbg) {
+    static long long big_min = -1;      // pixel-major tiles from which 256 / 512-channel layers take the pixels-on-N kernel (SKIT_TRANS_MIN_PM_TILES)
+    if (big_min < 0) { const char* e = getenv("SKIT_TRANS_MIN_PM_TILES"); big_min = e ? atoll(e) : 4 * 148; }
+    if (trans_enabled() && co >= 32 && (co <= 128 || (co <= 512 && co % 128 == 0 && pm_tiles >= big_min)) && !p.dbg) {
         // channels on M (tiles of 128), 192 / 256 pixels on N (conv_tc_halo_t_kernel) when the map fills the SMs.  For 256 / 512
         // output channels it is the same MMA work as the pixel-major N = 256 kernel with half the filter streaming per pixel (a
         // unit streams only its 128 filter rows); measured (tools/bench_trans.py, 768x768 step): 128 -> 256 at 384x384 208 -> 194 us,

@@ -326,14 +326,16 @@ def act_norm_bwd_reduce_ex(shape, dpad=None, pad=0, pad_mode=PAD_ZERO, dadd=None
     n, h, w, c = shape
     dev = (dpad if dpad is not None else dadd).device
     g = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
-    dsum = torch.empty((n, h, w, c), dtype=torch.float32, device=dev) if want_dsum else None
+    # without an activation the masked gradient g IS the incoming gradient: one tensor serves both (a ResnetBlock's second conv)
+    alias = want_dsum and act == ACT_NONE and not dadd_relu_mask
+    dsum = torch.empty((n, h, w, c), dtype=torch.float32, device=dev) if (want_dsum and not alias) else None
     sums = None
     if norm_mode != NORM_NONE:
         sums = zeros(((2 * SUM_REPLICAS + 1) * (n if norm_mode == NORM_INSTANCE else 1) * c + 1,), torch.float64, dev)
     L.call("skit_act_norm_bwd_reduce_ex2", _p(dpad), pad, pad_mode, _p(dadd), _p(dadd2), dadd_c0,
            c if dadd_ctot is None else dadd_ctot, int(dadd_relu_mask), _p(raw), n, h, w, c, _p(mr), norm_mode,
            _p(gamma), _p(beta), act, _p(g), _p(sums), _p(dsum), L.stream())
-    return (g, sums, dsum) if want_dsum else (g, sums)
+    return (g, sums, g if alias else dsum) if want_dsum else (g, sums)
 
 
 def conv_transpose2d_fwd(x, wg, stride, pad, bias=None, stats_mode=NORM_NONE, out=None, out_c0=0):
