@@ -433,6 +433,10 @@ int skit_maxpool2_bwd(const float* f, const float* dpool, int n, int h, int w, i
 int skit_lpips_layer(const float* f0, const float* f1, const float* lin_w, int n, int h, int w, int c, float gscale,
                      float* loss, float* df0, void* stream);
 
+/* Zero-fill `nbytes` at p on `stream` with cudaMemsetAsync (a memset node when the stream is being captured): the zero_grad of
+ * the flat gradient buckets (optimizer.zero_grad, sinskitG_model.py:648-694) and the scratch / scatter targets of the backward pass. */
+int skit_zero_bytes(void* p, long long nbytes, void* stream);
+
 /* ---- Evaluation metrics (models/model_utils.py:431-561 compute_evaluation_metric).  Device-side
  * reductions into fp64 / fp32 scalars the caller zero-initialises (minmax: {+inf, -inf}); nothing synchronises.
  *   skit_metric_minmax        out2 = {min(x), max(x)}: the real image's range for the [0, 1] rescale (:483-487)

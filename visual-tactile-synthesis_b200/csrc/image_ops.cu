@@ -569,6 +569,19 @@ static int fill_srcs(Srcs4& s, const float* const* srcs, const int* chans, const
     return off;
 }
 
+/* Zero-fill as a memset node (cudaMemsetAsync): inside a captured step graph this replaces the fill kernels torch.zeros / zero_()
+ * would launch for the gradient buckets, the split-K scratch of the weight gradients and the scatter targets. */
+extern "C" int skit_zero_bytes(void* p, long long nbytes, void* stream) {
+    SKIT_REQUIRE(p && nbytes >= 0, "zero_bytes: bad arguments");
+    if (nbytes == 0) return SKIT_OK;
+    cudaError_t e = cudaMemsetAsync(p, 0, (size_t)nbytes, as_stream(stream));
+    if (e != cudaSuccess) {
+        set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+        return SKIT_ERR_CUDA;
+    }
+    return SKIT_OK;
+}
+
 extern "C" int skit_nchw_cat_to_operand(const float* const* srcs, const int* chans, int nsrc,
                                         int n, int h, int w, const skit_operand* op, int pad, int pad_mode, void* stream) {
     Srcs4 s{};

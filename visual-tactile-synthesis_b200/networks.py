@@ -168,7 +168,10 @@ class _FlatParamsMixin:
 
     def zero_grad(self, set_to_none=False):  # grads are views of the flat bucket; never set to None
         if getattr(self, "flat_grad", None) is not None:
-            self.flat_grad.zero_()
+            if self.flat_grad.is_cuda:
+                ops.zero_(self.flat_grad)       # a memset node in the captured step graph
+            else:
+                self.flat_grad.zero_()
         else:
             super().zero_grad(set_to_none=False)
 
@@ -256,7 +259,7 @@ def _stage_bwd(layer, x_op, raw, mr, norm_mode, act, count, dpad=None, pad=0, pa
     Returns the gradient w.r.t. the conv's own haloed operand (NHWC fp32 [n, hp, wp, ci]) or None."""
     n, ho, wo, co = raw.shape
     if dpad is None and dadd is None:   # only a tapped-feature gradient on the raw output reaches this stage
-        dadd = torch.zeros_like(raw)
+        dadd = ops.zeros_big(raw.shape, torch.float32, raw.device)
     if dsum_out is not None:   # also materialise the incoming gradient fold(dpad) + dadd (a ResnetBlock's skip path needs it)
         g, sums, ds = ops.act_norm_bwd_reduce_ex(raw.shape, dpad=dpad, pad=pad, pad_mode=pad_mode, dadd=dadd, raw=raw, mr=mr,
                                                  norm_mode=norm_mode, act=act, gamma=gamma, beta=beta, want_dsum=True)
@@ -1412,7 +1415,7 @@ def define_G(input_nc, output_nc, ngf, netG, norm="batch", use_dropout=False, in
             raise NotImplementedError("B200 path: dropout is not built")
         net = CustomUnetGenerator(input_nc, output_nc, num_downs=8, ngf=ngf, num_layer_separate=num_layer_separate, opt=opt)
     elif netG in ("stylegan2", "smallstylegan2"):
-        from .sg2_generator import StyleGAN2Generator   # forward / feature taps only; no explicit backward yet
+        from .sg2_generator import StyleGAN2Generator   # forward, feature taps and explicit backward (sg2_generator.py)
         net = StyleGAN2Generator(input_nc, output_nc, ngf, use_dropout=use_dropout, n_blocks=6 if netG == "stylegan2" else 2, opt=opt)
     elif netG in ("unet_128", "unet_256"):
         raise NotImplementedError("Generator model name [%s] is on the roadmap of the B200 path but not built yet" % netG)

@@ -27,7 +27,7 @@ class ZeroArena:
 
     def begin(self):
         if self.high:
-            self.buf[:self.high].view(torch.float32).zero_()
+            zero_(self.buf[:self.high])
         self.clean, self.off = self.high, 0
 
     def take(self, shape, dtype):
@@ -40,7 +40,7 @@ class ZeroArena:
             return None
         view = self.buf[start:start + nbytes].view(dtype).view(shape)
         if end > self.clean:
-            view.zero_()
+            zero_(view)
         self.off = end
         self.high = max(self.high, end)
         return view
@@ -50,12 +50,24 @@ SUM_REPLICAS = 8   # SKIT_SUM_REPLICAS of include/skit_b200.h (tests/test_abi.py
 ARENA = None   # the active ZeroArena (set by the model around a train step)
 
 
+def zero_(t):
+    """t.zero_() as a memset (skit_zero_bytes): no fill kernel, a memset node inside a captured graph."""
+    L.call("skit_zero_bytes", _p(t), t.numel() * t.element_size(), L.stream())
+    L.launches -= 1     # a memset, not a kernel
+    return t
+
+
+def zeros_big(shape, dtype, device):
+    """torch.zeros for the large scratch / scatter buffers of the backward pass, through a memset."""
+    return zero_(torch.empty(tuple(shape), dtype=dtype, device=device))
+
+
 def zeros(shape, dtype, device):
     if ARENA is not None:
         t = ARENA.take(tuple(shape), dtype)
         if t is not None:
             return t
-    return torch.zeros(tuple(shape), dtype=dtype, device=device)
+    return zeros_big(shape, dtype, device)
 
 
 class Operand:
@@ -236,7 +248,7 @@ def conv2d_wgrad(x, org, dy, dy_org, k, stride, ho, wo, dw, dbias=None, impl=IMP
     """Accumulates into dw ([co][ci][k][k] view of the flat grad bucket) and dbias.  Operands may carry zero padding
     channels beyond dw's real (co, ci)."""
     co, ci = dy.c, x.c
-    scratch = torch.zeros((k * k * ci * co,), dtype=torch.float32, device=x.data.device)   # big, and off the critical path
+    scratch = zeros_big((k * k * ci * co,), torch.float32, x.data.device)   # big, and off the critical path
     L.call("skit_conv2d_wgrad_ex", x.ref(), org, dy.ref(), dy_org, k, stride, ho, wo, _p(scratch), _p(dw), _p(dbias), impl,
            int(dw.shape[0]), int(dw.shape[1]), L.stream())
 
@@ -251,14 +263,14 @@ def fold_x(thin, kw):
 
 def conv2d_wgrad_folded(xf, dy, dy_org, k, kw, cp, ho, wo, dw):
     """Weight gradient against an x-folded input operand; accumulates into dw [co][ci][k][kw]."""
-    scratch = torch.zeros((k * 64 * dy.c,), dtype=torch.float32, device=xf.data.device)
+    scratch = zeros_big((k * 64 * dy.c,), torch.float32, xf.data.device)
     L.call("skit_conv2d_wgrad_folded", xf.ref(), 0, dy.ref(), dy_org, k, kw, cp, ho, wo, _p(scratch), _p(dw),
            int(dw.shape[0]), int(dw.shape[1]), L.stream())
 
 
 def conv2d_wgrad_dyfolded(x, dyf, k, cp, ho, wo, dw):
     """Weight gradient of a thin-output k x k layer against its x-folded gradient operand; accumulates into dw [co][ci][k][k]."""
-    scratch = torch.zeros((k * 64 * x.c,), dtype=torch.float32, device=x.data.device)
+    scratch = zeros_big((k * 64 * x.c,), torch.float32, x.data.device)
     L.call("skit_conv2d_wgrad_dyfolded", x.ref(), dyf.ref(), k, cp, ho, wo, _p(scratch), _p(dw), int(dw.shape[0]), int(dw.shape[1]), L.stream())
 
 
@@ -550,14 +562,14 @@ def patch_sample_l2norm(feat_nhwc, ids, keep_pre=False):
 
 def patch_sample_l2norm_bwd(dout, pre, ids, feat_shape):
     b, h, w, c = feat_shape
-    dfeat = torch.zeros(feat_shape, dtype=torch.float32, device=dout.device)
+    dfeat = zeros_big(feat_shape, torch.float32, dout.device)
     L.call("skit_patch_sample_l2norm_bwd", _p(dout), _p(pre), b, h * w, c, _p(ids), int(ids.numel()), _p(dfeat), L.stream())
     return dfeat
 
 
 def rows_scatter_add(drows, ids, feat_shape):
     b, h, w, c = feat_shape
-    dfeat = torch.zeros(feat_shape, dtype=torch.float32, device=drows.device)
+    dfeat = zeros_big(feat_shape, torch.float32, drows.device)
     L.call("skit_rows_scatter_add", _p(drows), b, h * w, c, _p(ids), int(ids.numel()), _p(dfeat), L.stream())
     return dfeat
 

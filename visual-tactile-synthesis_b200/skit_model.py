@@ -544,7 +544,7 @@ class SinSKITGModel:
         NT, NF = self.NT, opt.add_fake_T_sample_size
         n = self.real_S.shape[0]
         ox, oy = self.ox, self.oy
-        L = torch.zeros(8 + 3 * NT + NF, dtype=torch.float32, device=self.device)
+        L = ops.zeros((8 + 3 * NT + NF,), torch.float32, self.device)      # a slice of the step's zero arena
         sl = dict(D_fake=L[0:1], D_real=L[1:2], G_GAN=L[2:3], G_L1=L[3:4], G2_L1=L[4:5], G_lpips=L[5:6], G2_lpips=L[6:7],
                   D2_fake=L[8:8 + NT], D2_real=L[8 + NT:8 + 2 * NT], G2_GAN=L[8 + 2 * NT:8 + 3 * NT], D2_more=L[8 + 3 * NT:])
         D.zero_grad()
@@ -655,7 +655,7 @@ class SinSKITGModel:
                 dI.add_(dI_lp)
                 sl["G_lpips"].add_(ln.sum() * (opt.lambda_G1_lpips / n))
             self._lp_out = None
-        dT = torch.zeros_like(fake_T)
+        dT = ops.zeros_big(fake_T.shape, torch.float32, self.device)
         ops.patch_scatter_add(dTp, 0, 2, ox, oy, dT)
         if self.nce_layers:
             self._join(6)
