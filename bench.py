@@ -233,7 +233,7 @@ def run_eager(a):
 # ----------------------------------------------------------------------------------------- the B200 arm
 def _ncu_field(size, field):
     """A per-launch figure of the dominant kernel from the committed `ncu --set full` summary under profiles/ (newest round first)."""
-    for rnd in ("r02", "r01"):
+    for rnd in ("r02f", "r02", "r01"):
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "%s_conv_tc_halo_fwd%d.json" % (rnd, size))))
             nested = {"tensor_pipe_pct_elapsed": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",

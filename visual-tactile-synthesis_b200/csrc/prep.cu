@@ -614,70 +614,66 @@ __global__ void bn_param_grad_kernel(const double* sums, int c, float count, flo
 
 // ------------------------------------------------------------------------------ blur resamplers
 // 1-D reflect(1) [1,2,1]/4 stride 2 down; bilinear-like [1,3,3,1]/4 stride 2 up with replicate edge.
+// The four resamplers share one launch shape: blockIdx.y = row of the tensor being WRITTEN, blockIdx.z = image, threads stride over
+// (x, 4 channels) of that row — no 64-bit div / mod per element.
 __global__ void __launch_bounds__(256) blur_down_fwd_kernel(const float* __restrict__ x, int n, int h, int w, int c, float* __restrict__ y) {
     const int ho = h / 2, wo = w / 2, cv = c / 4;
-    const long long total = (long long)n * ho * wo * cv;
+    const int oy = blockIdx.y, b = blockIdx.z;
     const float f[3] = {0.25f, 0.5f, 0.25f};
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % cv) * 4;
-        long long t = i / cv;
-        const int ox = (int)(t % wo); t /= wo;
-        const int oy = (int)(t % ho);
-        const int b = (int)(t / ho);
+    const float* rows[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) rows[a] = x + ((long long)b * h + pad_src(2 * oy + a, 1, h, SKIT_PAD_REFLECT)) * w * c;
+    float* orow = y + ((long long)b * ho + oy) * wo * c;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wo * cv; i += gridDim.x * blockDim.x) {
+        const int ox = i / cv, ch = (i - ox * cv) * 4;
         float4 acc = make_float4(0, 0, 0, 0);
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-            const int sy = pad_src(2 * oy + a, 1, h, SKIT_PAD_REFLECT);
+        for (int d = 0; d < 3; d++) {
+            const long long off = (long long)pad_src(2 * ox + d, 1, w, SKIT_PAD_REFLECT) * c + ch;
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                const int sx = pad_src(2 * ox + d, 1, w, SKIT_PAD_REFLECT);
+            for (int a = 0; a < 3; a++) {
                 const float wgt = f[a] * f[d];
-                const float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * h + sy) * w + sx) * c + ch);
+                const float4 v = *reinterpret_cast<const float4*>(rows[a] + off);
                 acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
             }
         }
-        *reinterpret_cast<float4*>(y + (((long long)b * ho + oy) * wo + ox) * c + ch) = acc;
+        *reinterpret_cast<float4*>(orow + (long long)ox * c + ch) = acc;
     }
 }
 
-// taps of the adjoint on one axis: for source index s, list (output index, weight)
-__device__ inline int blur_down_adj(int s, int len, int outs[4], float ws[4]) {
-    const float f[3] = {0.25f, 0.5f, 0.25f};
-    const int lo = len / 2;
-    int cnt = 0;
-    int cands[3]; int nc = 0;
-    cands[nc++] = s;
-    if (s == 1) cands[nc++] = -1;
-    if (s == len - 2) cands[nc++] = len;
-    for (int q = 0; q < nc; q++) {
-        const int pp = cands[q] + 1;  // padded coordinate
-        for (int a = 0; a < 3; a++) {
-            const int t = pp - a;
-            if (t >= 0 && (t & 1) == 0 && t / 2 < lo) { outs[cnt] = t / 2; ws[cnt] = f[a]; cnt++; }
-        }
-    }
-    return cnt;
+// Adjoint of blur_down in closed form (no tap lists in local memory): along one axis an even source index s feeds output s/2 with
+// 0.5; an odd one feeds (s-1)/2 and (s+1)/2 with 0.25 each — the latter only while it exists, and s = 1 also collects the reflected
+// padding sample (output 0, 0.25).  One block row per (image, source row): no 64-bit divisions per element.
+__device__ __forceinline__ void blur_down_adj2(int s, int lo, int& i0, float& w0, int& i1, float& w1) {
+    if ((s & 1) == 0) { i0 = s >> 1; w0 = 0.5f; i1 = i0; w1 = 0.f; return; }
+    i0 = (s - 1) >> 1; w0 = s == 1 ? 0.5f : 0.25f;
+    i1 = (s + 1) >> 1; w1 = i1 < lo ? 0.25f : 0.f;
+    if (i1 >= lo) i1 = i0;
 }
 
 __global__ void __launch_bounds__(256) blur_down_bwd_kernel(const float* __restrict__ dy, int n, int h, int w, int c, float* __restrict__ dx) {
     const int ho = h / 2, wo = w / 2, cv = c / 4;
-    const long long total = (long long)n * h * w * cv;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % cv) * 4;
-        long long t = i / cv;
-        const int x = (int)(t % w); t /= w;
-        const int y = (int)(t % h);
-        const int b = (int)(t / h);
-        int oys[4], oxs[4]; float wy[4], wx[4];
-        const int ny = blur_down_adj(y, h, oys, wy), nx = blur_down_adj(x, w, oxs, wx);
-        float4 acc = make_float4(0, 0, 0, 0);
-        for (int a = 0; a < ny; a++)
-            for (int d = 0; d < nx; d++) {
-                const float wgt = wy[a] * wx[d];
-                const float4 v = *reinterpret_cast<const float4*>(dy + (((long long)b * ho + oys[a]) * wo + oxs[d]) * c + ch);
-                acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
-            }
-        *reinterpret_cast<float4*>(dx + (((long long)b * h + y) * w + x) * c + ch) = acc;
+    const int y = blockIdx.y, b = blockIdx.z;
+    int oy0, oy1; float wy0, wy1;
+    blur_down_adj2(y, ho, oy0, wy0, oy1, wy1);
+    const float* r0 = dy + ((long long)b * ho + oy0) * wo * c;
+    const float* r1 = dy + ((long long)b * ho + oy1) * wo * c;
+    float* orow = dx + ((long long)b * h + y) * w * c;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * cv; i += gridDim.x * blockDim.x) {
+        const int x = i / cv, ch = (i - x * cv) * 4;
+        int ox0, ox1; float wx0, wx1;
+        blur_down_adj2(x, wo, ox0, wx0, ox1, wx1);
+        const float4 a00 = *reinterpret_cast<const float4*>(r0 + (long long)ox0 * c + ch);
+        const float4 a01 = *reinterpret_cast<const float4*>(r0 + (long long)ox1 * c + ch);
+        const float4 a10 = *reinterpret_cast<const float4*>(r1 + (long long)ox0 * c + ch);
+        const float4 a11 = *reinterpret_cast<const float4*>(r1 + (long long)ox1 * c + ch);
+        const float k00 = wy0 * wx0, k01 = wy0 * wx1, k10 = wy1 * wx0, k11 = wy1 * wx1;
+        float4 acc;
+        acc.x = k00 * a00.x + k01 * a01.x + k10 * a10.x + k11 * a11.x;
+        acc.y = k00 * a00.y + k01 * a01.y + k10 * a10.y + k11 * a11.y;
+        acc.z = k00 * a00.z + k01 * a01.z + k10 * a10.z + k11 * a11.z;
+        acc.w = k00 * a00.w + k01 * a01.w + k10 * a10.w + k11 * a11.w;
+        *reinterpret_cast<float4*>(orow + (long long)x * c + ch) = acc;
     }
 }
 
@@ -689,59 +685,62 @@ __device__ inline void blur_up_taps(int u, int len, int src[2], float ws[2]) {
 
 __global__ void __launch_bounds__(256) blur_up_fwd_kernel(const float* __restrict__ x, int n, int h, int w, int c, float* __restrict__ y) {
     const int ho = 2 * h, wo = 2 * w, cv = c / 4;
-    const long long total = (long long)n * ho * wo * cv;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % cv) * 4;
-        long long t = i / cv;
-        const int ox = (int)(t % wo); t /= wo;
-        const int oy = (int)(t % ho);
-        const int b = (int)(t / ho);
-        int sy[2], sx[2]; float wy[2], wx[2];
-        blur_up_taps(oy, h, sy, wy); blur_up_taps(ox, w, sx, wx);
-        float4 acc = make_float4(0, 0, 0, 0);
-#pragma unroll
-        for (int a = 0; a < 2; a++)
-#pragma unroll
-            for (int d = 0; d < 2; d++) {
-                const float wgt = wy[a] * wx[d];
-                const float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * h + sy[a]) * w + sx[d]) * c + ch);
-                acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
-            }
-        *reinterpret_cast<float4*>(y + (((long long)b * ho + oy) * wo + ox) * c + ch) = acc;
+    const int oy = blockIdx.y, b = blockIdx.z;
+    int sy[2]; float wy[2];
+    blur_up_taps(oy, h, sy, wy);
+    const float* r0 = x + ((long long)b * h + sy[0]) * w * c;
+    const float* r1 = x + ((long long)b * h + sy[1]) * w * c;
+    float* orow = y + ((long long)b * ho + oy) * wo * c;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wo * cv; i += gridDim.x * blockDim.x) {
+        const int ox = i / cv, ch = (i - ox * cv) * 4;
+        int sx[2]; float wx[2];
+        blur_up_taps(ox, w, sx, wx);
+        const float4 a00 = *reinterpret_cast<const float4*>(r0 + (long long)sx[0] * c + ch);
+        const float4 a01 = *reinterpret_cast<const float4*>(r0 + (long long)sx[1] * c + ch);
+        const float4 a10 = *reinterpret_cast<const float4*>(r1 + (long long)sx[0] * c + ch);
+        const float4 a11 = *reinterpret_cast<const float4*>(r1 + (long long)sx[1] * c + ch);
+        const float k00 = wy[0] * wx[0], k01 = wy[0] * wx[1], k10 = wy[1] * wx[0], k11 = wy[1] * wx[1];
+        float4 acc;
+        acc.x = k00 * a00.x + k01 * a01.x + k10 * a10.x + k11 * a11.x;
+        acc.y = k00 * a00.y + k01 * a01.y + k10 * a10.y + k11 * a11.y;
+        acc.z = k00 * a00.z + k01 * a01.z + k10 * a10.z + k11 * a11.z;
+        acc.w = k00 * a00.w + k01 * a01.w + k10 * a10.w + k11 * a11.w;
+        *reinterpret_cast<float4*>(orow + (long long)ox * c + ch) = acc;
     }
 }
 
-// adjoint taps on one axis for source index m (input length len, output length 2*len)
-__device__ inline int blur_up_adj(int m, int len, int outs[6], float ws[6]) {
-    int cnt = 0;
-    outs[cnt] = 2 * m; ws[cnt++] = 0.75f;
-    outs[cnt] = 2 * m + 1; ws[cnt++] = 0.75f;
-    if (m + 1 <= len - 1) { outs[cnt] = 2 * (m + 1); ws[cnt++] = 0.25f; }   // y[2m'] uses x[m'-1]
-    if (m - 1 >= 0) { outs[cnt] = 2 * (m - 1) + 1; ws[cnt++] = 0.25f; }     // y[2m'+1] uses x[m'+1]
-    if (m == 0) { outs[cnt] = 0; ws[cnt++] = 0.25f; }                       // clamp at the low edge
-    if (m == len - 1) { outs[cnt] = 2 * len - 1; ws[cnt++] = 0.25f; }       // clamp at the high edge
-    return cnt;
+// Adjoint of blur_up in closed form: source m feeds outputs 2m-1 (0.25, if m > 0), 2m (0.75, +0.25 at the clamped low edge),
+// 2m+1 (0.75, +0.25 at the clamped high edge) and 2m+2 (0.25, if m + 1 < len).
+__device__ __forceinline__ void blur_up_adj4(int m, int len, int idx[4], float wt[4]) {
+    idx[0] = m > 0 ? 2 * m - 1 : 0;            wt[0] = m > 0 ? 0.25f : 0.f;
+    idx[1] = 2 * m;                            wt[1] = m == 0 ? 1.0f : 0.75f;
+    idx[2] = 2 * m + 1;                        wt[2] = m == len - 1 ? 1.0f : 0.75f;
+    idx[3] = m + 1 < len ? 2 * m + 2 : 2 * m;  wt[3] = m + 1 < len ? 0.25f : 0.f;
 }
 
 __global__ void __launch_bounds__(256) blur_up_bwd_kernel(const float* __restrict__ dy, int n, int h, int w, int c, float* __restrict__ dx) {
     const int ho = 2 * h, wo = 2 * w, cv = c / 4;
-    const long long total = (long long)n * h * w * cv;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % cv) * 4;
-        long long t = i / cv;
-        const int x = (int)(t % w); t /= w;
-        const int y = (int)(t % h);
-        const int b = (int)(t / h);
-        int oys[6], oxs[6]; float wy[6], wx[6];
-        const int ny = blur_up_adj(y, h, oys, wy), nx = blur_up_adj(x, w, oxs, wx);
+    const int y = blockIdx.y, b = blockIdx.z;
+    int oys[4]; float wy[4];
+    blur_up_adj4(y, h, oys, wy);
+    const float* rows[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) rows[a] = dy + ((long long)b * ho + oys[a]) * wo * c;
+    float* orow = dx + ((long long)b * h + y) * w * c;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * cv; i += gridDim.x * blockDim.x) {
+        const int x = i / cv, ch = (i - x * cv) * 4;
+        int oxs[4]; float wx[4];
+        blur_up_adj4(x, w, oxs, wx);
         float4 acc = make_float4(0, 0, 0, 0);
-        for (int a = 0; a < ny; a++)
-            for (int d = 0; d < nx; d++) {
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
                 const float wgt = wy[a] * wx[d];
-                const float4 v = *reinterpret_cast<const float4*>(dy + (((long long)b * ho + oys[a]) * wo + oxs[d]) * c + ch);
+                const float4 v = *reinterpret_cast<const float4*>(rows[a] + (long long)oxs[d] * c + ch);
                 acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
             }
-        *reinterpret_cast<float4*>(dx + (((long long)b * h + y) * w + x) * c + ch) = acc;
+        *reinterpret_cast<float4*>(orow + (long long)x * c + ch) = acc;
     }
 }
 
@@ -987,12 +986,17 @@ extern "C" int skit_norm_bwd_apply_ex(const float* g, const float* raw, int n, i
     return SKIT_OK;
 }
 
-#define SKIT_BLUR_ENTRY(name, kernel, work_h, work_w, cond)                                              \
+// rows_out x width_out: the tensor the kernel writes (one block row per output row, a few CTAs per SM in total)
+#define SKIT_BLUR_ENTRY(name, kernel, rows_out, width_out, cond)                                         \
     extern "C" int name(const float* a, int n, int h, int w, int c, float* b, void* stream) {           \
         SKIT_REQUIRE(a && b && n > 0 && h > 1 && w > 1 && c > 0 && c % 4 == 0 && (cond),                 \
                      #name ": bad arguments (n=%d h=%d w=%d c=%d)", n, h, w, c);                         \
-        const long long work = (long long)n * (work_h) * (work_w) * (c / 4);                             \
-        kernel<<<grid_for(work, 256), 256, 0, as_stream(stream)>>>(a, n, h, w, c, b);                    \
+        const int rows = (rows_out), per_row = (width_out) * (c / 4);                                    \
+        SKIT_REQUIRE(rows <= 65535 && n <= 65535, #name ": map too tall / batch too large for the row grid"); \
+        int bx = cdiv(per_row, 256);                                                                     \
+        const int want = cdiv(kSMs * 8, rows * n);                                                       \
+        if (bx > want) bx = want < 1 ? 1 : want;                                                         \
+        kernel<<<dim3(bx, rows, n), 256, 0, as_stream(stream)>>>(a, n, h, w, c, b);                      \
         return check_launch(#kernel);                                                                    \
     }
 
