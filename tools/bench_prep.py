@@ -24,6 +24,17 @@ def run(n, h, w, c):
     t = timeit(lambda: ops.norm_act_pad(raw, mr, ops.NORM_INSTANCE, act=ops.ACT_RELU, pad=1, pad_mode=ops.PAD_REFLECT, fmt=ops.FMT_BF16X2))
     print("   norm_act_pad -> bf16x2 pad 1: %.1f us" % (t * 1e3))
 
-run(1, 128, 128, 256)
-run(1, 512, 512, 64)
-run(64, 17, 17, 64)
+if __name__ == "__main__":
+    import subprocess
+    if len(sys.argv) > 1 and sys.argv[1] == "--one":        # the trunk shape only (ncu target)
+        run(1, 192, 192, 256)
+    elif len(sys.argv) > 1 and sys.argv[1] == "--worker":
+        run(1, 192, 192, 256)
+        run(1, 128, 128, 256)
+        run(1, 768, 768, 64)
+        run(64, 17, 17, 64)
+    else:
+        for unroll in ("4", "2", "1"):
+            for per_sm in ("4", "6", "8", "12"):
+                print("SKIT_REDUCE_UNROLL=%s SKIT_REDUCE_BLOCKS_PER_SM=%s" % (unroll, per_sm), flush=True)
+                subprocess.run([sys.executable, __file__, "--one"], env=dict(os.environ, SKIT_REDUCE_BLOCKS_PER_SM=per_sm, SKIT_REDUCE_UNROLL=unroll))

@@ -2,6 +2,7 @@
 // residual + halo + bf16 split (forward), the two-phase norm/activation backward, and the
 // antialiased blur resamplers with their adjoints.  All are HBM/L2-bandwidth bound: float4
 // accesses along the channel axis, grid-stride loops sized in multiples of the SM count.
+#include <cstdlib>
 #include "skit_common.cuh"
 
 namespace skit {
@@ -370,7 +371,8 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_kernel(BwdAP p) {
 
 // Row-tiled variant of phase A (see norm_act_pad_rows_kernel): float4 loads of every stream, the halo fold without
 // per-pixel divisions, per-thread register sums reduced across the block's pixel lanes, one fp64 atomic per channel per CTA.
-__global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, int cv, int rows_per_block, int xseg) {
+template <int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) act_norm_bwd_reduce_rows_kernel(BwdAP p, int cv, int rows_per_block, int xseg) {
     __shared__ float red[256 * 8];
     const int n = blockIdx.y;
     const int cl = threadIdx.x % cv, pl = threadIdx.x / cv, PL = 256 / cv;
@@ -388,15 +390,20 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, 
     float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
     const int y_end = min(p.h, (int)(blockIdx.x + 1) * rows_per_block);
     for (int y = blockIdx.x * rows_per_block; y < y_end; y++) {
-        int ys[3];
-        const int ny = p.dpad ? fold_coords(y, p.pad, p.h, p.pad_mode, ys) : 0;
+        // padded rows that alias source row y: the interior one, and for reflect padding the mirrored halo rows (-1 = none).
+        // Scalars, not an index list: a list indexed by a run-time count lives in local memory and costs every pixel a store.
+        const bool refl = p.dpad && p.pad_mode == SKIT_PAD_REFLECT;
+        const int yc = y + p.pad;
+        const int ylo = (refl && y >= 1 && y <= p.pad) ? p.pad - y : -1;
+        const int yhi = (refl && y <= p.h - 2 && y >= p.h - 1 - p.pad) ? p.pad + 2 * (p.h - 1) - y : -1;
+        const bool row_border = ylo >= 0 || yhi >= 0;
         const long long srow = ((long long)n * p.h + y) * p.w;
         const int xend = min(p.w, (int)(blockIdx.z + 1) * xseg);
-        for (int x0 = blockIdx.z * xseg + pl; x0 < xend; x0 += 4 * PL) {
-            // 4 pixels per pass: every independent 16-byte load is issued before the first use
-            float4 d[4], rw[4], q0[4];
+        for (int x0 = blockIdx.z * xseg + pl; x0 < xend; x0 += U * PL) {
+            // U pixels per pass: every independent 16-byte load is issued before the first use
+            float4 d[U], rw[U], q0[U];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < U; u++) {
                 const int x = x0 + u * PL;
                 const bool ok = x < xend;
                 d[u] = make_float4(0, 0, 0, 0); rw[u] = d[u]; q0[u] = d[u];
@@ -410,10 +417,10 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, 
                     }
                 }
                 if (p.raw) rw[u] = *reinterpret_cast<const float4*>(p.raw + (srow + x) * p.c + ch);
-                if (p.dpad) q0[u] = *reinterpret_cast<const float4*>(p.dpad + (((long long)n * hp + ys[0]) * wp + x + p.pad) * p.c + ch);
+                if (p.dpad) q0[u] = *reinterpret_cast<const float4*>(p.dpad + (((long long)n * hp + yc) * wp + x + p.pad) * p.c + ch);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < U; u++) {
                 const int x = x0 + u * PL;
                 if (x >= xend) continue;
                 const long long src = (srow + x) * p.c + ch;
@@ -427,14 +434,17 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_rows_kernel(BwdAP p, 
                     for (int j = 0; j < 4; j++) if (!(pre[j] > 0.f)) dv[j] = 0.f;
                 }
                 if (p.dpad) {
-                    dv[0] += q0[u].x; dv[1] += q0[u].y; dv[2] += q0[u].z; dv[3] += q0[u].w;   // the interior position (ys[0], x + pad)
-                    int xs[3];
-                    const int nx = fold_coords(x, p.pad, p.w, p.pad_mode, xs);
-                    if (ny > 1 || nx > 1) {     // border pixels also collect their reflected halo positions
-                        for (int a = 0; a < ny; a++)
-                            for (int b = 0; b < nx; b++) {
-                                if (a == 0 && b == 0) continue;
-                                const float4 q = *reinterpret_cast<const float4*>(p.dpad + (((long long)n * hp + ys[a]) * wp + xs[b]) * p.c + ch);
+                    dv[0] += q0[u].x; dv[1] += q0[u].y; dv[2] += q0[u].z; dv[3] += q0[u].w;   // the interior position (yc, x + pad)
+                    const int xlo = (refl && x >= 1 && x <= p.pad) ? p.pad - x : -1;
+                    const int xhi = (refl && x <= p.w - 2 && x >= p.w - 1 - p.pad) ? p.pad + 2 * (p.w - 1) - x : -1;
+                    if (row_border || xlo >= 0 || xhi >= 0) {     // border pixels also collect their reflected halo positions
+                        const int ycand[3] = {yc, ylo, yhi}, xcand[3] = {x + p.pad, xlo, xhi};
+#pragma unroll
+                        for (int a = 0; a < 3; a++)
+#pragma unroll
+                            for (int b = 0; b < 3; b++) {
+                                if ((a == 0 && b == 0) || ycand[a] < 0 || xcand[b] < 0) continue;
+                                const float4 q = *reinterpret_cast<const float4*>(p.dpad + (((long long)n * hp + ycand[a]) * wp + xcand[b]) * p.c + ch);
                                 dv[0] += q.x; dv[1] += q.y; dv[2] += q.z; dv[3] += q.w;
                             }
                     }
@@ -914,10 +924,24 @@ extern "C" int skit_act_norm_bwd_reduce_ex2(const float* dpad, int pad, int pad_
     p.inv_count = 1.0 / ((double)h * w * (norm_mode == SKIT_NORM_BATCH ? n : 1));
     const int P = h * w;
     if (rows_layout_ok(c) && dadd_c0 % 4 == 0 && dadd_ctot % 4 == 0) {
-        const int rpb = rows_per_block_for(h, n);
-        const int xs = xseg_for(h, w, n, 256 / (c / 4));
-        dim3 grid(cdiv(h, rpb), n, cdiv(w, xs));
-        act_norm_bwd_reduce_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
+        // pixels per pass / resident blocks: 2 pixels at 3 blocks per SM measured 47.8 us at 192 x 192 x 256 against 56.5 us for
+        // 4 pixels at 2 blocks per SM (profiles/r02f_bench_prep.txt); SKIT_REDUCE_UNROLL = 4 | 2 | 1 selects the variant.
+        // grid: the kernel pays a per-block tail (shared-memory reduction, 8 fp64 atomics
+        // per channel lane, fence + ticket): `per_sm` blocks per SM in total (SKIT_REDUCE_BLOCKS_PER_SM, default 6)
+        static int per_sm = -1;
+        if (per_sm < 0) { const char* e = getenv("SKIT_REDUCE_BLOCKS_PER_SM"); per_sm = e ? atoi(e) : 6; if (per_sm < 1) per_sm = 6; }
+        const int want_blocks = max(1, (kSMs * per_sm) / max(1, n));
+        const int rpb = max(1, cdiv(h, want_blocks));
+        const int row_blocks = cdiv(h, rpb);
+        const int PLr = 256 / (c / 4);
+        int xs = max(4 * PLr, cdiv(w, max(1, want_blocks / row_blocks)));
+        if (xs > w) xs = w;
+        dim3 grid(row_blocks, n, cdiv(w, xs));
+        static int unroll = -1;
+        if (unroll < 0) { const char* e = getenv("SKIT_REDUCE_UNROLL"); unroll = e ? atoi(e) : 2; }
+        if (unroll == 2) act_norm_bwd_reduce_rows_kernel<2, 3><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
+        else if (unroll == 1) act_norm_bwd_reduce_rows_kernel<1, 4><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
+        else act_norm_bwd_reduce_rows_kernel<4, 2><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
         return check_launch("act_norm_bwd_reduce_rows_kernel");
     }
     const int lanes_c = min(c / vec, 256), PL = 256 / lanes_c;
