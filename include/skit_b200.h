@@ -454,6 +454,43 @@ int skit_metric_ssim(const float* a, const float* b, int planes, int h, int w, c
 int skit_metric_normal_angle(const float* real, const float* fake, int n, int h, int w, float scale_nz, int clamp_fake,
                              double* out, void* stream);
 
+/* ---- Data pipeline (data/singleskit_dataset.py, data/dataset_util.py).  Byte / integer / fp64 work,
+ * bit-identical with what the reference computes on the host through Pillow, NumPy and OpenCV.  Images are HWC uint8 device buffers.
+ *   skit_resize_u8            `PIL.Image.resize((dw, dh), filter)` for 8-bit images of 1..4 bands (dataset_util.py:159-163 zoom_img,
+ *                             :194-201 crop_img, :219-231 make_power_2_img): Pillow's two-pass fixed-point resampler
+ *                             (src/libImaging/Resample.c; coefficients in double on the host, 22-bit fixed point on the device).
+ *                             `filter` takes PIL.Image.Resampling's own values.
+ *   skit_u8_crop_to_tensor    `img.crop((x0, y0, x0+w, y0+h))` (pixels outside read 0) + `transforms.ToTensor()` [+ `Normalize(0.5, 0.5)`]
+ *                             (singleskit_dataset.py:301-315): fp32 CHW.
+ *   skit_contact_centers      the centre loop of process_all_valid_patches (singleskit_dataset.py:745,768-803) for P touch patches stored
+ *                             back to back (pix_off[P+1] pixel offsets): for each patch, in_mask = whether its rectangle touches the object
+ *                             mask M, and the row-major list (as np.where orders it) of the linear pixel indices with center_mask > 0 whose
+ *                             patch x patch window of touch_mask * M_patch / 255 reaches 1; centers uses the same per-patch offsets,
+ *                             counts[p] entries are valid.  scratch = 3 * total_pixels bytes.
+ *   skit_touch_squares        the sampled squares (:812-860): for K selections (patch, cx, cy) the patch x patch windows of gx and gy
+ *                             (elements of elem_size 4 or 8 bytes, copied verbatim) -> t_images [K][2][patch][patch], and
+ *                             square_mask = touch_mask * M_patch / 255 in fp64 -> i_masks [K][patch][patch].
+ *   skit_laplacian_var_u8     `variance_of_laplacian(S_patch, ref=255)` (util/util.py:261-265) of K size x size windows at (x0, y0) of a
+ *                             single-band image (outside reads 0, as PIL's crop): uint8 wrap of (image - ref), cv2.Laplacian ksize 1 with
+ *                             reflect-101 borders, population variance in fp64 = the resampling weight before its clamp (:1053-1056). */
+#define SKIT_RESAMPLE_LANCZOS 1
+#define SKIT_RESAMPLE_BILINEAR 2
+#define SKIT_RESAMPLE_BICUBIC 3
+#define SKIT_RESAMPLE_BOX 4
+#define SKIT_RESAMPLE_HAMMING 5
+int skit_resize_u8(const unsigned char* src, int sh, int sw, int c, unsigned char* dst, int dh, int dw, int filter, void* stream);
+int skit_u8_crop_to_tensor(const unsigned char* src, int sh, int sw, int c, int y0, int x0, int h, int w, int normalize,
+                           float* dst, void* stream);
+int skit_contact_centers(const double* touch_mask, const unsigned char* center_mask, const long long* pix_off, long long total_pixels,
+                         const int* ph, const int* pw, const int* roi_x, const int* roi_y, int P, const unsigned char* M, int mh,
+                         int mw, int patch, unsigned char* scratch, int* counts, int* centers, int* in_mask, void* stream);
+int skit_touch_squares(const double* touch_mask, const long long* pix_off, const int* ph, const int* pw, const int* roi_x,
+                       const int* roi_y, int P, const unsigned char* M, int mh, int mw, const void* gx, const void* gy, int elem_size,
+                       const int* sel_patch, const int* sel_cx, const int* sel_cy, int K, int patch, void* t_images, double* i_masks,
+                       void* stream);
+int skit_laplacian_var_u8(const unsigned char* img, int h, int w, const int* x0, const int* y0, int K, int size, int ref, double* out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,139 @@
+"""TEST INFRASTRUCTURE ONLY (oracle/): golden vectors for the data pipeline.
+
+Builds a small seeded synthetic dataset in the reference's on-disk format (`trainS/ trainI/ trainM/ trainT/ valT/`,
+`*_tactile.npz` with the keys `data/dataset_util.py:18` documents), runs the UNMODIFIED reference
+`data/singleskit_dataset.py:SingleSkitDataset` on it (imported in place through oracle/ref_loader.py, CPU) and stores
+what its `data_dict` holds, plus PIL resize outputs, under tests/golden/data_pipeline.npz.
+
+    python oracle/make_data_golden.py            # needs /root/reference; run in the build container only
+"""
+import argparse
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def synth_dataset(root, seed=0, W=300, H=290, n_train=14, n_val=6):
+    """Write the synthetic dataset; everything derives from `seed` (numpy Generator), PNG is lossless."""
+    from PIL import Image
+    g = np.random.default_rng(seed)
+    for d in ("trainS", "trainI", "trainM", "trainT", "valT"):
+        os.makedirs(os.path.join(root, d), exist_ok=True)
+    yy, xx = np.mgrid[0:H, 0:W]
+    # sketch: white background with dark strokes
+    S = np.full((H, W), 255, np.uint8)
+    for _ in range(40):
+        x0, y0 = g.integers(0, W), g.integers(0, H)
+        ang = g.uniform(0, np.pi)
+        t = np.arange(0, g.integers(30, 160))
+        px = np.clip((x0 + t * np.cos(ang)).astype(int), 0, W - 1)
+        py = np.clip((y0 + t * np.sin(ang)).astype(int), 0, H - 1)
+        S[py, px] = g.integers(0, 90)
+        S[np.clip(py + 1, 0, H - 1), px] = g.integers(0, 90)
+    I = (127 + 90 * np.sin(xx[..., None] / (7.0 + np.arange(3)) + yy[..., None] / 11.0) + g.normal(0, 3, (H, W, 3))).clip(0, 255).astype(np.uint8)
+    M = ((((xx - W / 2) / (0.42 * W)) ** 2 + ((yy - H / 2) / (0.40 * H)) ** 2) <= 1).astype(np.uint8) * 255
+    Image.fromarray(S, "L").save(os.path.join(root, "trainS", "syn.png"))
+    Image.fromarray(I, "RGB").save(os.path.join(root, "trainI", "syn.png"))
+    Image.fromarray(M, "L").save(os.path.join(root, "trainM", "syn.png"))
+    for sub, n in (("trainT", n_train), ("valT", n_val)):
+        for i in range(n):
+            h, w = int(g.integers(52, 72)), int(g.integers(56, 80))
+            # every patch inside the region every admissible crop covers: the reference indexes its valid-patch lists by the raw
+            # patch index (`singleskit_dataset.py:742-743`), which only works when no patch is rejected
+            x, y = int(g.integers(72, 112)), int(g.integers(72, 118))
+            gx = g.uniform(-0.3, 0.3, (h, w)).astype(np.float32)
+            gy = g.uniform(-0.3, 0.3, (h, w)).astype(np.float32)
+            ty, tx = np.mgrid[0:h, 0:w]
+            cy, cx = h / 2 + g.uniform(-4, 4), w / 2 + g.uniform(-4, 4)
+            blob = (((tx - cx) / (0.45 * w)) ** 2 + ((ty - cy) / (0.45 * h)) ** 2) <= 1
+            core = (((tx - cx) / (0.12 * w)) ** 2 + ((ty - cy) / (0.12 * h)) ** 2) <= 1
+            core &= (ty >= 16) & (ty <= h - 16) & (tx >= 16) & (tx <= w - 16)
+            # one file per sub-directory: the reference lists directories sorted but file names in OS order (image_folder.py:52-57)
+            os.makedirs(os.path.join(root, sub, "p%02d" % i), exist_ok=True)
+            np.savez(os.path.join(root, sub, "p%02d" % i, "syn_%02d_tactile.npz" % i), gx_raw=gx, gy_raw=gy,
+                     vision_mask_x=x, vision_mask_y=y, vision_mask_h=h, vision_mask_w=w,
+                     touch_thresh=blob.astype(np.uint8) * 255, touch_center_thresh=core.astype(np.uint8) * 255)
+    return root
+
+
+def dataset_options(root, **kw):
+    """The option fields `SingleSkitDataset` reads (`data/singleskit_dataset.py:84-196`, `models/sinskitG_model.py:202-300`)."""
+    o = dict(dataroot=root, subdir_S="trainS", subdir_I="trainI", subdir_T="trainT", subdir_M="trainM", subdir_valT="valT",
+             is_train=True, isTrain=True, max_dataset_size=float("inf"), sketch_nc=1, image_nc=3, use_bg_mask=True,
+             preprocess="crop", random_scale_max=3.0, batch_size=1, crop_size=256, center_w=160, center_h=150, data_len=4,
+             w_resampling=True, resampling_w_min=1, resampling_w_max=10, T_resolution_multiplier=1, batch_size_G2=8,
+             batch_size_G2_val=16, sample_bbox_per_patch=2, serial_batches=False, num_threads=0)
+    o.update(kw)
+    return argparse.Namespace(**o)
+
+
+CASES = {
+    "crop": dict(data_len=3),                                                                   # the reference's training default: crop only
+    "zoom_crop": dict(preprocess="zoom_crop", random_scale_max=1.5, crop_size=192, data_len=2),   # LANCZOS zoom, then 192 -> 256 "power 2" resize
+    "noresample": dict(w_resampling=False, sample_bbox_per_patch=1, data_len=1),
+}
+
+
+def run_reference(root, opt, seed):
+    from oracle import ref_loader
+    ref_loader.load_reference()
+    cwd = os.getcwd()
+    os.chdir(root)      # the reference creates ./logs/<date> (myutils.py:14-29)
+    try:
+        import contextlib
+        import io
+        from data.singleskit_dataset import SingleSkitDataset
+        random.seed(seed); np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ds = SingleSkitDataset(opt)
+        return ds
+    finally:
+        os.chdir(cwd)
+
+
+def flatten(prefix, item, out):
+    import torch
+    from oracle import data_oracle as DO
+    for k, v in item.items():
+        key = prefix + "/" + k
+        if k in ("S", "I", "M"):      # full-resolution tensors go in as the bytes they were made from (checked lossless)
+            t = v.numpy()
+            u8 = np.round((t * 0.5 + 0.5) * 255 if k != "M" else t * 255).astype(np.uint8).transpose(1, 2, 0)
+            assert np.array_equal(DO.to_tensor_norm(u8, normalize=k != "M"), t), k
+            out[key + "_u8"] = u8
+        elif isinstance(v, torch.Tensor):
+            out[key] = v.numpy()
+        elif isinstance(v, np.ndarray):
+            out[key] = v
+        elif isinstance(v, dict):
+            out[key] = np.array([float(v[a]) for a in sorted(v)], np.float64)
+            out[key + "__keys"] = np.array(sorted(v))
+        elif isinstance(v, (list, tuple)) and len(v) and not isinstance(v[0], str):
+            out[key] = np.array(v)
+        elif isinstance(v, (list, tuple)) and len(v) == 0:
+            out[key] = np.zeros((0,))
+
+
+def main():
+    root = "/tmp/vts_data_golden"
+    synth_dataset(root)
+    out = {}
+    for name, kw in CASES.items():
+        opt = dataset_options(root, **kw)
+        ds = run_reference(root, opt, seed=123)
+        for idx in range(len(ds)):
+            flatten("%s/%d" % (name, idx), ds[idx], out)
+        out[name + "/len"] = np.array(len(ds))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "data_pipeline.npz"), **out)
+    print("wrote", len(out), "arrays")
+    for k in sorted(out)[:40]:
+        print(k, out[k].shape, out[k].dtype)
+
+
+if __name__ == "__main__":
+    main()

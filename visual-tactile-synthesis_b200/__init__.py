@@ -12,11 +12,13 @@ repo root registers this package under that name).  Layout:
   skit_model.py SinSKITGModel / SKITGModel train step + forward           (reference: models/{sinskitG,skitG}_model.py)
   dist.py       one-process-per-GPU data parallel: flat gradient buckets + NCCL all-reduce
   eval_metrics.py compute_evaluation_metric: PSNR / SSIM / angle error / MSE reductions    (reference: models/model_utils.py:431-561)
+  data_pipeline.py SingleSkitDataset on the device: Pillow-exact resize, crop, contact-centre search (reference: data/singleskit_dataset.py, data/dataset_util.py)
 """
-from . import _lib, ops, networks, model_utils, patchnce, skit_model, dist, sg2_generator, lpips_vgg, eval_metrics  # noqa: F401
+from . import _lib, ops, networks, model_utils, patchnce, skit_model, dist, sg2_generator, lpips_vgg, eval_metrics, data_pipeline  # noqa: F401
 from .networks import define_D, define_F, define_G, GANLoss, PatchSampleF  # noqa: F401
 from .patchnce import PatchNCELoss  # noqa: F401
 from .model_utils import get_patch_in_input, compute_normal, find_coords_for_patch  # noqa: F401
+from .data_pipeline import SingleSkitDataset  # noqa: F401
 from .skit_model import SinSKITGModel, SKITGModel, default_options, reference_default_options  # noqa: F401
 
 __all__ = ["define_G", "define_D", "define_F", "GANLoss", "PatchSampleF", "ops", "networks"]

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libskit_b200.so")
-SOURCES = ["simt_conv.cu", "tc_conv.cu", "tc_conv_halo.cu", "tc_wgrad.cu", "prep.cu", "image_ops.cu", "sg2_ops.cu", "lpips_ops.cu", "metrics.cu"]
+SOURCES = ["simt_conv.cu", "tc_conv.cu", "tc_conv_halo.cu", "tc_wgrad.cu", "prep.cu", "image_ops.cu", "sg2_ops.cu", "lpips_ops.cu", "metrics.cu", "data_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -225,7 +225,7 @@ class SinSKITGModel:
         self.data_phase = phase
         n, _, h, w = input["S"].shape
         # without use_bg_mask the reference skips every mask multiply (:721-726,1317-1319,1339-1341): an all-ones mask is the same
-        M = input["M"].float() if opt.use_bg_mask else torch.ones(n, 1, h, w)
+        M = input["M"].float() if opt.use_bg_mask else torch.ones(n, 1, h, w, device=input["S"].device)
         host = {"M": M, "real_S": input["S"].float()}
         if "I" in input:
             host["real_I"] = input["I"].float()
@@ -239,7 +239,7 @@ class SinSKITGModel:
                                           % (tuple(T.shape),))
             host["I_masks"] = input[pre + "I_masks"].float().reshape(NT, 1, 32, 32)
             host["real_T"] = T.reshape(NT, 2, 32, 32)
-            ox, oy, cs = find_coords_for_patch(input[pre + "T_coords"].numpy() if torch.is_tensor(input[pre + "T_coords"]) else input[pre + "T_coords"])
+            ox, oy, cs = find_coords_for_patch(input[pre + "T_coords"].cpu().numpy() if torch.is_tensor(input[pre + "T_coords"]) else input[pre + "T_coords"])
             if np.any(np.asarray(cs) != 32 * opt.T_resolution_multiplier):
                 # the reference then cuts a smaller / larger window and resizes it (model_utils.py:337-341): not built
                 raise NotImplementedError("patch cutout size %s != patch size 32 (resize_ratio != 1): the resampling gather of "
@@ -253,6 +253,11 @@ class SinSKITGModel:
         self.h2d_bytes = 0
         for k, v in host.items():
             v = v.contiguous()
+            if v.is_cuda:
+                # items of the device dataset (data_pipeline.SingleSkitDataset) are already in HBM: a device-to-device copy into the
+                # persistent buffer (the source is the dataset's cached tensor and must not be masked in place)
+                self._stage(k, v.to(dev))
+                continue
             if not v.is_pinned():
                 v = v.pin_memory()
             self.h2d_bytes += v.numel() * v.element_size()
@@ -312,7 +317,8 @@ class SinSKITGModel:
         if torch.is_tensor(cur) and cur.is_cuda and cur.shape == host_t.shape and cur.dtype == host_t.dtype:
             cur.copy_(host_t, non_blocking=True)
         else:
-            setattr(self, name, host_t.to(self.device, non_blocking=True))
+            # a tensor that already lives on the device is cloned: the staged buffers are masked in place below
+            setattr(self, name, host_t.to(self.device).clone() if host_t.is_cuda else host_t.to(self.device, non_blocking=True))
             self._input_gen += 1
 
     _RING = 4
