@@ -154,3 +154,117 @@ def laplacian_var_u8(patch_u8, ref=255):
     p = np.pad(a, 1, mode="reflect")
     lap = p[:-2, 1:-1] + p[2:, 1:-1] + p[1:-1, :-2] + p[1:-1, 2:] - 4 * a
     return float(np.var(lap.astype(np.float64)))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# The dataset itself: a plain numpy restatement of SingleSkitDataset.preprocess_data (data/singleskit_dataset.py:194-432),
+# find_validate_touch_patches_and_coords (:434-660) and process_all_valid_patches (:662-1128) for the cases the reference's own
+# data satisfies (every touch patch inside every crop, contact masks present, T_resolution_multiplier 1).  Draws from Python's
+# `random` / `np.random` in the reference's call order, so a seeded run reproduces its items (tests/golden/data_pipeline.npz).
+# Also the CPU arm of tools/bench_data.py.
+def _walk_files(d, suffix):
+    import os
+    out = []
+    for root, _, fnames in sorted(os.walk(d, followlinks=True)):            # data/image_folder.py:28-61
+        for f in fnames:
+            if f.endswith(suffix):
+                out.append(os.path.join(root, f))
+    return out
+
+
+def _load_touch(path):
+    z = np.load(path)                                                       # data/dataset_util.py:5-62
+    tm, cm = z["touch_thresh"], z["touch_center_thresh"]
+    if np.max(tm) > 1:
+        tm = tm / 255
+    if np.max(cm) > 1:
+        cm = cm / 255
+    return z["gx_raw"], z["gy_raw"], z["vision_mask_x"], z["vision_mask_y"], z["vision_mask_h"], z["vision_mask_w"], tm, cm
+
+
+def dataset_items(opt):
+    """-> list of item dicts (numpy arrays; S / I / M as the final uint8 images `S_u8` ...)."""
+    import os
+    import random
+    from PIL import Image
+    n_items = opt.data_len
+    S = np.array(Image.open(_walk_files(os.path.join(opt.dataroot, opt.subdir_S), ".png")[0]).convert("L"))
+    I = np.array(Image.open(_walk_files(os.path.join(opt.dataroot, opt.subdir_I), ".png")[0]).convert("RGB"))
+    M = np.array(Image.open(_walk_files(os.path.join(opt.dataroot, opt.subdir_M), ".png")[0]).convert("L"))
+    sets = {"": [_load_touch(p) for p in _walk_files(os.path.join(opt.dataroot, opt.subdir_T), "_tactile.npz")]}
+    if opt.subdir_valT is not None:
+        sets["val_"] = [_load_touch(p) for p in _walk_files(os.path.join(opt.dataroot, opt.subdir_valT), "_tactile.npz")]
+    A_zoom = 1 / opt.random_scale_max if opt.is_train else 1                # :176-186
+    zoom = np.random.uniform(A_zoom, 1.0, size=(n_items // opt.batch_size + 1, 1, 2))
+    zoom = np.reshape(np.tile(zoom, (1, opt.batch_size, 1)), [-1, 2])
+    items = []
+    crop = opt.crop_size
+    for index in range(n_items):
+        sf_h, sf_w = (zoom[0] if "zoom" in opt.preprocess else (1, 1))      # :238-254 (always level 0)
+
+        def stage12(img):
+            h, w = img.shape[:2]
+            if "zoom" in opt.preprocess:
+                img = pil_resize_u8(img, int(round(h * sf_h)), int(round(w * sf_w)))        # dataset_util.py:159-163
+            h, w = img.shape[:2]
+            ratio = 1 if (w >= crop and h >= crop) else max(crop / w, crop / h)             # :188-192
+            return pil_resize_u8(img, int(round(h * ratio)), int(round(w * ratio))), ratio
+        S2, ratio = stage12(S)
+        I2, _ = stage12(I)
+        M2, _ = stage12(M)
+        h, w = S2.shape[:2]
+        if "crop" not in opt.preprocess:                                     # dataset_util.py:165-183
+            cx, cy = (w - crop) // 2, (h - crop) // 2
+        elif opt.center_w > 0 or opt.center_h > 0:
+            buf = min(max(0, (w - opt.center_w) // 2), max(0, (h - opt.center_h) // 2), h - crop, w - crop)
+            cx = random.randint(0, buf); cy = random.randint(0, buf)
+        else:
+            cx = random.randint(0, max(0, w - crop)); cy = random.randint(0, max(0, h - crop))
+        t = int(round(crop / 256) * 256)                                     # :219-231
+        rr = 1 if t == crop else t / crop
+        fin = lambda a: pil_resize_u8(a[cy:cy + crop, cx:cx + crop], t, t)
+        S3, I3, M3 = fin(S2), fin(I2), fin(M2)
+        item = {"S_u8": S3, "I_u8": I3, "M_u8": M3,
+                "augmentation_params": {"H": S.shape[1], "W": S.shape[0], "scale_factor_h": sf_h, "scale_factor_w": sf_w, "crop_size_h": crop,
+                                        "crop_size_w": crop, "resize_ratio": ratio, "crop_pos_x": cx, "crop_pos_y": cy, "resize_ratio_w": rr,
+                                        "resize_ratio_h": rr, "patch_crop_size": 32}}
+        for pre, patches in sets.items():
+            rois = []
+            for (_, _, x, y, ph, pw, _, _) in patches:                       # :492-560
+                if "padded" in opt.dataroot:
+                    ps = int(opt.dataroot.split("padded_")[1].split("/")[0].split("_")[0])
+                    x = x + (ps - opt.center_w) // 2; y = y + (ps - opt.center_h) // 2
+                x1, y1, h1, w1 = x * sf_w, y * sf_h, ph * sf_h, pw * sf_w
+                x2, y2, h2, w2 = x1 * ratio - cx, y1 * ratio - cy, h1 * ratio, w1 * ratio
+                assert not (x2 < 0 or x2 + w2 > crop or y2 < 0 or y2 + h2 > crop), "patch outside the crop (singleskit_dataset.py:742-751)"
+                rois.append([int(round(x2 * rr)), int(round(y2 * rr)), int(round(h2 * rr)), int(round(w2 * rr))])
+            T_images, coords, masks, full = [], [], [], []
+            for (gx, gy, _, _, _, _, tm, cm), (x3, y3, h3, w3) in zip(patches, rois):       # :738-860
+                if np.sum(M3[y3:y3 + h3, x3:x3 + w3]) == 0:
+                    continue
+                full.append([x3, y3, h3, w3])
+                cs = contact_centers(tm, cm, M3, x3, y3)
+                num = min(len(cs), opt.sample_bbox_per_patch)
+                sel = random.sample(range(len(cs)), num) if opt.is_train else np.arange(len(cs) // 2, len(cs) // 2 + num)
+                for k in sel:
+                    px, py = cs[k]
+                    win = (slice(py - 16, py + 16), slice(px - 16, px + 16))
+                    T_images.append(np.stack([gx[win], gy[win]]))
+                    coords.append([x3, y3, h3, w3, 32, 1, px - 16, py - 16])
+                    masks.append(tm[win] * crop_zero(M3, x3 + px - 16, y3 + py - 16, 32) / 255)
+            n = len(coords)
+            if pre == "" and opt.is_train and opt.w_resampling:              # :1000-1056, :623-631
+                wts = [min(max(opt.resampling_w_min, laplacian_var_u8(crop_zero(S3, c[0] + c[6], c[1] + c[7], 32))), opt.resampling_w_max)
+                       for c in coords]
+                pick = random.choices(range(n), weights=np.array(wts), k=min(opt.batch_size_G2, n) if opt.batch_size_G2 > 0 else n)
+            elif opt.is_train:
+                k = opt.batch_size_G2 if pre == "" else opt.batch_size_G2_val
+                pick = random.sample(range(n), min(k, n) if k > 0 else n)
+            else:
+                pick = list(range(n))
+            item[pre + "T_images"] = np.stack(T_images)[pick]
+            item[pre + "T_coords"] = np.stack(coords)[pick]
+            item[pre + "I_masks"] = np.stack(masks)[pick]
+            item[pre + "full_T_coords"] = np.array(full)
+        items.append(item)
+    return items

@@ -18,7 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def synth_dataset(root, seed=0, W=300, H=290, n_train=14, n_val=6):
+def synth_dataset(root, seed=0, W=300, H=290, n_train=14, n_val=6, patch_h=(52, 72), patch_w=(56, 80), patch_x=(72, 112), patch_y=(72, 118),
+                  strokes=40):
     """Write the synthetic dataset; everything derives from `seed` (numpy Generator), PNG is lossless."""
     from PIL import Image
     g = np.random.default_rng(seed)
@@ -27,7 +28,7 @@ def synth_dataset(root, seed=0, W=300, H=290, n_train=14, n_val=6):
     yy, xx = np.mgrid[0:H, 0:W]
     # sketch: white background with dark strokes
     S = np.full((H, W), 255, np.uint8)
-    for _ in range(40):
+    for _ in range(strokes):
         x0, y0 = g.integers(0, W), g.integers(0, H)
         ang = g.uniform(0, np.pi)
         t = np.arange(0, g.integers(30, 160))
@@ -42,10 +43,10 @@ def synth_dataset(root, seed=0, W=300, H=290, n_train=14, n_val=6):
     Image.fromarray(M, "L").save(os.path.join(root, "trainM", "syn.png"))
     for sub, n in (("trainT", n_train), ("valT", n_val)):
         for i in range(n):
-            h, w = int(g.integers(52, 72)), int(g.integers(56, 80))
+            h, w = int(g.integers(*patch_h)), int(g.integers(*patch_w))
             # every patch inside the region every admissible crop covers: the reference indexes its valid-patch lists by the raw
             # patch index (`singleskit_dataset.py:742-743`), which only works when no patch is rejected
-            x, y = int(g.integers(72, 112)), int(g.integers(72, 118))
+            x, y = int(g.integers(*patch_x)), int(g.integers(*patch_y))
             gx = g.uniform(-0.3, 0.3, (h, w)).astype(np.float32)
             gy = g.uniform(-0.3, 0.3, (h, w)).astype(np.float32)
             ty, tx = np.mgrid[0:h, 0:w]

@@ -101,3 +101,24 @@ def test_oracle_reproduces_reference_touch_squares(tmp_path):
         assert (cx, cy) in centres
         win = tm[cy - 16:cy + 16, cx - 16:cx + 16] * DO.crop_zero(M3, int(row[0]) + cx - 16, int(row[1]) + cy - 16, 32) / 255
         assert np.array_equal(win, mask)
+
+
+@pytest.mark.parametrize("case", ["crop", "zoom_crop", "noresample"])
+def test_dataset_oracle_reproduces_reference_items(case, tmp_path):
+    """The numpy restatement of the whole dataset (oracle `dataset_items`), seeded like the golden run, gives the reference's items."""
+    import random
+    pytest.importorskip("PIL.Image")
+    d = np.load(GOLD)
+    root = MG.synth_dataset(str(tmp_path / "ds"))
+    opt = MG.dataset_options(root, **MG.CASES[case])
+    random.seed(123); np.random.seed(123)
+    items = DO.dataset_items(opt)
+    assert len(items) == int(d[case + "/len"])
+    for idx, item in enumerate(items):
+        pre = "%s/%d/" % (case, idx)
+        assert np.array_equal(item["S_u8"], d[pre + "S_u8"][:, :, 0]) and np.array_equal(item["I_u8"], d[pre + "I_u8"])
+        assert np.array_equal(item["M_u8"], d[pre + "M_u8"][:, :, 0])
+        for k in ("T_images", "T_coords", "I_masks", "full_T_coords", "val_T_images", "val_T_coords", "val_I_masks", "val_full_T_coords"):
+            assert np.array_equal(item[k], d[pre + k]), (case, idx, k)
+        keys = list(d[pre + "augmentation_params__keys"])
+        assert np.array_equal(np.array([float(item["augmentation_params"][a]) for a in keys]), d[pre + "augmentation_params"])

@@ -185,3 +185,20 @@ def test_dataset_rejects_patches_outside_the_crop(V, tmp_path):
     random.seed(5); np.random.seed(5)
     with pytest.raises(IndexError, match="valid-patch bookkeeping"):
         V.SingleSkitDataset(opt)
+
+
+def test_host_items_go_through_a_pinning_loader(V, tmp_path):
+    """The reference's loader settings (data/__init__.py:75-82: pin_memory=True) with `host_items`: same values, host tensors."""
+    d = np.load(GOLD)
+    root = MG.synth_dataset(str(tmp_path / "ds"))
+    opt = MG.dataset_options(root, **MG.CASES["crop"])
+    random.seed(123); np.random.seed(123)
+    ds = V.SingleSkitDataset(opt, host_items=True)
+    loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=0, drop_last=True, pin_memory=True)
+    for idx, batch in enumerate(loader):
+        assert not batch["S"].is_cuda and batch["S"].is_pinned()
+        item = {k: (v[0] if torch.is_tensor(v) else v) for k, v in batch.items()}
+        ref = DO.to_tensor_norm(d["crop/%d/S_u8" % idx])
+        assert np.array_equal(item["S"].numpy(), ref)
+        assert np.array_equal(item["T_images"].numpy(), d["crop/%d/T_images" % idx])
+        assert np.array_equal(item["T_coords"].numpy(), d["crop/%d/T_coords" % idx])

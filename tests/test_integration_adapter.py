@@ -74,3 +74,24 @@ def test_reference_option_parser_accepts_the_adapter(ref_models, tmp_path):
                      # skitG-only options (models/skitG_model.py:255-276), read with their defaults when absent
                      "use_style_code", "style_code_mode", "style_code_mapping_mode", "style_code_dim", "num_layer_style_code"):
             assert hasattr(opt, k), k
+
+
+def test_reference_discovers_the_dataset_adapter(ref_models):
+    """data/__init__.py:18-40 finds `b200singleskit_dataset.py`, and its option setter carries the reference dataset's own flags."""
+    import argparse
+    import data
+    import vts_b200
+    from data.base_dataset import BaseDataset
+    from data.singleskit_dataset import SingleSkitDataset as RefDataset
+    integ = os.path.join(ROOT, "integration")
+    if integ not in data.__path__:
+        data.__path__.append(integ)
+    cls = data.find_dataset_using_name("b200singleskit")
+    assert issubclass(cls, BaseDataset) and issubclass(cls, vts_b200.SingleSkitDataset)
+    for meth in ("__getitem__", "__len__", "preprocess_data", "find_validate_touch_patches_and_coords"):
+        assert getattr(cls, meth).__qualname__.split(".")[0] == "SingleSkitDataset", meth
+    assert not getattr(cls, "__abstractmethods__", None)
+    for is_train in (True, False):
+        mine = data.get_option_setter("b200singleskit")(argparse.ArgumentParser(), is_train).parse_args([])
+        ref = RefDataset.modify_commandline_options(argparse.ArgumentParser(), is_train).parse_args([])
+        assert vars(mine) == vars(ref)

@@ -312,7 +312,9 @@ class SingleSkitDataset(torch.utils.data.Dataset):
             parser.set_defaults(subdir_S="testS", subdir_I="testI", subdir_T="testT", subdir_M="testM", subdir_valT=None, is_train=False)
         return parser
 
-    def __init__(self, opt, verbose=False, default_len=1000, device=None, cache_bytes=8 << 30):
+    def __init__(self, opt, verbose=False, default_len=1000, device=None, cache_bytes=8 << 30, host_items=None):
+        """`host_items` (or `opt.data_host_items`): return host tensors, as the reference's items are — for its own
+        `CustomDatasetDataLoader` (data/__init__.py:75-82), whose `pin_memory=True` cannot take CUDA tensors.  Default: device items."""
         L.load()     # fails loudly when the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("SingleSkitDataset (B200 path) needs a CUDA device; there is no CPU fallback")
@@ -324,8 +326,10 @@ class SingleSkitDataset(torch.utils.data.Dataset):
         self.data_dict = {}
         self.data_len = opt.data_len if hasattr(opt, "data_len") else default_len
         self._cache_budget = cache_bytes
+        self.host_items = bool(getattr(opt, "data_host_items", False)) if host_items is None else bool(host_items)
         self._cache_used = 0
         self._image_cache = {}
+        self._host_cache = {}
 
         self.dir_S = os.path.join(opt.dataroot, opt.subdir_S)
         self.dir_I = os.path.join(opt.dataroot, opt.subdir_I)
@@ -568,6 +572,10 @@ class SingleSkitDataset(torch.utils.data.Dataset):
         assert index in self.data_dict.keys(), "Cannot find index %d in dataset" % (index)
         item = dict(self.data_dict[index])
         item.update(self._images_for(index))
+        if self.host_items:
+            if index not in self._host_cache:      # one device -> host copy per item, then the same host tensors every epoch
+                self._host_cache[index] = {k: v.cpu() for k, v in item.items() if torch.is_tensor(v)}
+            item.update(self._host_cache[index])
         return item
 
     def __len__(self):
