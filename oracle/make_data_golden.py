@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 
 
 def synth_dataset(root, seed=0, W=300, H=290, n_train=14, n_val=6, patch_h=(52, 72), patch_w=(56, 80), patch_x=(72, 112), patch_y=(72, 118),
-                  strokes=40):
+                  strokes=40, pad_offset=(0, 0)):
     """Write the synthetic dataset; everything derives from `seed` (numpy Generator), PNG is lossless."""
     from PIL import Image
     g = np.random.default_rng(seed)
@@ -46,7 +46,7 @@ def synth_dataset(root, seed=0, W=300, H=290, n_train=14, n_val=6, patch_h=(52, 
             h, w = int(g.integers(*patch_h)), int(g.integers(*patch_w))
             # every patch inside the region every admissible crop covers: the reference indexes its valid-patch lists by the raw
             # patch index (`singleskit_dataset.py:742-743`), which only works when no patch is rejected
-            x, y = int(g.integers(*patch_x)), int(g.integers(*patch_y))
+            x, y = int(g.integers(*patch_x)) - pad_offset[0], int(g.integers(*patch_y)) - pad_offset[1]
             gx = g.uniform(-0.3, 0.3, (h, w)).astype(np.float32)
             gy = g.uniform(-0.3, 0.3, (h, w)).astype(np.float32)
             ty, tx = np.mgrid[0:h, 0:w]
@@ -97,6 +97,40 @@ def run_reference(root, opt, seed):
         os.chdir(cwd)
 
 
+SKIT_MATERIALS = ("matA", "matB")
+SKIT_CASE = dict(preprocess="zoom_crop", random_scale_max=1.3, crop_size=256, data_len=3, material_list=list(SKIT_MATERIALS), padded_size=300,
+                 load_contact_mask=True)
+
+
+def synth_skit_datasets(base):
+    """Two materials in the directory layout `skit_dataset.py:141` expects under <base>/datasets/.  The ROIs are stored in the unpadded
+    (center_w x center_h) frame, as the reference's "padded" data does (`global_padding_find_coords`, dataset_util.py:240-243)."""
+    for k, mat in enumerate(SKIT_MATERIALS):
+        synth_dataset(os.path.join(base, "datasets", "singleskit_%s_padded_300_x1" % mat), seed=10 + k, pad_offset=((300 - 160) // 2, (300 - 150) // 2))
+    return base
+
+
+def skit_options(base):
+    return dataset_options(os.path.join("./datasets", "singleskit_%s_padded_300_x1/" % SKIT_MATERIALS[0]), **SKIT_CASE)
+
+
+def run_reference_skit(base, opt, seed):
+    from oracle import ref_loader
+    ref_loader.load_reference()
+    cwd = os.getcwd()
+    os.chdir(base)      # material directories are relative to the working directory (skit_dataset.py:141)
+    try:
+        import contextlib
+        import io
+        from data.skit_dataset import SkitDataset
+        random.seed(seed); np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ds = SkitDataset(opt)
+        return ds
+    finally:
+        os.chdir(cwd)
+
+
 def flatten(prefix, item, out):
     import torch
     from oracle import data_oracle as DO
@@ -130,6 +164,13 @@ def main():
         for idx in range(len(ds)):
             flatten("%s/%d" % (name, idx), ds[idx], out)
         out[name + "/len"] = np.array(len(ds))
+    base = synth_skit_datasets("/tmp/vts_data_golden_skit")
+    ds = run_reference_skit(base, skit_options(base), seed=321)
+    for idx in range(len(ds)):
+        flatten("skit/%d" % idx, ds[idx], out)
+        out["skit/%d/name" % idx] = np.array(ds[idx]["name"])
+        out["skit/%d/M_paths" % idx] = np.array(ds[idx]["M_paths"])
+    out["skit/len"] = np.array(len(ds))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "data_pipeline.npz"), **out)
     print("wrote", len(out), "arrays")
     for k in sorted(out)[:40]:

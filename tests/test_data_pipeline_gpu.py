@@ -202,3 +202,23 @@ def test_host_items_go_through_a_pinning_loader(V, tmp_path):
         assert np.array_equal(item["S"].numpy(), ref)
         assert np.array_equal(item["T_images"].numpy(), d["crop/%d/T_images" % idx])
         assert np.array_equal(item["T_coords"].numpy(), d["crop/%d/T_coords" % idx])
+
+
+def test_multi_material_dataset_matches_reference_golden(V, tmp_path, monkeypatch):
+    """`SkitDataset` (data/skit_dataset.py): two materials round-robin, a LANCZOS zoom level per index, ROIs through the "padded"
+    offset, the ratio resize of a zoomed source smaller than the crop — against the reference class's own items."""
+    d = np.load(GOLD)
+    base = MG.synth_skit_datasets(str(tmp_path / "skit"))
+    monkeypatch.chdir(base)                       # material directories are relative to the working directory, as in the reference
+    opt = MG.skit_options(base)
+    random.seed(321); np.random.seed(321)
+    ds = V.SkitDataset(opt)
+    assert len(ds) == int(d["skit/len"])
+    for idx in range(len(ds)):
+        item = ds[idx]
+        _check_item(d, "skit/%d" % idx, item)
+        assert item["name"] == str(d["skit/%d/name" % idx]) and item["M_paths"] == str(d["skit/%d/M_paths" % idx])
+    opt2 = MG.skit_options(base)
+    opt2.load_contact_mask = False
+    with pytest.raises(NotImplementedError, match="load_contact_mask"):
+        V.SkitDataset(opt2)

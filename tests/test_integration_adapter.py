@@ -86,6 +86,8 @@ def test_reference_discovers_the_dataset_adapter(ref_models):
     integ = os.path.join(ROOT, "integration")
     if integ not in data.__path__:
         data.__path__.append(integ)
+    multi = data.find_dataset_using_name("b200skit")
+    assert issubclass(multi, BaseDataset) and issubclass(multi, vts_b200.SkitDataset) and not getattr(multi, "__abstractmethods__", None)
     cls = data.find_dataset_using_name("b200singleskit")
     assert issubclass(cls, BaseDataset) and issubclass(cls, vts_b200.SingleSkitDataset)
     for meth in ("__getitem__", "__len__", "preprocess_data", "find_validate_touch_patches_and_coords"):

@@ -18,7 +18,7 @@ from . import _lib, ops, networks, model_utils, patchnce, skit_model, dist, sg2_
 from .networks import define_D, define_F, define_G, GANLoss, PatchSampleF  # noqa: F401
 from .patchnce import PatchNCELoss  # noqa: F401
 from .model_utils import get_patch_in_input, compute_normal, find_coords_for_patch  # noqa: F401
-from .data_pipeline import SingleSkitDataset  # noqa: F401
+from .data_pipeline import SingleSkitDataset, SkitDataset  # noqa: F401
 from .skit_model import SinSKITGModel, SKITGModel, default_options, reference_default_options  # noqa: F401
 
 __all__ = ["define_G", "define_D", "define_F", "GANLoss", "PatchSampleF", "ops", "networks"]

@@ -286,20 +286,31 @@ def laplacian_var(img1, x0, y0, size, ref=255):
 
 
 # ------------------------------------------------------------------------------------------------ the dataset
+class _Material:
+    """One object's resident sources: decoded uint8 images and its two touch sets."""
+
+    def __init__(self, S_path, S_img, I_img, M_img, M_path, touch, val_touch, extra=None):
+        self.S_path, self.S_img, self.I_img, self.M_img, self.M_path = S_path, S_img, I_img, M_img, M_path
+        self.touch, self.val_touch = touch, val_touch
+        self.extra = extra or {}          # further images that ride through the same zoom / crop / resize chain (skitG's style_I / style_M)
+
+
+def _str2bool(v):        # util/util.py str2bool
+    if isinstance(v, bool):
+        return v
+    if v.lower() in ("yes", "true", "t", "y", "1"):
+        return True
+    if v.lower() in ("no", "false", "f", "n", "0"):
+        return False
+    raise ValueError("Boolean value expected.")
+
+
 class SingleSkitDataset(torch.utils.data.Dataset):
     """data/singleskit_dataset.py:28 — one sketch / mask / image, `data_len` augmentations, touch patches with their coordinates."""
 
     @staticmethod
     def modify_commandline_options(parser, is_train):
-        """singleskit_dataset.py:43-82."""
-        def _str2bool(v):        # util/util.py str2bool
-            if isinstance(v, bool):
-                return v
-            if v.lower() in ("yes", "true", "t", "y", "1"):
-                return True
-            if v.lower() in ("no", "false", "f", "n", "0"):
-                return False
-            raise ValueError("Boolean value expected.")
+        """singleskit_dataset.py:43-82 (skit_dataset.py:43-84 declares the same arguments)."""
         parser.add_argument("--subdir_S", type=str, default="trainS", help="subdirectory for S input")
         parser.add_argument("--subdir_I", type=str, default="trainI", help="subdirectory for I input")
         parser.add_argument("--subdir_T", type=str, default="trainT", help="subdirectory for T input")
@@ -312,12 +323,14 @@ class SingleSkitDataset(torch.utils.data.Dataset):
             parser.set_defaults(subdir_S="testS", subdir_I="testI", subdir_T="testT", subdir_M="testM", subdir_valT=None, is_train=False)
         return parser
 
+    PATCH = 32
+
     def __init__(self, opt, verbose=False, default_len=1000, device=None, cache_bytes=8 << 30, host_items=None):
         """`host_items` (or `opt.data_host_items`): return host tensors, as the reference's items are — for its own
         `CustomDatasetDataLoader` (data/__init__.py:75-82), whose `pin_memory=True` cannot take CUDA tensors.  Default: device items."""
         L.load()     # fails loudly when the CUDA library is missing
         if not torch.cuda.is_available():
-            raise RuntimeError("SingleSkitDataset (B200 path) needs a CUDA device; there is no CPU fallback")
+            raise RuntimeError("%s (B200 path) needs a CUDA device; there is no CPU fallback" % type(self).__name__)
         self.opt = opt
         self.root = opt.dataroot
         self.current_epoch = 0
@@ -330,7 +343,39 @@ class SingleSkitDataset(torch.utils.data.Dataset):
         self._cache_used = 0
         self._image_cache = {}
         self._host_cache = {}
+        self._src_cache = {}
+        self._index_key = {}
+        if getattr(opt, "T_resolution_multiplier", 1) != 1:
+            raise NotImplementedError("T_resolution_multiplier != 1 is outside the B200 path (DESIGN.md section 10)")
+        self._load_materials()
+        for m in self.materials:
+            if m.touch is not None and m.M_img is None:
+                raise ValueError("touch patches are validated against the object mask (singleskit_dataset.py:742-745): use_bg_mask must be True")
+        A_zoom = 1 / self.opt.random_scale_max if self.opt.is_train else 1
+        zoom_levels_A = np.random.uniform(A_zoom, 1.0, size=(len(self) // opt.batch_size + 1, 1, 2))
+        self.zoom_levels_A = np.reshape(np.tile(zoom_levels_A, (1, opt.batch_size, 1)), [-1, 2])
+        self.preprocess_data()
 
+    # ---- what differs between the single- and the multi-material dataset
+    def _material_index(self, index):
+        return 0
+
+    def _zoom_index(self, index):
+        return 0                # singleskit_dataset.py:241 reads zoom_levels_A[0] for every index
+
+    def _name(self, m):
+        return os.path.splitext(ntpath.basename(m.S_path[0]))[0]      # `S_path[0]` of a str: the reference's own quirk (:409-410)
+
+    def _load_sketch(self, path):
+        opt = self.opt
+        if opt.sketch_nc == 1:
+            return load_image_u8(path, "L", self.device)
+        assert opt.sketch_nc == 3, "Load sketch either in grayscale or RGB"
+        return load_image_u8(path, "RGB", self.device)
+
+    def _load_materials(self):
+        """singleskit_dataset.py:84-173."""
+        opt = self.opt
         self.dir_S = os.path.join(opt.dataroot, opt.subdir_S)
         self.dir_I = os.path.join(opt.dataroot, opt.subdir_I)
         self.dir_T = os.path.join(opt.dataroot, opt.subdir_T)
@@ -339,22 +384,16 @@ class SingleSkitDataset(torch.utils.data.Dataset):
         if opt.subdir_valT is not None:
             self.dir_valT = os.path.join(opt.dataroot, opt.subdir_valT)
             assert os.path.exists(self.dir_valT), "missing val T data for train datasets {}".format(self.dir_valT)
-
         assert os.path.exists(self.dir_S), "missing S data for datasets {}".format(self.dir_S)
         self.S_paths = sorted(make_dataset(self.dir_S, opt.max_dataset_size))
         assert len(self.S_paths) == 1, "SingleSkitDataset class should be used with one image in sketch S_paths {}".format(self.S_paths)
-        if opt.sketch_nc == 1:
-            self.S_img = load_image_u8(self.S_paths[0], "L", self.device)
-        else:
-            assert opt.sketch_nc == 3, "Load sketch either in grayscale or RGB"
-            self.S_img = load_image_u8(self.S_paths[0], "RGB", self.device)
-        self.M_img = None
+        self.S_img = self._load_sketch(self.S_paths[0])
+        self.M_img, self.M_paths = None, [None]
         if self.opt.use_bg_mask is True:
             assert os.path.exists(self.dir_M), "Cannot find valid path for binary mask, %s" % self.dir_M
             self.M_paths = sorted(make_dataset(self.dir_M, opt.max_dataset_size))
             assert len(self.M_paths) == 1, "SingleSkitDataset class should be used with one image for mask"
             self.M_img = load_image_u8(self.M_paths[0], "L", self.device)
-
         if not os.path.exists(self.dir_I):
             print("Warning: missing I data opt dataroot {}, opt subdir_I {}".format(opt.dataroot, opt.subdir_I))
             assert "edit" in opt.dataroot, "I and T data are required for original sketches"
@@ -374,40 +413,41 @@ class SingleSkitDataset(torch.utils.data.Dataset):
             self.val_T_size = len(self.val_T_paths)
         else:
             self.val_T_paths, self.val_T_size = None, 0
+        self.touch = TouchSet(self.T_paths, self.device, self.PATCH) if self.T_size > 0 else None
+        self.val_touch = TouchSet(self.val_T_paths, self.device, self.PATCH) if self.val_T_size > 0 else None
+        self.materials = [_Material(self.S_paths[0], self.S_img, self.I_img, self.M_img, self.M_paths[0], self.touch, self.val_touch)]
 
-        if self.T_size > 0 and self.M_img is None:
-            raise ValueError("touch patches are validated against the object mask (singleskit_dataset.py:742-745): use_bg_mask must be True")
-        if getattr(opt, "T_resolution_multiplier", 1) != 1:
-            raise NotImplementedError("T_resolution_multiplier != 1 is outside the B200 path (DESIGN.md section 10)")
-        patch = 32
-        self.touch = TouchSet(self.T_paths, self.device, patch) if self.T_size > 0 else None
-        self.val_touch = TouchSet(self.val_T_paths, self.device, patch) if self.val_T_size > 0 else None
-
-        A_zoom = 1 / self.opt.random_scale_max if self.opt.is_train else 1
-        zoom_levels_A = np.random.uniform(A_zoom, 1.0, size=(len(self) // opt.batch_size + 1, 1, 2))
-        self.zoom_levels_A = np.reshape(np.tile(zoom_levels_A, (1, opt.batch_size, 1)), [-1, 2])
-        self.preprocess_data()
-
-    # ---- one-off work: the zoomed and ratio-resized sources (identical for every index)
-    def _prepare_sources(self):
+    # ---- the zoomed and ratio-resized sources of one (material, zoom level): computed once, shared by every index that uses them
+    def _sources(self, mi, zi):
+        key = (mi, zi)
+        if key in self._src_cache:
+            return self._src_cache[key]
+        m = self.materials[mi]
         method = LANCZOS
-        srcs = {"S": self.S_img, "I": self.I_img, "M": self.M_img}
+        srcs = {"S": m.S_img, "I": m.I_img, "M": m.M_img}
+        srcs.update(m.extra)
         if "zoom" in self.opt.preprocess:
-            self.scale_factor_h, self.scale_factor_w = self.zoom_levels_A[0]
-            srcs = {k: (zoom_img(v, self.scale_factor_h, self.scale_factor_w, method) if v is not None else None) for k, v in srcs.items()}
+            sf_h, sf_w = self.zoom_levels_A[zi]
+            srcs = {k: (zoom_img(v, sf_h, sf_w, method) if v is not None else None) for k, v in srcs.items()}
         else:
-            self.scale_factor_h = self.scale_factor_w = 1
+            sf_h = sf_w = 1
         crop = self.opt.crop_size
         w, h = size_of(srcs["S"])
-        self.resize_ratio = crop_resize_ratio((w, h), crop, crop)
-        rw, rh = int(round(w * self.resize_ratio)), int(round(h * self.resize_ratio))
-        self.src = {k: (resize_u8(v, rh, rw, method) if v is not None else None) for k, v in srcs.items()}      # same size -> copy, as Image.resize
-        self.p2_w, self.p2_h, self.resize_ratio_w, self.resize_ratio_h = make_power_2_size((crop, crop), 256)
+        ratio = crop_resize_ratio((w, h), crop, crop)
 
-    def _final_u8(self, key, crop_pos_x, crop_pos_y):
+        def ratio_resize(v):      # crop_img resizes every image by the sketch's ratio, from the image's own size (dataset_util.py:186-194)
+            vw, vh = size_of(v)
+            return resize_u8(v, int(round(vh * ratio)), int(round(vw * ratio)), method)      # same size -> copy, as Image.resize
+        out = {"img": {k: (ratio_resize(v) if v is not None else None) for k, v in srcs.items()}, "sf_h": sf_h, "sf_w": sf_w, "ratio": ratio}
+        nbytes = sum(v.numel() for v in out["img"].values() if v is not None)
+        if len(self._src_cache) == 0 or self._cache_used + nbytes <= self._cache_budget:
+            self._src_cache[key] = out
+            self._cache_used += nbytes
+        return out
+
+    def _final_u8(self, src, crop_pos_x, crop_pos_y):
         """The uint8 image after crop (+ the power-of-2 resize when the crop size is not a multiple of 256)."""
         crop = self.opt.crop_size
-        src = self.src[key]
         h, w, c = src.shape
         out = torch.zeros((crop, crop, c), dtype=torch.uint8, device=self.device)       # PIL's crop pads with 0 outside the image
         ye, xe = min(h, crop_pos_y + crop), min(w, crop_pos_x + crop)
@@ -416,57 +456,59 @@ class SingleSkitDataset(torch.utils.data.Dataset):
             out = resize_u8(out, self.p2_h, self.p2_w, LANCZOS)
         return out
 
-    def _image_tensor(self, key, crop_pos_x, crop_pos_y):
+    def _image_tensor(self, src, normalize, crop_pos_x, crop_pos_y):
         crop = self.opt.crop_size
-        normalize = key != "M"
         if (self.p2_w, self.p2_h) == (crop, crop):
-            return crop_to_tensor(self.src[key], crop_pos_x, crop_pos_y, crop, crop, normalize)
-        u8 = self._final_u8(key, crop_pos_x, crop_pos_y)
+            return crop_to_tensor(src, crop_pos_x, crop_pos_y, crop, crop, normalize)
+        u8 = self._final_u8(src, crop_pos_x, crop_pos_y)
         return crop_to_tensor(u8, 0, 0, self.p2_w, self.p2_h, normalize)
 
     def preprocess_data(self, timing=False, verbose=False, separate_val_set=False):
-        """singleskit_dataset.py:194-432: draws every augmentation's crop and touch-patch selection (the reference's `random` call
-        order), keeps the small tensors; the full-resolution S / I / M tensors are produced in `__getitem__`."""
-        self._prepare_sources()
+        """singleskit_dataset.py:194-432 / skit_dataset.py:211-500: draws every augmentation's crop and touch-patch selection (the
+        reference's `random` call order), keeps the small tensors; the full-resolution tensors are produced in `__getitem__`."""
         if "padded" in self.opt.dataroot:
             self.padded_size = int(self.opt.dataroot.split("padded_")[1].split("/")[0].split("_")[0])
-        W_, H_ = size_of(self.S_img)
-        H, W = W_, H_            # the reference's `H, W = S_img.size[:2]` (PIL size is (width, height)): kept as is
         crop = self.opt.crop_size
+        self.p2_w, self.p2_h, self.resize_ratio_w, self.resize_ratio_h = make_power_2_size((crop, crop), 256)
         for index in range(len(self)):
+            mi, zi = self._material_index(index), self._zoom_index(index)
+            m = self.materials[mi]
+            src = self._sources(mi, zi)
+            W_, H_ = size_of(m.S_img)
+            H, W = W_, H_            # the reference's `H, W = S_img.size[:2]` (PIL size is (width, height)): kept as is
             center_crop = "crop" not in self.opt.preprocess
-            crop_pos_x, crop_pos_y = get_params(size_of(self.src["S"]), crop_size_h=crop, crop_size_w=crop, center_w=self.opt.center_w,
+            crop_pos_x, crop_pos_y = get_params(size_of(src["img"]["S"]), crop_size_h=crop, crop_size_w=crop, center_w=self.opt.center_w,
                                                 center_h=self.opt.center_h, center_crop=center_crop)
             augmentation_params = {
                 "H": H, "W": W,
-                "scale_factor_h": self.scale_factor_h, "scale_factor_w": self.scale_factor_w,
+                "scale_factor_h": src["sf_h"], "scale_factor_w": src["sf_w"],
                 "crop_size_h": crop, "crop_size_w": crop,
-                "resize_ratio": self.resize_ratio, "crop_pos_x": crop_pos_x, "crop_pos_y": crop_pos_y,
+                "resize_ratio": src["ratio"], "crop_pos_x": crop_pos_x, "crop_pos_y": crop_pos_y,
                 "resize_ratio_w": self.resize_ratio_w, "resize_ratio_h": self.resize_ratio_h,
-                "patch_crop_size": 32,
+                "patch_crop_size": self.PATCH,
             }
-            name = os.path.splitext(ntpath.basename(self.S_paths[0][0]))[0]      # `S_path[0]` of a str: the reference's own quirk
-            item = {"name": name, "S_paths": self.S_paths[0], "augmentation_params": augmentation_params}
-            if self.I_img is not None:
+            item = {"name": self._name(m), "S_paths": self.S_paths[0], "augmentation_params": augmentation_params}
+            if m.I_img is not None:
                 M3 = S3 = None
-                if self.T_size > 0 or self.val_T_size > 0:
-                    M3 = self._final_u8("M", crop_pos_x, crop_pos_y)
-                    S3 = self._final_u8("S", crop_pos_x, crop_pos_y)
+                if m.touch is not None or m.val_touch is not None:
+                    M3 = self._final_u8(src["img"]["M"], crop_pos_x, crop_pos_y)
+                    S3 = self._final_u8(src["img"]["S"], crop_pos_x, crop_pos_y)
                 T_images, T_coords, full_T_coords, I_masks = [], [], [], []
-                if self.T_size > 0:
+                if m.touch is not None:
                     T_images, T_coords, full_T_coords, I_masks = self.find_validate_touch_patches_and_coords(
-                        self.touch, augmentation_params, S3, M3, is_train=self.opt.is_train, is_val=False)
+                        m.touch, augmentation_params, S3, M3, is_train=self.opt.is_train, is_val=False)
                 val_T_images, val_T_coords, val_full_T_coords, val_I_masks = [], [], [], []
-                if self.val_T_size > 0:
+                if m.val_touch is not None:
                     val_T_images, val_T_coords, val_full_T_coords, val_I_masks = self.find_validate_touch_patches_and_coords(
-                        self.val_touch, augmentation_params, S3, M3, is_train=self.opt.is_train, is_val=True)
+                        m.val_touch, augmentation_params, S3, M3, is_train=self.opt.is_train, is_val=True)
                 item.update({"I_masks": I_masks, "val_I_masks": val_I_masks, "T_images": T_images, "T_coords": T_coords,
                              "full_T_coords": full_T_coords, "val_T_images": val_T_images, "val_T_coords": val_T_coords,
                              "val_full_T_coords": val_full_T_coords})
             else:
                 item["T_images"] = []
-            if self.M_img is not None:
-                item["M_paths"] = self.M_paths[0]
+            if m.M_img is not None:
+                item["M_paths"] = m.M_path
+            self._index_key[index] = (mi, zi)
             self.data_dict[index] = item
 
     def find_validate_touch_patches_and_coords(self, touch, augmentation_params, S3, M3, is_train=False, is_val=False):
@@ -557,11 +599,11 @@ class SingleSkitDataset(torch.utils.data.Dataset):
         if index in self._image_cache:
             return self._image_cache[index]
         a = self.data_dict[index]["augmentation_params"]
-        out = {"S": self._image_tensor("S", a["crop_pos_x"], a["crop_pos_y"])}
-        if self.I_img is not None:
-            out["I"] = self._image_tensor("I", a["crop_pos_x"], a["crop_pos_y"])
-        if self.M_img is not None:
-            out["M"] = self._image_tensor("M", a["crop_pos_x"], a["crop_pos_y"])
+        img = self._sources(*self._index_key[index])["img"]
+        out = {}
+        for key, src in img.items():
+            if src is not None:
+                out[key] = self._image_tensor(src, not key.endswith("M"), a["crop_pos_x"], a["crop_pos_y"])     # masks: ToTensor only
         nbytes = sum(t.numel() * 4 for t in out.values())
         if self._cache_used + nbytes <= self._cache_budget:
             self._image_cache[index] = out
@@ -580,3 +622,72 @@ class SingleSkitDataset(torch.utils.data.Dataset):
 
     def __len__(self):
         return self.data_len
+
+
+class SkitDataset(SingleSkitDataset):
+    """data/skit_dataset.py:25 — the multi-material dataset of the skitG model: `opt.material_list` objects, item `index` belongs to
+    material `index % len(material_list)` (:240) and uses its own zoom level `zoom_levels_A[index]` (:278).  Each material's directory
+    is `<datasets_dir>/singleskit_<material>_padded_<padded_size>_x<T_resolution_multiplier>/` (:141; `datasets_dir` = `./datasets`
+    unless `opt.datasets_dir` says otherwise)."""
+
+    def _material_index(self, index):
+        return index % len(self.opt.material_list)
+
+    def _zoom_index(self, index):
+        return index
+
+    def _name(self, m):
+        return os.path.splitext(ntpath.basename(m.S_path))[0]
+
+    def _load_materials(self):
+        """skit_dataset.py:86-196."""
+        opt = self.opt
+        base = getattr(opt, "datasets_dir", "./datasets")
+        if not getattr(opt, "load_contact_mask", True):
+            raise NotImplementedError("load_contact_mask=False (PIL random square crops of the touch maps, singleskit_dataset.py:862-905) "
+                                      "is not built on the B200 path")
+        if hasattr(opt, "material_list"):
+            print("material_list is {}".format(opt.material_list))
+        self.S_paths, self.I_paths, self.M_paths, self.T_paths, self.T_sizes, self.val_T_paths, self.val_T_sizes = [], [], [], [], [], [], []
+        external = bool(getattr(opt, "use_external_test_input", False))
+        if external:
+            self.style_I_paths, self.style_M_paths = [], []
+            print("Use external test input")
+            assert hasattr(opt, "test_sketch_material"), "test_sketch_material is not defined"
+            sketch_root = os.path.join(base, f"singleskit_{opt.test_sketch_material}_padded_{opt.padded_size}_x{opt.T_resolution_multiplier}_edit0/")
+            self.S_paths.extend(sorted(make_dataset(os.path.join(sketch_root, opt.subdir_S), opt.max_dataset_size)))
+            self.M_paths.extend(sorted(make_dataset(os.path.join(sketch_root, opt.subdir_M), opt.max_dataset_size)))
+            style_root = os.path.join(base, f"singleskit_{opt.test_style_material}_padded_{opt.padded_size}_x{opt.T_resolution_multiplier}_edit0/")
+            self.style_I_paths.extend(sorted(make_dataset(os.path.join(style_root, opt.subdir_I), opt.max_dataset_size)))
+            self.style_M_paths.extend(sorted(make_dataset(os.path.join(style_root, opt.subdir_M), opt.max_dataset_size)))
+        else:
+            print("Iterate over material_list")
+            for material in opt.material_list:
+                dataroot = os.path.join(base, f"singleskit_{material}_padded_{opt.padded_size}_x{opt.T_resolution_multiplier}/")
+                dir_S, dir_I = os.path.join(dataroot, opt.subdir_S), os.path.join(dataroot, opt.subdir_I)
+                dir_T, dir_M = os.path.join(dataroot, opt.subdir_T), os.path.join(dataroot, opt.subdir_M)
+                dir_valT = os.path.join(dataroot, opt.subdir_valT) if opt.subdir_valT is not None else None
+                assert os.path.exists(dir_S) and os.path.exists(dir_I) and os.path.exists(dir_T) and os.path.exists(dir_M), \
+                    "datasets directories are invalid, \n dir_S {} \n dir_I {} \n dir_T {} \n dir_M {}".format(dir_S, dir_I, dir_T, dir_M)
+                self.S_paths.extend(sorted(make_dataset(dir_S, opt.max_dataset_size)))
+                self.I_paths.extend(sorted(make_dataset(dir_I, opt.max_dataset_size)))
+                self.M_paths.extend(sorted(make_dataset(dir_M, opt.max_dataset_size)))
+                T_paths = make_touch_image_dataset(dir_T, opt.max_dataset_size)
+                self.T_paths.append(T_paths)
+                self.T_sizes.append(len(T_paths))
+                val_T_paths = make_touch_image_dataset(dir_valT, opt.max_dataset_size) if dir_valT is not None else []
+                self.val_T_paths.append(val_T_paths)
+                self.val_T_sizes.append(len(val_T_paths))
+        assert opt.image_nc == 3, "Visual image should have RGB 3 channels"
+        self.materials = []
+        for k, S_path in enumerate(self.S_paths):
+            I_img = load_image_u8(self.I_paths[k], "RGB", self.device) if len(self.I_paths) > 0 else None
+            M_img = load_image_u8(self.M_paths[k], "L", self.device) if opt.use_bg_mask is True else None
+            extra = None
+            if external:
+                extra = {"style_I": load_image_u8(self.style_I_paths[k], "RGB", self.device),
+                         "style_M": load_image_u8(self.style_M_paths[k], "L", self.device)}
+            touch = TouchSet(self.T_paths[k], self.device, self.PATCH) if I_img is not None and self.T_sizes[k] > 0 else None
+            val_touch = TouchSet(self.val_T_paths[k], self.device, self.PATCH) if I_img is not None and self.val_T_sizes[k] > 0 else None
+            self.materials.append(_Material(S_path, self._load_sketch(S_path), I_img, M_img, self.M_paths[k] if opt.use_bg_mask else None,
+                                            touch, val_touch, extra))
