@@ -1,6 +1,7 @@
 // Generic fp32 CUDA-core implicit-GEMM convolution kernels (forward, gather dgrad, wgrad) and the
 // weight (un)packers.  These cover every layer shape of the path (tiny channel counts, strides,
 // first/last 7x7 convs); the tcgen05 kernel in tc_conv.cu takes the tensor-core-eligible layers.
+#include <cstdlib>
 #include "skit_common.cuh"
 
 namespace skit {
@@ -682,6 +683,57 @@ __global__ void __launch_bounds__(128) wgrad_thin_co_kernel(WgradP p) {
         if (o < p.co) atomicAdd(p.dwf + ((long long)tap * p.ci + c) * p.co + o, acc[o]);
 }
 
+// The same for ONE output channel, stride 1 and k*k <= 16 (the PatchGAN heads, 512 -> 1, k 4): the kernel above reads the whole
+// activation once per tap (16 x 19.7 MB for the 98 x 98 head of the 768^2 step: 128 us).  Here a thread owns one input channel and
+// walks INPUT positions: x[iy][ix][c] is loaded once and feeds all k*k taps, dw[ky][kx][c] += x[iy][ix][c] * dy[iy-ky][ix-kx], with
+// the k x k window of dy (block-uniform, broadcast loads) sliding along the row in registers.  grid: (channel chunks of 128, n * row splits).
+template <int XFMT, int DFMT, int K>
+__global__ void __launch_bounds__(128) wgrad_thin_co1_s1_kernel(WgradP p, int rows_per_block) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const int hi = p.ho + K - 1, wi = p.wo + K - 1;
+    const int nsplit = cdiv(hi, rows_per_block);
+    const int n = blockIdx.y / nsplit, sp = blockIdx.y - n * nsplit;
+    if (c >= p.ci) return;
+    float acc[K][K];
+#pragma unroll
+    for (int a = 0; a < K; a++)
+#pragma unroll
+        for (int b2 = 0; b2 < K; b2++) acc[a][b2] = 0.f;
+    const int iy_end = min(hi, (sp + 1) * rows_per_block);
+    for (int iy = sp * rows_per_block; iy < iy_end; iy++) {
+        float win[K][K];         // win[ky][kx] = dy[iy - ky][ix - kx] (0 outside the map)
+#pragma unroll
+        for (int a = 0; a < K; a++)
+#pragma unroll
+            for (int b2 = 0; b2 < K; b2++) win[a][b2] = 0.f;
+        const long long xrow = (((long long)n * p.hp + p.org + iy) * p.wp + p.org) * p.ci + c;
+        for (int ix = 0; ix < wi; ix++) {
+#pragma unroll
+            for (int a = 0; a < K; a++) {
+#pragma unroll
+                for (int b2 = K - 1; b2 > 0; b2--) win[a][b2] = win[a][b2 - 1];
+                const int oy = iy - a;
+                float dv = 0.f;
+                if (oy >= 0 && oy < p.ho && ix < p.wo) {
+                    const long long da = ((long long)n * p.dhp + p.dorg + oy) * p.dwp + p.dorg + ix;      // co == 1
+                    dv = (DFMT == SKIT_FMT_F32) ? __ldg(p.d0 + da) : (__bfloat162float(p.dh[da]) + __bfloat162float(p.dl[da]));
+                }
+                win[a][0] = dv;
+            }
+            const long long xa = xrow + (long long)ix * p.ci;
+            const float xv = (XFMT == SKIT_FMT_F32) ? __ldg(p.x0 + xa) : (__bfloat162float(p.xh[xa]) + __bfloat162float(p.xl[xa]));
+#pragma unroll
+            for (int a = 0; a < K; a++)
+#pragma unroll
+                for (int b2 = 0; b2 < K; b2++) acc[a][b2] = fmaf(win[a][b2], xv, acc[a][b2]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < K; a++)
+#pragma unroll
+        for (int b2 = 0; b2 < K; b2++) atomicAdd(p.dwf + (long long)(a * K + b2) * p.ci + c, acc[a][b2]);
+}
+
 // dbias[o] += sum over pixels of dy (operand with halo).  grid: (pixel chunks, n), block 256 = 8 pixel
 // lanes x 32 channel lanes: a warp reads 32 consecutive channels of one pixel (coalesced), the 8 pixel
 // lanes are combined through shared memory before one atomic per channel per CTA.
@@ -713,6 +765,46 @@ __global__ void __launch_bounds__(256) dbias_kernel(const float* d0, const __nv_
             atomicAdd(dbias + o, t);
         }
         __syncthreads();
+    }
+}
+
+// Vector variant for channel counts that are multiples of 4: a thread owns 4 consecutive channels (one 16-byte fp32 load, or two
+// 8-byte bf16 loads), 256 / (co / 4) pixel lanes per block; the pixel lanes are combined through shared memory.
+template <int DFMT>
+__global__ void __launch_bounds__(256) dbias_vec4_kernel(const float* __restrict__ d0, const __nv_bfloat16* __restrict__ dh,
+                                                         const __nv_bfloat16* __restrict__ dl, int dhp, int dwp, int co, int cs, int dorg,
+                                                         int ho, int wo, int chunk, float* dbias) {
+    __shared__ float red[256 * 4];
+    const int n = blockIdx.y;
+    const int P = ho * wo;
+    const int cv = co / 4;                 // <= 256
+    const int PL = 256 / cv;
+    const int cl = threadIdx.x % cv, pl = threadIdx.x / cv;
+    const int pbeg = blockIdx.x * chunk, pend = min(P, pbeg + chunk);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pl < PL) {
+        for (int pix = pbeg + pl; pix < pend; pix += PL) {
+            const int oy = pix / wo, ox = pix - oy * wo;
+            const long long a = (((long long)n * dhp + dorg + oy) * dwp + dorg + ox) * cs + cl * 4;
+            if (DFMT == SKIT_FMT_F32) {
+                const float4 v = *reinterpret_cast<const float4*>(d0 + a);
+                s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            } else {
+                const uint2 h = *reinterpret_cast<const uint2*>(dh + a), l = *reinterpret_cast<const uint2*>(dl + a);
+                const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&h.y);
+                const __nv_bfloat162 l0 = *reinterpret_cast<const __nv_bfloat162*>(&l.x), l1 = *reinterpret_cast<const __nv_bfloat162*>(&l.y);
+                s[0] += __low2float(h0) + __low2float(l0); s[1] += __high2float(h0) + __high2float(l0);
+                s[2] += __low2float(h1) + __low2float(l1); s[3] += __high2float(h1) + __high2float(l1);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) red[threadIdx.x * 4 + j] = s[j];
+    __syncthreads();
+    for (int t = threadIdx.x; t < co; t += 256) {
+        float tot = 0.f;
+        for (int q = 0; q < PL; q++) tot += red[(q * cv + t / 4) * 4 + (t & 3)];
+        atomicAdd(dbias + t, tot);
     }
 }
 
@@ -1104,18 +1196,31 @@ extern "C" int skit_conv_transpose2d_fwd(const float* x, int n, int h, int w, in
     return check_launch("conv_simt_kernel<convT>");
 }
 
+namespace skit {
+static int launch_dbias(const skit_operand* dy, int dy_org, int ho, int wo, int nch, float* dbias, cudaStream_t st) {
+    const int P = ho * wo, n = dy->n;
+    const int chunk = max(64, cdiv(P, max(1, (148 * 4) / n)));
+    dim3 grid(cdiv(P, chunk), n);
+    const bool f32 = dy->fmt == SKIT_FMT_F32;
+    const float* d0 = f32 ? (const float*)dy->p0 : nullptr;
+    const __nv_bfloat16* dh = f32 ? nullptr : (const __nv_bfloat16*)dy->p0;
+    const __nv_bfloat16* dl = f32 ? nullptr : (const __nv_bfloat16*)dy->p1;
+    if (nch % 4 == 0 && dy->c % 4 == 0 && nch <= 1024 && 256 % (nch / 4) == 0) {
+        if (f32) dbias_vec4_kernel<0><<<grid, 256, 0, st>>>(d0, dh, dl, dy->hp, dy->wp, nch, dy->c, dy_org, ho, wo, chunk, dbias);
+        else dbias_vec4_kernel<1><<<grid, 256, 0, st>>>(d0, dh, dl, dy->hp, dy->wp, nch, dy->c, dy_org, ho, wo, chunk, dbias);
+        return check_launch("dbias_vec4_kernel");
+    }
+    if (f32) dbias_kernel<0><<<grid, 256, 0, st>>>(d0, dh, dl, dy->hp, dy->wp, nch, dy->c, dy_org, ho, wo, chunk, dbias);
+    else dbias_kernel<1><<<grid, 256, 0, st>>>(d0, dh, dl, dy->hp, dy->wp, nch, dy->c, dy_org, ho, wo, chunk, dbias);
+    return check_launch("dbias_kernel");
+}
+}  // namespace skit
+
 // dbias[o] += sum over (n, pixels) of an operand's interior (bias gradient of layers without a norm).
 extern "C" int skit_dbias(const skit_operand* dy, int dy_org, int ho, int wo, float* dbias, void* stream) {
     SKIT_REQUIRE(dy && dy->p0 && dbias && ho > 0 && wo > 0, "dbias: bad arguments");
     SKIT_REQUIRE(dy_org + ho <= dy->hp && dy_org + wo <= dy->wp, "dbias: window exceeds the operand");
-    const int P = ho * wo, n = dy->n;
-    int chunk = max(64, cdiv(P, max(1, (148 * 4) / n)));
-    dim3 grid(cdiv(P, chunk), n);
-    if (dy->fmt == SKIT_FMT_F32)
-        dbias_kernel<0><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, dy->c, dy->c, dy_org, ho, wo, chunk, dbias);
-    else
-        dbias_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(nullptr, (const __nv_bfloat16*)dy->p0, (const __nv_bfloat16*)dy->p1, dy->hp, dy->wp, dy->c, dy->c, dy_org, ho, wo, chunk, dbias);
-    return check_launch("dbias_kernel");
+    return launch_dbias(dy, dy_org, ho, wo, dy->c, dbias, as_stream(stream));
 }
 
 namespace skit {
@@ -1159,7 +1264,27 @@ extern "C" int skit_conv2d_wgrad_ex(const skit_operand* x, int org, const skit_o
         p.d0 = (const float*)dy->p0; p.dh = (const __nv_bfloat16*)dy->p0; p.dl = (const __nv_bfloat16*)dy->p1;
         p.dhp = dy->hp; p.dwp = dy->wp; p.co = co; p.dorg = dy_org;
         p.k = k; p.stride = stride; p.ho = ho; p.wo = wo; p.Kf = k * k * ci; p.dwf = dwf;
-        if (co <= 4 && ci >= 64) {   // thin output side: channel-parallel reduction instead of a GEMM tile
+        static const bool co1_path = !(getenv("SKIT_WGRAD_CO1") && atoi(getenv("SKIT_WGRAD_CO1")) == 0);
+        if (co == 1 && ci >= 64 && stride == 1 && (k == 4 || k == 3) && co1_path) {
+            // one output channel, stride 1: every activation element read once for all taps
+            const int hi = ho + k - 1;
+            const int chunks = cdiv(ci, 128);
+            const int want = max(1, (148 * 8) / max(1, chunks * n));
+            const int rpb = max(1, cdiv(hi, want));
+            dim3 grid(chunks, n * cdiv(hi, rpb));
+            const bool xf = x->fmt == SKIT_FMT_F32, df = dy->fmt == SKIT_FMT_F32;
+#define SKIT_CO1(KK)                                                                                         \
+            do {                                                                                             \
+                if (xf && df) wgrad_thin_co1_s1_kernel<0, 0, KK><<<grid, 128, 0, st>>>(p, rpb);              \
+                else if (xf) wgrad_thin_co1_s1_kernel<0, 1, KK><<<grid, 128, 0, st>>>(p, rpb);               \
+                else if (df) wgrad_thin_co1_s1_kernel<1, 0, KK><<<grid, 128, 0, st>>>(p, rpb);               \
+                else wgrad_thin_co1_s1_kernel<1, 1, KK><<<grid, 128, 0, st>>>(p, rpb);                       \
+            } while (0)
+            if (k == 4) SKIT_CO1(4); else SKIT_CO1(3);
+#undef SKIT_CO1
+            int rc = check_launch("wgrad_thin_co1_s1_kernel");
+            if (rc) return rc;
+        } else if (co <= 4 && ci >= 64) {   // thin output side: channel-parallel reduction instead of a GEMM tile
             const int blocks = k * k * cdiv(ci, 128);
             int splits = max(1, min(cdiv(cdiv(148 * 8, blocks), n), cdiv(P, 32)));
             p.chunk = cdiv(P, splits);
@@ -1190,15 +1315,7 @@ extern "C" int skit_conv2d_wgrad_ex(const skit_operand* x, int org, const skit_o
         int rc = unpack_wgrad(dwf, co_real, ci_real, k, dw, 1, layout, st, co, ci);
         if (rc) return rc;
     }
-    if (dbias) {
-        int chunk = max(64, cdiv(P, max(1, (148 * 4) / n)));
-        dim3 grid(cdiv(P, chunk), n);
-        if (dy->fmt == SKIT_FMT_F32)
-            dbias_kernel<0><<<grid, 256, 0, st>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, co_real, co, dy_org, ho, wo, chunk, dbias);
-        else
-            dbias_kernel<1><<<grid, 256, 0, st>>>(nullptr, (const __nv_bfloat16*)dy->p0, (const __nv_bfloat16*)dy->p1, dy->hp, dy->wp, co_real, co, dy_org, ho, wo, chunk, dbias);
-        return check_launch("dbias_kernel");
-    }
+    if (dbias) return launch_dbias(dy, dy_org, ho, wo, co_real, dbias, st);
     return SKIT_OK;
 }
 
@@ -1242,12 +1359,5 @@ extern "C" int skit_conv2d_wgrad_dyfolded(const skit_operand* x, const skit_oper
 extern "C" int skit_dbias_n(const skit_operand* dy, int dy_org, int ho, int wo, int nch, float* dbias, void* stream) {
     SKIT_REQUIRE(dy && dy->p0 && dbias && ho > 0 && wo > 0 && nch > 0 && nch <= dy->c, "dbias_n: bad arguments");
     SKIT_REQUIRE(dy_org + ho <= dy->hp && dy_org + wo <= dy->wp, "dbias_n: window exceeds the operand");
-    const int P = ho * wo, n = dy->n;
-    int chunk = max(64, cdiv(P, max(1, (148 * 4) / n)));
-    dim3 grid(cdiv(P, chunk), n);
-    if (dy->fmt == SKIT_FMT_F32)
-        dbias_kernel<0><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy->p0, nullptr, nullptr, dy->hp, dy->wp, nch, dy->c, dy_org, ho, wo, chunk, dbias);
-    else
-        dbias_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(nullptr, (const __nv_bfloat16*)dy->p0, (const __nv_bfloat16*)dy->p1, dy->hp, dy->wp, nch, dy->c, dy_org, ho, wo, chunk, dbias);
-    return check_launch("dbias_kernel");
+    return launch_dbias(dy, dy_org, ho, wo, nch, dbias, as_stream(stream));
 }
