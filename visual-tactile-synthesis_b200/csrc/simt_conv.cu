@@ -1016,6 +1016,39 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int co, int c
     }
 }
 
+// Tiled variant: a block owns 32 output channels x TC input channels x all taps, reads the partial sums along their contiguous
+// axis (c for layout 1, o for layout 0) into shared memory and writes each output channel's TC * k * k consecutive weights as one
+// run — both sides coalesced (the element-wise kernel reads with a stride of cip * cop floats between neighbouring threads).
+template <int TC>
+__global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(const float* __restrict__ dwf, int co, int ci, int kk, float* dw, int accumulate,
+                                                                 int layout, int cop, int cip) {
+    extern __shared__ float tile[];      // [32 o][TC c][kk | 1]
+    const int kp = kk | 1;
+    const int o0 = blockIdx.y * 32, c0 = blockIdx.x * TC;
+    const int n = 32 * TC * kk;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        int tap, ol, cl;
+        if (layout == 1) { cl = i % TC; const int t = i / TC; ol = t % 32; tap = t / 32; }
+        else { ol = i % 32; const int t = i / 32; cl = t % TC; tap = t / TC; }
+        const int o = o0 + ol, c = c0 + cl;
+        float v = 0.f;
+        if (o < co && c < ci) v = layout == 0 ? dwf[((long long)tap * cip + c) * cop + o] : dwf[((long long)tap * cop + o) * cip + c];
+        tile[(ol * TC + cl) * kp + tap] = v;
+    }
+    __syncthreads();
+    const int run = TC * kk;
+    for (int i = threadIdx.x; i < 32 * run; i += 256) {
+        const int ol = i / run, j = i - ol * run;
+        const int cl = j / kk, tap = j - cl * kk;
+        const int o = o0 + ol, c = c0 + cl;
+        if (o >= co || c >= ci) continue;
+        const float v = tile[(ol * TC + cl) * kp + tap];
+        float* dst = dw + ((long long)o * ci + c) * kk + tap;
+        if (accumulate) atomicAdd(dst, v);
+        else *dst = v;
+    }
+}
+
 // dwf from wgrad_tc on a folded operand: taps = ky, x channels j = kx*cp + c.  layout 0: [(ky*64 + j)*cop + o], 1: [(ky*cop + o)*64 + j]
 __global__ void unpack_wgrad_folded_kernel(const float* __restrict__ dwf, int co, int ci, int k, int kw, int cp, float* dw, int layout, int cop) {
     const long long total = (long long)co * ci * k * kw;
@@ -1126,6 +1159,14 @@ extern "C" int skit_pack_conv_weights_padded(const float* w, int co, int ci, int
 static int unpack_wgrad(const float* dwf, int co, int ci, int k, float* dw, int accumulate, int layout, cudaStream_t st,
                         int cop = 0, int cip = 0) {
     long long total = (long long)co * ci * k * k;
+    const int kk = k * k;
+    static const bool tiled = !(getenv("SKIT_UNPACK_TILED") && atoi(getenv("SKIT_UNPACK_TILED")) == 0);
+    if (tiled && co >= 32 && ci >= 16 && kk <= 16) {      // the trunk / discriminator layers: both sides coalesced through a shared-memory tile
+        dim3 grid(cdiv(ci, 16), cdiv(co, 32));
+        unpack_wgrad_tiled_kernel<16><<<grid, 256, (size_t)32 * 16 * (kk | 1) * sizeof(float), st>>>(dwf, co, ci, kk, dw, accumulate, layout,
+                                                                                                    cop ? cop : co, cip ? cip : ci);
+        return check_launch("unpack_wgrad_tiled_kernel");
+    }
     int blocks = (int)min((long long)148 * 8, cdivll(total, 256));
     unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(dwf, co, ci, k, dw, accumulate, layout, cop ? cop : co, cip ? cip : ci);
     return check_launch("unpack_wgrad_kernel");
