@@ -7,6 +7,12 @@
 
 namespace skit {
 
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SKIT_PDL"); on = e ? (atoi(e) != 0) : 0; }
+    return on != 0;
+}
+
 constexpr int kSMs = 148;
 
 static inline int grid_for(long long work, int threads, int max_per_sm = 8) {
@@ -114,6 +120,8 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(PrepP p) {
 // 16-byte loads in flight per thread.
 template <int FMT>
 __global__ void __launch_bounds__(256) norm_act_pad_rows_kernel(PrepP p, int cv, int rows_per_block, int xseg) {
+    pdl_trigger();
+    pdl_wait();      // launched through launch_pdl: nothing above touches global memory
     const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
     const int xbeg = blockIdx.z * xseg, xend = min(wp, xbeg + xseg);   // blockIdx.z: segment of the row (small maps)
     const int n = blockIdx.y;
@@ -373,6 +381,8 @@ __global__ void __launch_bounds__(256) act_norm_bwd_reduce_kernel(BwdAP p) {
 // per-pixel divisions, per-thread register sums reduced across the block's pixel lanes, one fp64 atomic per channel per CTA.
 template <int U, int MINB>
 __global__ void __launch_bounds__(256, MINB) act_norm_bwd_reduce_rows_kernel(BwdAP p, int cv, int rows_per_block, int xseg) {
+    pdl_trigger();
+    pdl_wait();      // launched through launch_pdl: nothing above touches global memory
     __shared__ float red[256 * 8];
     const int n = blockIdx.y;
     const int cl = threadIdx.x % cv, pl = threadIdx.x / cv, PL = 256 / cv;
@@ -549,6 +559,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(BwdBP p) {
 // the two reduced sums, converted from double ONCE per thread) stay in registers.
 template <int FMT>
 __global__ void __launch_bounds__(256) norm_bwd_apply_rows_kernel(BwdBP p, int cv, int rows_per_block, int xseg) {
+    pdl_trigger();
+    pdl_wait();      // launched through launch_pdl: nothing above touches global memory
     const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
     const int xbeg = blockIdx.z * xseg, xend = min(wp, xbeg + xseg);
     const int n = blockIdx.y;
@@ -850,8 +862,8 @@ static int norm_act_pad_impl(const float* raw, int n, int h, int w, int c,
         const int rpb = rows_per_block_for(hp, n);
         const int xs = xseg_for(hp, wp, n, 256 / (c / 4));
         dim3 grid(cdiv(hp, rpb), n, cdiv(wp, xs));
-        if (!op || op->fmt == SKIT_FMT_F32) norm_act_pad_rows_kernel<SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
-        else norm_act_pad_rows_kernel<SKIT_FMT_BF16X2><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
+        if (!op || op->fmt == SKIT_FMT_F32) launch_pdl(norm_act_pad_rows_kernel<SKIT_FMT_F32>, grid, 256, 0, as_stream(stream), p, c / 4, rpb, xs);
+        else launch_pdl(norm_act_pad_rows_kernel<SKIT_FMT_BF16X2>, grid, 256, 0, as_stream(stream), p, c / 4, rpb, xs);
         return check_launch("norm_act_pad_rows_kernel");
     }
     if (c % 4 == 0 && oc % 4 == 0 && c_off % 4 == 0) norm_act_pad_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
@@ -939,9 +951,9 @@ extern "C" int skit_act_norm_bwd_reduce_ex2(const float* dpad, int pad, int pad_
         dim3 grid(row_blocks, n, cdiv(w, xs));
         static int unroll = -1;
         if (unroll < 0) { const char* e = getenv("SKIT_REDUCE_UNROLL"); unroll = e ? atoi(e) : 2; }
-        if (unroll == 2) act_norm_bwd_reduce_rows_kernel<2, 3><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
-        else if (unroll == 1) act_norm_bwd_reduce_rows_kernel<1, 4><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
-        else act_norm_bwd_reduce_rows_kernel<4, 2><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
+        if (unroll == 2) launch_pdl(act_norm_bwd_reduce_rows_kernel<2, 3>, grid, 256, 0, as_stream(stream), p, c / 4, rpb, xs);
+        else if (unroll == 1) launch_pdl(act_norm_bwd_reduce_rows_kernel<1, 4>, grid, 256, 0, as_stream(stream), p, c / 4, rpb, xs);
+        else launch_pdl(act_norm_bwd_reduce_rows_kernel<4, 2>, grid, 256, 0, as_stream(stream), p, c / 4, rpb, xs);
         return check_launch("act_norm_bwd_reduce_rows_kernel");
     }
     const int lanes_c = min(c / vec, 256), PL = 256 / lanes_c;
@@ -997,8 +1009,8 @@ extern "C" int skit_norm_bwd_apply_ex(const float* g, const float* raw, int n, i
         const int rpb = rows_per_block_for(hp, n);
         const int xs = xseg_for(hp, wp, n, 256 / (c / 4));
         dim3 grid(cdiv(hp, rpb), n, cdiv(wp, xs));
-        if (op->fmt == SKIT_FMT_F32) norm_bwd_apply_rows_kernel<SKIT_FMT_F32><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
-        else norm_bwd_apply_rows_kernel<SKIT_FMT_BF16X2><<<grid, 256, 0, as_stream(stream)>>>(p, c / 4, rpb, xs);
+        if (op->fmt == SKIT_FMT_F32) launch_pdl(norm_bwd_apply_rows_kernel<SKIT_FMT_F32>, grid, 256, 0, as_stream(stream), p, c / 4, rpb, xs);
+        else launch_pdl(norm_bwd_apply_rows_kernel<SKIT_FMT_BF16X2>, grid, 256, 0, as_stream(stream), p, c / 4, rpb, xs);
     } else if (c % 4 == 0) norm_bwd_apply_kernel<4><<<grid_for(pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(p);
     else norm_bwd_apply_kernel<1><<<grid_for(pix * c, 256), 256, 0, as_stream(stream)>>>(p);
     rc = check_launch("norm_bwd_apply_kernel");

@@ -70,4 +70,31 @@ __device__ inline double warp_sum_d(double v) {
     return v;
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl() may be scheduled while the kernel in front of it
+// in the stream is still draining; everything it does before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch, index
+// arithmetic — nothing that touches global memory) overlaps that tail, pdl_wait() returns once the predecessor has completed and its
+// writes are visible.  pdl_trigger() in the predecessor lets the dependent grid be scheduled as soon as every CTA of this grid has
+// started (without it: when the grid has completed, i.e. no overlap, still correct).  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef SKIT_PDL_EARLY_TRIGGER
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+// measured: triggering at kernel entry made the 768^2 step slower (27.1 vs 25.9 ms) — the early-scheduled dependents sit in their
+// wait holding SM slots the side-stream kernels (weight gradients, discriminator branches) would have used
+__device__ __forceinline__ void pdl_trigger() {}
+#endif
+
+bool pdl_enabled();      // SKIT_PDL=1 (default off: measured no gain on the train step, see below and DESIGN.md section 10); prep.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace skit

@@ -78,6 +78,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(128, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, TcConvP p) {
+    pdl_trigger();       // PDL: the next kernel in the stream may be scheduled once every CTA of this grid has started
     constexpr int W_BYTES = BN * 128;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -108,6 +109,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();          // PDL: barrier init / TMEM allocation / descriptor prefetch above overlap the predecessor's tail
     const uint32_t tmem_base = *tmem_slot_gen;
 
     const int num_k = p.k * p.k * p.kc;
@@ -223,7 +225,7 @@ static int launch_conv_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
         }
         attr_set = true;
     }
-    conv_tc_kernel<BN, STAGES><<<grid, 128, SMEM, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+    launch_pdl(conv_tc_kernel<BN, STAGES>, grid, 128, SMEM, st, a_hi, a_lo, w_hi, w_lo, p);
     return check_launch("conv_tc_kernel");
 }
 

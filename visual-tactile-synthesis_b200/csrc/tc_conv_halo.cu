@@ -76,6 +76,7 @@ template <int BN>
 __global__ void __launch_bounds__(128, 1)
 conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcHaloP p) {
+    pdl_trigger();       // PDL: the next kernel in the stream may be scheduled once every CTA of this grid has started
     constexpr int W_PLANE = BN * 128;       // BN rows x 64 channels x 2 B
     // a two-term launch stages the hi plane only: half-size stages, twice as many of them — the bytes in flight per SM (stages x
     // stage size against ~1.7 us of L2 latency under load), not the MMA rate, bound the two-term kernel with two 64 KB stages
@@ -138,6 +139,7 @@ conv_tc_halo_kernel(const __grid_constant__ AMaps tmA,
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();          // PDL: barrier init / TMEM allocation / descriptor prefetch above overlap the predecessor's tail
     const uint32_t tmem_base = *tmem_slot_gen;
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
@@ -351,6 +353,7 @@ template <int BN>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_halo_persist_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmW_hi,
                             const __grid_constant__ CUtensorMap tmW_lo, const TcPersistP pp) {
+    pdl_trigger();       // PDL: the next kernel in the stream may be scheduled once every CTA of this grid has started
     constexpr int W_PLANE = BN * 128;
     constexpr int TCOLS = BN < 32 ? 32 : BN;
     constexpr int STG = 36;
@@ -392,6 +395,7 @@ conv_tc_halo_persist_kernel(const __grid_constant__ AMaps tmA, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();          // PDL: barrier init / TMEM allocation / descriptor prefetch above overlap the predecessor's tail
     const uint32_t tmem_base = *tmem_slot_gen;
     const int tiles_per_n = pp.tiles * pp.ntiles;
 
@@ -627,7 +631,7 @@ static int launch_halo_persist(const AMaps& amaps, const CUtensorMap& w_hi, cons
         attr_set = true;
     }
     const int grid = pp.units < 148 ? pp.units : 148;
-    conv_tc_halo_persist_kernel<BN><<<grid, 256, smem, st>>>(amaps, w_hi, w_lo, pp);
+    launch_pdl(conv_tc_halo_persist_kernel<BN>, grid, 256, smem, st, amaps, w_hi, w_lo, pp);
     return check_launch("conv_tc_halo_persist_kernel");
 }
 
@@ -658,6 +662,7 @@ struct TcTransP {
 __global__ void __launch_bounds__(256, 1)
 conv_tc_halo_t_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmW_hi,
                       const __grid_constant__ CUtensorMap tmW_lo, const TcTransP pp) {
+    pdl_trigger();       // PDL: the next kernel in the stream may be scheduled once every CTA of this grid has started
     constexpr int BM = 128;
     constexpr int W_PLANE = BM * 128;
     constexpr int ACC_COLS = 256;
@@ -697,6 +702,7 @@ conv_tc_halo_t_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();          // PDL: barrier init / TMEM allocation / descriptor prefetch above overlap the predecessor's tail
     const uint32_t tmem_base = *tmem_slot_gen;
     const int tiles_per_n = pp.tiles * pp.mtiles;
 
@@ -918,7 +924,7 @@ static int launch_halo_t(const AMaps& amaps, const CUtensorMap& w_hi, const CUte
         attr_set = true;
     }
     const int grid = pp.units < 148 ? pp.units : 148;
-    conv_tc_halo_t_kernel<<<grid, 256, smem, st>>>(amaps, w_hi, w_lo, pp);
+    launch_pdl(conv_tc_halo_t_kernel, grid, 256, smem, st, amaps, w_hi, w_lo, pp);
     return check_launch("conv_tc_halo_t_kernel");
 }
 
@@ -970,7 +976,7 @@ static int launch_halo(const AMaps& amaps, const CUtensorMap& w_hi, const CUtens
         }
         attr_smem = MAX_SMEM;
     }
-    conv_tc_halo_kernel<BN><<<grid, 128, smem, st>>>(amaps, w_hi, w_lo, p);
+    launch_pdl(conv_tc_halo_kernel<BN>, grid, 128, smem, st, amaps, w_hi, w_lo, p);
     return check_launch("conv_tc_halo_kernel");
 }
 

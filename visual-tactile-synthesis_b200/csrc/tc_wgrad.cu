@@ -37,6 +37,7 @@ template <int BN, int STAGES_UNUSED>
 __global__ void __launch_bounds__(128, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
                 const __grid_constant__ CUtensorMap tmN_hi, const __grid_constant__ CUtensorMap tmN_lo, TcWgradP p) {
+    pdl_trigger();       // PDL: the next kernel in the stream may be scheduled once every CTA of this grid has started
     constexpr int M_BYTES = 2 * BOX_BYTES;          // 128 M-channels = 2 boxes (the second is TMA zero fill when Mdim == 64)
     constexpr int NBOX = BN >= 64 ? BN / 64 : 1;    // a thin N side (<= 16 channels) still lands as one 64-channel box, zero-filled
     constexpr int N_BYTES = NBOX * BOX_BYTES;
@@ -73,6 +74,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM_hi, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();          // PDL: barrier init / TMEM allocation / descriptor prefetch above overlap the predecessor's tail
     const uint32_t tmem_base = *tmem_slot_gen;
     const int num_it = t_end - t_beg;
 
@@ -184,7 +186,7 @@ static int launch_wgrad_tc(const CUtensorMap& m_hi, const CUtensorMap& m_lo, con
         }
         attr_set = true;
     }
-    wgrad_tc_kernel<BN, STAGES><<<grid, 128, SMEM, st>>>(m_hi, m_lo, n_hi, n_lo, p);
+    launch_pdl(wgrad_tc_kernel<BN, STAGES>, grid, 128, SMEM, st, m_hi, m_lo, n_hi, n_lo, p);
     return check_launch("wgrad_tc_kernel");
 }
 
