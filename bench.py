@@ -119,14 +119,17 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- the reference's own code path (CPU / eager GPU)
-def oracle_stepper(size, nce, lpips, device="cpu", seed=0):
+def oracle_stepper(size, nce, lpips, device="cpu", seed=0, arch="B"):
     """One train step of the oracle (oracle/skit_oracle.py: the reference's own ATen code path restated call for call and pinned
     to the real reference by tests/golden) at the FULL workload: size x size, NT 64, NF 32.  Weights come from the oracle's own
     init tables — the product package is not imported.  -> step(i) callable."""
     from oracle import skit_oracle as O
-    sds = [O.init_resnet_g(9, 5, 64, 9, seed=seed), O.init_multiscale_d(4, 64, 3, 3, seed=seed + 1), O.init_multiscale_d(7, 64, 3, 3, seed=seed + 2)]
+    if arch == "A":      # the reference's default architecture: unet256_custom ngf 10, multiscale PatchGAN ndf 8
+        sds = [O.init_unet_custom(9, 10, 8, 4, seed=seed), O.init_multiscale_d(4, 8, 3, 3, seed=seed + 1), O.init_multiscale_d(7, 8, 3, 3, seed=seed + 2)]
+    else:
+        sds = [O.init_resnet_g(9, 5, 64, 9, seed=seed), O.init_multiscale_d(4, 64, 3, 3, seed=seed + 1), O.init_multiscale_d(7, 64, 3, 3, seed=seed + 2)]
     sds = [{k: v.to(device) for k, v in sd.items()} for sd in sds]
-    cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_NCE=1.0 if nce else 0.0,
+    cfg = O.StepConfig(netG="unet256_custom" if arch == "A" else "resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF, lambda_NCE=1.0 if nce else 0.0,
                        lambda_G1_lpips=1.0 if lpips else 0.0, lambda_G2_lpips=10.0 if lpips else 0.0, foreach_adam=device != "cpu")
     sdL = {k: v.to(device) for k, v in O.lpips_random_state(0).items()} if lpips else None
     batch = O.step_inputs_from_batch(O.synthetic_batch(size, NT=NT, seed=seed), device=None if device == "cpu" else device)
@@ -185,7 +188,7 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
-def time_eager_gpu(size, nce, lpips, steps=3, warmup=1):
+def time_eager_gpu(size, nce, lpips, steps=3, warmup=1, arch="B"):
     """The reference's code path as eager PyTorch + cuDNN on this GPU: the oracle's train step with every tensor on cuda:0,
     autograd backward, multi-tensor Adam; CUDA-event timed.  TF32 convolutions on (torch's default) and off (the fp32 the parity
     gate is defined against)."""
@@ -196,7 +199,7 @@ def time_eager_gpu(size, nce, lpips, steps=3, warmup=1):
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.benchmark = True       # base_model.py:38
         try:
-            step = oracle_stepper(size, nce, lpips, device="cuda")
+            step = oracle_stepper(size, nce, lpips, device="cuda", arch=arch)
             for i in range(warmup):
                 step(i)
             torch.cuda.synchronize()
@@ -445,6 +448,7 @@ def run_b200(a):
                                                config="the reference's default architecture (unet256_custom ngf 10, ndf 8), PatchNCE off")
                 extra["infer_1024"] = [time_infer(1024, B, 6, ctx.local_rank) for B in (1, 8)]
                 line["eager_b200"] = time_eager_gpu(a.size, a.nce, a.lpips, steps=3, warmup=1)
+                extra["arch_A_default"]["eager_b200"] = time_eager_gpu(a.size, False, False, steps=5, warmup=2, arch="A")
             except Exception as e:       # a side measurement must never cost the headline line
                 extra["error"] = repr(e)[:300]
             line["extra"] = extra

@@ -892,6 +892,32 @@ def init_resnet_g(input_nc=9, output_nc=5, ngf=64, n_blocks=9, seed=0):
     return sd
 
 
+def init_unet_custom(input_nc=9, ngf=10, num_downs=8, num_layer_separate=4, seed=0):
+    """A state_dict with the keys / shapes of define_G(..., 'unet256_custom', norm='instance') — the reference's default generator
+    (models/networks.py:1430-1573; key map SURVEY.md A.1: 40 tensors at ngf 10), initialised like init_weights('xavier', 0.02).
+    ConvTranspose2d weights are [Cin, Cout, 4, 4]; levels num_layer_separate-1 .. 0 have twin RGB / touch decoders."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    ch = [ngf * min(2 ** i, 8) for i in range(num_downs)]          # 10, 20, 40, 80, 80, 80, 80, 80
+    cin = input_nc
+    for i in range(num_downs):
+        key = "down%d.model.%d" % (i, 0 if i == 0 else 1)
+        sd[key + ".weight"] = _xavier((ch[i], cin, 4, 4), g)
+        sd[key + ".bias"] = torch.zeros(ch[i])
+        cin = ch[i]
+    for i in range(num_downs - 1, -1, -1):
+        c_in = ch[i] if i == num_downs - 1 else 2 * ch[i]           # innermost level has no skip concatenation
+        outs = {"up%d" % i: (ch[i - 1] if i > 0 else 3)}
+        if i < num_layer_separate:
+            outs["up%d_T" % i] = ch[i - 1] if i > 0 else 2
+        if i == 0:
+            c_in = ch[0]        # up0 takes the level-1 decoder output only (networks.py:1567-1573; A.1: up0.model.1.weight (10, 3, 4, 4))
+        for name, c_out in outs.items():
+            sd[name + ".model.1.weight"] = _xavier((c_in, c_out, 4, 4), g)
+            sd[name + ".model.1.bias"] = torch.zeros(c_out)
+    return sd
+
+
 def init_multiscale_d(input_nc, ndf=64, n_layers=3, num_D=3, seed=0):
     """State_dict of define_D(..., 'multiscale', norm='batch') (models/networks.py:1649-1750; index map SURVEY.md A.5):
     conv weights xavier(0.02), biases 0, BatchNorm weight ~ N(1, 0.02), bias 0 (:223-226), fresh running statistics."""

@@ -263,6 +263,10 @@ def test_standalone_init_tables_match_reference_keys_and_shapes(golden_dir):
     """O.init_resnet_g / O.init_multiscale_d (the weights bench.py's reference arm starts from, built without the product
     package) carry exactly the reference networks' state_dict keys, shapes and blur buffers, and its xavier(0.02) statistics."""
     g = np.load(os.path.join(golden_dir, "networks.npz"))
+    gu = np.load(os.path.join(golden_dir, "step_unet.npz"))
+    ref_u = {k[len("G_before."):]: gu[k] for k in gu.files if k.startswith("G_before.")}
+    sd_u = O.init_unet_custom(9, 4, 8, 4, seed=3)        # the reference's default generator (unet256_custom) at the fixture's ngf 4
+    assert set(sd_u) == set(ref_u) and all(tuple(v.shape) == ref_u[k].shape for k, v in sd_u.items())
     for prefix, sd in (("Gres.", O.init_resnet_g(9, 5, 8, 9, seed=3)), ("D_before.", O.init_multiscale_d(7, 8, 3, 3, seed=3))):
         ref = {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)}
         assert set(sd) == set(ref), prefix
