@@ -309,6 +309,18 @@ static int launch_thin(const ConvP& p, int n_img, cudaStream_t st) {
     return launch_thin_pix<MODE, FMT, 1>(p, n_img, st);
 }
 
+// Packed fp32 FMA (Blackwell FFMA2): two independent FMAs per lane per instruction on 64-bit register pairs.  The three-register
+// FFMA issues every second cycle per scheduler; in the FMA-bound 7x7 head kernels the channel-quad dot product runs as two partial
+// sums (x,y lanes), added once at the end.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(rd)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
 // ---------------------------------------------------------------------------------- thin-output 7x7 head
 // Generator head: Conv2d(64 -> 5, k7) over the reflect-padded activation (networks.py:1124-1126).  On the tensor cores this
 // layer wastes >95 % of every MMA (5 useful columns) and is bound by the per-MMA operand fetch (0.55 ms at 512x512); its
@@ -329,13 +341,13 @@ __global__ void __launch_bounds__(256) conv_head7_kernel(const float* __restrict
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int n = blockIdx.z;
     const int x_0 = blockIdx.x * T, y_0 = blockIdx.y * T;
-    float acc[2][2][CO];
+    float2 acc[2][2][CO];       // two partial sums per output (FFMA2)
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int b = 0; b < 2; b++)
 #pragma unroll
-            for (int o = 0; o < CO; o++) acc[a][b][o] = 0.f;
+            for (int o = 0; o < CO; o++) acc[a][b][o] = make_float2(0.f, 0.f);
 
     for (int c0 = 0; c0 < ci; c0 += CH) {
         // stage the input tile: one (pixel, quad) per thread-iteration
@@ -392,9 +404,9 @@ __global__ void __launch_bounds__(256) conv_head7_kernel(const float* __restrict
                         for (int a = 0; a < 2; a++)
 #pragma unroll
                             for (int b = 0; b < 2; b++) {
-                                float t = acc[a][b][o];
-                                t = fmaf(in[a][b].x, w4.x, t); t = fmaf(in[a][b].y, w4.y, t);
-                                t = fmaf(in[a][b].z, w4.z, t); t = fmaf(in[a][b].w, w4.w, t);
+                                float2 t = acc[a][b][o];
+                                t = ffma2(make_float2(in[a][b].x, in[a][b].y), make_float2(w4.x, w4.y), t);
+                                t = ffma2(make_float2(in[a][b].z, in[a][b].w), make_float2(w4.z, w4.w), t);
                                 acc[a][b][o] = t;
                             }
                     }
@@ -412,7 +424,7 @@ __global__ void __launch_bounds__(256) conv_head7_kernel(const float* __restrict
             float* dst = y + (((long long)n * ho + oy) * wo + ox) * co;
 #pragma unroll
             for (int o = 0; o < CO; o++)
-                if (o < co) dst[o] = acc[a][b][o] + (bias ? bias[o] : 0.f);
+                if (o < co) dst[o] = (acc[a][b][o].x + acc[a][b][o].y) + (bias ? bias[o] : 0.f);
         }
 }
 
@@ -435,11 +447,11 @@ __global__ void __launch_bounds__(256) conv_head7_row8_kernel(const float* __res
     const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
     const int n = blockIdx.z;
     const int x_0 = blockIdx.x * TX, y_0 = blockIdx.y * TYH;
-    float acc[8][CO];
+    float2 acc[8][CO];          // two partial sums per output (FFMA2)
 #pragma unroll
     for (int j = 0; j < 8; j++)
 #pragma unroll
-        for (int o = 0; o < CO; o++) acc[j][o] = 0.f;
+        for (int o = 0; o < CO; o++) acc[j][o] = make_float2(0.f, 0.f);
 
     for (int c0 = 0; c0 < ci; c0 += CH) {
         for (int i = threadIdx.x; i < 2 * HTY * HTX; i += 256) {
@@ -490,9 +502,9 @@ __global__ void __launch_bounds__(256) conv_head7_row8_kernel(const float* __res
                         const float4 w4 = wq[o];
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            float t = acc[j][o];
-                            t = fmaf(in[j + kx].x, w4.x, t); t = fmaf(in[j + kx].y, w4.y, t);
-                            t = fmaf(in[j + kx].z, w4.z, t); t = fmaf(in[j + kx].w, w4.w, t);
+                            float2 t = acc[j][o];
+                            t = ffma2(make_float2(in[j + kx].x, in[j + kx].y), make_float2(w4.x, w4.y), t);
+                            t = ffma2(make_float2(in[j + kx].z, in[j + kx].w), make_float2(w4.z, w4.w), t);
                             acc[j][o] = t;
                         }
                     }
@@ -510,7 +522,7 @@ __global__ void __launch_bounds__(256) conv_head7_row8_kernel(const float* __res
         float* dst = y + (((long long)n * ho + oy) * wo + ox) * co;
 #pragma unroll
         for (int o = 0; o < CO; o++)
-            if (o < co) dst[o] = acc[j][o] + (bias ? bias[o] : 0.f);
+            if (o < co) dst[o] = (acc[j][o].x + acc[j][o].y) + (bias ? bias[o] : 0.f);
     }
 }
 
