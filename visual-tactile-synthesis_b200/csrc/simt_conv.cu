@@ -6,6 +6,19 @@
 
 namespace skit {
 
+// Packed fp32 FMA (Blackwell FFMA2): two independent FMAs per lane per instruction on 64-bit register pairs.  The three-register
+// FFMA issues every second cycle per scheduler; in the FMA-bound 7x7 head kernels the channel-quad dot product runs as two partial
+// sums (x,y lanes), added once at the end.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(rd)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+
 struct ConvP {
     const float* x0;
     const __nv_bfloat16* xh;
@@ -89,11 +102,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
             base[i] = 0;
         }
     }
-    float acc[8][CPT];
+    float2 acc2[4][CPT];        // rows (2i, 2i+1) of column j: packed fp32 FMAs, same summation order as scalar FMAs
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < CPT; j++) acc[i][j] = 0.f;
+        for (int j = 0; j < CPT; j++) acc2[i][j] = make_float2(0.f, 0.f);
 
     const int brow = tid >> 4, bcol = (tid & 15) * CPT;
 
@@ -151,21 +164,26 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
         __syncthreads();
 #pragma unroll
         for (int k2 = 0; k2 < BK; k2++) {
-            float a[8], b[CPT];
+            float b[CPT];
             const float4 a0 = *reinterpret_cast<const float4*>(&As[k2][ty * 8]);
             const float4 a1 = *reinterpret_cast<const float4*>(&As[k2][ty * 8 + 4]);
-
-            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
 #pragma unroll
             for (int j = 0; j < CPT; j++) b[j] = Bs[k2][tx * CPT + j];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int j = 0; j < CPT; j++) {
+                const float2 bb = make_float2(b[j], b[j]);
 #pragma unroll
-                for (int j = 0; j < CPT; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int i = 0; i < 4; i++) acc2[i][j] = ffma2(ap[i], bb, acc2[i][j]);
+            }
         }
         __syncthreads();
     }
+    float acc[8][CPT];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < CPT; j++) { acc[2 * i][j] = acc2[i][j].x; acc[2 * i + 1][j] = acc2[i][j].y; }
 
     float s[CPT], q[CPT];
 #pragma unroll
@@ -307,18 +325,6 @@ template <int MODE, int FMT>
 static int launch_thin(const ConvP& p, int n_img, cudaStream_t st) {
     if (MODE == 0 || p.stride == 1) return launch_thin_pix<MODE, FMT, 4>(p, n_img, st);
     return launch_thin_pix<MODE, FMT, 1>(p, n_img, st);
-}
-
-// Packed fp32 FMA (Blackwell FFMA2): two independent FMAs per lane per instruction on 64-bit register pairs.  The three-register
-// FFMA issues every second cycle per scheduler; in the FMA-bound 7x7 head kernels the channel-quad dot product runs as two partial
-// sums (x,y lanes), added once at the end.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long rd;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;"
-        : "=l"(rd)
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
-          "l"(*reinterpret_cast<unsigned long long*>(&c)));
-    return *reinterpret_cast<float2*>(&rd);
 }
 
 // ---------------------------------------------------------------------------------- thin-output 7x7 head
@@ -607,11 +613,11 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
         int ky = tap / p.k, kx = tap - ky * p.k;
         coloff[j] = ((long long)ky * p.wp + kx) * p.ci + c;
     }
-    float acc[4][4];
+    float2 acc2[4][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+        for (int j = 0; j < 2; j++) acc2[i][j] = make_float2(0.f, 0.f);
 
     for (int p0 = pbeg; p0 < pend; p0 += WK) {
         const int pix = p0 + pk;
@@ -641,14 +647,22 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
         for (int k2 = 0; k2 < WK; k2++) {
             const float4 a = *reinterpret_cast<const float4*>(&As[k2][ty * 4]);
             const float4 b = *reinterpret_cast<const float4*>(&Bs[k2][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float2 bp[2] = {make_float2(b.x, b.y), make_float2(b.z, b.w)};      // column pairs: packed fp32 FMAs
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int i = 0; i < 4; i++) {
+                const float2 aa = make_float2(av[i], av[i]);
 #pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < 2; j++) acc2[i][j] = ffma2(aa, bp[j], acc2[i][j]);
+            }
         }
         __syncthreads();
     }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) { acc[i][2 * j] = acc2[i][j].x; acc[i][2 * j + 1] = acc2[i][j].y; }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         int o = o0 + ty * 4 + i;
