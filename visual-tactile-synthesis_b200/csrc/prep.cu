@@ -204,28 +204,29 @@ struct FoldP {
     int n, hp, wp, cp, kw, wf;
     __nv_bfloat16* oh; __nv_bfloat16* ol;
 };
+// grid: one block per (image, row) — no per-element 64-bit divisions; a thread produces 8 folded channels of one pixel (one 16-byte
+// store per plane), the row's thin source (wp * cp floats, a few KB) stays in L1 across the kw shifted reads.
 __global__ void __launch_bounds__(256) fold_x_kernel(FoldP p) {
-    const long long total = (long long)p.n * p.hp * p.wf * 16;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int j0 = (int)(i % 16) * 4;
-        long long t = i / 16;
-        const int x = (int)(t % p.wf); t /= p.wf;
-        const int y = (int)(t % p.hp);
-        const int b = (int)(t / p.hp);
-        __nv_bfloat16 hi[4], lo[4];
+    const int row = blockIdx.x;                       // b * hp + y
+    const long long src_row = (long long)row * p.wp * p.cp;
+    const long long dst_row = (long long)row * p.wf * 64;
+    for (int i = threadIdx.x; i < p.wf * 8; i += 256) {
+        const int x = i >> 3, j0 = (i & 7) * 8;
+        __align__(16) __nv_bfloat16 hi[8], lo[8];
+        int kx = j0 / p.cp, c = j0 - kx * p.cp;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int j = j0 + q, kx = j / p.cp, c = j - kx * p.cp;
+        for (int q = 0; q < 8; q++) {
             float v = 0.f;
             if (kx < p.kw) {
-                const long long a = (((long long)b * p.hp + y) * p.wp + x + kx) * p.cp + c;
-                v = p.tfmt == SKIT_FMT_F32 ? p.t0[a] : (__bfloat162float(p.th[a]) + __bfloat162float(p.tl[a]));
+                const long long a = src_row + (long long)(x + kx) * p.cp + c;
+                v = p.tfmt == SKIT_FMT_F32 ? __ldg(p.t0 + a) : (__bfloat162float(p.th[a]) + __bfloat162float(p.tl[a]));
             }
             split_bf16(v, hi[q], lo[q]);
+            if (++c == p.cp) { c = 0; kx++; }
         }
-        const long long dst = (((long long)b * p.hp + y) * p.wf + x) * 64 + j0;
-        *reinterpret_cast<uint2*>(p.oh + dst) = *reinterpret_cast<uint2*>(hi);
-        *reinterpret_cast<uint2*>(p.ol + dst) = *reinterpret_cast<uint2*>(lo);
+        const long long dst = dst_row + (long long)x * 64 + j0;
+        *reinterpret_cast<uint4*>(p.oh + dst) = *reinterpret_cast<uint4*>(hi);
+        *reinterpret_cast<uint4*>(p.ol + dst) = *reinterpret_cast<uint4*>(lo);
     }
 }
 
@@ -818,7 +819,7 @@ extern "C" int skit_fold_x_operand(const skit_operand* thin, int kw, const skit_
     p.t0 = (const float*)thin->p0; p.th = (const __nv_bfloat16*)thin->p0; p.tl = (const __nv_bfloat16*)thin->p1; p.tfmt = thin->fmt;
     p.n = thin->n; p.hp = thin->hp; p.wp = thin->wp; p.cp = thin->c; p.kw = kw; p.wf = folded->wp;
     p.oh = (__nv_bfloat16*)folded->p0; p.ol = (__nv_bfloat16*)folded->p1;
-    fold_x_kernel<<<grid_for((long long)p.n * p.hp * p.wf * 16, 256), 256, 0, as_stream(stream)>>>(p);
+    fold_x_kernel<<<p.n * p.hp, 256, 0, as_stream(stream)>>>(p);
     return check_launch("fold_x_kernel");
 }
 
