@@ -77,6 +77,8 @@ CASES = {
     "crop": dict(data_len=3),                                                                   # the reference's training default: crop only
     "zoom_crop": dict(preprocess="zoom_crop", random_scale_max=1.5, crop_size=192, data_len=2),   # LANCZOS zoom, then 192 -> 256 "power 2" resize
     "noresample": dict(w_resampling=False, sample_bbox_per_patch=1, data_len=1),
+    # the test phase (models/sinskitG_model.py:359-374): no augmentation, centre crop, every patch, the centre-most squares, no validation set
+    "test": dict(is_train=False, isTrain=False, preprocess="none", data_len=1, sample_bbox_per_patch=1, batch_size_G2=100, subdir_valT=None),
 }
 
 

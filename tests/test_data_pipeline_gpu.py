@@ -132,16 +132,19 @@ def _check_item(d, prefix, item):
         assert item[k].is_cuda and np.array_equal(item[k].cpu().numpy(), ref), (prefix, k)
     for k in ("T_images", "I_masks", "val_T_images", "val_I_masks"):
         ref = d["%s/%s" % (prefix, k)]
+        if ref.size == 0:                       # the test phase has no validation set: the reference stores []
+            assert len(item[k]) == 0
+            continue
         got = item[k].cpu().numpy()
         assert got.dtype == ref.dtype and np.array_equal(got, ref), (prefix, k)
     for k in ("T_coords", "val_T_coords", "full_T_coords", "val_full_T_coords"):
-        assert np.array_equal(np.asarray(item[k]), d["%s/%s" % (prefix, k)]), (prefix, k)
+        assert np.array_equal(np.asarray(item[k]).reshape(d["%s/%s" % (prefix, k)].shape), d["%s/%s" % (prefix, k)]), (prefix, k)
     keys = list(d[prefix + "/augmentation_params__keys"])
     assert sorted(item["augmentation_params"]) == keys
     assert np.array_equal(np.array([float(item["augmentation_params"][a]) for a in keys]), d[prefix + "/augmentation_params"])
 
 
-@pytest.mark.parametrize("case", ["crop", "zoom_crop", "noresample"])
+@pytest.mark.parametrize("case", ["crop", "zoom_crop", "noresample", "test"])
 def test_dataset_matches_reference_golden(V, case, tmp_path):
     """Same seeded directory, same seeds, same options -> the reference's items bit for bit (LANCZOS zoom and power-of-2 resize
     included in the zoom_crop case)."""
