@@ -491,6 +491,13 @@ int skit_touch_squares(const double* touch_mask, const long long* pix_off, const
 int skit_laplacian_var_u8(const unsigned char* img, int h, int w, const int* x0, const int* y0, int K, int size, int ref, double* out,
                           void* stream);
 
+/* Candidate offsets of get_patch_in_input's random mode (models/model_utils.py:212-218): clamp(conv2d(M, ones(k, k), padding=pad), 0, 1)
+ * != 0 for a non-negative single-channel mask M [h][w], on the oh x ow = (h + 2 pad - k + 1) x (w + 2 pad - k + 1) map.  bits: oh rows of
+ * ceil(ow / 32) 32-bit words (bit c % 32 of word c / 32 = position (r, c), the order torch.nonzero lists them in); rowcount[oh] = set
+ * bits per row.  scratch = h * ow bytes. */
+int skit_mask_box_bits(const float* M, int h, int w, int k, int pad, unsigned char* scratch, unsigned int* bits, int* rowcount,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

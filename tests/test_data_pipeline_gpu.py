@@ -225,3 +225,28 @@ def test_multi_material_dataset_matches_reference_golden(V, tmp_path, monkeypatc
     opt2.load_contact_mask = False
     with pytest.raises(NotImplementedError, match="load_contact_mask"):
         V.SkitDataset(opt2)
+
+
+@pytest.mark.parametrize("hw", [(64, 80), (97, 131), (300, 290)])
+def test_device_offset_table_matches_host_table(V, hw):
+    """The random-patch candidate table built by the kernel (bit map + row counts) lists the same (row, col) positions, in the same
+    order, as the host table (whose construction tests/test_host_logic.py pins against the reference's conv2d + nonzero)."""
+    import random as pyrandom
+    MU = V.model_utils
+    h, w = hw
+    g = np.random.default_rng(h)
+    for kind in ("ellipse", "sparse", "ones", "zeros"):
+        if kind == "ellipse":
+            yy, xx = np.mgrid[0:h, 0:w]
+            m = ((((xx - w / 2) / (0.3 * w)) ** 2 + ((yy - h / 2) / (0.35 * h)) ** 2) <= 1).astype(np.float32)
+        elif kind == "sparse":
+            m = (g.random((h, w)) < 0.002).astype(np.float32)
+        else:
+            m = np.full((h, w), 1.0 if kind == "ones" else 0.0, np.float32)
+        M = torch.from_numpy(m)[None, None]
+        host, dev = MU.random_patch_offset_table(M), MU.random_patch_offset_table(M.cuda())
+        assert len(host) == len(dev), kind
+        assert np.array_equal(host.rows, dev.rows) and np.array_equal(host.cols, dev.cols), kind
+        if len(host) >= 8:
+            a = host.sample(8, rng=pyrandom.Random(3)); b = dev.sample(8, rng=pyrandom.Random(3))
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

@@ -110,6 +110,7 @@ SIGNATURES = {
     "skit_contact_centers": [_P, _P, _P, _LL, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "skit_touch_squares": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P],
     "skit_laplacian_var_u8": [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P],
+    "skit_mask_box_bits": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     "skit_patchnce": [_P, _P, _I, _I, _I, _F, _P, _P, _F, _P],
 }
 _NO_RC = {"skit_last_error": (C.c_char_p, []), "skit_version": (_I, []), "skit_built_arch": (_I, [])}

@@ -300,9 +300,57 @@ __global__ void __launch_bounds__(256) laplacian_var_kernel(const unsigned char*
     }
 }
 
+// ------------------------------------------------------------------------------------------------- random-patch candidates
+// get_patch_in_input's random mode (models/model_utils.py:212-218): clamp(conv2d(M, ones(k, k), padding=pad), 0, 1) != 0, i.e. for a
+// non-negative mask "some mask pixel in the k x k window", on the (h + 2 pad - k + 1) x (w + 2 pad - k + 1) map whose nonzero
+// positions are the candidate offsets.  Separable window-any; the result leaves as a bit map (bit c % 32 of word c / 32, row-major)
+// plus per-row counts, so the host keeps (h - 14) x (w - 14) / 8 bytes instead of pulling the mask over and running cumulative sums.
+__global__ void __launch_bounds__(256) mask_rowwin_kernel(const float* __restrict__ M, int h, int w, int k, int pad, int ow,
+                                                          unsigned char* __restrict__ rowwin) {
+    const long long total = (long long)h * ow;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / ow), c = (int)(i % ow);
+        const int lo = max(0, c - pad), hi = min(w, c - pad + k);
+        unsigned char any = 0;
+        for (int x = lo; x < hi; x++) any |= (M[(long long)y * w + x] > 0.f);
+        rowwin[i] = any;
+    }
+}
+// one block per output row r: box[r][c] = any(rowwin[r - pad .. r - pad + k - 1][c])
+__global__ void __launch_bounds__(256) mask_box_bits_kernel(const unsigned char* __restrict__ rowwin, int h, int k, int pad, int ow, int words,
+                                                            unsigned int* __restrict__ bits, int* __restrict__ rowcount) {
+    __shared__ int cnt;
+    const int r = blockIdx.x;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const int lo = max(0, r - pad), hi = min(h, r - pad + k);
+    int mine = 0;
+    for (int c0 = 0; c0 < words * 32; c0 += 256) {
+        const int c = c0 + threadIdx.x;
+        int any = 0;
+        if (c < ow)
+            for (int y = lo; y < hi && !any; y++) any = rowwin[(long long)y * ow + c];
+        const unsigned bal = __ballot_sync(0xffffffffu, any);
+        if ((threadIdx.x & 31) == 0 && (c >> 5) < words) { bits[(long long)r * words + (c >> 5)] = bal; mine += __popc(bal); }
+    }
+    if (mine) atomicAdd(&cnt, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) rowcount[r] = cnt;
+}
+
 }  // namespace skit
 
 using namespace skit;
+
+extern "C" int skit_mask_box_bits(const float* M, int h, int w, int k, int pad, unsigned char* scratch, unsigned int* bits, int* rowcount,
+                                  void* stream) {
+    const int oh = h + 2 * pad - k + 1, ow = w + 2 * pad - k + 1;
+    SKIT_REQUIRE(M && scratch && bits && rowcount && k >= 1 && pad >= 0 && oh > 0 && ow > 0, "mask_box_bits: bad arguments (%d x %d, k %d, pad %d)", h, w, k, pad);
+    const int words = (ow + 31) / 32;
+    mask_rowwin_kernel<<<grid_for((long long)h * ow), 256, 0, as_stream(stream)>>>(M, h, w, k, pad, ow, scratch);
+    mask_box_bits_kernel<<<oh, 256, 0, as_stream(stream)>>>(scratch, h, k, pad, ow, words, bits, rowcount);
+    return check_launch("mask_box_bits");
+}
 
 extern "C" int skit_resize_u8(const unsigned char* src, int sh, int sw, int c, unsigned char* dst, int dh, int dw, int filter, void* stream) {
     SKIT_REQUIRE(src && dst && sh > 0 && sw > 0 && dh > 0 && dw > 0 && c >= 1 && c <= 4, "resize_u8: bad shape %dx%dx%d -> %dx%d", sh, sw, c, dh, dw);

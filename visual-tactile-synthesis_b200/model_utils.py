@@ -65,11 +65,59 @@ class _OffsetTable:
         return cols.astype(np.int32), rows.astype(np.int32)  # (offset_x, offset_y)
 
 
+class _BitOffsetTable(_OffsetTable):
+    """The same table from the device kernel's output: one bit per position (row-major, little-endian within each 32-bit word) and
+    the per-row counts; only the sampled rows are ever unpacked."""
+
+    def __init__(self, bits, rowcount, oh, ow):
+        self.bits, self.oh, self.ow = bits, oh, ow           # bits: uint8 [oh, 4 * words]
+        self.box = None
+        self.rowcum = np.cumsum(rowcount.astype(np.int64))
+        self.n = int(self.rowcum[-1]) if oh > 0 else 0
+
+    def _row(self, r):
+        return np.flatnonzero(np.unpackbits(self.bits[r], bitorder="little")[:self.ow])
+
+    def at(self, picks):
+        picks = np.asarray(picks, dtype=np.int64)
+        rows = np.searchsorted(self.rowcum, picks, side="right")
+        before = np.where(rows > 0, self.rowcum[np.maximum(rows - 1, 0)], 0)
+        cols = np.array([self._row(r)[k] for r, k in zip(rows, picks - before)], dtype=np.int64)
+        return rows, cols
+
+    @property
+    def rows(self):
+        return np.concatenate([np.full(len(self._row(r)), r, dtype=np.int64) for r in range(self.oh)]) if self.oh else np.zeros(0, np.int64)
+
+    @property
+    def cols(self):
+        return np.concatenate([self._row(r) for r in range(self.oh)]) if self.oh else np.zeros(0, np.int64)
+
+
+def _device_offset_table(M):
+    """random_patch_offset_table for a mask that already lives on the device (the staged `self.M`): the 17 x 17 window-any runs as a
+    kernel and (H - 14) x (W - 14) / 8 bytes + the row counts come back, instead of the whole mask going to the host for cumulative sums
+    (17 ms per `set_input` at 1536 x 1536 with a real object mask)."""
+    from . import _lib as L
+    m = M[0, 0].contiguous().float()
+    H, W = m.shape
+    k, pad = 17, 1
+    oh, ow = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    words = (ow + 31) // 32
+    scratch = torch.empty(H * ow, dtype=torch.uint8, device=m.device)
+    bits = torch.empty((oh, words), dtype=torch.int32, device=m.device)
+    rowcount = torch.empty(oh, dtype=torch.int32, device=m.device)
+    L.call("skit_mask_box_bits", L.ptr(m), H, W, k, pad, L.ptr(scratch), L.ptr(bits), L.ptr(rowcount), L.stream())
+    return _BitOffsetTable(bits.cpu().numpy().view(np.uint8).reshape(oh, words * 4), rowcount.cpu().numpy(), oh, ow)
+
+
 def random_patch_offset_table(M):
     """`clamp(conv2d(M, ones(1,1,17,17), padding=1), 0, 1)` then torch.nonzero in row-major order
     (model_utils.py:212-218); the map is (H-14)x(W-14) and its (row, col) are used directly as
     (offset_y, offset_x).  Host side: for a non-negative mask "box sum > 0" is a 17x17 dilation, done separably with
     two integer running sums (exact for the 0/1 masks the datasets produce)."""
+    if torch.is_tensor(M) and M.is_cuda:
+        return _device_offset_table(M)
     m = np.asarray(M[0, 0].cpu()) > 0
     H, W = m.shape
     oh, ow = H + 2 - 17 + 1, W + 2 - 17 + 1

@@ -283,7 +283,7 @@ class SinSKITGModel:
             self.fake_in[:, 6:7] = self.I_masks
             self.real_in[:, 6:7] = self.I_masks
             self.real_in[:, 0:2] = self.real_T
-            self._offset_table = random_patch_offset_table(M) if opt.use_more_fakeT else None
+            self._offset_table = random_patch_offset_table(self.M) if opt.use_more_fakeT else None     # on the staged device mask
         self.name = input.get("name")
         self.image_paths = input.get("S_paths", [])
         self.augmentation_params = input.get("augmentation_params")
