@@ -1,4 +1,5 @@
-"""Host-side phases of the training loop with the device dataset (fetch + collate, set_input, train step), synchronised per phase:\n    python tools/prof_e2e_loop.py      # 1536 x 1536, arch B, 4 augmentations x 4 epochs"""
+"""Host-side phases of the training loop with the device dataset (fetch + collate, set_input, train step), synchronised per phase:
+    python tools/prof_e2e_loop.py      # 1536 x 1536, arch B, 4 augmentations x 4 epochs"""
 import os, sys, time, random
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
