@@ -174,6 +174,9 @@ def test_dataset_feeds_the_train_step(V, tmp_path):
             m.set_input(batch)
             m.optimize_parameters()
     assert m.h2d_bytes < 4096                          # nothing but the patch offsets crosses the bus
+    ref_t = V.model_utils.random_patch_offset_table(ds[1]["M"][None].cpu())        # host construction on the item's mask
+    got_t = V.model_utils.offset_table_from_arrays(ds[1]["M_box_bits"].numpy(), ds[1]["M_box_rowcount"].numpy(), 256, 256)
+    assert len(ref_t) == len(got_t) and np.array_equal(ref_t.rows, got_t.rows) and np.array_equal(ref_t.cols, got_t.cols)
     assert torch.equal(ds[0]["S"], before)             # the model masks its own staged copy, not the dataset's cached tensor
     losses = m.get_current_losses()
     assert all(np.isfinite(float(v)) for v in losses.values())

@@ -488,8 +488,8 @@ class SingleSkitDataset(torch.utils.data.Dataset):
                 "patch_crop_size": self.PATCH,
             }
             item = {"name": self._name(m), "S_paths": self.S_paths[0], "augmentation_params": augmentation_params}
+            M3 = S3 = None
             if m.I_img is not None:
-                M3 = S3 = None
                 if m.touch is not None or m.val_touch is not None:
                     M3 = self._final_u8(src["img"]["M"], crop_pos_x, crop_pos_y)
                     S3 = self._final_u8(src["img"]["S"], crop_pos_x, crop_pos_y)
@@ -508,6 +508,12 @@ class SingleSkitDataset(torch.utils.data.Dataset):
                 item["T_images"] = []
             if m.M_img is not None:
                 item["M_paths"] = m.M_path
+                if M3 is not None:
+                    # extension (ignored by the reference model): the candidate table of get_patch_in_input's random fake patches for
+                    # this item's mask, so that the B200 model's set_input does no device work for it
+                    from .model_utils import offset_table_arrays
+                    bits, rowcount = offset_table_arrays(M3[:, :, 0])
+                    item["M_box_bits"], item["M_box_rowcount"] = torch.from_numpy(bits.copy()), torch.from_numpy(rowcount)
             self._index_key[index] = (mi, zi)
             self.data_dict[index] = item
 

@@ -111,6 +111,18 @@ def _device_offset_table(M):
     return _BitOffsetTable(bits.cpu().numpy().view(np.uint8).reshape(oh, words * 4), rowcount.cpu().numpy(), oh, ow)
 
 
+def offset_table_arrays(m2d_device):
+    """(bits uint8 [oh, 4 * words], rowcount int32 [oh]) host arrays of the candidate table for a device mask [H, W] (any dtype,
+    > 0 = inside): what the device dataset stores with each item so that `set_input` needs no device work for it."""
+    t = _device_offset_table(m2d_device[None, None])
+    return t.bits, np.diff(np.concatenate([[0], t.rowcum])).astype(np.int32)
+
+
+def offset_table_from_arrays(bits, rowcount, H, W):
+    oh, ow = H + 2 - 17 + 1, W + 2 - 17 + 1
+    return _BitOffsetTable(np.ascontiguousarray(bits).reshape(oh, -1), np.asarray(rowcount).reshape(oh), oh, ow)
+
+
 def random_patch_offset_table(M):
     """`clamp(conv2d(M, ones(1,1,17,17), padding=1), 0, 1)` then torch.nonzero in row-major order
     (model_utils.py:212-218); the map is (H-14)x(W-14) and its (row, col) are used directly as

@@ -26,7 +26,7 @@ import torch
 
 from . import _lib as L_
 from . import networks, ops
-from .model_utils import find_coords_for_patch, random_patch_offset_table, spe_grid
+from .model_utils import find_coords_for_patch, offset_table_from_arrays, random_patch_offset_table, spe_grid
 
 
 def default_options(**kw):
@@ -283,11 +283,30 @@ class SinSKITGModel:
             self.fake_in[:, 6:7] = self.I_masks
             self.real_in[:, 6:7] = self.I_masks
             self.real_in[:, 0:2] = self.real_T
-            self._offset_table = random_patch_offset_table(self.M) if opt.use_more_fakeT else None     # on the staged device mask
+            self._offset_table = self._make_offset_table(input, M) if opt.use_more_fakeT else None
         self.name = input.get("name")
         self.image_paths = input.get("S_paths", [])
         self.augmentation_params = input.get("augmentation_params")
         self.full_T_coords = input.get("full_T_coords")
+
+    def _make_offset_table(self, input, M):
+        """Candidate offsets of the NF random fake patches (model_utils.py:212-218) without stalling the launching stream: items of the
+        device dataset carry the table (built when the item was made); a host mask is uploaded and dilated on a side stream of its
+        own, so the small read-back waits for that stream only, not for the previous train step still running on the main one."""
+        if "M_box_bits" in input:
+            bits, rc = input["M_box_bits"], input["M_box_rowcount"]
+            bits = bits.cpu().numpy() if torch.is_tensor(bits) else np.asarray(bits)
+            rc = rc.cpu().numpy() if torch.is_tensor(rc) else np.asarray(rc)
+            return offset_table_from_arrays(bits, rc, M.shape[-2], M.shape[-1])
+        if M.is_cuda:
+            return random_patch_offset_table(M)
+        if bool((M[0, 0] > 0).all()):
+            return random_patch_offset_table(M)          # every position is a candidate: nothing to compute
+        if getattr(self, "_aux", None) is None:
+            self._aux = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._aux):
+            md = M[:1].contiguous().pin_memory().to(self.device, non_blocking=True)
+            return random_patch_offset_table(md)
 
     def _style_code_from(self, input):
         """The generator's style code as a host fp32 [N, style_code_dim] tensor.  The reference computes it in forward() with CLIP
