@@ -109,6 +109,19 @@ def test_patch_coordinates_match_reference_golden(golden_dir):
     random.seed(1)
     b = O.random_patch_offsets(ones, 5)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # the bit-map form of the table (what the device kernel returns and the device dataset stores with each item): same picks as
+    # the reference golden when built from the host table's own box
+    host = MU.random_patch_offset_table(M)
+    oh, ow = host.box.shape
+    words = (ow + 31) // 32
+    padded = np.zeros((oh, words * 32), np.uint8)
+    padded[:, :ow] = host.box
+    bits = np.packbits(padded, axis=1, bitorder="little")
+    tb = MU.offset_table_from_arrays(bits, host.box.sum(1).astype(np.int32), M.shape[-2], M.shape[-1])
+    random.seed(5)
+    box, boy = tb.sample(12)
+    assert np.array_equal(box, g["rand_ox"]) and np.array_equal(boy, g["rand_oy"])
+    assert len(tb) == len(host) and np.array_equal(tb.rows, host.rows) and np.array_equal(tb.cols, host.cols)
 
 
 def test_positional_encoding_matches_reference_golden(golden_dir):
