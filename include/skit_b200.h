@@ -345,6 +345,11 @@ int skit_patch_scatter_add(const float* dpatch, int ctot, int coff, int cs, int 
 /* GANLoss 'nonsaturating' on one scale (networks.py:500-522): loss[b] += mean_hw softplus(sign * pred[b]).
  * sign = -1 for target_is_real, +1 for fake.  If dpred != NULL: dpred = gscale * sign * sigmoid(sign*pred)/(h*w). */
 int skit_gan_softplus(const float* pred, int n, int hw, float sign, float* loss, float* dpred, float gscale, void* stream);
+/* GANLoss.get_loss_for_single_scale_discriminator in every mode (models/networks.py:500-522): mode 0 nonsaturating, 1 hinge, 2 wgan /
+ * wgangp (value only: the gradient penalty is not part of GANLoss), 3 lsgan (MSE against `target`), 4 vanilla (BCE-with-logits against
+ * `target`).  loss[b] += mean over sample b's hw elements; dpred (optional) = gscale * d(that mean)/d(pred). */
+int skit_gan_loss(const float* pred, int n, int hw, int mode, int target_is_real, float target, float* loss, float* dpred,
+                  float gscale, void* stream);
 
 /* L1: loss[0] += scale * sum |a-b| ; if grad != NULL: grad (+)= gscale * sign(a-b)  (sinskitG_model.py:1702,1812). */
 int skit_l1_loss(const float* a, const float* b, long long numel, float scale, float* loss,

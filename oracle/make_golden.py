@@ -432,9 +432,34 @@ def make_metrics():
     print("metrics.npz: T_AE %.6f deg, T_MSE %.6f" % (ae.item(), mse.item()))
 
 
+def make_ganloss():
+    """GANLoss (models/networks.py:448-542) in every mode it defines, with and without label smoothing (sinskitG_model.py:485-490), on a
+    multiscale prediction list and on a bare tensor, real and fake targets: loss values and d(loss.mean())/d(prediction)."""
+    N = ref_networks()
+    g = torch.Generator().manual_seed(33)
+    preds = [torch.randn(3, 1, 9, 9, generator=g) * 1.5, torch.randn(3, 1, 5, 5, generator=g) * 1.5, torch.randn(3, 1, 4, 4, generator=g) * 1.5]
+    out = {"pred%d" % i: p.numpy() for i, p in enumerate(preds)}
+    for mode in ("nonsaturating", "hinge", "wgan", "wgangp", "lsgan", "vanilla"):
+        for smooth in (False, True):
+            crit = N.GANLoss(mode, target_real_label=0.8, target_fake_label=0.0) if smooth else N.GANLoss(mode)
+            for is_real in (True, False):
+                ps = [p.clone().requires_grad_(True) for p in preds]
+                loss = crit([[p] for p in ps], is_real)
+                loss.mean().backward()
+                key = "%s/%d/%d" % (mode, int(smooth), int(is_real))
+                out[key + "/multi"] = loss.detach().numpy()
+                for i, p in enumerate(ps):
+                    out[key + "/grad%d" % i] = p.grad.numpy()
+                out[key + "/bare"] = crit([preds[0]], is_real).detach().numpy()      # a list holding one tensor: input[-1]
+    np.savez_compressed(os.path.join(OUT, "ganloss.npz"), **out)
+    print("ganloss.npz: %d arrays" % len(out))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["networks", "ops", "step", "stylegan2", "options", "step_lpips", "metrics"]
+    which = sys.argv[1:] or ["networks", "ops", "step", "stylegan2", "options", "step_lpips", "metrics", "ganloss"]
+    if "ganloss" in which:
+        make_ganloss()
     if "metrics" in which:
         make_metrics()
     if "options" in which:

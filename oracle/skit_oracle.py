@@ -376,7 +376,7 @@ def multiscale_d_forward(sd, x, num_D=3, n_layers=3, update_running=True):
     return out
 
 
-def gan_loss(pred, target_is_real, gan_mode="nonsaturating"):
+def gan_loss(pred, target_is_real, gan_mode="nonsaturating", real_label=1.0, fake_label=0.0):
     """GANLoss.__call__ (models/networks.py:500-542).  Multiscale (list of lists) sums the
     per-sample losses of the last map of each scale; a bare tensor uses `input[-1]`, i.e.
     the LAST BATCH ELEMENT only (reference quirk, :541-542)."""
@@ -388,6 +388,11 @@ def gan_loss(pred, target_is_real, gan_mode="nonsaturating"):
             return F.relu(1.0 - p if target_is_real else 1.0 + p).view(bs, -1).mean(dim=1)
         if gan_mode in ("wgan", "wgangp"):
             return -p.mean() if target_is_real else p.mean()
+        t = torch.full_like(p, real_label if target_is_real else fake_label)        # get_target_tensor (:482-497)
+        if gan_mode == "lsgan":
+            return F.mse_loss(p, t)
+        if gan_mode == "vanilla":
+            return F.binary_cross_entropy_with_logits(p, t)
         raise NotImplementedError(gan_mode)
 
     if isinstance(pred[0], list):
@@ -533,6 +538,7 @@ class StepConfig:
 
     def __init__(self, **kw):
         self.netG = "resnet_9blocks"
+        self.gan_mode = "nonsaturating"      # 'hinge' is the only other mode the reference's own G2 loss survives (len() of a 0-d tensor, :1783)
         self.n_blocks = 9
         self.num_D = 3
         self.n_layers_D = 3
@@ -663,16 +669,16 @@ def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.
     # ---- D1 step
     d_params_on(sdD)
     pf = multiscale_d_forward(sdD, torch.cat([real_S, fake_I.detach()], 1), cfg.num_D, cfg.n_layers_D)
-    l_f = gan_loss(pf, False).mean() * cfg.lambda_G1_GAN
+    l_f = gan_loss(pf, False, cfg.gan_mode).mean() * cfg.lambda_G1_GAN
     pr = multiscale_d_forward(sdD, torch.cat([real_S, real_I], 1), cfg.num_D, cfg.n_layers_D)
-    l_r = gan_loss(pr, True).mean() * cfg.lambda_G1_GAN
+    l_r = gan_loss(pr, True, cfg.gan_mode).mean() * cfg.lambda_G1_GAN
     losses["D_fake_I"], losses["D_real_I"] = l_f.item(), l_r.item()
     grads_D = run_opt("D", sdD, cfg.lr, (l_f + l_r) * 0.5)
 
     # ---- D2 step
     d_params_on(sdD2)
     fake_in = torch.cat([fake_T_p.detach(), S_p, afake_p], 1)
-    l_f2 = gan_loss(multiscale_d_forward(sdD2, fake_in, cfg.num_D, cfg.n_layers_D), False).mean() * cfg.lambda_G2_GAN
+    l_f2 = gan_loss(multiscale_d_forward(sdD2, fake_in, cfg.num_D, cfg.n_layers_D), False, cfg.gan_mode).mean() * cfg.lambda_G2_GAN
     # full-resolution D2 pass (:1495): visualisation only, but it updates BN running stats
     full_in = torch.cat([fake_T.detach(), real_S, fw["aug_fake_I"].detach(), M], 1)
     with torch.no_grad():
@@ -686,20 +692,20 @@ def train_step(cfg, sdG, sdD, sdD2, opt_state, batch, rand, step=1, lr_factor=1.
                           gather_patches(real_S, fox, foy, csf),
                           gather_patches(fake_I.detach(), fox, foy, csf),
                           torch.ones(NF, 1, 32, 32, device=real_S.device)], 1)
-        l_m2 = gan_loss(multiscale_d_forward(sdD2, more, cfg.num_D, cfg.n_layers_D), False).mean() * cfg.lambda_G2_GAN
+        l_m2 = gan_loss(multiscale_d_forward(sdD2, more, cfg.num_D, cfg.n_layers_D), False, cfg.gan_mode).mean() * cfg.lambda_G2_GAN
         losses["D_more_fake_T"] = l_m2.item()
     real_in = torch.cat([real_T, S_p, areal_p], 1)
-    l_r2 = gan_loss(multiscale_d_forward(sdD2, real_in, cfg.num_D, cfg.n_layers_D), True).mean() * cfg.lambda_G2_GAN
+    l_r2 = gan_loss(multiscale_d_forward(sdD2, real_in, cfg.num_D, cfg.n_layers_D), True, cfg.gan_mode).mean() * cfg.lambda_G2_GAN
     losses["D_fake_T_concat"], losses["D_real_T_concat"] = l_f2.item(), l_r2.item()
     grads_D2 = run_opt("D2", sdD2, cfg.lr_G2, (l_f2 + l_m2 + l_r2) * 0.5)
 
     # ---- G step (D, D2 already updated; their params frozen)
     pg = multiscale_d_forward(sdD, torch.cat([real_S, fake_I], 1), cfg.num_D, cfg.n_layers_D)
-    l_gan = gan_loss(pg, True).mean() * cfg.lambda_G1_GAN
+    l_gan = gan_loss(pg, True, cfg.gan_mode).mean() * cfg.lambda_G1_GAN
     l_l1 = (fake_I - real_I).abs().mean() * cfg.lambda_G1_L1
     with torch.no_grad():  # value only: computed on a detached clone (:1751,1781)
         pg2 = multiscale_d_forward(sdD2, fake_in, cfg.num_D, cfg.n_layers_D)
-        l_g2 = (gan_loss(pg2, True) * cfg.lambda_G2_GAN).view(-1, NT).mean(dim=0).sum()
+        l_g2 = (gan_loss(pg2, True, cfg.gan_mode) * cfg.lambda_G2_GAN).view(-1, NT).mean(dim=0).sum()
     l_l1_2 = ((fake_T_p - real_T).abs() * cfg.lambda_G2_L1).view(-1, NT, *fake_T_p.shape[1:]).sum(dim=1).mean()
     losses.update(G_GAN=l_gan.item(), G_L1=l_l1.item(), G2_GAN=l_g2.item(), G2_L1=l_l1_2.item())
     loss_G = l_gan + l_l1 + l_g2 + l_l1_2

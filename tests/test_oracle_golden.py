@@ -298,3 +298,21 @@ def test_evaluation_metrics_oracle(golden_dir):
     # the min-max rescale uses the REAL image's range (model_utils.py:483-487): an affine change of both images is undone
     m2 = O.evaluation_metrics((a * 2 - 1) * 3 + 1, (b * 2 - 1) * 3 + 1, rT, fT)
     assert abs(m2["I_PSNR"] - m["I_PSNR"]) < 1e-3 and abs(m2["I_SSIM"] - m["I_SSIM"]) < 1e-5
+
+
+def test_gan_loss_oracle_all_modes(golden_dir):
+    """O.gan_loss in every mode of the reference's GANLoss (values and autograd gradients) against tests/golden/ganloss.npz."""
+    g = np.load(os.path.join(golden_dir, "ganloss.npz"))
+    preds = [torch.from_numpy(g["pred%d" % i]) for i in range(3)]
+    for mode in ("nonsaturating", "hinge", "wgan", "wgangp", "lsgan", "vanilla"):
+        for smooth in (0, 1):
+            for is_real in (1, 0):
+                key = "%s/%d/%d" % (mode, smooth, is_real)
+                ps = [p.clone().requires_grad_(True) for p in preds]
+                loss = O.gan_loss([[p] for p in ps], bool(is_real), mode, real_label=0.8 if smooth else 1.0, fake_label=0.0)
+                loss.mean().backward()
+                np.testing.assert_allclose(loss.detach().numpy(), g[key + "/multi"], rtol=1e-6, atol=1e-7, err_msg=key)
+                for i, p in enumerate(ps):
+                    np.testing.assert_allclose(p.grad.numpy(), g[key + "/grad%d" % i], rtol=1e-6, atol=1e-8, err_msg=key)
+                bare = O.gan_loss([preds[0]], bool(is_real), mode, real_label=0.8 if smooth else 1.0, fake_label=0.0)
+                np.testing.assert_allclose(bare.numpy(), g[key + "/bare"], rtol=1e-6, atol=1e-7, err_msg=key)

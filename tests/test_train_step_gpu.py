@@ -98,13 +98,15 @@ def test_train_step_matches_reference_golden(golden_dir, tag, netG, wkey):
                 np.testing.assert_allclose(sd_now[k].detach().cpu().numpy(), z[ak], rtol=1e-3, atol=3e-4)
 
 
-def test_train_step_ngf64_tcgen05_vs_oracle():
-    """Tensor-core configuration (arch B: resnet_9blocks ngf 64 + multiscale ndf 64) at S = 64."""
+@pytest.mark.parametrize("gan_mode", ["nonsaturating", "hinge"])
+def test_train_step_ngf64_tcgen05_vs_oracle(gan_mode):
+    """Tensor-core configuration (arch B: resnet_9blocks ngf 64 + multiscale ndf 64) at S = 64, in both GAN modes the reference's
+    step can run (per-sample losses: 'nonsaturating', the default, and 'hinge')."""
     import vts_b200
     from oracle import skit_oracle as O
     S, NT, NF = 64, 8, 4
     torch.manual_seed(1)
-    opt = vts_b200.default_options(batch_size_G2=NT, add_fake_T_sample_size=NF, run_full_res_D2=True)
+    opt = vts_b200.default_options(batch_size_G2=NT, add_fake_T_sample_size=NF, run_full_res_D2=True, gan_mode=gan_mode)
     m = vts_b200.SinSKITGModel(opt)
     sds = [{k: v.detach().cpu().clone() for k, v in net.state_dict().items()} for net in (m.netG, m.netD, m.netD2)]
     batch = O.synthetic_batch(S, NT=NT, seed=0, ellipse_mask=True)
@@ -113,7 +115,7 @@ def test_train_step_ngf64_tcgen05_vs_oracle():
     m.set_input(batch)
     m.optimize_parameters(1, rand=rand)
     torch.cuda.synchronize()
-    cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF)
+    cfg = O.StepConfig(netG="resnet_9blocks", batch_size_G2=NT, add_fake_T_sample_size=NF, gan_mode=gan_mode)
     sdG, sdD, sdD2 = [copy.deepcopy(s) for s in sds]
     res = O.train_step(cfg, sdG, sdD, sdD2, {}, O.step_inputs_from_batch(batch), rand, step=1)
     losses = m.current_losses()
@@ -317,3 +319,12 @@ def test_inference_forward_graph_and_batches():
         torch.cuda.synchronize()
         assert rel(fI, ref["fake_I"]) < GATE and rel(fT, ref["fake_T"]) < GATE and rel(fN, ref["fake_N"]) < GATE, i
     assert m._tgraph is not None
+
+
+def test_unsupported_gan_modes_raise():
+    """'lsgan' / 'vanilla' / 'wgan(gp)' make GANLoss return a 0-d tensor, on which the reference's own compute_G2_loss fails
+    (len() of a 0-d tensor, sinskitG_model.py:1782-1784): the B200 step refuses them instead of silently running another loss."""
+    import vts_b200
+    for mode in ("lsgan", "vanilla", "wgangp"):
+        with pytest.raises(NotImplementedError, match="gan_mode"):
+            vts_b200.SinSKITGModel(vts_b200.default_options(gan_mode=mode, batch_size_G2=8, add_fake_T_sample_size=4))

@@ -93,6 +93,7 @@ SIGNATURES = {
     "skit_patch_gather": [C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, _I, _I, _P, _P, _I, _I, _P, _I, _P],
     "skit_patch_scatter_add": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P],
     "skit_gan_softplus": [_P, _I, _I, _F, _P, _P, _F, _P],
+    "skit_gan_loss": [_P, _I, _I, _I, _I, _F, _P, _P, _F, _P],
     "skit_l1_loss": [_P, _P, _LL, _F, _P, _P, _F, _I, _P],
     "skit_adam_step": [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _P],
     "skit_adam_step_dev": [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _P],

@@ -339,6 +339,36 @@ __global__ void __launch_bounds__(256) gan_softplus_kernel(const float* __restri
     }
 }
 
+// GANLoss in every mode the reference defines (models/networks.py:500-522).  mode: 0 nonsaturating softplus(s x), 1 hinge relu(1 + s x),
+// 2 wgan s x, 3 lsgan (x - t)^2, 4 vanilla BCE-with-logits(x, t); s = -1 for a real target, +1 for a fake one, t = the label.
+// loss[b] += mean over the sample's hw elements; dpred = gscale * d(mean)/dx.
+__global__ void __launch_bounds__(256) gan_loss_kernel(const float* __restrict__ pred, int hw, int mode, float sign, float target, float* loss,
+                                                       float* dpred, float gscale) {
+    __shared__ float red[8];
+    const int b = blockIdx.y;
+    const float inv = 1.f / (float)hw;
+    float s = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+        const float x = pred[(long long)b * hw + i];
+        float f, d;
+        if (mode == 0) { const float z = sign * x; f = softplus_f(z); d = sign / (1.f + expf(-z)); }
+        else if (mode == 1) { const float z = 1.f + sign * x; f = fmaxf(z, 0.f); d = z > 0.f ? sign : 0.f; }
+        else if (mode == 2) { f = sign * x; d = sign; }
+        else if (mode == 3) { const float e = x - target; f = e * e; d = 2.f * e; }
+        else { f = fmaxf(x, 0.f) - x * target + log1pf(expf(-fabsf(x))); d = 1.f / (1.f + expf(-x)) - target; }
+        s += f;
+        if (dpred) dpred[(long long)b * hw + i] = gscale * inv * d;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int k = 0; k < 8; k++) tot += red[k];
+        atomicAdd(loss + b, tot * inv);
+    }
+}
+
 __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, long long numel, float scale,
                                                       float* loss, float* grad, float gscale, int accumulate) {
     __shared__ float red[8];
@@ -695,6 +725,14 @@ extern "C" int skit_gan_softplus(const float* pred, int n, int hw, float sign, f
     dim3 grid(min(cdiv(hw, 256), 64), n);
     gan_softplus_kernel<<<grid, 256, 0, as_stream(stream)>>>(pred, hw, sign, loss, dpred, gscale);
     return check_launch("gan_softplus_kernel");
+}
+
+extern "C" int skit_gan_loss(const float* pred, int n, int hw, int mode, int target_is_real, float target, float* loss, float* dpred,
+                             float gscale, void* stream) {
+    SKIT_REQUIRE(pred && loss && n > 0 && hw > 0 && mode >= 0 && mode <= 4, "gan_loss: bad arguments (mode %d)", mode);
+    dim3 grid(min(cdiv(hw, 256), 64), n);
+    gan_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(pred, hw, mode, target_is_real ? -1.f : 1.f, target, loss, dpred, gscale);
+    return check_launch("gan_loss_kernel");
 }
 
 extern "C" int skit_l1_loss(const float* a, const float* b, long long numel, float scale, float* loss,

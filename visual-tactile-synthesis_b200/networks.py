@@ -1158,9 +1158,10 @@ class MultiscaleDiscriminator(_FlatParamsMixin, nn.Module):
 
 # ----------------------------------------------------------------------------- GAN loss
 class GANLoss(nn.Module):
-    """GANLoss (networks.py:448-542).  'nonsaturating' (the skitG default) runs on the fused
-    softplus-mean kernel; multiscale predictions sum the per-sample losses over scales; a bare
-    tensor uses `input[-1]`, i.e. the LAST batch element only (reference quirk, :541-542)."""
+    """GANLoss (networks.py:448-542) in all of its modes on one fused kernel (value here; value + gradient inside the train step).
+    'nonsaturating' / 'hinge' return the per-sample means [bs]; 'lsgan' / 'vanilla' / 'wgan' / 'wgangp' the mean over everything (a
+    0-d tensor), as `nn.MSELoss` / `nn.BCEWithLogitsLoss` / `.mean()` do.  Multiscale predictions sum over scales; a bare tensor uses
+    `input[-1]`, i.e. the LAST batch element only (reference quirk, :541-542)."""
 
     def __init__(self, gan_mode, target_real_label=1.0, target_fake_label=0.0):
         super().__init__()
@@ -1169,15 +1170,16 @@ class GANLoss(nn.Module):
         self.gan_mode = gan_mode
         if gan_mode not in ("lsgan", "vanilla", "wgan", "wgangp", "nonsaturating", "hinge"):
             raise NotImplementedError("gan mode %s not implemented" % gan_mode)
-        if gan_mode != "nonsaturating":
-            raise NotImplementedError("gan mode %s is outside the B200 hot path (only 'nonsaturating', the skitG/sinskitG default)" % gan_mode)
+        self._labels = (float(target_real_label), float(target_fake_label))
 
     def get_loss_for_single_scale_discriminator(self, prediction, target_is_real):
         _require_cuda(prediction, "GANLoss")
         bs = prediction.shape[0]
         loss = torch.zeros(bs, dtype=torch.float32, device=prediction.device)
-        ops.gan_softplus(prediction.contiguous().float(), -1.0 if target_is_real else 1.0, loss)
-        return loss
+        ops.gan_loss(prediction.contiguous().float(), self.gan_mode, target_is_real, self._labels[0 if target_is_real else 1], loss)
+        if self.gan_mode in ("nonsaturating", "hinge"):
+            return loss
+        return loss.mean()          # equal-sized samples: the mean of the per-sample means is the mean over all elements
 
     def __call__(self, input, target_is_real):
         if isinstance(input[0], list):

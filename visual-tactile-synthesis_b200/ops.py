@@ -536,6 +536,17 @@ def gan_softplus(pred, sign, loss, dpred=None, gscale=0.0):
     L.call("skit_gan_softplus", _p(pred), n, hw, float(sign), _p(loss), _p(dpred), float(gscale), L.stream())
 
 
+GAN_MODES = {"nonsaturating": 0, "hinge": 1, "wgan": 2, "wgangp": 2, "lsgan": 3, "vanilla": 4}
+
+
+def gan_loss(pred, mode, target_is_real, target, loss, dpred=None, gscale=0.0):
+    """GANLoss for one scale in any of the reference's modes (networks.py:500-522); loss: [N] per-sample accumulator."""
+    n = pred.shape[0]
+    hw = pred.numel() // n
+    L.call("skit_gan_loss", _p(pred), n, hw, GAN_MODES[mode], int(bool(target_is_real)), float(target), _p(loss), _p(dpred), float(gscale),
+           L.stream())
+
+
 def l1_loss(a, b, scale, loss, grad=None, gscale=0.0, accumulate=False):
     L.call("skit_l1_loss", _p(a), _p(b), a.numel(), float(scale), _p(loss), _p(grad), float(gscale), int(accumulate), L.stream())
 

@@ -139,6 +139,12 @@ class SinSKITGModel:
         # num_D_D2, n_layers_D2: sinskitG_model.py:137-200,505-573), falling back to default_options()'s older spellings
         s_nc = self.sketch_nc = _opt(opt, "sketch_nc", _opt(opt, "input_nc", 1))
         out_nc = _opt(opt, "image_nc", 3) + _opt(opt, "touch_nc", 2) if hasattr(opt, "image_nc") else _opt(opt, "output_nc", 5)
+        gan_mode = _opt(opt, "gan_mode", "nonsaturating")
+        if gan_mode not in ("nonsaturating", "hinge"):
+            # the per-sample modes are the ones the reference's own step survives: with 'lsgan' / 'vanilla' / 'wgan(gp)' GANLoss returns a
+            # 0-d tensor and compute_G2_loss fails on len(loss_G2_GAN) (sinskitG_model.py:1782-1784); wgangp also needs a double backward
+            raise NotImplementedError("gan_mode %r: the train step is built for 'nonsaturating' (the model default) and 'hinge'; "
+                                      "networks.GANLoss itself supports every mode" % gan_mode)
         if (s_nc, out_nc) != (1, 5):
             raise NotImplementedError("the explicit step is built for sketch_nc 1, image_nc 3, touch_nc 2 (the model defaults)")
         if not (_opt(opt, "use_cGAN", True) and _opt(opt, "use_cGAN_G2_S", True) and _opt(opt, "use_cGAN_G2_I", True)):
@@ -475,13 +481,14 @@ class SinSKITGModel:
                           self.opt.beta1, self.opt.beta2, 1e-8, scale)
         net.refresh_packs()
 
-    @staticmethod
-    def _gan(preds, sign, loss_slot, gscale=None):
-        """Sum over scales of the per-sample softplus loss; returns the per-scale dpred list if gscale."""
+    def _gan(self, preds, sign, loss_slot, gscale=None):
+        """Sum over scales of the per-sample GAN loss (softplus or hinge; sign -1 = real target, +1 = fake); returns the per-scale
+        dpred list if gscale."""
+        mode = _opt(self.opt, "gan_mode", "nonsaturating")
         dps = []
         for p in preds:
             dp = torch.empty_like(p) if gscale is not None else None
-            ops.gan_softplus(p, sign, loss_slot, dp, gscale or 0.0)
+            ops.gan_loss(p, mode, sign < 0, 0.0, loss_slot, dp, gscale or 0.0)
             dps.append(dp)
         return dps
 
