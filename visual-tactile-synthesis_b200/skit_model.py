@@ -44,7 +44,7 @@ def default_options(**kw):
         use_positional_encoding=True, use_bg_mask=True, use_diffaug=True, diffaugment="bs", use_more_fakeT=True,
         gan_mode="nonsaturating",
         lambda_G1_GAN=1.0, lambda_G1_L1=100.0, lambda_G1_lpips=0.0, lambda_G2_GAN=5.0, lambda_G2_L1=10.0,
-        lambda_G2_lpips=0.0, use_vision_aided_loss=False,
+        lambda_G2_lpips=0.0, lambda_G2_GAN_feat=1.0, smooth_GAN_label=True, use_vision_aided_loss=False,
         num_layer_separate=4, use_style_code=False, style_code_mode="concat", style_code_mapping_mode="tile",
         style_code_dim=512, num_layer_style_code=1,
         batch_size=1, batch_size_G2=64, add_fake_T_sample_size=32, scale_nz=0.25, T_resolution_multiplier=1,
@@ -800,9 +800,13 @@ class SinSKITGModel:
         loss_names order (sinskitG_model.py:430-456); the gradient penalties are identically 0 outside gan_mode 'wgangp'."""
         raw = self.current_losses()
         order = ["G_GAN", "D_real_I", "D_fake_I", "D_I_grad_penalty", "G_L1", "G_lpips", "G2_GAN", "D_real_T_concat",
-                 "D_fake_T_concat", "D_T_grad_penalty", "D_more_fake_T", "G2_L1", "G2_lpips", "NCE"]
+                 "D_fake_T_concat", "D_T_grad_penalty", "D_more_fake_T", "G2_L1", "G2_lpips", "G2_GAN_feat", "NCE"]
         raw.setdefault("D_I_grad_penalty", 0.0)
         raw.setdefault("D_T_grad_penalty", 0.0)
+        if _opt(self.opt, "lambda_G2_GAN_feat", 0.0) > 0.0:
+            # listed by the reference whenever the weight is positive (default 1, :455-456) and always 0: its feature-matching branch
+            # compares a module with a string (`self.netD2 == "multiscale"`, :1794) and never runs
+            raw.setdefault("G2_GAN_feat", 0.0)
         return collections.OrderedDict(("l_" + k, raw[k]) for k in order if k in raw)
 
     # ------------------------------------------------------------------ BaseModel contract (models/base_model.py:71-230)
