@@ -253,3 +253,33 @@ def test_device_offset_table_matches_host_table(V, hw):
         if len(host) >= 8:
             a = host.sample(8, rng=pyrandom.Random(3)); b = dev.sample(8, rng=pyrandom.Random(3))
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_float64_touch_maps_and_sketch_only_dataset(V, tmp_path):
+    """Touch maps stored as float64 keep their dtype through the gather (ToTensor on a float64 array gives a DoubleTensor in the
+    reference too); a directory without trainI ("edit" sketches, singleskit_dataset.py:139-145) yields sketch / mask items only."""
+    import shutil
+    root = MG.synth_dataset(str(tmp_path / "ds"))
+    for sub in ("trainT", "valT"):
+        for r, _, fs in os.walk(os.path.join(root, sub)):
+            for f in fs:
+                z = dict(np.load(os.path.join(r, f)))
+                z["gx_raw"] = z["gx_raw"].astype(np.float64); z["gy_raw"] = z["gy_raw"].astype(np.float64)
+                np.savez(os.path.join(r, f), **z)
+    opt = MG.dataset_options(root, data_len=1)
+    random.seed(2); np.random.seed(2)
+    item = V.SingleSkitDataset(opt)[0]
+    assert item["T_images"].dtype == torch.float64 and item["T_images"].shape[1:] == (2, 32, 32)
+    # the same draw on float32 copies gives the same values
+    ref_root = MG.synth_dataset(str(tmp_path / "ds32"))
+    random.seed(2); np.random.seed(2)
+    ref = V.SingleSkitDataset(MG.dataset_options(ref_root, data_len=1))[0]
+    assert torch.equal(item["T_images"].float(), ref["T_images"]) and np.array_equal(item["T_coords"], ref["T_coords"])
+    # sketch-only ("edit") directory
+    edit = str(tmp_path / "ds_edit0")
+    shutil.copytree(root, edit)
+    shutil.rmtree(os.path.join(edit, "trainI"))
+    random.seed(2); np.random.seed(2)
+    e = V.SingleSkitDataset(MG.dataset_options(edit, data_len=2))[1]
+    assert set(e) >= {"S", "M", "name", "S_paths", "M_paths", "augmentation_params"} and "I" not in e and e["T_images"] == []
+    assert tuple(e["S"].shape) == (1, 256, 256) and tuple(e["M"].shape) == (1, 256, 256)
