@@ -112,6 +112,26 @@ def synth_skit_datasets(base):
     return base
 
 
+def synth_skit_external(base):
+    """The `_edit0` directories `use_external_test_input` reads (skit_dataset.py:116-137): sketch + mask of one material, image + mask
+    of the style material."""
+    import shutil
+    synth_skit_datasets(base)
+    for mat in SKIT_MATERIALS:
+        src = os.path.join(base, "datasets", "singleskit_%s_padded_300_x1" % mat)
+        dst = src + "_edit0"
+        if not os.path.exists(dst):
+            shutil.copytree(src, dst)
+    return base
+
+
+def skit_external_options(base):
+    return dataset_options(os.path.join("./datasets", "singleskit_%s_padded_300_x1/" % SKIT_MATERIALS[0]), is_train=False, isTrain=False,
+                           preprocess="none", data_len=1, material_list=[SKIT_MATERIALS[0]], padded_size=300, load_contact_mask=True,
+                           use_external_test_input=True, test_sketch_material=SKIT_MATERIALS[0], test_style_material=SKIT_MATERIALS[1],
+                           subdir_valT=None)
+
+
 def skit_options(base):
     return dataset_options(os.path.join("./datasets", "singleskit_%s_padded_300_x1/" % SKIT_MATERIALS[0]), **SKIT_CASE)
 
@@ -173,6 +193,14 @@ def main():
         out["skit/%d/name" % idx] = np.array(ds[idx]["name"])
         out["skit/%d/M_paths" % idx] = np.array(ds[idx]["M_paths"])
     out["skit/len"] = np.array(len(ds))
+    base = synth_skit_external("/tmp/vts_data_golden_skit")
+    ds = run_reference_skit(base, skit_external_options(base), seed=11)
+    item = ds[0]
+    flatten("skit_ext/0", {k: v for k, v in item.items() if k not in ("style_I", "style_M")}, out)
+    for k in ("style_I", "style_M"):
+        t = item[k].numpy()
+        out["skit_ext/0/%s_u8" % k] = np.round((t * 0.5 + 0.5) * 255 if k == "style_I" else t * 255).astype(np.uint8).transpose(1, 2, 0)
+    out["skit_ext/0/keys"] = np.array(sorted(item))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "data_pipeline.npz"), **out)
     print("wrote", len(out), "arrays")
     for k in sorted(out)[:40]:

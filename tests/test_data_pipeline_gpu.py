@@ -283,3 +283,20 @@ def test_float64_touch_maps_and_sketch_only_dataset(V, tmp_path):
     e = V.SingleSkitDataset(MG.dataset_options(edit, data_len=2))[1]
     assert set(e) >= {"S", "M", "name", "S_paths", "M_paths", "augmentation_params"} and "I" not in e and e["T_images"] == []
     assert tuple(e["S"].shape) == (1, 256, 256) and tuple(e["M"].shape) == (1, 256, 256)
+
+
+def test_multi_material_external_sketch_matches_reference_golden(V, tmp_path, monkeypatch):
+    """`SkitDataset` with `use_external_test_input` (skit_dataset.py:116-137, test.py's path for new sketches): the sketch / mask of one
+    `_edit0` directory and the style image / mask of another ride through the same centre crop — against the reference class's item."""
+    d = np.load(GOLD)
+    base = MG.synth_skit_external(str(tmp_path / "skit"))
+    monkeypatch.chdir(base)
+    random.seed(11); np.random.seed(11)
+    item = V.SkitDataset(MG.skit_external_options(base))[0]
+    assert sorted(k for k in item if not k.startswith("M_box")) == list(d["skit_ext/0/keys"])
+    for k in ("S", "M", "style_I", "style_M"):
+        ref = DO.to_tensor_norm(d["skit_ext/0/%s_u8" % k], normalize=not k.endswith("M"))
+        assert np.array_equal(item[k].cpu().numpy(), ref), k
+    assert item["T_images"] == []
+    keys = list(d["skit_ext/0/augmentation_params__keys"])
+    assert np.array_equal(np.array([float(item["augmentation_params"][a]) for a in keys]), d["skit_ext/0/augmentation_params"])
