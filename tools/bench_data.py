@@ -33,6 +33,48 @@ def options(root, data_len):
                               sample_bbox_per_patch=2)
 
 
+def _time(fn, reps=20):
+    import torch
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def kernel_rooflines(ds):
+    """The data kernels against the HBM roofline (all are byte movers): algorithmic bytes = source read once + result written once."""
+    import torch
+    from vts_b200 import data_pipeline as DP
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak, src = 6500.0, "fallback 6.5 TB/s"
+    I = ds.I_img                                            # 1800 x 1800 x 3 uint8
+    h, w, c = I.shape
+    oh, ow = int(round(h * 0.8)), int(round(w * 0.9))
+    res = {}
+    t = _time(lambda: DP.resize_u8(I, oh, ow, DP.LANCZOS))
+    byt = h * w * c + h * ow * c * 2 + oh * ow * c          # source, the horizontal pass's intermediate (written + read), result
+    res["resize_u8 LANCZOS 1800x1800x3 -> %dx%d" % (oh, ow)] = dict(us=t * 1e6, gbs=byt / t / 1e9, frac=byt / t / 1e9 / peak)
+    crop = ds.opt.crop_size
+    t = _time(lambda: DP.crop_to_tensor(I, 100, 120, crop, crop, True))
+    byt = crop * crop * c * (1 + 4)
+    res["u8_crop_to_tensor %dx%dx3" % (crop, crop)] = dict(us=t * 1e6, gbs=byt / t / 1e9, frac=byt / t / 1e9 / peak)
+    M3 = ds._final_u8(ds._sources(0, 0)["img"]["M"], 100, 120)
+    ts = ds.touch
+    rx = [int(r[0]) % 1000 for r in ts.roi]; ry = [int(r[1]) % 700 for r in ts.roi]
+    t = _time(lambda: ts.contact_centers(M3, rx, ry))
+    byt = ts.total * (8 + 1 + 3 + 3 + 4)                    # contact mask fp64 + centre mask + three byte maps written and read back + centre list
+    res["contact_centers %d patches, %d pixels (incl. the count read-back)" % (ts.P, ts.total)] = dict(us=t * 1e6, gbs=byt / t / 1e9, frac=byt / t / 1e9 / peak)
+    return {"peak_gbs": peak, "peak_source": src, "kernels": res}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--data-len", type=int, default=200)
@@ -67,6 +109,7 @@ def main():
     e1.record(); torch.cuda.synchronize()
     out.update(impl="b200", data_len=a.data_len, build_s=t_build, s_per_augmentation=t_build / a.data_len,
                item_fetch_ms=e0.elapsed_time(e1) / a.data_len, item_bytes=sum(v.numel() * v.element_size() for v in item.values() if torch.is_tensor(v)))
+    out["kernels"] = kernel_rooflines(ds)
     if a.cpu_items > 0:
         from oracle import data_oracle as DO
         opt = options(root, a.cpu_items)

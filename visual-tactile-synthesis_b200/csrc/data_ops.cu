@@ -94,23 +94,47 @@ __device__ __forceinline__ unsigned char rs_clip8(int v) {
     return (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// one thread per output byte (y, xx, ch): rows are contiguous, so a warp reads a few consecutive source segments
-__global__ void __launch_bounds__(256) resize_h_kernel(const unsigned char* __restrict__ src, int rows, int sw, int c,
-                                                       unsigned char* __restrict__ dst, int dw, const int* __restrict__ tab, int ksize) {
-    const long long total = (long long)rows * dw * c;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % c);
-        const int xx = (int)((i / c) % dw);
-        const long long y = i / ((long long)c * dw);
-        const int* row = tab + (long long)xx * (2 + ksize);
+// horizontal pass: one thread per output pixel, all bands at once (the bands of a pixel share bounds and coefficients); consecutive
+// threads take consecutive output pixels of a row, so a warp reads one contiguous source segment
+template <int C>
+__global__ void __launch_bounds__(256) resize_h_kernel(const unsigned char* __restrict__ src, int rows, int sw, unsigned char* __restrict__ dst,
+                                                       int dw, const int* __restrict__ tab, int ksize) {
+    const int total = rows * dw;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / dw, xx = i - y * dw;
+        const int* row = tab + xx * (2 + ksize);
         const int xmin = row[0], xmax = row[1];
-        int acc = 1 << (RS_PRECISION_BITS - 1);
-        const unsigned char* s = src + (y * sw + xmin) * c + ch;
-        for (int x = 0; x < xmax; x++) acc += (int)s[(long long)x * c] * row[2 + x];
-        dst[i] = rs_clip8(acc);
+        int acc[C];
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) acc[ch] = 1 << (RS_PRECISION_BITS - 1);
+        const unsigned char* s = src + ((size_t)y * sw + xmin) * C;
+        for (int x = 0; x < xmax; x++) {
+            const int k = row[2 + x];
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) acc[ch] += (int)s[x * C + ch] * k;
+        }
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) dst[(size_t)i * C + ch] = rs_clip8(acc[ch]);
     }
 }
-// vertical pass: consecutive threads walk along a row of the output, every tap is a coalesced row read
+// vertical pass: a thread owns 4 consecutive bytes of an output row (one 32-bit load per tap, one 32-bit store); rows are wc bytes,
+// wc4 = wc / 4 words (the caller pads nothing: wc % 4 != 0 takes the byte kernel below)
+__global__ void __launch_bounds__(256) resize_v4_kernel(const unsigned int* __restrict__ src, int wc4, unsigned int* __restrict__ dst, int dh,
+                                                        const int* __restrict__ tab, int ksize) {
+    const int total = dh * wc4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int yy = i / wc4, xq = i - yy * wc4;
+        const int* row = tab + yy * (2 + ksize);
+        const int ymin = row[0], ymax = row[1];
+        int a0 = 1 << (RS_PRECISION_BITS - 1), a1 = a0, a2 = a0, a3 = a0;
+        for (int y = 0; y < ymax; y++) {
+            const unsigned int v = src[(size_t)(ymin + y) * wc4 + xq];
+            const int k = row[2 + y];
+            a0 += (int)(v & 255u) * k; a1 += (int)((v >> 8) & 255u) * k; a2 += (int)((v >> 16) & 255u) * k; a3 += (int)(v >> 24) * k;
+        }
+        dst[i] = (unsigned int)rs_clip8(a0) | ((unsigned int)rs_clip8(a1) << 8) | ((unsigned int)rs_clip8(a2) << 16) | ((unsigned int)rs_clip8(a3) << 24);
+    }
+}
 __global__ void __launch_bounds__(256) resize_v_kernel(const unsigned char* __restrict__ src, int sh, int wc,
                                                        unsigned char* __restrict__ dst, int dh, const int* __restrict__ tab, int ksize) {
     const long long total = (long long)dh * wc;
@@ -128,16 +152,34 @@ __global__ void __launch_bounds__(256) resize_v_kernel(const unsigned char* __re
 static int grid_for(long long n) { return (int)std::min<long long>(cdivll(n, 256), 148LL * 16); }
 
 // ------------------------------------------------------------------------------------------------- crop -> fp32 CHW
-__global__ void __launch_bounds__(256) crop_to_tensor_kernel(const unsigned char* __restrict__ src, int sh, int sw, int c, int y0, int x0,
+// a thread produces 4 consecutive pixels of one output row for every band: C x 4 source bytes in (contiguous), one 16-byte store per
+// band out.  grid: (ceil(w / 4 / 256), h)
+template <int C>
+__global__ void __launch_bounds__(256) crop_to_tensor_kernel(const unsigned char* __restrict__ src, int sh, int sw, int y0, int x0,
                                                              int h, int w, int normalize, float* __restrict__ dst) {
-    const long long total = (long long)c * h * w;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(i % w), y = (int)((i / w) % h), ch = (int)(i / ((long long)w * h));
-        const int sy = y + y0, sx = x + x0;
-        const unsigned char u = (sy >= 0 && sy < sh && sx >= 0 && sx < sw) ? src[((long long)sy * sw + sx) * c + ch] : 0;   // PIL crop pads with 0
-        float v = __fdiv_rn((float)u, 255.f);                              // ToTensor: byte -> float, .div(255)
-        if (normalize) v = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);            // Normalize(0.5, 0.5)
-        dst[i] = v;
+    const int y = blockIdx.y, xq = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = xq * 4;
+    if (x >= w) return;
+    const int sy = y + y0;
+    float v[C][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int sx = x + k + x0;
+        const bool in = sy >= 0 && sy < sh && sx >= 0 && sx < sw && x + k < w;            // PIL crop pads with 0
+        const unsigned char* s = src + ((size_t)sy * sw + sx) * C;
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) {
+            float f = __fdiv_rn(in ? (float)s[ch] : 0.f, 255.f);                          // ToTensor: byte -> float, .div(255)
+            if (normalize) f = __fdiv_rn(__fsub_rn(f, 0.5f), 0.5f);                       // Normalize(0.5, 0.5)
+            v[ch][k] = f;
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) {
+        float* d = dst + ((size_t)ch * h + y) * w + x;
+        if ((w & 3) == 0) *reinterpret_cast<float4*>(d) = make_float4(v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+        else
+            for (int k = 0; k < 4 && x + k < w; k++) d[k] = v[ch][k];
     }
 }
 
@@ -352,43 +394,80 @@ extern "C" int skit_mask_box_bits(const float* M, int h, int w, int k, int pad, 
     return check_launch("mask_box_bits");
 }
 
+namespace {
+// device copies of the coefficient tables, keyed by (in, out, filter): a dataset resizes a handful of shapes again and again, and the
+// table build (sin() in double per tap) plus its upload cost more than the kernels
+struct RsTable { int in, out, kind, ksize; int* dev; };
+RsTable g_rs_tables[16];
+int g_rs_count = 0, g_rs_next = 0;
+int rs_table(int in, int out, int kind, cudaStream_t st, const int** dev) {
+    for (int i = 0; i < g_rs_count; i++)
+        if (g_rs_tables[i].in == in && g_rs_tables[i].out == out && g_rs_tables[i].kind == kind) { *dev = g_rs_tables[i].dev; return g_rs_tables[i].ksize; }
+    std::vector<int> t;
+    const int ksize = rs_coeffs(in, out, kind, t);
+    int* d = nullptr;
+    if (cudaMalloc(&d, t.size() * sizeof(int)) != cudaSuccess) return -1;
+    cudaMemcpyAsync(d, t.data(), t.size() * sizeof(int), cudaMemcpyHostToDevice, st);     // pageable source: staged before the call returns
+    RsTable& e = g_rs_tables[g_rs_count < 16 ? g_rs_count++ : (g_rs_next++ % 16)];
+    if (e.dev && &e < g_rs_tables + 16 && e.in) { cudaStreamSynchronize(st); cudaFree(e.dev); }
+    e = RsTable{in, out, kind, ksize, d};
+    *dev = d;
+    return ksize;
+}
+}  // namespace
+
 extern "C" int skit_resize_u8(const unsigned char* src, int sh, int sw, int c, unsigned char* dst, int dh, int dw, int filter, void* stream) {
     SKIT_REQUIRE(src && dst && sh > 0 && sw > 0 && dh > 0 && dw > 0 && c >= 1 && c <= 4, "resize_u8: bad shape %dx%dx%d -> %dx%d", sh, sw, c, dh, dw);
     SKIT_REQUIRE(rs_support(filter) > 0, "resize_u8: unsupported filter %d (BOX 4, BILINEAR 2, HAMMING 5, BICUBIC 3, LANCZOS 1)", filter);
+    SKIT_REQUIRE((long long)sh * dw < (1ll << 31) / 4 && (long long)dh * dw * c < (1ll << 31), "resize_u8: image too large for 32-bit indexing");
     cudaStream_t st = as_stream(stream);
     if (sh == dh && sw == dw) {      // Image.resize returns a copy
         cudaMemcpyAsync(dst, src, (size_t)sh * sw * c, cudaMemcpyDeviceToDevice, st);
         return check_launch("resize_u8 copy");
     }
-    std::vector<int> th, tv;
+    const int *d_th = nullptr, *d_tv = nullptr;
     int kh = 0, kv = 0;
-    if (sw != dw) kh = rs_coeffs(sw, dw, filter, th);
-    if (sh != dh) kv = rs_coeffs(sh, dh, filter, tv);
+    if (sw != dw) { kh = rs_table(sw, dw, filter, st, &d_th); SKIT_REQUIRE(kh > 0, "resize_u8: coefficient table allocation failed"); }
+    if (sh != dh) { kv = rs_table(sh, dh, filter, st, &d_tv); SKIT_REQUIRE(kv > 0, "resize_u8: coefficient table allocation failed"); }
     // Pillow's horizontal pass only covers the source rows the vertical pass reads; the result is the same as covering all rows
-    int *d_th = nullptr, *d_tv = nullptr;
     unsigned char* tmp = nullptr;
-    if (kh) { cudaMallocAsync(&d_th, th.size() * sizeof(int), st); cudaMemcpyAsync(d_th, th.data(), th.size() * sizeof(int), cudaMemcpyHostToDevice, st); }
-    if (kv) { cudaMallocAsync(&d_tv, tv.size() * sizeof(int), st); cudaMemcpyAsync(d_tv, tv.data(), tv.size() * sizeof(int), cudaMemcpyHostToDevice, st); }
     const unsigned char* vsrc = src;
     if (kh) {
         unsigned char* hout = dst;
         if (kv) { cudaMallocAsync(&tmp, (size_t)sh * dw * c, st); hout = tmp; }
-        resize_h_kernel<<<grid_for((long long)sh * dw * c), 256, 0, st>>>(src, sh, sw, c, hout, dw, d_th, kh);
+        const int g = grid_for((long long)sh * dw);
+        switch (c) {
+            case 1: resize_h_kernel<1><<<g, 256, 0, st>>>(src, sh, sw, hout, dw, d_th, kh); break;
+            case 2: resize_h_kernel<2><<<g, 256, 0, st>>>(src, sh, sw, hout, dw, d_th, kh); break;
+            case 3: resize_h_kernel<3><<<g, 256, 0, st>>>(src, sh, sw, hout, dw, d_th, kh); break;
+            default: resize_h_kernel<4><<<g, 256, 0, st>>>(src, sh, sw, hout, dw, d_th, kh); break;
+        }
         vsrc = hout;
     }
-    if (kv) resize_v_kernel<<<grid_for((long long)dh * dw * c), 256, 0, st>>>(vsrc, sh, dw * c, dst, dh, d_tv, kv);
+    if (kv) {
+        const int wc = dw * c;
+        // 32-bit path: rows must start on 4-byte boundaries in both buffers (cudaMalloc'd bases are 256-byte aligned; row pitch wc)
+        if (wc % 4 == 0 && ((uintptr_t)vsrc & 3) == 0 && ((uintptr_t)dst & 3) == 0)
+            resize_v4_kernel<<<grid_for((long long)dh * (wc / 4)), 256, 0, st>>>((const unsigned int*)vsrc, wc / 4, (unsigned int*)dst, dh, d_tv, kv);
+        else
+            resize_v_kernel<<<grid_for((long long)dh * wc), 256, 0, st>>>(vsrc, sh, wc, dst, dh, d_tv, kv);
+    }
     const int rc = check_launch("resize_u8");
-    // the tables were copied from pageable host vectors: the copies are complete once cudaMemcpyAsync returns for pageable memory
-    if (d_th) cudaFreeAsync(d_th, st);
-    if (d_tv) cudaFreeAsync(d_tv, st);
     if (tmp) cudaFreeAsync(tmp, st);
     return rc;
 }
 
 extern "C" int skit_u8_crop_to_tensor(const unsigned char* src, int sh, int sw, int c, int y0, int x0, int h, int w, int normalize,
                                       float* dst, void* stream) {
-    SKIT_REQUIRE(src && dst && sh > 0 && sw > 0 && h > 0 && w > 0 && c >= 1, "u8_crop_to_tensor: bad shape");
-    crop_to_tensor_kernel<<<grid_for((long long)c * h * w), 256, 0, as_stream(stream)>>>(src, sh, sw, c, y0, x0, h, w, normalize, dst);
+    SKIT_REQUIRE(src && dst && sh > 0 && sw > 0 && h > 0 && w > 0 && c >= 1 && c <= 4, "u8_crop_to_tensor: bad shape");
+    dim3 grid(cdiv(cdiv(w, 4), 256), h);
+    cudaStream_t st = as_stream(stream);
+    switch (c) {
+        case 1: crop_to_tensor_kernel<1><<<grid, 256, 0, st>>>(src, sh, sw, y0, x0, h, w, normalize, dst); break;
+        case 2: crop_to_tensor_kernel<2><<<grid, 256, 0, st>>>(src, sh, sw, y0, x0, h, w, normalize, dst); break;
+        case 3: crop_to_tensor_kernel<3><<<grid, 256, 0, st>>>(src, sh, sw, y0, x0, h, w, normalize, dst); break;
+        default: crop_to_tensor_kernel<4><<<grid, 256, 0, st>>>(src, sh, sw, y0, x0, h, w, normalize, dst); break;
+    }
     return check_launch("crop_to_tensor_kernel");
 }
 
