@@ -398,18 +398,19 @@ namespace {
 // device copies of the coefficient tables, keyed by (in, out, filter): a dataset resizes a handful of shapes again and again, and the
 // table build (sin() in double per tap) plus its upload cost more than the kernels
 struct RsTable { int in, out, kind, ksize; int* dev; };
-RsTable g_rs_tables[16];
-int g_rs_count = 0, g_rs_next = 0;
+constexpr int RS_CACHE = 16;
+RsTable g_rs_tables[RS_CACHE];       // zero-initialised: dev == nullptr marks a free slot
+int g_rs_next = 0;
 int rs_table(int in, int out, int kind, cudaStream_t st, const int** dev) {
-    for (int i = 0; i < g_rs_count; i++)
-        if (g_rs_tables[i].in == in && g_rs_tables[i].out == out && g_rs_tables[i].kind == kind) { *dev = g_rs_tables[i].dev; return g_rs_tables[i].ksize; }
+    for (const RsTable& e : g_rs_tables)
+        if (e.dev && e.in == in && e.out == out && e.kind == kind) { *dev = e.dev; return e.ksize; }
     std::vector<int> t;
     const int ksize = rs_coeffs(in, out, kind, t);
     int* d = nullptr;
     if (cudaMalloc(&d, t.size() * sizeof(int)) != cudaSuccess) return -1;
     cudaMemcpyAsync(d, t.data(), t.size() * sizeof(int), cudaMemcpyHostToDevice, st);     // pageable source: staged before the call returns
-    RsTable& e = g_rs_tables[g_rs_count < 16 ? g_rs_count++ : (g_rs_next++ % 16)];
-    if (e.dev && &e < g_rs_tables + 16 && e.in) { cudaStreamSynchronize(st); cudaFree(e.dev); }
+    RsTable& e = g_rs_tables[g_rs_next++ % RS_CACHE];                                     // round-robin replacement
+    if (e.dev) { cudaStreamSynchronize(st); cudaFree(e.dev); }                            // a kernel in flight may still read the old table
     e = RsTable{in, out, kind, ksize, d};
     *dev = d;
     return ksize;
