@@ -125,3 +125,18 @@ def test_dataset_oracle_reproduces_reference_items(case, tmp_path):
             assert np.array_equal(item[k], d[pre + k]), (case, idx, k)
         keys = list(d[pre + "augmentation_params__keys"])
         assert np.array_equal(np.array([float(item["augmentation_params"][a]) for a in keys]), d[pre + "augmentation_params"])
+
+
+def test_resize_oracle_random_shapes_against_pillow():
+    """Randomised sweep (seeded): up- and down-scaling by arbitrary ratios, 1 and 3 bands, extreme aspect ratios — bit-exact with Pillow."""
+    Image = pytest.importorskip("PIL.Image")
+    g = np.random.default_rng(2024)
+    for _ in range(24):
+        h, w = int(g.integers(1, 90)), int(g.integers(1, 90))
+        oh, ow = int(g.integers(1, 120)), int(g.integers(1, 120))
+        c = int(g.choice([1, 3]))
+        a = g.integers(0, 256, (h, w, c), dtype=np.uint8)
+        a = a[:, :, 0] if c == 1 else a
+        for kind, pk in ((DO.LANCZOS, Image.LANCZOS), (DO.BICUBIC, Image.BICUBIC)):
+            ref = np.array(Image.fromarray(a).resize((ow, oh), pk))
+            assert np.array_equal(ref, DO.pil_resize_u8(a, oh, ow, kind)), (h, w, c, oh, ow, kind)
